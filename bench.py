@@ -1,0 +1,335 @@
+#!/usr/bin/env python3
+"""bench.py -- the hot path's headline metric on B200: variant pairs/sec (r2 + D', 5008 haplotypes).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Workload at N=1 is BASELINE.json configs[1]: ld_triangle, all-pairs r2/D' for 2,000 variants x
+5008 haplotypes (1,999,000 pairs).  One *step* = one all-pairs pass over one 2,000-variant set.
+With N GPUs every rank owns its own 2,000-variant set (the reference parallelises over source
+files, ld_triangle.py:406-408) -- weak scaling, no data-path collective; value = pairs of all
+ranks / max-over-ranks device time.
+
+Printed JSON (one line, rank 0):
+  value        pairs/s with the bit planes already resident in HBM and results left in HBM
+  e2e          pairs/s through the public API with HOST buffers: planes H2D (pinned) + mask/count
+               kernel + all-pairs kernel + packed results D2H, every step
+  roofline     dominant kernel (the all-pairs kernel) against the pipe that bounds it
+  cpu_baseline the reference algorithm (pure-Python port, oracle/calc_ld_port.py) on the host cores
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_VARIANTS, N_HAP = 2000, 5008
+WORKLOAD = "ld_triangle: all-pairs r2/D' matrix, 2000 variants x 5008 haplotypes (BASELINE configs[1])"
+OPS_PER_PAIR_I8 = 2 * N_HAP               # int8 Gram-matrix formulation: one MAC per haplotype
+POPC_PER_PAIR = (N_HAP + 31) // 32        # AND+POPC formulation: 32-bit popcounts per pair
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "sm_max_mhz": float(p.get("sm_max_mhz", 1965.0)), "source": "measured"}
+    except Exception:
+        # B200_PROFILING.md fallback figures
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+# --------------------------------------------------------------------------- CPU baseline
+_W = {}
+
+
+def _cpu_init(seed_base):
+    """Per-process state: genotype lists of 64 synthetic variants, extracted once."""
+    import multiprocessing as mp
+    from ld_tools_b200.synth import synth_haplotypes
+    ident = mp.current_process()._identity
+    seed = seed_base + (ident[0] if ident else 0)
+    h = synth_haplotypes(64, N_HAP, seed=seed)
+    _W["lists"] = [list(map(int, row)) for row in h]
+    _W["rng"] = np.random.default_rng(seed)
+
+
+def _cpu_step(n_pairs):
+    from oracle.calc_ld_port import calc_ld
+    lists, rng = _W["lists"], _W["rng"]
+    pairs = [(int(a), int(b)) for a, b in rng.integers(0, len(lists), size=(n_pairs, 2))]
+    t0 = time.perf_counter()
+    for a, b in pairs:
+        calc_ld(lists[a], lists[b])
+    return n_pairs, time.perf_counter() - t0
+
+
+class CpuArm:
+    """The reference algorithm (pure-Python port of backend/calc_ld.py, oracle/calc_ld_port.py) on
+    all host cores, genotype lists pre-extracted -- generous to the reference, whose drivers also
+    pay two tabix fetches and 2 x 2504 pysam lookups per pair (ld_triangle.py:158-186)."""
+
+    def __init__(self, cores=None):
+        import multiprocessing as mp
+        self.cores = cores or os.cpu_count() or 1
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_init, initargs=(1000,))
+        self.pool.map(_cpu_step, [2] * self.cores)           # force start-up + initialisers
+
+    def step(self, pairs_per_core):
+        res = self.pool.map(_cpu_step, [pairs_per_core] * self.cores, chunksize=1)
+        n = sum(r[0] for r in res)
+        return n, max(r[1] for r in res)                     # concurrent workers: time = slowest
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_baseline(pairs_per_core, cores=None):
+    arm = CpuArm(cores)
+    n, busy = arm.step(pairs_per_core)
+    arm.close()
+    return {"value": n / busy, "unit": "pairs/s", "cores": arm.cores, "kind": "port",
+            "sample": f"{n} calc_ld calls (pure-Python port of backend/calc_ld.py) on random pairs of "
+                      f"synthetic 5008-haplotype variants, {pairs_per_core} per process x {arm.cores} "
+                      f"processes, genotype lists pre-extracted",
+            "per_core": n / busy / arm.cores}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU algorithm for the same metric on the host cores."""
+    if rank != 0:
+        return
+    # each step is a bounded sample sized so that the whole run stays within ~2 minutes
+    budget_s = 120.0 / max(args.steps + args.warmup, 1)
+    per_core = int(min(2000, max(20, budget_s / 1.0e-3)))
+    arm = CpuArm()
+    for _ in range(args.warmup):
+        arm.step(per_core)
+    n_tot, t_tot = 0, 0.0
+    for _ in range(args.steps):
+        n, t = arm.step(per_core)
+        n_tot += n
+        t_tot += t
+    arm.close()
+    v = n_tot / t_tot
+    n_pairs_step = per_core * arm.cores
+    last = {"unit": "pairs/s", "cores": arm.cores, "kind": "port", "per_core": v / arm.cores,
+            "sample": f"{n_pairs_step} calc_ld calls per step (pure-Python port of backend/calc_ld.py) on random "
+                      f"pairs of synthetic 5008-haplotype variants, {per_core} per process x {arm.cores} "
+                      f"processes, genotype lists pre-extracted"}
+    line = {"impl": "reference", "metric": "variant pairs/sec (r2+D', 5008 haplotypes)", "value": v,
+            "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * n_pairs_step / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "step": f"bounded sample: {n_pairs_step} pairs per step"},
+            "cpu_baseline": dict(last, value=v),
+            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- clocks sampler
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._halt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                r = get(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from ld_tools_b200 import Context, Store
+    from ld_tools_b200.engine import ENGINE_AUTO, ENGINE_MMA, ENGINE_POPC
+    from ld_tools_b200.synth import pack_bits, synth_haplotypes
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    engine = {"auto": ENGINE_AUTO, "popc": ENGINE_POPC, "mma": ENGINE_MMA}[args.engine]
+
+    # synthetic 1000G-shaped input: this rank's own 2,000-variant set
+    h = synth_haplotypes(N_VARIANTS, N_HAP, seed=20130502 + rank)
+    planes_np = pack_bits(h)
+    n_pairs = N_VARIANTS * (N_VARIANTS - 1) // 2
+    rows = np.arange(N_VARIANTS, dtype=np.int64)
+    mask_np = np.zeros(planes_np.shape[1], dtype="<u8")
+    mask_np[:N_HAP // 64] = ~np.uint64(0)
+    mask_np[N_HAP // 64] = np.uint64((1 << (N_HAP % 64)) - 1)
+
+    ctx = Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    store = Store.from_planes(ctx, planes_np, N_HAP)
+    store.set_mask(mask_np)
+    d_packed = torch.empty(n_pairs, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- leg 1: device-resident ("value"): kernel(s) + near-tie settlement per step
+    def step_resident():
+        store.triangle_dev(rows, d_packed.data_ptr(), engine=engine)
+        ctx.resolve()
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    for s0, s1, s2 in ev:
+        flush.zero_()                       # L2 flush between timed iterations (outside the event pair)
+        s0.record(stream)
+        store.triangle_dev(rows, d_packed.data_ptr(), engine=engine)
+        s1.record(stream)                   # s0..s1 = the all-pairs kernel(s) alone
+        ctx.resolve()
+        s2.record(stream)                   # s0..s2 = the step
+    barrier()
+    launches = ctx.launch_count - launches0
+    step_ms = float(sum(a.elapsed_time(c) for a, _, c in ev))
+    kern_ms = float(sum(a.elapsed_time(b) for a, b, _ in ev))
+
+    # ---- leg 2: end to end through the host API: pinned planes H2D + mask/count kernel +
+    #      all-pairs kernel + packed results D2H
+    planes_pin = torch.from_numpy(planes_np.view(np.int64)).pin_memory()
+    out_pin = torch.empty(n_pairs, dtype=torch.int32).pin_memory()
+    planes_host = planes_pin.numpy().view("<u8")
+    out_host = out_pin.numpy().view(np.uint32)
+
+    def step_e2e():
+        store.upload(0, planes_host)
+        store.set_mask(mask_np)
+        store.triangle(rows, engine=engine, out=out_host)
+
+    for _ in range(max(args.warmup // 2, 3)):
+        step_e2e()
+    barrier()
+    e_steps = max(args.steps // 4, 5)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        step_e2e()
+    e1.record(stream)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    e2e_ms = float(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+
+    # ---- max over ranks
+    t = torch.tensor([step_ms, kern_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms, kern_ms, e2e_ms = t.tolist()
+    total_pairs = n_pairs * world
+    value = total_pairs * args.steps / (step_ms * 1e-3)
+    e2e_value = total_pairs * e_steps / (e2e_ms * 1e-3)
+    kern_s = kern_ms * 1e-3 / args.steps
+
+    # parity spot-check of what was just timed (device-resident result vs host-API result)
+    same = bool((d_packed.cpu().numpy().view(np.uint32) == out_host).all())
+
+    used_mma = engine == ENGINE_MMA or (engine == ENGINE_AUTO and os.environ.get("LDX_BENCH_ENGINE_USED") == "mma")
+    if used_mma:
+        peak = 2.0 * peaks["bf16_tflops"]      # dense int8 = 2 x dense bf16 on sm_100a
+        roof = {"bound": "tensor", "achieved": n_pairs * OPS_PER_PAIR_I8 / kern_s / 1e12, "peak": peak,
+                "unit": "TFLOP/s", "peak_source": f"2 x {peaks['source']} cuBLAS bf16 ({peaks['bf16_tflops']} TFLOP/s)"}
+    else:
+        # AND+POPC engine: bounded by the integer POPC pipe (16 lanes/clk/SM), not by HBM or tensor
+        peak = 148 * 16 * peaks["sm_max_mhz"] * 1e6 / 1e12
+        roof = {"bound": "popc", "achieved": n_pairs * POPC_PER_PAIR / kern_s / 1e12, "peak": peak,
+                "unit": "TPOPC32/s", "peak_source": "148 SM x 16 POPC/clk x clocks.max.sm"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["traffic"] = None
+    roof["kernel_ms"] = kern_s * 1e3
+
+    line = {"metric": "variant pairs/sec (r2+D', 5008 haplotypes)", "value": value, "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 popcount + f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": n_pairs, "engine": args.engine,
+                       "l2": "flushed (256 MiB write) between timed iterations", "sharding": "one variant set per GPU"},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(planes_np.nbytes + mask_np.nbytes + rows.nbytes),
+                    "d2h_bytes_per_step": int(out_host.nbytes), "steps": e_steps, "wall_s": e2e_wall},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "parity_selfcheck": same}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_pairs_per_core)
+        print(json.dumps(line), flush=True)
+    store.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--engine", choices=["auto", "popc", "mma"], default="auto")
+    ap.add_argument("--cpu-pairs-per-core", type=int, default=2000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,197 @@
+/* ldx.h -- C ABI of libldx.so, the B200 (sm_100a) engine behind ld-tools' LD hot path.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no C++/torch types.  It is what
+ * the reference's Python would bind with ctypes.  Every entry point names the
+ * reference code it replaces; paths are relative to the ld-tools repository root.
+ *
+ * Conventions
+ *   - Every function returns an int32 status: LDX_OK (0) or a negative LDX_ERR_* code;
+ *     ldx_last_error() returns a thread-local message for the last failure.
+ *   - No C++ exception crosses the boundary.  The caller allocates and owns every host buffer.
+ *   - CUDA is initialised by ldx_init() only -- call it AFTER fork (the reference fans out with
+ *     multiprocessing.Pool, ld_area.py:336 / ld_triangle.py:406); one ctx per process and device.
+ *   - Calls on one ctx are not concurrent.  Distinct contexts/processes are independent.
+ *   - There is no CPU fallback: without a CUDA device ldx_init() fails.
+ *
+ * Data model
+ *   A *store* holds one chromosome's biallelic phased variants as bit planes in HBM: haplotype
+ *   h (= 2*sample + allele slot, the order of the flat list the drivers build with
+ *   `+= rec.samples[name]['GT']`, ld_area.py:182-187) is bit (h % 64) of 64-bit word (h / 64)
+ *   of the variant's row.  Row pitch = ceil(n_hap/64) rounded up to 16 words (128 B); pad bits
+ *   are zero.  5008 haplotypes -> 79 words -> 640-byte rows.  A *mask* plane selects the
+ *   haplotypes of the chosen samples (get_sample_names.py:17-31); N = popcount(mask).
+ *
+ * Packed pair result (uint32) -- the reference's rounded outputs (calc_ld.py:94-95) as integers:
+ *   bits  0..13  round(r2, 4) * 10^4          (0..10000)
+ *   bit   14     internal (always 0 in results returned to the caller)
+ *   bit   15     r2 is the reference's INT 0   (calc_ld.py:89-90; prints "0", not "0.0")
+ *   bits 16..29  round(D', 4) * 10^4
+ *   bit   30     pair is below the caller's threshold (triangle only; ld_triangle.py:223-225)
+ *   bit   31     D' is the reference's INT 0   (ZeroDivisionError branch, calc_ld.py:68-69,75-76)
+ *   value / 10000.0 in the caller's language reproduces Python's round(x, 4) bit for bit.
+ */
+#ifndef LDX_H
+#define LDX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDX_ABI_VERSION 1
+
+enum {
+    LDX_OK = 0,
+    LDX_ERR_ARG = -1,        /* bad argument */
+    LDX_ERR_CUDA = -2,       /* CUDA runtime/driver failure (incl. no device) */
+    LDX_ERR_NOMEM = -3,      /* host or device allocation failed */
+    LDX_ERR_EMPTY = -4,      /* N == 0: the reference raises ZeroDivisionError (calc_ld.py:33) */
+    LDX_ERR_CAPACITY = -5,   /* output buffer too small; *n_out holds the size needed */
+    LDX_ERR_STATE = -6,      /* call order (e.g. compute before ldx_store_set_mask) */
+    LDX_ERR_DATA = -7        /* input outside the supported domain */
+};
+
+enum { LDX_MEASURE_R2 = 0, LDX_MEASURE_DPRIME = 1 };      /* -l r_square | d_prime */
+enum { LDX_ENGINE_AUTO = 0, LDX_ENGINE_POPC = 1, LDX_ENGINE_MMA = 2 };
+
+#define LDX_R2_MASK      0x00003fffu
+#define LDX_R2_INT0      0x00008000u
+#define LDX_DP_SHIFT     16
+#define LDX_DP_MASK      0x3fff0000u
+#define LDX_BELOW_THRES  0x40000000u
+#define LDX_DP_INT0      0x80000000u
+
+typedef struct ldx_ctx ldx_ctx;
+typedef struct ldx_store ldx_store;
+
+/* One kept (query, opposing variant) pair of a window scan: the row ld_area.py:264-276 emits. */
+typedef struct {
+    int32_t query;     /* index into the call's query arrays */
+    int32_t row;       /* store row of the opposing variant */
+    int32_t n11;       /* (alt, alt) haplotype count, calc_ld.py:32 */
+    uint32_t packed;   /* rounded r2 / D' + type flags, format above */
+} ldx_hit;
+
+/* Result of the list-level calculator (ldx_calc_ld_lists): every intermediate of calc_ld.py. */
+typedef struct {
+    int64_t n_hap, n_11, n_a1, n_a0, n_b1, n_b0;   /* calc_ld.py:31-32, :37-40 */
+    double d, dprime, r2, p_a, p_b;                /* before rounding, calc_ld.py:33-90 */
+    double r2_e4, dprime_e4, p_a_e4, p_b_e4;       /* round(x,4)*10^4 as exact integers in fp64 */
+    int32_t dprime_is_int0, r2_is_int0;            /* the reference's int-0 sentinels */
+} ldx_ld_result;
+
+/* ---------------------------------------------------------------- lifecycle */
+int32_t ldx_abi_version(void);
+const char *ldx_last_error(void);
+int32_t ldx_device_count(int32_t *n_out);
+/* device < 0 selects the current device.  Creates the ctx's stream and scratch buffers. */
+int32_t ldx_init(int32_t device, ldx_ctx **ctx_out);
+int32_t ldx_destroy(ldx_ctx *ctx);
+/* Launch on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream) instead of
+ * the ctx's own; NULL restores the ctx stream. */
+int32_t ldx_set_stream(ldx_ctx *ctx, void *cuda_stream);
+int32_t ldx_synchronize(ldx_ctx *ctx);
+int32_t ldx_sm_count(ldx_ctx *ctx, int32_t *n_out);
+/* Kernels launched by this ctx since creation (bench.py's gpu_launches claim). */
+int32_t ldx_launch_count(ldx_ctx *ctx, int64_t *n_out);
+
+/* ---------------------------------------------------------------- the list-level calculator
+ * Replaces backend/calc_ld.py:3-99 for one pair given as genotype codes: 0 = ref, 1 = alt,
+ * any other byte = "other" (None, 2, ...: paired but in neither allele count, calc_ld.py:37-40).
+ * Unequal lengths pair up to the shorter one (zip, calc_ld.py:30-31) while the allele counts run
+ * over the full vectors.  len == 0 -> LDX_ERR_EMPTY. */
+int32_t ldx_calc_ld_lists(ldx_ctx *ctx, const uint8_t *g_a, int64_t len_a, const uint8_t *g_b,
+                          int64_t len_b, ldx_ld_result *out);
+
+/* ---------------------------------------------------------------- the bit-plane store
+ * Replaces the per-pair pysam genotype extraction (ld_lite.py:109-137, ld_area.py:182-187 and
+ * :230-235, ld_triangle.py:158-186) and the prep_intgen_data/create_src_dict cache as the
+ * thing the calculator reads. */
+int32_t ldx_store_create(ldx_ctx *ctx, int64_t n_variants, int32_t n_hap, ldx_store **store_out);
+int32_t ldx_store_destroy(ldx_store *store);
+int32_t ldx_store_shape(const ldx_store *store, int64_t *n_variants, int32_t *n_hap,
+                        int32_t *stride_words);
+/* Device address of the planes ([n_variants][stride_words] uint64), for zero-copy interop. */
+int32_t ldx_store_planes_ptr(const ldx_store *store, void **dev_ptr_out);
+
+/* GPU bit-packing of VCF genotype text (kernel K1).  `text` is host memory holding, for each of
+ * n_rows variants, n_samples fields "a|b" each followed by one separator byte, starting at
+ * byte row_off[i] (row_off == NULL: row i starts at i * row_pitch).  Rows land at store rows
+ * first_row...  row_status[i] (may be NULL) = 0 ok, 1 = a field outside the phased diploid
+ * biallelic alphabet {0|0, 0|1, 1|0, 1|1} (such rows are packed with non-'1' alleles as 0). */
+int32_t ldx_store_pack_gt(ldx_store *store, int64_t first_row, int64_t n_rows, const uint8_t *text,
+                          int64_t text_bytes, const int64_t *row_off, int64_t row_pitch,
+                          int32_t n_samples, uint8_t *row_status);
+/* Load / read back ready-made planes (host, [n_rows][stride_words] uint64). */
+int32_t ldx_store_upload(ldx_store *store, int64_t first_row, int64_t n_rows, const uint64_t *planes);
+int32_t ldx_store_download(const ldx_store *store, int64_t first_row, int64_t n_rows, uint64_t *planes);
+
+/* Select samples: mask[stride_words] (host).  Runs the per-variant count kernel (K2):
+ * n1[v] = popcount(mask & plane[v]) (calc_ld.py:37,39), N = popcount(mask) (calc_ld.py:31), and
+ * the per-variant frequencies.  N == 0 -> LDX_ERR_EMPTY. */
+int32_t ldx_store_set_mask(ldx_store *store, const uint64_t *mask);
+/* n1_out[n_variants], p_e4_out[n_variants] = round(n1/N, 4)*10^4 (ld_area.py:188-189); any may be NULL. */
+int32_t ldx_store_counts(const ldx_store *store, int32_t *n1_out, int32_t *p_e4_out, int32_t *n_hap_sel_out);
+/* New store holding only the selected haplotype columns (sel[k] = source haplotype of new
+ * haplotype k), mask = all ones: 5x less HBM traffic for a 503-sample subset. */
+int32_t ldx_store_subset(const ldx_store *store, const int32_t *sel, int32_t n_sel, ldx_store **store_out);
+/* Per-row annotations the fused ld_area filters need (host arrays of n_variants):
+ * pos0 = POS-1, end0 = POS-1+len(REF) (pysam fetch overlap, ld_area.py:215-217),
+ * idnum = digits of the rsID (ld_area.py:222 same-id test), eligible = id matches rs\d+$ and
+ * the record is not MULTI_ALLELIC (ld_area.py:223-224). */
+int32_t ldx_store_set_annotations(ldx_store *store, const int32_t *pos0, const int32_t *end0,
+                                  const int64_t *idnum, const uint8_t *eligible);
+
+/* ---------------------------------------------------------------- pair list (kernel K3)
+ * Replaces calc_ld(g1, g2) at ld_lite.py:143 for n pairs of store rows (var_1 = ia[k],
+ * var_2 = ib[k]).  Outputs are host arrays of n, each may be NULL. */
+int32_t ldx_pairs(ldx_store *store, const int64_t *ia, const int64_t *ib, int64_t n, int32_t *n11,
+                  double *d, double *dprime, double *r2, uint32_t *packed);
+
+/* ---------------------------------------------------------------- window scan (kernel K4)
+ * Replaces the ld_area.py:215-249 loop for nq queries at once.  Query k is store row q_row[k];
+ * candidates are store rows [lo[k], hi[k]) (a superset chosen by the caller's position index);
+ * the kernel keeps row j iff it overlaps the 0-based half-open window [win_start[k], win_end[k])
+ * (pos0[j] < win_end && end0[j] > win_start), is eligible, has a different idnum than the query,
+ * and its ROUNDED measure >= thres_e4 / 10^4 (ld_area.py:248).  var_1 = query, var_2 = row j.
+ * hits[cap] is filled sorted by (query, row); *n_hits = number kept (LDX_ERR_CAPACITY if > cap,
+ * with *n_hits = size needed).  *n_scanned (may be NULL) = candidate pairs evaluated. */
+int32_t ldx_window(ldx_store *store, const int64_t *q_row, const int64_t *lo, const int64_t *hi,
+                   const int32_t *win_start, const int32_t *win_end, int64_t nq, int32_t measure,
+                   int32_t thres_e4, ldx_hit *hits, int64_t cap, int64_t *n_hits, int64_t *n_scanned);
+
+/* ---------------------------------------------------------------- all pairs (kernels K5 / K5')
+ * Replaces the ld_triangle.py:133-230 double loop.  rows[v] = store rows in matrix order (the
+ * caller sorts by position, ld_triangle.py:88).  For row > col: var_1 = rows[row], var_2 =
+ * rows[col] (ld_triangle.py:193).  Output is the lower triangle packed by rows:
+ * index = row*(row-1)/2 + col, v*(v-1)/2 entries.  has_thres != 0 sets LDX_BELOW_THRES on pairs
+ * whose rounded measure < thres_e4/10^4.  packed / n11 are host arrays and may be NULL. */
+int32_t ldx_triangle(ldx_store *store, const int64_t *rows, int64_t v, int32_t measure,
+                     int32_t has_thres, int32_t thres_e4, int32_t engine, uint32_t *packed,
+                     int32_t *n11);
+
+/* ---------------------------------------------------------------- device-resident variants
+ * Same kernels, but outputs stay in HBM (caller-allocated device memory) and the call only
+ * enqueues work on the ctx stream.  ldx_resolve() then finishes the rounding of the (very rare)
+ * pairs whose r2 sits within 1e-10 of a rounding tie -- there the reference's libm pow decides
+ * the last digit -- and must be called before the outputs are consumed (it synchronises).
+ * Index arrays (rows, q_row, ...) are HOST arrays; pinned ones must stay valid until the next
+ * ldx_synchronize()/ldx_resolve().
+ * ldx_window_dev: dev_hits must be 16-byte aligned; dev_n_hits points at TWO int64 in device
+ * memory: [0] = hits found (may exceed cap; only the first cap are stored), [1] = pairs scanned.
+ * Hits are unordered; a hit that ldx_resolve() finds below the threshold after exact rounding
+ * gets LDX_BELOW_THRES set in its packed word instead of being removed. */
+int32_t ldx_triangle_dev(ldx_store *store, const int64_t *rows, int64_t v, int32_t measure,
+                         int32_t has_thres, int32_t thres_e4, int32_t engine,
+                         uint32_t *dev_packed, int32_t *dev_n11);
+int32_t ldx_window_dev(ldx_store *store, const int64_t *q_row, const int64_t *lo, const int64_t *hi,
+                       const int32_t *win_start, const int32_t *win_end, int64_t nq,
+                       int32_t measure, int32_t thres_e4, ldx_hit *dev_hits, int64_t cap,
+                       int64_t *dev_n_hits);
+int32_t ldx_resolve(ldx_ctx *ctx, int64_t *n_fixed_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDX_H */

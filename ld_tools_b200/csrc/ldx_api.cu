@@ -1,0 +1,666 @@
+// ldx_api.cu -- the C ABI declared in include/ldx.h: context, store, and the host-side halves of
+// the compute entry points (staging, launch, copy-back, near-tie settlement, hit ordering).
+#include <algorithm>
+#include <cmath>
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "ldx_internal.h"
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+namespace ldx {
+int set_error(int code, const std::string &msg) { g_last_error = msg; return code; }
+int cuda_fail(cudaError_t e, const char *what) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();   // clear the sticky-less error state
+    return LDX_ERR_CUDA;
+}
+}  // namespace ldx
+using namespace ldx;
+
+#define LDX_TRY(expr) do { int rc__ = (expr); if (rc__ != LDX_OK) return rc__; } while (0)
+#define LDX_REQUIRE(cond, msg) do { if (!(cond)) return set_error(LDX_ERR_ARG, msg); } while (0)
+
+// grow-only device scratch owned by the ctx (avoids cudaMalloc/cudaFree on every call)
+struct Arena {
+    enum { SLOTS = 12 };
+    void *ptr[SLOTS] = {};
+    size_t bytes[SLOTS] = {};
+};
+static Arena *arena_of(ldx_ctx *ctx) { return reinterpret_cast<Arena *>(ctx->d_scratch); }
+
+static int arena_get(ldx_ctx *ctx, int slot, size_t bytes, void **out) {
+    Arena *a = arena_of(ctx);
+    if (bytes == 0) bytes = 16;
+    if (a->bytes[slot] < bytes) {
+        if (a->ptr[slot]) { cudaStreamSynchronize(ctx->stream); cudaFree(a->ptr[slot]); a->ptr[slot] = nullptr; a->bytes[slot] = 0; }
+        const size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&a->ptr[slot], want);
+        if (e != cudaSuccess) { cudaGetLastError(); return set_error(LDX_ERR_NOMEM, "device scratch allocation failed"); }
+        a->bytes[slot] = want;
+    }
+    *out = a->ptr[slot];
+    return LDX_OK;
+}
+enum { S_IA = 0, S_IB, S_PACKED, S_N11, S_D, S_DP, S_R2, S_TEXT, S_ROWOFF, S_STATUS, S_HITS, S_MISC };
+
+// ------------------------------------------------------------------------------------------ lifecycle
+extern "C" int32_t ldx_abi_version(void) { return LDX_ABI_VERSION; }
+extern "C" const char *ldx_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int32_t ldx_device_count(int32_t *n_out) {
+    LDX_REQUIRE(n_out, "n_out is NULL");
+    int n = 0;
+    LDX_CUDA(cudaGetDeviceCount(&n));
+    *n_out = n;
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_init(int32_t device, ldx_ctx **ctx_out) {
+    LDX_REQUIRE(ctx_out, "ctx_out is NULL");
+    *ctx_out = nullptr;
+    int n = 0;
+    LDX_CUDA(cudaGetDeviceCount(&n));
+    if (n <= 0) return set_error(LDX_ERR_CUDA, "no CUDA device: libldx has no CPU fallback");
+    if (device < 0) LDX_CUDA(cudaGetDevice(&device));
+    LDX_REQUIRE(device < n, "device index out of range");
+    LDX_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LDX_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return set_error(LDX_ERR_CUDA, std::string("libldx is built for sm_100a only; device is ") + prop.name);
+    ldx_ctx *ctx = new (std::nothrow) ldx_ctx();
+    if (!ctx) return set_error(LDX_ERR_NOMEM, "ctx allocation failed");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->d_scratch = new (std::nothrow) Arena();
+    ctx->fix_capacity = 1u << 20;
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fix, sizeof(FixupRec) * (size_t)ctx->fix_capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fix_count, 4 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_fix_count, 0, 4 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_fix_count, 4 * sizeof(uint32_t));
+    if (e != cudaSuccess) { ldx_destroy(ctx); return cuda_fail(e, "ldx_init"); }
+    ctx->stream = ctx->own_stream;
+    *ctx_out = ctx;
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_destroy(ldx_ctx *ctx) {
+    if (!ctx) return LDX_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (Arena *a = arena_of(ctx)) {
+        for (int i = 0; i < Arena::SLOTS; ++i) if (a->ptr[i]) cudaFree(a->ptr[i]);
+        delete a;
+    }
+    if (ctx->d_fix) cudaFree(ctx->d_fix);
+    if (ctx->d_fix_count) cudaFree(ctx->d_fix_count);
+    if (ctx->h_fix_count) cudaFreeHost(ctx->h_fix_count);
+    if (ctx->d_mma_ops) cudaFree(ctx->d_mma_ops);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_set_stream(ldx_ctx *ctx, void *cuda_stream) {
+    LDX_REQUIRE(ctx, "ctx is NULL");
+    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_synchronize(ldx_ctx *ctx) {
+    LDX_REQUIRE(ctx, "ctx is NULL");
+    LDX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_sm_count(ldx_ctx *ctx, int32_t *n_out) {
+    LDX_REQUIRE(ctx && n_out, "NULL argument");
+    *n_out = ctx->sm_count;
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_launch_count(ldx_ctx *ctx, int64_t *n_out) {
+    LDX_REQUIRE(ctx && n_out, "NULL argument");
+    *n_out = ctx->launches;
+    return LDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Near-tie settlement.  The kernels compute d*d; CPython computes pow(d, 2.0) (calc_ld.py:87),
+// which glibc rounds differently for ~0.1% of inputs (1 ulp).  That can only change the printed
+// value when r2*10^4 is within an ulp of k + 0.5; the kernels flag a far wider band (1e-6) and
+// the few flagged pairs are re-evaluated here from their integer counts with the real libm pow.
+// gcc folds pow(x, 2.0) into x*x, hence the volatile pointer.
+static double (*volatile libm_pow)(double, double) = pow;
+
+static double host_round4_e4(double x) {
+    const double hi = x * 1.0e4;
+    const double lo = std::fma(x, 1.0e4, -hi);
+    const double k = std::floor(hi);
+    const double frac = hi - k;
+    if (frac > 0.5 || (frac == 0.5 && lo > 0.0)) return k + 1.0;
+    if (frac == 0.5 && lo == 0.0) return k + (double)(((long long)k) & 1);
+    return k;
+}
+
+// calc_ld.py:33-97 on the host for biallelic complete data; returns the packed word.
+static uint32_t host_finalise_packed(double N, int32_t n11, int32_t n1a, int32_t n1b, double *r2_raw) {
+    const double f11 = (double)n11 / N;
+    const double pa = (double)n1a / N, qa = (double)((int32_t)N - n1a) / N;
+    const double pb = (double)n1b / N, qb = (double)((int32_t)N - n1b) / N;
+    const double t = pa * pb;
+    const double d = f11 - t;
+    double bound;
+    if (d >= 0.0) { const double x = pa * qb, y = qa * pb; bound = (y < x) ? y : x; }
+    else { const double x = -t, y = -(qa * qb); bound = (y > x) ? y : x; }
+    if (r2_raw) *r2_raw = 0.0;
+    if (bound == 0.0) return LDX_DP_INT0 | LDX_R2_INT0;
+    const double dp = d / bound;
+    uint32_t word = ((uint32_t)host_round4_e4(dp)) << LDX_DP_SHIFT;
+    if (dp != 0.0) {
+        const double r2 = libm_pow(d, 2.0) / (((pa * qa) * pb) * qb);
+        if (r2_raw) *r2_raw = r2;
+        word |= (uint32_t)host_round4_e4(r2);
+    } else word |= LDX_R2_INT0;
+    return word;
+}
+
+static inline int32_t word_measure(uint32_t w, int measure) {
+    return measure == LDX_MEASURE_R2 ? (int32_t)(w & LDX_R2_MASK) : (int32_t)((w & LDX_DP_MASK) >> LDX_DP_SHIFT);
+}
+
+// Fetch (and clear) the device fix-up list.  Synchronises the stream.
+static int collect_fixups(ldx_ctx *ctx, std::vector<FixupRec> &recs) {
+    recs.clear();
+    LDX_CUDA(cudaMemcpyAsync(ctx->h_fix_count, ctx->d_fix_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    LDX_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint32_t n = ctx->h_fix_count[0];
+    if (n == 0) return LDX_OK;
+    if (n > ctx->fix_capacity) {
+        cudaMemsetAsync(ctx->d_fix_count, 0, sizeof(uint32_t), ctx->stream);
+        return set_error(LDX_ERR_CAPACITY, "near-tie list overflow (more than 2^20 flagged pairs in one call)");
+    }
+    recs.resize(n);
+    LDX_CUDA(cudaMemcpyAsync(recs.data(), ctx->d_fix, sizeof(FixupRec) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    LDX_CUDA(cudaMemsetAsync(ctx->d_fix_count, 0, sizeof(uint32_t), ctx->stream));
+    LDX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LDX_OK;
+}
+
+static uint32_t settle_word(const FixupRec &r, double N, int measure, int has_thres, int thres_e4) {
+    uint32_t w = host_finalise_packed(N, r.n11, r.n1a, r.n1b, nullptr);
+    if (has_thres && word_measure(w, measure) < thres_e4) w |= LDX_BELOW_THRES;
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------ lists
+extern "C" int32_t ldx_calc_ld_lists(ldx_ctx *ctx, const uint8_t *g_a, int64_t len_a, const uint8_t *g_b,
+                                     int64_t len_b, ldx_ld_result *out) {
+    LDX_REQUIRE(ctx && out, "NULL argument");
+    LDX_REQUIRE(len_a >= 0 && len_b >= 0 && (g_a || !len_a) && (g_b || !len_b), "bad genotype vectors");
+    if (len_a == 0 || len_b == 0)
+        return set_error(LDX_ERR_EMPTY, "division by zero");   // calc_ld.py:33 with an empty pairing
+    LDX_CUDA(cudaSetDevice(ctx->device));
+    uint8_t *d_buf; ldx_ld_result *d_out;
+    const size_t off_b = ((size_t)len_a + 15) / 16 * 16;
+    LDX_TRY(arena_get(ctx, S_TEXT, off_b + (size_t)len_b + 16, (void **)&d_buf));
+    LDX_TRY(arena_get(ctx, S_MISC, sizeof(ldx_ld_result), (void **)&d_out));
+    LDX_CUDA(cudaMemcpyAsync(d_buf, g_a, (size_t)len_a, cudaMemcpyHostToDevice, ctx->stream));
+    LDX_CUDA(cudaMemcpyAsync(d_buf + off_b, g_b, (size_t)len_b, cudaMemcpyHostToDevice, ctx->stream));
+    LDX_TRY(launch_lists(ctx, d_buf, len_a, d_buf + off_b, len_b, d_out));
+    LDX_CUDA(cudaMemcpyAsync(out, d_out, sizeof(ldx_ld_result), cudaMemcpyDeviceToHost, ctx->stream));
+    LDX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (out->r2_is_int0 == 2) {   // near a rounding tie: the reference's libm pow decides (calc_ld.py:87)
+        const double N = (double)out->n_hap;
+        const double pa = (double)out->n_a1 / N, qa = (double)out->n_a0 / N;
+        const double pb = (double)out->n_b1 / N, qb = (double)out->n_b0 / N;
+        const double r2 = libm_pow(out->d, 2.0) / (((pa * qa) * pb) * qb);
+        out->r2 = r2;
+        out->r2_e4 = host_round4_e4(r2);
+        out->r2_is_int0 = 0;
+    }
+    return LDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ store
+extern "C" int32_t ldx_store_create(ldx_ctx *ctx, int64_t n_variants, int32_t n_hap, ldx_store **store_out) {
+    LDX_REQUIRE(ctx && store_out, "NULL argument");
+    LDX_REQUIRE(n_variants >= 0 && n_variants < (1ll << 31), "n_variants out of range");
+    LDX_REQUIRE(n_hap > 0 && n_hap <= (1 << 24), "n_hap out of range");
+    *store_out = nullptr;
+    LDX_CUDA(cudaSetDevice(ctx->device));
+    ldx_store *s = new (std::nothrow) ldx_store();
+    if (!s) return set_error(LDX_ERR_NOMEM, "store allocation failed");
+    s->ctx = ctx; s->n_variants = n_variants; s->n_hap = n_hap;
+    s->words = (n_hap + 63) / 64;
+    s->stride_words = (s->words + 15) / 16 * 16;
+    const size_t nv = (size_t)std::max<int64_t>(n_variants, 1);
+    cudaError_t e = cudaMalloc(&s->d_planes, nv * s->stride_words * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_planes, 0, nv * s->stride_words * sizeof(uint64_t), ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_mask, s->stride_words * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_freq, nv * sizeof(VarFreq));
+    if (e != cudaSuccess) { ldx_store_destroy(s); cudaGetLastError(); return set_error(LDX_ERR_NOMEM, std::string("store device allocation: ") + cudaGetErrorString(e)); }
+    *store_out = s;
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_store_destroy(ldx_store *s) {
+    if (!s) return LDX_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    cudaFree(s->d_planes); cudaFree(s->d_mask); cudaFree(s->d_freq);
+    cudaFree(s->d_pos0); cudaFree(s->d_end0); cudaFree(s->d_idnum); cudaFree(s->d_eligible);
+    delete s;
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_store_shape(const ldx_store *s, int64_t *n_variants, int32_t *n_hap, int32_t *stride_words) {
+    LDX_REQUIRE(s, "store is NULL");
+    if (n_variants) *n_variants = s->n_variants;
+    if (n_hap) *n_hap = s->n_hap;
+    if (stride_words) *stride_words = s->stride_words;
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_store_planes_ptr(const ldx_store *s, void **dev_ptr_out) {
+    LDX_REQUIRE(s && dev_ptr_out, "NULL argument");
+    *dev_ptr_out = s->d_planes;
+    return LDX_OK;
+}
+
+static int check_rows(const ldx_store *s, int64_t first_row, int64_t n_rows) {
+    LDX_REQUIRE(s, "store is NULL");
+    LDX_REQUIRE(first_row >= 0 && n_rows >= 0 && first_row + n_rows <= s->n_variants, "row range outside the store");
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_store_pack_gt(ldx_store *s, int64_t first_row, int64_t n_rows, const uint8_t *text,
+                                     int64_t text_bytes, const int64_t *row_off, int64_t row_pitch,
+                                     int32_t n_samples, uint8_t *row_status) {
+    LDX_TRY(check_rows(s, first_row, n_rows));
+    LDX_REQUIRE(text && text_bytes > 0, "text is empty");
+    LDX_REQUIRE(n_samples > 0 && 2 * n_samples == s->n_hap, "n_samples does not match the store (n_hap = 2 * n_samples)");
+    const int64_t row_bytes = 4ll * n_samples - 1;   // the last separator need not exist
+    if (row_off) {
+        for (int64_t i = 0; i < n_rows; ++i)
+            LDX_REQUIRE(row_off[i] >= 0 && row_off[i] + row_bytes <= text_bytes, "row_off outside text");
+    } else {
+        LDX_REQUIRE(row_pitch >= row_bytes && (n_rows == 0 || (n_rows - 1) * row_pitch + row_bytes <= text_bytes), "row_pitch/text_bytes mismatch");
+    }
+    if (n_rows == 0) return LDX_OK;
+    ldx_ctx *ctx = s->ctx;
+    LDX_CUDA(cudaSetDevice(ctx->device));
+    uint8_t *d_text, *d_status; int64_t *d_off = nullptr;
+    LDX_TRY(arena_get(ctx, S_TEXT, (size_t)text_bytes + 64, (void **)&d_text));
+    LDX_TRY(arena_get(ctx, S_STATUS, (size_t)n_rows, (void **)&d_status));
+    LDX_CUDA(cudaMemcpyAsync(d_text, text, (size_t)text_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (row_off) {
+        LDX_TRY(arena_get(ctx, S_ROWOFF, sizeof(int64_t) * (size_t)n_rows, (void **)&d_off));
+        LDX_CUDA(cudaMemcpyAsync(d_off, row_off, sizeof(int64_t) * (size_t)n_rows, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    LDX_TRY(launch_pack_gt(ctx, d_text, d_off, row_pitch, n_rows, n_samples,
+                           s->d_planes + first_row * s->stride_words, s->stride_words, d_status));
+    if (row_status)
+        LDX_CUDA(cudaMemcpyAsync(row_status, d_status, (size_t)n_rows, cudaMemcpyDeviceToHost, ctx->stream));
+    LDX_CUDA(cudaStreamSynchronize(ctx->stream));
+    s->mask_set = false;   // counts are stale
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_store_upload(ldx_store *s, int64_t first_row, int64_t n_rows, const uint64_t *planes) {
+    LDX_TRY(check_rows(s, first_row, n_rows));
+    LDX_REQUIRE(planes || n_rows == 0, "planes is NULL");
+    if (n_rows == 0) return LDX_OK;
+    LDX_CUDA(cudaSetDevice(s->ctx->device));
+    LDX_CUDA(cudaMemcpyAsync(s->d_planes + first_row * s->stride_words, planes,
+                             sizeof(uint64_t) * (size_t)n_rows * s->stride_words, cudaMemcpyHostToDevice, s->ctx->stream));
+    LDX_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    s->mask_set = false;
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_store_download(const ldx_store *s, int64_t first_row, int64_t n_rows, uint64_t *planes) {
+    LDX_TRY(check_rows(s, first_row, n_rows));
+    LDX_REQUIRE(planes || n_rows == 0, "planes is NULL");
+    if (n_rows == 0) return LDX_OK;
+    LDX_CUDA(cudaSetDevice(s->ctx->device));
+    LDX_CUDA(cudaMemcpyAsync(planes, s->d_planes + first_row * s->stride_words,
+                             sizeof(uint64_t) * (size_t)n_rows * s->stride_words, cudaMemcpyDeviceToHost, s->ctx->stream));
+    LDX_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_store_set_mask(ldx_store *s, const uint64_t *mask) {
+    LDX_REQUIRE(s && mask, "NULL argument");
+    std::vector<uint64_t> m(s->stride_words, 0);
+    int64_t n_sel = 0;
+    for (int w = 0; w < s->words; ++w) {
+        uint64_t x = mask[w];
+        if (w == s->words - 1 && (s->n_hap & 63)) x &= (1ull << (s->n_hap & 63)) - 1;   // ignore pad bits
+        m[w] = x;
+        n_sel += __builtin_popcountll(x);
+    }
+    if (n_sel == 0) return set_error(LDX_ERR_EMPTY, "division by zero");   // empty sample selection, calc_ld.py:33
+    LDX_CUDA(cudaSetDevice(s->ctx->device));
+    s->n_sel = (int32_t)n_sel;
+    s->fc.n_hap = (double)n_sel;
+    s->fc.rcp_n = 1.0 / (double)n_sel;
+    // prove the two-FMA quotient equals the IEEE quotient for every count that can occur
+    s->fc.exact_div = 1;
+    for (int64_t n = 0; n <= n_sel; ++n) {
+        const double x = (double)n, q0 = x * s->fc.rcp_n;
+        const double r = std::fma(-q0, s->fc.n_hap, x);
+        if (std::fma(r, s->fc.rcp_n, q0) != x / s->fc.n_hap) { s->fc.exact_div = 0; break; }
+    }
+    LDX_CUDA(cudaMemcpyAsync(s->d_mask, m.data(), sizeof(uint64_t) * s->stride_words, cudaMemcpyHostToDevice, s->ctx->stream));
+    LDX_CUDA(cudaStreamSynchronize(s->ctx->stream));   // m goes out of scope
+    LDX_TRY(launch_variant_freq(s));
+    s->mask_set = true;
+    return LDX_OK;
+}
+
+static int require_mask(const ldx_store *s) {
+    LDX_REQUIRE(s, "store is NULL");
+    if (!s->mask_set) return set_error(LDX_ERR_STATE, "ldx_store_set_mask() must be called first (and again after loading rows)");
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_store_counts(const ldx_store *s, int32_t *n1_out, int32_t *p_e4_out, int32_t *n_hap_sel_out) {
+    LDX_TRY(require_mask(s));
+    if (n_hap_sel_out) *n_hap_sel_out = s->n_sel;
+    if ((n1_out || p_e4_out) && s->n_variants > 0) {
+        LDX_CUDA(cudaSetDevice(s->ctx->device));
+        std::vector<VarFreq> f((size_t)s->n_variants);
+        LDX_CUDA(cudaMemcpyAsync(f.data(), s->d_freq, sizeof(VarFreq) * f.size(), cudaMemcpyDeviceToHost, s->ctx->stream));
+        LDX_CUDA(cudaStreamSynchronize(s->ctx->stream));
+        for (int64_t v = 0; v < s->n_variants; ++v) {
+            if (n1_out) n1_out[v] = f[v].n1;
+            if (p_e4_out) p_e4_out[v] = f[v].p_e4;
+        }
+    }
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_store_subset(const ldx_store *src, const int32_t *sel, int32_t n_sel, ldx_store **store_out) {
+    LDX_REQUIRE(src && sel && store_out, "NULL argument");
+    LDX_REQUIRE(n_sel > 0, "empty selection");
+    for (int32_t k = 0; k < n_sel; ++k) LDX_REQUIRE(sel[k] >= 0 && sel[k] < src->n_hap, "sel[] outside the source haplotypes");
+    ldx_ctx *ctx = src->ctx;
+    ldx_store *dst = nullptr;
+    LDX_TRY(ldx_store_create(ctx, src->n_variants, n_sel, &dst));
+    int32_t *d_sel;
+    int rc = arena_get(ctx, S_MISC, sizeof(int32_t) * (size_t)n_sel, (void **)&d_sel);
+    if (rc == LDX_OK && cudaMemcpyAsync(d_sel, sel, sizeof(int32_t) * (size_t)n_sel, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+        rc = cuda_fail(cudaGetLastError(), "subset: copy sel");
+    if (rc == LDX_OK) rc = launch_subset(src, d_sel, dst);
+    if (rc == LDX_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "subset: sync");
+    if (rc == LDX_OK && src->annotated) {
+        const size_t nv = (size_t)src->n_variants;
+        cudaError_t e = cudaMalloc(&dst->d_pos0, nv * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&dst->d_end0, nv * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&dst->d_idnum, nv * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&dst->d_eligible, nv);
+        if (e == cudaSuccess) e = cudaMemcpy(dst->d_pos0, src->d_pos0, nv * 4, cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dst->d_end0, src->d_end0, nv * 4, cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dst->d_idnum, src->d_idnum, nv * 8, cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dst->d_eligible, src->d_eligible, nv, cudaMemcpyDeviceToDevice);
+        if (e != cudaSuccess) rc = cuda_fail(e, "subset: annotations");
+        else dst->annotated = true;
+    }
+    if (rc == LDX_OK) {
+        std::vector<uint64_t> ones(dst->stride_words, ~0ull);
+        rc = ldx_store_set_mask(dst, ones.data());
+    }
+    if (rc != LDX_OK) { ldx_store_destroy(dst); return rc; }
+    *store_out = dst;
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_store_set_annotations(ldx_store *s, const int32_t *pos0, const int32_t *end0,
+                                             const int64_t *idnum, const uint8_t *eligible) {
+    LDX_REQUIRE(s && pos0 && end0 && idnum && eligible, "NULL argument");
+    LDX_CUDA(cudaSetDevice(s->ctx->device));
+    const size_t nv = (size_t)std::max<int64_t>(s->n_variants, 1);
+    if (!s->d_pos0) {
+        LDX_CUDA(cudaMalloc(&s->d_pos0, nv * 4));
+        LDX_CUDA(cudaMalloc(&s->d_end0, nv * 4));
+        LDX_CUDA(cudaMalloc(&s->d_idnum, nv * 8));
+        LDX_CUDA(cudaMalloc(&s->d_eligible, nv));
+    }
+    const size_t n = (size_t)s->n_variants;
+    cudaStream_t st = s->ctx->stream;
+    LDX_CUDA(cudaMemcpyAsync(s->d_pos0, pos0, n * 4, cudaMemcpyHostToDevice, st));
+    LDX_CUDA(cudaMemcpyAsync(s->d_end0, end0, n * 4, cudaMemcpyHostToDevice, st));
+    LDX_CUDA(cudaMemcpyAsync(s->d_idnum, idnum, n * 8, cudaMemcpyHostToDevice, st));
+    LDX_CUDA(cudaMemcpyAsync(s->d_eligible, eligible, n, cudaMemcpyHostToDevice, st));
+    LDX_CUDA(cudaStreamSynchronize(st));
+    s->annotated = true;
+    return LDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ pairs
+extern "C" int32_t ldx_pairs(ldx_store *s, const int64_t *ia, const int64_t *ib, int64_t n, int32_t *n11,
+                             double *d, double *dprime, double *r2, uint32_t *packed) {
+    LDX_TRY(require_mask(s));
+    LDX_REQUIRE(n >= 0 && (n == 0 || (ia && ib)), "bad pair list");
+    for (int64_t k = 0; k < n; ++k)
+        LDX_REQUIRE(ia[k] >= 0 && ia[k] < s->n_variants && ib[k] >= 0 && ib[k] < s->n_variants, "pair index outside the store");
+    if (n == 0) return LDX_OK;
+    ldx_ctx *ctx = s->ctx;
+    LDX_CUDA(cudaSetDevice(ctx->device));
+    int64_t *d_ia, *d_ib; int32_t *d_n11 = nullptr; double *d_d = nullptr, *d_dp = nullptr, *d_r2 = nullptr; uint32_t *d_pk = nullptr;
+    LDX_TRY(arena_get(ctx, S_IA, sizeof(int64_t) * (size_t)n, (void **)&d_ia));
+    LDX_TRY(arena_get(ctx, S_IB, sizeof(int64_t) * (size_t)n, (void **)&d_ib));
+    if (n11) LDX_TRY(arena_get(ctx, S_N11, sizeof(int32_t) * (size_t)n, (void **)&d_n11));
+    if (d) LDX_TRY(arena_get(ctx, S_D, sizeof(double) * (size_t)n, (void **)&d_d));
+    if (dprime) LDX_TRY(arena_get(ctx, S_DP, sizeof(double) * (size_t)n, (void **)&d_dp));
+    if (r2) LDX_TRY(arena_get(ctx, S_R2, sizeof(double) * (size_t)n, (void **)&d_r2));
+    if (packed) LDX_TRY(arena_get(ctx, S_PACKED, sizeof(uint32_t) * (size_t)n, (void **)&d_pk));
+    cudaStream_t st = ctx->stream;
+    LDX_CUDA(cudaMemcpyAsync(d_ia, ia, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    LDX_CUDA(cudaMemcpyAsync(d_ib, ib, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    LDX_TRY(launch_pairs(s, d_ia, d_ib, n, d_n11, d_d, d_dp, d_r2, d_pk));
+    if (n11) LDX_CUDA(cudaMemcpyAsync(n11, d_n11, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (d) LDX_CUDA(cudaMemcpyAsync(d, d_d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (dprime) LDX_CUDA(cudaMemcpyAsync(dprime, d_dp, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (r2) LDX_CUDA(cudaMemcpyAsync(r2, d_r2, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (packed) LDX_CUDA(cudaMemcpyAsync(packed, d_pk, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    std::vector<FixupRec> recs;
+    LDX_TRY(collect_fixups(ctx, recs));   // synchronises
+    for (const FixupRec &r : recs) {
+        double r2_exact;
+        const uint32_t w = host_finalise_packed(s->fc.n_hap, r.n11, r.n1a, r.n1b, &r2_exact);
+        if (packed) packed[r.out_index] = w;
+        if (r2) r2[r.out_index] = r2_exact;
+    }
+    return LDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ window
+static int stage_window(ldx_store *s, const int64_t *q_row, const int64_t *lo, const int64_t *hi,
+                        const int32_t *ws, const int32_t *we, int64_t nq, int64_t **d_arrays5,
+                        int64_t *n_chunks_out, int64_t *n_candidates_out) {
+    LDX_TRY(require_mask(s));
+    if (!s->annotated) return set_error(LDX_ERR_STATE, "ldx_store_set_annotations() must be called before a window scan");
+    LDX_REQUIRE(nq >= 0 && nq < (1ll << 31) && (nq == 0 || (q_row && lo && hi && ws && we)), "bad query arrays");
+    std::vector<int64_t> prefix((size_t)nq + 1, 0);
+    int64_t cand = 0;
+    for (int64_t k = 0; k < nq; ++k) {
+        LDX_REQUIRE(q_row[k] >= 0 && q_row[k] < s->n_variants, "q_row outside the store");
+        LDX_REQUIRE(lo[k] >= 0 && lo[k] <= hi[k] && hi[k] <= s->n_variants, "candidate range outside the store");
+        prefix[k + 1] = prefix[k] + (hi[k] - lo[k] + WINDOW_CHUNK - 1) / WINDOW_CHUNK;
+        cand += hi[k] - lo[k];
+    }
+    *n_chunks_out = prefix[nq];
+    *n_candidates_out = cand;
+    if (nq == 0) return LDX_OK;
+    ldx_ctx *ctx = s->ctx;
+    LDX_CUDA(cudaSetDevice(ctx->device));
+    // one staging block: q_row | lo | hi | prefix (int64) | ws | we (int32)
+    const size_t n64 = (size_t)nq * 3 + (size_t)nq + 1;
+    const size_t bytes = n64 * 8 + (size_t)nq * 8;
+    uint8_t *blk;
+    LDX_TRY(arena_get(ctx, S_IA, bytes + 64, (void **)&blk));
+    int64_t *d_q = (int64_t *)blk, *d_lo = d_q + nq, *d_hi = d_lo + nq, *d_pref = d_hi + nq;
+    int32_t *d_ws = (int32_t *)(d_pref + nq + 1), *d_we = d_ws + nq;
+    cudaStream_t st = ctx->stream;
+    LDX_CUDA(cudaMemcpyAsync(d_q, q_row, 8 * (size_t)nq, cudaMemcpyHostToDevice, st));
+    LDX_CUDA(cudaMemcpyAsync(d_lo, lo, 8 * (size_t)nq, cudaMemcpyHostToDevice, st));
+    LDX_CUDA(cudaMemcpyAsync(d_hi, hi, 8 * (size_t)nq, cudaMemcpyHostToDevice, st));
+    LDX_CUDA(cudaMemcpyAsync(d_pref, prefix.data(), 8 * ((size_t)nq + 1), cudaMemcpyHostToDevice, st));
+    LDX_CUDA(cudaMemcpyAsync(d_ws, ws, 4 * (size_t)nq, cudaMemcpyHostToDevice, st));
+    LDX_CUDA(cudaMemcpyAsync(d_we, we, 4 * (size_t)nq, cudaMemcpyHostToDevice, st));
+    LDX_CUDA(cudaStreamSynchronize(st));   // prefix is a local
+    d_arrays5[0] = d_q; d_arrays5[1] = d_lo; d_arrays5[2] = d_hi; d_arrays5[3] = d_pref;
+    d_arrays5[4] = (int64_t *)d_ws; d_arrays5[5] = (int64_t *)d_we;
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_window_dev(ldx_store *s, const int64_t *q_row, const int64_t *lo, const int64_t *hi,
+                                  const int32_t *win_start, const int32_t *win_end, int64_t nq,
+                                  int32_t measure, int32_t thres_e4, ldx_hit *dev_hits, int64_t cap,
+                                  int64_t *dev_n_hits) {
+    LDX_REQUIRE(measure == LDX_MEASURE_R2 || measure == LDX_MEASURE_DPRIME, "bad measure");
+    LDX_REQUIRE(dev_hits && dev_n_hits && cap >= 0, "bad output arguments");
+    LDX_REQUIRE((reinterpret_cast<uintptr_t>(dev_hits) & 15) == 0, "dev_hits must be 16-byte aligned");
+    int64_t *arr[6] = {}; int64_t n_chunks = 0, cand = 0;
+    LDX_TRY(stage_window(s, q_row, lo, hi, win_start, win_end, nq, arr, &n_chunks, &cand));
+    ldx_ctx *ctx = s->ctx;
+    // dev_n_hits: [0] hits, [1] pairs scanned
+    LDX_CUDA(cudaMemsetAsync(dev_n_hits, 0, 2 * sizeof(int64_t), ctx->stream));
+    if (nq == 0 || n_chunks == 0) return LDX_OK;
+    LDX_TRY(launch_window(s, arr[0], arr[1], arr[2], (const int32_t *)arr[4], (const int32_t *)arr[5], arr[3], nq,
+                          n_chunks, measure, thres_e4, dev_hits, cap, reinterpret_cast<unsigned long long *>(dev_n_hits)));
+    ctx->pending.kind = 2; ctx->pending.dev_out = dev_hits; ctx->pending.n_hap = s->fc.n_hap;
+    ctx->pending.measure = measure; ctx->pending.has_thres = 1; ctx->pending.thres_e4 = thres_e4;
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_window(ldx_store *s, const int64_t *q_row, const int64_t *lo, const int64_t *hi,
+                              const int32_t *win_start, const int32_t *win_end, int64_t nq, int32_t measure,
+                              int32_t thres_e4, ldx_hit *hits, int64_t cap, int64_t *n_hits, int64_t *n_scanned) {
+    LDX_REQUIRE(n_hits && cap >= 0 && (hits || cap == 0), "bad output arguments");
+    LDX_REQUIRE(s, "store is NULL");
+    ldx_ctx *ctx = s->ctx;
+    *n_hits = 0;
+    if (n_scanned) *n_scanned = 0;
+    ldx_hit *d_hits; int64_t *d_cnt;
+    LDX_TRY(arena_get(ctx, S_HITS, sizeof(ldx_hit) * (size_t)std::max<int64_t>(cap, 1), (void **)&d_hits));
+    LDX_TRY(arena_get(ctx, S_MISC, 2 * sizeof(int64_t), (void **)&d_cnt));
+    LDX_TRY(ldx_window_dev(s, q_row, lo, hi, win_start, win_end, nq, measure, thres_e4, d_hits, cap, d_cnt));
+    ctx->pending.kind = 0;
+    int64_t h_cnt[2] = {0, 0};
+    LDX_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof h_cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    LDX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_scanned) *n_scanned = h_cnt[1];
+    std::vector<FixupRec> recs;
+    if (h_cnt[0] > cap) {
+        collect_fixups(ctx, recs);
+        *n_hits = h_cnt[0];
+        return set_error(LDX_ERR_CAPACITY, "hit buffer too small");
+    }
+    const int64_t n = h_cnt[0];
+    if (n) LDX_CUDA(cudaMemcpyAsync(hits, d_hits, sizeof(ldx_hit) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    LDX_TRY(collect_fixups(ctx, recs));   // synchronises
+    for (const FixupRec &r : recs) {
+        const uint32_t w = settle_word(r, s->fc.n_hap, measure, 1, thres_e4);
+        hits[r.out_index].packed = w;      // LDX_BELOW_THRES marks hits the exact rounding rejects
+    }
+    int64_t kept = n;
+    if (!recs.empty()) {
+        kept = 0;
+        for (int64_t k = 0; k < n; ++k)
+            if (!(hits[k].packed & LDX_BELOW_THRES)) hits[kept++] = hits[k];
+    }
+    // the reference emits rows in VCF order per query (ld_area.py:215): sort by (query, row)
+    std::sort(hits, hits + kept, [](const ldx_hit &a, const ldx_hit &b) {
+        return a.query != b.query ? a.query < b.query : a.row < b.row;
+    });
+    *n_hits = kept;
+    return LDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ triangle
+static int stage_rows(ldx_store *s, const int64_t *rows, int64_t v, int64_t **d_rows_out) {
+    LDX_TRY(require_mask(s));
+    LDX_REQUIRE(v >= 0 && v < (1ll << 31) && (v == 0 || rows), "bad rows");
+    for (int64_t k = 0; k < v; ++k) LDX_REQUIRE(rows[k] >= 0 && rows[k] < s->n_variants, "rows[] outside the store");
+    if (v == 0) { *d_rows_out = nullptr; return LDX_OK; }
+    ldx_ctx *ctx = s->ctx;
+    LDX_CUDA(cudaSetDevice(ctx->device));
+    LDX_TRY(arena_get(ctx, S_IA, sizeof(int64_t) * (size_t)v, (void **)d_rows_out));
+    LDX_CUDA(cudaMemcpyAsync(*d_rows_out, rows, sizeof(int64_t) * (size_t)v, cudaMemcpyHostToDevice, ctx->stream));
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_triangle_dev(ldx_store *s, const int64_t *rows, int64_t v, int32_t measure,
+                                    int32_t has_thres, int32_t thres_e4, int32_t engine,
+                                    uint32_t *dev_packed, int32_t *dev_n11) {
+    LDX_REQUIRE(measure == LDX_MEASURE_R2 || measure == LDX_MEASURE_DPRIME, "bad measure");
+    LDX_REQUIRE(engine >= LDX_ENGINE_AUTO && engine <= LDX_ENGINE_MMA, "bad engine");
+    int64_t *d_rows;
+    LDX_TRY(stage_rows(s, rows, v, &d_rows));
+    if (v < 2) return LDX_OK;
+    ldx_ctx *ctx = s->ctx;
+    if (engine == LDX_ENGINE_MMA && !triangle_mma_available())
+        return set_error(LDX_ERR_ARG, "the tcgen05 engine is not available in this build");
+    const bool use_mma = engine == LDX_ENGINE_MMA || (engine == LDX_ENGINE_AUTO && triangle_mma_available() && v >= 256);
+    // rows[] staging is consumed by the kernel on the same stream; the caller's array may be
+    // freed after return, so wait for the H2D copy (tiny) before returning.
+    int rc = use_mma ? launch_triangle_mma(s, d_rows, v, measure, has_thres, thres_e4, dev_packed, dev_n11)
+                     : launch_triangle_popc(s, d_rows, v, measure, has_thres, thres_e4, dev_packed, dev_n11);
+    LDX_TRY(rc);
+    ctx->pending.kind = 1; ctx->pending.dev_out = dev_packed; ctx->pending.n_hap = s->fc.n_hap;
+    ctx->pending.measure = measure; ctx->pending.has_thres = has_thres; ctx->pending.thres_e4 = thres_e4;
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_triangle(ldx_store *s, const int64_t *rows, int64_t v, int32_t measure,
+                                int32_t has_thres, int32_t thres_e4, int32_t engine, uint32_t *packed,
+                                int32_t *n11) {
+    LDX_REQUIRE(s, "store is NULL");
+    ldx_ctx *ctx = s->ctx;
+    const int64_t n_pairs = v > 1 ? v * (v - 1) / 2 : 0;
+    uint32_t *d_pk = nullptr; int32_t *d_n11 = nullptr;
+    if (n_pairs) {
+        LDX_TRY(arena_get(ctx, S_PACKED, sizeof(uint32_t) * (size_t)n_pairs, (void **)&d_pk));   // always: fix-ups index it
+        if (n11) LDX_TRY(arena_get(ctx, S_N11, sizeof(int32_t) * (size_t)n_pairs, (void **)&d_n11));
+    }
+    LDX_TRY(ldx_triangle_dev(s, rows, v, measure, has_thres, thres_e4, engine, d_pk, d_n11));
+    ctx->pending.kind = 0;
+    if (!n_pairs) return LDX_OK;
+    if (packed) LDX_CUDA(cudaMemcpyAsync(packed, d_pk, sizeof(uint32_t) * (size_t)n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n11) LDX_CUDA(cudaMemcpyAsync(n11, d_n11, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<FixupRec> recs;
+    LDX_TRY(collect_fixups(ctx, recs));   // synchronises
+    if (packed)
+        for (const FixupRec &r : recs) packed[r.out_index] = settle_word(r, s->fc.n_hap, measure, has_thres, thres_e4);
+    return LDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ resolve
+extern "C" int32_t ldx_resolve(ldx_ctx *ctx, int64_t *n_fixed_out) {
+    LDX_REQUIRE(ctx, "ctx is NULL");
+    if (n_fixed_out) *n_fixed_out = 0;
+    LDX_CUDA(cudaSetDevice(ctx->device));
+    std::vector<FixupRec> recs;
+    LDX_TRY(collect_fixups(ctx, recs));
+    const ldx_ctx::Pending p = ctx->pending;
+    ctx->pending.kind = 0;
+    if (recs.empty() || p.kind == 0) return LDX_OK;
+    for (const FixupRec &r : recs) {
+        const uint32_t w = settle_word(r, p.n_hap, p.measure, p.has_thres, p.thres_e4);
+        uint8_t *dst = p.kind == 1 ? reinterpret_cast<uint8_t *>(p.dev_out) + r.out_index * sizeof(uint32_t)
+                                   : reinterpret_cast<uint8_t *>(p.dev_out) + r.out_index * sizeof(ldx_hit) + offsetof(ldx_hit, packed);
+        LDX_CUDA(cudaMemcpyAsync(dst, &w, sizeof w, cudaMemcpyHostToDevice, ctx->stream));
+        LDX_CUDA(cudaStreamSynchronize(ctx->stream));   // w is a local; fix-ups are rare
+    }
+    if (n_fixed_out) *n_fixed_out = (int64_t)recs.size();
+    return LDX_OK;
+}

@@ -1,0 +1,91 @@
+// ldx_internal.h -- host-side structs and kernel launchers shared by the .cu files of libldx.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "ldx_common.cuh"
+
+struct ldx_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;        // the stream kernels are launched on
+    int64_t launches = 0;
+    // near-tie fix-up list (device) + pinned host mirror
+    ldx::FixupRec *d_fix = nullptr;
+    uint32_t *d_fix_count = nullptr;      // [0] = records appended (may exceed capacity)
+    uint32_t fix_capacity = 0;
+    ldx::FixupRec *h_fix = nullptr;       // pinned
+    uint32_t *h_fix_count = nullptr;      // pinned
+    // what the pending fix-ups refer to (set by the last *_dev call)
+    struct Pending {
+        int kind = 0;                     // 0 none, 1 packed array, 2 hit array
+        void *dev_out = nullptr;
+        double n_hap = 0;
+        int measure = 0, has_thres = 0, thres_e4 = 0;
+    } pending;
+    // scratch for small per-call index arrays
+    void *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // MMA-path scratch (expanded operand panels), grown on demand
+    void *d_mma_ops = nullptr;
+    size_t mma_ops_bytes = 0;
+    std::vector<int> mma_checked;         // lazily filled: tcgen05 path self-test verdicts
+};
+
+struct ldx_store {
+    ldx_ctx *ctx = nullptr;
+    int64_t n_variants = 0;
+    int32_t n_hap = 0;          // haplotype columns in the planes
+    int32_t words = 0;          // ceil(n_hap / 64)
+    int32_t stride_words = 0;   // row pitch in uint64 (multiple of 16)
+    uint64_t *d_planes = nullptr;
+    uint64_t *d_mask = nullptr; // [stride_words]
+    ldx::VarFreq *d_freq = nullptr;   // [n_variants], valid once mask_set
+    int32_t n_sel = 0;          // N = popcount(mask)
+    bool mask_set = false;
+    ldx::FinalCtx fc{};
+    // annotations for the fused window filters
+    int32_t *d_pos0 = nullptr, *d_end0 = nullptr;
+    int64_t *d_idnum = nullptr;
+    uint8_t *d_eligible = nullptr;
+    bool annotated = false;
+};
+
+namespace ldx {
+
+int set_error(int code, const std::string &msg);   // returns code
+int cuda_fail(cudaError_t e, const char *what);    // records + returns LDX_ERR_CUDA
+
+#define LDX_CUDA(call)                                                   \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) return ldx::cuda_fail(e__, #call);       \
+    } while (0)
+
+// ---- kernel launchers (each enqueues on ctx->stream and bumps ctx->launches)
+int launch_pack_gt(ldx_ctx *ctx, const uint8_t *d_text, const int64_t *d_row_off, int64_t row_pitch,
+                   int64_t n_rows, int32_t n_samples, uint64_t *d_planes_first, int32_t stride_words,
+                   uint8_t *d_status);
+int launch_variant_freq(ldx_store *s);
+int launch_subset(const ldx_store *src, const int32_t *d_sel, ldx_store *dst);
+int launch_pairs(ldx_store *s, const int64_t *d_ia, const int64_t *d_ib, int64_t n, int32_t *d_n11,
+                 double *d_d, double *d_dp, double *d_r2, uint32_t *d_packed);
+int launch_lists(ldx_ctx *ctx, const uint8_t *d_ga, int64_t len_a, const uint8_t *d_gb, int64_t len_b,
+                 ldx_ld_result *d_out);
+int launch_window(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, const int64_t *d_hi,
+                  const int32_t *d_ws, const int32_t *d_we, const int64_t *d_chunk_prefix, int64_t nq,
+                  int64_t n_chunks, int measure, int thres_e4, ldx_hit *d_hits, int64_t cap,
+                  unsigned long long *d_n_hits);
+int launch_triangle_popc(ldx_store *s, const int64_t *d_rows, int64_t v, int measure, int has_thres,
+                         int thres_e4, uint32_t *d_packed, int32_t *d_n11);
+int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int measure, int has_thres,
+                        int thres_e4, uint32_t *d_packed, int32_t *d_n11);
+bool triangle_mma_available();
+
+constexpr int WINDOW_CHUNK = 256;   // rows per work item of the window kernel
+
+}  // namespace ldx

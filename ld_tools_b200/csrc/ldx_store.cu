@@ -1,0 +1,182 @@
+// ldx_store.cu -- kernels that build and summarise the bit-plane store.
+//
+//   K1 pack_gt_kernel      VCF GT text -> one bit per haplotype (replaces the per-sample
+//                          `rec.samples[name]['GT']` loops, ld_area.py:182-187 / :230-235,
+//                          ld_triangle.py:158-186, ld_lite.py:109-137)
+//   K2 variant_freq_kernel n1 = popcount(mask & plane), p, q, p*q, round(p,4)
+//                          (calc_ld.py:37-44, :96-97; ld_area.py:188-189)
+//   subset_kernel          gather selected haplotype columns into a narrower store
+#include "ldx_internal.h"
+
+namespace ldx {
+
+// ------------------------------------------------------------------------------------------ K1
+// One CTA per variant row (grid-stride).  The row's text (4 bytes per sample, arbitrary byte
+// alignment inside the VCF line) is staged into shared memory with aligned 16-byte loads, then
+// each warp turns 32 samples into one 64-bit word: two ballots (allele slot 0 / slot 1) that one
+// lane bit-interleaves, because haplotype 2*s+a lives at bit 2*s+a.
+constexpr int PACK_THREADS = 256;
+
+__device__ __forceinline__ uint64_t spread_bits(uint32_t x) {   // bit i -> bit 2i
+    uint64_t v = x;
+    v = (v | (v << 16)) & 0x0000ffff0000ffffull;
+    v = (v | (v << 8)) & 0x00ff00ff00ff00ffull;
+    v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+
+__global__ void __launch_bounds__(PACK_THREADS)
+pack_gt_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_off, int64_t row_pitch,
+               int64_t n_rows, int32_t n_samples, uint64_t *__restrict__ planes, int32_t stride_words,
+               uint8_t *__restrict__ status) {
+    extern __shared__ uint4 stage[];                 // row text, 16-byte granules
+    __shared__ int s_bad;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_warps = PACK_THREADS / 32;
+    const int64_t row_bytes = 4ll * n_samples;
+    const int n_words_data = (2 * n_samples + 63) / 64;
+    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const int64_t off = row_off ? row_off[r] : r * row_pitch;
+        const int64_t aligned = off & ~15ll;
+        const int skew = (int)(off - aligned);
+        const int n_gran = (int)((skew + row_bytes + 15) >> 4);
+        const uint4 *src = reinterpret_cast<const uint4 *>(text + aligned);
+        if (threadIdx.x == 0) s_bad = 0;
+        for (int g = threadIdx.x; g < n_gran; g += PACK_THREADS) stage[g] = ldg_u4_stream(src + g);
+        __syncthreads();
+        const uint8_t *row = reinterpret_cast<const uint8_t *>(stage) + skew;
+        uint64_t *out = planes + r * (int64_t)stride_words;
+        int bad = 0;
+        for (int w = warp; w < stride_words; w += n_warps) {
+            uint64_t word = 0;
+            if (w < n_words_data) {
+                const int s = w * 32 + lane;
+                uint32_t a0 = 0, a1 = 0;
+                if (s < n_samples) {
+                    const uint8_t c0 = row[4 * s], sep = row[4 * s + 1], c1 = row[4 * s + 2];
+                    a0 = c0 == '1'; a1 = c1 == '1';
+                    bad |= (c0 != '0' && c0 != '1') || (c1 != '0' && c1 != '1') || sep != '|';
+                }
+                const uint32_t b0 = __ballot_sync(0xffffffffu, a0);
+                const uint32_t b1 = __ballot_sync(0xffffffffu, a1);
+                word = spread_bits(b0) | (spread_bits(b1) << 1);
+            }
+            if (lane == 0) out[w] = word;            // pad words are written as zero
+        }
+        if (bad) atomicOr(&s_bad, 1);
+        __syncthreads();
+        if (threadIdx.x == 0 && status) status[r] = (uint8_t)s_bad;
+        __syncthreads();
+    }
+}
+
+int launch_pack_gt(ldx_ctx *ctx, const uint8_t *d_text, const int64_t *d_row_off, int64_t row_pitch,
+                   int64_t n_rows, int32_t n_samples, uint64_t *d_planes_first, int32_t stride_words,
+                   uint8_t *d_status) {
+    if (n_rows <= 0) return LDX_OK;
+    const size_t smem = ((size_t)4 * n_samples + 15 + 16) / 16 * 16 + 16;
+    if (smem > 200 * 1024) return set_error(LDX_ERR_ARG, "pack_gt: row too long for shared memory");
+    if (smem > 48 * 1024)
+        LDX_CUDA(cudaFuncSetAttribute(pack_gt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t want = (int64_t)ctx->sm_count * 8;
+    const int grid = (int)(n_rows < want ? n_rows : want);
+    pack_gt_kernel<<<grid, PACK_THREADS, smem, ctx->stream>>>(d_text, d_row_off, row_pitch, n_rows,
+                                                               n_samples, d_planes_first, stride_words,
+                                                               d_status);
+    ctx->launches++;
+    LDX_CUDA(cudaGetLastError());
+    return LDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ K2
+// Eight lanes per variant: lane l of a group loads 16-byte granules l, l+8, ... of the 128-byte
+// aligned row (each group load is one full 128-byte line), popcounts under the mask, and a
+// 3-step shuffle tree sums the group.  HBM-bound: one pass over the store.
+constexpr int FREQ_THREADS = 256;
+
+__global__ void __launch_bounds__(FREQ_THREADS)
+variant_freq_kernel(const uint4 *__restrict__ planes, const uint4 *__restrict__ mask, int32_t stride_u4,
+                    int64_t n_variants, FinalCtx fc, VarFreq *__restrict__ freq) {
+    const int sub = threadIdx.x & 7;
+    const int64_t group0 = ((int64_t)blockIdx.x * FREQ_THREADS + threadIdx.x) >> 3;
+    const int64_t n_groups = ((int64_t)gridDim.x * FREQ_THREADS) >> 3;   // multiple of 4
+    // the loop bound is warp-uniform (first group of the warp) so the shuffles stay converged
+    for (int64_t vb = group0 & ~3ll; vb < n_variants; vb += n_groups) {
+        const int64_t v = vb + (group0 & 3);
+        const bool valid = v < n_variants;
+        const uint4 *row = planes + (valid ? v : 0) * stride_u4;
+        int cnt = 0;
+        if (valid)
+            for (int g = sub; g < stride_u4; g += 8) cnt += popc_and_u4(ldg_u4_stream(row + g), __ldg(mask + g));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+        if (sub == 0 && valid) {
+            VarFreq f;
+            f.n1 = cnt;
+            f.p = __ddiv_rn((double)cnt, fc.n_hap);                        // calc_ld.py:41
+            f.q = __ddiv_rn((double)((int)fc.n_hap - cnt), fc.n_hap);      // calc_ld.py:42
+            f.pq = __dmul_rn(f.p, f.q);
+            bool tie;
+            f.p_e4 = (int32_t)round4_e4(f.p, tie);                         // calc_ld.py:96
+            freq[v] = f;
+        }
+    }
+}
+
+int launch_variant_freq(ldx_store *s) {
+    if (s->n_variants <= 0) return LDX_OK;
+    ldx_ctx *ctx = s->ctx;
+    // whole warps must stay converged for the shuffles: every group of a warp iterates the same
+    // number of times because the loop bound is rounded up per warp below.
+    const int64_t groups_needed = (s->n_variants + 3) / 4 * 4;
+    int64_t blocks = (groups_needed * 8 + FREQ_THREADS - 1) / FREQ_THREADS;
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    variant_freq_kernel<<<(int)blocks, FREQ_THREADS, 0, ctx->stream>>>(
+        reinterpret_cast<const uint4 *>(s->d_planes), reinterpret_cast<const uint4 *>(s->d_mask),
+        s->stride_words / 2, s->n_variants, s->fc, s->d_freq);
+    ctx->launches++;
+    LDX_CUDA(cudaGetLastError());
+    return LDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ subset
+// dst bit k of variant v = src bit sel[k].  One thread per destination word.
+__global__ void subset_kernel(const uint64_t *__restrict__ src, int32_t src_stride, const int32_t *__restrict__ sel,
+                              int32_t n_sel, int64_t n_variants, uint64_t *__restrict__ dst, int32_t dst_stride) {
+    const int64_t total = n_variants * dst_stride;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = i / dst_stride;
+        const int w = (int)(i - v * dst_stride);
+        const uint64_t *row = src + v * src_stride;
+        uint64_t word = 0;
+        const int k0 = w * 64;
+        for (int b = 0; b < 64; ++b) {
+            const int k = k0 + b;
+            if (k < n_sel) {
+                const int h = __ldg(sel + k);
+                word |= ((row[h >> 6] >> (h & 63)) & 1ull) << b;
+            }
+        }
+        dst[i] = word;
+    }
+}
+
+int launch_subset(const ldx_store *src, const int32_t *d_sel, ldx_store *dst) {
+    if (src->n_variants <= 0) return LDX_OK;
+    ldx_ctx *ctx = src->ctx;
+    const int64_t total = src->n_variants * dst->stride_words;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    subset_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(src->d_planes, src->stride_words, d_sel, dst->n_hap,
+                                                         src->n_variants, dst->d_planes, dst->stride_words);
+    ctx->launches++;
+    LDX_CUDA(cudaGetLastError());
+    return LDX_OK;
+}
+
+}  // namespace ldx

@@ -1,0 +1,277 @@
+"""Thin object layer over the C ABI (include/ldx.h): Context and Store.
+
+Everything numeric happens in libldx.so on the GPU; this module only marshals numpy arrays,
+turns status codes into exceptions and decodes the packed result words into the Python objects
+the reference returns (int `0` vs float, calc_ld.py:68-69/:89-90; round(x, 4), calc_ld.py:94-97).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (BELOW_THRES, DP_INT0, DP_MASK, DP_SHIFT, ENGINE_AUTO, ENGINE_MMA, ENGINE_POPC,  # noqa: F401
+                   HIT_DTYPE, LD_RESULT_DTYPE, MEASURE_DPRIME, MEASURE_R2, R2_INT0, R2_MASK, LdxError,
+                   check, ptr)
+
+MEASURES = {"r_square": MEASURE_R2, "d_prime": MEASURE_DPRIME}   # the CLI's -l choices
+
+
+def stride_words(n_hap):
+    """Row pitch of a store in 64-bit words: ceil(n_hap/64) rounded up to 16 (128-byte rows)."""
+    return ((n_hap + 63) // 64 + 15) // 16 * 16
+
+
+def threshold_e4(thres):
+    """Smallest integer n with n / 10000.0 >= thres: the rounded-value test of ld_area.py:248
+    (`trg_vals[measure] < thres -> skip`) restated on round(x,4)*10^4 integers, exactly."""
+    n = int(np.floor(float(thres) * 10000.0))
+    while n / 10000.0 >= thres:
+        n -= 1
+    while n / 10000.0 < thres:
+        n += 1
+    return max(n, 0)
+
+
+def r2_e4(packed):
+    return (np.asarray(packed) & R2_MASK).astype(np.int32)
+
+
+def dprime_e4(packed):
+    return ((np.asarray(packed) & DP_MASK) >> DP_SHIFT).astype(np.int32)
+
+
+def r2_value(word):
+    """Packed word -> the object calc_ld returns under 'r_square' (int 0 or a rounded float)."""
+    word = int(word)
+    return 0 if word & R2_INT0 else (word & R2_MASK) / 10000.0
+
+
+def dprime_value(word):
+    word = int(word)
+    return 0 if word & DP_INT0 else ((word & DP_MASK) >> DP_SHIFT) / 10000.0
+
+
+def measure_value(word, measure):
+    return r2_value(word) if measure in ("r_square", MEASURE_R2) else dprime_value(word)
+
+
+def _measure_code(measure):
+    return MEASURES[measure] if isinstance(measure, str) else int(measure)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+class Context:
+    """One CUDA context/stream of libldx.  Create it AFTER fork (see include/ldx.h)."""
+
+    def __init__(self, device=-1):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        check(self._lib.ldx_init(int(device), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ldx_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_stream(self, cuda_stream):
+        check(self._lib.ldx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        check(self._lib.ldx_synchronize(self._h))
+
+    @property
+    def sm_count(self):
+        n = C.c_int32()
+        check(self._lib.ldx_sm_count(self._h, C.byref(n)))
+        return n.value
+
+    @property
+    def launch_count(self):
+        n = C.c_int64()
+        check(self._lib.ldx_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def resolve(self):
+        n = C.c_int64()
+        check(self._lib.ldx_resolve(self._h, C.byref(n)))
+        return n.value
+
+    def calc_ld_lists(self, codes_a, codes_b):
+        """Genotype byte codes (0 ref, 1 alt, other = neither) -> LD_RESULT_DTYPE record."""
+        a = np.ascontiguousarray(codes_a, dtype=np.uint8)
+        b = np.ascontiguousarray(codes_b, dtype=np.uint8)
+        out = np.zeros(1, dtype=LD_RESULT_DTYPE)
+        rc = self._lib.ldx_calc_ld_lists(self._h, ptr(a), a.shape[0], ptr(b), b.shape[0], ptr(out))
+        if rc == _lib.ERR_EMPTY:
+            raise ZeroDivisionError("division by zero")   # what calc_ld.py:33 raises on empty input
+        check(rc)
+        return out[0]
+
+
+class Store:
+    """Bit-plane store of one chromosome in HBM (see include/ldx.h "Data model")."""
+
+    def __init__(self, ctx, n_variants, n_hap, _handle=None):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        if _handle is None:
+            _handle = C.c_void_p()
+            check(self._lib.ldx_store_create(ctx._h, int(n_variants), int(n_hap), C.byref(_handle)))
+        self._h = _handle
+        nv, nh, sw = C.c_int64(), C.c_int32(), C.c_int32()
+        check(self._lib.ldx_store_shape(self._h, C.byref(nv), C.byref(nh), C.byref(sw)))
+        self.n_variants, self.n_hap, self.stride_words = nv.value, nh.value, sw.value
+
+    @classmethod
+    def from_planes(cls, ctx, planes, n_hap):
+        planes = np.ascontiguousarray(planes, dtype="<u8")
+        s = cls(ctx, planes.shape[0], n_hap)
+        assert planes.shape[1] == s.stride_words, (planes.shape, s.stride_words)
+        s.upload(0, planes)
+        return s
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self._lib.ldx_store_destroy(self._h)
+        self._h = None
+
+    __del__ = close
+
+    @property
+    def planes_ptr(self):
+        p = C.c_void_p()
+        check(self._lib.ldx_store_planes_ptr(self._h, C.byref(p)))
+        return p.value
+
+    # ---- loading
+    def pack_gt(self, first_row, text, n_samples, row_off=None, row_pitch=0):
+        """GPU bit-packing of VCF GT text (K1).  Returns the per-row status bytes."""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        n_rows = len(row_off) if row_off is not None else (text.shape[0] + 1) // row_pitch if row_pitch else 0
+        off = _i64(row_off) if row_off is not None else None
+        status = np.zeros(n_rows, dtype=np.uint8)
+        check(self._lib.ldx_store_pack_gt(self._h, int(first_row), n_rows, ptr(text), text.shape[0], ptr(off),
+                                          int(row_pitch), int(n_samples), ptr(status)))
+        return status
+
+    def upload(self, first_row, planes):
+        planes = np.ascontiguousarray(planes, dtype="<u8")
+        check(self._lib.ldx_store_upload(self._h, int(first_row), planes.shape[0], ptr(planes)))
+
+    def download(self, first_row=0, n_rows=None):
+        n_rows = self.n_variants - first_row if n_rows is None else n_rows
+        out = np.zeros((n_rows, self.stride_words), dtype="<u8")
+        check(self._lib.ldx_store_download(self._h, int(first_row), int(n_rows), ptr(out)))
+        return out
+
+    # ---- sample selection
+    def set_mask(self, mask_words):
+        m = np.zeros(self.stride_words, dtype="<u8")
+        mask_words = np.asarray(mask_words, dtype="<u8")
+        m[:mask_words.shape[0]] = mask_words
+        rc = self._lib.ldx_store_set_mask(self._h, ptr(m))
+        if rc == _lib.ERR_EMPTY:
+            raise ZeroDivisionError("division by zero")
+        check(rc)
+
+    def select_haplotypes(self, hap_idx):
+        """Mask from haplotype column indices (2*sample_column + allele slot)."""
+        bits = np.zeros(self.stride_words * 64, dtype=np.uint8)
+        bits[np.asarray(hap_idx, dtype=np.int64)] = 1
+        self.set_mask(np.packbits(bits, bitorder="little").view("<u8"))
+
+    def select_all(self):
+        self.select_haplotypes(np.arange(self.n_hap))
+
+    def counts(self):
+        n1 = np.zeros(self.n_variants, dtype=np.int32)
+        p_e4 = np.zeros(self.n_variants, dtype=np.int32)
+        n = C.c_int32()
+        check(self._lib.ldx_store_counts(self._h, ptr(n1), ptr(p_e4), C.byref(n)))
+        return n1, p_e4, n.value
+
+    def subset(self, hap_idx):
+        sel = np.ascontiguousarray(hap_idx, dtype=np.int32)
+        h = C.c_void_p()
+        rc = self._lib.ldx_store_subset(self._h, ptr(sel), sel.shape[0], C.byref(h))
+        check(rc)
+        return Store(self.ctx, self.n_variants, sel.shape[0], _handle=h)
+
+    def set_annotations(self, pos0, end0, idnum, eligible):
+        pos0 = np.ascontiguousarray(pos0, dtype=np.int32)
+        end0 = np.ascontiguousarray(end0, dtype=np.int32)
+        idnum = _i64(idnum)
+        eligible = np.ascontiguousarray(eligible, dtype=np.uint8)
+        assert pos0.shape[0] == end0.shape[0] == idnum.shape[0] == eligible.shape[0] == self.n_variants
+        check(self._lib.ldx_store_set_annotations(self._h, ptr(pos0), ptr(end0), ptr(idnum), ptr(eligible)))
+
+    # ---- compute
+    def pairs(self, ia, ib, raw=True):
+        """LD of explicit row pairs (var_1 = ia[k], var_2 = ib[k]).  -> dict of arrays."""
+        ia, ib = _i64(ia), _i64(ib)
+        n = ia.shape[0]
+        out = {"n11": np.zeros(n, np.int32), "packed": np.zeros(n, np.uint32)}
+        if raw:
+            out.update(d=np.zeros(n), dprime=np.zeros(n), r2=np.zeros(n))
+        check(self._lib.ldx_pairs(self._h, ptr(ia), ptr(ib), n, ptr(out["n11"]), ptr(out.get("d")),
+                                  ptr(out.get("dprime")), ptr(out.get("r2")), ptr(out["packed"])))
+        return out
+
+    def window(self, q_row, lo, hi, win_start, win_end, measure, thres_e4_, cap=None):
+        """Fused ld_area scan.  -> (hits sorted by (query, row), pairs scanned)."""
+        q_row, lo, hi = _i64(q_row), _i64(lo), _i64(hi)
+        ws = np.ascontiguousarray(win_start, dtype=np.int32)
+        we = np.ascontiguousarray(win_end, dtype=np.int32)
+        nq = q_row.shape[0]
+        if cap is None:
+            cap = int(min(max(int((hi - lo).sum()), 1), 1 << 22))
+        while True:
+            hits = np.zeros(cap, dtype=HIT_DTYPE)
+            n_hits, n_scanned = C.c_int64(), C.c_int64()
+            rc = self._lib.ldx_window(self._h, ptr(q_row), ptr(lo), ptr(hi), ptr(ws), ptr(we), nq,
+                                      _measure_code(measure), int(thres_e4_), ptr(hits), cap,
+                                      C.byref(n_hits), C.byref(n_scanned))
+            if rc == _lib.ERR_CAPACITY:
+                cap = int(n_hits.value) + 1024
+                continue
+            check(rc)
+            return hits[:n_hits.value], n_scanned.value
+
+    def triangle(self, rows, measure="r_square", thres_e4_=None, engine=ENGINE_AUTO, want_n11=False, out=None):
+        """All pairs of `rows` (matrix order).  -> (packed lower triangle by rows, n11 or None).
+        `out` may be a caller-owned uint32 array (e.g. pinned memory) of v*(v-1)/2 entries."""
+        rows = _i64(rows)
+        v = rows.shape[0]
+        n_pairs = v * (v - 1) // 2
+        packed = np.zeros(n_pairs, dtype=np.uint32) if out is None else out
+        assert packed.dtype == np.uint32 and packed.shape[0] == n_pairs and packed.flags.c_contiguous
+        n11 = np.zeros(n_pairs, dtype=np.int32) if want_n11 else None
+        check(self._lib.ldx_triangle(self._h, ptr(rows), v, _measure_code(measure), int(thres_e4_ is not None),
+                                     int(thres_e4_ or 0), int(engine), ptr(packed), ptr(n11)))
+        return packed, n11
+
+    def triangle_dev(self, rows, dev_packed, dev_n11=0, measure="r_square", thres_e4_=None, engine=ENGINE_AUTO):
+        """Device-resident output (raw device addresses); enqueue only.  Call ctx.resolve() after."""
+        rows = _i64(rows)
+        check(self._lib.ldx_triangle_dev(self._h, ptr(rows), rows.shape[0], _measure_code(measure),
+                                         int(thres_e4_ is not None), int(thres_e4_ or 0), int(engine),
+                                         C.c_void_p(dev_packed), C.c_void_p(dev_n11 or 0)))
+
+    def window_dev(self, q_row, lo, hi, win_start, win_end, measure, thres_e4_, dev_hits, cap, dev_counters):
+        q_row, lo, hi = _i64(q_row), _i64(lo), _i64(hi)
+        ws = np.ascontiguousarray(win_start, dtype=np.int32)
+        we = np.ascontiguousarray(win_end, dtype=np.int32)
+        check(self._lib.ldx_window_dev(self._h, ptr(q_row), ptr(lo), ptr(hi), ptr(ws), ptr(we), q_row.shape[0],
+                                       _measure_code(measure), int(thres_e4_), C.c_void_p(dev_hits), int(cap),
+                                       C.c_void_p(dev_counters)))
+
+
+def tri_index(row, col):
+    """Position of pair (row > col) in the packed lower triangle."""
+    return row * (row - 1) // 2 + col

@@ -199,3 +199,22 @@ void ldo_pack_gt(const uint8_t *text, const int64_t *row_off, int64_t n_variants
 }
 
 int64_t ldo_sizeof_result(void) { return (int64_t)sizeof(ldo_result); }
+
+/* The engine's packed result word (include/ldx.h) derived from an oracle result: lets the tests
+ * compare millions of pairs array-to-array.  0x8000 = r2 is int 0, 0x80000000 = D' is int 0. */
+uint32_t ldo_packed_word(const ldo_result *r) {
+    uint32_t w = 0;
+    if (r->r2_is_int0) w |= 0x00008000u; else w |= (uint32_t)llround(r->r2_rounded * 10000.0);
+    if (r->dprime_is_int0) w |= 0x80000000u; else w |= ((uint32_t)llround(r->dprime_rounded * 10000.0)) << 16;
+    return w;
+}
+
+int ldo_finalise_packed_many(int64_t n_hap, const int32_t *n11, const int32_t *n1a, const int32_t *n1b,
+                             int64_t n, uint32_t *out) {
+    for (int64_t k = 0; k < n; ++k) {
+        ldo_result r;
+        if (ldo_finalise(n_hap, n11[k], n1a[k], n_hap - n1a[k], n1b[k], n_hap - n1b[k], &r)) return -1;
+        out[k] = ldo_packed_word(&r);
+    }
+    return 0;
+}

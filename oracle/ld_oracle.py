@@ -124,6 +124,26 @@ def finalise_many(n_hap, n_11, n_a1, n_b1):
     return out
 
 
+def packed_words(n_hap, n_11, n_a1, n_b1):
+    """Engine-format packed words (include/ldx.h) for arrays of counts, via the C oracle."""
+    n_11 = np.ascontiguousarray(n_11, dtype=np.int32)
+    a1 = np.ascontiguousarray(np.broadcast_to(np.asarray(n_a1, dtype=np.int32), n_11.shape))
+    b1 = np.ascontiguousarray(np.broadcast_to(np.asarray(n_b1, dtype=np.int32), n_11.shape))
+    out = np.zeros(n_11.shape[0], dtype=np.uint32)
+    if lib().ldo_finalise_packed_many(_i64(n_hap), _p(n_11), _p(a1), _p(b1), _i64(n_11.shape[0]), _p(out)):
+        raise ZeroDivisionError("division by zero")
+    return out
+
+
+def packed_of(res):
+    """Packed words of an array of ldo_result records."""
+    res = np.atleast_1d(res)
+    w = np.where(res["r2_is_int0"] != 0, 0x8000, np.rint(res["r2_rounded"] * 10000.0).astype(np.int64))
+    w = w | np.where(res["dprime_is_int0"] != 0, 0x80000000,
+                     np.rint(res["dprime_rounded"] * 10000.0).astype(np.int64) << 16)
+    return w.astype(np.uint32)
+
+
 def encode_genotypes(g):
     """Python genotype sequence -> byte codes 0 / 1 / 255 (anything that is neither == 0 nor == 1)."""
     arr = np.asarray(list(g), dtype=object)

@@ -1,0 +1,322 @@
+"""Parity of the CUDA path (through the C ABI, libldx.so) against the CPU oracle and the golden
+vectors produced by the reference's own calc_ld.  Run on a B200: `pytest -m gpu`.
+
+Bars (BASELINE.json north_star): counts bit-exact; D / D' / r2 within 1e-12 absolute of the
+reference before rounding (they are in fact bit-exact except r2, which can differ in the last
+ulp because the reference squares D with libm pow); rounded outputs identical, including the
+reference's int-0 vs float types; ld_area pair sets identical.
+"""
+import numpy as np
+import pytest
+
+from conftest import decode_genotypes, decode_raw
+from oracle import calc_ld_port, ld_oracle
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("r_square", "d_prime", "var_1_alt_freq", "var_2_alt_freq")
+TOL = 1e-12   # absolute, pre-rounding (north_star)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from ld_tools_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def same_obj(a, b):
+    return type(a) is type(b) and repr(a) == repr(b)
+
+
+def planes_from_counts(cases, n):
+    """Two store rows per (n11, n1a, n1b) case with exactly those counts (scattered bit positions)."""
+    rng = np.random.default_rng(n)
+    h = np.zeros((2 * len(cases), n), dtype=np.uint8)
+    for k, (n11, a, b) in enumerate(cases):
+        perm = rng.permutation(n)
+        oa, ob = a - n11, b - n11
+        h[2 * k, perm[:n11 + oa]] = 1
+        h[2 * k + 1, perm[:n11]] = 1
+        h[2 * k + 1, perm[n11 + oa:n11 + oa + ob]] = 1
+    return ld_oracle.pack_bits(h)
+
+
+# ------------------------------------------------------------------ calc_ld drop-in (lists)
+
+def test_calc_ld_dropin_matches_reference_golden(golden, ctx):
+    from ld_tools_b200 import calc_ld
+    for name, sa, sb, *out in golden["list_cases"]:
+        g1, g2 = decode_genotypes(sa), decode_genotypes(sb)
+        if name == "tuple_inputs":
+            g1, g2 = tuple(g1), tuple(g2)
+        got = calc_ld(g1, g2)
+        assert list(got) == list(KEYS)
+        for k, want in zip(KEYS, out[:4]):
+            assert repr(got[k]) == want, (name, k, got[k], want)
+
+
+def test_calc_ld_lists_raw_values_and_counts(golden, ctx):
+    from ld_tools_b200.calc_ld import encode_genotypes
+    for name, sa, sb, *out in golden["list_cases"]:
+        g1, g2 = decode_genotypes(sa), decode_genotypes(sb)
+        res = ctx.calc_ld_lists(encode_genotypes(g1), encode_genotypes(g2))
+        full = calc_ld_port.calc_ld_full(g1, g2)
+        for f_dev, f_port in (("n_hap", "n_hap"), ("n_11", "n_11"), ("n_a1", "n_a1"), ("n_a0", "n_a0"),
+                              ("n_b1", "n_b1"), ("n_b0", "n_b0")):
+            assert int(res[f_dev]) == full[f_port], (name, f_dev)
+        raw = [decode_raw(x) for x in out[4:9]]
+        assert float(res["d"]).hex() == float(raw[4]).hex(), name             # D bit-exact
+        assert float(res["p_a"]).hex() == float(raw[2]).hex() and float(res["p_b"]).hex() == float(raw[3]).hex()
+        assert bool(res["dprime_is_int0"]) == isinstance(raw[1], int), name
+        assert bool(res["r2_is_int0"]) == isinstance(raw[0], int), name
+        if not isinstance(raw[1], int):
+            assert float(res["dprime"]).hex() == raw[1].hex(), name             # D' bit-exact
+        if not isinstance(raw[0], int):
+            assert abs(float(res["r2"]) - raw[0]) <= TOL, name
+
+
+def test_calc_ld_empty_raises_zero_division(ctx):
+    from ld_tools_b200 import calc_ld
+    with pytest.raises(ZeroDivisionError):
+        calc_ld([], [])
+    with pytest.raises(ZeroDivisionError):
+        calc_ld([1, 0], [])
+
+
+def test_calc_ld_numeric_types(ctx):
+    """list.count semantics: 1.0 and True count as alt, None / 2 as neither (calc_ld.py:37-40)."""
+    from ld_tools_b200 import calc_ld
+    g1, g2 = [1.0, 0.0, True, False, 1, 0, None, 2], [1, 0, 1.0, 0, 0.0, True, 1, 1]
+    assert calc_ld(g1, g2) == calc_ld_port.calc_ld(g1, g2)
+    assert all(same_obj(calc_ld(g1, g2)[k], calc_ld_port.calc_ld(g1, g2)[k]) for k in KEYS)
+
+
+# ------------------------------------------------------------------ store rows: pairs kernel
+
+def test_pairs_match_reference_golden_counts(golden, ctx):
+    from ld_tools_b200 import Store
+    from ld_tools_b200.engine import dprime_value, r2_value
+    by_n = {}
+    for tag, n, n11, a, b, *out in golden["count_cases"]:
+        by_n.setdefault(n, []).append(((n11, a, b), out))
+    for n, items in by_n.items():
+        planes = planes_from_counts([c for c, _ in items], n)
+        st = Store.from_planes(ctx, planes, n)
+        st.select_all()
+        n1, p_e4, n_sel = st.counts()
+        assert n_sel == n
+        k = np.arange(len(items))
+        res = st.pairs(2 * k, 2 * k + 1)
+        for i, ((n11, a, b), out) in enumerate(items):
+            assert res["n11"][i] == n11 and n1[2 * i] == a and n1[2 * i + 1] == b
+            word = res["packed"][i]
+            assert repr(r2_value(word)) == out[0], (n, n11, a, b, r2_value(word), out[0])
+            assert repr(dprime_value(word)) == out[1], (n, n11, a, b)
+            assert repr(p_e4[2 * i] / 10000.0) == out[2] and repr(p_e4[2 * i + 1] / 10000.0) == out[3]
+            raw_r2, raw_dp, raw_d = decode_raw(out[4]), decode_raw(out[5]), decode_raw(out[8])
+            assert float(res["d"][i]).hex() == float(raw_d).hex()
+            if not isinstance(raw_dp, int):
+                assert float(res["dprime"][i]).hex() == raw_dp.hex()
+            if not isinstance(raw_r2, int):
+                assert abs(res["r2"][i] - raw_r2) <= TOL
+        st.close()
+
+
+def test_pairs_with_mask_and_subset_store(ctx):
+    from ld_tools_b200 import Store
+    rng = np.random.default_rng(21)
+    n_hap = 5008
+    h = (rng.random((300, n_hap)) < rng.beta(0.3, 1.5, size=(300, 1))).astype(np.uint8)
+    h[10] = 0; h[11] = 1; h[12] = h[13]          # monomorphic rows, identical rows
+    planes = ld_oracle.pack_bits(h)
+    st = Store.from_planes(ctx, planes, n_hap)
+    sel = np.sort(rng.choice(n_hap, size=1006, replace=False))
+    mask = ld_oracle.mask_from_haplotypes(sel, n_hap)
+    st.set_mask(mask)
+    n1, p_e4, n_sel = st.counts()
+    assert n_sel == 1006
+    assert (n1 == ld_oracle.variant_counts(planes, mask, n_hap)).all()
+    ia = rng.integers(0, 300, size=4000); ib = rng.integers(0, 300, size=4000)
+    ia[:4], ib[:4] = [10, 11, 12, 10], [5, 5, 13, 11]
+    got = st.pairs(ia, ib)
+    want = ld_oracle.pairs(planes, mask, n_hap, ia, ib)
+    assert (got["n11"] == want["n_11"]).all()
+    assert (got["packed"] == ld_oracle.packed_of(want)).all()
+    assert (got["d"] == want["d"]).all()                       # bit-exact
+    assert (got["dprime"] == want["dprime"]).all()             # bit-exact
+    assert np.abs(got["r2"] - want["r2"]).max() <= TOL
+    # the same answers from a store that physically holds only the selected columns
+    sub = st.subset(sel)
+    assert sub.n_hap == 1006 and sub.stride_words == 16
+    assert (ld_oracle.unpack_bits(sub.download(), 1006) == h[:, sel]).all()
+    got2 = sub.pairs(ia, ib)
+    for k in ("n11", "packed", "d", "dprime", "r2"):
+        assert (got2[k] == got[k]).all(), k
+    sub.close(); st.close()
+
+
+def test_empty_mask_raises_like_reference(ctx):
+    from ld_tools_b200 import Store
+    st = Store(ctx, 4, 130)
+    with pytest.raises(ZeroDivisionError):
+        st.set_mask(np.zeros(st.stride_words, dtype="<u8"))
+    st.close()
+
+
+# ------------------------------------------------------------------ K1: GT text packing
+
+def test_pack_gt_text_matches_oracle(ctx):
+    from ld_tools_b200 import Store
+    from ld_tools_b200.synth import gt_row_text
+    rng = np.random.default_rng(5)
+    for n_samples in (1, 37, 503, 2504):
+        n_var = 23
+        gt = (rng.random((n_var, 2 * n_samples)) < 0.3).astype(np.uint8)
+        text, offs = b"", []
+        for v in range(n_var):
+            prefix = f"22\t{100 + v}\trs{v}\tA\tG\t100\tPASS\tAC=1;VT=SNP{'x' * (v % 7)}\tGT\t".encode()
+            offs.append(len(text) + len(prefix))
+            text += prefix + gt_row_text(gt[v]) + b"\n"
+        buf = np.frombuffer(text, dtype=np.uint8).copy()
+        buf[offs[2] + 4 * (n_samples // 2)] = ord(".")             # missing allele
+        buf[offs[4] + 4 * (n_samples - 1) + 1] = ord("/")          # unphased last sample
+        want_planes, want_status = ld_oracle.pack_gt(buf, np.array(offs), n_samples)
+        st = Store(ctx, n_var, 2 * n_samples)
+        status = st.pack_gt(0, buf, n_samples, row_off=offs)
+        assert status.tolist() == want_status.tolist()
+        assert (st.download() == want_planes).all()
+        st.close()
+
+
+# ------------------------------------------------------------------ K5': all pairs (popcount engine)
+
+def make_store(ctx, n_var, n_hap, seed, sel_frac=None):
+    from ld_tools_b200 import Store
+    from ld_tools_b200.synth import synth_haplotypes
+    h = synth_haplotypes(n_var, n_hap, seed=seed)
+    planes = ld_oracle.pack_bits(h)
+    st = Store.from_planes(ctx, planes, n_hap)
+    rng = np.random.default_rng(seed)
+    sel = np.arange(n_hap) if sel_frac is None else np.sort(rng.choice(n_hap, int(n_hap * sel_frac), replace=False))
+    mask = ld_oracle.mask_from_haplotypes(sel, n_hap)
+    st.set_mask(mask)
+    return st, planes, mask
+
+
+@pytest.mark.parametrize("n_var,n_hap,sel_frac", [(2, 5008, None), (65, 5008, None), (200, 5008, 0.2),
+                                                  (131, 198, None), (150, 6000, None)])
+def test_triangle_matches_oracle(ctx, n_var, n_hap, sel_frac):
+    from ld_tools_b200.engine import ENGINE_POPC
+    st, planes, mask = make_store(ctx, max(n_var, 8), n_hap, seed=100 + n_var, sel_frac=sel_frac)
+    rng = np.random.default_rng(n_var)
+    rows = rng.permutation(max(n_var, 8))[:n_var]          # arbitrary matrix order
+    packed, n11 = st.triangle(rows, engine=ENGINE_POPC, want_n11=True)
+    want = ld_oracle.triangle(planes, mask, n_hap, rows)
+    assert (n11 == want["n_11"]).all()
+    assert (packed == ld_oracle.packed_of(want)).all()
+    # orientation: var_1 = row variant (ld_triangle.py:193) -- spot check through the list-level port
+    bits = ld_oracle.unpack_bits(planes & mask[None, :], n_hap)
+    selcols = np.flatnonzero(ld_oracle.unpack_bits(mask[None, :], n_hap)[0])
+    from ld_tools_b200.engine import dprime_value, r2_value, tri_index
+    for r, c in [(1, 0), (n_var - 1, 0), (n_var - 1, n_var - 2)]:
+        if r <= c:
+            continue
+        ref = calc_ld_port.calc_ld(list(map(int, bits[rows[r], selcols])), list(map(int, bits[rows[c], selcols])))
+        w = packed[tri_index(r, c)]
+        assert same_obj(r2_value(w), ref["r_square"]) and same_obj(dprime_value(w), ref["d_prime"])
+    st.close()
+
+
+def test_triangle_threshold_flag(ctx):
+    from ld_tools_b200.engine import BELOW_THRES, ENGINE_POPC, dprime_e4, r2_e4, threshold_e4
+    st, planes, mask = make_store(ctx, 180, 1006, seed=9)
+    rows = np.arange(180)
+    for measure, getter in (("r_square", r2_e4), ("d_prime", dprime_e4)):
+        t = threshold_e4(0.8)
+        packed, _ = st.triangle(rows, measure=measure, thres_e4_=t, engine=ENGINE_POPC)
+        base, _ = st.triangle(rows, measure=measure, engine=ENGINE_POPC)
+        assert ((packed & ~np.uint32(BELOW_THRES)) == base).all()
+        assert (((packed & BELOW_THRES) != 0) == (getter(base) < t)).all()
+    st.close()
+
+
+def test_triangle_full_size_properties(ctx):
+    """BASELINE config 2 shape: 2,000 variants x 5008 haplotypes = 1,999,000 pairs."""
+    from ld_tools_b200.engine import ENGINE_POPC
+    st, planes, mask = make_store(ctx, 2000, 5008, seed=2)
+    rows = np.arange(2000)
+    packed, n11 = st.triangle(rows, engine=ENGINE_POPC, want_n11=True)
+    bits = ld_oracle.unpack_bits(planes, 5008).astype(np.float32)
+    gram = (bits @ bits.T).astype(np.int64)                # exact: counts < 2^24
+    r, c = np.tril_indices(2000, -1)
+    assert (n11 == gram[r, c]).all()
+    n1 = np.diag(gram)
+    want = ld_oracle.packed_words(5008, n11, n1[r], n1[c])
+    assert (packed == want).all()
+    st.close()
+
+
+# ------------------------------------------------------------------ K4: ld_area window scan
+
+def annotated_store(ctx, n_var, n_hap, seed):
+    from ld_tools_b200.synth import make_records
+    st, planes, mask = make_store(ctx, n_var, n_hap, seed=seed, sel_frac=0.3)
+    recs = make_records(n_var, seed=seed, mean_gap=40)
+    pos0 = np.array([r["pos"] - 1 for r in recs], dtype=np.int32)
+    end0 = pos0 + np.array([len(r["ref"]) for r in recs], dtype=np.int32)
+    import re
+    elig = np.array([bool(re.match(r"rs\d+$", r["id"])) and not r["multi"] for r in recs], dtype=np.uint8)
+    idnum = np.array([int(r["id"][2:]) if re.match(r"rs\d+$", r["id"]) else -1 - i for i, r in enumerate(recs)],
+                     dtype=np.int64)
+    st.set_annotations(pos0, end0, idnum, elig)
+    return st, planes, mask, pos0, end0, idnum, elig
+
+
+@pytest.mark.parametrize("measure,thres", [("r_square", 0.8), ("d_prime", 0.95), ("r_square", 0.0), ("r_square", 0.05)])
+def test_window_matches_oracle_full_scan(ctx, measure, thres):
+    from ld_tools_b200.engine import threshold_e4
+    n_var, n_hap = 3000, 5008
+    st, planes, mask, pos0, end0, idnum, elig = annotated_store(ctx, n_var, n_hap, seed=33)
+    rng = np.random.default_rng(1)
+    q_rows = np.concatenate([[0, 1, n_var - 1], rng.choice(np.flatnonzero(elig), 37, replace=False)])
+    flank = 5000
+    pos = pos0 + 1
+    low = np.maximum(pos[q_rows] - flank, 0)                # ld_area.py:174-176
+    high = pos[q_rows] + flank                              # ld_area.py:177
+    # candidate superset from the position index, with slack for long REF alleles on the left
+    max_len = int((end0 - pos0).max())
+    lo = np.searchsorted(pos0, low - max_len, side="left")
+    hi = np.searchsorted(pos0, high, side="left")
+    hits, scanned = st.window(q_rows, lo, hi, low, high, measure, threshold_e4(thres))
+    mcode = 0 if measure == "r_square" else 1
+    total = 0
+    for k, q in enumerate(q_rows):
+        rows, res = ld_oracle.window(planes, mask, n_hap, pos0, end0, idnum, elig, q, low[k], high[k], mcode, thres)
+        mine = hits[hits["query"] == k]
+        assert mine["row"].tolist() == rows.tolist(), (k, q)
+        assert (mine["n11"] == res["n_11"]).all()
+        assert (mine["packed"] == ld_oracle.packed_of(res)).all()
+        total += len(rows)
+    assert len(hits) == total
+    if thres == 0.0:
+        assert scanned == len(hits)                         # everything scanned is kept at threshold 0
+    st.close()
+
+
+def test_window_edge_cases(ctx):
+    from ld_tools_b200.engine import threshold_e4
+    st, planes, mask, pos0, end0, idnum, elig = annotated_store(ctx, 600, 198, seed=44)
+    # no queries
+    hits, scanned = st.window([], [], [], [], [], "r_square", 0)
+    assert len(hits) == 0 and scanned == 0
+    # empty candidate range and a window that contains only the query itself
+    hits, _ = st.window([5, 7], [5, 7], [5, 8], [pos0[5], pos0[7]], [pos0[5] + 1, pos0[7] + 1], "r_square", 0)
+    assert len(hits) == 0
+    # capacity retry path: tiny cap forces LDX_ERR_CAPACITY then a second call
+    q = int(np.flatnonzero(elig)[10])
+    hits, _ = st.window([q], [0], [600], [0], [int(end0.max()) + 1], "r_square", 0, cap=3)
+    rows, _ = ld_oracle.window(planes, mask, 198, pos0, end0, idnum, elig, q, 0, int(end0.max()) + 1, 0, 0.0)
+    assert hits["row"].tolist() == rows.tolist() and len(rows) > 3
+    st.close()

@@ -201,7 +201,8 @@ def run_ours(args, rank, world, local_rank):
     mask_np[N_HAP // 64] = np.uint64((1 << (N_HAP % 64)) - 1)
 
     ctx = Context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)       # kernels, copies and timing events all on this stream
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     store = Store.from_planes(ctx, planes_np, N_HAP)
     store.set_mask(mask_np)

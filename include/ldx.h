@@ -89,8 +89,10 @@ int32_t ldx_device_count(int32_t *n_out);
 int32_t ldx_init(int32_t device, ldx_ctx **ctx_out);
 int32_t ldx_destroy(ldx_ctx *ctx);
 /* Launch on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream) instead of
- * the ctx's own; NULL restores the ctx stream. */
+ * the ctx's own.  The handle is used as given: NULL is CUDA's legacy default stream.
+ * ldx_use_own_stream() goes back to the ctx's private non-blocking stream. */
 int32_t ldx_set_stream(ldx_ctx *ctx, void *cuda_stream);
+int32_t ldx_use_own_stream(ldx_ctx *ctx);
 int32_t ldx_synchronize(ldx_ctx *ctx);
 int32_t ldx_sm_count(ldx_ctx *ctx, int32_t *n_out);
 /* Kernels launched by this ctx since creation (bench.py's gpu_launches claim). */

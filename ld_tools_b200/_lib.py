@@ -39,6 +39,7 @@ SIGNATURES = {
     "ldx_init": [_i32, _P(_vp)],
     "ldx_destroy": [_vp],
     "ldx_set_stream": [_vp, _vp],
+    "ldx_use_own_stream": [_vp],
     "ldx_synchronize": [_vp],
     "ldx_sm_count": [_vp, _P(_i32)],
     "ldx_launch_count": [_vp, _P(_i64)],

@@ -93,7 +93,7 @@ extern "C" int32_t ldx_init(int32_t device, ldx_ctx **ctx_out) {
 extern "C" int32_t ldx_destroy(ldx_ctx *ctx) {
     if (!ctx) return LDX_OK;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
     if (Arena *a = arena_of(ctx)) {
         for (int i = 0; i < Arena::SLOTS; ++i) if (a->ptr[i]) cudaFree(a->ptr[i]);
         delete a;
@@ -109,7 +109,13 @@ extern "C" int32_t ldx_destroy(ldx_ctx *ctx) {
 
 extern "C" int32_t ldx_set_stream(ldx_ctx *ctx, void *cuda_stream) {
     LDX_REQUIRE(ctx, "ctx is NULL");
-    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_use_own_stream(ldx_ctx *ctx) {
+    LDX_REQUIRE(ctx, "ctx is NULL");
+    ctx->stream = ctx->own_stream;
     return LDX_OK;
 }
 

@@ -80,7 +80,11 @@ class Context:
     __del__ = close
 
     def set_stream(self, cuda_stream):
+        """Launch on the given cudaStream_t handle (0 = CUDA's legacy default stream)."""
         check(self._lib.ldx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def use_own_stream(self):
+        check(self._lib.ldx_use_own_stream(self._h))
 
     def synchronize(self):
         check(self._lib.ldx_synchronize(self._h))

@@ -114,7 +114,7 @@ def test_pairs_match_reference_golden_counts(golden, ctx):
             word = res["packed"][i]
             assert repr(r2_value(word)) == out[0], (n, n11, a, b, r2_value(word), out[0])
             assert repr(dprime_value(word)) == out[1], (n, n11, a, b)
-            assert repr(p_e4[2 * i] / 10000.0) == out[2] and repr(p_e4[2 * i + 1] / 10000.0) == out[3]
+            assert repr(int(p_e4[2 * i]) / 10000.0) == out[2] and repr(int(p_e4[2 * i + 1]) / 10000.0) == out[3]
             raw_r2, raw_dp, raw_d = decode_raw(out[4]), decode_raw(out[5]), decode_raw(out[8])
             assert float(res["d"][i]).hex() == float(raw_d).hex()
             if not isinstance(raw_dp, int):

@@ -119,6 +119,22 @@ extern "C" int32_t ldx_use_own_stream(ldx_ctx *ctx) {
     return LDX_OK;
 }
 
+extern "C" int32_t ldx_set_tuning(ldx_ctx *ctx, int32_t key, int32_t value) {
+    LDX_REQUIRE(ctx, "ctx is NULL");
+    switch (key) {
+        case LDX_TUNE_MMA_TILE_N:
+            LDX_REQUIRE(value == 0 || value == 64 || value == 128 || value == 256, "tile width must be 0, 64, 128 or 256");
+            ctx->mma_tile_n = value;
+            return LDX_OK;
+        case LDX_TUNE_MMA_MIN_V:
+            LDX_REQUIRE(value >= 2, "minimum variant count must be >= 2");
+            ctx->mma_min_v = value;
+            return LDX_OK;
+        default:
+            return set_error(LDX_ERR_ARG, "unknown tuning key");
+    }
+}
+
 extern "C" int32_t ldx_synchronize(ldx_ctx *ctx) {
     LDX_REQUIRE(ctx, "ctx is NULL");
     LDX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -184,8 +200,13 @@ static inline int32_t word_measure(uint32_t w, int measure) {
 // Fetch (and clear) the device fix-up list.  Synchronises the stream.
 static int collect_fixups(ldx_ctx *ctx, std::vector<FixupRec> &recs) {
     recs.clear();
-    LDX_CUDA(cudaMemcpyAsync(ctx->h_fix_count, ctx->d_fix_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    // [0] = near-tie records appended, [1] = tcgen05 pipeline error flag
+    LDX_CUDA(cudaMemcpyAsync(ctx->h_fix_count, ctx->d_fix_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     LDX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_fix_count[1]) {
+        cudaMemsetAsync(ctx->d_fix_count, 0, 2 * sizeof(uint32_t), ctx->stream);
+        return set_error(LDX_ERR_CUDA, "tcgen05 pipeline timed out (mbarrier wait exceeded 2 s); results are invalid");
+    }
     const uint32_t n = ctx->h_fix_count[0];
     if (n == 0) return LDX_OK;
     if (n > ctx->fix_capacity) {
@@ -616,7 +637,7 @@ extern "C" int32_t ldx_triangle_dev(ldx_store *s, const int64_t *rows, int64_t v
     ldx_ctx *ctx = s->ctx;
     if (engine == LDX_ENGINE_MMA && !triangle_mma_available())
         return set_error(LDX_ERR_ARG, "the tcgen05 engine is not available in this build");
-    const bool use_mma = engine == LDX_ENGINE_MMA || (engine == LDX_ENGINE_AUTO && triangle_mma_available() && v >= 256);
+    const bool use_mma = engine == LDX_ENGINE_MMA || (engine == LDX_ENGINE_AUTO && triangle_mma_available() && v >= ctx->mma_min_v);
     // rows[] staging is consumed by the kernel on the same stream; the caller's array may be
     // freed after return, so wait for the H2D copy (tiny) before returning.
     int rc = use_mma ? launch_triangle_mma(s, d_rows, v, measure, has_thres, thres_e4, dev_packed, dev_n11)

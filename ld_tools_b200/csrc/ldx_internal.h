@@ -33,7 +33,8 @@ struct ldx_ctx {
     // MMA-path scratch (expanded operand panels), grown on demand
     void *d_mma_ops = nullptr;
     size_t mma_ops_bytes = 0;
-    std::vector<int> mma_checked;         // lazily filled: tcgen05 path self-test verdicts
+    int mma_tile_n = 0;                   // tcgen05 tile width override (0 = heuristic)
+    int mma_min_v = 256;                  // ENGINE_AUTO uses the tcgen05 engine from this many variants
 };
 
 struct ldx_store {

@@ -89,6 +89,9 @@ class Context:
     def synchronize(self):
         check(self._lib.ldx_synchronize(self._h))
 
+    def set_tuning(self, key, value):
+        check(self._lib.ldx_set_tuning(self._h, int(key), int(value)))
+
     @property
     def sm_count(self):
         n = C.c_int32()

@@ -320,3 +320,47 @@ def test_window_edge_cases(ctx):
     rows, _ = ld_oracle.window(planes, mask, 198, pos0, end0, idnum, elig, q, 0, int(end0.max()) + 1, 0, 0.0)
     assert hits["row"].tolist() == rows.tolist() and len(rows) > 3
     st.close()
+
+
+# ------------------------------------------------------------------ K5: tcgen05 int8 Gram engine
+
+@pytest.mark.parametrize("tile_n", [64, 128, 256])
+@pytest.mark.parametrize("n_var,n_hap,sel_frac", [(2, 5008, None), (129, 5008, None), (700, 5008, 0.2),
+                                                  (300, 198, None), (513, 6000, None)])
+def test_triangle_mma_bit_exact_vs_popcount_and_oracle(ctx, tile_n, n_var, n_hap, sel_frac):
+    """The tensor-core engine must reproduce the popcount engine's counts and words bit for bit."""
+    from ld_tools_b200._lib import TUNE_MMA_TILE_N
+    from ld_tools_b200.engine import ENGINE_MMA, ENGINE_POPC
+    st, planes, mask = make_store(ctx, max(n_var, 8), n_hap, seed=300 + n_var, sel_frac=sel_frac)
+    rng = np.random.default_rng(n_var)
+    rows = rng.permutation(max(n_var, 8))[:n_var]
+    ctx.set_tuning(TUNE_MMA_TILE_N, tile_n)
+    try:
+        packed, n11 = st.triangle(rows, engine=ENGINE_MMA, want_n11=True)
+    finally:
+        ctx.set_tuning(TUNE_MMA_TILE_N, 0)
+    ref_packed, ref_n11 = st.triangle(rows, engine=ENGINE_POPC, want_n11=True)
+    assert (n11 == ref_n11).all()
+    assert (packed == ref_packed).all()
+    if n_var <= 300:
+        want = ld_oracle.triangle(planes, mask, n_hap, rows)
+        assert (n11 == want["n_11"]).all() and (packed == ld_oracle.packed_of(want)).all()
+    st.close()
+
+
+def test_triangle_mma_full_size_and_threshold(ctx):
+    from ld_tools_b200.engine import BELOW_THRES, ENGINE_MMA, r2_e4, threshold_e4
+    st, planes, mask = make_store(ctx, 2000, 5008, seed=2)
+    rows = np.arange(2000)
+    packed, n11 = st.triangle(rows, engine=ENGINE_MMA, want_n11=True)
+    bits = ld_oracle.unpack_bits(planes, 5008).astype(np.float32)
+    gram = (bits @ bits.T).astype(np.int64)
+    r, c = np.tril_indices(2000, -1)
+    assert (n11 == gram[r, c]).all()
+    n1 = np.diag(gram)
+    assert (packed == ld_oracle.packed_words(5008, n11, n1[r], n1[c])).all()
+    t = threshold_e4(0.8)
+    flagged, _ = st.triangle(rows, measure="r_square", thres_e4_=t, engine=ENGINE_MMA)
+    assert ((flagged & ~np.uint32(BELOW_THRES)) == packed).all()
+    assert (((flagged & BELOW_THRES) != 0) == (r2_e4(packed) < t)).all()
+    st.close()

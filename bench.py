@@ -204,6 +204,9 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.Stream(device=dev)       # kernels, copies and timing events all on this stream
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
+    if args.tile_n:
+        from ld_tools_b200._lib import TUNE_MMA_TILE_N
+        ctx.set_tuning(TUNE_MMA_TILE_N, args.tile_n)
     store = Store.from_planes(ctx, planes_np, N_HAP)
     store.set_mask(mask_np)
     d_packed = torch.empty(n_pairs, dtype=torch.int32, device=dev)
@@ -280,7 +283,7 @@ def run_ours(args, rank, world, local_rank):
     # parity spot-check of what was just timed (device-resident result vs host-API result)
     same = bool((d_packed.cpu().numpy().view(np.uint32) == out_host).all())
 
-    used_mma = engine == ENGINE_MMA or (engine == ENGINE_AUTO and os.environ.get("LDX_BENCH_ENGINE_USED") == "mma")
+    used_mma = engine in (ENGINE_MMA, ENGINE_AUTO)      # AUTO picks tcgen05 from 256 variants up
     if used_mma:
         peak = 2.0 * peaks["bf16_tflops"]      # dense int8 = 2 x dense bf16 on sm_100a
         roof = {"bound": "tensor", "achieved": n_pairs * OPS_PER_PAIR_I8 / kern_s / 1e12, "peak": peak,
@@ -320,6 +323,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--engine", choices=["auto", "popc", "mma"], default="auto")
+    ap.add_argument("--tile-n", type=int, default=0, help="tcgen05 tile width override (0 = heuristic)")
     ap.add_argument("--cpu-pairs-per-core", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -111,6 +111,13 @@ int32_t ldx_launch_count(ldx_ctx *ctx, int64_t *n_out);
 int32_t ldx_calc_ld_lists(ldx_ctx *ctx, const uint8_t *g_a, int64_t len_a, const uint8_t *g_b,
                           int64_t len_b, ldx_ld_result *out);
 
+/* calc_ld.py:33-97 alone, for n pairs given as integer counts under n_hap haplotypes:
+ * n11 = (alt, alt) haplotypes, n1a / n1b = alt alleles of var_1 / var_2 (ref = n_hap - alt).
+ * Outputs are host arrays of n (each may be NULL): D, D', r2 before rounding and the packed word. */
+int32_t ldx_finalise_counts(ldx_ctx *ctx, int32_t n_hap, const int32_t *n11, const int32_t *n1a,
+                            const int32_t *n1b, int64_t n, double *d, double *dprime, double *r2,
+                            uint32_t *packed);
+
 /* ---------------------------------------------------------------- the bit-plane store
  * Replaces the per-pair pysam genotype extraction (ld_lite.py:109-137, ld_area.py:182-187 and
  * :230-235, ld_triangle.py:158-186) and the prep_intgen_data/create_src_dict cache as the

@@ -46,6 +46,7 @@ SIGNATURES = {
     "ldx_sm_count": [_vp, _P(_i32)],
     "ldx_launch_count": [_vp, _P(_i64)],
     "ldx_calc_ld_lists": [_vp, _vp, _i64, _vp, _i64, _vp],
+    "ldx_finalise_counts": [_vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "ldx_store_create": [_vp, _i64, _i32, _P(_vp)],
     "ldx_store_destroy": [_vp],
     "ldx_store_shape": [_vp, _P(_i64), _P(_i32), _P(_i32)],

@@ -255,6 +255,60 @@ extern "C" int32_t ldx_calc_ld_lists(ldx_ctx *ctx, const uint8_t *g_a, int64_t l
     return LDX_OK;
 }
 
+// ------------------------------------------------------------------------------------------ counts
+static int make_final_ctx(int64_t n_sel, FinalCtx *fc) {
+    fc->n_hap = (double)n_sel;
+    fc->rcp_n = 1.0 / (double)n_sel;
+    // prove the two-FMA quotient equals the IEEE quotient for every count that can occur
+    fc->exact_div = 1;
+    for (int64_t n = 0; n <= n_sel; ++n) {
+        const double x = (double)n, q0 = x * fc->rcp_n;
+        const double r = std::fma(-q0, fc->n_hap, x);
+        if (std::fma(r, fc->rcp_n, q0) != x / fc->n_hap) { fc->exact_div = 0; break; }
+    }
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_finalise_counts(ldx_ctx *ctx, int32_t n_hap, const int32_t *n11, const int32_t *n1a,
+                                       const int32_t *n1b, int64_t n, double *d, double *dprime, double *r2,
+                                       uint32_t *packed) {
+    LDX_REQUIRE(ctx, "ctx is NULL");
+    LDX_REQUIRE(n >= 0 && (n == 0 || (n11 && n1a && n1b)), "bad count arrays");
+    LDX_REQUIRE(n_hap <= (1 << 24), "n_hap out of range");
+    if (n_hap <= 0) return set_error(LDX_ERR_EMPTY, "division by zero");
+    for (int64_t k = 0; k < n; ++k)
+        LDX_REQUIRE(n1a[k] >= 0 && n1a[k] <= n_hap && n1b[k] >= 0 && n1b[k] <= n_hap && n11[k] >= 0 &&
+                    n11[k] <= n1a[k] && n11[k] <= n1b[k] && n1a[k] + n1b[k] - n11[k] <= n_hap, "inconsistent counts");
+    if (n == 0) return LDX_OK;
+    LDX_CUDA(cudaSetDevice(ctx->device));
+    FinalCtx fc;
+    make_final_ctx(n_hap, &fc);
+    int32_t *d_in; double *d_d = nullptr, *d_dp = nullptr, *d_r2 = nullptr; uint32_t *d_pk;
+    LDX_TRY(arena_get(ctx, S_IA, sizeof(int32_t) * 3 * (size_t)n, (void **)&d_in));
+    if (d) LDX_TRY(arena_get(ctx, S_D, sizeof(double) * (size_t)n, (void **)&d_d));
+    if (dprime) LDX_TRY(arena_get(ctx, S_DP, sizeof(double) * (size_t)n, (void **)&d_dp));
+    if (r2) LDX_TRY(arena_get(ctx, S_R2, sizeof(double) * (size_t)n, (void **)&d_r2));
+    LDX_TRY(arena_get(ctx, S_PACKED, sizeof(uint32_t) * (size_t)n, (void **)&d_pk));
+    cudaStream_t st = ctx->stream;
+    LDX_CUDA(cudaMemcpyAsync(d_in, n11, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    LDX_CUDA(cudaMemcpyAsync(d_in + n, n1a, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    LDX_CUDA(cudaMemcpyAsync(d_in + 2 * n, n1b, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    LDX_TRY(launch_finalise_counts(ctx, fc, d_in, d_in + n, d_in + 2 * n, n, d_d, d_dp, d_r2, d_pk));
+    if (d) LDX_CUDA(cudaMemcpyAsync(d, d_d, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (dprime) LDX_CUDA(cudaMemcpyAsync(dprime, d_dp, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (r2) LDX_CUDA(cudaMemcpyAsync(r2, d_r2, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (packed) LDX_CUDA(cudaMemcpyAsync(packed, d_pk, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    std::vector<FixupRec> recs;
+    LDX_TRY(collect_fixups(ctx, recs));   // synchronises
+    for (const FixupRec &r : recs) {
+        double r2_exact;
+        const uint32_t w = host_finalise_packed(fc.n_hap, r.n11, r.n1a, r.n1b, &r2_exact);
+        if (packed) packed[r.out_index] = w;
+        if (r2) r2[r.out_index] = r2_exact;
+    }
+    return LDX_OK;
+}
+
 // ------------------------------------------------------------------------------------------ store
 extern "C" int32_t ldx_store_create(ldx_ctx *ctx, int64_t n_variants, int32_t n_hap, ldx_store **store_out) {
     LDX_REQUIRE(ctx && store_out, "NULL argument");
@@ -376,15 +430,7 @@ extern "C" int32_t ldx_store_set_mask(ldx_store *s, const uint64_t *mask) {
     if (n_sel == 0) return set_error(LDX_ERR_EMPTY, "division by zero");   // empty sample selection, calc_ld.py:33
     LDX_CUDA(cudaSetDevice(s->ctx->device));
     s->n_sel = (int32_t)n_sel;
-    s->fc.n_hap = (double)n_sel;
-    s->fc.rcp_n = 1.0 / (double)n_sel;
-    // prove the two-FMA quotient equals the IEEE quotient for every count that can occur
-    s->fc.exact_div = 1;
-    for (int64_t n = 0; n <= n_sel; ++n) {
-        const double x = (double)n, q0 = x * s->fc.rcp_n;
-        const double r = std::fma(-q0, s->fc.n_hap, x);
-        if (std::fma(r, s->fc.rcp_n, q0) != x / s->fc.n_hap) { s->fc.exact_div = 0; break; }
-    }
+    make_final_ctx(n_sel, &s->fc);
     LDX_CUDA(cudaMemcpyAsync(s->d_mask, m.data(), sizeof(uint64_t) * s->stride_words, cudaMemcpyHostToDevice, s->ctx->stream));
     LDX_CUDA(cudaStreamSynchronize(s->ctx->stream));   // m goes out of scope
     LDX_TRY(launch_variant_freq(s));

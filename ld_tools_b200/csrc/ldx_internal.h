@@ -34,6 +34,8 @@ struct ldx_ctx {
     void *d_mma_ops = nullptr;
     size_t mma_ops_bytes = 0;
     int mma_tile_n = 0;                   // tcgen05 tile width override (0 = heuristic)
+    int64_t mma_tiles_v = -1;             // tile list cached in d_mma_ops: built for this (v, N)
+    int mma_tiles_n = 0;
     int mma_min_v = 256;                  // ENGINE_AUTO uses the tcgen05 engine from this many variants
 };
 
@@ -75,6 +77,8 @@ int launch_variant_freq(ldx_store *s);
 int launch_subset(const ldx_store *src, const int32_t *d_sel, ldx_store *dst);
 int launch_pairs(ldx_store *s, const int64_t *d_ia, const int64_t *d_ib, int64_t n, int32_t *d_n11,
                  double *d_d, double *d_dp, double *d_r2, uint32_t *d_packed);
+int launch_finalise_counts(ldx_ctx *ctx, const ldx::FinalCtx &fc, const int32_t *d_n11, const int32_t *d_n1a,
+                           const int32_t *d_n1b, int64_t n, double *d_d, double *d_dp, double *d_r2, uint32_t *d_packed);
 int launch_lists(ldx_ctx *ctx, const uint8_t *d_ga, int64_t len_a, const uint8_t *d_gb, int64_t len_b,
                  ldx_ld_result *d_out);
 int launch_window(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, const int64_t *d_hi,

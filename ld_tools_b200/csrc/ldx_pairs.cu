@@ -67,6 +67,46 @@ int launch_pairs(ldx_store *s, const int64_t *d_ia, const int64_t *d_ib, int64_t
 }
 
 // ------------------------------------------------------------------------------------------
+// calc_ld.py:33-97 for arrays of integer counts (n11, n1 of var_1, n1 of var_2) under a given N:
+// the finalisation alone, for callers that already hold counts, and the direct test hook for the
+// fp64 path (tests compare millions of count triples with the reference arithmetic).
+__global__ void __launch_bounds__(256)
+finalise_counts_kernel(FinalCtx fc, const int32_t *__restrict__ n11, const int32_t *__restrict__ n1a,
+                       const int32_t *__restrict__ n1b, int64_t n, double *__restrict__ o_d, double *__restrict__ o_dp,
+                       double *__restrict__ o_r2, uint32_t *__restrict__ o_packed, FixupSink fix) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        VarFreq fa, fb;
+        bool tie;
+        fa.n1 = n1a[k]; fb.n1 = n1b[k];
+        fa.p = __ddiv_rn((double)fa.n1, fc.n_hap); fa.q = __ddiv_rn((double)((int)fc.n_hap - fa.n1), fc.n_hap);
+        fb.p = __ddiv_rn((double)fb.n1, fc.n_hap); fb.q = __ddiv_rn((double)((int)fc.n_hap - fb.n1), fc.n_hap);
+        fa.pq = __dmul_rn(fa.p, fa.q); fb.pq = __dmul_rn(fb.p, fb.q);
+        fa.p_e4 = (int32_t)round4_e4(fa.p, tie); fb.p_e4 = (int32_t)round4_e4(fb.p, tie);
+        const PairFinal f = finalise_pair(n11[k], fa, fb, fc);
+        if (o_d) o_d[k] = f.d;
+        if (o_dp) o_dp[k] = f.dprime;
+        if (o_r2) o_r2[k] = f.r2;
+        if (o_packed) {
+            o_packed[k] = f.packed;
+            if (f.packed & LDX_R2_NEARTIE) fixup_append(fix, (uint64_t)k, n11[k], fa.n1, fb.n1, f.packed);
+        }
+    }
+}
+
+int launch_finalise_counts(ldx_ctx *ctx, const FinalCtx &fc, const int32_t *d_n11, const int32_t *d_n1a,
+                           const int32_t *d_n1b, int64_t n, double *d_d, double *d_dp, double *d_r2, uint32_t *d_packed) {
+    if (n <= 0) return LDX_OK;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    finalise_counts_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(fc, d_n11, d_n1a, d_n1b, n, d_d, d_dp, d_r2, d_packed,
+                                                                  FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity});
+    ctx->launches++;
+    LDX_CUDA(cudaGetLastError());
+    return LDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // List-level calculator: one CTA counts over byte-coded genotypes, thread 0 finalises with the
 // general formula (explicit ref counts, so "other" alleles and unequal lengths behave exactly
 // like the reference's list.count() calls).
@@ -115,15 +155,15 @@ lists_kernel(const uint8_t *__restrict__ ga, int64_t len_a, const uint8_t *__res
     r.d = d; r.dprime = 0.0; r.r2 = 0.0; r.dprime_e4 = 0.0; r.r2_e4 = 0.0;
     r.dprime_is_int0 = 0; r.r2_is_int0 = 0;
     r.p_a = pa; r.p_b = pb;
-    r.p_a_e4 = round4_e4(pa, tie); r.p_b_e4 = round4_e4(pb, tie);       // :96-97
+    r.p_a_e4 = round4_e4_wide(pa, tie); r.p_b_e4 = round4_e4_wide(pb, tie);       // :96-97
     if (bound == 0.0) { r.dprime_is_int0 = 1; r.r2_is_int0 = 1; }       // :68-69, :89-90
     else {
         r.dprime = __ddiv_rn(d, bound);                                  // :67 / :74
-        r.dprime_e4 = round4_e4(r.dprime, tie);
+        r.dprime_e4 = round4_e4_wide(r.dprime, tie);
         if (r.dprime != 0.0) {
             const double den = __dmul_rn(__dmul_rn(__dmul_rn(pa, qa), pb), qb);   // :87-88
             r.r2 = __ddiv_rn(__dmul_rn(d, d), den);
-            r.r2_e4 = round4_e4(r.r2, tie);
+            r.r2_e4 = round4_e4_wide(r.r2, tie);
             if (tie) r.r2_is_int0 = 2;      // in-flight marker: host settles the tie with libm pow
         } else r.r2_is_int0 = 1;
     }

@@ -4,26 +4,35 @@
 //
 // Replaces the double loop at ld_triangle.py:133-230 (var_1 = row variant, var_2 = column
 // variant, ld_triangle.py:193); the counting step is calc_ld.py:30-32 for 128 x N pairs at once:
-//     n11[r][c] = sum_h  A[r][h] * A[c][h],   A[v][h] = (plane[v] & mask) bit h  in {0, 1}
-// Products of 0/1 bytes accumulated in int32 are exact, so the counts equal the popcount
-// engine's bit for bit (tests/test_parity_gpu.py compares them).
+//     n11[r][c] = sum_h  a[r][h] * a[c][h],   a[v][h] = (plane[v] & mask) bit h
+// Operand bytes are 0x00 / 0x80 (see expand_row), so every product is 0 or 2^14 and the int32
+// accumulator holds n11 * 2^14 exactly (n11 <= 2^17 haplotypes would still fit); the epilogue
+// shifts it back.  The counts equal the popcount engine's bit for bit (tests/test_parity_gpu.py).
 //
-// Pipeline of one CTA (= one 128 x N tile of the lower triangle, 10 warps):
-//   expand_kernel (separate launch, O(V)): bit planes -> 0/1 bytes, written to global memory
-//       ALREADY in the shared-memory image tcgen05 wants: [panel of 128 variants][128-haplotype
-//       chunk][row][128 B] with the 128-byte swizzle (16-byte unit j of row r stored at j ^ (r&7)).
-//       Every pipeline stage is then ONE contiguous 16 KB block per operand panel.
-//   warp 0   producer: cp.async.bulk (UBLKCP, the TMA engine's linear mode) global -> shared,
-//            completion counted on an mbarrier (complete_tx).  No tensor map needed.
-//   warp 1   MMA issuer: one elected lane issues 4 x tcgen05.mma (K = 32 each) per stage and
-//            tcgen05.commit's the stage back to the producer; owns the TMEM allocation.
-//   warps 2-9 epilogue: tcgen05.ld the int32 counts (lane = row, column = column variant),
-//            run calc_ld.py:33-97 in fp64 (ldx_common.cuh) and store packed results.
-// Several CTAs are resident per SM (N <= 128), so one tile's tensor work overlaps another tile's
-// fp64 epilogue without an intra-CTA software pipeline.
+// Data movement is designed around the L2: the operands stay BIT-PACKED in global memory/L2
+// (16 B per variant per 128-haplotype chunk, gathered once per call by gather_bits_kernel, O(V))
+// and are widened to bytes inside the SM.  Streaming pre-widened int8 panels from L2 was measured
+// first (profiles/r01_ncu_full_mma_v1_int8_from_l2_tile64.txt): 7.6 TB/s of L2->SM traffic with
+// both the tensor and the fp64 pipe under 14% busy.  Bit-packed operands cut that traffic 8x and
+// keep a 100k-variant operand set (64 MB) resident in the 126 MB L2.
+//
+// One CTA = one 128 x N tile of the lower triangle, 10 warps:
+//   warp 0     producer: cp.async.bulk (UBLKCP, the TMA engine's linear mode) brings the tile's
+//              bit blocks (2 KB per 128 variants per chunk) into an 8-deep shared-memory ring;
+//              completion is counted on mbarriers (complete_tx).
+//   warps 2-9  workers, phase 1: each thread widens one variant-row of the chunk (128 bits ->
+//              128 bytes) straight into the 128-byte-swizzled operand tile tcgen05 reads
+//              (LOP on the ALU pipe + IMAD on the FMA pipe, one 16-byte STS per 16 haplotypes),
+//              fence.proxy.async, mbarrier arrive.
+//   warp 1     MMA issuer: one elected lane issues 4 x tcgen05.mma (K = 32 each) per chunk and
+//              tcgen05.commit's the operand stage back to the workers; owns the TMEM allocation.
+//   warps 2-9  workers, phase 2 (epilogue): tcgen05.ld the int32 counts (lane = row variant,
+//              column = column variant), calc_ld.py:33-97 in fp64 (ldx_common.cuh), packed stores.
+// Two or three CTAs are resident per SM (N <= 128), so one tile's tensor work overlaps another
+// tile's fp64 epilogue without an intra-CTA software pipeline.
 //
 // Roofline: int8 tensor pipe, 2 * n_hap int8 ops per pair; co-bounds are the fp64 epilogue
-// (~45 fp64 instructions per pair) and L2 -> SM operand traffic ((128 + N) * 128 B per stage).
+// (~45 fp64 instructions per pair) and the widening ALU work ((128 + N) rows per 128 * N pairs).
 #include <vector>
 
 #include "ldx_internal.h"
@@ -103,42 +112,59 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
     return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// ------------------------------------------------------------------------------------------ expand
-// bit planes -> swizzled 0/1 byte panels.  One thread = one 16-byte unit (16 haplotypes of one
-// variant).  Four bits at a time: x * 0x00204081 puts bit i of the nibble at bit 8*i, & 0x01010101.
+// ------------------------------------------------------------------------------------------ gather
+// Store rows (gathered through rows[], masked) -> chunk-blocked bit panels:
+//   bits[panel][chunk][row 0..127][16 B],  panel = matrix_row / 128,  chunk = haplotype / 128
+// so that the 128 rows of one pipeline stage are ONE contiguous 2 KB block (one bulk copy).
 __global__ void __launch_bounds__(256)
-expand_kernel(const uint64_t *__restrict__ planes, const uint64_t *__restrict__ mask, int32_t stride_words,
-              const int64_t *__restrict__ rows, int64_t v, int64_t v_pad, int32_t kc_count,
-              const VarFreq *__restrict__ freq, uint8_t *__restrict__ ops, VarFreq *__restrict__ freq_rows) {
+gather_bits_kernel(const uint64_t *__restrict__ planes, const uint64_t *__restrict__ mask, int32_t stride_words,
+                   const int64_t *__restrict__ rows, int64_t v, int64_t v_pad, int32_t kc_count,
+                   const VarFreq *__restrict__ freq, uint4 *__restrict__ bits, VarFreq *__restrict__ freq_rows) {
     const int kc = blockIdx.y;
-    const int64_t r = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);   // matrix row
-    const int j = threadIdx.x & 7;                                      // 16-byte unit in the 128 B row
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;          // matrix row
     if (r >= v_pad) return;
-    uint32_t bits = 0;
+    uint4 out = make_uint4(0, 0, 0, 0);
     if (r < v) {
         const int64_t srow = rows[r];
-        const int h0 = kc * KCHUNK + j * 16;                            // first haplotype of this unit
-        const uint64_t w = planes[srow * stride_words + (h0 >> 6)] & mask[h0 >> 6];
-        bits = (uint32_t)(w >> (h0 & 63)) & 0xffffu;
-        if (kc == 0 && j == 0) freq_rows[r] = freq[srow];
-    } else if (kc == 0 && j == 0) {
+        const uint4 x = __ldg(reinterpret_cast<const uint4 *>(planes + srow * stride_words) + kc);
+        const uint4 m = __ldg(reinterpret_cast<const uint4 *>(mask) + kc);
+        out = make_uint4(x.x & m.x, x.y & m.y, x.z & m.z, x.w & m.w);
+        if (kc == 0) freq_rows[r] = freq[srow];
+    } else if (kc == 0) {
         VarFreq z; z.p = 0.0; z.q = 0.0; z.pq = 0.0; z.n1 = 0; z.p_e4 = 0;
         freq_rows[r] = z;
     }
-    uint4 out;
-    out.x = ((bits & 0xf) * 0x00204081u) & 0x01010101u;
-    out.y = (((bits >> 4) & 0xf) * 0x00204081u) & 0x01010101u;
-    out.z = (((bits >> 8) & 0xf) * 0x00204081u) & 0x01010101u;
-    out.w = (((bits >> 12) & 0xf) * 0x00204081u) & 0x01010101u;
-    const int64_t panel = r >> 7;
-    const int rl = (int)(r & 127);
-    uint8_t *dst = ops + (panel * kc_count + kc) * (int64_t)PANEL_BYTES + rl * KCHUNK + ((j ^ (rl & 7)) << 4);
-    *reinterpret_cast<uint4 *>(dst) = out;
+    bits[((r >> 7) * kc_count + kc) * 128 + (r & 127)] = out;
 }
+
+// ------------------------------------------------------------------------------------------ widen
+// 32 haplotype bits -> 32 operand bytes of value 0x00 / 0x80:  (w << s) & 0x80808080 for
+// s = 0..7 picks bits 7-s, 15-s, 23-s, 31-s.  The left shifts are IMADs (FMA pipe), the masks
+// LOPs (ALU pipe), so the two pipes share the work.  The haplotype ORDER inside a chunk is
+// permuted by this, identically for both operands -- a dot product does not care.
+__device__ __forceinline__ uint4 widen4(uint32_t w, int s0) {
+    uint4 o;
+    o.x = (w << s0) & 0x80808080u;
+    o.y = (w << (s0 + 1)) & 0x80808080u;
+    o.z = (w << (s0 + 2)) & 0x80808080u;
+    o.w = (w << (s0 + 3)) & 0x80808080u;
+    return o;
+}
+// One variant-row of a chunk: 128 bits -> 8 x 16-byte units at the 128B-swizzled positions
+// (unit j of row r lives at j ^ (r & 7)); a quarter-warp's STS.128 then covers all 32 banks.
+__device__ __forceinline__ void expand_row(uint8_t *row_base, int r7, const uint4 &b) {
+    const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        *reinterpret_cast<uint4 *>(row_base + (((2 * q) ^ r7) << 4)) = widen4(w[q], 0);
+        *reinterpret_cast<uint4 *>(row_base + (((2 * q + 1) ^ r7) << 4)) = widen4(w[q], 4);
+    }
+}
+constexpr int ACC_SHIFT = 14;   // 0x80 * 0x80 = 2^14 per (alt, alt) haplotype
 
 // ------------------------------------------------------------------------------------------ GEMM + epilogue
 struct MmaArgs {
-    const uint8_t *ops; int32_t kc_count;
+    const uint4 *bits; int32_t kc_count;
     const VarFreq *freq_rows; FinalCtx fc;
     const int2 *tiles;
     int64_t v; int measure, has_thres, thres_e4;
@@ -148,13 +174,22 @@ struct MmaArgs {
 };
 
 template <int N> struct MmaCfg {
-    static constexpr int STAGES = N == 64 ? 4 : (N == 128 ? 3 : 4);
-    static constexpr int B_BYTES = N * KCHUNK;
-    static constexpr int STAGE_BYTES = PANEL_BYTES + B_BYTES;
+    static constexpr int ROWS = MMA_M + N;                    // variant-rows widened per chunk
+    static constexpr int OP_STAGES = 2;                       // widened operand tiles (SM-local producer: shallow)
+    static constexpr int OP_BYTES = ROWS * KCHUNK;
+    static constexpr int BIT_STAGES = N <= 64 ? 6 : 8;        // bit blocks in flight from L2 (latency: deep)
+    static constexpr int BIT_BYTES = ROWS * 16;
     static constexpr int TMEM_COLS = N < 32 ? 32 : N;
-    static constexpr int CTAS_PER_SM = N <= 128 ? 2 : 1;
-    static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + N * sizeof(VarFreq) + 256;
+    static constexpr int CTAS_PER_SM = N <= 64 ? 3 : (N <= 128 ? 2 : 1);
+    static constexpr int N_BARS = 2 * OP_STAGES + 2 * BIT_STAGES + 1;
+    static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)OP_STAGES * OP_BYTES + (size_t)BIT_STAGES * BIT_BYTES +
+                                   N * sizeof(VarFreq) + N_BARS * 8 + 64;
 };
+constexpr int N_WORKER_WARPS = 8;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
 
 template <int N>
 __global__ void __launch_bounds__(MMA_THREADS, MmaCfg<N>::CTAS_PER_SM)
@@ -163,11 +198,14 @@ triangle_mma_kernel(const MmaArgs A) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t *smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);      // swizzle-128B needs 1 KB alignment
-    VarFreq *fb_s = reinterpret_cast<VarFreq *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint8_t *op_s = smem;                                                        // [OP_STAGES][ROWS][128 B]
+    uint8_t *bit_s = smem + Cfg::OP_STAGES * Cfg::OP_BYTES;                      // [BIT_STAGES][ROWS][16 B]
+    VarFreq *fb_s = reinterpret_cast<VarFreq *>(bit_s + Cfg::BIT_STAGES * Cfg::BIT_BYTES);
     uint64_t *bars = reinterpret_cast<uint64_t *>(fb_s + N);
-    const uint32_t full_bar = smem_u32(bars), empty_bar = smem_u32(bars + Cfg::STAGES);
-    const uint32_t tmem_full_bar = smem_u32(bars + 2 * Cfg::STAGES);
-    uint32_t *tmem_ptr_s = reinterpret_cast<uint32_t *>(bars + 2 * Cfg::STAGES + 1);
+    const uint32_t op_full = smem_u32(bars), op_empty = op_full + 8 * Cfg::OP_STAGES;
+    const uint32_t bit_full = op_empty + 8 * Cfg::OP_STAGES, bit_empty = bit_full + 8 * Cfg::BIT_STAGES;
+    const uint32_t tmem_full_bar = bit_empty + 8 * Cfg::BIT_STAGES;
+    uint32_t *tmem_ptr_s = reinterpret_cast<uint32_t *>(bars + Cfg::N_BARS);
     volatile int *abort_s = reinterpret_cast<volatile int *>(tmem_ptr_s + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -176,7 +214,8 @@ triangle_mma_kernel(const MmaArgs A) {
     const int kc_count = A.kc_count;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        for (int s = 0; s < Cfg::OP_STAGES; ++s) { mbar_init(op_full + 8 * s, N_WORKER_WARPS); mbar_init(op_empty + 8 * s, 1); }
+        for (int s = 0; s < Cfg::BIT_STAGES; ++s) { mbar_init(bit_full + 8 * s, 1); mbar_init(bit_empty + 8 * s, N_WORKER_WARPS); }
         mbar_init(tmem_full_bar, 1);
         *abort_s = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -193,22 +232,22 @@ triangle_mma_kernel(const MmaArgs A) {
     const uint32_t tmem_acc = *tmem_ptr_s;
 
     if (warp == 0) {
-        // ===== producer: two linear bulk copies per stage (A panel chunk, B rows chunk)
+        // ===== producer: bit blocks L2 -> shared memory ring (2 KB for the row panel + 16*N B for the columns)
         if (lane == 0) {
-            const uint8_t *a_src = A.ops + (int64_t)tile.x * kc_count * PANEL_BYTES;
+            const uint4 *a_src = A.bits + (int64_t)tile.x * kc_count * 128;
             for (int kc = 0; kc < kc_count; ++kc) {
-                const int s = kc % Cfg::STAGES, it = kc / Cfg::STAGES;
-                if (!mbar_wait(empty_bar + 8 * s, (it & 1) ^ 1, abort_s, A.error_flag)) break;
-                const uint32_t bar = full_bar + 8 * s;
-                mbar_arrive_expect_tx(bar, Cfg::STAGE_BYTES);
-                const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                bulk_g2s(sa, a_src + (int64_t)kc * PANEL_BYTES, PANEL_BYTES, bar);
+                const int s = kc % Cfg::BIT_STAGES, it = kc / Cfg::BIT_STAGES;
+                if (!mbar_wait(bit_empty + 8 * s, (it & 1) ^ 1, abort_s, A.error_flag)) break;
+                const uint32_t bar = bit_full + 8 * s;
+                mbar_arrive_expect_tx(bar, Cfg::BIT_BYTES);
+                const uint32_t dst = smem_u32(bit_s + s * Cfg::BIT_BYTES);
+                bulk_g2s(dst, a_src + (int64_t)kc * 128, MMA_M * 16, bar);
 #pragma unroll
                 for (int part = 0; part < (N + 127) / 128; ++part) {
                     const int64_t crow = c0 + part * 128;                 // first column variant of this part
                     const int rows_here = N < 128 ? N : 128;
-                    const uint8_t *b_src = A.ops + ((crow >> 7) * kc_count + kc) * (int64_t)PANEL_BYTES + (crow & 127) * KCHUNK;
-                    bulk_g2s(sa + PANEL_BYTES + part * PANEL_BYTES, b_src, rows_here * KCHUNK, bar);
+                    bulk_g2s(dst + (MMA_M + part * 128) * 16, A.bits + ((crow >> 7) * kc_count + kc) * 128 + (crow & 127),
+                             rows_here * 16, bar);
                 }
             }
         }
@@ -217,25 +256,46 @@ triangle_mma_kernel(const MmaArgs A) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(MMA_M, N);
             bool ok = true;
-            for (int kc = 0; kc < kc_count && ok; ++kc) {
-                const int s = kc % Cfg::STAGES, it = kc / Cfg::STAGES;
-                ok = mbar_wait(full_bar + 8 * s, it & 1, abort_s, A.error_flag);
+            for (int kc = 0; kc < kc_count; ++kc) {
+                const int s = kc % Cfg::OP_STAGES, it = kc / Cfg::OP_STAGES;
+                ok = mbar_wait(op_full + 8 * s, it & 1, abort_s, A.error_flag);
                 if (!ok) break;
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                const uint32_t sa = smem_u32(op_s + s * Cfg::OP_BYTES);
                 const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + PANEL_BYTES);
 #pragma unroll
                 for (int k = 0; k < KCHUNK / MMA_K; ++k)     // +32 B along K inside the swizzle atom = +2 encoded
                     umma_i8(tmem_acc, da + 2 * k, db + 2 * k, idesc, (uint32_t)((kc | k) != 0));
-                umma_commit(empty_bar + 8 * s);               // stage reusable once these MMAs have read it
+                umma_commit(op_empty + 8 * s);                // stage reusable once these MMAs have read it
             }
             if (ok) umma_commit(tmem_full_bar);               // accumulator complete
         }
     } else {
-        // ===== epilogue: warp w may only touch TMEM lanes 32*(w%4) .. +31
+        // ===== workers, phase 1: widen bit rows into the swizzled operand tile
+        const int wt = (warp - 2) * 32 + lane;                // 0..255
+        bool ok = true;
+        for (int kc = 0; kc < kc_count && ok; ++kc) {
+            const int sb = kc % Cfg::BIT_STAGES, itb = kc / Cfg::BIT_STAGES;
+            const int so = kc % Cfg::OP_STAGES, ito = kc / Cfg::OP_STAGES;
+            ok = mbar_wait(bit_full + 8 * sb, itb & 1, abort_s, A.error_flag);
+            if (!ok) break;
+            const uint4 *bsrc = reinterpret_cast<const uint4 *>(bit_s + sb * Cfg::BIT_BYTES);
+            uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
+            if (wt < Cfg::ROWS) b0 = bsrc[wt];
+            if (Cfg::ROWS > 256 && wt + 256 < Cfg::ROWS) b1 = bsrc[wt + 256];
+            ok = mbar_wait(op_empty + 8 * so, (ito & 1) ^ 1, abort_s, A.error_flag);
+            if (!ok) break;
+            uint8_t *ops = op_s + so * Cfg::OP_BYTES;
+            if (wt < Cfg::ROWS) expand_row(ops + wt * KCHUNK, wt & 7, b0);
+            if (Cfg::ROWS > 256 && wt + 256 < Cfg::ROWS) expand_row(ops + (wt + 256) * KCHUNK, wt & 7, b1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(op_full + 8 * so); mbar_arrive(bit_empty + 8 * sb); }
+        }
+        // ===== workers, phase 2: epilogue.  Warp w may only touch TMEM lanes 32*(w%4) .. +31
         const int quad = warp & 3, half = (warp - 2) >> 2;
         const int64_t r = r0 + quad * 32 + lane;
-        const bool ok = mbar_wait(tmem_full_bar, 0, abort_s, A.error_flag);
+        if (ok) ok = mbar_wait(tmem_full_bar, 0, abort_s, A.error_flag);
         tc_fence_after();
         if (ok) {
             const VarFreq fa = A.freq_rows[r];
@@ -252,7 +312,7 @@ triangle_mma_kernel(const MmaArgs A) {
                         const int64_t col = c0 + c + j;
                         if (col < r) {
                             const VarFreq fb = fb_s[c + j];
-                            const int32_t cnt = (int32_t)acc[j];
+                            const int32_t cnt = (int32_t)(acc[j] >> ACC_SHIFT);
                             const PairFinal f = finalise_pair(cnt, fa, fb, A.fc);   // var_1 = row, var_2 = column
                             uint32_t word = f.packed;
                             if (A.has_thres && measure_e4(word, A.measure) < A.thres_e4) word |= LDX_BELOW_THRES;
@@ -295,51 +355,62 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
                         int thres_e4, uint32_t *d_packed, int32_t *d_n11) {
     if (v < 2) return LDX_OK;
     ldx_ctx *ctx = s->ctx;
-    const int kc_count = (s->n_hap + KCHUNK - 1) / KCHUNK;
+    if (s->n_hap > (1 << 17)) return set_error(LDX_ERR_ARG, "tcgen05 engine: more than 2^17 haplotypes would overflow the int32 accumulator");
+    const int kc_count = (s->n_hap + KCHUNK - 1) / KCHUNK;     // stride_words*64 >= kc_count*128 (rows are 128 B multiples)
     const int64_t v_pad = (v + 255) / 256 * 256;
     const int64_t panels = v_pad / MMA_M;
-    // tile width: narrow tiles fill the SMs for small matrices, wide tiles cut L2 traffic for large ones
+    // tile width: narrow tiles fill the SMs for small matrices, wide tiles amortise the widening work
     int n_tile = ctx->mma_tile_n;
     if (n_tile == 0) n_tile = v <= 4096 ? 64 : 128;
-    // ---- tile list: every 128 x N tile that holds at least one pair with row > col, row-panel major
-    std::vector<int2> tiles;
+    // ---- tile list (cached): every 128 x N tile holding at least one pair with row > col, row-panel major
+    const size_t bits_bytes = (size_t)panels * kc_count * 128 * sizeof(uint4);
+    const size_t freq_bytes = (size_t)v_pad * sizeof(VarFreq);
+    size_t n_tiles = 0;
     for (int64_t bi = 0; bi < (v + MMA_M - 1) / MMA_M; ++bi) {
         const int64_t rmax = std::min<int64_t>(bi * MMA_M + MMA_M - 1, v - 1);
-        for (int64_t bj = 0; bj * n_tile < rmax; ++bj) tiles.push_back(make_int2((int)bi, (int)bj));
+        n_tiles += (size_t)((rmax + n_tile - 1) / n_tile);
     }
-    if (tiles.empty()) return LDX_OK;
-    // ---- scratch: operand panels | gathered VarFreq | tile list
-    const size_t ops_bytes = (size_t)panels * kc_count * PANEL_BYTES;
-    const size_t freq_bytes = (size_t)v_pad * sizeof(VarFreq);
-    const size_t tile_bytes = tiles.size() * sizeof(int2);
-    const size_t need = ops_bytes + freq_bytes + tile_bytes + 1024;
+    if (n_tiles == 0) return LDX_OK;
+    const size_t tile_bytes = n_tiles * sizeof(int2);
+    const size_t need = bits_bytes + freq_bytes + tile_bytes + 1024;
     if (ctx->mma_ops_bytes < need) {
         if (ctx->d_mma_ops) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_mma_ops); ctx->d_mma_ops = nullptr; ctx->mma_ops_bytes = 0; }
         if (cudaMalloc(&ctx->d_mma_ops, need) != cudaSuccess) { cudaGetLastError(); return set_error(LDX_ERR_NOMEM, "tcgen05 operand scratch allocation failed"); }
         ctx->mma_ops_bytes = need;
+        ctx->mma_tiles_v = -1;
     }
-    uint8_t *d_ops = reinterpret_cast<uint8_t *>(ctx->d_mma_ops);
-    VarFreq *d_freq_rows = reinterpret_cast<VarFreq *>(d_ops + ops_bytes);
-    int2 *d_tiles = reinterpret_cast<int2 *>(d_ops + ops_bytes + freq_bytes);
-    LDX_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tile_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    LDX_CUDA(cudaStreamSynchronize(ctx->stream));   // `tiles` is a local (pageable copy is staged, but be explicit)
+    uint8_t *base = reinterpret_cast<uint8_t *>(ctx->d_mma_ops);
+    uint4 *d_bits = reinterpret_cast<uint4 *>(base);
+    VarFreq *d_freq_rows = reinterpret_cast<VarFreq *>(base + bits_bytes);
+    int2 *d_tiles = reinterpret_cast<int2 *>(base + bits_bytes + freq_bytes);
+    if (ctx->mma_tiles_v != v || ctx->mma_tiles_n != n_tile) {          // the list depends on (v, N) only
+        std::vector<int2> tiles;
+        tiles.reserve(n_tiles);
+        for (int64_t bi = 0; bi < (v + MMA_M - 1) / MMA_M; ++bi) {
+            const int64_t rmax = std::min<int64_t>(bi * MMA_M + MMA_M - 1, v - 1);
+            for (int64_t bj = 0; bj * n_tile < rmax; ++bj) tiles.push_back(make_int2((int)bi, (int)bj));
+        }
+        LDX_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tile_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        LDX_CUDA(cudaStreamSynchronize(ctx->stream));   // `tiles` is a local
+        ctx->mma_tiles_v = v; ctx->mma_tiles_n = n_tile;
+    }
 
-    dim3 egrid((unsigned)((v_pad + 31) / 32), (unsigned)kc_count);
-    expand_kernel<<<egrid, 256, 0, ctx->stream>>>(s->d_planes, s->d_mask, s->stride_words, d_rows, v, v_pad, kc_count,
-                                                  s->d_freq, d_ops, d_freq_rows);
+    dim3 ggrid((unsigned)((v_pad + 255) / 256), (unsigned)kc_count);
+    gather_bits_kernel<<<ggrid, 256, 0, ctx->stream>>>(s->d_planes, s->d_mask, s->stride_words, d_rows, v, v_pad, kc_count,
+                                                       s->d_freq, d_bits, d_freq_rows);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
 
     MmaArgs A;
-    A.ops = d_ops; A.kc_count = kc_count; A.freq_rows = d_freq_rows; A.fc = s->fc; A.tiles = d_tiles;
+    A.bits = d_bits; A.kc_count = kc_count; A.freq_rows = d_freq_rows; A.fc = s->fc; A.tiles = d_tiles;
     A.v = v; A.measure = measure; A.has_thres = has_thres; A.thres_e4 = thres_e4;
     A.packed = d_packed; A.n11 = d_n11;
     A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity};
     A.error_flag = reinterpret_cast<int32_t *>(ctx->d_fix_count + 1);
     switch (n_tile) {
-        case 64: return launch_tiles<64>(ctx, A, (int)tiles.size());
-        case 128: return launch_tiles<128>(ctx, A, (int)tiles.size());
-        case 256: return launch_tiles<256>(ctx, A, (int)tiles.size());
+        case 64: return launch_tiles<64>(ctx, A, (int)n_tiles);
+        case 128: return launch_tiles<128>(ctx, A, (int)n_tiles);
+        case 256: return launch_tiles<256>(ctx, A, (int)n_tiles);
         default: return set_error(LDX_ERR_ARG, "tcgen05 tile width must be 64, 128 or 256");
     }
 }

@@ -109,6 +109,20 @@ class Context:
         check(self._lib.ldx_resolve(self._h, C.byref(n)))
         return n.value
 
+    def finalise_counts(self, n_hap, n11, n1a, n1b):
+        """calc_ld.py:33-97 for arrays of counts.  -> dict(d, dprime, r2, packed)."""
+        n11 = np.ascontiguousarray(n11, dtype=np.int32)
+        n1a = np.ascontiguousarray(np.broadcast_to(np.asarray(n1a, dtype=np.int32), n11.shape))
+        n1b = np.ascontiguousarray(np.broadcast_to(np.asarray(n1b, dtype=np.int32), n11.shape))
+        n = n11.shape[0]
+        out = {"d": np.zeros(n), "dprime": np.zeros(n), "r2": np.zeros(n), "packed": np.zeros(n, np.uint32)}
+        rc = self._lib.ldx_finalise_counts(self._h, int(n_hap), ptr(n11), ptr(n1a), ptr(n1b), n, ptr(out["d"]),
+                                           ptr(out["dprime"]), ptr(out["r2"]), ptr(out["packed"]))
+        if rc == _lib.ERR_EMPTY:
+            raise ZeroDivisionError("division by zero")
+        check(rc)
+        return out
+
     def calc_ld_lists(self, codes_a, codes_b):
         """Genotype byte codes (0 ref, 1 alt, other = neither) -> LD_RESULT_DTYPE record."""
         a = np.ascontiguousarray(codes_a, dtype=np.uint8)

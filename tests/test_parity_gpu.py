@@ -364,3 +364,53 @@ def test_triangle_mma_full_size_and_threshold(ctx):
     assert ((flagged & ~np.uint32(BELOW_THRES)) == packed).all()
     assert (((flagged & BELOW_THRES) != 0) == (r2_e4(packed) < t)).all()
     st.close()
+
+
+# ------------------------------------------------------------------ fp64 finalisation at scale
+
+def test_finalise_counts_golden(golden, ctx):
+    """Every golden count case through the count-level entry point: rounded values identical,
+    D and D' bit-exact, r2 within 1e-12 (bit-exact unless the reference's pow rounds the other way)."""
+    from ld_tools_b200.engine import dprime_value, r2_value
+    by_n = {}
+    for tag, n, n11, a, b, *out in golden["count_cases"]:
+        by_n.setdefault(n, []).append(((n11, a, b), out))
+    for n, items in by_n.items():
+        c = np.array([x for x, _ in items], dtype=np.int32)
+        res = ctx.finalise_counts(n, c[:, 0], c[:, 1], c[:, 2])
+        for i, (_, out) in enumerate(items):
+            assert repr(r2_value(res["packed"][i])) == out[0] and repr(dprime_value(res["packed"][i])) == out[1]
+            raw_r2, raw_dp, raw_d = decode_raw(out[4]), decode_raw(out[5]), decode_raw(out[8])
+            assert float(res["d"][i]).hex() == float(raw_d).hex()
+            if not isinstance(raw_dp, int):
+                assert float(res["dprime"][i]).hex() == raw_dp.hex()
+            if not isinstance(raw_r2, int):
+                assert abs(res["r2"][i] - raw_r2) <= TOL
+
+
+@pytest.mark.parametrize("n_hap", [2, 7, 198, 1006, 5008, 131072])
+def test_finalise_counts_random_vs_oracle(ctx, n_hap):
+    """Millions of random count triples: the branch-free division / rounding path must agree with
+    the C oracle (IEEE division, libm pow, printf-rounding) on every packed word."""
+    rng = np.random.default_rng(n_hap)
+    n = 1_500_000 if n_hap >= 198 else 20000
+    a = rng.integers(0, n_hap + 1, size=n)
+    b = rng.integers(0, n_hap + 1, size=n)
+    rare = rng.random(n) < 0.4
+    a[rare] = rng.integers(0, min(n_hap, 30) + 1, size=int(rare.sum()))
+    rare = rng.random(n) < 0.3
+    b[rare] = rng.integers(0, min(n_hap, 30) + 1, size=int(rare.sum()))
+    lo, hi = np.maximum(0, a + b - n_hap), np.minimum(a, b)
+    n11 = lo + (rng.random(n) * (hi - lo + 1)).astype(np.int64)
+    n11 = np.minimum(n11, hi)
+    full = rng.random(n) < 0.2
+    n11[full] = hi[full]
+    res = ctx.finalise_counts(n_hap, n11, a, b)
+    want = ld_oracle.packed_words(n_hap, n11, a, b)
+    bad = np.flatnonzero(res["packed"] != want)
+    assert bad.size == 0, (bad[:5], n11[bad[:5]], a[bad[:5]], b[bad[:5]])
+    sub = rng.choice(n, 3000, replace=False)
+    exact = ld_oracle.finalise_many(n_hap, n11[sub], a[sub], b[sub])
+    assert (res["d"][sub] == exact["d"]).all()
+    assert (res["dprime"][sub] == exact["dprime"]).all()
+    assert np.abs(res["r2"][sub] - exact["r2"]).max() <= TOL

@@ -42,6 +42,7 @@ SIGNATURES = {
     "ldx_set_stream": [_vp, _vp],
     "ldx_use_own_stream": [_vp],
     "ldx_synchronize": [_vp],
+    "ldx_debug_trace": [_vp, _i32, _vp],
     "ldx_set_tuning": [_vp, _i32, _i32],
     "ldx_sm_count": [_vp, _P(_i32)],
     "ldx_launch_count": [_vp, _P(_i64)],

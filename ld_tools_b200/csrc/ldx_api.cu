@@ -1,6 +1,7 @@
 // ldx_api.cu -- the C ABI declared in include/ldx.h: context, store, and the host-side halves of
 // the compute entry points (staging, launch, copy-back, near-tie settlement, hit ordering).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
@@ -27,7 +28,7 @@ using namespace ldx;
 
 // grow-only device scratch owned by the ctx (avoids cudaMalloc/cudaFree on every call)
 struct Arena {
-    enum { SLOTS = 12 };
+    enum { SLOTS = 13 };
     void *ptr[SLOTS] = {};
     size_t bytes[SLOTS] = {};
 };
@@ -46,7 +47,7 @@ static int arena_get(ldx_ctx *ctx, int slot, size_t bytes, void **out) {
     *out = a->ptr[slot];
     return LDX_OK;
 }
-enum { S_IA = 0, S_IB, S_PACKED, S_N11, S_D, S_DP, S_R2, S_TEXT, S_ROWOFF, S_STATUS, S_HITS, S_MISC };
+enum { S_IA = 0, S_IB, S_PACKED, S_N11, S_D, S_DP, S_R2, S_TEXT, S_ROWOFF, S_STATUS, S_HITS, S_MISC, S_ROWS };
 
 // ------------------------------------------------------------------------------------------ lifecycle
 extern "C" int32_t ldx_abi_version(void) { return LDX_ABI_VERSION; }
@@ -84,6 +85,8 @@ extern "C" int32_t ldx_init(int32_t device, ldx_ctx **ctx_out) {
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fix_count, 4 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_fix_count, 0, 4 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_fix_count, 4 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&ctx->h_mailbox, 4 * sizeof(uint32_t), cudaHostAllocMapped);
+    if (e == cudaSuccess) { for (int i = 0; i < 4; ++i) ctx->h_mailbox[i] = 0; e = cudaHostGetDevicePointer((void **)&ctx->d_mailbox, (void *)ctx->h_mailbox, 0); }
     if (e != cudaSuccess) { ldx_destroy(ctx); return cuda_fail(e, "ldx_init"); }
     ctx->stream = ctx->own_stream;
     *ctx_out = ctx;
@@ -101,7 +104,9 @@ extern "C" int32_t ldx_destroy(ldx_ctx *ctx) {
     if (ctx->d_fix) cudaFree(ctx->d_fix);
     if (ctx->d_fix_count) cudaFree(ctx->d_fix_count);
     if (ctx->h_fix_count) cudaFreeHost(ctx->h_fix_count);
+    if (ctx->h_mailbox) cudaFreeHost((void *)ctx->h_mailbox);
     if (ctx->d_mma_ops) cudaFree(ctx->d_mma_ops);
+    if (ctx->d_trace) cudaFree(ctx->d_trace);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return LDX_OK;
@@ -133,6 +138,21 @@ extern "C" int32_t ldx_set_tuning(ldx_ctx *ctx, int32_t key, int32_t value) {
         default:
             return set_error(LDX_ERR_ARG, "unknown tuning key");
     }
+}
+
+extern "C" int32_t ldx_debug_trace(ldx_ctx *ctx, int32_t enable, uint64_t *stamps8) {
+    LDX_REQUIRE(ctx, "ctx is NULL");
+    LDX_CUDA(cudaSetDevice(ctx->device));
+    if (enable && !ctx->d_trace) {
+        LDX_CUDA(cudaMalloc(&ctx->d_trace, 256 * sizeof(unsigned long long)));
+        LDX_CUDA(cudaMemset(ctx->d_trace, 0, 256 * sizeof(unsigned long long)));
+    }
+    if (stamps8 && ctx->d_trace) {
+        LDX_CUDA(cudaStreamSynchronize(ctx->stream));
+        LDX_CUDA(cudaMemcpy(stamps8, ctx->d_trace, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    if (!enable && ctx->d_trace) { cudaFree(ctx->d_trace); ctx->d_trace = nullptr; }
+    return LDX_OK;
 }
 
 extern "C" int32_t ldx_synchronize(ldx_ctx *ctx) {
@@ -197,17 +217,30 @@ static inline int32_t word_measure(uint32_t w, int measure) {
     return measure == LDX_MEASURE_R2 ? (int32_t)(w & LDX_R2_MASK) : (int32_t)((w & LDX_DP_MASK) >> LDX_DP_SHIFT);
 }
 
-// Fetch (and clear) the device fix-up list.  Synchronises the stream.
-static int collect_fixups(ldx_ctx *ctx, std::vector<FixupRec> &recs) {
+// Fetch (and clear) the device fix-up list.  Waits for the stream's work: through the mailbox
+// (a host-memory poll) when the last enqueued call published one, else by synchronising.
+static int collect_fixups(ldx_ctx *ctx, std::vector<FixupRec> &recs, bool use_mailbox = false) {
     recs.clear();
-    // [0] = near-tie records appended, [1] = tcgen05 pipeline error flag
-    LDX_CUDA(cudaMemcpyAsync(ctx->h_fix_count, ctx->d_fix_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    LDX_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_fix_count[1]) {
+    uint32_t n, err;
+    bool polled = false;
+    if (use_mailbox && ctx->seq != 0) {
+        const uint32_t want = ctx->seq;
+        for (long spins = 0; spins < 200000000L; ++spins)
+            if (ctx->h_mailbox[0] == want) { polled = true; break; }
+    }
+    if (polled) {
+        std::atomic_thread_fence(std::memory_order_acquire);
+        n = ctx->h_mailbox[1]; err = ctx->h_mailbox[2];
+    } else {
+        // [0] = near-tie records appended, [1] = tcgen05 pipeline error flag
+        LDX_CUDA(cudaMemcpyAsync(ctx->h_fix_count, ctx->d_fix_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        LDX_CUDA(cudaStreamSynchronize(ctx->stream));
+        n = ctx->h_fix_count[0]; err = ctx->h_fix_count[1];
+    }
+    if (err) {
         cudaMemsetAsync(ctx->d_fix_count, 0, 2 * sizeof(uint32_t), ctx->stream);
         return set_error(LDX_ERR_CUDA, "tcgen05 pipeline timed out (mbarrier wait exceeded 2 s); results are invalid");
     }
-    const uint32_t n = ctx->h_fix_count[0];
     if (n == 0) return LDX_OK;
     if (n > ctx->fix_capacity) {
         cudaMemsetAsync(ctx->d_fix_count, 0, sizeof(uint32_t), ctx->stream);
@@ -258,15 +291,21 @@ extern "C" int32_t ldx_calc_ld_lists(ldx_ctx *ctx, const uint8_t *g_a, int64_t l
 // ------------------------------------------------------------------------------------------ counts
 static int make_final_ctx(int64_t n_sel, FinalCtx *fc) {
     fc->n_hap = (double)n_sel;
-    fc->rcp_n = 1.0 / (double)n_sel;
-    // prove the two-FMA quotient equals the IEEE quotient for every count that can occur
-    fc->exact_div = 1;
-    for (int64_t n = 0; n <= n_sel; ++n) {
-        const double x = (double)n, q0 = x * fc->rcp_n;
-        const double r = std::fma(-q0, fc->n_hap, x);
-        if (std::fma(r, fc->rcp_n, q0) != x / fc->n_hap) { fc->exact_div = 0; break; }
+    // Prove the three-operation quotient of div_by_n (ldx_common.cuh) equals the IEEE quotient for
+    // every count that can occur.  RN(1/N) always passed in testing (Markstein's theorem); its
+    // two neighbours are tried before giving up so that the device needs no fallback division.
+    const double rn = 1.0 / (double)n_sel;
+    const double cand[3] = {rn, std::nextafter(rn, 0.0), std::nextafter(rn, 2.0)};
+    for (double rcp : cand) {
+        bool ok = true;
+        for (int64_t n = 0; n <= n_sel && ok; ++n) {
+            const double x = (double)n, q0 = x * rcp;
+            const double r = std::fma(-q0, fc->n_hap, x);
+            ok = std::fma(r, rcp, q0) == x / fc->n_hap;
+        }
+        if (ok) { fc->rcp_n = rcp; return LDX_OK; }
     }
-    return LDX_OK;
+    return set_error(LDX_ERR_DATA, "no exact reciprocal found for this haplotype count");
 }
 
 extern "C" int32_t ldx_finalise_counts(ldx_ctx *ctx, int32_t n_hap, const int32_t *n11, const int32_t *n1a,
@@ -282,7 +321,7 @@ extern "C" int32_t ldx_finalise_counts(ldx_ctx *ctx, int32_t n_hap, const int32_
     if (n == 0) return LDX_OK;
     LDX_CUDA(cudaSetDevice(ctx->device));
     FinalCtx fc;
-    make_final_ctx(n_hap, &fc);
+    LDX_TRY(make_final_ctx(n_hap, &fc));
     int32_t *d_in; double *d_d = nullptr, *d_dp = nullptr, *d_r2 = nullptr; uint32_t *d_pk;
     LDX_TRY(arena_get(ctx, S_IA, sizeof(int32_t) * 3 * (size_t)n, (void **)&d_in));
     if (d) LDX_TRY(arena_get(ctx, S_D, sizeof(double) * (size_t)n, (void **)&d_d));
@@ -430,7 +469,7 @@ extern "C" int32_t ldx_store_set_mask(ldx_store *s, const uint64_t *mask) {
     if (n_sel == 0) return set_error(LDX_ERR_EMPTY, "division by zero");   // empty sample selection, calc_ld.py:33
     LDX_CUDA(cudaSetDevice(s->ctx->device));
     s->n_sel = (int32_t)n_sel;
-    make_final_ctx(n_sel, &s->fc);
+    LDX_TRY(make_final_ctx(n_sel, &s->fc));
     LDX_CUDA(cudaMemcpyAsync(s->d_mask, m.data(), sizeof(uint64_t) * s->stride_words, cudaMemcpyHostToDevice, s->ctx->stream));
     LDX_CUDA(cudaStreamSynchronize(s->ctx->stream));   // m goes out of scope
     LDX_TRY(launch_variant_freq(s));
@@ -610,6 +649,8 @@ extern "C" int32_t ldx_window_dev(ldx_store *s, const int64_t *q_row, const int6
     if (nq == 0 || n_chunks == 0) return LDX_OK;
     LDX_TRY(launch_window(s, arr[0], arr[1], arr[2], (const int32_t *)arr[4], (const int32_t *)arr[5], arr[3], nq,
                           n_chunks, measure, thres_e4, dev_hits, cap, reinterpret_cast<unsigned long long *>(dev_n_hits)));
+    ++ctx->seq;
+    LDX_TRY(launch_publish(ctx));
     ctx->pending.kind = 2; ctx->pending.dev_out = dev_hits; ctx->pending.n_hap = s->fc.n_hap;
     ctx->pending.measure = measure; ctx->pending.has_thres = 1; ctx->pending.thres_e4 = thres_e4;
     return LDX_OK;
@@ -663,12 +704,20 @@ extern "C" int32_t ldx_window(ldx_store *s, const int64_t *q_row, const int64_t 
 static int stage_rows(ldx_store *s, const int64_t *rows, int64_t v, int64_t **d_rows_out) {
     LDX_TRY(require_mask(s));
     LDX_REQUIRE(v >= 0 && v < (1ll << 31) && (v == 0 || rows), "bad rows");
-    for (int64_t k = 0; k < v; ++k) LDX_REQUIRE(rows[k] >= 0 && rows[k] < s->n_variants, "rows[] outside the store");
     if (v == 0) { *d_rows_out = nullptr; return LDX_OK; }
     ldx_ctx *ctx = s->ctx;
     LDX_CUDA(cudaSetDevice(ctx->device));
-    LDX_TRY(arena_get(ctx, S_IA, sizeof(int64_t) * (size_t)v, (void **)d_rows_out));
-    LDX_CUDA(cudaMemcpyAsync(*d_rows_out, rows, sizeof(int64_t) * (size_t)v, cudaMemcpyHostToDevice, ctx->stream));
+    Arena *a = arena_of(ctx);
+    void *before = a->ptr[S_ROWS];
+    LDX_TRY(arena_get(ctx, S_ROWS, sizeof(int64_t) * (size_t)v, (void **)d_rows_out));
+    // repeated calls on the same variant list (the usual case) skip validation and the upload
+    const bool same = before == a->ptr[S_ROWS] && (int64_t)ctx->rows_cache.size() == v &&
+                      std::memcmp(ctx->rows_cache.data(), rows, sizeof(int64_t) * (size_t)v) == 0;
+    if (same) return LDX_OK;
+    ctx->rows_cache.clear();
+    for (int64_t k = 0; k < v; ++k) LDX_REQUIRE(rows[k] >= 0 && rows[k] < s->n_variants, "rows[] outside the store");
+    ctx->rows_cache.assign(rows, rows + v);
+    LDX_CUDA(cudaMemcpyAsync(*d_rows_out, ctx->rows_cache.data(), sizeof(int64_t) * (size_t)v, cudaMemcpyHostToDevice, ctx->stream));
     return LDX_OK;
 }
 
@@ -689,6 +738,8 @@ extern "C" int32_t ldx_triangle_dev(ldx_store *s, const int64_t *rows, int64_t v
     int rc = use_mma ? launch_triangle_mma(s, d_rows, v, measure, has_thres, thres_e4, dev_packed, dev_n11)
                      : launch_triangle_popc(s, d_rows, v, measure, has_thres, thres_e4, dev_packed, dev_n11);
     LDX_TRY(rc);
+    ++ctx->seq;
+    LDX_TRY(launch_publish(ctx));
     ctx->pending.kind = 1; ctx->pending.dev_out = dev_packed; ctx->pending.n_hap = s->fc.n_hap;
     ctx->pending.measure = measure; ctx->pending.has_thres = has_thres; ctx->pending.thres_e4 = thres_e4;
     return LDX_OK;
@@ -723,7 +774,7 @@ extern "C" int32_t ldx_resolve(ldx_ctx *ctx, int64_t *n_fixed_out) {
     if (n_fixed_out) *n_fixed_out = 0;
     LDX_CUDA(cudaSetDevice(ctx->device));
     std::vector<FixupRec> recs;
-    LDX_TRY(collect_fixups(ctx, recs));
+    LDX_TRY(collect_fixups(ctx, recs, true));
     const ldx_ctx::Pending p = ctx->pending;
     ctx->pending.kind = 0;
     if (recs.empty() || p.kind == 0) return LDX_OK;

@@ -36,6 +36,14 @@ struct ldx_ctx {
     int mma_tile_n = 0;                   // tcgen05 tile width override (0 = heuristic)
     int64_t mma_tiles_v = -1;             // tile list cached in d_mma_ops: built for this (v, N)
     int mma_tiles_n = 0;
+    // completion mailbox: pinned, device-mapped {seq, near-tie count, error flag}; a 1-thread kernel
+    // publishes it after each *_dev call so that ldx_resolve() can poll host memory instead of
+    // paying a stream synchronisation (tens of microseconds) per call
+    volatile uint32_t *h_mailbox = nullptr;
+    uint32_t *d_mailbox = nullptr;
+    uint32_t seq = 0;
+    std::vector<int64_t> rows_cache;      // host copy of the variant list last staged on the device
+    unsigned long long *d_trace = nullptr;   // diagnostics: globaltimer stamps written by the tcgen05 kernel
     int mma_min_v = 256;                  // ENGINE_AUTO uses the tcgen05 engine from this many variants
 };
 
@@ -90,6 +98,7 @@ int launch_triangle_popc(ldx_store *s, const int64_t *d_rows, int64_t v, int mea
 int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int measure, int has_thres,
                         int thres_e4, uint32_t *d_packed, int32_t *d_n11);
 bool triangle_mma_available();
+int launch_publish(ldx_ctx *ctx);   // enqueue the mailbox update for ctx->seq
 
 constexpr int WINDOW_CHUNK = 256;   // rows per work item of the window kernel
 

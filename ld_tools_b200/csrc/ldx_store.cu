@@ -179,4 +179,21 @@ int launch_subset(const ldx_store *src, const int32_t *d_sel, ldx_store *dst) {
     return LDX_OK;
 }
 
+// ------------------------------------------------------------------------------------------ mailbox
+// One thread copies {near-tie count, error flag} and the call's sequence number to pinned host
+// memory.  __threadfence_system() orders the payload before the sequence number.
+__global__ void publish_kernel(const uint32_t *__restrict__ fix_count, volatile uint32_t *mailbox, uint32_t seq) {
+    mailbox[1] = fix_count[0];
+    mailbox[2] = fix_count[1];
+    __threadfence_system();
+    mailbox[0] = seq;
+}
+
+int launch_publish(ldx_ctx *ctx) {
+    publish_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_fix_count, ctx->d_mailbox, ctx->seq);
+    ctx->launches++;
+    LDX_CUDA(cudaGetLastError());
+    return LDX_OK;
+}
+
 }  // namespace ldx

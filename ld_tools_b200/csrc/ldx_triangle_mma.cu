@@ -5,9 +5,8 @@
 // Replaces the double loop at ld_triangle.py:133-230 (var_1 = row variant, var_2 = column
 // variant, ld_triangle.py:193); the counting step is calc_ld.py:30-32 for 128 x N pairs at once:
 //     n11[r][c] = sum_h  a[r][h] * a[c][h],   a[v][h] = (plane[v] & mask) bit h
-// Operand bytes are 0x00 / 0x80 (see expand_row), so every product is 0 or 2^14 and the int32
-// accumulator holds n11 * 2^14 exactly (n11 <= 2^17 haplotypes would still fit); the epilogue
-// shifts it back.  The counts equal the popcount engine's bit for bit (tests/test_parity_gpu.py).
+// Operand bytes are 0 or a power of two chosen so that every (alt, alt) product is 2^7 (see
+// widen4): the int32 accumulator holds n11 * 128 exactly; the epilogue shifts it back.  The counts equal the popcount engine's bit for bit (tests/test_parity_gpu.py).
 //
 // Data movement is designed around the L2: the operands stay BIT-PACKED in global memory/L2
 // (16 B per variant per 128-haplotype chunk, gathered once per call by gather_bits_kernel, O(V))
@@ -16,23 +15,26 @@
 // both the tensor and the fp64 pipe under 14% busy.  Bit-packed operands cut that traffic 8x and
 // keep a 100k-variant operand set (64 MB) resident in the 126 MB L2.
 //
-// One CTA = one 128 x N tile of the lower triangle, 10 warps:
-//   warp 0     producer: cp.async.bulk (UBLKCP, the TMA engine's linear mode) brings the tile's
-//              bit blocks (2 KB per 128 variants per chunk) into an 8-deep shared-memory ring;
-//              completion is counted on mbarriers (complete_tx).
-//   warps 2-9  workers, phase 1: each thread widens one variant-row of the chunk (128 bits ->
-//              128 bytes) straight into the 128-byte-swizzled operand tile tcgen05 reads
-//              (LOP on the ALU pipe + IMAD on the FMA pipe, one 16-byte STS per 16 haplotypes),
-//              fence.proxy.async, mbarrier arrive.
-//   warp 1     MMA issuer: one elected lane issues 4 x tcgen05.mma (K = 32 each) per chunk and
-//              tcgen05.commit's the operand stage back to the workers; owns the TMEM allocation.
-//   warps 2-9  workers, phase 2 (epilogue): tcgen05.ld the int32 counts (lane = row variant,
-//              column = column variant), calc_ld.py:33-97 in fp64 (ldx_common.cuh), packed stores.
-// Two or three CTAs are resident per SM (N <= 128), so one tile's tensor work overlaps another
-// tile's fp64 epilogue without an intra-CTA software pipeline.
+// Persistent, warp-specialised CTAs (one per SM, 18 warps), each looping over 128 x N tiles of
+// the lower triangle:
+//   warp 0      producer: cp.async.bulk (UBLKCP, the TMA engine's linear mode) brings the tiles'
+//               bit blocks (2 KB per 128 variants per chunk) into an 8-deep shared-memory ring;
+//               completion is counted on mbarriers (complete_tx).  Runs ahead across tiles.
+//   warps 2-9   wideners: each thread turns one variant-row of a chunk (128 bits) into 128 operand
+//               bytes, written straight into the 128-byte-swizzled tile tcgen05 reads (LOP on the
+//               ALU pipe + IMAD on the FMA pipe, one 16-byte STS per 16 haplotypes), then
+//               fence.proxy.async + mbarrier arrive.  3-deep operand ring.
+//   warp 1      MMA issuer: one elected lane issues 4 x tcgen05.mma (K = 32 each) per chunk,
+//               tcgen05.commit's the operand stage back to the wideners and, per tile, the TMEM
+//               accumulator to the epilogue; owns the TMEM allocation (2 accumulators of N columns).
+//   warps 10-17 epilogue: tcgen05.ld the int32 counts (lane = row variant, column = column
+//               variant), calc_ld.py:33-97 in fp64 (ldx_common.cuh, branch-free so that the 16
+//               pairs of a chunk interleave), transpose through shared memory and store rows of
+//               packed results coalesced.  Works on accumulator t while the tensor pipe fills t+1.
 //
 // Roofline: int8 tensor pipe, 2 * n_hap int8 ops per pair; co-bounds are the fp64 epilogue
 // (~45 fp64 instructions per pair) and the widening ALU work ((128 + N) rows per 128 * N pairs).
+#include <cstdlib>
 #include <vector>
 
 #include "ldx_internal.h"
@@ -44,7 +46,6 @@ constexpr int MMA_M = 128;            // rows (variants) per tile = TMEM lanes
 constexpr int KCHUNK = 128;           // haplotypes (= bytes) per shared-memory row: one swizzle atom
 constexpr int MMA_K = 32;             // int8 K of one tcgen05.mma
 constexpr int PANEL_BYTES = MMA_M * KCHUNK;   // 16 KB: one (panel, chunk) block
-constexpr int MMA_THREADS = 320;      // 1 producer + 1 MMA + 8 epilogue warps
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,13 +62,17 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
                  "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
-// Bounded wait: a pipeline bug must end in an error code, never in a hung GPU.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int *abort_s, int32_t *err) {
+// Bounded wait: a pipeline bug must end in an error code, never in a hung GPU.  The common case
+// (phase already complete) is one try_wait; the slow path polls, optionally sleeping between
+// polls so that long waits (the epilogue waiting out a whole K loop) do not steal issue slots
+// from the warps doing the work, and checks the abort flag / a 2 s deadline now and then.
+__device__ __forceinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, volatile int *abort_s, int32_t *err, uint32_t sleep_ns) {
     unsigned long long t0 = 0;
     for (uint32_t spins = 1;; ++spins) {
         if (mbar_try_wait(bar, parity)) return true;
-        if (*abort_s) return false;
-        if ((spins & 0x3ff) == 0) {
+        if (sleep_ns) __nanosleep(sleep_ns);
+        if ((spins & 0x3f) == 0) {
+            if (*abort_s) return false;
             unsigned long long t;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
             if (!t0) t0 = t;
@@ -75,9 +80,21 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
         }
     }
 }
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int *abort_s, int32_t *err, uint32_t sleep_ns = 0) {
+    if (mbar_try_wait(bar, parity)) return true;
+    return mbar_wait_slow(bar, parity, abort_s, err, sleep_ns);
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// One lane of a fully converged warp; the surrounding control flow stays warp-uniform so that the
+// compiler keeps descriptors/addresses in uniform registers (issuing tcgen05/bulk-copy instructions
+// from a lane-divergent region costs an R2UR waterfall loop per instruction).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -116,10 +133,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 // Store rows (gathered through rows[], masked) -> chunk-blocked bit panels:
 //   bits[panel][chunk][row 0..127][16 B],  panel = matrix_row / 128,  chunk = haplotype / 128
 // so that the 128 rows of one pipeline stage are ONE contiguous 2 KB block (one bulk copy).
+// A second copy with each byte bit-reversed feeds the column operand.
 __global__ void __launch_bounds__(256)
 gather_bits_kernel(const uint64_t *__restrict__ planes, const uint64_t *__restrict__ mask, int32_t stride_words,
                    const int64_t *__restrict__ rows, int64_t v, int64_t v_pad, int32_t kc_count,
-                   const VarFreq *__restrict__ freq, uint4 *__restrict__ bits, VarFreq *__restrict__ freq_rows) {
+                   const VarFreq *__restrict__ freq, uint4 *__restrict__ bits, uint4 *__restrict__ bits_rev,
+                   VarFreq *__restrict__ freq_rows) {
     const int kc = blockIdx.y;
     const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;          // matrix row
     if (r >= v_pad) return;
@@ -134,65 +153,92 @@ gather_bits_kernel(const uint64_t *__restrict__ planes, const uint64_t *__restri
         VarFreq z; z.p = 0.0; z.q = 0.0; z.pq = 0.0; z.n1 = 0; z.p_e4 = 0;
         freq_rows[r] = z;
     }
-    bits[((r >> 7) * kc_count + kc) * 128 + (r & 127)] = out;
+    const int64_t o = ((r >> 7) * kc_count + kc) * 128 + (r & 127);
+    bits[o] = out;
+    // the same bits with every BYTE bit-reversed: the column operand's source (see widen_row)
+    bits_rev[o] = make_uint4(__byte_perm(__brev(out.x), 0, 0x0123), __byte_perm(__brev(out.y), 0, 0x0123),
+                             __byte_perm(__brev(out.z), 0, 0x0123), __byte_perm(__brev(out.w), 0, 0x0123));
 }
 
 // ------------------------------------------------------------------------------------------ widen
-// 32 haplotype bits -> 32 operand bytes of value 0x00 / 0x80:  (w << s) & 0x80808080 for
-// s = 0..7 picks bits 7-s, 15-s, 23-s, 31-s.  The left shifts are IMADs (FMA pipe), the masks
-// LOPs (ALU pipe), so the two pipes share the work.  The haplotype ORDER inside a chunk is
-// permuted by this, identically for both operands -- a dot product does not care.
-__device__ __forceinline__ uint4 widen4(uint32_t w, int s0) {
+// 32 haplotype bits -> 32 operand bytes with ONE logic instruction per 4 bytes and no shifts:
+//     row operand     byte(j, p) = w  & (0x01 << p)        -> value 2^p      for haplotype 8j+p
+//     column operand  byte(j, p) = w' & (0x80 >> p)        -> value 2^(7-p)  (w' = w with every
+//                                                              byte bit-reversed, so bit 7-p of
+//                                                              byte j is haplotype 8j+p again)
+// The two operands scale the same haplotype by 2^p and 2^(7-p): every (alt, alt) product is 2^7,
+// the int32 accumulator holds n11 * 128 exactly, and the epilogue shifts it back.  The haplotype
+// ORDER inside a chunk is permuted by this, identically for both operands -- a dot product does
+// not care.  (All LOPs: the ALU pipe issues them at 64 lanes/clk/SM.)
+template <bool COLUMN>
+__device__ __forceinline__ uint4 widen4(uint32_t w, int e) {   // e = 0: p = 0..3, e = 1: p = 4..7
     uint4 o;
-    o.x = (w << s0) & 0x80808080u;
-    o.y = (w << (s0 + 1)) & 0x80808080u;
-    o.z = (w << (s0 + 2)) & 0x80808080u;
-    o.w = (w << (s0 + 3)) & 0x80808080u;
+    if (!COLUMN) {
+        o.x = w & (0x01010101u << (4 * e));     o.y = w & (0x01010101u << (4 * e + 1));
+        o.z = w & (0x01010101u << (4 * e + 2)); o.w = w & (0x01010101u << (4 * e + 3));
+    } else {
+        o.x = w & (0x80808080u >> (4 * e));     o.y = w & (0x80808080u >> (4 * e + 1));
+        o.z = w & (0x80808080u >> (4 * e + 2)); o.w = w & (0x80808080u >> (4 * e + 3));
+    }
     return o;
 }
 // One variant-row of a chunk: 128 bits -> 8 x 16-byte units at the 128B-swizzled positions
 // (unit j of row r lives at j ^ (r & 7)); a quarter-warp's STS.128 then covers all 32 banks.
+template <bool COLUMN>
 __device__ __forceinline__ void expand_row(uint8_t *row_base, int r7, const uint4 &b) {
     const uint32_t w[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        *reinterpret_cast<uint4 *>(row_base + (((2 * q) ^ r7) << 4)) = widen4(w[q], 0);
-        *reinterpret_cast<uint4 *>(row_base + (((2 * q + 1) ^ r7) << 4)) = widen4(w[q], 4);
+        *reinterpret_cast<uint4 *>(row_base + (((2 * q) ^ r7) << 4)) = widen4<COLUMN>(w[q], 0);
+        *reinterpret_cast<uint4 *>(row_base + (((2 * q + 1) ^ r7) << 4)) = widen4<COLUMN>(w[q], 1);
     }
 }
-constexpr int ACC_SHIFT = 14;   // 0x80 * 0x80 = 2^14 per (alt, alt) haplotype
+constexpr int ACC_SHIFT = 7;   // 2^p * 2^(7-p) = 2^7 per (alt, alt) haplotype
 
 // ------------------------------------------------------------------------------------------ GEMM + epilogue
 struct MmaArgs {
-    const uint4 *bits; int32_t kc_count;
+    const uint4 *bits, *bits_rev; int32_t kc_count;
     const VarFreq *freq_rows; FinalCtx fc;
-    const int2 *tiles;
+    const int2 *tiles; int32_t n_tiles;
     int64_t v; int measure, has_thres, thres_e4;
     uint32_t *packed; int32_t *n11;
     FixupSink fix;
     int32_t *error_flag;
+    unsigned long long *trace;   // optional [256]: globaltimer stamps of CTA 0 (diagnostics)
+    int dbg;                     // diagnostics: 1 = skip the widening stores (results invalid)
 };
+
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
+constexpr int N_WIDEN_WARPS = 8, N_WIDEN_GROUPS = 2, N_EPI_WARPS = 8;   // groups widen alternate chunks
+constexpr int WIDEN_GROUP_WARPS = N_WIDEN_WARPS / N_WIDEN_GROUPS;
+// Warp roles, aligned to warpgroups (4 warps) so that setmaxnreg can move registers between them:
+//   warps 0-3   producer (0), MMA issuer (1), two spare warps      -> 40 registers
+//   warps 4-11  wideners                                           -> 48 registers
+//   warps 12-19 epilogue (fp64 heavy, pairs interleaved)            -> 168 registers (the pool is the CTA's own 640 x 96: 128*56 + 256*48 freed >= 256*72 needed)
+constexpr int FIRST_WIDEN_WARP = 4, FIRST_EPI_WARP = FIRST_WIDEN_WARP + N_WIDEN_WARPS;
+constexpr int MMA_THREADS = 32 * (FIRST_EPI_WARP + N_EPI_WARPS);   // 640
+constexpr int EPI_PITCH = 17;                                          // words per staged row (bank-conflict-free)
 
 template <int N> struct MmaCfg {
     static constexpr int ROWS = MMA_M + N;                    // variant-rows widened per chunk
-    static constexpr int OP_STAGES = 2;                       // widened operand tiles (SM-local producer: shallow)
+    static constexpr int OP_STAGES = N <= 128 ? 3 : 2;        // widened operand tiles (SM-local producer)
     static constexpr int OP_BYTES = ROWS * KCHUNK;
-    static constexpr int BIT_STAGES = N <= 64 ? 6 : 8;        // bit blocks in flight from L2 (latency: deep)
+    static constexpr int BIT_STAGES = 8;                      // bit blocks in flight from L2 (latency: deep)
     static constexpr int BIT_BYTES = ROWS * 16;
-    static constexpr int TMEM_COLS = N < 32 ? 32 : N;
-    static constexpr int CTAS_PER_SM = N <= 64 ? 3 : (N <= 128 ? 2 : 1);
-    static constexpr int N_BARS = 2 * OP_STAGES + 2 * BIT_STAGES + 1;
+    static constexpr int TMEM_COLS = 2 * N;                   // two accumulators
+    static constexpr int N_BARS = 2 * OP_STAGES + 2 * BIT_STAGES + 4;
+    static constexpr int EPI_BYTES = N_EPI_WARPS * 32 * EPI_PITCH * 4;
     static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)OP_STAGES * OP_BYTES + (size_t)BIT_STAGES * BIT_BYTES +
-                                   N * sizeof(VarFreq) + N_BARS * 8 + 64;
+                                   2 * N * sizeof(VarFreq) + EPI_BYTES + N_BARS * 8 + 64;
 };
-constexpr int N_WORKER_WARPS = 8;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 
-template <int N>
-__global__ void __launch_bounds__(MMA_THREADS, MmaCfg<N>::CTAS_PER_SM)
+template <int N, bool WANT_N11>
+__global__ void __launch_bounds__(MMA_THREADS, 1)
 triangle_mma_kernel(const MmaArgs A) {
     using Cfg = MmaCfg<N>;
     extern __shared__ uint8_t smem_raw[];
@@ -200,23 +246,22 @@ triangle_mma_kernel(const MmaArgs A) {
     uint8_t *smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);      // swizzle-128B needs 1 KB alignment
     uint8_t *op_s = smem;                                                        // [OP_STAGES][ROWS][128 B]
     uint8_t *bit_s = smem + Cfg::OP_STAGES * Cfg::OP_BYTES;                      // [BIT_STAGES][ROWS][16 B]
-    VarFreq *fb_s = reinterpret_cast<VarFreq *>(bit_s + Cfg::BIT_STAGES * Cfg::BIT_BYTES);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(fb_s + N);
+    VarFreq *fb_s = reinterpret_cast<VarFreq *>(bit_s + Cfg::BIT_STAGES * Cfg::BIT_BYTES);   // [2][N]
+    uint32_t *epi_s = reinterpret_cast<uint32_t *>(fb_s + 2 * N);                // [N_EPI_WARPS][32][EPI_PITCH]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(epi_s) + Cfg::EPI_BYTES);
     const uint32_t op_full = smem_u32(bars), op_empty = op_full + 8 * Cfg::OP_STAGES;
     const uint32_t bit_full = op_empty + 8 * Cfg::OP_STAGES, bit_empty = bit_full + 8 * Cfg::BIT_STAGES;
-    const uint32_t tmem_full_bar = bit_empty + 8 * Cfg::BIT_STAGES;
+    const uint32_t tmem_full = bit_empty + 8 * Cfg::BIT_STAGES, tmem_empty = tmem_full + 16;
     uint32_t *tmem_ptr_s = reinterpret_cast<uint32_t *>(bars + Cfg::N_BARS);
     volatile int *abort_s = reinterpret_cast<volatile int *>(tmem_ptr_s + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int2 tile = A.tiles[blockIdx.x];
-    const int64_t r0 = (int64_t)tile.x * MMA_M, c0 = (int64_t)tile.y * N;
     const int kc_count = A.kc_count;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::OP_STAGES; ++s) { mbar_init(op_full + 8 * s, N_WORKER_WARPS); mbar_init(op_empty + 8 * s, 1); }
-        for (int s = 0; s < Cfg::BIT_STAGES; ++s) { mbar_init(bit_full + 8 * s, 1); mbar_init(bit_empty + 8 * s, N_WORKER_WARPS); }
-        mbar_init(tmem_full_bar, 1);
+        for (int s = 0; s < Cfg::OP_STAGES; ++s) { mbar_init(op_full + 8 * s, WIDEN_GROUP_WARPS); mbar_init(op_empty + 8 * s, 1); }
+        for (int s = 0; s < Cfg::BIT_STAGES; ++s) { mbar_init(bit_full + 8 * s, 1); mbar_init(bit_empty + 8 * s, WIDEN_GROUP_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + 8 * s, 1); mbar_init(tmem_empty + 8 * s, N_EPI_WARPS); }
         *abort_s = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -225,141 +270,239 @@ triangle_mma_kernel(const MmaArgs A) {
                      :: "r"(smem_u32(tmem_ptr_s)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < N; i += MMA_THREADS) fb_s[i] = A.freq_rows[c0 + i];   // column variants
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_acc = *tmem_ptr_s;
+    const uint32_t tmem_base = *tmem_ptr_s;
+    if (A.trace && blockIdx.x == 0 && threadIdx.x == 0) A.trace[0] = gtime();   // prologue done
 
     if (warp == 0) {
         // ===== producer: bit blocks L2 -> shared memory ring (2 KB for the row panel + 16*N B for the columns)
-        if (lane == 0) {
+        // The whole warp runs the loop; one elected lane issues the copies.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        uint32_t g = 0;
+        for (int t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
+            const int2 tile = A.tiles[t];
+            const int64_t c0 = (int64_t)tile.y * N;
             const uint4 *a_src = A.bits + (int64_t)tile.x * kc_count * 128;
-            for (int kc = 0; kc < kc_count; ++kc) {
-                const int s = kc % Cfg::BIT_STAGES, it = kc / Cfg::BIT_STAGES;
-                if (!mbar_wait(bit_empty + 8 * s, (it & 1) ^ 1, abort_s, A.error_flag)) break;
+            for (int kc = 0; kc < kc_count; ++kc, ++g) {
+                const uint32_t s = g % Cfg::BIT_STAGES, it = g / Cfg::BIT_STAGES;
+                if (!mbar_wait(bit_empty + 8 * s, (it & 1) ^ 1, abort_s, A.error_flag)) goto done;
                 const uint32_t bar = bit_full + 8 * s;
-                mbar_arrive_expect_tx(bar, Cfg::BIT_BYTES);
                 const uint32_t dst = smem_u32(bit_s + s * Cfg::BIT_BYTES);
-                bulk_g2s(dst, a_src + (int64_t)kc * 128, MMA_M * 16, bar);
+                if (elect_one()) {
+                    if (A.trace && blockIdx.x == 0 && g < 48) A.trace[128 + g] = gtime();
+                    mbar_arrive_expect_tx(bar, Cfg::BIT_BYTES);
+                    bulk_g2s(dst, a_src + (int64_t)kc * 128, MMA_M * 16, bar);
 #pragma unroll
-                for (int part = 0; part < (N + 127) / 128; ++part) {
-                    const int64_t crow = c0 + part * 128;                 // first column variant of this part
-                    const int rows_here = N < 128 ? N : 128;
-                    bulk_g2s(dst + (MMA_M + part * 128) * 16, A.bits + ((crow >> 7) * kc_count + kc) * 128 + (crow & 127),
-                             rows_here * 16, bar);
+                    for (int part = 0; part < (N + 127) / 128; ++part) {
+                        const int64_t crow = c0 + part * 128;             // first column variant of this part
+                        const int rows_here = N < 128 ? N : 128;
+                        bulk_g2s(dst + (MMA_M + part * 128) * 16, A.bits_rev + ((crow >> 7) * kc_count + kc) * 128 + (crow & 127),
+                                 rows_here * 16, bar);
+                    }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(MMA_M, N);
-            bool ok = true;
-            for (int kc = 0; kc < kc_count; ++kc) {
-                const int s = kc % Cfg::OP_STAGES, it = kc / Cfg::OP_STAGES;
-                ok = mbar_wait(op_full + 8 * s, it & 1, abort_s, A.error_flag);
-                if (!ok) break;
+        // ===== MMA issuer: warp-uniform loop, one elected lane issues
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        constexpr uint32_t idesc = make_idesc(MMA_M, N);
+        uint32_t g = 0, tl = 0;
+        for (int t = blockIdx.x; t < A.n_tiles; t += gridDim.x, ++tl) {
+            const uint32_t buf = tl & 1;
+            if (!mbar_wait(tmem_empty + 8 * buf, ((tl >> 1) & 1) ^ 1, abort_s, A.error_flag)) goto done;   // epilogue drained it
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + buf * N;
+            for (int kc = 0; kc < kc_count; ++kc, ++g) {
+                const uint32_t s = g % Cfg::OP_STAGES, it = g / Cfg::OP_STAGES;
+                if (!mbar_wait(op_full + 8 * s, it & 1, abort_s, A.error_flag)) goto done;
                 tc_fence_after();
                 const uint32_t sa = smem_u32(op_s + s * Cfg::OP_BYTES);
                 const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + PANEL_BYTES);
+                if (elect_one()) {
+                    if (A.trace && blockIdx.x == 0 && g < 48) A.trace[64 + g] = gtime();
 #pragma unroll
-                for (int k = 0; k < KCHUNK / MMA_K; ++k)     // +32 B along K inside the swizzle atom = +2 encoded
-                    umma_i8(tmem_acc, da + 2 * k, db + 2 * k, idesc, (uint32_t)((kc | k) != 0));
-                umma_commit(op_empty + 8 * s);                // stage reusable once these MMAs have read it
+                    for (int k = 0; k < KCHUNK / MMA_K; ++k)     // +32 B along K inside the swizzle atom = +2 encoded
+                        umma_i8(tmem_acc, da + 2 * k, db + 2 * k, idesc, (uint32_t)((kc | k) != 0));
+                    umma_commit(op_empty + 8 * s);                // stage reusable once these MMAs have read it
+                    if (kc == kc_count - 1) umma_commit(tmem_full + 8 * buf);   // accumulator complete
+                }
+                __syncwarp();
             }
-            if (ok) umma_commit(tmem_full_bar);               // accumulator complete
+        }
+    } else if (warp < FIRST_WIDEN_WARP) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // spare warps: hand their registers over and wait
+    } else if (warp < FIRST_EPI_WARP) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        // ===== wideners: bit rows -> swizzled 0x00/0x80 operand bytes
+        const int group = (warp - FIRST_WIDEN_WARP) / WIDEN_GROUP_WARPS;         // chunks g with g % groups == group are ours
+        const int wt = ((warp - FIRST_WIDEN_WARP) % WIDEN_GROUP_WARPS) * 32 + lane;   // 0..127: rows wt, wt+128, (wt+256)
+        constexpr int GT = 32 * WIDEN_GROUP_WARPS;
+        constexpr int RPT = Cfg::ROWS / GT + (Cfg::ROWS % GT != 0);   // rows per thread
+        uint32_t g = 0;
+        for (int t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
+            for (int kc = 0; kc < kc_count; ++kc, ++g) {
+                if ((int)(g % N_WIDEN_GROUPS) != group) continue;
+                const uint32_t sb = g % Cfg::BIT_STAGES, itb = g / Cfg::BIT_STAGES;
+                const uint32_t so = g % Cfg::OP_STAGES, ito = g / Cfg::OP_STAGES;
+                const bool tr = A.trace && blockIdx.x == 0 && g == 20 && wt == 0;
+                long long c0k = 0, c1k = 0, c2k = 0, c3k = 0, c4k = 0, c5k = 0;
+                if (tr) c0k = clock64();
+                if (!mbar_wait(bit_full + 8 * sb, itb & 1, abort_s, A.error_flag)) goto done;
+                if (A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[192 + g] = gtime();
+                if (tr) c1k = clock64();
+                const uint4 *bsrc = reinterpret_cast<const uint4 *>(bit_s + sb * Cfg::BIT_BYTES);
+                uint4 b[RPT];
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                    const int row = wt + i * GT;
+                    b[i] = row < Cfg::ROWS ? bsrc[row] : make_uint4(0, 0, 0, 0);
+                }
+                if (!mbar_wait(op_empty + 8 * so, (ito & 1) ^ 1, abort_s, A.error_flag)) goto done;
+                if (tr) c2k = clock64();
+                uint8_t *ops = op_s + so * Cfg::OP_BYTES;
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                    const int row = wt + i * GT;
+                    if (row < MMA_M) expand_row<false>(ops + row * KCHUNK, wt & 7, b[i]);          // row operand
+                    else if (row < Cfg::ROWS) expand_row<true>(ops + row * KCHUNK, wt & 7, b[i]);   // column operand
+                }
+                if (tr) c3k = clock64();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05
+                if (tr) c4k = clock64();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(op_full + 8 * so); mbar_arrive(bit_empty + 8 * sb); }
+                if (tr) { c5k = clock64(); A.trace[240] = c1k - c0k; A.trace[241] = c2k - c1k; A.trace[242] = c3k - c2k; A.trace[243] = c4k - c3k; A.trace[244] = c5k - c4k; }
+                if (A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[8 + g] = gtime();
+            }
         }
     } else {
-        // ===== workers, phase 1: widen bit rows into the swizzled operand tile
-        const int wt = (warp - 2) * 32 + lane;                // 0..255
-        bool ok = true;
-        for (int kc = 0; kc < kc_count && ok; ++kc) {
-            const int sb = kc % Cfg::BIT_STAGES, itb = kc / Cfg::BIT_STAGES;
-            const int so = kc % Cfg::OP_STAGES, ito = kc / Cfg::OP_STAGES;
-            ok = mbar_wait(bit_full + 8 * sb, itb & 1, abort_s, A.error_flag);
-            if (!ok) break;
-            const uint4 *bsrc = reinterpret_cast<const uint4 *>(bit_s + sb * Cfg::BIT_BYTES);
-            uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
-            if (wt < Cfg::ROWS) b0 = bsrc[wt];
-            if (Cfg::ROWS > 256 && wt + 256 < Cfg::ROWS) b1 = bsrc[wt + 256];
-            ok = mbar_wait(op_empty + 8 * so, (ito & 1) ^ 1, abort_s, A.error_flag);
-            if (!ok) break;
-            uint8_t *ops = op_s + so * Cfg::OP_BYTES;
-            if (wt < Cfg::ROWS) expand_row(ops + wt * KCHUNK, wt & 7, b0);
-            if (Cfg::ROWS > 256 && wt + 256 < Cfg::ROWS) expand_row(ops + (wt + 256) * KCHUNK, wt & 7, b1);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(op_full + 8 * so); mbar_arrive(bit_empty + 8 * sb); }
-        }
-        // ===== workers, phase 2: epilogue.  Warp w may only touch TMEM lanes 32*(w%4) .. +31
-        const int quad = warp & 3, half = (warp - 2) >> 2;
-        const int64_t r = r0 + quad * 32 + lane;
-        if (ok) ok = mbar_wait(tmem_full_bar, 0, abort_s, A.error_flag);
-        tc_fence_after();
-        if (ok) {
+        // ===== epilogue.  Warp w may only touch TMEM lanes 32*(w%4) .. +31
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+        const int ew = warp - FIRST_EPI_WARP;                     // 0..7
+        const int quad = warp & 3, half = ew >> 2;
+        const int et = ew * 32 + lane;                            // 0..255
+        uint32_t *stage = epi_s + ew * 32 * EPI_PITCH;
+        const uint32_t m_shift = A.measure == LDX_MEASURE_R2 ? 0u : (uint32_t)LDX_DP_SHIFT;
+        const uint32_t thres = A.has_thres ? (uint32_t)A.thres_e4 : 0u;      // rounded values are >= 0: 0 flags nothing
+        uint32_t tl = 0;
+        for (int t = blockIdx.x; t < A.n_tiles; t += gridDim.x, ++tl) {
+            const uint32_t buf = tl & 1;
+            const int2 tile = A.tiles[t];
+            const int64_t r0 = (int64_t)tile.x * MMA_M, c0 = (int64_t)tile.y * N;
+            VarFreq *fb = fb_s + buf * N;
+            for (int i = et; i < N; i += 32 * N_EPI_WARPS) fb[i] = A.freq_rows[c0 + i];     // column variants
+            asm volatile("bar.sync 1, %0;" :: "n"(32 * N_EPI_WARPS) : "memory");
+            const int64_t r = r0 + quad * 32 + lane;
             const VarFreq fa = A.freq_rows[r];
-            const int64_t rbase = r * (r - 1) / 2;
-            const int64_t warp_rmax = r0 + quad * 32 + 31;
+            if (!mbar_wait(tmem_full + 8 * buf, (tl >> 1) & 1, abort_s, A.error_flag, 128)) goto done;
+            tc_fence_after();
+            if (A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[1 + 2 * tl] = gtime();   // accumulator ready
+            const uint32_t tmem_acc = tmem_base + buf * N + ((uint32_t)(quad * 32) << 16);
+            const int64_t warp_r0 = r0 + quad * 32, warp_rmax = warp_r0 + 31;
 #pragma unroll 1
             for (int c = half * (N / 2); c < (half + 1) * (N / 2); c += 16) {
                 if (c0 + c >= warp_rmax || c0 + c >= A.v) break;        // warp-uniform: nothing below the diagonal
                 uint32_t acc[16];
-                tmem_ld16(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, acc);
-                if (r < A.v) {
+                tmem_ld16(tmem_acc + (uint32_t)c, acc);
+                uint32_t ties = 0;
+                uint32_t word[16];      // kept in registers until every fb[] load of a group has issued:
+                                        // a shared-memory store in between would serialise the pairs
+                // four pairs at a time: enough independent fp64 chains to cover the pipe latency
+                // without pushing the register allocator into spills
+#pragma unroll
+                for (int j0 = 0; j0 < 16; j0 += 4) {
+#pragma unroll
+                    for (int j = j0; j < j0 + 4; ++j) {
+                        const int32_t cnt = (int32_t)(acc[j] >> ACC_SHIFT);
+                        const PairFinal f = finalise_pair(cnt, fa, fb[c + j], A.fc);    // var_1 = row, var_2 = column
+                        uint32_t w = f.packed;
+                        w |= (((w >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;   // no branch
+                        ties |= ((w >> 14) & 1u) << j;
+                        word[j] = w;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) stage[lane * EPI_PITCH + j] = word[j];
+                if (WANT_N11) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int64_t col = c0 + c + j;
-                        if (col < r) {
-                            const VarFreq fb = fb_s[c + j];
-                            const int32_t cnt = (int32_t)(acc[j] >> ACC_SHIFT);
-                            const PairFinal f = finalise_pair(cnt, fa, fb, A.fc);   // var_1 = row, var_2 = column
-                            uint32_t word = f.packed;
-                            if (A.has_thres && measure_e4(word, A.measure) < A.thres_e4) word |= LDX_BELOW_THRES;
-                            const int64_t o = rbase + col;
-                            if (A.packed) {
-                                A.packed[o] = word;
-                                if (word & LDX_R2_NEARTIE) fixup_append(A.fix, (uint64_t)o, cnt, fa.n1, fb.n1, word);
-                            }
-                            if (A.n11) A.n11[o] = cnt;
-                        }
+                        if (r < A.v && col < r) A.n11[r * (r - 1) / 2 + col] = (int32_t)(acc[j] >> ACC_SHIFT);
                     }
                 }
+                __syncwarp();
+                // transposed write-out: 16 lanes cover the 16 columns of one row (64 contiguous bytes)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int rl = 2 * i + (lane >> 4), cl = lane & 15;
+                    const int64_t rg = warp_r0 + rl, cg = c0 + c + cl;
+                    const uint32_t word = stage[rl * EPI_PITCH + cl];
+                    if (rg < A.v && cg < rg) A.packed[rg * (rg - 1) / 2 + cg] = word;
+                }
+                __syncwarp();
+                if (__any_sync(0xffffffffu, ties != 0 && r < A.v)) {     // rare: r2 next to a rounding tie
+                    uint32_t again[16];
+                    tmem_ld16(tmem_acc + (uint32_t)c, again);            // counts are still in TMEM
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int64_t col = c0 + c + j;
+                        if (((ties >> j) & 1u) && r < A.v && col < r)
+                            fixup_append(A.fix, (uint64_t)(r * (r - 1) / 2 + col), (int32_t)(again[j] >> ACC_SHIFT), fa.n1,
+                                         fb[c + j].n1, stage[lane * EPI_PITCH + j]);
+                    }
+                }
+                __syncwarp();
             }
+            // this warp's TMEM reads of the tile are complete: hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + 8 * buf);
+            if (A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[2 + 2 * tl] = gtime();       // epilogue of this tile done
         }
     }
+done:
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_acc), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
     }
 }
 
 bool triangle_mma_available() { return true; }
 
-template <int N>
-static int launch_tiles(ldx_ctx *ctx, const MmaArgs &A, int n_tiles) {
+template <int N, bool WANT_N11>
+static int launch_tiles_t(ldx_ctx *ctx, const MmaArgs &A) {
     static bool attr_set = false;
     if (!attr_set) {
-        LDX_CUDA(cudaFuncSetAttribute(triangle_mma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmaCfg<N>::SMEM));
+        LDX_CUDA(cudaFuncSetAttribute(triangle_mma_kernel<N, WANT_N11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmaCfg<N>::SMEM));
         attr_set = true;
     }
-    triangle_mma_kernel<N><<<n_tiles, MMA_THREADS, MmaCfg<N>::SMEM, ctx->stream>>>(A);
+    const int grid = A.n_tiles < ctx->sm_count ? A.n_tiles : ctx->sm_count;     // persistent: one CTA per SM
+    triangle_mma_kernel<N, WANT_N11><<<grid, MMA_THREADS, MmaCfg<N>::SMEM, ctx->stream>>>(A);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
     return LDX_OK;
+}
+template <int N>
+static int launch_tiles(ldx_ctx *ctx, const MmaArgs &A) {
+    return A.n11 ? launch_tiles_t<N, true>(ctx, A) : launch_tiles_t<N, false>(ctx, A);
 }
 
 int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int measure, int has_thres,
                         int thres_e4, uint32_t *d_packed, int32_t *d_n11) {
     if (v < 2) return LDX_OK;
     ldx_ctx *ctx = s->ctx;
-    if (s->n_hap > (1 << 17)) return set_error(LDX_ERR_ARG, "tcgen05 engine: more than 2^17 haplotypes would overflow the int32 accumulator");
+    if (!d_packed) return set_error(LDX_ERR_ARG, "tcgen05 engine: the packed output is required");
+    if (s->n_hap > (1 << 23)) return set_error(LDX_ERR_ARG, "tcgen05 engine: more than 2^23 haplotypes would overflow the int32 accumulator");
     const int kc_count = (s->n_hap + KCHUNK - 1) / KCHUNK;     // stride_words*64 >= kc_count*128 (rows are 128 B multiples)
     const int64_t v_pad = (v + 255) / 256 * 256;
     const int64_t panels = v_pad / MMA_M;
-    // tile width: narrow tiles fill the SMs for small matrices, wide tiles amortise the widening work
+    // tile width: narrow tiles give every SM several tiles to overlap for small matrices, wide
+    // tiles amortise the widening work for large ones
     int n_tile = ctx->mma_tile_n;
     if (n_tile == 0) n_tile = v <= 4096 ? 64 : 128;
     // ---- tile list (cached): every 128 x N tile holding at least one pair with row > col, row-panel major
@@ -371,8 +514,9 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
         n_tiles += (size_t)((rmax + n_tile - 1) / n_tile);
     }
     if (n_tiles == 0) return LDX_OK;
+    if (n_tiles > 0x7fffffffull) return set_error(LDX_ERR_ARG, "tcgen05 engine: too many tiles");
     const size_t tile_bytes = n_tiles * sizeof(int2);
-    const size_t need = bits_bytes + freq_bytes + tile_bytes + 1024;
+    const size_t need = 2 * bits_bytes + freq_bytes + tile_bytes + 1024;
     if (ctx->mma_ops_bytes < need) {
         if (ctx->d_mma_ops) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_mma_ops); ctx->d_mma_ops = nullptr; ctx->mma_ops_bytes = 0; }
         if (cudaMalloc(&ctx->d_mma_ops, need) != cudaSuccess) { cudaGetLastError(); return set_error(LDX_ERR_NOMEM, "tcgen05 operand scratch allocation failed"); }
@@ -380,10 +524,12 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
         ctx->mma_tiles_v = -1;
     }
     uint8_t *base = reinterpret_cast<uint8_t *>(ctx->d_mma_ops);
-    uint4 *d_bits = reinterpret_cast<uint4 *>(base);
-    VarFreq *d_freq_rows = reinterpret_cast<VarFreq *>(base + bits_bytes);
-    int2 *d_tiles = reinterpret_cast<int2 *>(base + bits_bytes + freq_bytes);
+    uint4 *d_bits = reinterpret_cast<uint4 *>(base), *d_bits_rev = reinterpret_cast<uint4 *>(base + bits_bytes);
+    VarFreq *d_freq_rows = reinterpret_cast<VarFreq *>(base + 2 * bits_bytes);
+    int2 *d_tiles = reinterpret_cast<int2 *>(base + 2 * bits_bytes + freq_bytes);
     if (ctx->mma_tiles_v != v || ctx->mma_tiles_n != n_tile) {          // the list depends on (v, N) only
+        // Longest tiles first is not needed (all tiles cost the same K loop); the list is ordered so
+        // that the tiles a wave of CTAs works on share row panels and neighbouring column blocks in L2.
         std::vector<int2> tiles;
         tiles.reserve(n_tiles);
         for (int64_t bi = 0; bi < (v + MMA_M - 1) / MMA_M; ++bi) {
@@ -397,20 +543,23 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
 
     dim3 ggrid((unsigned)((v_pad + 255) / 256), (unsigned)kc_count);
     gather_bits_kernel<<<ggrid, 256, 0, ctx->stream>>>(s->d_planes, s->d_mask, s->stride_words, d_rows, v, v_pad, kc_count,
-                                                       s->d_freq, d_bits, d_freq_rows);
+                                                       s->d_freq, d_bits, d_bits_rev, d_freq_rows);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
 
     MmaArgs A;
-    A.bits = d_bits; A.kc_count = kc_count; A.freq_rows = d_freq_rows; A.fc = s->fc; A.tiles = d_tiles;
+    A.bits = d_bits; A.bits_rev = d_bits_rev; A.kc_count = kc_count; A.freq_rows = d_freq_rows; A.fc = s->fc; A.tiles = d_tiles;
+    A.n_tiles = (int32_t)n_tiles;
     A.v = v; A.measure = measure; A.has_thres = has_thres; A.thres_e4 = thres_e4;
     A.packed = d_packed; A.n11 = d_n11;
     A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity};
     A.error_flag = reinterpret_cast<int32_t *>(ctx->d_fix_count + 1);
+    A.trace = ctx->d_trace;
+    A.dbg = getenv("LDX_DEBUG_MMA") ? atoi(getenv("LDX_DEBUG_MMA")) : 0;
     switch (n_tile) {
-        case 64: return launch_tiles<64>(ctx, A, (int)n_tiles);
-        case 128: return launch_tiles<128>(ctx, A, (int)n_tiles);
-        case 256: return launch_tiles<256>(ctx, A, (int)n_tiles);
+        case 64: return launch_tiles<64>(ctx, A);
+        case 128: return launch_tiles<128>(ctx, A);
+        case 256: return launch_tiles<256>(ctx, A);
         default: return set_error(LDX_ERR_ARG, "tcgen05 tile width must be 64, 128 or 256");
     }
 }

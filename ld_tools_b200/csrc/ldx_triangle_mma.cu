@@ -105,6 +105,25 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64
                  "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// The same with the A operand (row variants) read from TENSOR MEMORY: lane = row, 32-bit column c holds
+// K elements 4c..4c+3.  Shared-memory bandwidth is what bounds this kernel (the widened operands are
+// written once and read once per chunk), and this variant takes A's write AND read off that port.
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 consecutive 32-bit columns of this thread's TMEM lane (lane 32*(warp%4) + laneid).
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+                 "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+                    "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+                    "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+                 : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 // mbarrier arrives once every previously issued tcgen05.mma of this thread has completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
@@ -210,8 +229,7 @@ struct MmaArgs {
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
-constexpr int N_WIDEN_WARPS = 8, N_WIDEN_GROUPS = 2, N_EPI_WARPS = 8;   // groups widen alternate chunks
-constexpr int WIDEN_GROUP_WARPS = N_WIDEN_WARPS / N_WIDEN_GROUPS;
+constexpr int N_WIDEN_WARPS = 8, N_EPI_WARPS = 8;   // wideners: 4 warps for the row operand (TMEM), 4 for the column operand (smem)
 // Warp roles, aligned to warpgroups (4 warps) so that setmaxnreg can move registers between them:
 //   warps 0-3   producer (0), MMA issuer (1), two spare warps      -> 40 registers
 //   warps 4-11  wideners                                           -> 48 registers
@@ -222,11 +240,15 @@ constexpr int EPI_PITCH = 17;                                          // words 
 
 template <int N> struct MmaCfg {
     static constexpr int ROWS = MMA_M + N;                    // variant-rows widened per chunk
-    static constexpr int OP_STAGES = N <= 128 ? 3 : 2;        // widened operand tiles (SM-local producer)
-    static constexpr int OP_BYTES = ROWS * KCHUNK;
+    static constexpr int OP_STAGES = 3;                       // widened operand stages (A in TMEM, B in smem)
+    static constexpr int OP_BYTES = N * KCHUNK;               // B tile of one stage
     static constexpr int BIT_STAGES = 8;                      // bit blocks in flight from L2 (latency: deep)
     static constexpr int BIT_BYTES = ROWS * 16;
-    static constexpr int TMEM_COLS = 2 * N;                   // two accumulators
+    static constexpr int A_COLS = KCHUNK / 4;                 // TMEM columns of one A stage (32)
+    static constexpr int ACC_BUFS = N <= 128 ? 2 : 1;         // accumulators (512 TMEM columns in total)
+    static constexpr int TMEM_A0 = ACC_BUFS * N;              // first A column
+    static constexpr int TMEM_COLS = 512;
+    static_assert(TMEM_A0 + OP_STAGES * A_COLS <= 512, "TMEM budget");
     static constexpr int N_BARS = 2 * OP_STAGES + 2 * BIT_STAGES + 4;
     static constexpr int EPI_BYTES = N_EPI_WARPS * 32 * EPI_PITCH * 4;
     static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)OP_STAGES * OP_BYTES + (size_t)BIT_STAGES * BIT_BYTES +
@@ -244,7 +266,7 @@ triangle_mma_kernel(const MmaArgs A) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t *smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);      // swizzle-128B needs 1 KB alignment
-    uint8_t *op_s = smem;                                                        // [OP_STAGES][ROWS][128 B]
+    uint8_t *op_s = smem;                                                        // [OP_STAGES][N][128 B] column operand
     uint8_t *bit_s = smem + Cfg::OP_STAGES * Cfg::OP_BYTES;                      // [BIT_STAGES][ROWS][16 B]
     VarFreq *fb_s = reinterpret_cast<VarFreq *>(bit_s + Cfg::BIT_STAGES * Cfg::BIT_BYTES);   // [2][N]
     uint32_t *epi_s = reinterpret_cast<uint32_t *>(fb_s + 2 * N);                // [N_EPI_WARPS][32][EPI_PITCH]
@@ -259,8 +281,8 @@ triangle_mma_kernel(const MmaArgs A) {
     const int kc_count = A.kc_count;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::OP_STAGES; ++s) { mbar_init(op_full + 8 * s, WIDEN_GROUP_WARPS); mbar_init(op_empty + 8 * s, 1); }
-        for (int s = 0; s < Cfg::BIT_STAGES; ++s) { mbar_init(bit_full + 8 * s, 1); mbar_init(bit_empty + 8 * s, WIDEN_GROUP_WARPS); }
+        for (int s = 0; s < Cfg::OP_STAGES; ++s) { mbar_init(op_full + 8 * s, N_WIDEN_WARPS); mbar_init(op_empty + 8 * s, 1); }
+        for (int s = 0; s < Cfg::BIT_STAGES; ++s) { mbar_init(bit_full + 8 * s, 1); mbar_init(bit_empty + 8 * s, N_WIDEN_WARPS); }
         for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + 8 * s, 1); mbar_init(tmem_empty + 8 * s, N_EPI_WARPS); }
         *abort_s = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -311,21 +333,21 @@ triangle_mma_kernel(const MmaArgs A) {
         constexpr uint32_t idesc = make_idesc(MMA_M, N);
         uint32_t g = 0, tl = 0;
         for (int t = blockIdx.x; t < A.n_tiles; t += gridDim.x, ++tl) {
-            const uint32_t buf = tl & 1;
-            if (!mbar_wait(tmem_empty + 8 * buf, ((tl >> 1) & 1) ^ 1, abort_s, A.error_flag)) goto done;   // epilogue drained it
+            const uint32_t buf = tl % Cfg::ACC_BUFS;
+            if (!mbar_wait(tmem_empty + 8 * buf, ((tl / Cfg::ACC_BUFS) & 1) ^ 1, abort_s, A.error_flag)) goto done;   // epilogue drained it
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + buf * N;
             for (int kc = 0; kc < kc_count; ++kc, ++g) {
                 const uint32_t s = g % Cfg::OP_STAGES, it = g / Cfg::OP_STAGES;
                 if (!mbar_wait(op_full + 8 * s, it & 1, abort_s, A.error_flag)) goto done;
                 tc_fence_after();
-                const uint32_t sa = smem_u32(op_s + s * Cfg::OP_BYTES);
-                const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + PANEL_BYTES);
+                const uint64_t db = make_smem_desc(smem_u32(op_s + s * Cfg::OP_BYTES));
+                const uint32_t ta = tmem_base + Cfg::TMEM_A0 + s * Cfg::A_COLS;
                 if (elect_one()) {
                     if (A.trace && blockIdx.x == 0 && g < 48) A.trace[64 + g] = gtime();
 #pragma unroll
-                    for (int k = 0; k < KCHUNK / MMA_K; ++k)     // +32 B along K inside the swizzle atom = +2 encoded
-                        umma_i8(tmem_acc, da + 2 * k, db + 2 * k, idesc, (uint32_t)((kc | k) != 0));
+                    for (int k = 0; k < KCHUNK / MMA_K; ++k)     // K = 32: 8 TMEM columns of A, +32 B (= +2 encoded) of B
+                        umma_i8_ts(tmem_acc, ta + 8 * k, db + 2 * k, idesc, (uint32_t)((kc | k) != 0));
                     umma_commit(op_empty + 8 * s);                // stage reusable once these MMAs have read it
                     if (kc == kc_count - 1) umma_commit(tmem_full + 8 * buf);   // accumulator complete
                 }
@@ -337,45 +359,46 @@ triangle_mma_kernel(const MmaArgs A) {
     } else if (warp < FIRST_EPI_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         // ===== wideners: bit rows -> swizzled 0x00/0x80 operand bytes
-        const int group = (warp - FIRST_WIDEN_WARP) / WIDEN_GROUP_WARPS;         // chunks g with g % groups == group are ours
-        const int wt = ((warp - FIRST_WIDEN_WARP) % WIDEN_GROUP_WARPS) * 32 + lane;   // 0..127: rows wt, wt+128, (wt+256)
-        constexpr int GT = 32 * WIDEN_GROUP_WARPS;
-        constexpr int RPT = Cfg::ROWS / GT + (Cfg::ROWS % GT != 0);   // rows per thread
+        // warps 4-7: row operand -> TMEM (lane = row; warp%4 is the TMEM quadrant the warp may write);
+        // warps 8-11: column operand -> 128B-swizzled shared memory.  One row per thread and chunk
+        // (two for N = 256, fewer for N = 64).
+        const bool is_a = warp < FIRST_WIDEN_WARP + 4;
+        const int wt = ((warp - FIRST_WIDEN_WARP) & 3) * 32 + lane;     // 0..127
+        constexpr int B_RPT = (N + 127) / 128;
         uint32_t g = 0;
         for (int t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
             for (int kc = 0; kc < kc_count; ++kc, ++g) {
-                if ((int)(g % N_WIDEN_GROUPS) != group) continue;
                 const uint32_t sb = g % Cfg::BIT_STAGES, itb = g / Cfg::BIT_STAGES;
                 const uint32_t so = g % Cfg::OP_STAGES, ito = g / Cfg::OP_STAGES;
-                const bool tr = A.trace && blockIdx.x == 0 && g == 20 && wt == 0;
-                long long c0k = 0, c1k = 0, c2k = 0, c3k = 0, c4k = 0, c5k = 0;
-                if (tr) c0k = clock64();
                 if (!mbar_wait(bit_full + 8 * sb, itb & 1, abort_s, A.error_flag)) goto done;
-                if (A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[192 + g] = gtime();
-                if (tr) c1k = clock64();
+                if (A.trace && blockIdx.x == 0 && g < 48 && wt == 0 && is_a) A.trace[192 + g] = gtime();
                 const uint4 *bsrc = reinterpret_cast<const uint4 *>(bit_s + sb * Cfg::BIT_BYTES);
-                uint4 b[RPT];
+                if (is_a) {
+                    const uint4 b = bsrc[wt];
+                    const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+                    uint32_t v[32];
 #pragma unroll
-                for (int i = 0; i < RPT; ++i) {
-                    const int row = wt + i * GT;
-                    b[i] = row < Cfg::ROWS ? bsrc[row] : make_uint4(0, 0, 0, 0);
-                }
-                if (!mbar_wait(op_empty + 8 * so, (ito & 1) ^ 1, abort_s, A.error_flag)) goto done;
-                if (tr) c2k = clock64();
-                uint8_t *ops = op_s + so * Cfg::OP_BYTES;
+                    for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int i = 0; i < RPT; ++i) {
-                    const int row = wt + i * GT;
-                    if (row < MMA_M) expand_row<false>(ops + row * KCHUNK, wt & 7, b[i]);          // row operand
-                    else if (row < Cfg::ROWS) expand_row<true>(ops + row * KCHUNK, wt & 7, b[i]);   // column operand
+                        for (int p = 0; p < 8; ++p) v[q * 8 + p] = w[q] & (0x01010101u << p);   // same byte order as expand_row<false>
+                    if (!mbar_wait(op_empty + 8 * so, (ito & 1) ^ 1, abort_s, A.error_flag)) goto done;
+                    tc_fence_after();
+                    tmem_st32(tmem_base + Cfg::TMEM_A0 + so * Cfg::A_COLS + ((uint32_t)(((warp - FIRST_WIDEN_WARP) & 3) * 32) << 16), v);
+                    tc_fence_before();
+                } else {
+                    uint4 b[B_RPT];
+#pragma unroll
+                    for (int i = 0; i < B_RPT; ++i) b[i] = (wt + i * 128 < N) ? bsrc[MMA_M + wt + i * 128] : make_uint4(0, 0, 0, 0);
+                    if (!mbar_wait(op_empty + 8 * so, (ito & 1) ^ 1, abort_s, A.error_flag)) goto done;
+                    uint8_t *ops = op_s + so * Cfg::OP_BYTES;
+#pragma unroll
+                    for (int i = 0; i < B_RPT; ++i)
+                        if (wt + i * 128 < N) expand_row<true>(ops + (wt + i * 128) * KCHUNK, wt & 7, b[i]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05
                 }
-                if (tr) c3k = clock64();
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05
-                if (tr) c4k = clock64();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(op_full + 8 * so); mbar_arrive(bit_empty + 8 * sb); }
-                if (tr) { c5k = clock64(); A.trace[240] = c1k - c0k; A.trace[241] = c2k - c1k; A.trace[242] = c3k - c2k; A.trace[243] = c4k - c3k; A.trace[244] = c5k - c4k; }
-                if (A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[8 + g] = gtime();
+                if (A.trace && blockIdx.x == 0 && g < 48 && wt == 0 && is_a) A.trace[8 + g] = gtime();
             }
         }
     } else {
@@ -389,15 +412,15 @@ triangle_mma_kernel(const MmaArgs A) {
         const uint32_t thres = A.has_thres ? (uint32_t)A.thres_e4 : 0u;      // rounded values are >= 0: 0 flags nothing
         uint32_t tl = 0;
         for (int t = blockIdx.x; t < A.n_tiles; t += gridDim.x, ++tl) {
-            const uint32_t buf = tl & 1;
+            const uint32_t buf = tl % Cfg::ACC_BUFS;
             const int2 tile = A.tiles[t];
             const int64_t r0 = (int64_t)tile.x * MMA_M, c0 = (int64_t)tile.y * N;
-            VarFreq *fb = fb_s + buf * N;
+            VarFreq *fb = fb_s + (tl & 1) * N;
             for (int i = et; i < N; i += 32 * N_EPI_WARPS) fb[i] = A.freq_rows[c0 + i];     // column variants
             asm volatile("bar.sync 1, %0;" :: "n"(32 * N_EPI_WARPS) : "memory");
             const int64_t r = r0 + quad * 32 + lane;
             const VarFreq fa = A.freq_rows[r];
-            if (!mbar_wait(tmem_full + 8 * buf, (tl >> 1) & 1, abort_s, A.error_flag, 128)) goto done;
+            if (!mbar_wait(tmem_full + 8 * buf, (tl / Cfg::ACC_BUFS) & 1, abort_s, A.error_flag, 128)) goto done;
             tc_fence_after();
             if (A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[1 + 2 * tl] = gtime();   // accumulator ready
             const uint32_t tmem_acc = tmem_base + buf * N + ((uint32_t)(quad * 32) << 16);

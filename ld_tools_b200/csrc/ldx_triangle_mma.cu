@@ -122,7 +122,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
                     "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
                     "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
                  : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 // mbarrier arrives once every previously issued tcgen05.mma of this thread has completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -214,12 +213,44 @@ __device__ __forceinline__ void expand_row(uint8_t *row_base, int r7, const uint
 }
 constexpr int ACC_SHIFT = 7;   // 2^p * 2^(7-p) = 2^7 per (alt, alt) haplotype
 
+// ------------------------------------------------------------------------------------------ screening arithmetic
+// The epilogue's fast path.  With complete biallelic data every quantity of calc_ld.py:33-90 is a
+// ratio of small integers:
+//     Dn = n11*N - n1a*n1b                  d  = Dn / N^2                       (calc_ld.py:50)
+//     m  = Dn > 0 ? min(n1a*n0b, n0a*n1b)   D' = |Dn| / m                       (calc_ld.py:63-76)
+//                 : min(n1a*n1b, n0a*n0b)
+//     den = n1a*n0a*n1b*n0b                 r2 = Dn^2 / den                     (calc_ld.py:86-88)
+// The integers are exact in fp64 (N <= 32768), so x = value * 10^4 is evaluated here to a relative
+// error below 2^-45 with ONE shared reciprocal, 1 / (m * den).  The reference rounds ITS OWN fp64
+// chain, whose distance from the exact ratio is bounded by the cancellation in f11 - p1*p2:
+// |x_ref - x_exact| <= 10^4 * 16 * 2^-53 * N^2 for r2 (half of that for D').  Whenever x is farther
+// than that bound (+1e-6) from every k + 1/2, Python's round(x_ref, 4) and the rounding of x agree,
+// and the packed word is final.  Otherwise -- and when Dn == 0 for two polymorphic variants, where
+// only the reference's own rounding errors decide between int 0 and 0.0 -- `slow` is set and the
+// caller redoes the pair with the reference's operation sequence (finalise_pair).
+// Monomorphic variants (den == 0) need no arithmetic: d is exactly 0 and the bound is exactly 0 in
+// the reference as well (calc_ld.py:68-69, :89-90): both int-0 flags.
+__device__ __forceinline__ double rcp_newton(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = __fma_rn(-x, y, 1.0);
+    e = __fma_rn(e, e, e);
+    y = __fma_rn(y, e, y);
+    e = __fma_rn(-x, y, 1.0);
+    return __fma_rn(y, e, y);
+}
+struct ColRec;
+__device__ __forceinline__ uint32_t fast_pair(int32_t n11, int32_t Nn, int32_t n1a, int32_t aN, int32_t cN, double da,
+                                              const ColRec &cr, double lim_dp, double lim_r2, bool &slow);
+
 // ------------------------------------------------------------------------------------------ GEMM + epilogue
 struct MmaArgs {
     const uint4 *bits, *bits_rev; int32_t kc_count;
     const VarFreq *freq_rows; FinalCtx fc;
     const int2 *tiles; int32_t n_tiles;
     int64_t v; int measure, has_thres, thres_e4;
+    int32_t n_sel;               // N = selected haplotypes
+    double lim_dp, lim_r2;       // 0.5 - guard band of the screening arithmetic (see fast_pair); <= 0 disables it
     uint32_t *packed; int32_t *n11;
     FixupSink fix;
     int32_t *error_flag;
@@ -229,22 +260,37 @@ struct MmaArgs {
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
-constexpr int N_WIDEN_WARPS = 8, N_EPI_WARPS = 8;   // wideners: 4 warps for the row operand (TMEM), 4 for the column operand (smem)
+constexpr int N_WIDEN_WARPS = 8, N_EPI_WARPS = 8;   // wideners: two teams of 4 warps taking alternate pipeline stages
+constexpr int WIDEN_TEAMS = 2, TEAM_WARPS = N_WIDEN_WARPS / WIDEN_TEAMS;
 // Warp roles, aligned to warpgroups (4 warps) so that setmaxnreg can move registers between them:
 //   warps 0-3   producer (0), MMA issuer (1), two spare warps      -> 40 registers
-//   warps 4-11  wideners                                           -> 48 registers
-//   warps 12-19 epilogue (fp64 heavy, pairs interleaved)            -> 168 registers (the pool is the CTA's own 640 x 96: 128*56 + 256*48 freed >= 256*72 needed)
+//   warps 4-11  wideners                                           -> 56 registers
+//   warps 12-19 epilogue (fp64 heavy, pairs interleaved)            -> 160 registers
+// The pool is the CTA's own 640 x 96 registers: setmaxnreg.inc BLOCKS until enough have been released,
+// so the budget must close: 128*(96-40) + 256*(96-56) = 17408 freed >= 256*(160-96) = 16384 needed.
+constexpr int REGS_LAUNCH = 96, REGS_CTRL = 40, REGS_WIDEN = 56, REGS_EPI = 160;
+static_assert(128 * (REGS_LAUNCH - REGS_CTRL) + 256 * (REGS_LAUNCH - REGS_WIDEN) >= 256 * (REGS_EPI - REGS_LAUNCH), "setmaxnreg budget");
 constexpr int FIRST_WIDEN_WARP = 4, FIRST_EPI_WARP = FIRST_WIDEN_WARP + N_WIDEN_WARPS;
 constexpr int MMA_THREADS = 32 * (FIRST_EPI_WARP + N_EPI_WARPS);   // 640
-constexpr int EPI_PITCH = 17;                                          // words per staged row (bank-conflict-free)
+constexpr int EPI_PITCH = 20;                                          // words per staged row: 16-byte aligned rows, conflict-free STS.128
+
+// Per column variant, what the screening arithmetic of the epilogue needs (one 16-byte broadcast load per pair).
+struct __align__(16) ColRec {
+    double prod;     // n1 * (N - n1), exact
+    int32_t n1;      // alt alleles under the mask
+    int32_t n1N;     // n1 * N
+};
 
 template <int N> struct MmaCfg {
     static constexpr int ROWS = MMA_M + N;                    // variant-rows widened per chunk
-    static constexpr int OP_STAGES = 3;                       // widened operand stages (A in TMEM, B in smem)
-    static constexpr int OP_BYTES = N * KCHUNK;               // B tile of one stage
-    static constexpr int BIT_STAGES = 8;                      // bit blocks in flight from L2 (latency: deep)
-    static constexpr int BIT_BYTES = ROWS * 16;
-    static constexpr int A_COLS = KCHUNK / 4;                 // TMEM columns of one A stage (32)
+    static constexpr int CH = 2;                              // 128-haplotype chunks per pipeline stage
+    static constexpr int B_ROWS = N < 128 ? N : 128;          // column variants per 128-row bit block
+    static constexpr int B_PARTS = (N + 127) / 128;
+    static constexpr int OP_STAGES = N <= 128 ? 3 : 2;        // widened operand stages (A in TMEM, B in smem)
+    static constexpr int OP_BYTES = N * KCHUNK * CH;          // B tile of one stage: CH swizzle atoms side by side
+    static constexpr int BIT_STAGES = N <= 128 ? 8 : 4;       // bit blocks in flight from L2 (latency: deep)
+    static constexpr int BIT_BYTES = ROWS * 16 * CH;
+    static constexpr int A_COLS = CH * KCHUNK / 4;            // TMEM columns of one A stage (64)
     static constexpr int ACC_BUFS = N <= 128 ? 2 : 1;         // accumulators (512 TMEM columns in total)
     static constexpr int TMEM_A0 = ACC_BUFS * N;              // first A column
     static constexpr int TMEM_COLS = 512;
@@ -252,8 +298,33 @@ template <int N> struct MmaCfg {
     static constexpr int N_BARS = 2 * OP_STAGES + 2 * BIT_STAGES + 4;
     static constexpr int EPI_BYTES = N_EPI_WARPS * 32 * EPI_PITCH * 4;
     static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)OP_STAGES * OP_BYTES + (size_t)BIT_STAGES * BIT_BYTES +
-                                   2 * N * sizeof(VarFreq) + EPI_BYTES + N_BARS * 8 + 64;
+                                   2 * N * sizeof(ColRec) + EPI_BYTES + N_BARS * 8 + 64;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
+
+__device__ __forceinline__ uint32_t fast_pair(int32_t n11, int32_t Nn, int32_t n1a, int32_t aN, int32_t cN, double da,
+                                              const ColRec &cr, double lim_dp, double lim_r2, bool &slow) {
+    const int32_t P = n1a * cr.n1;                       // n1a*n1b
+    const int32_t Dn = n11 * Nn - P;
+    const int32_t m_pos = min(aN, cr.n1N) - P;           // min(n1a*n0b, n0a*n1b)
+    const int32_t m_neg = min(P, cN - cr.n1N + P);       // min(n1a*n1b, n0a*n0b)
+    const int32_t m = Dn > 0 ? m_pos : m_neg;
+    const double aD = u32_to_double((uint32_t)abs(Dn));
+    const double md = u32_to_double((uint32_t)m);
+    const double den = __dmul_rn(da, cr.prod);
+    const double R = rcp_newton(__dmul_rn(md, den));     // garbage (inf/nan) when den == 0: masked below
+    const double D4 = __dmul_rn(aD, 1.0e4);
+    const double x_dp = __dmul_rn(__dmul_rn(D4, den), R);
+    const double x_r2 = __dmul_rn(__dmul_rn(__dmul_rn(D4, aD), md), R);
+    const double t_dp = __dadd_rn(x_dp, 4503599627370496.0), t_r2 = __dadd_rn(x_r2, 4503599627370496.0);
+    const double f_dp = __dsub_rn(x_dp, __dsub_rn(t_dp, 4503599627370496.0));
+    const double f_r2 = __dsub_rn(x_r2, __dsub_rn(t_r2, 4503599627370496.0));
+    const bool mono = __double2hiint(den) == 0;          // den is an exact integer: 0.0 or >= 1.0
+    // !(<=) rather than (>): a NaN from an unforeseen input must fall to the exact path, never pass
+    slow = !mono && (!(fabs(f_dp) <= lim_dp) || !(fabs(f_r2) <= lim_r2) || Dn == 0);
+    const uint32_t w = ((uint32_t)__double2loint(t_r2) & LDX_R2_MASK) | (((uint32_t)__double2loint(t_dp) << LDX_DP_SHIFT) & LDX_DP_MASK);
+    return mono ? (LDX_DP_INT0 | LDX_R2_INT0) : w;
+}
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
@@ -268,8 +339,8 @@ triangle_mma_kernel(const MmaArgs A) {
     uint8_t *smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);      // swizzle-128B needs 1 KB alignment
     uint8_t *op_s = smem;                                                        // [OP_STAGES][N][128 B] column operand
     uint8_t *bit_s = smem + Cfg::OP_STAGES * Cfg::OP_BYTES;                      // [BIT_STAGES][ROWS][16 B]
-    VarFreq *fb_s = reinterpret_cast<VarFreq *>(bit_s + Cfg::BIT_STAGES * Cfg::BIT_BYTES);   // [2][N]
-    uint32_t *epi_s = reinterpret_cast<uint32_t *>(fb_s + 2 * N);                // [N_EPI_WARPS][32][EPI_PITCH]
+    ColRec *col_s = reinterpret_cast<ColRec *>(bit_s + Cfg::BIT_STAGES * Cfg::BIT_BYTES);   // [2][N]
+    uint32_t *epi_s = reinterpret_cast<uint32_t *>(col_s + 2 * N);               // [N_EPI_WARPS][32][EPI_PITCH]
     uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(epi_s) + Cfg::EPI_BYTES);
     const uint32_t op_full = smem_u32(bars), op_empty = op_full + 8 * Cfg::OP_STAGES;
     const uint32_t bit_full = op_empty + 8 * Cfg::OP_STAGES, bit_empty = bit_full + 8 * Cfg::BIT_STAGES;
@@ -281,8 +352,8 @@ triangle_mma_kernel(const MmaArgs A) {
     const int kc_count = A.kc_count;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::OP_STAGES; ++s) { mbar_init(op_full + 8 * s, N_WIDEN_WARPS); mbar_init(op_empty + 8 * s, 1); }
-        for (int s = 0; s < Cfg::BIT_STAGES; ++s) { mbar_init(bit_full + 8 * s, 1); mbar_init(bit_empty + 8 * s, N_WIDEN_WARPS); }
+        for (int s = 0; s < Cfg::OP_STAGES; ++s) { mbar_init(op_full + 8 * s, TEAM_WARPS); mbar_init(op_empty + 8 * s, 1); }
+        for (int s = 0; s < Cfg::BIT_STAGES; ++s) { mbar_init(bit_full + 8 * s, 1); mbar_init(bit_empty + 8 * s, TEAM_WARPS); }
         for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + 8 * s, 1); mbar_init(tmem_empty + 8 * s, N_EPI_WARPS); }
         *abort_s = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -298,8 +369,10 @@ triangle_mma_kernel(const MmaArgs A) {
     const uint32_t tmem_base = *tmem_ptr_s;
     if (A.trace && blockIdx.x == 0 && threadIdx.x == 0) A.trace[0] = gtime();   // prologue done
 
+    const int ks_count = kc_count / Cfg::CH;                  // pipeline stages per tile (kc_count is even)
     if (warp == 0) {
-        // ===== producer: bit blocks L2 -> shared memory ring (2 KB for the row panel + 16*N B for the columns)
+        // ===== producer: bit blocks L2 -> shared memory ring.  One stage = CH chunks of the row panel
+        // (CH x 2 KB, contiguous in global memory) + the same for the tile's column variants.
         // The whole warp runs the loop; one elected lane issues the copies.
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         uint32_t g = 0;
@@ -307,21 +380,27 @@ triangle_mma_kernel(const MmaArgs A) {
             const int2 tile = A.tiles[t];
             const int64_t c0 = (int64_t)tile.y * N;
             const uint4 *a_src = A.bits + (int64_t)tile.x * kc_count * 128;
-            for (int kc = 0; kc < kc_count; ++kc, ++g) {
+            for (int ks = 0; ks < ks_count; ++ks, ++g) {
                 const uint32_t s = g % Cfg::BIT_STAGES, it = g / Cfg::BIT_STAGES;
                 if (!mbar_wait(bit_empty + 8 * s, (it & 1) ^ 1, abort_s, A.error_flag)) goto done;
                 const uint32_t bar = bit_full + 8 * s;
                 const uint32_t dst = smem_u32(bit_s + s * Cfg::BIT_BYTES);
+                const int kc = ks * Cfg::CH;
                 if (elect_one()) {
                     if (A.trace && blockIdx.x == 0 && g < 48) A.trace[128 + g] = gtime();
                     mbar_arrive_expect_tx(bar, Cfg::BIT_BYTES);
-                    bulk_g2s(dst, a_src + (int64_t)kc * 128, MMA_M * 16, bar);
+                    bulk_g2s(dst, a_src + (int64_t)kc * 128, Cfg::CH * MMA_M * 16, bar);       // [CH][128] rows
 #pragma unroll
-                    for (int part = 0; part < (N + 127) / 128; ++part) {
+                    for (int part = 0; part < Cfg::B_PARTS; ++part) {
                         const int64_t crow = c0 + part * 128;             // first column variant of this part
-                        const int rows_here = N < 128 ? N : 128;
-                        bulk_g2s(dst + (MMA_M + part * 128) * 16, A.bits_rev + ((crow >> 7) * kc_count + kc) * 128 + (crow & 127),
-                                 rows_here * 16, bar);
+                        const uint4 *b_src = A.bits_rev + ((crow >> 7) * kc_count + kc) * 128 + (crow & 127);
+                        const uint32_t b_dst = dst + (Cfg::CH * MMA_M + part * Cfg::CH * Cfg::B_ROWS) * 16;   // [part][CH][B_ROWS]
+                        if (Cfg::B_ROWS == 128) {
+                            bulk_g2s(b_dst, b_src, Cfg::CH * 128 * 16, bar);              // whole blocks: contiguous
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < Cfg::CH; ++c) bulk_g2s(b_dst + c * Cfg::B_ROWS * 16, b_src + c * 128, Cfg::B_ROWS * 16, bar);
+                        }
                     }
                 }
                 __syncwarp();
@@ -337,7 +416,7 @@ triangle_mma_kernel(const MmaArgs A) {
             if (!mbar_wait(tmem_empty + 8 * buf, ((tl / Cfg::ACC_BUFS) & 1) ^ 1, abort_s, A.error_flag)) goto done;   // epilogue drained it
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + buf * N;
-            for (int kc = 0; kc < kc_count; ++kc, ++g) {
+            for (int ks = 0; ks < ks_count; ++ks, ++g) {
                 const uint32_t s = g % Cfg::OP_STAGES, it = g / Cfg::OP_STAGES;
                 if (!mbar_wait(op_full + 8 * s, it & 1, abort_s, A.error_flag)) goto done;
                 tc_fence_after();
@@ -346,10 +425,10 @@ triangle_mma_kernel(const MmaArgs A) {
                 if (elect_one()) {
                     if (A.trace && blockIdx.x == 0 && g < 48) A.trace[64 + g] = gtime();
 #pragma unroll
-                    for (int k = 0; k < KCHUNK / MMA_K; ++k)     // K = 32: 8 TMEM columns of A, +32 B (= +2 encoded) of B
-                        umma_i8_ts(tmem_acc, ta + 8 * k, db + 2 * k, idesc, (uint32_t)((kc | k) != 0));
+                    for (int k = 0; k < Cfg::CH * KCHUNK / MMA_K; ++k)     // K = 32: 8 TMEM columns of A; B: atom k/4 (N*128 B apart), +32 B per step inside
+                        umma_i8_ts(tmem_acc, ta + 8 * k, db + (uint64_t)((k >> 2) * (N * KCHUNK >> 4) + (k & 3) * 2), idesc, (uint32_t)((ks | k) != 0));
                     umma_commit(op_empty + 8 * s);                // stage reusable once these MMAs have read it
-                    if (kc == kc_count - 1) umma_commit(tmem_full + 8 * buf);   // accumulator complete
+                    if (ks == ks_count - 1) umma_commit(tmem_full + 8 * buf);   // accumulator complete
                 }
                 __syncwarp();
             }
@@ -357,98 +436,138 @@ triangle_mma_kernel(const MmaArgs A) {
     } else if (warp < FIRST_WIDEN_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // spare warps: hand their registers over and wait
     } else if (warp < FIRST_EPI_WARP) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-        // ===== wideners: bit rows -> swizzled 0x00/0x80 operand bytes
-        // warps 4-7: row operand -> TMEM (lane = row; warp%4 is the TMEM quadrant the warp may write);
-        // warps 8-11: column operand -> 128B-swizzled shared memory.  One row per thread and chunk
-        // (two for N = 256, fewer for N = 64).
-        const bool is_a = warp < FIRST_WIDEN_WARP + 4;
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // ===== wideners: bit rows -> operand bytes.  Two teams of four warps take alternate stages, so
+        // that the fixed latencies of a stage (two mbarrier waits, the TMEM store, the proxy fence)
+        // of one team overlap the other team's.  Thread wt of a team widens row variant wt of the
+        // stage into TENSOR MEMORY (lane = row; warp%4 is the TMEM quadrant the warp may write) and
+        // column variant(s) wt (+128) into the 128B-swizzled shared-memory tile.
+        const int team = (warp - FIRST_WIDEN_WARP) / TEAM_WARPS;
         const int wt = ((warp - FIRST_WIDEN_WARP) & 3) * 32 + lane;     // 0..127
-        constexpr int B_RPT = (N + 127) / 128;
+        const uint32_t tmem_lane = (uint32_t)(((warp - FIRST_WIDEN_WARP) & 3) * 32) << 16;
         uint32_t g = 0;
         for (int t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
-            for (int kc = 0; kc < kc_count; ++kc, ++g) {
+            for (int ks = 0; ks < ks_count; ++ks, ++g) {
+                if ((int)(g % WIDEN_TEAMS) != team) continue;
                 const uint32_t sb = g % Cfg::BIT_STAGES, itb = g / Cfg::BIT_STAGES;
                 const uint32_t so = g % Cfg::OP_STAGES, ito = g / Cfg::OP_STAGES;
                 if (!mbar_wait(bit_full + 8 * sb, itb & 1, abort_s, A.error_flag)) goto done;
-                if (A.trace && blockIdx.x == 0 && g < 48 && wt == 0 && is_a) A.trace[192 + g] = gtime();
+                if (A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[192 + g] = gtime();
                 const uint4 *bsrc = reinterpret_cast<const uint4 *>(bit_s + sb * Cfg::BIT_BYTES);
-                if (is_a) {
-                    const uint4 b = bsrc[wt];
-                    const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+                uint4 ba[Cfg::CH];
+#pragma unroll
+                for (int c = 0; c < Cfg::CH; ++c) ba[c] = bsrc[c * MMA_M + wt];
+                if (!mbar_wait(op_empty + 8 * so, (ito & 1) ^ 1, abort_s, A.error_flag)) goto done;
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < Cfg::CH; ++c) {
+                    const uint32_t w[4] = {ba[c].x, ba[c].y, ba[c].z, ba[c].w};
                     uint32_t v[32];
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
 #pragma unroll
-                        for (int p = 0; p < 8; ++p) v[q * 8 + p] = w[q] & (0x01010101u << p);   // same byte order as expand_row<false>
-                    if (!mbar_wait(op_empty + 8 * so, (ito & 1) ^ 1, abort_s, A.error_flag)) goto done;
-                    tc_fence_after();
-                    tmem_st32(tmem_base + Cfg::TMEM_A0 + so * Cfg::A_COLS + ((uint32_t)(((warp - FIRST_WIDEN_WARP) & 3) * 32) << 16), v);
-                    tc_fence_before();
-                } else {
-                    uint4 b[B_RPT];
-#pragma unroll
-                    for (int i = 0; i < B_RPT; ++i) b[i] = (wt + i * 128 < N) ? bsrc[MMA_M + wt + i * 128] : make_uint4(0, 0, 0, 0);
-                    if (!mbar_wait(op_empty + 8 * so, (ito & 1) ^ 1, abort_s, A.error_flag)) goto done;
-                    uint8_t *ops = op_s + so * Cfg::OP_BYTES;
-#pragma unroll
-                    for (int i = 0; i < B_RPT; ++i)
-                        if (wt + i * 128 < N) expand_row<true>(ops + (wt + i * 128) * KCHUNK, wt & 7, b[i]);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05
+                        for (int p = 0; p < 8; ++p) v[q * 8 + p] = w[q] & (0x01010101u << p);   // same byte order as expand_row
+                    tmem_st32(tmem_base + Cfg::TMEM_A0 + so * Cfg::A_COLS + c * (KCHUNK / 4) + tmem_lane, v);
                 }
+                uint8_t *ops = op_s + so * Cfg::OP_BYTES;
+                if (wt < Cfg::B_ROWS) {
+#pragma unroll
+                    for (int c = 0; c < Cfg::CH; ++c)
+#pragma unroll
+                        for (int i = 0; i < Cfg::B_PARTS; ++i)
+                            expand_row<true>(ops + c * (N * KCHUNK) + (wt + i * 128) * KCHUNK, wt & 7,
+                                             bsrc[Cfg::CH * MMA_M + (i * Cfg::CH + c) * Cfg::B_ROWS + wt]);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(op_full + 8 * so); mbar_arrive(bit_empty + 8 * sb); }
-                if (A.trace && blockIdx.x == 0 && g < 48 && wt == 0 && is_a) A.trace[8 + g] = gtime();
+                if (A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[8 + g] = gtime();
             }
         }
     } else {
         // ===== epilogue.  Warp w may only touch TMEM lanes 32*(w%4) .. +31
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
         const int ew = warp - FIRST_EPI_WARP;                     // 0..7
         const int quad = warp & 3, half = ew >> 2;
         const int et = ew * 32 + lane;                            // 0..255
         uint32_t *stage = epi_s + ew * 32 * EPI_PITCH;
         const uint32_t m_shift = A.measure == LDX_MEASURE_R2 ? 0u : (uint32_t)LDX_DP_SHIFT;
         const uint32_t thres = A.has_thres ? (uint32_t)A.thres_e4 : 0u;      // rounded values are >= 0: 0 flags nothing
+        const int32_t Nn = A.n_sel;
+        const double lim_dp = A.lim_dp, lim_r2 = A.lim_r2;
         uint32_t tl = 0;
         for (int t = blockIdx.x; t < A.n_tiles; t += gridDim.x, ++tl) {
             const uint32_t buf = tl % Cfg::ACC_BUFS;
             const int2 tile = A.tiles[t];
             const int64_t r0 = (int64_t)tile.x * MMA_M, c0 = (int64_t)tile.y * N;
-            VarFreq *fb = fb_s + (tl & 1) * N;
-            for (int i = et; i < N; i += 32 * N_EPI_WARPS) fb[i] = A.freq_rows[c0 + i];     // column variants
+            ColRec *cols = col_s + (tl & 1) * N;
+            for (int i = et; i < N; i += 32 * N_EPI_WARPS) {      // column variants of this tile
+                const int32_t n1 = A.freq_rows[c0 + i].n1;
+                ColRec cr; cr.n1 = n1; cr.n1N = n1 * Nn; cr.prod = u32_to_double((uint32_t)(n1 * (Nn - n1)));
+                cols[i] = cr;
+            }
             asm volatile("bar.sync 1, %0;" :: "n"(32 * N_EPI_WARPS) : "memory");
             const int64_t r = r0 + quad * 32 + lane;
-            const VarFreq fa = A.freq_rows[r];
+            // row variant of this lane: n1a, n1a*N, N^2 - n1a*N, n1a*n0a
+            const int32_t n1a = A.freq_rows[r].n1;
+            const int32_t aN = n1a * Nn, cN = Nn * Nn - aN;
+            const double da = u32_to_double((uint32_t)(n1a * (Nn - n1a)));
             if (!mbar_wait(tmem_full + 8 * buf, (tl / Cfg::ACC_BUFS) & 1, abort_s, A.error_flag, 128)) goto done;
             tc_fence_after();
             if (A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[1 + 2 * tl] = gtime();   // accumulator ready
             const uint32_t tmem_acc = tmem_base + buf * N + ((uint32_t)(quad * 32) << 16);
             const int64_t warp_r0 = r0 + quad * 32, warp_rmax = warp_r0 + 31;
+            // write-out: lane handles column (lane & 15) of rows warp_r0 + (lane >> 4) + 2i; the packed
+            // index advances by tri(rg + 2) - tri(rg) = 2 rg + 1 per step
+            const int64_t wr0 = warp_r0 + (lane >> 4);
+            const int64_t out0 = wr0 * (wr0 - 1) / 2 + c0 + (lane & 15);
 #pragma unroll 1
             for (int c = half * (N / 2); c < (half + 1) * (N / 2); c += 16) {
                 if (c0 + c >= warp_rmax || c0 + c >= A.v) break;        // warp-uniform: nothing below the diagonal
                 uint32_t acc[16];
                 tmem_ld16(tmem_acc + (uint32_t)c, acc);
-                uint32_t ties = 0;
-                uint32_t word[16];      // kept in registers until every fb[] load of a group has issued:
-                                        // a shared-memory store in between would serialise the pairs
+                uint32_t slow = 0;
                 // four pairs at a time: enough independent fp64 chains to cover the pipe latency
-                // without pushing the register allocator into spills
 #pragma unroll
                 for (int j0 = 0; j0 < 16; j0 += 4) {
+                    uint32_t word[4];
 #pragma unroll
                     for (int j = j0; j < j0 + 4; ++j) {
-                        const int32_t cnt = (int32_t)(acc[j] >> ACC_SHIFT);
-                        const PairFinal f = finalise_pair(cnt, fa, fb[c + j], A.fc);    // var_1 = row, var_2 = column
-                        uint32_t w = f.packed;
+                        const ColRec cr = cols[c + j];
+                        bool s;
+                        uint32_t w = fast_pair((int32_t)(acc[j] >> ACC_SHIFT), Nn, n1a, aN, cN, da, cr, lim_dp, lim_r2, s);
                         w |= (((w >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;   // no branch
-                        ties |= ((w >> 14) & 1u) << j;
-                        word[j] = w;
+                        slow |= (uint32_t)s << j;
+                        word[j - j0] = w;
+                    }
+                    *reinterpret_cast<uint4 *>(stage + lane * EPI_PITCH + j0) = make_uint4(word[0], word[1], word[2], word[3]);
+                }
+                if (r >= A.v) slow = 0;
+                if (__any_sync(0xffffffffu, slow != 0)) {
+                    // Rare: a screened value sits inside the guard band of a rounding boundary (or D is
+                    // exactly 0 for two polymorphic variants).  Redo those pairs with the reference's own
+                    // operation sequence (finalise_pair); near-ties of r2 go to the host list as before.
+                    const VarFreq fa = A.freq_rows[r < A.v ? r : 0];
+#pragma unroll 1
+                    for (int j = 0; j < 16; ++j) {
+                        if (!__any_sync(0xffffffffu, (slow >> j) & 1u)) continue;
+                        uint32_t cnt;
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(cnt) : "r"(tmem_acc + (uint32_t)(c + j)));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        const int64_t col = c0 + c + j;
+                        if (((slow >> j) & 1u) && col < r) {
+                            const VarFreq fb = A.freq_rows[col];
+                            const int32_t n11 = (int32_t)(cnt >> ACC_SHIFT);
+                            const PairFinal f = finalise_pair(n11, fa, fb, A.fc);    // var_1 = row, var_2 = column
+                            uint32_t w = f.packed;
+                            w |= (((w >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;
+                            stage[lane * EPI_PITCH + j] = w;
+                            if (w & LDX_R2_NEARTIE) fixup_append(A.fix, (uint64_t)(r * (r - 1) / 2 + col), n11, fa.n1, fb.n1, w);
+                        }
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) stage[lane * EPI_PITCH + j] = word[j];
                 if (WANT_N11) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
@@ -458,23 +577,16 @@ triangle_mma_kernel(const MmaArgs A) {
                 }
                 __syncwarp();
                 // transposed write-out: 16 lanes cover the 16 columns of one row (64 contiguous bytes)
+                {
+                    int64_t rg = wr0, idx = out0 + c;
+                    const int64_t cg = c0 + c + (lane & 15);
+                    const uint32_t *src = stage + (lane >> 4) * EPI_PITCH + (lane & 15);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int rl = 2 * i + (lane >> 4), cl = lane & 15;
-                    const int64_t rg = warp_r0 + rl, cg = c0 + c + cl;
-                    const uint32_t word = stage[rl * EPI_PITCH + cl];
-                    if (rg < A.v && cg < rg) A.packed[rg * (rg - 1) / 2 + cg] = word;
-                }
-                __syncwarp();
-                if (__any_sync(0xffffffffu, ties != 0 && r < A.v)) {     // rare: r2 next to a rounding tie
-                    uint32_t again[16];
-                    tmem_ld16(tmem_acc + (uint32_t)c, again);            // counts are still in TMEM
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int64_t col = c0 + c + j;
-                        if (((ties >> j) & 1u) && r < A.v && col < r)
-                            fixup_append(A.fix, (uint64_t)(r * (r - 1) / 2 + col), (int32_t)(again[j] >> ACC_SHIFT), fa.n1,
-                                         fb[c + j].n1, stage[lane * EPI_PITCH + j]);
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t w = src[2 * i * EPI_PITCH];
+                        if (rg < A.v && cg < rg) A.packed[idx] = w;
+                        idx += 2 * rg + 1;
+                        rg += 2;
                     }
                 }
                 __syncwarp();
@@ -521,7 +633,9 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
     ldx_ctx *ctx = s->ctx;
     if (!d_packed) return set_error(LDX_ERR_ARG, "tcgen05 engine: the packed output is required");
     if (s->n_hap > (1 << 23)) return set_error(LDX_ERR_ARG, "tcgen05 engine: more than 2^23 haplotypes would overflow the int32 accumulator");
-    const int kc_count = (s->n_hap + KCHUNK - 1) / KCHUNK;     // stride_words*64 >= kc_count*128 (rows are 128 B multiples)
+    // 128-haplotype chunks, rounded up to whole pipeline stages of two (rows are 128 B multiples,
+    // i.e. a multiple of 8 chunks, so the padding chunk is inside the row and zero)
+    const int kc_count = ((s->n_hap + KCHUNK - 1) / KCHUNK + 1) / 2 * 2;
     const int64_t v_pad = (v + 255) / 256 * 256;
     const int64_t panels = v_pad / MMA_M;
     // tile width: narrow tiles give every SM several tiles to overlap for small matrices, wide
@@ -575,6 +689,14 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
     A.n_tiles = (int32_t)n_tiles;
     A.v = v; A.measure = measure; A.has_thres = has_thres; A.thres_e4 = thres_e4;
     A.packed = d_packed; A.n11 = d_n11;
+    A.n_sel = s->n_sel;
+    {   // guard band of the screening arithmetic (see fast_pair); beyond N = 32768 the int32 products
+        // would overflow and the band would swallow everything: every pair then takes the exact path
+        const double n = (double)s->n_sel, g = 1.0e4 * 16.0 * 1.1102230246251565e-16 * n * n;
+        const bool ok = s->n_sel <= 32768;
+        A.lim_r2 = ok ? 0.5 - (g + 1.0e-6) : -1.0;
+        A.lim_dp = ok ? 0.5 - (0.5 * g + 1.0e-6) : -1.0;
+    }
     A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity};
     A.error_flag = reinterpret_cast<int32_t *>(ctx->d_fix_count + 1);
     A.trace = ctx->d_trace;

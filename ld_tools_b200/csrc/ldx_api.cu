@@ -238,7 +238,8 @@ static int collect_fixups(ldx_ctx *ctx, std::vector<FixupRec> &recs, bool use_ma
         n = ctx->h_fix_count[0]; err = ctx->h_fix_count[1];
     }
     if (err) {
-        cudaMemsetAsync(ctx->d_fix_count, 0, 2 * sizeof(uint32_t), ctx->stream);
+        cudaMemsetAsync(ctx->d_fix_count, 0, 4 * sizeof(uint32_t), ctx->stream);
+        if (err == 2) return set_error(LDX_ERR_CAPACITY, "tcgen05 engine: deferred-pair list overflow (degenerate input); use LDX_ENGINE_POPC for this variant set");
         return set_error(LDX_ERR_CUDA, "tcgen05 pipeline timed out (mbarrier wait exceeded 2 s); results are invalid");
     }
     if (n == 0) return LDX_OK;
@@ -732,14 +733,16 @@ extern "C" int32_t ldx_triangle_dev(ldx_store *s, const int64_t *rows, int64_t v
     ldx_ctx *ctx = s->ctx;
     if (engine == LDX_ENGINE_MMA && !triangle_mma_available())
         return set_error(LDX_ERR_ARG, "the tcgen05 engine is not available in this build");
-    const bool use_mma = engine == LDX_ENGINE_MMA || (engine == LDX_ENGINE_AUTO && triangle_mma_available() && v >= ctx->mma_min_v);
+    const bool use_mma = engine == LDX_ENGINE_MMA || (engine == LDX_ENGINE_AUTO && triangle_mma_available() && v >= ctx->mma_min_v &&
+                                                      s->n_sel <= triangle_mma_max_haplotypes());
     // rows[] staging is consumed by the kernel on the same stream; the caller's array may be
     // freed after return, so wait for the H2D copy (tiny) before returning.
-    int rc = use_mma ? launch_triangle_mma(s, d_rows, v, measure, has_thres, thres_e4, dev_packed, dev_n11)
+    const uint32_t seq = ctx->seq + 1 ? ctx->seq + 1 : 1;     // 0 means "nothing published"
+    int rc = use_mma ? launch_triangle_mma(s, d_rows, v, measure, has_thres, thres_e4, dev_packed, dev_n11, seq)
                      : launch_triangle_popc(s, d_rows, v, measure, has_thres, thres_e4, dev_packed, dev_n11);
     LDX_TRY(rc);
-    ++ctx->seq;
-    LDX_TRY(launch_publish(ctx));
+    ctx->seq = seq;
+    if (!use_mma) LDX_TRY(launch_publish(ctx));
     ctx->pending.kind = 1; ctx->pending.dev_out = dev_packed; ctx->pending.n_hap = s->fc.n_hap;
     ctx->pending.measure = measure; ctx->pending.has_thres = has_thres; ctx->pending.thres_e4 = thres_e4;
     return LDX_OK;

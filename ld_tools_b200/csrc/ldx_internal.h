@@ -95,9 +95,11 @@ int launch_window(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, cons
                   unsigned long long *d_n_hits);
 int launch_triangle_popc(ldx_store *s, const int64_t *d_rows, int64_t v, int measure, int has_thres,
                          int thres_e4, uint32_t *d_packed, int32_t *d_n11);
+// publish_seq != 0: the engine's last kernel also publishes the completion record for that sequence number
 int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int measure, int has_thres,
-                        int thres_e4, uint32_t *d_packed, int32_t *d_n11);
+                        int thres_e4, uint32_t *d_packed, int32_t *d_n11, uint32_t publish_seq);
 bool triangle_mma_available();
+int triangle_mma_max_haplotypes();
 int launch_publish(ldx_ctx *ctx);   // enqueue the mailbox update for ctx->seq
 
 constexpr int WINDOW_CHUNK = 256;   // rows per work item of the window kernel

@@ -250,7 +250,8 @@ struct MmaArgs {
     const int2 *tiles; int32_t n_tiles;
     int64_t v; int measure, has_thres, thres_e4;
     int32_t n_sel;               // N = selected haplotypes
-    double lim_dp, lim_r2;       // 0.5 - guard band of the screening arithmetic (see fast_pair); <= 0 disables it
+    double lim_dp, lim_r2;       // 0.5 - guard band of the screening arithmetic (see fast_pair)
+    uint4 *slow; uint32_t *slow_count; uint32_t slow_cap;   // deferred pairs {row, col, n11, -} for slow_pairs_kernel
     uint32_t *packed; int32_t *n11;
     FixupSink fix;
     int32_t *error_flag;
@@ -272,6 +273,7 @@ constexpr int REGS_LAUNCH = 96, REGS_CTRL = 40, REGS_WIDEN = 56, REGS_EPI = 160;
 static_assert(128 * (REGS_LAUNCH - REGS_CTRL) + 256 * (REGS_LAUNCH - REGS_WIDEN) >= 256 * (REGS_EPI - REGS_LAUNCH), "setmaxnreg budget");
 constexpr int FIRST_WIDEN_WARP = 4, FIRST_EPI_WARP = FIRST_WIDEN_WARP + N_WIDEN_WARPS;
 constexpr int MMA_THREADS = 32 * (FIRST_EPI_WARP + N_EPI_WARPS);   // 640
+constexpr int SLOW_BUF = 64;                                           // deferred pairs buffered per epilogue warp
 constexpr int EPI_PITCH = 20;                                          // words per staged row: 16-byte aligned rows, conflict-free STS.128
 
 // Per column variant, what the screening arithmetic of the epilogue needs (one 16-byte broadcast load per pair).
@@ -296,7 +298,7 @@ template <int N> struct MmaCfg {
     static constexpr int TMEM_COLS = 512;
     static_assert(TMEM_A0 + OP_STAGES * A_COLS <= 512, "TMEM budget");
     static constexpr int N_BARS = 2 * OP_STAGES + 2 * BIT_STAGES + 4;
-    static constexpr int EPI_BYTES = N_EPI_WARPS * 32 * EPI_PITCH * 4;
+    static constexpr int EPI_BYTES = N_EPI_WARPS * (32 * EPI_PITCH * 4 + SLOW_BUF * 16);   // staging + deferred-pair buffer per warp
     static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)OP_STAGES * OP_BYTES + (size_t)BIT_STAGES * BIT_BYTES +
                                    2 * N * sizeof(ColRec) + EPI_BYTES + N_BARS * 8 + 64;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
@@ -328,6 +330,60 @@ __device__ __forceinline__ uint32_t fast_pair(int32_t n11, int32_t Nn, int32_t n
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
+// Warp-collective: move a warp's buffered deferred pairs to the global list.  Returns the new count (0).
+__device__ __forceinline__ uint32_t flush_slow(const MmaArgs &A, const uint4 *sbuf, uint32_t cnt, int lane) {
+    if (cnt == 0) return 0;
+    __syncwarp();
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(A.slow_count, cnt);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (uint32_t i = lane; i < cnt; i += 32)
+        if (base + i < A.slow_cap) A.slow[base + i] = sbuf[i];     // overflow is detected from the count
+    __syncwarp();
+    return 0;
+}
+
+// The pairs the epilogue's screening could not settle, redone with the reference's own operation
+// sequence (finalise_pair): one thread per pair, fully parallel.  The last block to finish publishes
+// the call's completion record (near-tie count, error flag, sequence number) to the host mailbox.
+__global__ void __launch_bounds__(256)
+slow_pairs_kernel(const uint4 *__restrict__ list, uint32_t *__restrict__ counters /* d_fix_count */, uint32_t cap,
+                  const VarFreq *__restrict__ freq_rows, FinalCtx fc, int measure, int has_thres, int thres_e4,
+                  uint32_t *__restrict__ packed, FixupSink fix, volatile uint32_t *mailbox, uint32_t seq) {
+    const uint32_t total = counters[2];
+    const uint32_t n = total < cap ? total : cap;
+    const uint32_t m_shift = measure == LDX_MEASURE_R2 ? 0u : (uint32_t)LDX_DP_SHIFT;
+    const uint32_t thres = has_thres ? (uint32_t)thres_e4 : 0u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 e = list[i];
+        const int64_t r = e.x, col = e.y;
+        const VarFreq fa = freq_rows[r], fb = freq_rows[col];
+        const PairFinal f = finalise_pair((int32_t)e.z, fa, fb, fc);       // var_1 = row, var_2 = column
+        uint32_t w = f.packed;
+        w |= (((w >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;
+        const uint64_t idx = (uint64_t)(r * (r - 1) / 2 + col);
+        if (w & LDX_R2_NEARTIE) fixup_append(fix, idx, (int32_t)e.z, fa.n1, fb.n1, w);
+        packed[idx] = w;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (total > cap) atomicExch(&counters[1], 2u);                    // deferred-pair list overflow: results incomplete
+        const uint32_t ticket = atomicAdd(&counters[3], 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            counters[3] = 0;
+            counters[2] = 0;
+            if (mailbox) {
+                mailbox[1] = *(volatile uint32_t *)&counters[0];
+                mailbox[2] = *(volatile uint32_t *)&counters[1];
+                __threadfence_system();
+                mailbox[0] = seq;
+            }
+        }
+    }
 }
 
 template <int N, bool WANT_N11>
@@ -492,7 +548,10 @@ triangle_mma_kernel(const MmaArgs A) {
         const int ew = warp - FIRST_EPI_WARP;                     // 0..7
         const int quad = warp & 3, half = ew >> 2;
         const int et = ew * 32 + lane;                            // 0..255
-        uint32_t *stage = epi_s + ew * 32 * EPI_PITCH;
+        uint32_t *stage = epi_s + ew * (32 * EPI_PITCH + SLOW_BUF * 4);
+        uint4 *sbuf = reinterpret_cast<uint4 *>(stage + 32 * EPI_PITCH);
+        uint32_t slow_cnt = 0;                                    // warp-uniform: entries buffered in sbuf
+        const uint32_t lanemask_lt = (1u << lane) - 1u;
         const uint32_t m_shift = A.measure == LDX_MEASURE_R2 ? 0u : (uint32_t)LDX_DP_SHIFT;
         const uint32_t thres = A.has_thres ? (uint32_t)A.thres_e4 : 0u;      // rounded values are >= 0: 0 flags nothing
         const int32_t Nn = A.n_sel;
@@ -544,29 +603,30 @@ triangle_mma_kernel(const MmaArgs A) {
                     }
                     *reinterpret_cast<uint4 *>(stage + lane * EPI_PITCH + j0) = make_uint4(word[0], word[1], word[2], word[3]);
                 }
-                if (r >= A.v) slow = 0;
-                if (__any_sync(0xffffffffu, slow != 0)) {
-                    // Rare: a screened value sits inside the guard band of a rounding boundary (or D is
-                    // exactly 0 for two polymorphic variants).  Redo those pairs with the reference's own
-                    // operation sequence (finalise_pair); near-ties of r2 go to the host list as before.
-                    const VarFreq fa = A.freq_rows[r < A.v ? r : 0];
-#pragma unroll 1
-                    for (int j = 0; j < 16; ++j) {
-                        if (!__any_sync(0xffffffffu, (slow >> j) & 1u)) continue;
-                        uint32_t cnt;
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(cnt) : "r"(tmem_acc + (uint32_t)(c + j)));
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        const int64_t col = c0 + c + j;
-                        if (((slow >> j) & 1u) && col < r) {
-                            const VarFreq fb = A.freq_rows[col];
-                            const int32_t n11 = (int32_t)(cnt >> ACC_SHIFT);
-                            const PairFinal f = finalise_pair(n11, fa, fb, A.fc);    // var_1 = row, var_2 = column
-                            uint32_t w = f.packed;
-                            w |= (((w >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;
-                            stage[lane * EPI_PITCH + j] = w;
-                            if (w & LDX_R2_NEARTIE) fixup_append(A.fix, (uint64_t)(r * (r - 1) / 2 + col), n11, fa.n1, fb.n1, w);
-                        }
+                {   // only pairs of the triangle matter: columns c0+c+j < r, r < v
+                    const int64_t nvalid = r < A.v ? r - (c0 + c) : 0;
+                    slow &= nvalid >= 16 ? 0xffffu : nvalid > 0 ? (1u << (int)nvalid) - 1u : 0u;
+                }
+                // Rare (about 6 * guard band of the pairs): a screened value sits next to a rounding
+                // boundary, or D is exactly 0 for two polymorphic variants.  Those pairs are not redone
+                // here -- one lane running the reference's operation sequence would stall the warp for
+                // a microsecond -- but queued for slow_pairs_kernel, which runs after this kernel and
+                // overwrites their words.  The queue is per warp in shared memory (ballot compaction,
+                // no atomics) and is flushed to the global list when it fills up and at the end.
+                while (true) {
+                    const uint32_t bal = __ballot_sync(0xffffffffu, slow != 0);
+                    if (bal == 0) break;
+                    if (slow_cnt > SLOW_BUF - 32) slow_cnt = flush_slow(A, sbuf, slow_cnt, lane);
+                    if (slow) {
+                        const int j = __ffs(slow) - 1;
+                        slow &= slow - 1;
+                        uint32_t a = acc[0];
+#pragma unroll
+                        for (int jj = 1; jj < 16; ++jj) a = (j == jj) ? acc[jj] : a;
+                        sbuf[slow_cnt + __popc(bal & lanemask_lt)] = make_uint4((uint32_t)r, (uint32_t)(c0 + c + j), a >> ACC_SHIFT, 0u);
                     }
+                    slow_cnt += __popc(bal);
+                    __syncwarp();
                 }
                 if (WANT_N11) {
 #pragma unroll
@@ -597,6 +657,7 @@ triangle_mma_kernel(const MmaArgs A) {
             if (lane == 0) mbar_arrive(tmem_empty + 8 * buf);
             if (A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[2 + 2 * tl] = gtime();       // epilogue of this tile done
         }
+        flush_slow(A, sbuf, slow_cnt, lane);
     }
 done:
     tc_fence_before();
@@ -608,6 +669,9 @@ done:
 }
 
 bool triangle_mma_available() { return true; }
+// The screening arithmetic's guard band grows with N^2 (see fast_pair): up to this many selected
+// haplotypes fewer than 1% of the pairs are deferred; beyond it ENGINE_AUTO uses the popcount engine.
+int triangle_mma_max_haplotypes() { return 8192; }
 
 template <int N, bool WANT_N11>
 static int launch_tiles_t(ldx_ctx *ctx, const MmaArgs &A) {
@@ -628,9 +692,11 @@ static int launch_tiles(ldx_ctx *ctx, const MmaArgs &A) {
 }
 
 int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int measure, int has_thres,
-                        int thres_e4, uint32_t *d_packed, int32_t *d_n11) {
+                        int thres_e4, uint32_t *d_packed, int32_t *d_n11, uint32_t publish_seq) {
     if (v < 2) return LDX_OK;
     ldx_ctx *ctx = s->ctx;
+    if (s->n_sel > triangle_mma_max_haplotypes())
+        return set_error(LDX_ERR_ARG, "tcgen05 engine: more than 8192 selected haplotypes (use LDX_ENGINE_POPC or LDX_ENGINE_AUTO)");
     if (!d_packed) return set_error(LDX_ERR_ARG, "tcgen05 engine: the packed output is required");
     if (s->n_hap > (1 << 23)) return set_error(LDX_ERR_ARG, "tcgen05 engine: more than 2^23 haplotypes would overflow the int32 accumulator");
     // 128-haplotype chunks, rounded up to whole pipeline stages of two (rows are 128 B multiples,
@@ -652,8 +718,13 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
     }
     if (n_tiles == 0) return LDX_OK;
     if (n_tiles > 0x7fffffffull) return set_error(LDX_ERR_ARG, "tcgen05 engine: too many tiles");
-    const size_t tile_bytes = n_tiles * sizeof(int2);
-    const size_t need = 2 * bits_bytes + freq_bytes + tile_bytes + 1024;
+    const size_t tile_bytes = (n_tiles * sizeof(int2) + 15) / 16 * 16;
+    // deferred-pair list: the guard band defers < 1% of the pairs (triangle_mma_max_haplotypes)
+    const uint64_t n_pairs = (uint64_t)v * (uint64_t)(v - 1) / 2;
+    const uint64_t slow_cap64 = n_pairs / 64 + 65536;
+    if (slow_cap64 > 0xffffffffull) return set_error(LDX_ERR_ARG, "tcgen05 engine: too many pairs for one call");
+    const size_t slow_bytes = (size_t)slow_cap64 * sizeof(uint4);
+    const size_t need = 2 * bits_bytes + freq_bytes + tile_bytes + slow_bytes + 1024;
     if (ctx->mma_ops_bytes < need) {
         if (ctx->d_mma_ops) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_mma_ops); ctx->d_mma_ops = nullptr; ctx->mma_ops_bytes = 0; }
         if (cudaMalloc(&ctx->d_mma_ops, need) != cudaSuccess) { cudaGetLastError(); return set_error(LDX_ERR_NOMEM, "tcgen05 operand scratch allocation failed"); }
@@ -664,6 +735,7 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
     uint4 *d_bits = reinterpret_cast<uint4 *>(base), *d_bits_rev = reinterpret_cast<uint4 *>(base + bits_bytes);
     VarFreq *d_freq_rows = reinterpret_cast<VarFreq *>(base + 2 * bits_bytes);
     int2 *d_tiles = reinterpret_cast<int2 *>(base + 2 * bits_bytes + freq_bytes);
+    uint4 *d_slow = reinterpret_cast<uint4 *>(base + 2 * bits_bytes + freq_bytes + tile_bytes);
     if (ctx->mma_tiles_v != v || ctx->mma_tiles_n != n_tile) {          // the list depends on (v, N) only
         // Longest tiles first is not needed (all tiles cost the same K loop); the list is ordered so
         // that the tiles a wave of CTAs works on share row panels and neighbouring column blocks in L2.
@@ -673,7 +745,7 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
             const int64_t rmax = std::min<int64_t>(bi * MMA_M + MMA_M - 1, v - 1);
             for (int64_t bj = 0; bj * n_tile < rmax; ++bj) tiles.push_back(make_int2((int)bi, (int)bj));
         }
-        LDX_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tile_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        LDX_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), n_tiles * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
         LDX_CUDA(cudaStreamSynchronize(ctx->stream));   // `tiles` is a local
         ctx->mma_tiles_v = v; ctx->mma_tiles_n = n_tile;
     }
@@ -699,14 +771,24 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
     }
     A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity};
     A.error_flag = reinterpret_cast<int32_t *>(ctx->d_fix_count + 1);
+    A.slow = d_slow; A.slow_count = ctx->d_fix_count + 2; A.slow_cap = (uint32_t)slow_cap64;
     A.trace = ctx->d_trace;
     A.dbg = getenv("LDX_DEBUG_MMA") ? atoi(getenv("LDX_DEBUG_MMA")) : 0;
+    int rc;
     switch (n_tile) {
-        case 64: return launch_tiles<64>(ctx, A);
-        case 128: return launch_tiles<128>(ctx, A);
-        case 256: return launch_tiles<256>(ctx, A);
+        case 64: rc = launch_tiles<64>(ctx, A); break;
+        case 128: rc = launch_tiles<128>(ctx, A); break;
+        case 256: rc = launch_tiles<256>(ctx, A); break;
         default: return set_error(LDX_ERR_ARG, "tcgen05 tile width must be 64, 128 or 256");
     }
+    if (rc != LDX_OK) return rc;
+    // deferred pairs + completion record (d_fix_count: [0] near-ties, [1] error flag, [2] deferred pairs, [3] ticket)
+    const int sgrid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 2, std::max<uint64_t>(1, n_pairs / (1u << 20)));
+    slow_pairs_kernel<<<sgrid, 256, 0, ctx->stream>>>(d_slow, ctx->d_fix_count, A.slow_cap, d_freq_rows, s->fc, measure, has_thres,
+                                                      thres_e4, d_packed, A.fix, publish_seq ? ctx->d_mailbox : nullptr, publish_seq);
+    ctx->launches++;
+    LDX_CUDA(cudaGetLastError());
+    return LDX_OK;
 }
 
 }  // namespace ldx

@@ -95,7 +95,7 @@ int32_t ldx_set_stream(ldx_ctx *ctx, void *cuda_stream);
 int32_t ldx_use_own_stream(ldx_ctx *ctx);
 int32_t ldx_synchronize(ldx_ctx *ctx);
 /* Tuning knobs (benchmarks/tests; defaults are chosen per call):
- *   LDX_TUNE_MMA_TILE_N  column width of the tcgen05 all-pairs tile: 0 = heuristic, 64, 128, 256
+ *   LDX_TUNE_MMA_TILE_N  column width of the tcgen05 all-pairs tile: 0 = heuristic, 64 or 128
  *   LDX_TUNE_MMA_MIN_V   LDX_ENGINE_AUTO uses the tcgen05 engine from this many variants (256) */
 enum { LDX_TUNE_MMA_TILE_N = 1, LDX_TUNE_MMA_MIN_V = 2 };
 int32_t ldx_set_tuning(ldx_ctx *ctx, int32_t key, int32_t value);

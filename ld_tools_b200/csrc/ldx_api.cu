@@ -128,7 +128,7 @@ extern "C" int32_t ldx_set_tuning(ldx_ctx *ctx, int32_t key, int32_t value) {
     LDX_REQUIRE(ctx, "ctx is NULL");
     switch (key) {
         case LDX_TUNE_MMA_TILE_N:
-            LDX_REQUIRE(value == 0 || value == 64 || value == 128 || value == 256, "tile width must be 0, 64, 128 or 256");
+            LDX_REQUIRE(value == 0 || value == 64 || value == 128, "tile width must be 0, 64 or 128");
             ctx->mma_tile_n = value;
             return LDX_OK;
         case LDX_TUNE_MMA_MIN_V:

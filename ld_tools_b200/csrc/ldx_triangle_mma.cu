@@ -220,28 +220,35 @@ constexpr int ACC_SHIFT = 7;   // 2^p * 2^(7-p) = 2^7 per (alt, alt) haplotype
 //     m  = Dn > 0 ? min(n1a*n0b, n0a*n1b)   D' = |Dn| / m                       (calc_ld.py:63-76)
 //                 : min(n1a*n1b, n0a*n0b)
 //     den = n1a*n0a*n1b*n0b                 r2 = Dn^2 / den                     (calc_ld.py:86-88)
-// The integers are exact in fp64 (N <= 32768), so x = value * 10^4 is evaluated here to a relative
-// error below 2^-45 with ONE shared reciprocal, 1 / (m * den).  The reference rounds ITS OWN fp64
-// chain, whose distance from the exact ratio is bounded by the cancellation in f11 - p1*p2:
-// |x_ref - x_exact| <= 10^4 * 16 * 2^-53 * N^2 for r2 (half of that for D').  Whenever x is farther
-// than that bound (+1e-6) from every k + 1/2, Python's round(x_ref, 4) and the rounding of x agree,
-// and the packed word is final.  Otherwise -- and when Dn == 0 for two polymorphic variants, where
-// only the reference's own rounding errors decide between int 0 and 0.0 -- `slow` is set and the
-// caller redoes the pair with the reference's operation sequence (finalise_pair).
+// Dn and m are formed exactly in int32 (N <= 8192: |Dn| <= 2^26, m <= 2^24).  x = value * 10^4 is
+// then evaluated in SINGLE precision -- the epilogue is bound by instruction issue, and an fp32
+// chain is half the instructions of an fp64 one -- with a relative error below SCREEN_C_* * 2^-24:
+//     fD = RN(|Dn|) (1 rounding), fm = m and n1a*n0a, n1b*n0b exact (<= 2^24),
+//     x_dp = (fD * 1e4) * rcp(fm)                : 3 roundings + rcp.approx (<= 2^-23)  -> 6 u
+//     x_r2 = ((fD * 1e4) * fD) * rcp(da * dc)    : 6 roundings + rcp.approx            -> 9 u
+// The reference rounds ITS OWN fp64 chain, whose distance from the exact ratio is bounded by the
+// cancellation in f11 - p1*p2: |x_ref - x_exact| <= 10^4 * 16 * 2^-53 * N^2 for r2 (half of that for
+// D').  Whenever x is farther than both bounds together (+1e-5) from every k + 1/2, Python's
+// round(x_ref, 4) and the rounding of x agree, and the packed word is final.  Otherwise -- and when
+// Dn == 0 for two polymorphic variants, where only the reference's own rounding errors decide
+// between int 0 and 0.0 -- `slow` is set and the pair is redone with the reference's operation
+// sequence in fp64 (finalise_pair, slow_pairs_kernel): about 1% of the pairs.
 // Monomorphic variants (den == 0) need no arithmetic: d is exactly 0 and the bound is exactly 0 in
 // the reference as well (calc_ld.py:68-69, :89-90): both int-0 flags.
-__device__ __forceinline__ double rcp_newton(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = __fma_rn(-x, y, 1.0);
-    e = __fma_rn(e, e, e);
-    y = __fma_rn(y, e, y);
-    e = __fma_rn(-x, y, 1.0);
-    return __fma_rn(y, e, y);
+constexpr float SCREEN_U = 5.9604644775390625e-08f;      // 2^-24
+constexpr float SCREEN_C_DP = 7.0f * SCREEN_U;            // 6 u proven + 1 u slack
+constexpr float SCREEN_C_R2 = 10.0f * SCREEN_U;           // 9 u proven + 1 u slack
+constexpr float ROUND_MAGIC = 12582912.0f;                // 1.5 * 2^23: x + MAGIC has ulp 1 for 0 <= x < 2^22
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 struct ColRec;
-__device__ __forceinline__ uint32_t fast_pair(int32_t n11, int32_t Nn, int32_t n1a, int32_t aN, int32_t cN, double da,
-                                              const ColRec &cr, double lim_dp, double lim_r2, bool &slow);
+template <bool THRES>
+__device__ __forceinline__ uint32_t fast_pair(int32_t n11, int32_t Nn, int32_t n1a, int32_t aN, int32_t cN, float fa,
+                                              const ColRec &cr, float lim_dp, float lim_r2, uint32_t m_shift, uint32_t thres,
+                                              bool &slow);
 
 // ------------------------------------------------------------------------------------------ GEMM + epilogue
 struct MmaArgs {
@@ -250,7 +257,7 @@ struct MmaArgs {
     const int2 *tiles; int32_t n_tiles;
     int64_t v; int measure, has_thres, thres_e4;
     int32_t n_sel;               // N = selected haplotypes
-    double lim_dp, lim_r2;       // 0.5 - guard band of the screening arithmetic (see fast_pair)
+    float lim_dp, lim_r2;        // 0.5 - guard band of the screening arithmetic at x = 0 (see fast_pair)
     uint4 *slow; uint32_t *slow_count; uint32_t slow_cap;   // deferred pairs {row, col, n11, -} for slow_pairs_kernel
     uint32_t *packed; int32_t *n11;
     FixupSink fix;
@@ -278,9 +285,10 @@ constexpr int EPI_PITCH = 20;                                          // words 
 
 // Per column variant, what the screening arithmetic of the epilogue needs (one 16-byte broadcast load per pair).
 struct __align__(16) ColRec {
-    double prod;     // n1 * (N - n1), exact
+    float prod;      // n1 * (N - n1), exact (<= 2^24)
     int32_t n1;      // alt alleles under the mask
     int32_t n1N;     // n1 * N
+    int32_t pad;
 };
 
 template <int N> struct MmaCfg {
@@ -304,73 +312,89 @@ template <int N> struct MmaCfg {
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-__device__ __forceinline__ uint32_t fast_pair(int32_t n11, int32_t Nn, int32_t n1a, int32_t aN, int32_t cN, double da,
-                                              const ColRec &cr, double lim_dp, double lim_r2, bool &slow) {
+template <bool THRES>
+__device__ __forceinline__ uint32_t fast_pair(int32_t n11, int32_t Nn, int32_t n1a, int32_t aN, int32_t cN, float fa,
+                                              const ColRec &cr, float lim_dp, float lim_r2, uint32_t m_shift, uint32_t thres,
+                                              bool &slow) {
     const int32_t P = n1a * cr.n1;                       // n1a*n1b
     const int32_t Dn = n11 * Nn - P;
     const int32_t m_pos = min(aN, cr.n1N) - P;           // min(n1a*n0b, n0a*n1b)
-    const int32_t m_neg = min(P, cN - cr.n1N + P);       // min(n1a*n1b, n0a*n0b)
+    const int32_t m_neg = P + min(0, cN - cr.n1N);       // min(n1a*n1b, n0a*n0b)
     const int32_t m = Dn > 0 ? m_pos : m_neg;
-    const double aD = u32_to_double((uint32_t)abs(Dn));
-    const double md = u32_to_double((uint32_t)m);
-    const double den = __dmul_rn(da, cr.prod);
-    const double R = rcp_newton(__dmul_rn(md, den));     // garbage (inf/nan) when den == 0: masked below
-    const double D4 = __dmul_rn(aD, 1.0e4);
-    const double x_dp = __dmul_rn(__dmul_rn(D4, den), R);
-    const double x_r2 = __dmul_rn(__dmul_rn(__dmul_rn(D4, aD), md), R);
-    const double t_dp = __dadd_rn(x_dp, 4503599627370496.0), t_r2 = __dadd_rn(x_r2, 4503599627370496.0);
-    const double f_dp = __dsub_rn(x_dp, __dsub_rn(t_dp, 4503599627370496.0));
-    const double f_r2 = __dsub_rn(x_r2, __dsub_rn(t_r2, 4503599627370496.0));
-    const bool mono = __double2hiint(den) == 0;          // den is an exact integer: 0.0 or >= 1.0
+    const float fD = __int2float_rn(abs(Dn));
+    const float fm = __int2float_rn(m);                  // exact
+    const float den = __fmul_rn(fa, cr.prod);
+    const float R1 = rcp_approx(fm), R2 = rcp_approx(den);     // inf when monomorphic: masked below
+    const float D4 = __fmul_rn(fD, 1.0e4f);
+    const float x_dp = __fmul_rn(D4, R1);
+    const float x_r2 = __fmul_rn(__fmul_rn(D4, fD), R2);
+    const float t_dp = __fadd_rn(x_dp, ROUND_MAGIC), t_r2 = __fadd_rn(x_r2, ROUND_MAGIC);
+    const float f_dp = __fsub_rn(x_dp, __fsub_rn(t_dp, ROUND_MAGIC));    // exact: x - nearest integer
+    const float f_r2 = __fsub_rn(x_r2, __fsub_rn(t_r2, ROUND_MAGIC));
+    const float l_dp = __fmaf_rn(-SCREEN_C_DP, x_dp, lim_dp);            // guard band grows with x
+    const float l_r2 = __fmaf_rn(-SCREEN_C_R2, x_r2, lim_r2);
+    const bool mono = den == 0.0f;                       // den is a product of exact integers: 0 or >= 1
     // !(<=) rather than (>): a NaN from an unforeseen input must fall to the exact path, never pass
-    slow = !mono && (!(fabs(f_dp) <= lim_dp) || !(fabs(f_r2) <= lim_r2) || Dn == 0);
-    const uint32_t w = ((uint32_t)__double2loint(t_r2) & LDX_R2_MASK) | (((uint32_t)__double2loint(t_dp) << LDX_DP_SHIFT) & LDX_DP_MASK);
-    return mono ? (LDX_DP_INT0 | LDX_R2_INT0) : w;
+    // (bitwise, not short-circuit: the sixteen pairs of a chunk must stay one straight-line block)
+    slow = (bool)((uint32_t)!mono & ((uint32_t)!(fabsf(f_dp) <= l_dp) | (uint32_t)!(fabsf(f_r2) <= l_r2) | (uint32_t)(Dn == 0)));
+    uint32_t w = ((uint32_t)__float_as_int(t_r2) & LDX_R2_MASK) | (((uint32_t)__float_as_int(t_dp) << LDX_DP_SHIFT) & LDX_DP_MASK);
+    w = mono ? (LDX_DP_INT0 | LDX_R2_INT0) : w;
+    if (THRES) w |= (((w >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;   // no branch
+    return w;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 
+// One deferred pair {row, col, n11, -} redone with the reference's own operation sequence (finalise_pair).
+__device__ __forceinline__ void settle_slow_pair(const uint4 e, const VarFreq *__restrict__ freq_rows, const FinalCtx &fc,
+                                                 uint32_t m_shift, uint32_t thres, uint32_t *__restrict__ packed, const FixupSink &fix) {
+    const int64_t r = e.x, col = e.y;
+    const VarFreq fa = freq_rows[r], fb = freq_rows[col];
+    const PairFinal f = finalise_pair((int32_t)e.z, fa, fb, fc);       // var_1 = row, var_2 = column
+    uint32_t w = f.packed;
+    w |= (((w >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;
+    const uint64_t idx = (uint64_t)(r * (r - 1) / 2 + col);
+    if (w & LDX_R2_NEARTIE) fixup_append(fix, idx, (int32_t)e.z, fa.n1, fb.n1, w);
+    packed[idx] = w;
+}
+
 // Warp-collective: move a warp's buffered deferred pairs to the global list.  Returns the new count (0).
-__device__ __forceinline__ uint32_t flush_slow(const MmaArgs &A, const uint4 *sbuf, uint32_t cnt, int lane) {
+// Entries that do not fit the list any more (degenerate inputs with far more near-boundary pairs than
+// the ~1% the list is sized for) are settled right here -- slower, never wrong.  Every buffered entry
+// belongs to a chunk whose provisional words this warp has already stored (and __syncwarp orders the
+// warp's stores), so the settled word is the one that stays.
+__device__ __forceinline__ uint32_t flush_slow(const MmaArgs &A, const uint4 *sbuf, uint32_t cnt, int lane, uint32_t m_shift, uint32_t thres) {
     if (cnt == 0) return 0;
     __syncwarp();
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(A.slow_count, cnt);
     base = __shfl_sync(0xffffffffu, base, 0);
-    for (uint32_t i = lane; i < cnt; i += 32)
-        if (base + i < A.slow_cap) A.slow[base + i] = sbuf[i];     // overflow is detected from the count
+    for (uint32_t i = lane; i < cnt; i += 32) {
+        if (base + i < A.slow_cap) A.slow[base + i] = sbuf[i];
+        else settle_slow_pair(sbuf[i], A.freq_rows, A.fc, m_shift, thres, A.packed, A.fix);
+    }
     __syncwarp();
     return 0;
 }
 
-// The pairs the epilogue's screening could not settle, redone with the reference's own operation
-// sequence (finalise_pair): one thread per pair, fully parallel.  The last block to finish publishes
-// the call's completion record (near-tie count, error flag, sequence number) to the host mailbox.
+// The pairs the epilogue's screening could not settle: one thread per pair, fully parallel.  The last
+// block to finish publishes the call's completion record (near-tie count, error flag, sequence number)
+// to the host mailbox.
 __global__ void __launch_bounds__(256)
 slow_pairs_kernel(const uint4 *__restrict__ list, uint32_t *__restrict__ counters /* d_fix_count */, uint32_t cap,
                   const VarFreq *__restrict__ freq_rows, FinalCtx fc, int measure, int has_thres, int thres_e4,
                   uint32_t *__restrict__ packed, FixupSink fix, volatile uint32_t *mailbox, uint32_t seq) {
     const uint32_t total = counters[2];
-    const uint32_t n = total < cap ? total : cap;
+    const uint32_t n = total < cap ? total : cap;              // the rest was settled in the epilogue (flush_slow)
     const uint32_t m_shift = measure == LDX_MEASURE_R2 ? 0u : (uint32_t)LDX_DP_SHIFT;
     const uint32_t thres = has_thres ? (uint32_t)thres_e4 : 0u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint4 e = list[i];
-        const int64_t r = e.x, col = e.y;
-        const VarFreq fa = freq_rows[r], fb = freq_rows[col];
-        const PairFinal f = finalise_pair((int32_t)e.z, fa, fb, fc);       // var_1 = row, var_2 = column
-        uint32_t w = f.packed;
-        w |= (((w >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;
-        const uint64_t idx = (uint64_t)(r * (r - 1) / 2 + col);
-        if (w & LDX_R2_NEARTIE) fixup_append(fix, idx, (int32_t)e.z, fa.n1, fb.n1, w);
-        packed[idx] = w;
-    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        settle_slow_pair(list[i], freq_rows, fc, m_shift, thres, packed, fix);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (total > cap) atomicExch(&counters[1], 2u);                    // deferred-pair list overflow: results incomplete
         const uint32_t ticket = atomicAdd(&counters[3], 1u);
         if (ticket == gridDim.x - 1) {
             __threadfence();
@@ -386,7 +410,7 @@ slow_pairs_kernel(const uint4 *__restrict__ list, uint32_t *__restrict__ counter
     }
 }
 
-template <int N, bool WANT_N11>
+template <int N, bool WANT_N11, bool THRES>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 triangle_mma_kernel(const MmaArgs A) {
     using Cfg = MmaCfg<N>;
@@ -555,7 +579,7 @@ triangle_mma_kernel(const MmaArgs A) {
         const uint32_t m_shift = A.measure == LDX_MEASURE_R2 ? 0u : (uint32_t)LDX_DP_SHIFT;
         const uint32_t thres = A.has_thres ? (uint32_t)A.thres_e4 : 0u;      // rounded values are >= 0: 0 flags nothing
         const int32_t Nn = A.n_sel;
-        const double lim_dp = A.lim_dp, lim_r2 = A.lim_r2;
+        const float lim_dp = A.lim_dp, lim_r2 = A.lim_r2;
         uint32_t tl = 0;
         for (int t = blockIdx.x; t < A.n_tiles; t += gridDim.x, ++tl) {
             const uint32_t buf = tl % Cfg::ACC_BUFS;
@@ -564,7 +588,7 @@ triangle_mma_kernel(const MmaArgs A) {
             ColRec *cols = col_s + (tl & 1) * N;
             for (int i = et; i < N; i += 32 * N_EPI_WARPS) {      // column variants of this tile
                 const int32_t n1 = A.freq_rows[c0 + i].n1;
-                ColRec cr; cr.n1 = n1; cr.n1N = n1 * Nn; cr.prod = u32_to_double((uint32_t)(n1 * (Nn - n1)));
+                ColRec cr; cr.n1 = n1; cr.n1N = n1 * Nn; cr.prod = __int2float_rn(n1 * (Nn - n1)); cr.pad = 0;
                 cols[i] = cr;
             }
             asm volatile("bar.sync 1, %0;" :: "n"(32 * N_EPI_WARPS) : "memory");
@@ -572,7 +596,7 @@ triangle_mma_kernel(const MmaArgs A) {
             // row variant of this lane: n1a, n1a*N, N^2 - n1a*N, n1a*n0a
             const int32_t n1a = A.freq_rows[r].n1;
             const int32_t aN = n1a * Nn, cN = Nn * Nn - aN;
-            const double da = u32_to_double((uint32_t)(n1a * (Nn - n1a)));
+            const float fa = __int2float_rn(n1a * (Nn - n1a));
             if (!mbar_wait(tmem_full + 8 * buf, (tl / Cfg::ACC_BUFS) & 1, abort_s, A.error_flag, 128)) goto done;
             tc_fence_after();
             if (A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[1 + 2 * tl] = gtime();   // accumulator ready
@@ -596,8 +620,7 @@ triangle_mma_kernel(const MmaArgs A) {
                     for (int j = j0; j < j0 + 4; ++j) {
                         const ColRec cr = cols[c + j];
                         bool s;
-                        uint32_t w = fast_pair((int32_t)(acc[j] >> ACC_SHIFT), Nn, n1a, aN, cN, da, cr, lim_dp, lim_r2, s);
-                        w |= (((w >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;   // no branch
+                        const uint32_t w = fast_pair<THRES>((int32_t)(acc[j] >> ACC_SHIFT), Nn, n1a, aN, cN, fa, cr, lim_dp, lim_r2, m_shift, thres, s);
                         slow |= (uint32_t)s << j;
                         word[j - j0] = w;
                     }
@@ -616,7 +639,7 @@ triangle_mma_kernel(const MmaArgs A) {
                 while (true) {
                     const uint32_t bal = __ballot_sync(0xffffffffu, slow != 0);
                     if (bal == 0) break;
-                    if (slow_cnt > SLOW_BUF - 32) slow_cnt = flush_slow(A, sbuf, slow_cnt, lane);
+                    if (slow_cnt > SLOW_BUF - 32) slow_cnt = flush_slow(A, sbuf, slow_cnt, lane, m_shift, thres);
                     if (slow) {
                         const int j = __ffs(slow) - 1;
                         slow &= slow - 1;
@@ -657,7 +680,7 @@ triangle_mma_kernel(const MmaArgs A) {
             if (lane == 0) mbar_arrive(tmem_empty + 8 * buf);
             if (A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[2 + 2 * tl] = gtime();       // epilogue of this tile done
         }
-        flush_slow(A, sbuf, slow_cnt, lane);
+        flush_slow(A, sbuf, slow_cnt, lane, m_shift, thres);
     }
 done:
     tc_fence_before();
@@ -673,22 +696,23 @@ bool triangle_mma_available() { return true; }
 // haplotypes fewer than 1% of the pairs are deferred; beyond it ENGINE_AUTO uses the popcount engine.
 int triangle_mma_max_haplotypes() { return 8192; }
 
-template <int N, bool WANT_N11>
+template <int N, bool WANT_N11, bool THRES>
 static int launch_tiles_t(ldx_ctx *ctx, const MmaArgs &A) {
     static bool attr_set = false;
     if (!attr_set) {
-        LDX_CUDA(cudaFuncSetAttribute(triangle_mma_kernel<N, WANT_N11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmaCfg<N>::SMEM));
+        LDX_CUDA(cudaFuncSetAttribute(triangle_mma_kernel<N, WANT_N11, THRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmaCfg<N>::SMEM));
         attr_set = true;
     }
     const int grid = A.n_tiles < ctx->sm_count ? A.n_tiles : ctx->sm_count;     // persistent: one CTA per SM
-    triangle_mma_kernel<N, WANT_N11><<<grid, MMA_THREADS, MmaCfg<N>::SMEM, ctx->stream>>>(A);
+    triangle_mma_kernel<N, WANT_N11, THRES><<<grid, MMA_THREADS, MmaCfg<N>::SMEM, ctx->stream>>>(A);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
     return LDX_OK;
 }
 template <int N>
 static int launch_tiles(ldx_ctx *ctx, const MmaArgs &A) {
-    return A.n11 ? launch_tiles_t<N, true>(ctx, A) : launch_tiles_t<N, false>(ctx, A);
+    if (A.has_thres) return A.n11 ? launch_tiles_t<N, true, true>(ctx, A) : launch_tiles_t<N, false, true>(ctx, A);
+    return A.n11 ? launch_tiles_t<N, true, false>(ctx, A) : launch_tiles_t<N, false, false>(ctx, A);
 }
 
 int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int measure, int has_thres,
@@ -762,12 +786,13 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
     A.v = v; A.measure = measure; A.has_thres = has_thres; A.thres_e4 = thres_e4;
     A.packed = d_packed; A.n11 = d_n11;
     A.n_sel = s->n_sel;
-    {   // guard band of the screening arithmetic (see fast_pair); beyond N = 32768 the int32 products
-        // would overflow and the band would swallow everything: every pair then takes the exact path
+    {   // guard band of the screening arithmetic (see fast_pair).  Its fp32 half needs m and n1*n0 exact
+        // (<= 2^24, i.e. N <= 8192); should a caller ever get past the check above with more, every pair
+        // takes the exact path.
         const double n = (double)s->n_sel, g = 1.0e4 * 16.0 * 1.1102230246251565e-16 * n * n;
-        const bool ok = s->n_sel <= 32768;
-        A.lim_r2 = ok ? 0.5 - (g + 1.0e-6) : -1.0;
-        A.lim_dp = ok ? 0.5 - (0.5 * g + 1.0e-6) : -1.0;
+        const bool ok = s->n_sel <= 8192;
+        A.lim_r2 = ok ? (float)(0.5 - (g + 1.0e-5)) : -1.0f;
+        A.lim_dp = ok ? (float)(0.5 - (0.5 * g + 1.0e-5)) : -1.0f;
     }
     A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity};
     A.error_flag = reinterpret_cast<int32_t *>(ctx->d_fix_count + 1);
@@ -778,12 +803,12 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
     switch (n_tile) {
         case 64: rc = launch_tiles<64>(ctx, A); break;
         case 128: rc = launch_tiles<128>(ctx, A); break;
-        case 256: rc = launch_tiles<256>(ctx, A); break;
-        default: return set_error(LDX_ERR_ARG, "tcgen05 tile width must be 64, 128 or 256");
+        default: return set_error(LDX_ERR_ARG, "tcgen05 tile width must be 64 or 128");
     }
     if (rc != LDX_OK) return rc;
     // deferred pairs + completion record (d_fix_count: [0] near-ties, [1] error flag, [2] deferred pairs, [3] ticket)
-    const int sgrid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 2, std::max<uint64_t>(1, n_pairs / (1u << 20)));
+    // ~1% of the pairs are deferred: size the grid for two pairs per thread at that rate
+    const int sgrid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 4, std::max<uint64_t>(1, n_pairs / (1u << 16)));
     slow_pairs_kernel<<<sgrid, 256, 0, ctx->stream>>>(d_slow, ctx->d_fix_count, A.slow_cap, d_freq_rows, s->fc, measure, has_thres,
                                                       thres_e4, d_packed, A.fix, publish_seq ? ctx->d_mailbox : nullptr, publish_seq);
     ctx->launches++;

@@ -1,6 +1,6 @@
 """Steady-state throughput of the all-pairs engines on large variant sets (kernel-only, CUDA events).
 
-    python tools/bench_large.py [V ...] [--tiles 64,128,256] [--engine mma|popc] [--reps 3] [--trace]
+    python tools/bench_large.py [V ...] [--tiles 64,128] [--engine mma|popc] [--reps 3] [--trace]
 
 Prints pairs/s and the int8 tensor-pipe fraction for each (V, tile).  With --trace it also dumps
 the per-chunk pipeline stamps of CTA 0 (see ldx_debug_trace in include/ldx.h)."""
@@ -23,7 +23,7 @@ from ld_tools_b200.synth import random_planes  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("v", nargs="*", type=int, default=[2000, 8192, 32768])
-    ap.add_argument("--tiles", default="64,128,256")
+    ap.add_argument("--tiles", default="64,128")
     ap.add_argument("--engine", default="mma")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--n-hap", type=int, default=5008)

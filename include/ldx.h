@@ -102,8 +102,8 @@ int32_t ldx_set_tuning(ldx_ctx *ctx, int32_t key, int32_t value);
 /* Diagnostics: with enable != 0 the tcgen05 all-pairs kernel's first CTA records %globaltimer
  * stamps (ns): [0] prologue done, [1]/[2] accumulator ready / epilogue done of its 1st tile,
  * [3]/[4] 2nd tile, [5]/[6] 3rd tile; [8+g] widener done / [64+g] MMA start / [128+g] producer issue /
- * [192+g] bits landed, for its first 48 chunks g.  stamps8 (may be NULL, else 256 entries) receives
- * the last recording. */
+ * [192+g] bits landed / [256+g] operand stage free (widener) / [320+g] widening stores issued, for its
+ * first 48 pipeline stages g.  stamps8 (may be NULL, else 512 entries) receives the last recording. */
 int32_t ldx_debug_trace(ldx_ctx *ctx, int32_t enable, uint64_t *stamps8);
 int32_t ldx_sm_count(ldx_ctx *ctx, int32_t *n_out);
 /* Kernels launched by this ctx since creation (bench.py's gpu_launches claim). */

@@ -135,6 +135,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 16 lanes x 256 bits, four times along the columns (32 columns): see the epilogue for the register map.
+__device__ __forceinline__ void tmem_ld16x256(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
 // [0,14) start >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, 1) | [32,46) SBO >> 4 = 1024 B
 // between 8-row groups | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B).
@@ -262,24 +271,25 @@ struct MmaArgs {
     uint32_t *packed; int32_t *n11;
     FixupSink fix;
     int32_t *error_flag;
-    unsigned long long *trace;   // optional [256]: globaltimer stamps of CTA 0 (diagnostics)
+    unsigned long long *trace;   // optional [512]: globaltimer stamps of CTA 0 (diagnostics)
     int dbg;                     // diagnostics: 1 = skip the widening stores (results invalid)
 };
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
-constexpr int N_WIDEN_WARPS = 8, N_EPI_WARPS = 8;   // wideners: two teams of 4 warps taking alternate pipeline stages
-constexpr int WIDEN_TEAMS = 2, TEAM_WARPS = N_WIDEN_WARPS / WIDEN_TEAMS;
+constexpr int N_WIDEN_WARPS = 16, N_EPI_WARPS = 8;  // wideners: four teams of 4 warps, team k takes pipeline stages g = k mod 4
+constexpr int WIDEN_TEAMS = 4, TEAM_WARPS = N_WIDEN_WARPS / WIDEN_TEAMS;
 // Warp roles, aligned to warpgroups (4 warps) so that setmaxnreg can move registers between them:
 //   warps 0-3   producer (0), MMA issuer (1), two spare warps      -> 40 registers
-//   warps 4-11  wideners                                           -> 56 registers
-//   warps 12-19 epilogue (fp64 heavy, pairs interleaved)            -> 160 registers
-// The pool is the CTA's own 640 x 96 registers: setmaxnreg.inc BLOCKS until enough have been released,
-// so the budget must close: 128*(96-40) + 256*(96-56) = 17408 freed >= 256*(160-96) = 16384 needed.
-constexpr int REGS_LAUNCH = 96, REGS_CTRL = 40, REGS_WIDEN = 56, REGS_EPI = 160;
-static_assert(128 * (REGS_LAUNCH - REGS_CTRL) + 256 * (REGS_LAUNCH - REGS_WIDEN) >= 256 * (REGS_EPI - REGS_LAUNCH), "setmaxnreg budget");
+//   warps 4-19  wideners (latency-bound: many warps, few registers) -> 56 registers
+//   warps 20-27 epilogue (sixteen pairs in flight per lane)         -> 104 registers
+// The pool is the CTA's own 896 x 72 registers: setmaxnreg.inc BLOCKS until enough have been released,
+// so the budget must close: 128*(72-40) + 512*(72-56) = 12288 freed >= 256*(104-72) = 8192 needed.
+constexpr int REGS_LAUNCH = 72, REGS_CTRL = 40, REGS_WIDEN = 56, REGS_EPI = 104;
+static_assert(128 * (REGS_LAUNCH - REGS_CTRL) + 32 * N_WIDEN_WARPS * (REGS_LAUNCH - REGS_WIDEN) >= 32 * N_EPI_WARPS * (REGS_EPI - REGS_LAUNCH), "setmaxnreg budget");
 constexpr int FIRST_WIDEN_WARP = 4, FIRST_EPI_WARP = FIRST_WIDEN_WARP + N_WIDEN_WARPS;
-constexpr int MMA_THREADS = 32 * (FIRST_EPI_WARP + N_EPI_WARPS);   // 640
+constexpr int MMA_THREADS = 32 * (FIRST_EPI_WARP + N_EPI_WARPS);   // 896
+static_assert(MMA_THREADS * REGS_LAUNCH <= 65536, "register file");
 constexpr int SLOW_BUF = 64;                                           // deferred pairs buffered per epilogue warp
 constexpr int EPI_PITCH = 20;                                          // words per staged row: 16-byte aligned rows, conflict-free STS.128
 
@@ -296,7 +306,7 @@ template <int N> struct MmaCfg {
     static constexpr int CH = 2;                              // 128-haplotype chunks per pipeline stage
     static constexpr int B_ROWS = N < 128 ? N : 128;          // column variants per 128-row bit block
     static constexpr int B_PARTS = (N + 127) / 128;
-    static constexpr int OP_STAGES = N <= 128 ? 3 : 2;        // widened operand stages (A in TMEM, B in smem)
+    static constexpr int OP_STAGES = WIDEN_TEAMS;             // widened operand stages (A in TMEM, B in smem): one per team
     static constexpr int OP_BYTES = N * KCHUNK * CH;          // B tile of one stage: CH swizzle atoms side by side
     static constexpr int BIT_STAGES = N <= 128 ? 8 : 4;       // bit blocks in flight from L2 (latency: deep)
     static constexpr int BIT_BYTES = ROWS * 16 * CH;
@@ -410,7 +420,7 @@ slow_pairs_kernel(const uint4 *__restrict__ list, uint32_t *__restrict__ counter
     }
 }
 
-template <int N, bool WANT_N11, bool THRES>
+template <int N, bool WANT_N11, bool THRES, bool TRACE>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 triangle_mma_kernel(const MmaArgs A) {
     using Cfg = MmaCfg<N>;
@@ -447,7 +457,7 @@ triangle_mma_kernel(const MmaArgs A) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
-    if (A.trace && blockIdx.x == 0 && threadIdx.x == 0) A.trace[0] = gtime();   // prologue done
+    if (TRACE && A.trace && blockIdx.x == 0 && threadIdx.x == 0) A.trace[0] = gtime();   // prologue done
 
     const int ks_count = kc_count / Cfg::CH;                  // pipeline stages per tile (kc_count is even)
     if (warp == 0) {
@@ -467,7 +477,7 @@ triangle_mma_kernel(const MmaArgs A) {
                 const uint32_t dst = smem_u32(bit_s + s * Cfg::BIT_BYTES);
                 const int kc = ks * Cfg::CH;
                 if (elect_one()) {
-                    if (A.trace && blockIdx.x == 0 && g < 48) A.trace[128 + g] = gtime();
+                    if (TRACE && A.trace && blockIdx.x == 0 && g < 48) A.trace[128 + g] = gtime();
                     mbar_arrive_expect_tx(bar, Cfg::BIT_BYTES);
                     bulk_g2s(dst, a_src + (int64_t)kc * 128, Cfg::CH * MMA_M * 16, bar);       // [CH][128] rows
 #pragma unroll
@@ -503,7 +513,7 @@ triangle_mma_kernel(const MmaArgs A) {
                 const uint64_t db = make_smem_desc(smem_u32(op_s + s * Cfg::OP_BYTES));
                 const uint32_t ta = tmem_base + Cfg::TMEM_A0 + s * Cfg::A_COLS;
                 if (elect_one()) {
-                    if (A.trace && blockIdx.x == 0 && g < 48) A.trace[64 + g] = gtime();
+                    if (TRACE && A.trace && blockIdx.x == 0 && g < 48) A.trace[64 + g] = gtime();
 #pragma unroll
                     for (int k = 0; k < Cfg::CH * KCHUNK / MMA_K; ++k)     // K = 32: 8 TMEM columns of A; B: atom k/4 (N*128 B apart), +32 B per step inside
                         umma_i8_ts(tmem_acc, ta + 8 * k, db + (uint64_t)((k >> 2) * (N * KCHUNK >> 4) + (k & 3) * 2), idesc, (uint32_t)((ks | k) != 0));
@@ -532,13 +542,14 @@ triangle_mma_kernel(const MmaArgs A) {
                 const uint32_t sb = g % Cfg::BIT_STAGES, itb = g / Cfg::BIT_STAGES;
                 const uint32_t so = g % Cfg::OP_STAGES, ito = g / Cfg::OP_STAGES;
                 if (!mbar_wait(bit_full + 8 * sb, itb & 1, abort_s, A.error_flag)) goto done;
-                if (A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[192 + g] = gtime();
+                if (TRACE && A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[192 + g] = gtime();
                 const uint4 *bsrc = reinterpret_cast<const uint4 *>(bit_s + sb * Cfg::BIT_BYTES);
                 uint4 ba[Cfg::CH];
 #pragma unroll
                 for (int c = 0; c < Cfg::CH; ++c) ba[c] = bsrc[c * MMA_M + wt];
                 if (!mbar_wait(op_empty + 8 * so, (ito & 1) ^ 1, abort_s, A.error_flag)) goto done;
                 tc_fence_after();
+                if (TRACE && A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[256 + g] = gtime();
 #pragma unroll
                 for (int c = 0; c < Cfg::CH; ++c) {
                     const uint32_t w[4] = {ba[c].x, ba[c].y, ba[c].z, ba[c].w};
@@ -558,20 +569,27 @@ triangle_mma_kernel(const MmaArgs A) {
                             expand_row<true>(ops + c * (N * KCHUNK) + (wt + i * 128) * KCHUNK, wt & 7,
                                              bsrc[Cfg::CH * MMA_M + (i * Cfg::CH + c) * Cfg::B_ROWS + wt]);
                 }
+                if (TRACE && A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[320 + g] = gtime();
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(op_full + 8 * so); mbar_arrive(bit_empty + 8 * sb); }
-                if (A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[8 + g] = gtime();
+                if (TRACE && A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[8 + g] = gtime();
             }
         }
     } else {
-        // ===== epilogue.  Warp w may only touch TMEM lanes 32*(w%4) .. +31
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+        // ===== epilogue.  Warp w may only touch TMEM lanes 32*(w%4) .. +31.  Accumulators are read with
+        // the 16-lane x 256-bit shape: register i = 4k + 2g + e of lane l holds
+        //     row  rmin + l/4 + 8g,   column  cb + 8k + 2(l%4) + e            (tools/probe/tmem_layout.cu)
+        // so a lane works on TWO row variants and eight column variants per load, and the four lanes of
+        // a row own 8 consecutive result words (one 32-byte sector): results go straight from registers
+        // to global memory, no transposition through shared memory.
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         const int ew = warp - FIRST_EPI_WARP;                     // 0..7
         const int quad = warp & 3, half = ew >> 2;
         const int et = ew * 32 + lane;                            // 0..255
+        const int lq = lane >> 2, lr = lane & 3;
         uint32_t *stage = epi_s + ew * (32 * EPI_PITCH + SLOW_BUF * 4);
         uint4 *sbuf = reinterpret_cast<uint4 *>(stage + 32 * EPI_PITCH);
         uint32_t slow_cnt = 0;                                    // warp-uniform: entries buffered in sbuf
@@ -592,93 +610,97 @@ triangle_mma_kernel(const MmaArgs A) {
                 cols[i] = cr;
             }
             asm volatile("bar.sync 1, %0;" :: "n"(32 * N_EPI_WARPS) : "memory");
-            const int64_t r = r0 + quad * 32 + lane;
-            // row variant of this lane: n1a, n1a*N, N^2 - n1a*N, n1a*n0a
-            const int32_t n1a = A.freq_rows[r].n1;
-            const int32_t aN = n1a * Nn, cN = Nn * Nn - aN;
-            const float fa = __int2float_rn(n1a * (Nn - n1a));
             if (!mbar_wait(tmem_full + 8 * buf, (tl / Cfg::ACC_BUFS) & 1, abort_s, A.error_flag, 128)) goto done;
             tc_fence_after();
-            if (A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[1 + 2 * tl] = gtime();   // accumulator ready
-            const uint32_t tmem_acc = tmem_base + buf * N + ((uint32_t)(quad * 32) << 16);
-            const int64_t warp_r0 = r0 + quad * 32, warp_rmax = warp_r0 + 31;
-            // write-out: lane handles column (lane & 15) of rows warp_r0 + (lane >> 4) + 2i; the packed
-            // index advances by tri(rg + 2) - tri(rg) = 2 rg + 1 per step
-            const int64_t wr0 = warp_r0 + (lane >> 4);
-            const int64_t out0 = wr0 * (wr0 - 1) / 2 + c0 + (lane & 15);
+            if (TRACE && A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[1 + 2 * tl] = gtime();   // accumulator ready
 #pragma unroll 1
-            for (int c = half * (N / 2); c < (half + 1) * (N / 2); c += 16) {
-                if (c0 + c >= warp_rmax || c0 + c >= A.v) break;        // warp-uniform: nothing below the diagonal
-                uint32_t acc[16];
-                tmem_ld16(tmem_acc + (uint32_t)c, acc);
-                uint32_t slow = 0;
-                // four pairs at a time: enough independent fp64 chains to cover the pipe latency
-#pragma unroll
-                for (int j0 = 0; j0 < 16; j0 += 4) {
-                    uint32_t word[4];
-#pragma unroll
-                    for (int j = j0; j < j0 + 4; ++j) {
-                        const ColRec cr = cols[c + j];
-                        bool s;
-                        const uint32_t w = fast_pair<THRES>((int32_t)(acc[j] >> ACC_SHIFT), Nn, n1a, aN, cN, fa, cr, lim_dp, lim_r2, m_shift, thres, s);
-                        slow |= (uint32_t)s << j;
-                        word[j - j0] = w;
-                    }
-                    *reinterpret_cast<uint4 *>(stage + lane * EPI_PITCH + j0) = make_uint4(word[0], word[1], word[2], word[3]);
-                }
-                {   // only pairs of the triangle matter: columns c0+c+j < r, r < v
-                    const int64_t nvalid = r < A.v ? r - (c0 + c) : 0;
-                    slow &= nvalid >= 16 ? 0xffffu : nvalid > 0 ? (1u << (int)nvalid) - 1u : 0u;
-                }
-                // Rare (about 6 * guard band of the pairs): a screened value sits next to a rounding
-                // boundary, or D is exactly 0 for two polymorphic variants.  Those pairs are not redone
-                // here -- one lane running the reference's operation sequence would stall the warp for
-                // a microsecond -- but queued for slow_pairs_kernel, which runs after this kernel and
-                // overwrites their words.  The queue is per warp in shared memory (ballot compaction,
-                // no atomics) and is flushed to the global list when it fills up and at the end.
-                while (true) {
-                    const uint32_t bal = __ballot_sync(0xffffffffu, slow != 0);
-                    if (bal == 0) break;
-                    if (slow_cnt > SLOW_BUF - 32) slow_cnt = flush_slow(A, sbuf, slow_cnt, lane, m_shift, thres);
-                    if (slow) {
-                        const int j = __ffs(slow) - 1;
-                        slow &= slow - 1;
-                        uint32_t a = acc[0];
-#pragma unroll
-                        for (int jj = 1; jj < 16; ++jj) a = (j == jj) ? acc[jj] : a;
-                        sbuf[slow_cnt + __popc(bal & lanemask_lt)] = make_uint4((uint32_t)r, (uint32_t)(c0 + c + j), a >> ACC_SHIFT, 0u);
-                    }
-                    slow_cnt += __popc(bal);
-                    __syncwarp();
-                }
-                if (WANT_N11) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int64_t col = c0 + c + j;
-                        if (r < A.v && col < r) A.n11[r * (r - 1) / 2 + col] = (int32_t)(acc[j] >> ACC_SHIFT);
-                    }
-                }
-                __syncwarp();
-                // transposed write-out: 16 lanes cover the 16 columns of one row (64 contiguous bytes)
-                {
-                    int64_t rg = wr0, idx = out0 + c;
-                    const int64_t cg = c0 + c + (lane & 15);
-                    const uint32_t *src = stage + (lane >> 4) * EPI_PITCH + (lane & 15);
+            for (int h = 0; h < 2; ++h) {
+                const int64_t rmin = r0 + quad * 32 + 16 * h;    // this pass: rows rmin .. rmin + 15
+                if (rmin >= A.v) break;                           // warp-uniform
+                // the lane's two row variants: n1a, n1a*N, N^2 - n1a*N, n1a*n0a
+                const int64_t ra = rmin + lq, rb = ra + 8;
+                const int32_t n1a = A.freq_rows[ra].n1, n1b = A.freq_rows[rb].n1;
+                const int32_t aNa = n1a * Nn, cNa = Nn * Nn - aNa, aNb = n1b * Nn, cNb = Nn * Nn - aNb;
+                const float faa = __int2float_rn(n1a * (Nn - n1a)), fab = __int2float_rn(n1b * (Nn - n1b));
+                // result words of (row, column c0 + 2 lr + j) live at p?[j]
+                uint32_t *pa = A.packed + (ra * (ra - 1) / 2 + c0 + 2 * lr);
+                uint32_t *pb = A.packed + (rb * (rb - 1) / 2 + c0 + 2 * lr);
+                int32_t *qa = WANT_N11 ? A.n11 + (ra * (ra - 1) / 2 + c0 + 2 * lr) : nullptr;
+                int32_t *qb = WANT_N11 ? A.n11 + (rb * (rb - 1) / 2 + c0 + 2 * lr) : nullptr;
+                const uint32_t tmem_acc = tmem_base + buf * N + ((uint32_t)(quad * 32 + 16 * h) << 16);
+#pragma unroll 1
+                for (int cb = half * (N / 2); cb < (half + 1) * (N / 2); cb += 32) {
+                    const int64_t cg0 = c0 + cb;                  // first column of this load
+                    if (cg0 >= rmin + 15 || cg0 >= A.v) break;    // warp-uniform: nothing below the diagonal
+                    uint32_t acc[16];
+                    tmem_ld16x256(tmem_acc + (uint32_t)cb, acc);
+                    uint32_t word[16];
+                    uint32_t slow = 0;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const uint32_t w = src[2 * i * EPI_PITCH];
-                        if (rg < A.v && cg < rg) A.packed[idx] = w;
-                        idx += 2 * rg + 1;
-                        rg += 2;
+                        const int k = i >> 2, g = (i >> 1) & 1, e = i & 1;
+                        const ColRec cr = cols[cb + 8 * k + 2 * lr + e];
+                        bool s;
+                        word[i] = fast_pair<THRES>((int32_t)(acc[i] >> ACC_SHIFT), Nn, g ? n1b : n1a, g ? aNb : aNa, g ? cNb : cNa,
+                                                   g ? fab : faa, cr, lim_dp, lim_r2, m_shift, thres, s);
+                        slow |= (uint32_t)s << i;
+                    }
+                    const bool interior = cg0 + 32 <= rmin && rmin + 15 < A.v;   // warp-uniform: every pair is below the diagonal
+                    if (interior) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int k = i >> 2, g = (i >> 1) & 1, e = i & 1;
+                            (g ? pb : pa)[cb + 8 * k + e] = word[i];
+                            if (WANT_N11) (g ? qb : qa)[cb + 8 * k + e] = (int32_t)(acc[i] >> ACC_SHIFT);
+                        }
+                    } else {
+                        uint32_t valid = 0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int k = i >> 2, g = (i >> 1) & 1, e = i & 1;
+                            const int64_t row = g ? rb : ra, col = cg0 + 8 * k + 2 * lr + e;
+                            if (row < A.v && col < row) {
+                                valid |= 1u << i;
+                                (g ? pb : pa)[cb + 8 * k + e] = word[i];
+                                if (WANT_N11) (g ? qb : qa)[cb + 8 * k + e] = (int32_t)(acc[i] >> ACC_SHIFT);
+                            }
+                        }
+                        slow &= valid;                            // only pairs of the triangle matter
+                    }
+                    // Rare (about 1% of the pairs): a screened value sits next to a rounding boundary, or D
+                    // is exactly 0 for two polymorphic variants.  Those pairs are not redone here -- one lane
+                    // running the reference's operation sequence would stall the warp for a microsecond --
+                    // but queued for slow_pairs_kernel, which runs after this kernel and overwrites their
+                    // words.  The queue is per warp in shared memory (ballot compaction, no atomics) and is
+                    // flushed to the global list when it fills up and at the end.
+                    if (__any_sync(0xffffffffu, slow != 0)) {
+                        // park the counts in shared memory: a lane then fetches its flagged ones by index
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<uint4 *>(stage + lane * EPI_PITCH + i) = make_uint4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                        __syncwarp();
+                        while (true) {
+                            const uint32_t bal = __ballot_sync(0xffffffffu, slow != 0);
+                            if (bal == 0) break;
+                            if (slow_cnt > SLOW_BUF - 32) slow_cnt = flush_slow(A, sbuf, slow_cnt, lane, m_shift, thres);
+                            if (slow) {
+                                const int i = __ffs(slow) - 1;
+                                slow &= slow - 1;
+                                const uint32_t a = stage[lane * EPI_PITCH + i];
+                                const int64_t row = (i & 2) ? rb : ra, col = cg0 + 8 * (i >> 2) + 2 * lr + (i & 1);
+                                sbuf[slow_cnt + __popc(bal & lanemask_lt)] = make_uint4((uint32_t)row, (uint32_t)col, a >> ACC_SHIFT, 0u);
+                            }
+                            slow_cnt += __popc(bal);
+                            __syncwarp();
+                        }
                     }
                 }
-                __syncwarp();
             }
             // this warp's TMEM reads of the tile are complete: hand the accumulator back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + 8 * buf);
-            if (A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[2 + 2 * tl] = gtime();       // epilogue of this tile done
+            if (TRACE && A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[2 + 2 * tl] = gtime();       // epilogue of this tile done
         }
         flush_slow(A, sbuf, slow_cnt, lane, m_shift, thres);
     }
@@ -696,21 +718,22 @@ bool triangle_mma_available() { return true; }
 // haplotypes fewer than 1% of the pairs are deferred; beyond it ENGINE_AUTO uses the popcount engine.
 int triangle_mma_max_haplotypes() { return 8192; }
 
-template <int N, bool WANT_N11, bool THRES>
+template <int N, bool WANT_N11, bool THRES, bool TRACE = false>
 static int launch_tiles_t(ldx_ctx *ctx, const MmaArgs &A) {
     static bool attr_set = false;
     if (!attr_set) {
-        LDX_CUDA(cudaFuncSetAttribute(triangle_mma_kernel<N, WANT_N11, THRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmaCfg<N>::SMEM));
+        LDX_CUDA(cudaFuncSetAttribute(triangle_mma_kernel<N, WANT_N11, THRES, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmaCfg<N>::SMEM));
         attr_set = true;
     }
     const int grid = A.n_tiles < ctx->sm_count ? A.n_tiles : ctx->sm_count;     // persistent: one CTA per SM
-    triangle_mma_kernel<N, WANT_N11, THRES><<<grid, MMA_THREADS, MmaCfg<N>::SMEM, ctx->stream>>>(A);
+    triangle_mma_kernel<N, WANT_N11, THRES, TRACE><<<grid, MMA_THREADS, MmaCfg<N>::SMEM, ctx->stream>>>(A);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
     return LDX_OK;
 }
 template <int N>
 static int launch_tiles(ldx_ctx *ctx, const MmaArgs &A) {
+    if (A.trace && !A.has_thres && !A.n11) return launch_tiles_t<N, false, false, true>(ctx, A);   // diagnostics build of the kernel
     if (A.has_thres) return A.n11 ? launch_tiles_t<N, true, true>(ctx, A) : launch_tiles_t<N, false, true>(ctx, A);
     return A.n11 ? launch_tiles_t<N, true, false>(ctx, A) : launch_tiles_t<N, false, false>(ctx, A);
 }

@@ -63,7 +63,7 @@ def main():
             pps = n_pairs / best
             print(f"V={v} tile={tile} {best * 1e3:.3f} ms  {pps:.3e} pairs/s  int8 frac {pps * 2 * args.n_hap / peak_i8:.3f}", flush=True)
             if args.trace and engine == ENGINE_MMA:
-                s = np.zeros(256, dtype=np.uint64)
+                s = np.zeros(512, dtype=np.uint64)
                 ctx._lib.ldx_debug_trace(ctx._h, 1, ptr(s))
                 s = s.astype(np.int64)
                 t0 = s[0]
@@ -71,8 +71,9 @@ def main():
                 for g in range(0, 48, 1):
                     if not s[64 + g]:
                         break
-                    print("  g=%2d prod %.2f bits %.2f widened %.2f mma %.2f" %
-                          (g, (s[128 + g] - t0) / 1e3, (s[192 + g] - t0) / 1e3, (s[8 + g] - t0) / 1e3, (s[64 + g] - t0) / 1e3))
+                    print("  g=%2d prod %.2f bits %.2f opfree %.2f stored %.2f widened %.2f mma %.2f" %
+                          (g, (s[128 + g] - t0) / 1e3, (s[192 + g] - t0) / 1e3, (s[256 + g] - t0) / 1e3, (s[320 + g] - t0) / 1e3,
+                           (s[8 + g] - t0) / 1e3, (s[64 + g] - t0) / 1e3))
         del out
         st.close()
     ctx.close()

@@ -272,7 +272,8 @@ struct MmaArgs {
     FixupSink fix;
     int32_t *error_flag;
     unsigned long long *trace;   // optional [512]: globaltimer stamps of CTA 0 (diagnostics)
-    int dbg;                     // diagnostics: 1 = skip the widening stores (results invalid)
+    int dbg;                     // diagnostics build only (LDX_DEBUG_MMA; results invalid): 1 skip row-operand widening,
+                                 // 2 skip column-operand widening, 4 skip the epilogue arithmetic, 8 skip the MMAs
 };
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
@@ -331,7 +332,7 @@ __device__ __forceinline__ uint32_t fast_pair(int32_t n11, int32_t Nn, int32_t n
     const int32_t m_pos = min(aN, cr.n1N) - P;           // min(n1a*n0b, n0a*n1b)
     const int32_t m_neg = P + min(0, cN - cr.n1N);       // min(n1a*n1b, n0a*n0b)
     const int32_t m = Dn > 0 ? m_pos : m_neg;
-    const float fD = __int2float_rn(abs(Dn));
+    const float fD = fabsf(__int2float_rn(Dn));          // |.| is an operand modifier: free
     const float fm = __int2float_rn(m);                  // exact
     const float den = __fmul_rn(fa, cr.prod);
     const float R1 = rcp_approx(fm), R2 = rcp_approx(den);     // inf when monomorphic: masked below
@@ -347,7 +348,9 @@ __device__ __forceinline__ uint32_t fast_pair(int32_t n11, int32_t Nn, int32_t n
     // !(<=) rather than (>): a NaN from an unforeseen input must fall to the exact path, never pass
     // (bitwise, not short-circuit: the sixteen pairs of a chunk must stay one straight-line block)
     slow = (bool)((uint32_t)!mono & ((uint32_t)!(fabsf(f_dp) <= l_dp) | (uint32_t)!(fabsf(f_r2) <= l_r2) | (uint32_t)(Dn == 0)));
-    uint32_t w = ((uint32_t)__float_as_int(t_r2) & LDX_R2_MASK) | (((uint32_t)__float_as_int(t_dp) << LDX_DP_SHIFT) & LDX_DP_MASK);
+    // t = MAGIC + n has the bit pattern 0x4B400000 + n (n < 2^14), and 0x4B400000 << 16 vanishes mod 2^32:
+    // one multiply-add packs both fields (a valid n leaves bits 14, 15, 30, 31 clear by itself)
+    uint32_t w = (uint32_t)__float_as_int(t_dp) * 65536u + ((uint32_t)__float_as_int(t_r2) - 0x4B400000u);
     w = mono ? (LDX_DP_INT0 | LDX_R2_INT0) : w;
     if (THRES) w |= (((w >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;   // no branch
     return w;
@@ -514,6 +517,7 @@ triangle_mma_kernel(const MmaArgs A) {
                 const uint32_t ta = tmem_base + Cfg::TMEM_A0 + s * Cfg::A_COLS;
                 if (elect_one()) {
                     if (TRACE && A.trace && blockIdx.x == 0 && g < 48) A.trace[64 + g] = gtime();
+                    if (!(TRACE && (A.dbg & 8)))
 #pragma unroll
                     for (int k = 0; k < Cfg::CH * KCHUNK / MMA_K; ++k)     // K = 32: 8 TMEM columns of A; B: atom k/4 (N*128 B apart), +32 B per step inside
                         umma_i8_ts(tmem_acc, ta + 8 * k, db + (uint64_t)((k >> 2) * (N * KCHUNK >> 4) + (k & 3) * 2), idesc, (uint32_t)((ks | k) != 0));
@@ -527,20 +531,23 @@ triangle_mma_kernel(const MmaArgs A) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // spare warps: hand their registers over and wait
     } else if (warp < FIRST_EPI_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        // ===== wideners: bit rows -> operand bytes.  Two teams of four warps take alternate stages, so
-        // that the fixed latencies of a stage (two mbarrier waits, the TMEM store, the proxy fence)
-        // of one team overlap the other team's.  Thread wt of a team widens row variant wt of the
+        // ===== wideners: bit rows -> operand bytes.  Four teams of four warps take pipeline stages in turn,
+        // so that the fixed latencies of a stage (two mbarrier waits, the TMEM store, the proxy fence)
+        // of one team overlap the work of the others.  Thread wt of a team widens row variant wt of the
         // stage into TENSOR MEMORY (lane = row; warp%4 is the TMEM quadrant the warp may write) and
         // column variant(s) wt (+128) into the 128B-swizzled shared-memory tile.
         const int team = (warp - FIRST_WIDEN_WARP) / TEAM_WARPS;
         const int wt = ((warp - FIRST_WIDEN_WARP) & 3) * 32 + lane;     // 0..127
         const uint32_t tmem_lane = (uint32_t)(((warp - FIRST_WIDEN_WARP) & 3) * 32) << 16;
-        uint32_t g = 0;
-        for (int t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
-            for (int ks = 0; ks < ks_count; ++ks, ++g) {
-                if ((int)(g % WIDEN_TEAMS) != team) continue;
+        // the wideners do not care which tile a stage belongs to: team k takes stages g = k, k + TEAMS, ...
+        // of this CTA's stream, bit stage g % BIT_STAGES -> operand stage g % OP_STAGES (= its own: k)
+        const uint32_t my_tiles = (uint32_t)(A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / gridDim.x;
+        const uint32_t g_end = my_tiles * (uint32_t)ks_count;
+        static_assert(Cfg::OP_STAGES == WIDEN_TEAMS, "one operand stage per team");
+        {
+            for (uint32_t g = (uint32_t)team; g < g_end; g += WIDEN_TEAMS) {
                 const uint32_t sb = g % Cfg::BIT_STAGES, itb = g / Cfg::BIT_STAGES;
-                const uint32_t so = g % Cfg::OP_STAGES, ito = g / Cfg::OP_STAGES;
+                const uint32_t so = (uint32_t)team, ito = g / Cfg::OP_STAGES;
                 if (!mbar_wait(bit_full + 8 * sb, itb & 1, abort_s, A.error_flag)) goto done;
                 if (TRACE && A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[192 + g] = gtime();
                 const uint4 *bsrc = reinterpret_cast<const uint4 *>(bit_s + sb * Cfg::BIT_BYTES);
@@ -550,6 +557,7 @@ triangle_mma_kernel(const MmaArgs A) {
                 if (!mbar_wait(op_empty + 8 * so, (ito & 1) ^ 1, abort_s, A.error_flag)) goto done;
                 tc_fence_after();
                 if (TRACE && A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[256 + g] = gtime();
+                if (!(TRACE && (A.dbg & 1)))
 #pragma unroll
                 for (int c = 0; c < Cfg::CH; ++c) {
                     const uint32_t w[4] = {ba[c].x, ba[c].y, ba[c].z, ba[c].w};
@@ -561,7 +569,7 @@ triangle_mma_kernel(const MmaArgs A) {
                     tmem_st32(tmem_base + Cfg::TMEM_A0 + so * Cfg::A_COLS + c * (KCHUNK / 4) + tmem_lane, v);
                 }
                 uint8_t *ops = op_s + so * Cfg::OP_BYTES;
-                if (wt < Cfg::B_ROWS) {
+                if (wt < Cfg::B_ROWS && !(TRACE && (A.dbg & 2))) {
 #pragma unroll
                     for (int c = 0; c < Cfg::CH; ++c)
 #pragma unroll
@@ -616,7 +624,7 @@ triangle_mma_kernel(const MmaArgs A) {
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 const int64_t rmin = r0 + quad * 32 + 16 * h;    // this pass: rows rmin .. rmin + 15
-                if (rmin >= A.v) break;                           // warp-uniform
+                if (rmin >= A.v || (TRACE && (A.dbg & 4))) break; // warp-uniform
                 // the lane's two row variants: n1a, n1a*N, N^2 - n1a*N, n1a*n0a
                 const int64_t ra = rmin + lq, rb = ra + 8;
                 const int32_t n1a = A.freq_rows[ra].n1, n1b = A.freq_rows[rb].n1;
@@ -635,7 +643,7 @@ triangle_mma_kernel(const MmaArgs A) {
                     uint32_t acc[16];
                     tmem_ld16x256(tmem_acc + (uint32_t)cb, acc);
                     uint32_t word[16];
-                    uint32_t slow = 0;
+                    uint32_t slow = 0;                            // bit i: pair i must be redone exactly
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int k = i >> 2, g = (i >> 1) & 1, e = i & 1;
@@ -659,13 +667,13 @@ triangle_mma_kernel(const MmaArgs A) {
                         for (int i = 0; i < 16; ++i) {
                             const int k = i >> 2, g = (i >> 1) & 1, e = i & 1;
                             const int64_t row = g ? rb : ra, col = cg0 + 8 * k + 2 * lr + e;
-                            if (row < A.v && col < row) {
+                            if (row < A.v && col < row) {         // only pairs of the triangle exist
                                 valid |= 1u << i;
                                 (g ? pb : pa)[cb + 8 * k + e] = word[i];
                                 if (WANT_N11) (g ? qb : qa)[cb + 8 * k + e] = (int32_t)(acc[i] >> ACC_SHIFT);
                             }
                         }
-                        slow &= valid;                            // only pairs of the triangle matter
+                        slow &= valid;
                     }
                     // Rare (about 1% of the pairs): a screened value sits next to a rounding boundary, or D
                     // is exactly 0 for two polymorphic variants.  Those pairs are not redone here -- one lane

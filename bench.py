@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- the hot path's headline metric on B200: variant pairs/sec (r2 + D', 5008 haplotypes).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ld_triangle|ld_area]
 
 Workload at N=1 is BASELINE.json configs[1]: ld_triangle, all-pairs r2/D' for 2,000 variants x
 5008 haplotypes (1,999,000 pairs).  One *step* = one all-pairs pass over one 2,000-variant set.
@@ -13,7 +13,11 @@ Printed JSON (one line, rank 0):
   value        pairs/s with the bit planes already resident in HBM and results left in HBM
   e2e          pairs/s through the public API with HOST buffers: planes H2D (pinned) + mask/count
                kernel + all-pairs kernel + packed results D2H, every step
-  roofline     dominant kernel (the all-pairs kernel) against the pipe that bounds it
+  roofline     dominant kernel (the all-pairs kernel) against the pipe that bounds it; its duration is
+               measured live with CUDA events recorded around that kernel's launches on the stream it
+               runs on (ldx_kernel_timing), over the timed region
+  steady_state the same kernel on a 32,768-variant set (221 tiles per SM instead of one): what the engine
+               sustains once tile quantisation and launch latency stop dominating (BASELINE configs[3] regime)
   cpu_baseline the reference algorithm (pure-Python port, oracle/calc_ld_port.py) on the host cores
 """
 import argparse
@@ -229,6 +233,7 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ctx.launch_count
+    ctx.kernel_timing(True)                 # CUDA events around every all-pairs kernel launch from here on
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     for s0, s1, s2 in ev:
@@ -240,8 +245,9 @@ def run_ours(args, rank, world, local_rank):
         s2.record(stream)                   # s0..s2 = the step
     barrier()
     launches = ctx.launch_count - launches0
+    dom_ms, dom_launches = ctx.kernel_timing(False)      # the dominant kernel alone, summed over the timed steps
     step_ms = float(sum(a.elapsed_time(c) for a, _, c in ev))
-    kern_ms = float(sum(a.elapsed_time(b) for a, b, _ in ev))
+    kern_ms = float(sum(a.elapsed_time(b) for a, b, _ in ev))   # gather + all-pairs + deferred-pairs kernels
 
     # ---- leg 2: end to end through the host API: pinned planes H2D + mask/count kernel +
     #      all-pairs kernel + packed results D2H
@@ -271,14 +277,14 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop()
 
     # ---- max over ranks
-    t = torch.tensor([step_ms, kern_ms, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([step_ms, kern_ms, e2e_ms, dom_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms, kern_ms, e2e_ms = t.tolist()
+    step_ms, kern_ms, e2e_ms, dom_ms = t.tolist()
     total_pairs = n_pairs * world
     value = total_pairs * args.steps / (step_ms * 1e-3)
     e2e_value = total_pairs * e_steps / (e2e_ms * 1e-3)
-    kern_s = kern_ms * 1e-3 / args.steps
+    kern_s = dom_ms * 1e-3 / max(dom_launches, 1)        # average duration of one all-pairs kernel launch
 
     # parity spot-check of what was just timed (device-resident result vs host-API result)
     same = bool((d_packed.cpu().numpy().view(np.uint32) == out_host).all())
@@ -295,17 +301,49 @@ def run_ours(args, rank, world, local_rank):
                 "unit": "TPOPC32/s", "peak_source": "148 SM x 16 POPC/clk x clocks.max.sm"}
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["traffic"] = None
+    roof["kernel"] = "triangle_mma_kernel" if used_mma else "triangle_popc_kernel"
     roof["kernel_ms"] = kern_s * 1e3
+    roof["kernel_launches_timed"] = int(dom_launches)
+    roof["all_kernels_ms_per_step"] = kern_ms / args.steps
+    roof["algorithmic_per_launch"] = (f"{n_pairs} pairs x {OPS_PER_PAIR_I8} int8 ops" if used_mma
+                                      else f"{n_pairs} pairs x {POPC_PER_PAIR} POPC32")
+
+    # ---- steady state: one large variant set, kernel-only (rank 0's GPU; every rank runs it so clocks stay loaded)
+    steady = None
+    if used_mma and not args.no_steady:
+        from ld_tools_b200.synth import random_planes
+        v_big = 32768
+        big = Store.from_planes(ctx, random_planes(v_big, N_HAP, seed=11 + rank), N_HAP)
+        big.set_mask(mask_np)
+        rows_big = np.arange(v_big, dtype=np.int64)
+        pairs_big = v_big * (v_big - 1) // 2
+        out_big = torch.empty(pairs_big, dtype=torch.int32, device=dev)
+        for _ in range(2):
+            big.triangle_dev(rows_big, out_big.data_ptr(), engine=engine)
+            ctx.resolve()
+        ctx.kernel_timing(True)
+        for _ in range(3):
+            big.triangle_dev(rows_big, out_big.data_ptr(), engine=engine)
+            ctx.resolve()
+        big_ms, big_n = ctx.kernel_timing(False)
+        pps = pairs_big / (big_ms * 1e-3 / big_n)
+        steady = {"workload": f"ld_triangle, {v_big} variants x {N_HAP} haplotypes ({pairs_big} pairs), kernel only",
+                  "value": pps, "unit": "pairs/s", "kernel_ms": big_ms / big_n,
+                  "roofline_frac": pps * OPS_PER_PAIR_I8 / 1e12 / (2.0 * peaks["bf16_tflops"])}
+        del out_big
+        big.close()
 
     line = {"metric": "variant pairs/sec (r2+D', 5008 haplotypes)", "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 popcount + f64",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8 tensor (exact) + f32 screen / f64 settle" if used_mma else "u64 popcount + f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": n_pairs, "engine": args.engine,
                        "l2": "flushed (256 MiB write) between timed iterations", "sharding": "one variant set per GPU"},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(planes_np.nbytes + mask_np.nbytes + rows.nbytes),
                     "d2h_bytes_per_step": int(out_host.nbytes), "steps": e_steps, "wall_s": e2e_wall},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "parity_selfcheck": same}
+    if steady:
+        line["steady_state"] = steady
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_pairs_per_core)
@@ -326,6 +364,7 @@ def main():
     ap.add_argument("--tile-n", type=int, default=0, help="tcgen05 tile width override (0 = heuristic)")
     ap.add_argument("--cpu-pairs-per-core", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-steady", action="store_true", help="skip the 32,768-variant steady-state leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

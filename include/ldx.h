@@ -105,6 +105,12 @@ int32_t ldx_set_tuning(ldx_ctx *ctx, int32_t key, int32_t value);
  * [192+g] bits landed / [256+g] operand stage free (widener) / [320+g] widening stores issued, for its
  * first 48 pipeline stages g.  stamps8 (may be NULL, else 512 entries) receives the last recording. */
 int32_t ldx_debug_trace(ldx_ctx *ctx, int32_t enable, uint64_t *stamps8);
+/* Dominant-kernel timing for roofline reports: while enabled, every all-pairs kernel
+ * (triangle_mma_kernel / triangle_popc_kernel) and window kernel launch is bracketed by CUDA events
+ * on the ctx stream.  Each call returns (and clears) the device time in ms and the number of launches
+ * accumulated since the previous call, then sets the new state.  Reading synchronises with the last
+ * recorded event. */
+int32_t ldx_kernel_timing(ldx_ctx *ctx, int32_t enable, double *ms_out, int64_t *launches_out);
 int32_t ldx_sm_count(ldx_ctx *ctx, int32_t *n_out);
 /* Kernels launched by this ctx since creation (bench.py's gpu_launches claim). */
 int32_t ldx_launch_count(ldx_ctx *ctx, int64_t *n_out);
@@ -191,6 +197,15 @@ int32_t ldx_triangle(ldx_store *store, const int64_t *rows, int64_t v, int32_t m
                      int32_t has_thres, int32_t thres_e4, int32_t engine, uint32_t *packed,
                      int32_t *n11);
 
+/* A slice of the same triangle: only matrix rows row_begin .. row_end-1 (row_begin a multiple of 128),
+ * i.e. the pairs (row, col) with row_begin <= row < row_end, col < row.  The output holds
+ * tri(row_end) - tri(row_begin) entries, tri(r) = r*(r-1)/2, and entry 0 is pair (row_begin, 0): it is
+ * the contiguous range [tri(row_begin), tri(row_end)) of the full packed triangle.  This is the unit the
+ * multi-GPU path shards by (ld_tools_b200/shard.py: row ranges balanced by tile count). */
+int32_t ldx_triangle_rows(ldx_store *store, const int64_t *rows, int64_t v, int64_t row_begin,
+                          int64_t row_end, int32_t measure, int32_t has_thres, int32_t thres_e4,
+                          int32_t engine, uint32_t *packed, int32_t *n11);
+
 /* ---------------------------------------------------------------- device-resident variants
  * Same kernels, but outputs stay in HBM (caller-allocated device memory) and the call only
  * enqueues work on the ctx stream.  ldx_resolve() then finishes the rounding of the (very rare)
@@ -205,6 +220,9 @@ int32_t ldx_triangle(ldx_store *store, const int64_t *rows, int64_t v, int32_t m
 int32_t ldx_triangle_dev(ldx_store *store, const int64_t *rows, int64_t v, int32_t measure,
                          int32_t has_thres, int32_t thres_e4, int32_t engine,
                          uint32_t *dev_packed, int32_t *dev_n11);
+int32_t ldx_triangle_rows_dev(ldx_store *store, const int64_t *rows, int64_t v, int64_t row_begin,
+                              int64_t row_end, int32_t measure, int32_t has_thres, int32_t thres_e4,
+                              int32_t engine, uint32_t *dev_packed, int32_t *dev_n11);
 int32_t ldx_window_dev(ldx_store *store, const int64_t *q_row, const int64_t *lo, const int64_t *hi,
                        const int32_t *win_start, const int32_t *win_end, int64_t nq,
                        int32_t measure, int32_t thres_e4, ldx_hit *dev_hits, int64_t cap,

@@ -44,6 +44,7 @@ SIGNATURES = {
     "ldx_synchronize": [_vp],
     "ldx_debug_trace": [_vp, _i32, _vp],
     "ldx_set_tuning": [_vp, _i32, _i32],
+    "ldx_kernel_timing": [_vp, _i32, _P(C.c_double), _P(_i64)],
     "ldx_sm_count": [_vp, _P(_i32)],
     "ldx_launch_count": [_vp, _P(_i64)],
     "ldx_calc_ld_lists": [_vp, _vp, _i64, _vp, _i64, _vp],
@@ -63,6 +64,8 @@ SIGNATURES = {
     "ldx_window": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _P(_i64), _P(_i64)],
     "ldx_triangle": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp],
     "ldx_triangle_dev": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp],
+    "ldx_triangle_rows": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp],
+    "ldx_triangle_rows_dev": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp],
     "ldx_window_dev": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp],
     "ldx_resolve": [_vp, _P(_i64)],
 }

@@ -107,6 +107,7 @@ extern "C" int32_t ldx_destroy(ldx_ctx *ctx) {
     if (ctx->h_mailbox) cudaFreeHost((void *)ctx->h_mailbox);
     if (ctx->d_mma_ops) cudaFree(ctx->d_mma_ops);
     if (ctx->d_trace) cudaFree(ctx->d_trace);
+    for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return LDX_OK;
@@ -152,6 +153,46 @@ extern "C" int32_t ldx_debug_trace(ldx_ctx *ctx, int32_t enable, uint64_t *stamp
         LDX_CUDA(cudaMemcpy(stamps8, ctx->d_trace, 512 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     }
     if (!enable && ctx->d_trace) { cudaFree(ctx->d_trace); ctx->d_trace = nullptr; }
+    return LDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ kernel timing
+namespace ldx {
+static void timing_drain(ldx_ctx *ctx) {
+    if (ctx->timing_used == 0) return;
+    cudaEventSynchronize(ctx->timing_events[ctx->timing_used - 1]);
+    for (size_t i = 0; i + 1 < ctx->timing_used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->timing_events[i], ctx->timing_events[i + 1]) == cudaSuccess) ctx->timing_ms += ms;
+        ctx->timing_launches++;
+    }
+    ctx->timing_used = 0;
+}
+void timing_begin(ldx_ctx *ctx) {
+    if (!ctx->timing) return;
+    if (ctx->timing_used + 2 > 8192) timing_drain(ctx);
+    while (ctx->timing_events.size() < ctx->timing_used + 2) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); ctx->timing = false; return; }
+        ctx->timing_events.push_back(e);
+    }
+    cudaEventRecord(ctx->timing_events[ctx->timing_used], ctx->stream);
+}
+void timing_end(ldx_ctx *ctx) {
+    if (!ctx->timing) return;
+    cudaEventRecord(ctx->timing_events[ctx->timing_used + 1], ctx->stream);
+    ctx->timing_used += 2;
+}
+}  // namespace ldx
+
+extern "C" int32_t ldx_kernel_timing(ldx_ctx *ctx, int32_t enable, double *ms_out, int64_t *launches_out) {
+    LDX_REQUIRE(ctx, "ctx is NULL");
+    LDX_CUDA(cudaSetDevice(ctx->device));
+    timing_drain(ctx);
+    if (ms_out) *ms_out = ctx->timing_ms;
+    if (launches_out) *launches_out = ctx->timing_launches;
+    ctx->timing_ms = 0.0; ctx->timing_launches = 0;
+    ctx->timing = enable != 0;
     return LDX_OK;
 }
 
@@ -722,24 +763,25 @@ static int stage_rows(ldx_store *s, const int64_t *rows, int64_t v, int64_t **d_
     return LDX_OK;
 }
 
-extern "C" int32_t ldx_triangle_dev(ldx_store *s, const int64_t *rows, int64_t v, int32_t measure,
-                                    int32_t has_thres, int32_t thres_e4, int32_t engine,
-                                    uint32_t *dev_packed, int32_t *dev_n11) {
+extern "C" int32_t ldx_triangle_rows_dev(ldx_store *s, const int64_t *rows, int64_t v, int64_t row_begin, int64_t row_end,
+                                         int32_t measure, int32_t has_thres, int32_t thres_e4, int32_t engine,
+                                         uint32_t *dev_packed, int32_t *dev_n11) {
     LDX_REQUIRE(measure == LDX_MEASURE_R2 || measure == LDX_MEASURE_DPRIME, "bad measure");
     LDX_REQUIRE(engine >= LDX_ENGINE_AUTO && engine <= LDX_ENGINE_MMA, "bad engine");
+    LDX_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= v, "bad row range");
+    LDX_REQUIRE(row_begin % 128 == 0, "row_begin must be a multiple of 128");
     int64_t *d_rows;
     LDX_TRY(stage_rows(s, rows, v, &d_rows));
-    if (v < 2) return LDX_OK;
+    if (row_end < 2 || row_begin == row_end) return LDX_OK;
     ldx_ctx *ctx = s->ctx;
     if (engine == LDX_ENGINE_MMA && !triangle_mma_available())
         return set_error(LDX_ERR_ARG, "the tcgen05 engine is not available in this build");
-    const bool use_mma = engine == LDX_ENGINE_MMA || (engine == LDX_ENGINE_AUTO && triangle_mma_available() && v >= ctx->mma_min_v &&
+    const bool use_mma = engine == LDX_ENGINE_MMA || (engine == LDX_ENGINE_AUTO && triangle_mma_available() && row_end >= ctx->mma_min_v &&
                                                       s->n_sel <= triangle_mma_max_haplotypes());
-    // rows[] staging is consumed by the kernel on the same stream; the caller's array may be
-    // freed after return, so wait for the H2D copy (tiny) before returning.
+    // rows[] staging is consumed by the kernel on the same stream (stage_rows keeps a host copy alive)
     const uint32_t seq = ctx->seq + 1 ? ctx->seq + 1 : 1;     // 0 means "nothing published"
-    int rc = use_mma ? launch_triangle_mma(s, d_rows, v, measure, has_thres, thres_e4, dev_packed, dev_n11, seq)
-                     : launch_triangle_popc(s, d_rows, v, measure, has_thres, thres_e4, dev_packed, dev_n11);
+    int rc = use_mma ? launch_triangle_mma(s, d_rows, row_end, row_begin, measure, has_thres, thres_e4, dev_packed, dev_n11, seq)
+                     : launch_triangle_popc(s, d_rows, row_end, row_begin, measure, has_thres, thres_e4, dev_packed, dev_n11);
     LDX_TRY(rc);
     ctx->seq = seq;
     if (!use_mma) LDX_TRY(launch_publish(ctx));
@@ -748,18 +790,25 @@ extern "C" int32_t ldx_triangle_dev(ldx_store *s, const int64_t *rows, int64_t v
     return LDX_OK;
 }
 
-extern "C" int32_t ldx_triangle(ldx_store *s, const int64_t *rows, int64_t v, int32_t measure,
-                                int32_t has_thres, int32_t thres_e4, int32_t engine, uint32_t *packed,
-                                int32_t *n11) {
+extern "C" int32_t ldx_triangle_dev(ldx_store *s, const int64_t *rows, int64_t v, int32_t measure,
+                                    int32_t has_thres, int32_t thres_e4, int32_t engine,
+                                    uint32_t *dev_packed, int32_t *dev_n11) {
+    return ldx_triangle_rows_dev(s, rows, v, 0, v, measure, has_thres, thres_e4, engine, dev_packed, dev_n11);
+}
+
+extern "C" int32_t ldx_triangle_rows(ldx_store *s, const int64_t *rows, int64_t v, int64_t row_begin, int64_t row_end,
+                                     int32_t measure, int32_t has_thres, int32_t thres_e4, int32_t engine,
+                                     uint32_t *packed, int32_t *n11) {
     LDX_REQUIRE(s, "store is NULL");
+    LDX_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= v, "bad row range");
     ldx_ctx *ctx = s->ctx;
-    const int64_t n_pairs = v > 1 ? v * (v - 1) / 2 : 0;
+    const int64_t n_pairs = (row_end > 1 ? row_end * (row_end - 1) / 2 : 0) - (row_begin > 1 ? row_begin * (row_begin - 1) / 2 : 0);
     uint32_t *d_pk = nullptr; int32_t *d_n11 = nullptr;
     if (n_pairs) {
         LDX_TRY(arena_get(ctx, S_PACKED, sizeof(uint32_t) * (size_t)n_pairs, (void **)&d_pk));   // always: fix-ups index it
         if (n11) LDX_TRY(arena_get(ctx, S_N11, sizeof(int32_t) * (size_t)n_pairs, (void **)&d_n11));
     }
-    LDX_TRY(ldx_triangle_dev(s, rows, v, measure, has_thres, thres_e4, engine, d_pk, d_n11));
+    LDX_TRY(ldx_triangle_rows_dev(s, rows, v, row_begin, row_end, measure, has_thres, thres_e4, engine, d_pk, d_n11));
     ctx->pending.kind = 0;
     if (!n_pairs) return LDX_OK;
     if (packed) LDX_CUDA(cudaMemcpyAsync(packed, d_pk, sizeof(uint32_t) * (size_t)n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
@@ -769,6 +818,12 @@ extern "C" int32_t ldx_triangle(ldx_store *s, const int64_t *rows, int64_t v, in
     if (packed)
         for (const FixupRec &r : recs) packed[r.out_index] = settle_word(r, s->fc.n_hap, measure, has_thres, thres_e4);
     return LDX_OK;
+}
+
+extern "C" int32_t ldx_triangle(ldx_store *s, const int64_t *rows, int64_t v, int32_t measure,
+                                int32_t has_thres, int32_t thres_e4, int32_t engine, uint32_t *packed,
+                                int32_t *n11) {
+    return ldx_triangle_rows(s, rows, v, 0, v, measure, has_thres, thres_e4, engine, packed, n11);
 }
 
 // ------------------------------------------------------------------------------------------ resolve

@@ -36,6 +36,7 @@ struct ldx_ctx {
     int mma_tile_n = 0;                   // tcgen05 tile width override (0 = heuristic)
     int64_t mma_tiles_v = -1;             // tile list cached in d_mma_ops: built for this (v, N)
     int mma_tiles_n = 0;
+    int64_t mma_tiles_begin = 0;
     // completion mailbox: pinned, device-mapped {seq, near-tie count, error flag}; a 1-thread kernel
     // publishes it after each *_dev call so that ldx_resolve() can poll host memory instead of
     // paying a stream synchronisation (tens of microseconds) per call
@@ -45,6 +46,12 @@ struct ldx_ctx {
     std::vector<int64_t> rows_cache;      // host copy of the variant list last staged on the device
     unsigned long long *d_trace = nullptr;   // diagnostics: globaltimer stamps written by the tcgen05 kernel
     int mma_min_v = 256;                  // ENGINE_AUTO uses the tcgen05 engine from this many variants
+    // dominant-kernel timing (ldx_kernel_timing): CUDA event pairs around the all-pairs / window kernel
+    bool timing = false;
+    std::vector<cudaEvent_t> timing_events;   // pool, used pairwise
+    size_t timing_used = 0;               // events recorded since the last read
+    double timing_ms = 0.0;               // accumulated by drains
+    int64_t timing_launches = 0;
 };
 
 struct ldx_store {
@@ -93,14 +100,19 @@ int launch_window(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, cons
                   const int32_t *d_ws, const int32_t *d_we, const int64_t *d_chunk_prefix, int64_t nq,
                   int64_t n_chunks, int measure, int thres_e4, ldx_hit *d_hits, int64_t cap,
                   unsigned long long *d_n_hits);
-int launch_triangle_popc(ldx_store *s, const int64_t *d_rows, int64_t v, int measure, int has_thres,
+// Both all-pairs launchers work on the first v entries of d_rows and emit the pairs (row, col < row) of rows
+// row_begin .. v-1 (row_begin a multiple of 128); output index 0 is pair (row_begin, 0).
+int launch_triangle_popc(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t row_begin, int measure, int has_thres,
                          int thres_e4, uint32_t *d_packed, int32_t *d_n11);
 // publish_seq != 0: the engine's last kernel also publishes the completion record for that sequence number
-int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int measure, int has_thres,
+int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t row_begin, int measure, int has_thres,
                         int thres_e4, uint32_t *d_packed, int32_t *d_n11, uint32_t publish_seq);
 bool triangle_mma_available();
 int triangle_mma_max_haplotypes();
 int launch_publish(ldx_ctx *ctx);   // enqueue the mailbox update for ctx->seq
+// Dominant-kernel timing: bracket a launch with events on ctx->stream when ctx->timing is on.
+void timing_begin(ldx_ctx *ctx);
+void timing_end(ldx_ctx *ctx);
 
 constexpr int WINDOW_CHUNK = 256;   // rows per work item of the window kernel
 

@@ -265,6 +265,7 @@ struct MmaArgs {
     const VarFreq *freq_rows; FinalCtx fc;
     const int2 *tiles; int32_t n_tiles;
     int64_t v; int measure, has_thres, thres_e4;
+    int64_t out_off;             // packed index of the first pair of the call's row range: outputs are relative to it
     int32_t n_sel;               // N = selected haplotypes
     float lim_dp, lim_r2;        // 0.5 - guard band of the screening arithmetic at x = 0 (see fast_pair)
     uint4 *slow; uint32_t *slow_count; uint32_t slow_cap;   // deferred pairs {row, col, n11, -} for slow_pairs_kernel
@@ -362,13 +363,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 // One deferred pair {row, col, n11, -} redone with the reference's own operation sequence (finalise_pair).
 __device__ __forceinline__ void settle_slow_pair(const uint4 e, const VarFreq *__restrict__ freq_rows, const FinalCtx &fc,
-                                                 uint32_t m_shift, uint32_t thres, uint32_t *__restrict__ packed, const FixupSink &fix) {
+                                                 uint32_t m_shift, uint32_t thres, uint32_t *__restrict__ packed, int64_t out_off,
+                                                 const FixupSink &fix) {
     const int64_t r = e.x, col = e.y;
     const VarFreq fa = freq_rows[r], fb = freq_rows[col];
     const PairFinal f = finalise_pair((int32_t)e.z, fa, fb, fc);       // var_1 = row, var_2 = column
     uint32_t w = f.packed;
     w |= (((w >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;
-    const uint64_t idx = (uint64_t)(r * (r - 1) / 2 + col);
+    const uint64_t idx = (uint64_t)(r * (r - 1) / 2 + col - out_off);
     if (w & LDX_R2_NEARTIE) fixup_append(fix, idx, (int32_t)e.z, fa.n1, fb.n1, w);
     packed[idx] = w;
 }
@@ -386,7 +388,7 @@ __device__ __forceinline__ uint32_t flush_slow(const MmaArgs &A, const uint4 *sb
     base = __shfl_sync(0xffffffffu, base, 0);
     for (uint32_t i = lane; i < cnt; i += 32) {
         if (base + i < A.slow_cap) A.slow[base + i] = sbuf[i];
-        else settle_slow_pair(sbuf[i], A.freq_rows, A.fc, m_shift, thres, A.packed, A.fix);
+        else settle_slow_pair(sbuf[i], A.freq_rows, A.fc, m_shift, thres, A.packed, A.out_off, A.fix);
     }
     __syncwarp();
     return 0;
@@ -398,13 +400,13 @@ __device__ __forceinline__ uint32_t flush_slow(const MmaArgs &A, const uint4 *sb
 __global__ void __launch_bounds__(256)
 slow_pairs_kernel(const uint4 *__restrict__ list, uint32_t *__restrict__ counters /* d_fix_count */, uint32_t cap,
                   const VarFreq *__restrict__ freq_rows, FinalCtx fc, int measure, int has_thres, int thres_e4,
-                  uint32_t *__restrict__ packed, FixupSink fix, volatile uint32_t *mailbox, uint32_t seq) {
+                  uint32_t *__restrict__ packed, int64_t out_off, FixupSink fix, volatile uint32_t *mailbox, uint32_t seq) {
     const uint32_t total = counters[2];
     const uint32_t n = total < cap ? total : cap;              // the rest was settled in the epilogue (flush_slow)
     const uint32_t m_shift = measure == LDX_MEASURE_R2 ? 0u : (uint32_t)LDX_DP_SHIFT;
     const uint32_t thres = has_thres ? (uint32_t)thres_e4 : 0u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        settle_slow_pair(list[i], freq_rows, fc, m_shift, thres, packed, fix);
+        settle_slow_pair(list[i], freq_rows, fc, m_shift, thres, packed, out_off, fix);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -631,10 +633,10 @@ triangle_mma_kernel(const MmaArgs A) {
                 const int32_t aNa = n1a * Nn, cNa = Nn * Nn - aNa, aNb = n1b * Nn, cNb = Nn * Nn - aNb;
                 const float faa = __int2float_rn(n1a * (Nn - n1a)), fab = __int2float_rn(n1b * (Nn - n1b));
                 // result words of (row, column c0 + 2 lr + j) live at p?[j]
-                uint32_t *pa = A.packed + (ra * (ra - 1) / 2 + c0 + 2 * lr);
-                uint32_t *pb = A.packed + (rb * (rb - 1) / 2 + c0 + 2 * lr);
-                int32_t *qa = WANT_N11 ? A.n11 + (ra * (ra - 1) / 2 + c0 + 2 * lr) : nullptr;
-                int32_t *qb = WANT_N11 ? A.n11 + (rb * (rb - 1) / 2 + c0 + 2 * lr) : nullptr;
+                uint32_t *pa = A.packed + (ra * (ra - 1) / 2 - A.out_off + c0 + 2 * lr);
+                uint32_t *pb = A.packed + (rb * (rb - 1) / 2 - A.out_off + c0 + 2 * lr);
+                int32_t *qa = WANT_N11 ? A.n11 + (ra * (ra - 1) / 2 - A.out_off + c0 + 2 * lr) : nullptr;
+                int32_t *qb = WANT_N11 ? A.n11 + (rb * (rb - 1) / 2 - A.out_off + c0 + 2 * lr) : nullptr;
                 const uint32_t tmem_acc = tmem_base + buf * N + ((uint32_t)(quad * 32 + 16 * h) << 16);
 #pragma unroll 1
                 for (int cb = half * (N / 2); cb < (half + 1) * (N / 2); cb += 32) {
@@ -734,7 +736,9 @@ static int launch_tiles_t(ldx_ctx *ctx, const MmaArgs &A) {
         attr_set = true;
     }
     const int grid = A.n_tiles < ctx->sm_count ? A.n_tiles : ctx->sm_count;     // persistent: one CTA per SM
+    timing_begin(ctx);
     triangle_mma_kernel<N, WANT_N11, THRES, TRACE><<<grid, MMA_THREADS, MmaCfg<N>::SMEM, ctx->stream>>>(A);
+    timing_end(ctx);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
     return LDX_OK;
@@ -746,9 +750,11 @@ static int launch_tiles(ldx_ctx *ctx, const MmaArgs &A) {
     return A.n11 ? launch_tiles_t<N, true, false>(ctx, A) : launch_tiles_t<N, false, false>(ctx, A);
 }
 
-int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int measure, int has_thres,
+int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t row_begin, int measure, int has_thres,
                         int thres_e4, uint32_t *d_packed, int32_t *d_n11, uint32_t publish_seq) {
     if (v < 2) return LDX_OK;
+    if (row_begin % MMA_M) return set_error(LDX_ERR_ARG, "tcgen05 engine: row_begin must be a multiple of 128");
+    const int64_t panel_begin = row_begin / MMA_M;
     ldx_ctx *ctx = s->ctx;
     if (s->n_sel > triangle_mma_max_haplotypes())
         return set_error(LDX_ERR_ARG, "tcgen05 engine: more than 8192 selected haplotypes (use LDX_ENGINE_POPC or LDX_ENGINE_AUTO)");
@@ -762,12 +768,12 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
     // tile width: narrow tiles give every SM several tiles to overlap for small matrices, wide
     // tiles amortise the widening work for large ones
     int n_tile = ctx->mma_tile_n;
-    if (n_tile == 0) n_tile = v <= 4096 ? 64 : 128;
+    if (n_tile == 0) n_tile = v <= 1024 ? 64 : 128;
     // ---- tile list (cached): every 128 x N tile holding at least one pair with row > col, row-panel major
     const size_t bits_bytes = (size_t)panels * kc_count * 128 * sizeof(uint4);
     const size_t freq_bytes = (size_t)v_pad * sizeof(VarFreq);
     size_t n_tiles = 0;
-    for (int64_t bi = 0; bi < (v + MMA_M - 1) / MMA_M; ++bi) {
+    for (int64_t bi = panel_begin; bi < (v + MMA_M - 1) / MMA_M; ++bi) {
         const int64_t rmax = std::min<int64_t>(bi * MMA_M + MMA_M - 1, v - 1);
         n_tiles += (size_t)((rmax + n_tile - 1) / n_tile);
     }
@@ -775,7 +781,7 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
     if (n_tiles > 0x7fffffffull) return set_error(LDX_ERR_ARG, "tcgen05 engine: too many tiles");
     const size_t tile_bytes = (n_tiles * sizeof(int2) + 15) / 16 * 16;
     // deferred-pair list: the guard band defers < 1% of the pairs (triangle_mma_max_haplotypes)
-    const uint64_t n_pairs = (uint64_t)v * (uint64_t)(v - 1) / 2;
+    const uint64_t n_pairs = (uint64_t)v * (uint64_t)(v - 1) / 2 - (uint64_t)row_begin * (uint64_t)(row_begin > 0 ? row_begin - 1 : 0) / 2;
     const uint64_t slow_cap64 = n_pairs / 64 + 65536;
     if (slow_cap64 > 0xffffffffull) return set_error(LDX_ERR_ARG, "tcgen05 engine: too many pairs for one call");
     const size_t slow_bytes = (size_t)slow_cap64 * sizeof(uint4);
@@ -791,18 +797,18 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
     VarFreq *d_freq_rows = reinterpret_cast<VarFreq *>(base + 2 * bits_bytes);
     int2 *d_tiles = reinterpret_cast<int2 *>(base + 2 * bits_bytes + freq_bytes);
     uint4 *d_slow = reinterpret_cast<uint4 *>(base + 2 * bits_bytes + freq_bytes + tile_bytes);
-    if (ctx->mma_tiles_v != v || ctx->mma_tiles_n != n_tile) {          // the list depends on (v, N) only
+    if (ctx->mma_tiles_v != v || ctx->mma_tiles_n != n_tile || ctx->mma_tiles_begin != row_begin) {   // the list depends on (v, row_begin, N) only
         // Longest tiles first is not needed (all tiles cost the same K loop); the list is ordered so
         // that the tiles a wave of CTAs works on share row panels and neighbouring column blocks in L2.
         std::vector<int2> tiles;
         tiles.reserve(n_tiles);
-        for (int64_t bi = 0; bi < (v + MMA_M - 1) / MMA_M; ++bi) {
+        for (int64_t bi = panel_begin; bi < (v + MMA_M - 1) / MMA_M; ++bi) {
             const int64_t rmax = std::min<int64_t>(bi * MMA_M + MMA_M - 1, v - 1);
             for (int64_t bj = 0; bj * n_tile < rmax; ++bj) tiles.push_back(make_int2((int)bi, (int)bj));
         }
         LDX_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), n_tiles * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
         LDX_CUDA(cudaStreamSynchronize(ctx->stream));   // `tiles` is a local
-        ctx->mma_tiles_v = v; ctx->mma_tiles_n = n_tile;
+        ctx->mma_tiles_v = v; ctx->mma_tiles_n = n_tile; ctx->mma_tiles_begin = row_begin;
     }
 
     dim3 ggrid((unsigned)((v_pad + 255) / 256), (unsigned)kc_count);
@@ -815,6 +821,7 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
     A.bits = d_bits; A.bits_rev = d_bits_rev; A.kc_count = kc_count; A.freq_rows = d_freq_rows; A.fc = s->fc; A.tiles = d_tiles;
     A.n_tiles = (int32_t)n_tiles;
     A.v = v; A.measure = measure; A.has_thres = has_thres; A.thres_e4 = thres_e4;
+    A.out_off = row_begin * (row_begin - 1) / 2;
     A.packed = d_packed; A.n11 = d_n11;
     A.n_sel = s->n_sel;
     {   // guard band of the screening arithmetic (see fast_pair).  Its fp32 half needs m and n1*n0 exact
@@ -841,7 +848,7 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int meas
     // ~1% of the pairs are deferred: size the grid for two pairs per thread at that rate
     const int sgrid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 4, std::max<uint64_t>(1, n_pairs / (1u << 16)));
     slow_pairs_kernel<<<sgrid, 256, 0, ctx->stream>>>(d_slow, ctx->d_fix_count, A.slow_cap, d_freq_rows, s->fc, measure, has_thres,
-                                                      thres_e4, d_packed, A.fix, publish_seq ? ctx->d_mailbox : nullptr, publish_seq);
+                                                      thres_e4, d_packed, A.out_off, A.fix, publish_seq ? ctx->d_mailbox : nullptr, publish_seq);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
     return LDX_OK;

@@ -28,6 +28,7 @@ struct TriArgs {
     const uint64_t *planes; const uint64_t *mask; int32_t stride_words;
     const VarFreq *freq; FinalCtx fc;
     const int64_t *rows; int64_t v; int64_t n_tiles_side;
+    int64_t tile_begin, out_off;   // first tile (triangular order) and first packed index of the call's row range
     int measure, has_thres, thres_e4;
     uint32_t *packed; int32_t *n11;
     FixupSink fix;
@@ -50,7 +51,7 @@ triangle_popc_kernel(const TriArgs A) {
     __shared__ int64_t ra_s[TRI_TILE], rb_s[TRI_TILE];
 
     int64_t bi, bj;
-    tile_coords(blockIdx.x, bi, bj);
+    tile_coords(A.tile_begin + blockIdx.x, bi, bj);
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int64_t r0 = bi * TRI_TILE, c0 = bj * TRI_TILE;
 
@@ -105,7 +106,7 @@ triangle_popc_kernel(const TriArgs A) {
         const int64_t r = r0 + ty * 4 + i;
         if (r >= A.v) continue;
         const VarFreq fa = fa_s[ty * 4 + i];
-        const int64_t rbase = r * (r - 1) / 2;
+        const int64_t rbase = r * (r - 1) / 2 - A.out_off;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int64_t c = c0 + tx * 4 + j;
@@ -124,9 +125,10 @@ triangle_popc_kernel(const TriArgs A) {
     }
 }
 
-int launch_triangle_popc(ldx_store *s, const int64_t *d_rows, int64_t v, int measure, int has_thres,
+int launch_triangle_popc(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t row_begin, int measure, int has_thres,
                          int thres_e4, uint32_t *d_packed, int32_t *d_n11) {
     if (v < 2) return LDX_OK;
+    if (row_begin % TRI_TILE) return set_error(LDX_ERR_ARG, "popcount engine: row_begin must be a multiple of 64");
     ldx_ctx *ctx = s->ctx;
     TriArgs A;
     A.planes = s->d_planes; A.mask = s->d_mask; A.stride_words = s->stride_words;
@@ -135,7 +137,10 @@ int launch_triangle_popc(ldx_store *s, const int64_t *d_rows, int64_t v, int mea
     A.measure = measure; A.has_thres = has_thres; A.thres_e4 = thres_e4;
     A.packed = d_packed; A.n11 = d_n11;
     A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity};
-    const int64_t n_tiles = A.n_tiles_side * (A.n_tiles_side + 1) / 2;
+    const int64_t bi_begin = row_begin / TRI_TILE;
+    A.tile_begin = bi_begin * (bi_begin + 1) / 2;
+    A.out_off = row_begin * (row_begin - 1) / 2;
+    const int64_t n_tiles = A.n_tiles_side * (A.n_tiles_side + 1) / 2 - A.tile_begin;
     if (n_tiles > 0x7fffffffll) return set_error(LDX_ERR_ARG, "triangle: too many tiles for one launch");
     const size_t smem = (size_t)2 * TRI_TILE * TRI_PITCH * sizeof(uint64_t);
     static bool attr_set = false;
@@ -143,7 +148,9 @@ int launch_triangle_popc(ldx_store *s, const int64_t *d_rows, int64_t v, int mea
         LDX_CUDA(cudaFuncSetAttribute(triangle_popc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
+    timing_begin(ctx);
     triangle_popc_kernel<<<(int)n_tiles, TRI_THREADS, smem, ctx->stream>>>(A);
+    timing_end(ctx);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
     return LDX_OK;

@@ -173,7 +173,9 @@ static int launch_window_ng(ldx_ctx *ctx, const WindowArgs &A) {
     }
     int64_t grid = (int64_t)ctx->sm_count * per_sm;
     if (grid > A.n_chunks) grid = A.n_chunks;
+    timing_begin(ctx);
     window_kernel<NG><<<(int)grid, WIN_THREADS, 0, ctx->stream>>>(A);
+    timing_end(ctx);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
     return LDX_OK;

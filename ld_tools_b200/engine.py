@@ -92,6 +92,12 @@ class Context:
     def set_tuning(self, key, value):
         check(self._lib.ldx_set_tuning(self._h, int(key), int(value)))
 
+    def kernel_timing(self, enable):
+        """Read-and-clear the dominant-kernel timer (ms, launches), then switch it on/off."""
+        ms, n = C.c_double(), C.c_int64()
+        check(self._lib.ldx_kernel_timing(self._h, int(bool(enable)), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     @property
     def sm_count(self):
         n = C.c_int32()
@@ -277,6 +283,27 @@ class Store:
                                      int(thres_e4_ or 0), int(engine), ptr(packed), ptr(n11)))
         return packed, n11
 
+    def triangle_rows(self, rows, row_begin, row_end, measure="r_square", thres_e4_=None, engine=ENGINE_AUTO,
+                      want_n11=False, out=None):
+        """Matrix rows row_begin..row_end-1 of the triangle (row_begin % 128 == 0): the contiguous slice
+        [tri(row_begin), tri(row_end)) of the packed lower triangle.  The shard unit of the multi-GPU path."""
+        rows = _i64(rows)
+        n_pairs = tri_index(row_end, 0) - tri_index(row_begin, 0)
+        packed = np.zeros(n_pairs, dtype=np.uint32) if out is None else out
+        assert packed.dtype == np.uint32 and packed.shape[0] == n_pairs and packed.flags.c_contiguous
+        n11 = np.zeros(n_pairs, dtype=np.int32) if want_n11 else None
+        check(self._lib.ldx_triangle_rows(self._h, ptr(rows), rows.shape[0], int(row_begin), int(row_end),
+                                          _measure_code(measure), int(thres_e4_ is not None), int(thres_e4_ or 0),
+                                          int(engine), ptr(packed), ptr(n11)))
+        return packed, n11
+
+    def triangle_rows_dev(self, rows, row_begin, row_end, dev_packed, dev_n11=0, measure="r_square", thres_e4_=None,
+                          engine=ENGINE_AUTO):
+        rows = _i64(rows)
+        check(self._lib.ldx_triangle_rows_dev(self._h, ptr(rows), rows.shape[0], int(row_begin), int(row_end),
+                                              _measure_code(measure), int(thres_e4_ is not None), int(thres_e4_ or 0),
+                                              int(engine), C.c_void_p(dev_packed), C.c_void_p(dev_n11 or 0)))
+
     def triangle_dev(self, rows, dev_packed, dev_n11=0, measure="r_square", thres_e4_=None, engine=ENGINE_AUTO):
         """Device-resident output (raw device addresses); enqueue only.  Call ctx.resolve() after."""
         rows = _i64(rows)
@@ -295,4 +322,4 @@ class Store:
 
 def tri_index(row, col):
     """Position of pair (row > col) in the packed lower triangle."""
-    return row * (row - 1) // 2 + col
+    return row * (row - 1) // 2 + col if row > 0 else col

@@ -414,3 +414,53 @@ def test_finalise_counts_random_vs_oracle(ctx, n_hap):
     assert (res["d"][sub] == exact["d"]).all()
     assert (res["dprime"][sub] == exact["dprime"]).all()
     assert np.abs(res["r2"][sub] - exact["r2"]).max() <= TOL
+
+
+# ------------------------------------------------------------------ multi-GPU shard unit: row ranges of the triangle
+
+@pytest.mark.parametrize("engine_name", ["popc", "mma"])
+def test_triangle_rows_are_slices_of_the_full_triangle(ctx, engine_name):
+    """ldx_triangle_rows (the unit ld_tools_b200/shard.py hands to each GPU) against the oracle and
+    against the unsharded call: every range is the contiguous slice [tri(begin), tri(end))."""
+    from ld_tools_b200 import shard
+    from ld_tools_b200.engine import ENGINE_MMA, ENGINE_POPC, threshold_e4
+    engine = ENGINE_MMA if engine_name == "mma" else ENGINE_POPC
+    n_var, n_hap = 700, 5008
+    st, planes, mask = make_store(ctx, n_var, n_hap, seed=77, sel_frac=0.6)
+    rows = np.random.default_rng(3).permutation(n_var)
+    want = ld_oracle.triangle(planes, mask, n_hap, rows)
+    want_packed = ld_oracle.packed_of(want)
+    full, full_n11 = st.triangle(rows, engine=engine, want_n11=True)
+    assert (full == want_packed).all() and (full_n11 == want["n_11"]).all()
+    ranges = [(0, 128), (128, 384), (384, 700), (256, 256), (0, 700), (640, 700), (0, 1)]
+    for world in (2, 3, 8):
+        ranges += shard.triangle_row_ranges(n_var, world)
+    for a, b in ranges:
+        part, part_n11 = st.triangle_rows(rows, a, b, engine=engine, want_n11=True)
+        sl = shard.triangle_slice(a, b)
+        assert part.shape[0] == sl.stop - sl.start
+        assert (part == want_packed[sl]).all(), (a, b)
+        assert (part_n11 == want["n_11"][sl]).all(), (a, b)
+    # the threshold flag travels with the slice
+    t = threshold_e4(0.3)
+    part, _ = st.triangle_rows(rows, 128, 512, thres_e4_=t, engine=engine)
+    sl = shard.triangle_slice(128, 512)
+    below = (want_packed[sl] & 0x3FFF) < t
+    assert (((part & 0x40000000) != 0) == below).all()
+    with pytest.raises(Exception):
+        st.triangle_rows(rows, 64, 700, engine=engine)          # begin must sit on a 128-row panel
+    st.close()
+
+
+def test_kernel_timing_counts_the_all_pairs_launches(ctx):
+    st, planes, mask = make_store(ctx, 300, 5008, seed=5)
+    rows = np.arange(300)
+    ctx.kernel_timing(True)
+    for _ in range(3):
+        st.triangle(rows)
+    ms, n = ctx.kernel_timing(False)
+    assert n == 3 and 0.0 < ms < 50.0
+    st.triangle(rows)
+    ms, n = ctx.kernel_timing(False)
+    assert n == 0 and ms == 0.0
+    st.close()

@@ -827,6 +827,11 @@ extern "C" int32_t ldx_triangle(ldx_store *s, const int64_t *rows, int64_t v, in
 }
 
 // ------------------------------------------------------------------------------------------ resolve
+__global__ void scatter_words_kernel(uint8_t *base, const uint64_t *__restrict__ byte_off, const uint32_t *__restrict__ words, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) *reinterpret_cast<uint32_t *>(base + byte_off[i]) = words[i];
+}
+
 extern "C" int32_t ldx_resolve(ldx_ctx *ctx, int64_t *n_fixed_out) {
     LDX_REQUIRE(ctx, "ctx is NULL");
     if (n_fixed_out) *n_fixed_out = 0;
@@ -836,13 +841,24 @@ extern "C" int32_t ldx_resolve(ldx_ctx *ctx, int64_t *n_fixed_out) {
     const ldx_ctx::Pending p = ctx->pending;
     ctx->pending.kind = 0;
     if (recs.empty() || p.kind == 0) return LDX_OK;
-    for (const FixupRec &r : recs) {
-        const uint32_t w = settle_word(r, p.n_hap, p.measure, p.has_thres, p.thres_e4);
-        uint8_t *dst = p.kind == 1 ? reinterpret_cast<uint8_t *>(p.dev_out) + r.out_index * sizeof(uint32_t)
-                                   : reinterpret_cast<uint8_t *>(p.dev_out) + r.out_index * sizeof(ldx_hit) + offsetof(ldx_hit, packed);
-        LDX_CUDA(cudaMemcpyAsync(dst, &w, sizeof w, cudaMemcpyHostToDevice, ctx->stream));
-        LDX_CUDA(cudaStreamSynchronize(ctx->stream));   // w is a local; fix-ups are rare
+    // settle on the host (libm pow), then ONE upload and one scatter kernel: a 100,000-variant triangle
+    // has ~10^4 near-ties, far too many for a copy + synchronise each
+    const size_t n = recs.size();
+    std::vector<uint64_t> stage(n + (n + 1) / 2);                 // [n] byte offsets | [n] words
+    uint32_t *words = reinterpret_cast<uint32_t *>(stage.data() + n);
+    for (size_t i = 0; i < n; ++i) {
+        const FixupRec &r = recs[i];
+        words[i] = settle_word(r, p.n_hap, p.measure, p.has_thres, p.thres_e4);
+        stage[i] = p.kind == 1 ? r.out_index * sizeof(uint32_t) : r.out_index * sizeof(ldx_hit) + offsetof(ldx_hit, packed);
     }
+    uint64_t *d_stage;
+    LDX_TRY(arena_get(ctx, S_MISC, stage.size() * sizeof(uint64_t), (void **)&d_stage));
+    LDX_CUDA(cudaMemcpyAsync(d_stage, stage.data(), stage.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    scatter_words_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint8_t *>(p.dev_out), d_stage,
+                                                                              reinterpret_cast<const uint32_t *>(d_stage + n), n);
+    ctx->launches++;
+    LDX_CUDA(cudaGetLastError());
+    LDX_CUDA(cudaStreamSynchronize(ctx->stream));                 // `stage` is a local
     if (n_fixed_out) *n_fixed_out = (int64_t)recs.size();
     return LDX_OK;
 }

@@ -5,10 +5,12 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
 #include "ldx_internal.h"
+#include "ldx_fixup.cuh"
 
 // ------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_last_error;
@@ -19,6 +21,13 @@ int cuda_fail(cudaError_t e, const char *what) {
     g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
     cudaGetLastError();   // clear the sticky-less error state
     return LDX_ERR_CUDA;
+}
+int after_launch(ldx_ctx *ctx, const char *kernel) {
+    static const bool debug_sync = getenv("LDX_DEBUG_SYNC") != nullptr;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && debug_sync) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(e, kernel);
+    return LDX_OK;
 }
 }  // namespace ldx
 using namespace ldx;
@@ -295,6 +304,26 @@ static int collect_fixups(ldx_ctx *ctx, std::vector<FixupRec> &recs, bool use_ma
     return LDX_OK;
 }
 
+// A *_dev call: reserve the next slot of the pending queue and tag the fix-up records its kernels append.
+static int resolve_pending(ldx_ctx *ctx, int64_t *n_fixed_out);
+static int begin_dev_call(ldx_ctx *ctx) {
+    if (ctx->pending_q.size() >= 4096) LDX_TRY(resolve_pending(ctx, nullptr));   // keeps the tag within 16 bits
+    ctx->fix_tag = (uint64_t)(ctx->pending_q.size() + 1) << FIX_TAG_SHIFT;
+    return LDX_OK;
+}
+static void end_dev_call(ldx_ctx *ctx, int kind, void *dev_out, double n_hap, int measure, int has_thres, int thres_e4) {
+    ldx_ctx::Pending p;
+    p.kind = kind; p.dev_out = dev_out; p.n_hap = n_hap; p.measure = measure; p.has_thres = has_thres; p.thres_e4 = thres_e4;
+    ctx->pending_q.push_back(p);
+    ctx->fix_tag = 0;
+}
+// Host-buffer entry points collect every record on the device list as their own: settle what enqueued
+// device-resident calls left there first.
+static int settle_before_host_call(ldx_ctx *ctx) {
+    ctx->fix_tag = 0;
+    return ctx->pending_q.empty() ? (int)LDX_OK : resolve_pending(ctx, nullptr);
+}
+
 static uint32_t settle_word(const FixupRec &r, double N, int measure, int has_thres, int thres_e4) {
     uint32_t w = host_finalise_packed(N, r.n11, r.n1a, r.n1b, nullptr);
     if (has_thres && word_measure(w, measure) < thres_e4) w |= LDX_BELOW_THRES;
@@ -362,6 +391,7 @@ extern "C" int32_t ldx_finalise_counts(ldx_ctx *ctx, int32_t n_hap, const int32_
                     n11[k] <= n1a[k] && n11[k] <= n1b[k] && n1a[k] + n1b[k] - n11[k] <= n_hap, "inconsistent counts");
     if (n == 0) return LDX_OK;
     LDX_CUDA(cudaSetDevice(ctx->device));
+    LDX_TRY(settle_before_host_call(ctx));
     FinalCtx fc;
     LDX_TRY(make_final_ctx(n_hap, &fc));
     int32_t *d_in; double *d_d = nullptr, *d_dp = nullptr, *d_r2 = nullptr; uint32_t *d_pk;
@@ -608,6 +638,7 @@ extern "C" int32_t ldx_pairs(ldx_store *s, const int64_t *ia, const int64_t *ib,
     if (n == 0) return LDX_OK;
     ldx_ctx *ctx = s->ctx;
     LDX_CUDA(cudaSetDevice(ctx->device));
+    LDX_TRY(settle_before_host_call(ctx));
     int64_t *d_ia, *d_ib; int32_t *d_n11 = nullptr; double *d_d = nullptr, *d_dp = nullptr, *d_r2 = nullptr; uint32_t *d_pk = nullptr;
     LDX_TRY(arena_get(ctx, S_IA, sizeof(int64_t) * (size_t)n, (void **)&d_ia));
     LDX_TRY(arena_get(ctx, S_IB, sizeof(int64_t) * (size_t)n, (void **)&d_ib));
@@ -689,12 +720,12 @@ extern "C" int32_t ldx_window_dev(ldx_store *s, const int64_t *q_row, const int6
     // dev_n_hits: [0] hits, [1] pairs scanned
     LDX_CUDA(cudaMemsetAsync(dev_n_hits, 0, 2 * sizeof(int64_t), ctx->stream));
     if (nq == 0 || n_chunks == 0) return LDX_OK;
+    LDX_TRY(begin_dev_call(ctx));
     LDX_TRY(launch_window(s, arr[0], arr[1], arr[2], (const int32_t *)arr[4], (const int32_t *)arr[5], arr[3], nq,
                           n_chunks, measure, thres_e4, dev_hits, cap, reinterpret_cast<unsigned long long *>(dev_n_hits)));
     ++ctx->seq;
     LDX_TRY(launch_publish(ctx));
-    ctx->pending.kind = 2; ctx->pending.dev_out = dev_hits; ctx->pending.n_hap = s->fc.n_hap;
-    ctx->pending.measure = measure; ctx->pending.has_thres = 1; ctx->pending.thres_e4 = thres_e4;
+    end_dev_call(ctx, 2, dev_hits, s->fc.n_hap, measure, 1, thres_e4);
     return LDX_OK;
 }
 
@@ -708,9 +739,10 @@ extern "C" int32_t ldx_window(ldx_store *s, const int64_t *q_row, const int64_t 
     if (n_scanned) *n_scanned = 0;
     ldx_hit *d_hits; int64_t *d_cnt;
     LDX_TRY(arena_get(ctx, S_HITS, sizeof(ldx_hit) * (size_t)std::max<int64_t>(cap, 1), (void **)&d_hits));
+    LDX_TRY(settle_before_host_call(ctx));
     LDX_TRY(arena_get(ctx, S_MISC, 2 * sizeof(int64_t), (void **)&d_cnt));
     LDX_TRY(ldx_window_dev(s, q_row, lo, hi, win_start, win_end, nq, measure, thres_e4, d_hits, cap, d_cnt));
-    ctx->pending.kind = 0;
+    ctx->pending_q.clear();                // this call settles its own records below
     int64_t h_cnt[2] = {0, 0};
     LDX_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof h_cnt, cudaMemcpyDeviceToHost, ctx->stream));
     LDX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -726,7 +758,7 @@ extern "C" int32_t ldx_window(ldx_store *s, const int64_t *q_row, const int64_t 
     LDX_TRY(collect_fixups(ctx, recs));   // synchronises
     for (const FixupRec &r : recs) {
         const uint32_t w = settle_word(r, s->fc.n_hap, measure, 1, thres_e4);
-        hits[r.out_index].packed = w;      // LDX_BELOW_THRES marks hits the exact rounding rejects
+        hits[r.out_index & FIX_INDEX_MASK].packed = w;      // LDX_BELOW_THRES marks hits the exact rounding rejects
     }
     int64_t kept = n;
     if (!recs.empty()) {
@@ -780,13 +812,13 @@ extern "C" int32_t ldx_triangle_rows_dev(ldx_store *s, const int64_t *rows, int6
                                                       s->n_sel <= triangle_mma_max_haplotypes());
     // rows[] staging is consumed by the kernel on the same stream (stage_rows keeps a host copy alive)
     const uint32_t seq = ctx->seq + 1 ? ctx->seq + 1 : 1;     // 0 means "nothing published"
+    LDX_TRY(begin_dev_call(ctx));
     int rc = use_mma ? launch_triangle_mma(s, d_rows, row_end, row_begin, measure, has_thres, thres_e4, dev_packed, dev_n11, seq)
                      : launch_triangle_popc(s, d_rows, row_end, row_begin, measure, has_thres, thres_e4, dev_packed, dev_n11);
     LDX_TRY(rc);
     ctx->seq = seq;
     if (!use_mma) LDX_TRY(launch_publish(ctx));
-    ctx->pending.kind = 1; ctx->pending.dev_out = dev_packed; ctx->pending.n_hap = s->fc.n_hap;
-    ctx->pending.measure = measure; ctx->pending.has_thres = has_thres; ctx->pending.thres_e4 = thres_e4;
+    end_dev_call(ctx, 1, dev_packed, s->fc.n_hap, measure, has_thres, thres_e4);
     return LDX_OK;
 }
 
@@ -804,19 +836,20 @@ extern "C" int32_t ldx_triangle_rows(ldx_store *s, const int64_t *rows, int64_t 
     ldx_ctx *ctx = s->ctx;
     const int64_t n_pairs = (row_end > 1 ? row_end * (row_end - 1) / 2 : 0) - (row_begin > 1 ? row_begin * (row_begin - 1) / 2 : 0);
     uint32_t *d_pk = nullptr; int32_t *d_n11 = nullptr;
+    LDX_TRY(settle_before_host_call(ctx));
     if (n_pairs) {
         LDX_TRY(arena_get(ctx, S_PACKED, sizeof(uint32_t) * (size_t)n_pairs, (void **)&d_pk));   // always: fix-ups index it
         if (n11) LDX_TRY(arena_get(ctx, S_N11, sizeof(int32_t) * (size_t)n_pairs, (void **)&d_n11));
     }
     LDX_TRY(ldx_triangle_rows_dev(s, rows, v, row_begin, row_end, measure, has_thres, thres_e4, engine, d_pk, d_n11));
-    ctx->pending.kind = 0;
+    ctx->pending_q.clear();                // this call settles its own records below
     if (!n_pairs) return LDX_OK;
     if (packed) LDX_CUDA(cudaMemcpyAsync(packed, d_pk, sizeof(uint32_t) * (size_t)n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
     if (n11) LDX_CUDA(cudaMemcpyAsync(n11, d_n11, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<FixupRec> recs;
     LDX_TRY(collect_fixups(ctx, recs));   // synchronises
     if (packed)
-        for (const FixupRec &r : recs) packed[r.out_index] = settle_word(r, s->fc.n_hap, measure, has_thres, thres_e4);
+        for (const FixupRec &r : recs) packed[r.out_index & FIX_INDEX_MASK] = settle_word(r, s->fc.n_hap, measure, has_thres, thres_e4);
     return LDX_OK;
 }
 
@@ -832,33 +865,41 @@ __global__ void scatter_words_kernel(uint8_t *base, const uint64_t *__restrict__
     if (i < n) *reinterpret_cast<uint32_t *>(base + byte_off[i]) = words[i];
 }
 
-extern "C" int32_t ldx_resolve(ldx_ctx *ctx, int64_t *n_fixed_out) {
-    LDX_REQUIRE(ctx, "ctx is NULL");
+static int resolve_pending(ldx_ctx *ctx, int64_t *n_fixed_out) {
     if (n_fixed_out) *n_fixed_out = 0;
     LDX_CUDA(cudaSetDevice(ctx->device));
     std::vector<FixupRec> recs;
     LDX_TRY(collect_fixups(ctx, recs, true));
-    const ldx_ctx::Pending p = ctx->pending;
-    ctx->pending.kind = 0;
-    if (recs.empty() || p.kind == 0) return LDX_OK;
+    std::vector<ldx_ctx::Pending> q;
+    q.swap(ctx->pending_q);
+    ctx->fix_tag = 0;
+    if (recs.empty() || q.empty()) return LDX_OK;
     // settle on the host (libm pow), then ONE upload and one scatter kernel: a 100,000-variant triangle
     // has ~10^4 near-ties, far too many for a copy + synchronise each
     const size_t n = recs.size();
-    std::vector<uint64_t> stage(n + (n + 1) / 2);                 // [n] byte offsets | [n] words
+    std::vector<uint64_t> stage(n + (n + 1) / 2);                 // [n] device addresses | [n] words
     uint32_t *words = reinterpret_cast<uint32_t *>(stage.data() + n);
     for (size_t i = 0; i < n; ++i) {
         const FixupRec &r = recs[i];
+        const size_t call = (size_t)(r.out_index >> FIX_TAG_SHIFT);
+        if (call == 0 || call > q.size()) return set_error(LDX_ERR_STATE, "fix-up record without a pending call");
+        const ldx_ctx::Pending &p = q[call - 1];
+        const uint64_t idx = r.out_index & FIX_INDEX_MASK;
         words[i] = settle_word(r, p.n_hap, p.measure, p.has_thres, p.thres_e4);
-        stage[i] = p.kind == 1 ? r.out_index * sizeof(uint32_t) : r.out_index * sizeof(ldx_hit) + offsetof(ldx_hit, packed);
+        stage[i] = reinterpret_cast<uint64_t>(p.dev_out) + (p.kind == 1 ? idx * sizeof(uint32_t) : idx * sizeof(ldx_hit) + offsetof(ldx_hit, packed));
     }
     uint64_t *d_stage;
     LDX_TRY(arena_get(ctx, S_MISC, stage.size() * sizeof(uint64_t), (void **)&d_stage));
     LDX_CUDA(cudaMemcpyAsync(d_stage, stage.data(), stage.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    scatter_words_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint8_t *>(p.dev_out), d_stage,
-                                                                              reinterpret_cast<const uint32_t *>(d_stage + n), n);
+    scatter_words_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(nullptr, d_stage, reinterpret_cast<const uint32_t *>(d_stage + n), n);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
     LDX_CUDA(cudaStreamSynchronize(ctx->stream));                 // `stage` is a local
     if (n_fixed_out) *n_fixed_out = (int64_t)recs.size();
     return LDX_OK;
+}
+
+extern "C" int32_t ldx_resolve(ldx_ctx *ctx, int64_t *n_fixed_out) {
+    LDX_REQUIRE(ctx, "ctx is NULL");
+    return resolve_pending(ctx, n_fixed_out);
 }

@@ -20,13 +20,18 @@ struct ldx_ctx {
     uint32_t fix_capacity = 0;
     ldx::FixupRec *h_fix = nullptr;       // pinned
     uint32_t *h_fix_count = nullptr;      // pinned
-    // what the pending fix-ups refer to (set by the last *_dev call)
+    // What the fix-ups on the device list refer to: one entry per *_dev call enqueued since the last
+    // ldx_resolve().  Call number k (1-based index into pending_q) tags its records with k << 48 in
+    // out_index (fix_tag while its kernels are being launched); tag 0 = a host-buffer call, which
+    // collects its own records before returning.
     struct Pending {
-        int kind = 0;                     // 0 none, 1 packed array, 2 hit array
+        int kind = 0;                     // 1 packed array, 2 hit array
         void *dev_out = nullptr;
         double n_hap = 0;
         int measure = 0, has_thres = 0, thres_e4 = 0;
-    } pending;
+    };
+    std::vector<Pending> pending_q;
+    uint64_t fix_tag = 0;
     // scratch for small per-call index arrays
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -37,6 +42,7 @@ struct ldx_ctx {
     int64_t mma_tiles_v = -1;             // tile list cached in d_mma_ops: built for this (v, N)
     int mma_tiles_n = 0;
     int64_t mma_tiles_begin = 0;
+    const void *mma_tiles_ptr = nullptr;  // where in d_mma_ops that list lives (depends on the haplotype count too)
     // completion mailbox: pinned, device-mapped {seq, near-tie count, error flag}; a 1-thread kernel
     // publishes it after each *_dev call so that ldx_resolve() can poll host memory instead of
     // paying a stream synchronisation (tens of microseconds) per call
@@ -77,6 +83,11 @@ namespace ldx {
 
 int set_error(int code, const std::string &msg);   // returns code
 int cuda_fail(cudaError_t e, const char *what);    // records + returns LDX_ERR_CUDA
+
+// After every kernel launch: the launch error, and -- with LDX_DEBUG_SYNC=1 in the environment -- a stream
+// synchronisation, so that a faulting kernel is reported at its own launch site.
+int after_launch(ldx_ctx *ctx, const char *kernel);
+#define LDX_LAUNCHED(ctx, name) do { int rc__ = ldx::after_launch(ctx, name); if (rc__ != LDX_OK) return rc__; } while (0)
 
 #define LDX_CUDA(call)                                                   \
     do {                                                                 \

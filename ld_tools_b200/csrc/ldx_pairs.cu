@@ -60,7 +60,7 @@ int launch_pairs(ldx_store *s, const int64_t *d_ia, const int64_t *d_ib, int64_t
     pairs_kernel<<<(int)blocks, PAIRS_THREADS, 0, ctx->stream>>>(
         reinterpret_cast<const uint4 *>(s->d_planes), reinterpret_cast<const uint4 *>(s->d_mask),
         s->stride_words / 2, s->d_freq, s->fc, d_ia, d_ib, n, d_n11, d_d, d_dp, d_r2, d_packed,
-        FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity});
+        FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity, ctx->fix_tag});
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
     return LDX_OK;
@@ -100,7 +100,7 @@ int launch_finalise_counts(ldx_ctx *ctx, const FinalCtx &fc, const int32_t *d_n1
     const int64_t cap = (int64_t)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;
     finalise_counts_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(fc, d_n11, d_n1a, d_n1b, n, d_d, d_dp, d_r2, d_packed,
-                                                                  FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity});
+                                                                  FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity, ctx->fix_tag});
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
     return LDX_OK;

@@ -45,7 +45,7 @@ namespace ldx {
 constexpr int MMA_M = 128;            // rows (variants) per tile = TMEM lanes
 constexpr int KCHUNK = 128;           // haplotypes (= bytes) per shared-memory row: one swizzle atom
 constexpr int MMA_K = 32;             // int8 K of one tcgen05.mma
-constexpr int PANEL_BYTES = MMA_M * KCHUNK;   // 16 KB: one (panel, chunk) block
+
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -740,7 +740,7 @@ static int launch_tiles_t(ldx_ctx *ctx, const MmaArgs &A) {
     triangle_mma_kernel<N, WANT_N11, THRES, TRACE><<<grid, MMA_THREADS, MmaCfg<N>::SMEM, ctx->stream>>>(A);
     timing_end(ctx);
     ctx->launches++;
-    LDX_CUDA(cudaGetLastError());
+    LDX_LAUNCHED(ctx, "triangle_mma_kernel");
     return LDX_OK;
 }
 template <int N>
@@ -797,7 +797,8 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t 
     VarFreq *d_freq_rows = reinterpret_cast<VarFreq *>(base + 2 * bits_bytes);
     int2 *d_tiles = reinterpret_cast<int2 *>(base + 2 * bits_bytes + freq_bytes);
     uint4 *d_slow = reinterpret_cast<uint4 *>(base + 2 * bits_bytes + freq_bytes + tile_bytes);
-    if (ctx->mma_tiles_v != v || ctx->mma_tiles_n != n_tile || ctx->mma_tiles_begin != row_begin) {   // the list depends on (v, row_begin, N) only
+    if (ctx->mma_tiles_v != v || ctx->mma_tiles_n != n_tile || ctx->mma_tiles_begin != row_begin || ctx->mma_tiles_ptr != d_tiles) {
+        // the list depends on (v, row_begin, N) only; its PLACE in the scratch block also on the haplotype count
         // Longest tiles first is not needed (all tiles cost the same K loop); the list is ordered so
         // that the tiles a wave of CTAs works on share row panels and neighbouring column blocks in L2.
         std::vector<int2> tiles;
@@ -808,14 +809,14 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t 
         }
         LDX_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), n_tiles * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
         LDX_CUDA(cudaStreamSynchronize(ctx->stream));   // `tiles` is a local
-        ctx->mma_tiles_v = v; ctx->mma_tiles_n = n_tile; ctx->mma_tiles_begin = row_begin;
+        ctx->mma_tiles_v = v; ctx->mma_tiles_n = n_tile; ctx->mma_tiles_begin = row_begin; ctx->mma_tiles_ptr = d_tiles;
     }
 
     dim3 ggrid((unsigned)((v_pad + 255) / 256), (unsigned)kc_count);
     gather_bits_kernel<<<ggrid, 256, 0, ctx->stream>>>(s->d_planes, s->d_mask, s->stride_words, d_rows, v, v_pad, kc_count,
                                                        s->d_freq, d_bits, d_bits_rev, d_freq_rows);
     ctx->launches++;
-    LDX_CUDA(cudaGetLastError());
+    LDX_LAUNCHED(ctx, "gather_bits_kernel");
 
     MmaArgs A;
     A.bits = d_bits; A.bits_rev = d_bits_rev; A.kc_count = kc_count; A.freq_rows = d_freq_rows; A.fc = s->fc; A.tiles = d_tiles;
@@ -832,7 +833,7 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t 
         A.lim_r2 = ok ? (float)(0.5 - (g + 1.0e-5)) : -1.0f;
         A.lim_dp = ok ? (float)(0.5 - (0.5 * g + 1.0e-5)) : -1.0f;
     }
-    A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity};
+    A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity, ctx->fix_tag};
     A.error_flag = reinterpret_cast<int32_t *>(ctx->d_fix_count + 1);
     A.slow = d_slow; A.slow_count = ctx->d_fix_count + 2; A.slow_cap = (uint32_t)slow_cap64;
     A.trace = ctx->d_trace;
@@ -850,7 +851,7 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t 
     slow_pairs_kernel<<<sgrid, 256, 0, ctx->stream>>>(d_slow, ctx->d_fix_count, A.slow_cap, d_freq_rows, s->fc, measure, has_thres,
                                                       thres_e4, d_packed, A.out_off, A.fix, publish_seq ? ctx->d_mailbox : nullptr, publish_seq);
     ctx->launches++;
-    LDX_CUDA(cudaGetLastError());
+    LDX_LAUNCHED(ctx, "slow_pairs_kernel");
     return LDX_OK;
 }
 

@@ -136,7 +136,7 @@ int launch_triangle_popc(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t
     A.n_tiles_side = (v + TRI_TILE - 1) / TRI_TILE;
     A.measure = measure; A.has_thres = has_thres; A.thres_e4 = thres_e4;
     A.packed = d_packed; A.n11 = d_n11;
-    A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity};
+    A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity, ctx->fix_tag};
     const int64_t bi_begin = row_begin / TRI_TILE;
     A.tile_begin = bi_begin * (bi_begin + 1) / 2;
     A.out_off = row_begin * (row_begin - 1) / 2;
@@ -152,7 +152,7 @@ int launch_triangle_popc(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t
     triangle_popc_kernel<<<(int)n_tiles, TRI_THREADS, smem, ctx->stream>>>(A);
     timing_end(ctx);
     ctx->launches++;
-    LDX_CUDA(cudaGetLastError());
+    LDX_LAUNCHED(ctx, "triangle_popc_kernel");
     return LDX_OK;
 }
 

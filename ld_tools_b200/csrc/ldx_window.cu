@@ -177,7 +177,7 @@ static int launch_window_ng(ldx_ctx *ctx, const WindowArgs &A) {
     window_kernel<NG><<<(int)grid, WIN_THREADS, 0, ctx->stream>>>(A);
     timing_end(ctx);
     ctx->launches++;
-    LDX_CUDA(cudaGetLastError());
+    LDX_LAUNCHED(ctx, "window_kernel");
     return LDX_OK;
 }
 
@@ -197,7 +197,7 @@ int launch_window(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, cons
     A.chunk_prefix = d_chunk_prefix; A.nq = nq; A.n_chunks = n_chunks;
     A.measure = measure; A.thres_e4 = thres_e4;
     A.hits = d_hits; A.cap = cap; A.counters = d_counters;
-    A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity};
+    A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity, ctx->fix_tag};
     switch (A.stride_u4 / 8) {
         case 1: return launch_window_ng<1>(ctx, A);
         case 2: return launch_window_ng<2>(ctx, A);

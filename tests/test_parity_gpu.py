@@ -464,3 +464,39 @@ def test_kernel_timing_counts_the_all_pairs_launches(ctx):
     ms, n = ctx.kernel_timing(False)
     assert n == 0 and ms == 0.0
     st.close()
+
+
+def test_several_device_resident_calls_one_resolve(ctx):
+    """Calls enqueued back to back (each with its own result buffer) and settled by ONE ldx_resolve():
+    the near-tie records of every call must find their way to the right buffer.  Small haplotype
+    counts make exact rounding ties (r2 * 10^4 = k + 1/2) common.  (Same variant count as the 5008-
+    haplotype test before it: the cached tile list must not be taken for this call's.)"""
+    import torch
+    from ld_tools_b200.engine import ENGINE_MMA, ENGINE_POPC, threshold_e4
+    n_var, n_hap = 600, 198
+    st, planes, mask = make_store(ctx, n_var, n_hap, seed=12)
+    dev = torch.device("cuda", 0)
+    calls = []
+    rng = np.random.default_rng(8)
+    for k, (engine, measure, thres) in enumerate([(ENGINE_MMA, "r_square", None), (ENGINE_POPC, "d_prime", 0.5),
+                                                  (ENGINE_MMA, "r_square", 0.1), (ENGINE_MMA, "d_prime", None)]):
+        rows = rng.permutation(n_var)[: 300 + 100 * (k % 3)]
+        v = len(rows)
+        out = torch.zeros(v * (v - 1) // 2, dtype=torch.int32, device=dev)
+        t = None if thres is None else threshold_e4(thres)
+        torch.cuda.synchronize()
+        st.triangle_dev(rows, out.data_ptr(), measure=measure, thres_e4_=t, engine=engine)
+        calls.append((rows, out, measure, t))
+    n_fixed = ctx.resolve()
+    for rows, out, measure, t in calls:
+        want = ld_oracle.packed_of(ld_oracle.triangle(planes, mask, n_hap, rows))
+        if t is not None:
+            shift = 0 if measure == "r_square" else 16
+            want = want | np.where(((want >> shift) & 0x3FFF) < t, np.uint32(0x40000000), np.uint32(0))
+        got = out.cpu().numpy().view(np.uint32)
+        assert (got == want).all(), (measure, t, int((got != want).sum()))
+    assert n_fixed > 0, "this input is expected to contain rounding near-ties"
+    # a host-buffer call right after still sees a clean list
+    packed, _ = st.triangle(np.arange(200))
+    assert (packed == ld_oracle.packed_of(ld_oracle.triangle(planes, mask, n_hap, np.arange(200)))).all()
+    st.close()

@@ -365,12 +365,132 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------- ld_area workload (BASELINE configs[2])
+AREA_VARIANTS, AREA_QUERIES, AREA_FLANK, AREA_EUR_SAMPLES = 1_100_000, 1000, 500_000, 503
+AREA_WORKLOAD = ("ld_area: 1,000 query variants, +/-500 kb flanks, r2 >= 0.8, EUR subset (503 samples = 1006 of 5008 "
+                 "haplotypes, by mask), synthetic 1.1M-variant chr22 (BASELINE configs[2])")
+
+
+def run_area(args, rank, world, local_rank):
+    """The window scan (K4, ld_area.py:215-249): value = candidate pairs scanned per second with the store
+    resident in HBM; e2e = through the host API (query arrays H2D, kept hits D2H and sorted).  With N GPUs
+    every rank owns its own chromosome-sized store (region sharding: ld_tools_b200/shard.py)."""
+    import torch
+    import torch.distributed as dist
+    from ld_tools_b200 import Context, Store, shard
+    from ld_tools_b200.engine import threshold_e4
+    from ld_tools_b200.synth import random_planes
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    ctx = Context(local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    rng = np.random.default_rng(77 + rank)
+    nv = AREA_VARIANTS
+    st = Store(ctx, nv, N_HAP)
+    for a in range(0, nv, 100_000):                                   # built in slabs: bounded host memory
+        b = min(a + 100_000, nv)
+        st.upload(a, random_planes(b - a, N_HAP, seed=1000 * rank + a))
+    pos0 = np.sort(rng.integers(16_050_000, 51_200_000, size=nv)).astype(np.int32)
+    end0 = pos0 + 1
+    st.set_annotations(pos0, end0, np.arange(nv, dtype=np.int64), np.ones(nv, np.uint8))
+    hap = np.sort(rng.choice(N_HAP // 2, AREA_EUR_SAMPLES, replace=False))
+    st.select_haplotypes(np.concatenate([2 * hap, 2 * hap + 1]))      # get_sample_names -> mask plane
+    q_row = np.sort(rng.choice(nv, AREA_QUERIES, replace=False)).astype(np.int64)
+    lo, hi, ws, we = shard.window_bounds(pos0, 1, pos0[q_row].astype(np.int64) + 1, AREA_FLANK)
+    n_cand = int((hi - lo).sum())
+    thres = threshold_e4(0.8)
+    cap = 1 << 22
+    d_hits = torch.empty(cap * 4, dtype=torch.int32, device=dev)
+    d_cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        st.window_dev(q_row, lo, hi, ws, we, "r_square", thres, d_hits.data_ptr(), cap, d_cnt.data_ptr())
+        ctx.resolve()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count
+    ctx.kernel_timing(True)
+    ev = []
+    for _ in range(args.steps):
+        flush.zero_()                       # the 704 MB store is larger than L2 anyway; flushed for good measure
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        ev.append((e0, e1))
+    barrier()
+    launches = ctx.launch_count - launches0
+    dom_ms, dom_n = ctx.kernel_timing(False)
+    step_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    scanned = int(d_cnt.cpu()[1])
+    n_hits = int(d_cnt.cpu()[0])
+    # e2e: host API
+    for _ in range(2):
+        st.window(q_row, lo, hi, ws, we, "r_square", thres, cap=cap)
+    barrier()
+    e_steps = max(args.steps // 4, 3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        hits, sc = st.window(q_row, lo, hi, ws, we, "r_square", thres, cap=cap)
+    e1.record(stream)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    e2e_ms = float(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    t = torch.tensor([step_ms, e2e_ms, dom_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms, e2e_ms, dom_ms = t.tolist()
+    row_bytes = st.stride_words * 8
+    kern_s = dom_ms * 1e-3 / max(dom_n, 1)
+    roof = {"bound": "hbm", "achieved": scanned * row_bytes / kern_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "peak_source": f"{peaks['source']} copy bandwidth", "traffic": None, "kernel": "window_kernel", "kernel_ms": kern_s * 1e3,
+            "kernel_launches_timed": int(dom_n),
+            "algorithmic_per_launch": f"{scanned} pairs x {row_bytes} B (one candidate row each; query plane and mask in registers)"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    line = {"metric": "variant pairs/sec (r2+D', 5008 haplotypes)", "value": scanned * world * args.steps / (step_ms * 1e-3),
+            "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 popcount + f64", "data": "synthetic",
+            "config": {"workload": AREA_WORKLOAD, "pairs_per_step_per_gpu": scanned, "candidate_rows_per_step": n_cand,
+                       "hits_per_step": n_hits, "l2": "store (704 MB) larger than L2; 256 MiB flush between timed iterations",
+                       "sharding": "one chromosome store per GPU"},
+            "e2e": {"value": scanned * world * e_steps / (e2e_ms * 1e-3), "unit": "pairs/s",
+                    "h2d_bytes_per_step": int(q_row.nbytes + lo.nbytes + hi.nbytes + ws.nbytes + we.nbytes + 8 * (len(q_row) + 1)),
+                    "d2h_bytes_per_step": int(16 * len(hits) + 16), "steps": e_steps, "wall_s": e2e_wall},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    st.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=["ld_triangle", "ld_area"], default="ld_triangle",
+                    help="ld_triangle = BASELINE configs[1] (the headline); ld_area = configs[2], the HBM-bound window scan")
     ap.add_argument("--engine", choices=["auto", "popc", "mma"], default="auto")
     ap.add_argument("--tile-n", type=int, default=0, help="tcgen05 tile width override (0 = heuristic)")
     ap.add_argument("--cpu-pairs-per-core", type=int, default=2000)
@@ -383,6 +503,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+    elif args.workload == "ld_area":
+        run_area(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -31,12 +31,45 @@ struct WindowArgs {
     const int64_t *q_row, *lo, *hi; const int32_t *win_start, *win_end;
     const int64_t *chunk_prefix; int64_t nq, n_chunks;
     int measure, thres_e4;
+    int32_t n_sel;                 // N under the mask
+    float screen_t, screen_g;      // single-precision screen (see screen_below): threshold - 1/2 - slack, and the
+                                   // reference chain's own error bound; screen_t <= 0 switches the screen off
     ldx_hit *hits; int64_t cap; unsigned long long *counters;   // [0] hits, [1] pairs scanned
     FixupSink fix;
 };
 
+// Single-precision screen of the rounded-threshold test (ld_area.py:248).  Almost every candidate of a
+// window is far below an LD threshold like r2 >= 0.8; for those the fp64 chain of calc_ld.py:33-97 need not
+// run at all.  x = value * 10^4 is evaluated from the exact integers Dn = n11*N - n1a*n1b, ... with a
+// relative error below 12 * 2^-24 (same arithmetic and bound as the all-pairs epilogue,
+// ldx_triangle_mma.cu), and the reference's own chain is within g of the exact ratio: when
+// x + error < T - 1/2 the reference's round(value, 4) * 10^4 is at most T - 1 and the row is dropped.
+// A monomorphic pair is int 0 in the reference (calc_ld.py:68-69, :89-90): below any positive threshold.
+// Everything else -- including every kept row -- takes the exact path.  Needs N <= 8192 (int32 products).
+__device__ __forceinline__ bool screen_below(int32_t n11, int32_t N, int32_t n1a, int32_t n1b, int measure, float t_minus, float g) {
+    const int32_t n0a = N - n1a, n0b = N - n1b, P = n1a * n1b, Dn = n11 * N - P;
+    const float fD = fabsf(__int2float_rn(Dn));
+    float x, err;
+    if (measure == LDX_MEASURE_R2) {
+        const int32_t da = n1a * n0a, db = n1b * n0b;
+        if (da == 0 || db == 0) return true;
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(__int2float_rn(da), __int2float_rn(db))));
+        x = __fmul_rn(__fmul_rn(__fmul_rn(fD, 1.0e4f), fD), r);
+        err = __fmaf_rn(x, 12.0f * 5.9604644775390625e-08f, g);
+    } else {
+        const int32_t m = Dn > 0 ? min(n1a * n0b, n0a * n1b) : min(P, n0a * n0b);
+        if (m == 0) return true;
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__int2float_rn(m)));
+        x = __fmul_rn(__fmul_rn(fD, 1.0e4f), r);
+        err = __fmaf_rn(x, 8.0f * 5.9604644775390625e-08f, g);
+    }
+    return __fadd_rn(x, err) < t_minus;      // false for NaN: falls to the exact path
+}
+
 template <int NG>   // NG = 16-byte granules per lane per row; 0 = runtime loop
-__global__ void __launch_bounds__(WIN_THREADS)
+__global__ void __launch_bounds__(WIN_THREADS, 3)
 window_kernel(const WindowArgs A) {
     __shared__ int64_t s_q, s_base;
     const int tid = threadIdx.x, lane8 = tid & 7, group = tid >> 3;
@@ -129,8 +162,8 @@ window_kernel(const WindowArgs A) {
             const bool scan = A.pos0[row] < we && A.end0[row] > ws      // fetch overlap, ld_area.py:215-217
                               && A.eligible[row]                           // rs\d+$ and not MULTI_ALLELIC, :223-224
                               && A.idnum[row] != A.idnum[qrow];            // :222
-            if (scan) {
-                ++scanned;
+            if (scan) ++scanned;
+            if (scan && !(A.screen_t > 0.0f && screen_below(n11, A.n_sel, A.freq[qrow].n1, A.freq[row].n1, A.measure, A.screen_t, A.screen_g))) {
                 const VarFreq fa = A.freq[qrow], fb = A.freq[row];         // var_1 = query, var_2 = row (:242)
                 const PairFinal f = finalise_pair(n11, fa, fb, A.fc);
                 packed = f.packed;
@@ -196,6 +229,12 @@ int launch_window(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, cons
     A.q_row = d_qrow; A.lo = d_lo; A.hi = d_hi; A.win_start = d_ws; A.win_end = d_we;
     A.chunk_prefix = d_chunk_prefix; A.nq = nq; A.n_chunks = n_chunks;
     A.measure = measure; A.thres_e4 = thres_e4;
+    A.n_sel = s->n_sel;
+    {
+        const double n = (double)s->n_sel, g = 1.0e4 * 16.0 * 1.1102230246251565e-16 * n * n;
+        A.screen_g = (float)(g + 1.0e-4);
+        A.screen_t = (s->n_sel <= 8192 && thres_e4 > 0) ? (float)((double)thres_e4 - 0.5 - 1.0e-3) : 0.0f;
+    }
     A.hits = d_hits; A.cap = cap; A.counters = d_counters;
     A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity, ctx->fix_tag};
     switch (A.stride_u4 / 8) {

@@ -846,8 +846,9 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t 
     }
     if (rc != LDX_OK) return rc;
     // deferred pairs + completion record (d_fix_count: [0] near-ties, [1] error flag, [2] deferred pairs, [3] ticket)
-    // ~1% of the pairs are deferred: size the grid for two pairs per thread at that rate
-    const int sgrid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 4, std::max<uint64_t>(1, n_pairs / (1u << 16)));
+    // ~1% of the pairs are deferred and each costs a long, serial fp64 chain: one pair per thread at twice that
+    // rate (idle blocks are cheap, a thread looping over several pairs is not)
+    const int sgrid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 8, std::max<uint64_t>(1, n_pairs / (50u * 256u) + 1));
     slow_pairs_kernel<<<sgrid, 256, 0, ctx->stream>>>(d_slow, ctx->d_fix_count, A.slow_cap, d_freq_rows, s->fc, measure, has_thres,
                                                       thres_e4, d_packed, A.out_off, A.fix, publish_seq ? ctx->d_mailbox : nullptr, publish_seq);
     ctx->launches++;

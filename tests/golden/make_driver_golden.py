@@ -1,0 +1,69 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/drivers/: the output trees of the UNMODIFIED reference drivers
+(/root/reference/ld_area.py, ld_triangle.py, ld_lite.py) on the synthetic data set of
+tests/driver_cases.py.  pysam and plotly are absent from this container, so the drivers run against
+the pure-Python stand-ins in tests/refshim/ (see their docstrings).  Run here (needs /root/reference):
+
+    python tests/golden/make_driver_golden.py
+"""
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import driver_cases as dc  # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.join(HERE, "drivers")
+
+
+def run_ref(script, argv, cwd):
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "refshim"), PYTHONDONTWRITEBYTECODE="1", LANG="en_US.UTF-8",
+               LC_ALL="en_US.UTF-8", PYTHONWARNINGS="ignore")
+    r = subprocess.run([sys.executable, os.path.join(REF, script)] + argv, cwd=cwd, env=env, capture_output=True, text=True)
+    if r.returncode:
+        raise RuntimeError(f"{script} {argv}: rc={r.returncode}\n{r.stdout}\n{r.stderr}")
+    return r.stdout
+
+
+def main():
+    work = tempfile.mkdtemp(prefix="ldx_golden_")
+    intgen, srcs = dc.build_dataset(work)
+    if os.path.exists(OUT):
+        shutil.rmtree(OUT)
+    os.makedirs(OUT)
+    index = {}
+    for name, extra in dc.AREA_CASES:
+        trg = os.path.join(work, "out_" + name)
+        os.makedirs(trg)
+        run_ref("ld_area.py", ["-S", srcs["area"], "-D", intgen, "-t", trg, "-f", "-p", "1"] + extra, work)
+        shutil.copytree(trg, os.path.join(OUT, name))
+        index[name] = sorted(dc.read_tree(trg))
+    for name, extra in dc.TRIANGLE_CASES:
+        trg = os.path.join(work, "out_" + name)
+        os.makedirs(trg)
+        run_ref("ld_triangle.py", ["-S", srcs["triangle"], "-D", intgen, "-t", trg, "-f", "-p", "1"] + extra, work)
+        shutil.copytree(trg, os.path.join(OUT, name))
+        index[name] = sorted(dc.read_tree(trg))
+    for name, extra in dc.LITE_CASES:
+        os.makedirs(os.path.join(OUT, name))
+        for k, (a, b) in enumerate(srcs["lite_pairs"]):
+            text = run_ref("ld_lite.py", [a, b, "-D", intgen, "-f"] + extra, work)
+            with open(os.path.join(OUT, name, f"pair{k}.txt"), "w") as fh:
+                fh.write(text)
+        index[name] = sorted(os.listdir(os.path.join(OUT, name)))
+    with open(os.path.join(OUT, "index.json"), "w") as fh:
+        json.dump(index, fh, indent=1, sort_keys=True)
+    n = sum(len(v) for v in index.values())
+    print(f"wrote {n} golden files under {OUT}")
+    shutil.rmtree(work)
+
+
+if __name__ == "__main__":
+    main()

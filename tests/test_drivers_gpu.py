@@ -1,0 +1,93 @@
+"""End-to-end parity of the re-pointed drivers (ld_tools_b200/drivers.py: VCF ingest -> GPU bit packing
+-> one library call per chromosome -> the reference's writers) against the output trees the UNMODIFIED
+reference drivers produced on the same synthetic 1000G-format data (tests/golden/drivers/, made by
+tests/golden/make_driver_golden.py where /root/reference exists).  Byte for byte: file names, headers,
+row order, int-0 vs float, round(x, 4) formatting, empty-result files absent."""
+import argparse
+import json
+import os
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import driver_cases as dc  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(HERE, "golden", "drivers")
+
+
+@pytest.fixture(scope="module")
+def data(tmp_path_factory):
+    root = str(tmp_path_factory.mktemp("ldx_drivers"))
+    intgen, srcs = dc.build_dataset(root)
+    return root, intgen, srcs
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from ld_tools_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def parse(extra, kind):
+    """The reference's own option names (cli/ld_area_cli_en.py:36-60, cli/ld_triangle_cli_en.py:40-74)."""
+    ap = argparse.ArgumentParser()
+    ap.add_argument("-m", dest="meta_lines_quan", type=int, default=0)
+    ap.add_argument("-g", dest="gend_names", default="both")
+    ap.add_argument("-e", dest="pop_names", default="all")
+    if kind == "area":
+        ap.add_argument("-w", dest="flank_size", type=int, default=100000)
+        ap.add_argument("-l", dest="ld_thres_measure", default="r_square")
+        ap.add_argument("-z", dest="ld_low_thres", type=float, default=0.8)
+        ap.add_argument("-o", dest="trg_file_type", default="tsv")
+    elif kind == "triangle":
+        ap.add_argument("-l", dest="ld_measure", default="r_square")
+        ap.add_argument("-z", dest="ld_low_thres", type=float, default=None)
+        ap.add_argument("-o", dest="matrix_type", default="table")
+    return vars(ap.parse_args(extra))
+
+
+def assert_same_tree(got_root, name):
+    want = dc.read_tree(os.path.join(GOLD, name))
+    got = dc.read_tree(got_root)
+    assert sorted(got) == sorted(want), (sorted(set(got) ^ set(want)))
+    for rel in want:
+        assert got[rel] == want[rel], f"{name}/{rel} differs from the reference driver's output"
+    return len(want)
+
+
+@pytest.mark.parametrize("name,extra", dc.AREA_CASES)
+def test_ld_area_output_tree_identical(data, ctx, tmp_path, name, extra):
+    from ld_tools_b200 import drivers
+    root, intgen, srcs = data
+    kw = parse(extra, "area")
+    drivers.ld_area(srcs["area"], intgen, trg_top_dir_path=str(tmp_path), ctx=ctx, **kw)
+    n = assert_same_tree(str(tmp_path), name)
+    with open(os.path.join(GOLD, "index.json")) as fh:
+        assert n == len(json.load(fh)[name])
+
+
+@pytest.mark.parametrize("name,extra", dc.TRIANGLE_CASES)
+def test_ld_triangle_table_identical(data, ctx, tmp_path, name, extra):
+    from ld_tools_b200 import drivers
+    root, intgen, srcs = data
+    kw = parse(extra, "triangle")
+    kw.pop("matrix_type")
+    drivers.ld_triangle(srcs["triangle"], intgen, trg_top_dir_path=str(tmp_path), ctx=ctx, **kw)
+    assert assert_same_tree(str(tmp_path), name) == 1
+
+
+@pytest.mark.parametrize("name,extra", dc.LITE_CASES)
+def test_ld_lite_printout_identical(data, ctx, name, extra):
+    from ld_tools_b200 import drivers
+    root, intgen, srcs = data
+    kw = parse(extra, "lite")
+    kw.pop("meta_lines_quan")
+    for k, (a, b) in enumerate(srcs["lite_pairs"]):
+        text = drivers.ld_lite(a, b, intgen, ctx=ctx, **kw)
+        with open(os.path.join(GOLD, name, f"pair{k}.txt")) as fh:
+            assert text + "\n" == fh.read()

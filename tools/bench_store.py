@@ -1,0 +1,90 @@
+"""Kernel-level throughput of the store-side kernels on B200 (CUDA events around the library calls):
+K1 pack_gt (VCF GT text -> bit planes), K2 variant_freq (mask -> counts), K3 pairs, subset.
+
+    python tools/bench_store.py [--variants 200000]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from ld_tools_b200 import Context, Store  # noqa: E402
+from ld_tools_b200.synth import random_planes  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--variants", type=int, default=200_000)
+    args = ap.parse_args()
+    n_hap, n_samples, nv = 5008, 2504, args.variants
+    peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))
+    ctx = Context(0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+
+    def timed(fn, reps=5):
+        fn()
+        best = 1e9
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    out = {}
+    # ---- K2: mask + counts over the whole store
+    st = Store.from_planes(ctx, random_planes(nv, n_hap, seed=2), n_hap)
+    mask = np.full(st.stride_words, ~np.uint64(0), dtype="<u8")
+    ms = timed(lambda: st.set_mask(mask))
+    out["K2_variant_freq"] = {"ms": ms, "variants_per_s": nv / ms * 1e3, "GBps": nv * 640 / ms / 1e6,
+                              "note": "includes the host-side mask upload and the proof of the reciprocal (make_final_ctx)"}
+    # ---- K3: random pairs
+    rng = np.random.default_rng(1)
+    ia, ib = rng.integers(0, nv, 2_000_000), rng.integers(0, nv, 2_000_000)
+    ms = timed(lambda: st.pairs(ia, ib, raw=False), reps=3)
+    out["K3_pairs_host_api"] = {"ms": ms, "pairs_per_s": len(ia) / ms * 1e3, "GBps_rows": len(ia) * 1280 / ms / 1e6,
+                                "note": "host API: index upload + kernel + packed/n11 download"}
+    # ---- subset store (EUR-sized)
+    sel = np.sort(rng.choice(n_hap, 1006, replace=False)).astype(np.int32)
+    t0 = time.perf_counter()
+    sub = st.subset(sel)
+    ctx.synchronize()
+    out["subset_1006_of_5008"] = {"ms": (time.perf_counter() - t0) * 1e3, "variants": nv}
+    sub.close()
+    st.close()
+    # ---- K1: pack GT text (host text -> planes): H2D of the text dominates; report both
+    nv1 = min(nv, 50_000)
+    rowbytes = 4 * n_samples
+    text = np.empty((nv1, rowbytes), dtype=np.uint8)
+    bits = rng.integers(0, 2, size=(nv1, n_samples, 2), dtype=np.uint8)
+    text[:, 0::4] = bits[:, :, 0] + 48
+    text[:, 1::4] = 124
+    text[:, 2::4] = bits[:, :, 1] + 48
+    text[:, 3::4] = 9
+    flat = torch.from_numpy(text.reshape(-1)).pin_memory().numpy()
+    st1 = Store(ctx, nv1, n_hap)
+    ctx.kernel_timing(False)
+    ms = timed(lambda: st1.pack_gt(0, flat, n_samples, row_pitch=rowbytes), reps=3)
+    out["K1_pack_gt_host_api"] = {"ms": ms, "variants_per_s": nv1 / ms * 1e3, "text_GBps": nv1 * rowbytes / ms / 1e6,
+                                  "note": "pinned host text -> H2D -> pack kernel; PCIe-bound (the text is 16x the planes)"}
+    got = st1.download(0, 4)
+    want = np.packbits(bits[:4].reshape(4, -1), axis=1, bitorder="little")
+    assert (got.view(np.uint8)[:, : want.shape[1]] == want).all()
+    st1.close()
+    ctx.close()
+    print(json.dumps({"hbm_peak_GBps": peaks["hbm_gbs"], **out}, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -96,6 +96,14 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+// Programmatic dependent launch: the three kernels of a call (gather -> all-pairs -> deferred pairs) are
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization, so that a kernel's launch latency and
+// prologue overlap the tail of its predecessor.  pdl_wait() blocks until the predecessor grid has completed
+// and its writes are visible (a no-op without the attribute); pdl_launch_dependents() lets the successor
+// start being scheduled.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -166,6 +174,8 @@ gather_bits_kernel(const uint64_t *__restrict__ planes, const uint64_t *__restri
                    const int64_t *__restrict__ rows, int64_t v, int64_t v_pad, int32_t kc_count,
                    const VarFreq *__restrict__ freq, uint4 *__restrict__ bits, uint4 *__restrict__ bits_rev,
                    VarFreq *__restrict__ freq_rows) {
+    pdl_launch_dependents();                                            // the all-pairs kernel may start its prologue
+    pdl_wait();                                                         // the scratch is still read by the previous call's kernels
     const int kc = blockIdx.y;
     const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;          // matrix row
     if (r >= v_pad) return;
@@ -401,6 +411,8 @@ __global__ void __launch_bounds__(256)
 slow_pairs_kernel(const uint4 *__restrict__ list, uint32_t *__restrict__ counters /* d_fix_count */, uint32_t cap,
                   const VarFreq *__restrict__ freq_rows, FinalCtx fc, int measure, int has_thres, int thres_e4,
                   uint32_t *__restrict__ packed, int64_t out_off, FixupSink fix, volatile uint32_t *mailbox, uint32_t seq) {
+    pdl_launch_dependents();
+    pdl_wait();                                                 // everything below depends on the all-pairs kernel
     const uint32_t total = counters[2];
     const uint32_t n = total < cap ? total : cap;              // the rest was settled in the epilogue (flush_slow)
     const uint32_t m_shift = measure == LDX_MEASURE_R2 ? 0u : (uint32_t)LDX_DP_SHIFT;
@@ -462,6 +474,8 @@ triangle_mma_kernel(const MmaArgs A) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
+    pdl_launch_dependents();                                            // deferred-pairs kernel: launch latency hidden behind this grid
+    pdl_wait();                                                         // bit panels / frequencies / tile list come from the gather kernel
     if (TRACE && A.trace && blockIdx.x == 0 && threadIdx.x == 0) A.trace[0] = gtime();   // prologue done
 
     const int ks_count = kc_count / Cfg::CH;                  // pipeline stages per tile (kc_count is even)
@@ -737,7 +751,15 @@ static int launch_tiles_t(ldx_ctx *ctx, const MmaArgs &A) {
     }
     const int grid = A.n_tiles < ctx->sm_count ? A.n_tiles : ctx->sm_count;     // persistent: one CTA per SM
     timing_begin(ctx);
-    triangle_mma_kernel<N, WANT_N11, THRES, TRACE><<<grid, MMA_THREADS, MmaCfg<N>::SMEM, ctx->stream>>>(A);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(MMA_THREADS); cfg.dynamicSmemBytes = MmaCfg<N>::SMEM; cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        LDX_CUDA(cudaLaunchKernelEx(&cfg, triangle_mma_kernel<N, WANT_N11, THRES, TRACE>, A));
+    }
     timing_end(ctx);
     ctx->launches++;
     LDX_LAUNCHED(ctx, "triangle_mma_kernel");
@@ -813,8 +835,17 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t 
     }
 
     dim3 ggrid((unsigned)((v_pad + 255) / 256), (unsigned)kc_count);
-    gather_bits_kernel<<<ggrid, 256, 0, ctx->stream>>>(s->d_planes, s->d_mask, s->stride_words, d_rows, v, v_pad, kc_count,
-                                                       s->d_freq, d_bits, d_bits_rev, d_freq_rows);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = ggrid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        LDX_CUDA(cudaLaunchKernelEx(&cfg, gather_bits_kernel, (const uint64_t *)s->d_planes, (const uint64_t *)s->d_mask, (int32_t)s->stride_words,
+                                    (const int64_t *)d_rows, (int64_t)v, (int64_t)v_pad, (int32_t)kc_count, (const VarFreq *)s->d_freq, d_bits, d_bits_rev,
+                                    d_freq_rows));
+    }
     ctx->launches++;
     LDX_LAUNCHED(ctx, "gather_bits_kernel");
 
@@ -849,8 +880,17 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t 
     // ~1% of the pairs are deferred and each costs a long, serial fp64 chain: one pair per thread at twice that
     // rate (idle blocks are cheap, a thread looping over several pairs is not)
     const int sgrid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 8, std::max<uint64_t>(1, n_pairs / (50u * 256u) + 1));
-    slow_pairs_kernel<<<sgrid, 256, 0, ctx->stream>>>(d_slow, ctx->d_fix_count, A.slow_cap, d_freq_rows, s->fc, measure, has_thres,
-                                                      thres_e4, d_packed, A.out_off, A.fix, publish_seq ? ctx->d_mailbox : nullptr, publish_seq);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)sgrid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        LDX_CUDA(cudaLaunchKernelEx(&cfg, slow_pairs_kernel, (const uint4 *)d_slow, ctx->d_fix_count, A.slow_cap, (const VarFreq *)d_freq_rows, s->fc,
+                                    (int)measure, (int)has_thres, (int)thres_e4, d_packed, A.out_off, A.fix,
+                                    (volatile uint32_t *)(publish_seq ? ctx->d_mailbox : nullptr), publish_seq));
+    }
     ctx->launches++;
     LDX_LAUNCHED(ctx, "slow_pairs_kernel");
     return LDX_OK;

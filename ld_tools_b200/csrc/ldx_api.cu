@@ -98,6 +98,7 @@ extern "C" int32_t ldx_init(int32_t device, ldx_ctx **ctx_out) {
     if (e == cudaSuccess) { for (int i = 0; i < 4; ++i) ctx->h_mailbox[i] = 0; e = cudaHostGetDevicePointer((void **)&ctx->d_mailbox, (void *)ctx->h_mailbox, 0); }
     if (e != cudaSuccess) { ldx_destroy(ctx); return cuda_fail(e, "ldx_init"); }
     ctx->stream = ctx->own_stream;
+    if (const char *e = getenv("LDX_MMA_PAIR")) ctx->mma_pair = atoi(e) != 0;    // default of LDX_TUNE_MMA_PAIR
     *ctx_out = ctx;
     return LDX_OK;
 }
@@ -140,6 +141,10 @@ extern "C" int32_t ldx_set_tuning(ldx_ctx *ctx, int32_t key, int32_t value) {
         case LDX_TUNE_MMA_TILE_N:
             LDX_REQUIRE(value == 0 || value == 64 || value == 128, "tile width must be 0, 64 or 128");
             ctx->mma_tile_n = value;
+            return LDX_OK;
+        case LDX_TUNE_MMA_PAIR:
+            LDX_REQUIRE(value == 0 || value == 1, "pair mode must be 0 or 1");
+            ctx->mma_pair = value;
             return LDX_OK;
         case LDX_TUNE_MMA_MIN_V:
             LDX_REQUIRE(value >= 2, "minimum variant count must be >= 2");

@@ -62,6 +62,12 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
                  "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
 // Bounded wait: a pipeline bug must end in an error code, never in a hung GPU.  The common case
 // (phase already complete) is one try_wait; the slow path polls, optionally sleeping between
 // polls so that long waits (the epilogue waiting out a whole K loop) do not steal issue slots
@@ -80,7 +86,21 @@ __device__ __forceinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, vo
         }
     }
 }
+template <bool CLUSTER = false>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int *abort_s, int32_t *err, uint32_t sleep_ns = 0) {
+    if (CLUSTER) {      // the barrier also takes arrives from the peer CTA of a pair: acquire at cluster scope
+        unsigned long long t0 = 0;
+        for (uint32_t spins = 1;; ++spins) {
+            if (mbar_try_wait_cluster(bar, parity)) return true;
+            if ((spins & 0x3f) == 0) {
+                if (*abort_s) return false;
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+                if (!t0) t0 = t;
+                else if (t - t0 > 2000000000ull) { *abort_s = 1; atomicExch(err, 1); return false; }
+            }
+        }
+    }
     if (mbar_try_wait(bar, parity)) return true;
     return mbar_wait_slow(bar, parity, abort_s, err, sleep_ns);
 }
@@ -103,6 +123,32 @@ __device__ __forceinline__ bool elect_one() {
 // start being scheduled.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster share one 256 x N tile; rank 0 issues the MMAs
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> the same variable in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma_i8_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -263,12 +309,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-struct ColRec;
-template <bool THRES>
-__device__ __forceinline__ uint32_t fast_pair(int32_t n11, int32_t Nn, int32_t n1a, int32_t aN, int32_t cN, float fa,
-                                              const ColRec &cr, float lim_dp, float lim_r2, uint32_t m_shift, uint32_t thres,
-                                              bool &slow);
-
 // ------------------------------------------------------------------------------------------ GEMM + epilogue
 struct MmaArgs {
     const uint4 *bits, *bits_rev; int32_t kc_count;
@@ -277,7 +317,7 @@ struct MmaArgs {
     int64_t v; int measure, has_thres, thres_e4;
     int64_t out_off;             // packed index of the first pair of the call's row range: outputs are relative to it
     int32_t n_sel;               // N = selected haplotypes
-    float lim_dp, lim_r2;        // 0.5 - guard band of the screening arithmetic at x = 0 (see fast_pair)
+    float lim_dp, lim_r2;        // 0.5 - guard band of the screening arithmetic at x = 0 (see fast_pair2)
     uint4 *slow; uint32_t *slow_count; uint32_t slow_cap;   // deferred pairs {row, col, n11, -} for slow_pairs_kernel
     uint32_t *packed; int32_t *n11;
     FixupSink fix;
@@ -303,7 +343,7 @@ constexpr int FIRST_WIDEN_WARP = 4, FIRST_EPI_WARP = FIRST_WIDEN_WARP + N_WIDEN_
 constexpr int MMA_THREADS = 32 * (FIRST_EPI_WARP + N_EPI_WARPS);   // 896
 static_assert(MMA_THREADS * REGS_LAUNCH <= 65536, "register file");
 constexpr int SLOW_BUF = 64;                                           // deferred pairs buffered per epilogue warp
-constexpr int EPI_PITCH = 20;                                          // words per staged row: 16-byte aligned rows, conflict-free STS.128
+constexpr int EPI_PITCH = 16;                                          // words per parked row (rare path: bank conflicts do not matter)
 
 // Per column variant, what the screening arithmetic of the epilogue needs (one 16-byte broadcast load per pair).
 struct __align__(16) ColRec {
@@ -313,13 +353,17 @@ struct __align__(16) ColRec {
     int32_t pad;
 };
 
-template <int N> struct MmaCfg {
-    static constexpr int ROWS = MMA_M + N;                    // variant-rows widened per chunk
+// PAIR: two CTAs of a cluster work on one 256 x N tile with tcgen05.mma.cta_group::2; each widens its own 128
+// row variants (TMEM) and HALF of the column variants (N/2 rows of the shared-memory operand, which the
+// hardware reads from both CTAs): 128 + N/2 instead of 128 + N variant-rows per 128 x N results.
+template <int N, bool PAIR = false> struct MmaCfg {
+    static constexpr int NB = PAIR ? N / 2 : N;               // column variants widened by this CTA
+    static constexpr int ROWS = MMA_M + NB;                   // variant-rows widened per chunk
     static constexpr int CH = 2;                              // 128-haplotype chunks per pipeline stage
-    static constexpr int B_ROWS = N < 128 ? N : 128;          // column variants per 128-row bit block
-    static constexpr int B_PARTS = (N + 127) / 128;
+    static constexpr int B_ROWS = NB < 128 ? NB : 128;        // column variants per 128-row bit block
+    static constexpr int B_PARTS = (NB + 127) / 128;
     static constexpr int OP_STAGES = WIDEN_TEAMS;             // widened operand stages (A in TMEM, B in smem): one per team
-    static constexpr int OP_BYTES = N * KCHUNK * CH;          // B tile of one stage: CH swizzle atoms side by side
+    static constexpr int OP_BYTES = NB * KCHUNK * CH;         // B tile of one stage: CH swizzle atoms side by side
     static constexpr int BIT_STAGES = N <= 128 ? 8 : 4;       // bit blocks in flight from L2 (latency: deep)
     static constexpr int BIT_BYTES = ROWS * 16 * CH;
     static constexpr int A_COLS = CH * KCHUNK / 4;            // TMEM columns of one A stage (64)
@@ -330,41 +374,62 @@ template <int N> struct MmaCfg {
     static constexpr int N_BARS = 2 * OP_STAGES + 2 * BIT_STAGES + 4;
     static constexpr int EPI_BYTES = N_EPI_WARPS * (32 * EPI_PITCH * 4 + SLOW_BUF * 16);   // staging + deferred-pair buffer per warp
     static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)OP_STAGES * OP_BYTES + (size_t)BIT_STAGES * BIT_BYTES +
-                                   2 * N * sizeof(ColRec) + EPI_BYTES + N_BARS * 8 + 64;
+                                   N_EPI_WARPS * (N / 2) * sizeof(ColRec) + EPI_BYTES + N_BARS * 8 + 64;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    static_assert(!PAIR || (N == 128 && CH == 2), "the pair kernel splits the column widening as 64 rows x 2 chunks");
 };
 
+// ---- two pairs at a time with the packed single-precision instructions of sm_100 (FMUL2 / FADD2 / FFMA2:
+// one issue slot for two results; IEEE round-to-nearest per half, so the error analysis above is unchanged).
+// The epilogue is bound by instruction issue, which it shares with the wideners.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// Pairs (row, column j) and (row, column j + 1): the screening arithmetic described above.  The bound m carries the
+// sign of Dn (m = -min(n1a*n1b, n0a*n0b) for Dn <= 0), so that Dn / m is |D'| without an absolute value --
+// the packed instructions have no operand modifiers.
 template <bool THRES>
-__device__ __forceinline__ uint32_t fast_pair(int32_t n11, int32_t Nn, int32_t n1a, int32_t aN, int32_t cN, float fa,
-                                              const ColRec &cr, float lim_dp, float lim_r2, uint32_t m_shift, uint32_t thres,
-                                              bool &slow) {
-    const int32_t P = n1a * cr.n1;                       // n1a*n1b
-    const int32_t Dn = n11 * Nn - P;
-    const int32_t m_pos = min(aN, cr.n1N) - P;           // min(n1a*n0b, n0a*n1b)
-    const int32_t m_neg = P + min(0, cN - cr.n1N);       // min(n1a*n1b, n0a*n0b)
-    const int32_t m = Dn > 0 ? m_pos : m_neg;
-    const float fD = fabsf(__int2float_rn(Dn));          // |.| is an operand modifier: free
-    const float fm = __int2float_rn(m);                  // exact
-    const float den = __fmul_rn(fa, cr.prod);
-    const float R1 = rcp_approx(fm), R2 = rcp_approx(den);     // inf when monomorphic: masked below
-    const float D4 = __fmul_rn(fD, 1.0e4f);
-    const float x_dp = __fmul_rn(D4, R1);
-    const float x_r2 = __fmul_rn(__fmul_rn(D4, fD), R2);
-    const float t_dp = __fadd_rn(x_dp, ROUND_MAGIC), t_r2 = __fadd_rn(x_r2, ROUND_MAGIC);
-    const float f_dp = __fsub_rn(x_dp, __fsub_rn(t_dp, ROUND_MAGIC));    // exact: x - nearest integer
-    const float f_r2 = __fsub_rn(x_r2, __fsub_rn(t_r2, ROUND_MAGIC));
-    const float l_dp = __fmaf_rn(-SCREEN_C_DP, x_dp, lim_dp);            // guard band grows with x
-    const float l_r2 = __fmaf_rn(-SCREEN_C_R2, x_r2, lim_r2);
-    const bool mono = den == 0.0f;                       // den is a product of exact integers: 0 or >= 1
+__device__ __forceinline__ void fast_pair2(uint32_t acc0, uint32_t acc1, int32_t Nn, int32_t n1a, int32_t aN, int32_t cN, float fa,
+                                           const ColRec &c0, const ColRec &c1, float lim_dp, float lim_r2, uint32_t m_shift,
+                                           uint32_t thres, uint32_t &w0, uint32_t &w1, bool &slow0, bool &slow1) {
+    const int32_t P0 = n1a * c0.n1, P1 = n1a * c1.n1;
+    const int32_t Dn0 = (int32_t)(acc0 >> ACC_SHIFT) * Nn - P0, Dn1 = (int32_t)(acc1 >> ACC_SHIFT) * Nn - P1;
+    const int32_t mp0 = min(aN, c0.n1N) - P0, mp1 = min(aN, c1.n1N) - P1;            //  min(n1a*n0b, n0a*n1b)
+    const int32_t mn0 = max(0, c0.n1N - cN) - P0, mn1 = max(0, c1.n1N - cN) - P1;    // -min(n1a*n1b, n0a*n0b)
+    const int32_t m0 = Dn0 > 0 ? mp0 : mn0, m1 = Dn1 > 0 ? mp1 : mn1;
+    const uint64_t fD = pk2(__int2float_rn(Dn0), __int2float_rn(Dn1));
+    const uint64_t den = mul2(pk2(fa, fa), pk2(c0.prod, c1.prod));
+    float den0, den1;
+    upk2(den, den0, den1);
+    const uint64_t R1 = pk2(rcp_approx(__int2float_rn(m0)), rcp_approx(__int2float_rn(m1)));    // m is exact in fp32
+    const uint64_t R2 = pk2(rcp_approx(den0), rcp_approx(den1));                                  // inf when monomorphic: masked below
+    const uint64_t D4 = mul2(fD, pk2(1.0e4f, 1.0e4f));
+    const uint64_t x_dp = mul2(D4, R1);
+    const uint64_t x_r2 = mul2(mul2(D4, fD), R2);
+    const uint64_t magic = pk2(ROUND_MAGIC, ROUND_MAGIC), nmagic = pk2(-ROUND_MAGIC, -ROUND_MAGIC), neg1 = pk2(-1.0f, -1.0f);
+    const uint64_t t_dp = add2(x_dp, magic), t_r2 = add2(x_r2, magic);
+    const uint64_t f_dp = fma2(add2(t_dp, nmagic), neg1, x_dp);          // exact: x - nearest integer
+    const uint64_t f_r2 = fma2(add2(t_r2, nmagic), neg1, x_r2);
+    const uint64_t l_dp = fma2(x_dp, pk2(-SCREEN_C_DP, -SCREEN_C_DP), pk2(lim_dp, lim_dp));   // guard band grows with x
+    const uint64_t l_r2 = fma2(x_r2, pk2(-SCREEN_C_R2, -SCREEN_C_R2), pk2(lim_r2, lim_r2));
+    float td0, td1, tr0, tr1, fd0, fd1, fr0, fr1, ld0, ld1, lr0, lr1;
+    upk2(t_dp, td0, td1); upk2(t_r2, tr0, tr1); upk2(f_dp, fd0, fd1); upk2(f_r2, fr0, fr1); upk2(l_dp, ld0, ld1); upk2(l_r2, lr0, lr1);
+    const bool mono0 = den0 == 0.0f, mono1 = den1 == 0.0f;
     // !(<=) rather than (>): a NaN from an unforeseen input must fall to the exact path, never pass
-    // (bitwise, not short-circuit: the sixteen pairs of a chunk must stay one straight-line block)
-    slow = (bool)((uint32_t)!mono & ((uint32_t)!(fabsf(f_dp) <= l_dp) | (uint32_t)!(fabsf(f_r2) <= l_r2) | (uint32_t)(Dn == 0)));
-    // t = MAGIC + n has the bit pattern 0x4B400000 + n (n < 2^14), and 0x4B400000 << 16 vanishes mod 2^32:
-    // one multiply-add packs both fields (a valid n leaves bits 14, 15, 30, 31 clear by itself)
-    uint32_t w = (uint32_t)__float_as_int(t_dp) * 65536u + ((uint32_t)__float_as_int(t_r2) - 0x4B400000u);
-    w = mono ? (LDX_DP_INT0 | LDX_R2_INT0) : w;
-    if (THRES) w |= (((w >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;   // no branch
-    return w;
+    slow0 = (bool)((uint32_t)!mono0 & ((uint32_t)!(fabsf(fd0) <= ld0) | (uint32_t)!(fabsf(fr0) <= lr0) | (uint32_t)(Dn0 == 0)));
+    slow1 = (bool)((uint32_t)!mono1 & ((uint32_t)!(fabsf(fd1) <= ld1) | (uint32_t)!(fabsf(fr1) <= lr1) | (uint32_t)(Dn1 == 0)));
+    uint32_t a = (uint32_t)__float_as_int(td0) * 65536u + ((uint32_t)__float_as_int(tr0) - 0x4B400000u);
+    uint32_t b = (uint32_t)__float_as_int(td1) * 65536u + ((uint32_t)__float_as_int(tr1) - 0x4B400000u);
+    a = mono0 ? (LDX_DP_INT0 | LDX_R2_INT0) : a;
+    b = mono1 ? (LDX_DP_INT0 | LDX_R2_INT0) : b;
+    if (THRES) {
+        a |= (((a >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;
+        b |= (((b >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;
+    }
+    w0 = a; w1 = b;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -437,17 +502,21 @@ slow_pairs_kernel(const uint4 *__restrict__ list, uint32_t *__restrict__ counter
     }
 }
 
-template <int N, bool WANT_N11, bool THRES, bool TRACE>
+template <int N, bool WANT_N11, bool THRES, bool TRACE, bool PAIR>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 triangle_mma_kernel(const MmaArgs A) {
-    using Cfg = MmaCfg<N>;
+    using Cfg = MmaCfg<N, PAIR>;
+    // work units: a CTA (tile = 128 x N), or a CTA pair (tile = 256 x N, this CTA owns rows 128 * rank ...)
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t *smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);      // swizzle-128B needs 1 KB alignment
     uint8_t *op_s = smem;                                                        // [OP_STAGES][N][128 B] column operand
     uint8_t *bit_s = smem + Cfg::OP_STAGES * Cfg::OP_BYTES;                      // [BIT_STAGES][ROWS][16 B]
-    ColRec *col_s = reinterpret_cast<ColRec *>(bit_s + Cfg::BIT_STAGES * Cfg::BIT_BYTES);   // [2][N]
-    uint32_t *epi_s = reinterpret_cast<uint32_t *>(col_s + 2 * N);               // [N_EPI_WARPS][32][EPI_PITCH]
+    ColRec *col_s = reinterpret_cast<ColRec *>(bit_s + Cfg::BIT_STAGES * Cfg::BIT_BYTES);   // [N_EPI_WARPS][N / 2]: private to each epilogue warp
+    uint32_t *epi_s = reinterpret_cast<uint32_t *>(col_s + N_EPI_WARPS * (N / 2));  // [N_EPI_WARPS][32][EPI_PITCH]
     uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(epi_s) + Cfg::EPI_BYTES);
     const uint32_t op_full = smem_u32(bars), op_empty = op_full + 8 * Cfg::OP_STAGES;
     const uint32_t bit_full = op_empty + 8 * Cfg::OP_STAGES, bit_empty = bit_full + 8 * Cfg::BIT_STAGES;
@@ -459,19 +528,27 @@ triangle_mma_kernel(const MmaArgs A) {
     const int kc_count = A.kc_count;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::OP_STAGES; ++s) { mbar_init(op_full + 8 * s, TEAM_WARPS); mbar_init(op_empty + 8 * s, 1); }
+        // pair: the leader's op_full / tmem_empty also count the peer's wideners / epilogue warps (remote arrives)
+        for (int s = 0; s < Cfg::OP_STAGES; ++s) { mbar_init(op_full + 8 * s, (PAIR ? 2 : 1) * TEAM_WARPS); mbar_init(op_empty + 8 * s, 1); }
         for (int s = 0; s < Cfg::BIT_STAGES; ++s) { mbar_init(bit_full + 8 * s, 1); mbar_init(bit_empty + 8 * s, TEAM_WARPS); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + 8 * s, 1); mbar_init(tmem_empty + 8 * s, N_EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + 8 * s, 1); mbar_init(tmem_empty + 8 * s, (PAIR ? 2 : 1) * N_EPI_WARPS); }
         *abort_s = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // one warp allocates TMEM (power-of-two columns >= 32) and later frees it
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(tmem_ptr_s)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(tmem_ptr_s)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(tmem_ptr_s)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();      // the peer's barriers are initialised before anyone arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
     pdl_launch_dependents();                                            // deferred-pairs kernel: launch latency hidden behind this grid
@@ -485,10 +562,10 @@ triangle_mma_kernel(const MmaArgs A) {
         // The whole warp runs the loop; one elected lane issues the copies.
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         uint32_t g = 0;
-        for (int t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
+        for (int t = unit; t < A.n_tiles; t += n_units) {
             const int2 tile = A.tiles[t];
-            const int64_t c0 = (int64_t)tile.y * N;
-            const uint4 *a_src = A.bits + (int64_t)tile.x * kc_count * 128;
+            const int64_t c0 = (int64_t)tile.y * N + (PAIR ? rank * Cfg::NB : 0);      // pair: this CTA's half of the columns
+            const uint4 *a_src = A.bits + (int64_t)(PAIR ? tile.x * 2 + rank : tile.x) * kc_count * 128;
             for (int ks = 0; ks < ks_count; ++ks, ++g) {
                 const uint32_t s = g % Cfg::BIT_STAGES, it = g / Cfg::BIT_STAGES;
                 if (!mbar_wait(bit_empty + 8 * s, (it & 1) ^ 1, abort_s, A.error_flag)) goto done;
@@ -518,16 +595,17 @@ triangle_mma_kernel(const MmaArgs A) {
     } else if (warp == 1) {
         // ===== MMA issuer: warp-uniform loop, one elected lane issues
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        constexpr uint32_t idesc = make_idesc(MMA_M, N);
+        constexpr uint32_t idesc = make_idesc(PAIR ? 2 * MMA_M : MMA_M, N);
         uint32_t g = 0, tl = 0;
-        for (int t = blockIdx.x; t < A.n_tiles; t += gridDim.x, ++tl) {
+        if (PAIR && rank != 0) goto done;      // only the leader of a pair issues (and waits for both CTAs' operands)
+        for (int t = unit; t < A.n_tiles; t += n_units, ++tl) {
             const uint32_t buf = tl % Cfg::ACC_BUFS;
-            if (!mbar_wait(tmem_empty + 8 * buf, ((tl / Cfg::ACC_BUFS) & 1) ^ 1, abort_s, A.error_flag)) goto done;   // epilogue drained it
+            if (!mbar_wait<PAIR>(tmem_empty + 8 * buf, ((tl / Cfg::ACC_BUFS) & 1) ^ 1, abort_s, A.error_flag)) goto done;   // epilogue(s) drained it
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + buf * N;
             for (int ks = 0; ks < ks_count; ++ks, ++g) {
                 const uint32_t s = g % Cfg::OP_STAGES, it = g / Cfg::OP_STAGES;
-                if (!mbar_wait(op_full + 8 * s, it & 1, abort_s, A.error_flag)) goto done;
+                if (!mbar_wait<PAIR>(op_full + 8 * s, it & 1, abort_s, A.error_flag)) goto done;
                 tc_fence_after();
                 const uint64_t db = make_smem_desc(smem_u32(op_s + s * Cfg::OP_BYTES));
                 const uint32_t ta = tmem_base + Cfg::TMEM_A0 + s * Cfg::A_COLS;
@@ -535,10 +613,18 @@ triangle_mma_kernel(const MmaArgs A) {
                     if (TRACE && A.trace && blockIdx.x == 0 && g < 48) A.trace[64 + g] = gtime();
                     if (!(TRACE && (A.dbg & 8)))
 #pragma unroll
-                    for (int k = 0; k < Cfg::CH * KCHUNK / MMA_K; ++k)     // K = 32: 8 TMEM columns of A; B: atom k/4 (N*128 B apart), +32 B per step inside
-                        umma_i8_ts(tmem_acc, ta + 8 * k, db + (uint64_t)((k >> 2) * (N * KCHUNK >> 4) + (k & 3) * 2), idesc, (uint32_t)((ks | k) != 0));
-                    umma_commit(op_empty + 8 * s);                // stage reusable once these MMAs have read it
-                    if (ks == ks_count - 1) umma_commit(tmem_full + 8 * buf);   // accumulator complete
+                    for (int k = 0; k < Cfg::CH * KCHUNK / MMA_K; ++k) {   // K = 32: 8 TMEM columns of A; B: atom k/4 (NB*128 B apart), +32 B per step inside
+                        const uint64_t dbk = db + (uint64_t)((k >> 2) * (Cfg::NB * KCHUNK >> 4) + (k & 3) * 2);
+                        if (PAIR) umma_i8_ts_pair(tmem_acc, ta + 8 * k, dbk, idesc, (uint32_t)((ks | k) != 0));
+                        else umma_i8_ts(tmem_acc, ta + 8 * k, dbk, idesc, (uint32_t)((ks | k) != 0));
+                    }
+                    if (PAIR) {
+                        umma_commit_pair(op_empty + 8 * s);       // both CTAs' wideners get their stage back
+                        if (ks == ks_count - 1) umma_commit_pair(tmem_full + 8 * buf);
+                    } else {
+                        umma_commit(op_empty + 8 * s);            // stage reusable once these MMAs have read it
+                        if (ks == ks_count - 1) umma_commit(tmem_full + 8 * buf);   // accumulator complete
+                    }
                 }
                 __syncwarp();
             }
@@ -557,7 +643,8 @@ triangle_mma_kernel(const MmaArgs A) {
         const uint32_t tmem_lane = (uint32_t)(((warp - FIRST_WIDEN_WARP) & 3) * 32) << 16;
         // the wideners do not care which tile a stage belongs to: team k takes stages g = k, k + TEAMS, ...
         // of this CTA's stream, bit stage g % BIT_STAGES -> operand stage g % OP_STAGES (= its own: k)
-        const uint32_t my_tiles = (uint32_t)(A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / gridDim.x;
+        const uint32_t my_tiles = (uint32_t)(A.n_tiles - unit + n_units - 1) / (uint32_t)n_units;
+        const uint32_t op_full_leader = PAIR ? mapa_u32(op_full, 0) : 0u;     // pair: everybody reports to rank 0's barrier
         const uint32_t g_end = my_tiles * (uint32_t)ks_count;
         static_assert(Cfg::OP_STAGES == WIDEN_TEAMS, "one operand stage per team");
         {
@@ -585,6 +672,12 @@ triangle_mma_kernel(const MmaArgs A) {
                     tmem_st32(tmem_base + Cfg::TMEM_A0 + so * Cfg::A_COLS + c * (KCHUNK / 4) + tmem_lane, v);
                 }
                 uint8_t *ops = op_s + so * Cfg::OP_BYTES;
+                if (PAIR) {
+                    // 64 column variants x 2 chunks over the team's 128 threads: one row-chunk each
+                    const int brow = wt & 63, c = wt >> 6;
+                    if (!(TRACE && (A.dbg & 2)))
+                        expand_row<true>(ops + c * (Cfg::NB * KCHUNK) + brow * KCHUNK, brow & 7, bsrc[Cfg::CH * MMA_M + c * Cfg::B_ROWS + brow]);
+                } else
                 if (wt < Cfg::B_ROWS && !(TRACE && (A.dbg & 2))) {
 #pragma unroll
                     for (int c = 0; c < Cfg::CH; ++c)
@@ -598,7 +691,10 @@ triangle_mma_kernel(const MmaArgs A) {
                 tc_fence_before();
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(op_full + 8 * so); mbar_arrive(bit_empty + 8 * sb); }
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_remote(op_full_leader + 8 * so); else mbar_arrive(op_full + 8 * so);
+                    mbar_arrive(bit_empty + 8 * sb);
+                }
                 if (TRACE && A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[8 + g] = gtime();
             }
         }
@@ -612,7 +708,6 @@ triangle_mma_kernel(const MmaArgs A) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         const int ew = warp - FIRST_EPI_WARP;                     // 0..7
         const int quad = warp & 3, half = ew >> 2;
-        const int et = ew * 32 + lane;                            // 0..255
         const int lq = lane >> 2, lr = lane & 3;
         uint32_t *stage = epi_s + ew * (32 * EPI_PITCH + SLOW_BUF * 4);
         uint4 *sbuf = reinterpret_cast<uint4 *>(stage + 32 * EPI_PITCH);
@@ -623,17 +718,21 @@ triangle_mma_kernel(const MmaArgs A) {
         const int32_t Nn = A.n_sel;
         const float lim_dp = A.lim_dp, lim_r2 = A.lim_r2;
         uint32_t tl = 0;
-        for (int t = blockIdx.x; t < A.n_tiles; t += gridDim.x, ++tl) {
+        const uint32_t tmem_empty_leader = PAIR ? mapa_u32(tmem_empty, 0) : 0u;
+        for (int t = unit; t < A.n_tiles; t += n_units, ++tl) {
             const uint32_t buf = tl % Cfg::ACC_BUFS;
             const int2 tile = A.tiles[t];
-            const int64_t r0 = (int64_t)tile.x * MMA_M, c0 = (int64_t)tile.y * N;
-            ColRec *cols = col_s + (tl & 1) * N;
-            for (int i = et; i < N; i += 32 * N_EPI_WARPS) {      // column variants of this tile
+            const int64_t r0 = (int64_t)(PAIR ? tile.x * 2 + rank : tile.x) * MMA_M, c0 = (int64_t)tile.y * N;
+            // the column variants this warp works on (its half of the tile's columns): a private copy per warp costs
+            // a few redundant loads and saves a barrier across the eight epilogue warps on every tile
+            ColRec *cols = col_s + ew * (N / 2) - half * (N / 2);         // indexed by the column's offset in the tile
+            __syncwarp();                                                 // the previous tile's readers are done
+            for (int i = half * (N / 2) + lane; i < (half + 1) * (N / 2); i += 32) {
                 const int32_t n1 = A.freq_rows[c0 + i].n1;
                 ColRec cr; cr.n1 = n1; cr.n1N = n1 * Nn; cr.prod = __int2float_rn(n1 * (Nn - n1)); cr.pad = 0;
                 cols[i] = cr;
             }
-            asm volatile("bar.sync 1, %0;" :: "n"(32 * N_EPI_WARPS) : "memory");
+            __syncwarp();
             if (!mbar_wait(tmem_full + 8 * buf, (tl / Cfg::ACC_BUFS) & 1, abort_s, A.error_flag, 128)) goto done;
             tc_fence_after();
             if (TRACE && A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[1 + 2 * tl] = gtime();   // accumulator ready
@@ -661,13 +760,13 @@ triangle_mma_kernel(const MmaArgs A) {
                     uint32_t word[16];
                     uint32_t slow = 0;                            // bit i: pair i must be redone exactly
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int k = i >> 2, g = (i >> 1) & 1, e = i & 1;
-                        const ColRec cr = cols[cb + 8 * k + 2 * lr + e];
-                        bool s;
-                        word[i] = fast_pair<THRES>((int32_t)(acc[i] >> ACC_SHIFT), Nn, g ? n1b : n1a, g ? aNb : aNa, g ? cNb : cNa,
-                                                   g ? fab : faa, cr, lim_dp, lim_r2, m_shift, thres, s);
-                        slow |= (uint32_t)s << i;
+                    for (int i = 0; i < 16; i += 2) {                 // registers i, i + 1: same row, adjacent columns
+                        const int k = i >> 2, g = (i >> 1) & 1;
+                        const ColRec cr0 = cols[cb + 8 * k + 2 * lr], cr1 = cols[cb + 8 * k + 2 * lr + 1];
+                        bool s0, s1;
+                        fast_pair2<THRES>(acc[i], acc[i + 1], Nn, g ? n1b : n1a, g ? aNb : aNa, g ? cNb : cNa, g ? fab : faa, cr0, cr1,
+                                          lim_dp, lim_r2, m_shift, thres, word[i], word[i + 1], s0, s1);
+                        slow |= ((uint32_t)s0 << i) | ((uint32_t)s1 << (i + 1));
                     }
                     const bool interior = cg0 + 32 <= rmin && rmin + 15 < A.v;   // warp-uniform: every pair is below the diagonal
                     if (interior) {
@@ -698,10 +797,12 @@ triangle_mma_kernel(const MmaArgs A) {
                     // words.  The queue is per warp in shared memory (ballot compaction, no atomics) and is
                     // flushed to the global list when it fills up and at the end.
                     if (__any_sync(0xffffffffu, slow != 0)) {
-                        // park the counts in shared memory: a lane then fetches its flagged ones by index
+                        // a lane with flagged pairs parks its counts in shared memory and fetches them by index
+                        if (slow) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<uint4 *>(stage + lane * EPI_PITCH + i) = make_uint4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                            for (int i = 0; i < 16; i += 4)
+                                *reinterpret_cast<uint4 *>(stage + lane * EPI_PITCH + i) = make_uint4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                        }
                         __syncwarp();
                         while (true) {
                             const uint32_t bal = __ballot_sync(0xffffffffu, slow != 0);
@@ -723,7 +824,7 @@ triangle_mma_kernel(const MmaArgs A) {
             // this warp's TMEM reads of the tile are complete: hand the accumulator back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + 8 * buf);
+            if (lane == 0) { if (PAIR) mbar_arrive_remote(tmem_empty_leader + 8 * buf); else mbar_arrive(tmem_empty + 8 * buf); }
             if (TRACE && A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[2 + 2 * tl] = gtime();       // epilogue of this tile done
         }
         flush_slow(A, sbuf, slow_cnt, lane, m_shift, thres);
@@ -731,52 +832,58 @@ triangle_mma_kernel(const MmaArgs A) {
 done:
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();      // the peer may still read this CTA's operands / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
     }
 }
 
 bool triangle_mma_available() { return true; }
-// The screening arithmetic's guard band grows with N^2 (see fast_pair): up to this many selected
+// The screening arithmetic's guard band grows with N^2 (see fast_pair2): up to this many selected
 // haplotypes fewer than 1% of the pairs are deferred; beyond it ENGINE_AUTO uses the popcount engine.
 int triangle_mma_max_haplotypes() { return 8192; }
 
-template <int N, bool WANT_N11, bool THRES, bool TRACE = false>
+template <int N, bool WANT_N11, bool THRES, bool TRACE, bool PAIR>
 static int launch_tiles_t(ldx_ctx *ctx, const MmaArgs &A) {
     static bool attr_set = false;
     if (!attr_set) {
-        LDX_CUDA(cudaFuncSetAttribute(triangle_mma_kernel<N, WANT_N11, THRES, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmaCfg<N>::SMEM));
+        LDX_CUDA(cudaFuncSetAttribute(triangle_mma_kernel<N, WANT_N11, THRES, TRACE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)MmaCfg<N, PAIR>::SMEM));
         attr_set = true;
     }
-    const int grid = A.n_tiles < ctx->sm_count ? A.n_tiles : ctx->sm_count;     // persistent: one CTA per SM
+    // persistent: one CTA per SM; a pair kernel runs sm_count / 2 clusters of two
+    const int units = PAIR ? ctx->sm_count / 2 : ctx->sm_count;
+    const int grid = (A.n_tiles < units ? A.n_tiles : units) * (PAIR ? 2 : 1);
     timing_begin(ctx);
     {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(MMA_THREADS); cfg.dynamicSmemBytes = MmaCfg<N>::SMEM; cfg.stream = ctx->stream;
-        cudaLaunchAttribute attr[1];
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(MMA_THREADS); cfg.dynamicSmemBytes = MmaCfg<N, PAIR>::SMEM; cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        LDX_CUDA(cudaLaunchKernelEx(&cfg, triangle_mma_kernel<N, WANT_N11, THRES, TRACE>, A));
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = PAIR ? 2 : 1;
+        LDX_CUDA(cudaLaunchKernelEx(&cfg, triangle_mma_kernel<N, WANT_N11, THRES, TRACE, PAIR>, A));
     }
     timing_end(ctx);
     ctx->launches++;
     LDX_LAUNCHED(ctx, "triangle_mma_kernel");
     return LDX_OK;
 }
-template <int N>
+template <int N, bool PAIR>
 static int launch_tiles(ldx_ctx *ctx, const MmaArgs &A) {
-    if (A.trace && !A.has_thres && !A.n11) return launch_tiles_t<N, false, false, true>(ctx, A);   // diagnostics build of the kernel
-    if (A.has_thres) return A.n11 ? launch_tiles_t<N, true, true>(ctx, A) : launch_tiles_t<N, false, true>(ctx, A);
-    return A.n11 ? launch_tiles_t<N, true, false>(ctx, A) : launch_tiles_t<N, false, false>(ctx, A);
+    if (A.trace && !A.has_thres && !A.n11) return launch_tiles_t<N, false, false, true, PAIR>(ctx, A);   // diagnostics build of the kernel
+    if (A.has_thres) return A.n11 ? launch_tiles_t<N, true, true, false, PAIR>(ctx, A) : launch_tiles_t<N, false, true, false, PAIR>(ctx, A);
+    return A.n11 ? launch_tiles_t<N, true, false, false, PAIR>(ctx, A) : launch_tiles_t<N, false, false, false, PAIR>(ctx, A);
 }
 
 int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t row_begin, int measure, int has_thres,
                         int thres_e4, uint32_t *d_packed, int32_t *d_n11, uint32_t publish_seq) {
     if (v < 2) return LDX_OK;
     if (row_begin % MMA_M) return set_error(LDX_ERR_ARG, "tcgen05 engine: row_begin must be a multiple of 128");
-    const int64_t panel_begin = row_begin / MMA_M;
     ldx_ctx *ctx = s->ctx;
     if (s->n_sel > triangle_mma_max_haplotypes())
         return set_error(LDX_ERR_ARG, "tcgen05 engine: more than 8192 selected haplotypes (use LDX_ENGINE_POPC or LDX_ENGINE_AUTO)");
@@ -791,12 +898,15 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t 
     // tiles amortise the widening work for large ones
     int n_tile = ctx->mma_tile_n;
     if (n_tile == 0) n_tile = v <= 1024 ? 64 : 128;
+    // CTA pairs (256 x 128 tiles, cta_group::2): a quarter less widening work per result
+    const bool pair = ctx->mma_pair && n_tile == 128 && row_begin % (2 * MMA_M) == 0 && ctx->sm_count % 2 == 0;
+    const int64_t ph = pair ? 2 * MMA_M : MMA_M;             // tile height
     // ---- tile list (cached): every 128 x N tile holding at least one pair with row > col, row-panel major
     const size_t bits_bytes = (size_t)panels * kc_count * 128 * sizeof(uint4);
     const size_t freq_bytes = (size_t)v_pad * sizeof(VarFreq);
     size_t n_tiles = 0;
-    for (int64_t bi = panel_begin; bi < (v + MMA_M - 1) / MMA_M; ++bi) {
-        const int64_t rmax = std::min<int64_t>(bi * MMA_M + MMA_M - 1, v - 1);
+    for (int64_t bi = row_begin / ph; bi < (v + ph - 1) / ph; ++bi) {
+        const int64_t rmax = std::min<int64_t>(bi * ph + ph - 1, v - 1);
         n_tiles += (size_t)((rmax + n_tile - 1) / n_tile);
     }
     if (n_tiles == 0) return LDX_OK;
@@ -819,19 +929,20 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t 
     VarFreq *d_freq_rows = reinterpret_cast<VarFreq *>(base + 2 * bits_bytes);
     int2 *d_tiles = reinterpret_cast<int2 *>(base + 2 * bits_bytes + freq_bytes);
     uint4 *d_slow = reinterpret_cast<uint4 *>(base + 2 * bits_bytes + freq_bytes + tile_bytes);
-    if (ctx->mma_tiles_v != v || ctx->mma_tiles_n != n_tile || ctx->mma_tiles_begin != row_begin || ctx->mma_tiles_ptr != d_tiles) {
+    if (ctx->mma_tiles_v != v || ctx->mma_tiles_n != n_tile || ctx->mma_tiles_begin != row_begin || ctx->mma_tiles_ptr != d_tiles ||
+        ctx->mma_tiles_pair != pair) {
         // the list depends on (v, row_begin, N) only; its PLACE in the scratch block also on the haplotype count
         // Longest tiles first is not needed (all tiles cost the same K loop); the list is ordered so
         // that the tiles a wave of CTAs works on share row panels and neighbouring column blocks in L2.
         std::vector<int2> tiles;
         tiles.reserve(n_tiles);
-        for (int64_t bi = panel_begin; bi < (v + MMA_M - 1) / MMA_M; ++bi) {
-            const int64_t rmax = std::min<int64_t>(bi * MMA_M + MMA_M - 1, v - 1);
+        for (int64_t bi = row_begin / ph; bi < (v + ph - 1) / ph; ++bi) {
+            const int64_t rmax = std::min<int64_t>(bi * ph + ph - 1, v - 1);
             for (int64_t bj = 0; bj * n_tile < rmax; ++bj) tiles.push_back(make_int2((int)bi, (int)bj));
         }
         LDX_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), n_tiles * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
         LDX_CUDA(cudaStreamSynchronize(ctx->stream));   // `tiles` is a local
-        ctx->mma_tiles_v = v; ctx->mma_tiles_n = n_tile; ctx->mma_tiles_begin = row_begin; ctx->mma_tiles_ptr = d_tiles;
+        ctx->mma_tiles_v = v; ctx->mma_tiles_n = n_tile; ctx->mma_tiles_begin = row_begin; ctx->mma_tiles_ptr = d_tiles; ctx->mma_tiles_pair = pair;
     }
 
     dim3 ggrid((unsigned)((v_pad + 255) / 256), (unsigned)kc_count);
@@ -856,7 +967,7 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t 
     A.out_off = row_begin * (row_begin - 1) / 2;
     A.packed = d_packed; A.n11 = d_n11;
     A.n_sel = s->n_sel;
-    {   // guard band of the screening arithmetic (see fast_pair).  Its fp32 half needs m and n1*n0 exact
+    {   // guard band of the screening arithmetic (see fast_pair2).  Its fp32 half needs m and n1*n0 exact
         // (<= 2^24, i.e. N <= 8192); should a caller ever get past the check above with more, every pair
         // takes the exact path.
         const double n = (double)s->n_sel, g = 1.0e4 * 16.0 * 1.1102230246251565e-16 * n * n;
@@ -871,8 +982,8 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t 
     A.dbg = getenv("LDX_DEBUG_MMA") ? atoi(getenv("LDX_DEBUG_MMA")) : 0;
     int rc;
     switch (n_tile) {
-        case 64: rc = launch_tiles<64>(ctx, A); break;
-        case 128: rc = launch_tiles<128>(ctx, A); break;
+        case 64: rc = launch_tiles<64, false>(ctx, A); break;
+        case 128: rc = pair ? launch_tiles<128, true>(ctx, A) : launch_tiles<128, false>(ctx, A); break;
         default: return set_error(LDX_ERR_ARG, "tcgen05 tile width must be 64 or 128");
     }
     if (rc != LDX_OK) return rc;

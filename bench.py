@@ -142,8 +142,9 @@ def run_reference(args, rank):
 
 # --------------------------------------------------------------------------- clocks sampler
 class ClockSampler(threading.Thread):
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.005):
         super().__init__(daemon=True)
+        self.period_s = period_s
         self.index, self.samples, self.reasons, self.max_mhz, self._halt = index, [], set(), None, threading.Event()
         try:
             import pynvml
@@ -172,7 +173,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(self.period_s)
 
     def stop(self):
         self._halt.set()
@@ -228,8 +229,11 @@ def run_ours(args, rank, world, local_rank):
     #      all-pairs kernel + deferred-pairs kernel, results left in HBM.  Calls are enqueued asynchronously, up
     #      to `depth` in flight (each with its own result buffer); ldx_resolve() then settles the near-tie pairs
     #      of all of them (the one host round trip of the path) -- inside the timed region.
+    host = {"enqueue_s": 0.0, "resolve_s": 0.0}           # host-side cost of the loop (diagnostic: is the GPU ever starved?)
+
     def run_steps(n, timed):
         marks = []
+        t_h = time.perf_counter()
         for k in range(n):
             f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
             s1 = torch.cuda.Event(enable_timing=True)
@@ -240,12 +244,17 @@ def run_ours(args, rank, world, local_rank):
             s1.record(stream)                   # f1..s1 = the step's kernels
             marks.append((f0, f1, s1))
             if (k + 1) % depth == 0 or k == n - 1:
+                t_r = time.perf_counter()
                 ctx.resolve()
+                if timed:
+                    host["resolve_s"] += time.perf_counter() - t_r
+        if timed:
+            host["enqueue_s"] += time.perf_counter() - t_h - host["resolve_s"]
         return marks
 
     run_steps(args.warmup, False)
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.sampler_ms * 1e-3)
     sampler.start()
     launches0 = ctx.launch_count
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -359,7 +368,9 @@ def run_ours(args, rank, world, local_rank):
                        "calls_in_flight": depth, "sharding": "one variant set per GPU"},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(planes_np.nbytes + mask_np.nbytes + rows.nbytes),
                     "d2h_bytes_per_step": int(out_host.nbytes), "steps": e_steps, "wall_s": e2e_wall},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "parity_selfcheck": same}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "parity_selfcheck": same,
+            "host": {"enqueue_us_per_step": 1e6 * host["enqueue_s"] / args.steps, "resolve_wait_us_per_step": 1e6 * host["resolve_s"] / args.steps,
+                     "flush_us_per_step": 1e3 * flush_ms / args.steps}}
     if steady:
         line["steady_state"] = steady
     if rank == 0:
@@ -502,7 +513,8 @@ def main():
     ap.add_argument("--tile-n", type=int, default=0, help="tcgen05 tile width override (0 = heuristic)")
     ap.add_argument("--cpu-pairs-per-core", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=8, help="device-resident calls in flight per ldx_resolve()")
+    ap.add_argument("--pipeline", type=int, default=32, help="device-resident calls in flight per ldx_resolve()")
+    ap.add_argument("--sampler-ms", type=float, default=5.0, help="period of the NVML clock sampler thread")
     ap.add_argument("--no-steady", action="store_true", help="skip the 32,768-variant steady-state leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -104,7 +104,9 @@ int32_t ldx_set_tuning(ldx_ctx *ctx, int32_t key, int32_t value);
  * stamps (ns): [0] prologue done, [1]/[2] accumulator ready / epilogue done of its 1st tile,
  * [3]/[4] 2nd tile, [5]/[6] 3rd tile; [8+g] widener done / [64+g] MMA start / [128+g] producer issue /
  * [192+g] bits landed / [256+g] operand stage free (widener) / [320+g] widening stores issued, for its
- * first 48 pipeline stages g.  stamps8 (may be NULL, else 512 entries) receives the last recording. */
+ * first 48 pipeline stages g; [7] kernel entry, [56] all roles done; every CTA c < 192 also records its life
+ * cycle at [512 + 8c + k], k = 0 entry, 1 prologue done, 2 first accumulator ready, 3 first epilogue done,
+ * 4 all roles done, 5 SM id.  stamps8 (may be NULL, else 2048 entries) receives the last recording. */
 int32_t ldx_debug_trace(ldx_ctx *ctx, int32_t enable, uint64_t *stamps8);
 /* Dominant-kernel timing for roofline reports: while enabled, every all-pairs kernel
  * (triangle_mma_kernel / triangle_popc_kernel) and window kernel launch is bracketed by CUDA events

@@ -159,12 +159,12 @@ extern "C" int32_t ldx_debug_trace(ldx_ctx *ctx, int32_t enable, uint64_t *stamp
     LDX_REQUIRE(ctx, "ctx is NULL");
     LDX_CUDA(cudaSetDevice(ctx->device));
     if (enable && !ctx->d_trace) {
-        LDX_CUDA(cudaMalloc(&ctx->d_trace, 512 * sizeof(unsigned long long)));
-        LDX_CUDA(cudaMemset(ctx->d_trace, 0, 512 * sizeof(unsigned long long)));
+        LDX_CUDA(cudaMalloc(&ctx->d_trace, 2048 * sizeof(unsigned long long)));
+        LDX_CUDA(cudaMemset(ctx->d_trace, 0, 2048 * sizeof(unsigned long long)));
     }
     if (stamps8 && ctx->d_trace) {
         LDX_CUDA(cudaStreamSynchronize(ctx->stream));
-        LDX_CUDA(cudaMemcpy(stamps8, ctx->d_trace, 512 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        LDX_CUDA(cudaMemcpy(stamps8, ctx->d_trace, 2048 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     }
     if (!enable && ctx->d_trace) { cudaFree(ctx->d_trace); ctx->d_trace = nullptr; }
     return LDX_OK;

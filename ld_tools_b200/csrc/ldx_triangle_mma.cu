@@ -327,7 +327,10 @@ struct MmaArgs {
                                  // 2 skip column-operand widening, 4 skip the epilogue arithmetic, 8 skip the MMAs
 };
 
-__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) :: "memory"); return t; }
+// diagnostics: per-CTA life-cycle stamps at trace[512 + 8 * cta + k] (k: 0 entry, 1 prologue done, 2 first accumulator ready,
+// 3 first epilogue done, 4 all roles done, 5 SM id)
+#define LDX_CTA_STAMP(k) do { if (TRACE && A.trace && blockIdx.x < 192) A.trace[512 + 8 * blockIdx.x + (k)] = gtime(); } while (0)
 
 constexpr int N_WIDEN_WARPS = 16, N_EPI_WARPS = 8;  // wideners: four teams of 4 warps, team k takes pipeline stages g = k mod 4
 constexpr int WIDEN_TEAMS = 4, TEAM_WARPS = N_WIDEN_WARPS / WIDEN_TEAMS;
@@ -526,6 +529,11 @@ triangle_mma_kernel(const MmaArgs A) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kc_count = A.kc_count;
+    if (TRACE && A.trace && blockIdx.x == 0 && threadIdx.x == 0) A.trace[7] = gtime();    // kernel entry
+    if (threadIdx.x == 0) {
+        LDX_CTA_STAMP(0);
+        if (TRACE && A.trace && blockIdx.x < 192) { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); A.trace[512 + 8 * blockIdx.x + 5] = smid; }
+    }
 
     if (threadIdx.x == 0) {
         // pair: the leader's op_full / tmem_empty also count the peer's wideners / epilogue warps (remote arrives)
@@ -554,6 +562,7 @@ triangle_mma_kernel(const MmaArgs A) {
     pdl_launch_dependents();                                            // deferred-pairs kernel: launch latency hidden behind this grid
     pdl_wait();                                                         // bit panels / frequencies / tile list come from the gather kernel
     if (TRACE && A.trace && blockIdx.x == 0 && threadIdx.x == 0) A.trace[0] = gtime();   // prologue done
+    if (threadIdx.x == 0) LDX_CTA_STAMP(1);
 
     const int ks_count = kc_count / Cfg::CH;                  // pipeline stages per tile (kc_count is even)
     if (warp == 0) {
@@ -736,6 +745,7 @@ triangle_mma_kernel(const MmaArgs A) {
             if (!mbar_wait(tmem_full + 8 * buf, (tl / Cfg::ACC_BUFS) & 1, abort_s, A.error_flag, 128)) goto done;
             tc_fence_after();
             if (TRACE && A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[1 + 2 * tl] = gtime();   // accumulator ready
+            if (ew == 0 && lane == 0 && tl == 0) LDX_CTA_STAMP(2);
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 const int64_t rmin = r0 + quad * 32 + 16 * h;    // this pass: rows rmin .. rmin + 15
@@ -826,12 +836,15 @@ triangle_mma_kernel(const MmaArgs A) {
             __syncwarp();
             if (lane == 0) { if (PAIR) mbar_arrive_remote(tmem_empty_leader + 8 * buf); else mbar_arrive(tmem_empty + 8 * buf); }
             if (TRACE && A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[2 + 2 * tl] = gtime();       // epilogue of this tile done
+            if (ew == 0 && lane == 0 && tl == 0) LDX_CTA_STAMP(3);
         }
         flush_slow(A, sbuf, slow_cnt, lane, m_shift, thres);
     }
 done:
     tc_fence_before();
     __syncthreads();
+    if (TRACE && A.trace && blockIdx.x == 0 && threadIdx.x == 0) A.trace[56] = gtime();   // all roles done
+    if (threadIdx.x == 0) LDX_CTA_STAMP(4);
     if (PAIR) cluster_sync_all();      // the peer may still read this CTA's operands / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();

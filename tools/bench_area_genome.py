@@ -1,0 +1,250 @@
+"""BASELINE configs[4]: genome-scale ld_area -- 50,000 queries over a synthetic chr1-22 (~80 M variants,
+5008 haplotypes), +/-1 Mb flanks, r2 >= 0.8, region-sharded over the GPUs of a node.  Launch with
+torchrun, one rank per GPU (or plain `python` for one GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29512 tools/bench_area_genome.py [--variants 80000000] [--queries 50000]
+
+The job is the reference's loop ld_area.py:152-292 over 22 per-chromosome VCFs.  Here every chromosome
+is a bit-plane store (640 B per variant: 51 GB for the genome, resident in one B200's HBM) and the
+queries of a chromosome are ONE ldx_window_dev call.  Sharding (ld_tools_b200/shard.py): the
+genome-wide query list, ordered by (chromosome, position), is cut into `world` contiguous pieces with
+equal candidate-pair counts; a rank holds, per chromosome it touches, the rows its queries' windows
+reach (slab + halo) and nothing else.  No data-path collective; the kept pairs are gathered with
+shard.gather_hits (NCCL), timed separately.
+
+Synthetic data is generated ON the GPU straight into the stores (ldx_store_planes_ptr), from a counter-
+based generator seeded per (chromosome, 2^18-row block), so that every rank sees the same genome whatever
+rows it holds.  Variants come in groups of 8 neighbours sharing a base pattern (alt frequency 1/4) with
+1/64 of the haplotypes flipped independently: neighbours are in strong LD (r2 ~ 0.85-0.95), everything
+else is not -- the r2 >= 0.8 filter keeps a few pairs per query, as on real data.
+
+Parity at full size: for a seeded sample of each rank's queries the whole window is recomputed on the host
+(numpy popcounts + the oracle's C finalisation) and the kept rows, counts and packed words must be equal.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+# GRCh38 autosome lengths (Mb), chr1..chr22
+CHR_MB = [248.96, 242.19, 198.30, 190.21, 181.54, 170.81, 159.35, 145.14, 138.39, 133.80, 135.09,
+          133.28, 114.36, 107.04, 101.99, 90.34, 83.26, 80.37, 58.62, 64.44, 46.71, 50.82]
+BLOCK = 1 << 18            # rows per generator block
+GROUP = 8                  # neighbours sharing a base pattern
+
+
+class _DevView:
+    """A raw device address as a CUDA array: torch.as_tensor() wraps it without a copy."""
+
+    def __init__(self, addr, n_words):
+        self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (addr, False), "version": 3}
+
+
+def fill_rows(torch, dev, planes, stride, n_hap, chrom, row_begin, row_end):
+    """planes: int64 tensor view [rows, stride] of a store holding chromosome rows row_begin..row_end-1."""
+    words = (n_hap + 63) // 64
+
+    def rnd(n, g):      # n x stride uniformly random 64-bit words (two int32 draws per word)
+        return torch.randint(-(1 << 31), 1 << 31, (n, 2 * stride), generator=g, device=dev, dtype=torch.int32).view(torch.int64)
+
+    for b in range(row_begin // BLOCK, (row_end + BLOCK - 1) // BLOCK):
+        g = torch.Generator(device=dev)
+        g.manual_seed(1_000_003 * (chrom + 1) + b)
+        base = rnd(BLOCK // GROUP, g) & rnd(BLOCK // GROUP, g)
+        noise = rnd(BLOCK, g)
+        for _ in range(5):
+            noise &= rnd(BLOCK, g)
+        rows = base.repeat_interleave(GROUP, dim=0) ^ noise
+        rows[:, words:] = 0
+        if n_hap & 63:
+            rows[:, words - 1] &= (1 << (n_hap & 63)) - 1
+        a, e = max(b * BLOCK, row_begin), min((b + 1) * BLOCK, row_end)
+        planes[a - row_begin:e - row_begin] = rows[a - b * BLOCK:e - b * BLOCK]
+        del base, noise, rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--variants", type=int, default=80_000_000)
+    ap.add_argument("--queries", type=int, default=50_000)
+    ap.add_argument("--flank", type=int, default=1_000_000)
+    ap.add_argument("--n-hap", type=int, default=5008)
+    ap.add_argument("--thres", type=float, default=0.8)
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--check", type=int, default=6, help="queries per rank verified against the oracle")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from ld_tools_b200 import Context, Store, shard
+    from ld_tools_b200._lib import BELOW_THRES, HIT_DTYPE, R2_MASK
+    from ld_tools_b200.engine import threshold_e4
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = Context(local)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    n_hap = args.n_hap
+    thres = threshold_e4(args.thres)
+
+    # ---- the job, identically on every rank: per chromosome sorted positions, query rows, candidate ranges
+    t_plan = time.perf_counter()
+    tot_mb = sum(CHR_MB)
+    chroms = []
+    for c, mb in enumerate(CHR_MB):
+        nv = int(round(args.variants * mb / tot_mb))
+        nq = max(1, int(round(args.queries * mb / tot_mb)))
+        rng = np.random.default_rng(9000 + c)
+        pos0 = np.sort(rng.integers(10_000, int(mb * 1e6), size=nv, dtype=np.int64)).astype(np.int32)
+        q_row = np.sort(rng.choice(nv, nq, replace=False)).astype(np.int64)
+        lo, hi, ws, we = shard.window_bounds(pos0, 1, pos0[q_row].astype(np.int64) + 1, args.flank)
+        chroms.append({"nv": nv, "pos0": pos0, "q_row": q_row, "lo": lo, "hi": hi, "ws": ws, "we": we})
+    work = np.concatenate([ch["hi"] - ch["lo"] for ch in chroms]).astype(np.float64)
+    q_chrom = np.concatenate([np.full(len(ch["q_row"]), c) for c, ch in enumerate(chroms)])
+    q_first = np.concatenate([[0], np.cumsum([len(ch["q_row"]) for ch in chroms])])
+    cum = np.concatenate([[0.0], np.cumsum(work)])
+    cuts = [int(np.searchsorted(cum, cum[-1] * k / world, side="left")) for k in range(world)] + [len(work)]
+    a, b = cuts[rank], cuts[rank + 1]
+    plan_s = time.perf_counter() - t_plan
+
+    # ---- this rank's pieces: per chromosome the queries [qa, qb) and the rows their windows reach
+    t_build = time.perf_counter()
+    pieces = []
+    store_bytes = 0
+    for c in sorted(set(q_chrom[a:b].tolist())):
+        ch = chroms[c]
+        qa, qb = max(a, q_first[c]) - q_first[c], min(b, q_first[c + 1]) - q_first[c]
+        rb = int(min(ch["lo"][qa:qb].min(), ch["q_row"][qa]))
+        re = int(max(ch["hi"][qa:qb].max(), ch["q_row"][qb - 1] + 1))
+        st = Store(ctx, re - rb, n_hap)
+        planes = torch.as_tensor(_DevView(st.planes_ptr, (re - rb) * st.stride_words), device=dev).view(re - rb, st.stride_words)
+        fill_rows(torch, dev, planes, st.stride_words, n_hap, c, rb, re)
+        torch.cuda.synchronize()
+        pos0 = ch["pos0"][rb:re]
+        st.set_annotations(pos0, pos0 + 1, (np.int64(c) << 32) + np.arange(rb, re, dtype=np.int64), np.ones(re - rb, np.uint8))
+        st.select_all()
+        nq = qb - qa
+        cap = 64 * nq + 65536
+        pieces.append({"chrom": c, "st": st, "rb": rb, "re": re, "qa": qa, "qb": qb, "cap": cap,
+                       "q": ch["q_row"][qa:qb] - rb, "lo": ch["lo"][qa:qb] - rb, "hi": ch["hi"][qa:qb] - rb,
+                       "ws": ch["ws"][qa:qb], "we": ch["we"][qa:qb],
+                       "d_hits": torch.empty(cap * 4, dtype=torch.int32, device=dev),
+                       "d_cnt": torch.zeros(2, dtype=torch.int64, device=dev)})
+        store_bytes += (re - rb) * st.stride_words * 8
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t_build
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def job():
+        for p in pieces:
+            p["st"].window_dev(p["q"], p["lo"], p["hi"], p["ws"], p["we"], "r_square", thres, p["d_hits"].data_ptr(), p["cap"],
+                               p["d_cnt"].data_ptr())
+        ctx.resolve()
+
+    job()                                                        # warm-up
+    times = []
+    for _ in range(args.reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        job()
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+
+    # ---- results: kept pairs in job-wide numbering (query index of the genome-wide list, chromosome row)
+    scanned, overflow, mine = 0, 0, []
+    for p in pieces:
+        n_found, n_scanned = (int(x) for x in p["d_cnt"].cpu())
+        scanned += n_scanned
+        overflow += max(0, n_found - p["cap"])
+        h = p["d_hits"][:4 * min(n_found, p["cap"])].cpu().numpy().view(HIT_DTYPE).copy()
+        h = h[(h["packed"] & BELOW_THRES) == 0]
+        h["query"] += p["qa"] + q_first[p["chrom"]]
+        h["row"] += p["rb"]
+        p["hits"] = h
+        mine.append(h)
+    mine = np.concatenate(mine) if mine else np.zeros(0, dtype=HIT_DTYPE)
+    t_g = time.perf_counter()
+    if world > 1:
+        allh = shard.gather_hits(mine, device=dev)
+        torch.cuda.synchronize()
+    else:
+        allh = mine[np.lexsort((mine["row"], mine["query"]))]
+    gather_s = time.perf_counter() - t_g
+
+    # ---- parity on a seeded sample of this rank's queries: the full window recomputed on the host
+    from oracle import ld_oracle
+    rng = np.random.default_rng(500 + rank)
+    ok, n_checked, pairs_checked = True, 0, 0
+    words = (n_hap + 63) // 64
+    for _ in range(args.check):
+        p = pieces[int(rng.integers(len(pieces)))]
+        k = int(rng.integers(len(p["q"])))
+        lo, hi, q = int(p["lo"][k]), int(p["hi"][k]), int(p["q"][k])
+        win = p["st"].download(lo, hi - lo)[:, :words]
+        qrow = p["st"].download(q, 1)[0, :words]
+        n1 = np.bitwise_count(win).sum(axis=1).astype(np.int32)
+        n11 = np.bitwise_count(win & qrow[None, :]).sum(axis=1).astype(np.int32)
+        n1q = np.full(hi - lo, int(np.bitwise_count(qrow).sum()), dtype=np.int32)
+        want_w = ld_oracle.packed_words(n_hap, n11, n1q, n1)              # var_1 = query, var_2 = window row (ld_area.py:242)
+        keep = ((want_w & R2_MASK) >= thres) & (np.arange(lo, hi) != q)      # rounded measure >= thres (ld_area.py:248), not the query itself (:222)
+        got = p["hits"][p["hits"]["query"] == k + p["qa"] + q_first[p["chrom"]]]
+        got = got[np.argsort(got["row"])]
+        want_rows = np.flatnonzero(keep) + lo + p["rb"]
+        same = (got["row"].tolist() == want_rows.tolist() and (got["n11"] == n11[keep]).all()
+                and ((got["packed"] & ~np.uint32(BELOW_THRES)) == want_w[keep]).all())
+        ok &= bool(same)
+        n_checked += 1
+        pairs_checked += hi - lo
+    flag = torch.tensor([1 if ok else 0, scanned, overflow, n_checked, pairs_checked, store_bytes, len(pieces)], dtype=torch.int64, device=dev)
+    parts = [torch.zeros_like(flag) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(parts, flag)
+    else:
+        parts = [flag]
+    parts = [p.tolist() for p in parts]
+    best = min(times)
+    if rank == 0:
+        total_scanned = sum(p[1] for p in parts)
+        row_bytes = pieces[0]["st"].stride_words * 8
+        print(json.dumps({
+            "workload": f"genome-scale ld_area: {sum(len(ch['q_row']) for ch in chroms)} queries over synthetic chr1-22 "
+                        f"({sum(ch['nv'] for ch in chroms)} variants x {n_hap} haplotypes), +/-{args.flank} bp, r2 >= {args.thres}, region-sharded",
+            "n_gpus": world, "scaling": "strong", "ms": best, "ms_all": times, "pairs_scanned": total_scanned,
+            "value": total_scanned / (best * 1e-3), "unit": "pairs/s",
+            "algorithmic_GBps_per_gpu": total_scanned * row_bytes / (best * 1e-3) / 1e9 / world,
+            "kept_pairs": int(allh.shape[0]), "hit_overflow": sum(p[2] for p in parts),
+            "store_GB_per_rank": [round(p[5] / 1e9, 2) for p in parts], "chromosome_pieces_per_rank": [p[6] for p in parts],
+            "pairs_per_rank": [p[1] for p in parts], "gather_hits_s": gather_s, "plan_s": plan_s, "build_s_rank0": build_s,
+            "queries_checked": sum(p[3] for p in parts), "pairs_checked": sum(p[4] for p in parts),
+            "parity_sample_ok": all(p[0] == 1 for p in parts)}), flush=True)
+    for p in pieces:
+        p["st"].close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -63,11 +63,21 @@ def main():
             pps = n_pairs / best
             print(f"V={v} tile={tile} {best * 1e3:.3f} ms  {pps:.3e} pairs/s  int8 frac {pps * 2 * args.n_hap / peak_i8:.3f}", flush=True)
             if args.trace and engine == ENGINE_MMA:
-                s = np.zeros(512, dtype=np.uint64)
+                s = np.zeros(2048, dtype=np.uint64)
                 ctx._lib.ldx_debug_trace(ctx._h, 1, ptr(s))
                 s = s.astype(np.int64)
                 t0 = s[0]
+                print("  kernel entry %.2f us before the prologue's end; all roles done at %.2f us" % ((t0 - s[7]) / 1e3, (s[56] - t0) / 1e3))
                 print("  tile stamps (us after prologue): " + " ".join("%.2f" % ((x - t0) / 1e3) for x in s[1:7] if x))
+                c = s[512:512 + 8 * 192].reshape(192, 8)
+                c = c[c[:, 0] > 0]
+                if len(c):
+                    e0 = c[:, 0].min()
+                    print("  per-CTA life cycle (us after the first CTA's entry): entry / prologue done / accumulator ready / epilogue done / all done")
+                    for q in (0, 10, 50, 90, 100):
+                        print("    p%-3d  %s" % (q, "  ".join("%6.2f" % (np.percentile(c[:, k] - e0, q) / 1e3) for k in range(5))))
+                    last = int(np.argmax(c[:, 4]))
+                    print("    slowest CTA %d on SM %d: %s" % (last, c[last, 5], "  ".join("%6.2f" % ((c[last, k] - e0) / 1e3) for k in range(5))))
                 for g in range(0, 48, 1):
                     if not s[64 + g]:
                         break

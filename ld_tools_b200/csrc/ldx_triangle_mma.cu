@@ -319,6 +319,10 @@ struct MmaArgs {
     int32_t n_sel;               // N = selected haplotypes
     float lim_dp, lim_r2;        // 0.5 - guard band of the screening arithmetic at x = 0 (see fast_pair2)
     uint4 *slow; uint32_t *slow_count; uint32_t slow_cap;   // deferred pairs {row, col, n11, -} for slow_pairs_kernel
+    // single-wave calls (at most one tile per CTA): no follow-up kernel -- every epilogue warp settles its own deferred
+    // pairs and the last CTA publishes the completion record (counters = d_fix_count, see slow_pairs_kernel)
+    int inline_settle; uint32_t *counters; volatile uint32_t *mailbox; uint32_t seq;
+    int help;                    // single-wave calls: the wideners, idle once the K loop is done, take half of the epilogue
     uint32_t *packed; int32_t *n11;
     FixupSink fix;
     int32_t *error_flag;
@@ -336,12 +340,13 @@ constexpr int N_WIDEN_WARPS = 16, N_EPI_WARPS = 8;  // wideners: four teams of 4
 constexpr int WIDEN_TEAMS = 4, TEAM_WARPS = N_WIDEN_WARPS / WIDEN_TEAMS;
 // Warp roles, aligned to warpgroups (4 warps) so that setmaxnreg can move registers between them:
 //   warps 0-3   producer (0), MMA issuer (1), two spare warps      -> 40 registers
-//   warps 4-19  wideners (latency-bound: many warps, few registers) -> 56 registers
+//   warps 4-19  wideners (latency-bound: many warps, few registers) -> 56 registers (64 in the single-wave kernel, where
+//               they also run a share of the epilogue)
 //   warps 20-27 epilogue (sixteen pairs in flight per lane)         -> 104 registers
 // The pool is the CTA's own 896 x 72 registers: setmaxnreg.inc BLOCKS until enough have been released,
-// so the budget must close: 128*(72-40) + 512*(72-56) = 12288 freed >= 256*(104-72) = 8192 needed.
-constexpr int REGS_LAUNCH = 72, REGS_CTRL = 40, REGS_WIDEN = 56, REGS_EPI = 104;
-static_assert(128 * (REGS_LAUNCH - REGS_CTRL) + 32 * N_WIDEN_WARPS * (REGS_LAUNCH - REGS_WIDEN) >= 32 * N_EPI_WARPS * (REGS_EPI - REGS_LAUNCH), "setmaxnreg budget");
+// so the budget must close: 128*(72-40) + 512*(72-64) = 8192 freed >= 256*(104-72) = 8192 needed (single-wave kernel).
+constexpr int REGS_LAUNCH = 72, REGS_CTRL = 40, REGS_WIDEN_SINGLE = 64 /* 56 in the multi-wave kernel */, REGS_EPI = 104;
+static_assert(128 * (REGS_LAUNCH - REGS_CTRL) + 32 * N_WIDEN_WARPS * (REGS_LAUNCH - REGS_WIDEN_SINGLE) >= 32 * N_EPI_WARPS * (REGS_EPI - REGS_LAUNCH), "setmaxnreg budget");
 constexpr int FIRST_WIDEN_WARP = 4, FIRST_EPI_WARP = FIRST_WIDEN_WARP + N_WIDEN_WARPS;
 constexpr int MMA_THREADS = 32 * (FIRST_EPI_WARP + N_EPI_WARPS);   // 896
 static_assert(MMA_THREADS * REGS_LAUNCH <= 65536, "register file");
@@ -458,9 +463,15 @@ __device__ __forceinline__ void settle_slow_pair(const uint4 e, const VarFreq *_
 // the ~1% the list is sized for) are settled right here -- slower, never wrong.  Every buffered entry
 // belongs to a chunk whose provisional words this warp has already stored (and __syncwarp orders the
 // warp's stores), so the settled word is the one that stays.
+template <bool SINGLE>
 __device__ __forceinline__ uint32_t flush_slow(const MmaArgs &A, const uint4 *sbuf, uint32_t cnt, int lane, uint32_t m_shift, uint32_t thres) {
     if (cnt == 0) return 0;
     __syncwarp();
+    if (SINGLE) {          // warp-uniform: one deferred pair per lane, right here
+        for (uint32_t i = lane; i < cnt; i += 32) settle_slow_pair(sbuf[i], A.freq_rows, A.fc, m_shift, thres, A.packed, A.out_off, A.fix);
+        __syncwarp();
+        return 0;
+    }
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(A.slow_count, cnt);
     base = __shfl_sync(0xffffffffu, base, 0);
@@ -505,7 +516,10 @@ slow_pairs_kernel(const uint4 *__restrict__ list, uint32_t *__restrict__ counter
     }
 }
 
-template <int N, bool WANT_N11, bool THRES, bool TRACE, bool PAIR>
+// SINGLE: the call is one wave of tiles (every CTA has exactly one): deferred pairs are settled in this kernel, the last CTA
+// publishes the completion record, and the wideners share the epilogue.  The multi-wave instantiation carries none of that
+// code: its hot loops are sensitive to every change in register allocation and code layout.
+template <int N, bool WANT_N11, bool THRES, bool TRACE, bool PAIR, bool SINGLE>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 triangle_mma_kernel(const MmaArgs A) {
     using Cfg = MmaCfg<N, PAIR>;
@@ -559,8 +573,11 @@ triangle_mma_kernel(const MmaArgs A) {
     if (PAIR) cluster_sync_all();      // the peer's barriers are initialised before anyone arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
+    // the tile list is uploaded by the host (and cached), not written by the preceding kernel: the first tile's
+    // coordinates can be fetched while that kernel is still running
+    const int2 first_tile = SINGLE && unit < A.n_tiles ? A.tiles[unit] : make_int2(0, 0);
     pdl_launch_dependents();                                            // deferred-pairs kernel: launch latency hidden behind this grid
-    pdl_wait();                                                         // bit panels / frequencies / tile list come from the gather kernel
+    pdl_wait();                                                         // bit panels / frequencies come from the gather kernel
     if (TRACE && A.trace && blockIdx.x == 0 && threadIdx.x == 0) A.trace[0] = gtime();   // prologue done
     if (threadIdx.x == 0) LDX_CTA_STAMP(1);
 
@@ -572,7 +589,7 @@ triangle_mma_kernel(const MmaArgs A) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         uint32_t g = 0;
         for (int t = unit; t < A.n_tiles; t += n_units) {
-            const int2 tile = A.tiles[t];
+            const int2 tile = SINGLE ? first_tile : A.tiles[t];
             const int64_t c0 = (int64_t)tile.y * N + (PAIR ? rank * Cfg::NB : 0);      // pair: this CTA's half of the columns
             const uint4 *a_src = A.bits + (int64_t)(PAIR ? tile.x * 2 + rank : tile.x) * kc_count * 128;
             for (int ks = 0; ks < ks_count; ++ks, ++g) {
@@ -641,7 +658,8 @@ triangle_mma_kernel(const MmaArgs A) {
     } else if (warp < FIRST_WIDEN_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // spare warps: hand their registers over and wait
     } else if (warp < FIRST_EPI_WARP) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (SINGLE) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         // ===== wideners: bit rows -> operand bytes.  Four teams of four warps take pipeline stages in turn,
         // so that the fixed latencies of a stage (two mbarrier waits, the TMEM store, the proxy fence)
         // of one team overlap the work of the others.  Thread wt of a team widens row variant wt of the
@@ -707,6 +725,77 @@ triangle_mma_kernel(const MmaArgs A) {
                 if (TRACE && A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[8 + g] = gtime();
             }
         }
+        if (SINGLE && N == 128 && !PAIR && A.help && my_tiles) {
+            // ===== single wave: this CTA's only tile has no successor to widen for.  Widener warp (quadrant, team)
+            // takes the epilogue of rows 16..31 of its TMEM quadrant x columns 32*team..+31 -- the same arithmetic
+            // as the epilogue warps below (which then do rows 0..15 only), with the column records formed on the
+            // fly.  A pair the screen cannot settle leaves its count in the result word and is redone by the lane
+            // that found it (finalise_pair); a lane's own store is visible to its own later load.
+            const int quad = warp & 3, lq = lane >> 2, lr = lane & 3;
+            const uint32_t m_shift = A.measure == LDX_MEASURE_R2 ? 0u : (uint32_t)LDX_DP_SHIFT;
+            const uint32_t thres = A.has_thres ? (uint32_t)A.thres_e4 : 0u;
+            const int32_t Nn = A.n_sel;
+            const int64_t r0 = (int64_t)(PAIR ? first_tile.x * 2 + rank : first_tile.x) * MMA_M, c0 = (int64_t)first_tile.y * N;
+            const int64_t rmin = r0 + quad * 32 + 16;
+            const int cb = team * 32;
+            const int64_t cg0 = c0 + cb;
+            const bool mine = N == 128 && rmin < A.v && cg0 < rmin + 15 && cg0 < A.v && !(TRACE && (A.dbg & 4));   // warp-uniform
+            const int64_t ra = rmin + lq, rb = ra + 8;
+            int32_t n1a = 0, n1b = 0, cn1[8];
+            if (mine) {                             // the counts this lane needs, fetched while the tensor pipe finishes
+                n1a = A.freq_rows[ra].n1; n1b = A.freq_rows[rb].n1;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { cn1[2 * k] = A.freq_rows[cg0 + 8 * k + 2 * lr].n1; cn1[2 * k + 1] = A.freq_rows[cg0 + 8 * k + 2 * lr + 1].n1; }
+            }
+            if (!mbar_wait(tmem_full, 0, abort_s, A.error_flag, 64)) goto done;
+            tc_fence_after();
+            if (mine) {
+                const int32_t aNa = n1a * Nn, cNa = Nn * Nn - aNa, aNb = n1b * Nn, cNb = Nn * Nn - aNb;
+                const float faa = __int2float_rn(n1a * (Nn - n1a)), fab = __int2float_rn(n1b * (Nn - n1b));
+                uint32_t *pa = A.packed + (ra * (ra - 1) / 2 - A.out_off + cg0 + 2 * lr);
+                uint32_t *pb = A.packed + (rb * (rb - 1) / 2 - A.out_off + cg0 + 2 * lr);
+                int32_t *qa = WANT_N11 ? A.n11 + (ra * (ra - 1) / 2 - A.out_off + cg0 + 2 * lr) : nullptr;
+                int32_t *qb = WANT_N11 ? A.n11 + (rb * (rb - 1) / 2 - A.out_off + cg0 + 2 * lr) : nullptr;
+                uint32_t acc[16];
+                tmem_ld16x256(tmem_base + ((uint32_t)(quad * 32 + 16) << 16) + (uint32_t)cb, acc);
+                uint32_t slow = 0;
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    const int k = i >> 2, g = (i >> 1) & 1;
+                    const int64_t col = cg0 + 8 * k + 2 * lr;
+                    ColRec cr0, cr1;
+                    cr0.n1 = cn1[2 * k]; cr1.n1 = cn1[2 * k + 1];
+                    cr0.n1N = cr0.n1 * Nn; cr1.n1N = cr1.n1 * Nn;
+                    cr0.prod = __int2float_rn(cr0.n1 * (Nn - cr0.n1)); cr1.prod = __int2float_rn(cr1.n1 * (Nn - cr1.n1));
+                    uint32_t w0, w1;
+                    bool s0, s1;
+                    fast_pair2<THRES>(acc[i], acc[i + 1], Nn, g ? n1b : n1a, g ? aNb : aNa, g ? cNb : cNa, g ? fab : faa, cr0, cr1,
+                                      A.lim_dp, A.lim_r2, m_shift, thres, w0, w1, s0, s1);
+                    const int64_t row = g ? rb : ra;
+                    const bool v0 = row < A.v && col < row, v1 = row < A.v && col + 1 < row;
+                    if (v0) {
+                        (g ? pb : pa)[8 * k] = s0 ? (acc[i] >> ACC_SHIFT) : w0;
+                        if (WANT_N11) (g ? qb : qa)[8 * k] = (int32_t)(acc[i] >> ACC_SHIFT);
+                        slow |= (uint32_t)s0 << i;
+                    }
+                    if (v1) {
+                        (g ? pb : pa)[8 * k + 1] = s1 ? (acc[i + 1] >> ACC_SHIFT) : w1;
+                        if (WANT_N11) (g ? qb : qa)[8 * k + 1] = (int32_t)(acc[i + 1] >> ACC_SHIFT);
+                        slow |= (uint32_t)s1 << (i + 1);
+                    }
+                }
+                while (slow) {
+                    const int i = __ffs(slow) - 1;
+                    slow &= slow - 1;
+                    const int k = i >> 2, e = i & 1;
+                    const int64_t row = (i & 2) ? rb : ra, col = cg0 + 8 * k + 2 * lr + e;
+                    const uint32_t n11 = ((i & 2) ? pb : pa)[8 * k + e];
+                    settle_slow_pair(make_uint4((uint32_t)row, (uint32_t)col, n11, 0u), A.freq_rows, A.fc, m_shift, thres, A.packed, A.out_off, A.fix);
+                }
+                __threadfence();
+            }
+            tc_fence_before();
+        }
     } else {
         // ===== epilogue.  Warp w may only touch TMEM lanes 32*(w%4) .. +31.  Accumulators are read with
         // the 16-lane x 256-bit shape: register i = 4k + 2g + e of lane l holds
@@ -730,7 +819,7 @@ triangle_mma_kernel(const MmaArgs A) {
         const uint32_t tmem_empty_leader = PAIR ? mapa_u32(tmem_empty, 0) : 0u;
         for (int t = unit; t < A.n_tiles; t += n_units, ++tl) {
             const uint32_t buf = tl % Cfg::ACC_BUFS;
-            const int2 tile = A.tiles[t];
+            const int2 tile = SINGLE ? first_tile : A.tiles[t];
             const int64_t r0 = (int64_t)(PAIR ? tile.x * 2 + rank : tile.x) * MMA_M, c0 = (int64_t)tile.y * N;
             // the column variants this warp works on (its half of the tile's columns): a private copy per warp costs
             // a few redundant loads and saves a barrier across the eight epilogue warps on every tile
@@ -742,17 +831,23 @@ triangle_mma_kernel(const MmaArgs A) {
                 cols[i] = cr;
             }
             __syncwarp();
-            if (!mbar_wait(tmem_full + 8 * buf, (tl / Cfg::ACC_BUFS) & 1, abort_s, A.error_flag, 128)) goto done;
+            // the first pass's row counts, fetched before the wait (freq_rows is padded to whole tiles)
+            const int32_t n1a_first = SINGLE ? A.freq_rows[r0 + quad * 32 + lq].n1 : 0, n1b_first = SINGLE ? A.freq_rows[r0 + quad * 32 + lq + 8].n1 : 0;
+            if (!mbar_wait(tmem_full + 8 * buf, (tl / Cfg::ACC_BUFS) & 1, abort_s, A.error_flag, 128)) {
+                if (SINGLE) break;            // aborted: still meet the other epilogue warps at the barrier below
+                goto done;
+            }
             tc_fence_after();
             if (TRACE && A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[1 + 2 * tl] = gtime();   // accumulator ready
             if (ew == 0 && lane == 0 && tl == 0) LDX_CTA_STAMP(2);
+            const int h_end = SINGLE && N == 128 && !PAIR && A.help ? 1 : 2;     // single wave: rows 16..31 of the quadrant belong to the wideners
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < h_end; ++h) {
                 const int64_t rmin = r0 + quad * 32 + 16 * h;    // this pass: rows rmin .. rmin + 15
                 if (rmin >= A.v || (TRACE && (A.dbg & 4))) break; // warp-uniform
                 // the lane's two row variants: n1a, n1a*N, N^2 - n1a*N, n1a*n0a
                 const int64_t ra = rmin + lq, rb = ra + 8;
-                const int32_t n1a = A.freq_rows[ra].n1, n1b = A.freq_rows[rb].n1;
+                const int32_t n1a = SINGLE && h == 0 ? n1a_first : A.freq_rows[ra].n1, n1b = SINGLE && h == 0 ? n1b_first : A.freq_rows[rb].n1;
                 const int32_t aNa = n1a * Nn, cNa = Nn * Nn - aNa, aNb = n1b * Nn, cNb = Nn * Nn - aNb;
                 const float faa = __int2float_rn(n1a * (Nn - n1a)), fab = __int2float_rn(n1b * (Nn - n1b));
                 // result words of (row, column c0 + 2 lr + j) live at p?[j]
@@ -817,7 +912,7 @@ triangle_mma_kernel(const MmaArgs A) {
                         while (true) {
                             const uint32_t bal = __ballot_sync(0xffffffffu, slow != 0);
                             if (bal == 0) break;
-                            if (slow_cnt > SLOW_BUF - 32) slow_cnt = flush_slow(A, sbuf, slow_cnt, lane, m_shift, thres);
+                            if (slow_cnt > SLOW_BUF - 32) slow_cnt = flush_slow<SINGLE>(A, sbuf, slow_cnt, lane, m_shift, thres);
                             if (slow) {
                                 const int i = __ffs(slow) - 1;
                                 slow &= slow - 1;
@@ -838,11 +933,46 @@ triangle_mma_kernel(const MmaArgs A) {
             if (TRACE && A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[2 + 2 * tl] = gtime();       // epilogue of this tile done
             if (ew == 0 && lane == 0 && tl == 0) LDX_CTA_STAMP(3);
         }
-        flush_slow(A, sbuf, slow_cnt, lane, m_shift, thres);
+        if (SINGLE) {
+            // Single wave: no follow-up kernel.  The eight warps pool their deferred pairs (about 1% of the tile,
+            // unevenly spread) and settle them one pair per thread: one pass of the fp64 chain instead of one per
+            // 32 entries of the fullest warp.  bar.sync orders the warps' provisional stores before the settled words.
+            constexpr int WARP_WORDS = 32 * EPI_PITCH + SLOW_BUF * 4;
+            __syncwarp();
+            if (lane == 0) stage[0] = slow_cnt;
+            asm volatile("bar.sync 1, %0;" :: "n"(32 * N_EPI_WARPS) : "memory");
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < N_EPI_WARPS; ++w) total += epi_s[w * WARP_WORDS];
+            for (uint32_t j = (uint32_t)(ew * 32 + lane); j < total; j += 32 * N_EPI_WARPS) {
+                uint32_t k = j;
+                int w = 0;
+                while (k >= epi_s[w * WARP_WORDS]) { k -= epi_s[w * WARP_WORDS]; ++w; }
+                const uint4 e = reinterpret_cast<const uint4 *>(epi_s + w * WARP_WORDS + 32 * EPI_PITCH)[k];
+                settle_slow_pair(e, A.freq_rows, A.fc, m_shift, thres, A.packed, A.out_off, A.fix);
+            }
+            __threadfence();                      // results and fix-up records visible before the completion record
+        } else {
+            flush_slow<false>(A, sbuf, slow_cnt, lane, m_shift, thres);
+        }
     }
 done:
     tc_fence_before();
     __syncthreads();
+    if (SINGLE && threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t ticket = atomicAdd(&A.counters[3], 1u);
+        if (ticket == gridDim.x - 1) {            // last CTA: what slow_pairs_kernel's last block does otherwise
+            __threadfence();
+            A.counters[3] = 0;
+            if (A.mailbox) {
+                A.mailbox[1] = *(volatile uint32_t *)&A.counters[0];
+                A.mailbox[2] = *(volatile uint32_t *)&A.counters[1];
+                __threadfence_system();
+                A.mailbox[0] = A.seq;
+            }
+        }
+    }
     if (TRACE && A.trace && blockIdx.x == 0 && threadIdx.x == 0) A.trace[56] = gtime();   // all roles done
     if (threadIdx.x == 0) LDX_CTA_STAMP(4);
     if (PAIR) cluster_sync_all();      // the peer may still read this CTA's operands / arrive on its barriers
@@ -858,11 +988,11 @@ bool triangle_mma_available() { return true; }
 // haplotypes fewer than 1% of the pairs are deferred; beyond it ENGINE_AUTO uses the popcount engine.
 int triangle_mma_max_haplotypes() { return 8192; }
 
-template <int N, bool WANT_N11, bool THRES, bool TRACE, bool PAIR>
+template <int N, bool WANT_N11, bool THRES, bool TRACE, bool PAIR, bool SINGLE>
 static int launch_tiles_t(ldx_ctx *ctx, const MmaArgs &A) {
     static bool attr_set = false;
     if (!attr_set) {
-        LDX_CUDA(cudaFuncSetAttribute(triangle_mma_kernel<N, WANT_N11, THRES, TRACE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        LDX_CUDA(cudaFuncSetAttribute(triangle_mma_kernel<N, WANT_N11, THRES, TRACE, PAIR, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)MmaCfg<N, PAIR>::SMEM));
         attr_set = true;
     }
@@ -879,18 +1009,22 @@ static int launch_tiles_t(ldx_ctx *ctx, const MmaArgs &A) {
         attr[1].id = cudaLaunchAttributeClusterDimension;
         attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = PAIR ? 2 : 1;
-        LDX_CUDA(cudaLaunchKernelEx(&cfg, triangle_mma_kernel<N, WANT_N11, THRES, TRACE, PAIR>, A));
+        LDX_CUDA(cudaLaunchKernelEx(&cfg, triangle_mma_kernel<N, WANT_N11, THRES, TRACE, PAIR, SINGLE>, A));
     }
     timing_end(ctx);
     ctx->launches++;
     LDX_LAUNCHED(ctx, "triangle_mma_kernel");
     return LDX_OK;
 }
+template <int N, bool PAIR, bool SINGLE>
+static int launch_tiles_s(ldx_ctx *ctx, const MmaArgs &A) {
+    if (A.trace && !A.has_thres && !A.n11) return launch_tiles_t<N, false, false, true, PAIR, SINGLE>(ctx, A);   // diagnostics build of the kernel
+    if (A.has_thres) return A.n11 ? launch_tiles_t<N, true, true, false, PAIR, SINGLE>(ctx, A) : launch_tiles_t<N, false, true, false, PAIR, SINGLE>(ctx, A);
+    return A.n11 ? launch_tiles_t<N, true, false, false, PAIR, SINGLE>(ctx, A) : launch_tiles_t<N, false, false, false, PAIR, SINGLE>(ctx, A);
+}
 template <int N, bool PAIR>
 static int launch_tiles(ldx_ctx *ctx, const MmaArgs &A) {
-    if (A.trace && !A.has_thres && !A.n11) return launch_tiles_t<N, false, false, true, PAIR>(ctx, A);   // diagnostics build of the kernel
-    if (A.has_thres) return A.n11 ? launch_tiles_t<N, true, true, false, PAIR>(ctx, A) : launch_tiles_t<N, false, true, false, PAIR>(ctx, A);
-    return A.n11 ? launch_tiles_t<N, true, false, false, PAIR>(ctx, A) : launch_tiles_t<N, false, false, false, PAIR>(ctx, A);
+    return A.inline_settle ? launch_tiles_s<N, PAIR, true>(ctx, A) : launch_tiles_s<N, PAIR, false>(ctx, A);
 }
 
 int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t row_begin, int measure, int has_thres,
@@ -993,6 +1127,12 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t 
     A.slow = d_slow; A.slow_count = ctx->d_fix_count + 2; A.slow_cap = (uint32_t)slow_cap64;
     A.trace = ctx->d_trace;
     A.dbg = getenv("LDX_DEBUG_MMA") ? atoi(getenv("LDX_DEBUG_MMA")) : 0;
+    // one wave of tiles (e.g. the 2,000-variant workload: 136 tiles on 148 SMs): a follow-up kernel for ~1% of the
+    // pairs costs more (launch boundary + its own tail) than settling them in the epilogue warps
+    static const int inline_env = getenv("LDX_INLINE_SETTLE") ? atoi(getenv("LDX_INLINE_SETTLE")) : -1;
+    A.inline_settle = inline_env >= 0 ? inline_env : (n_tiles <= (size_t)(pair ? ctx->sm_count / 2 : ctx->sm_count) ? 1 : 0);
+    A.counters = ctx->d_fix_count; A.mailbox = publish_seq ? ctx->d_mailbox : nullptr; A.seq = publish_seq;
+    A.help = A.inline_settle && n_tile == 128 && !pair && !getenv("LDX_NO_HELP");
     int rc;
     switch (n_tile) {
         case 64: rc = launch_tiles<64, false>(ctx, A); break;
@@ -1000,6 +1140,7 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t 
         default: return set_error(LDX_ERR_ARG, "tcgen05 tile width must be 64 or 128");
     }
     if (rc != LDX_OK) return rc;
+    if (A.inline_settle) return LDX_OK;
     // deferred pairs + completion record (d_fix_count: [0] near-ties, [1] error flag, [2] deferred pairs, [3] ticket)
     // ~1% of the pairs are deferred and each costs a long, serial fp64 chain: one pair per thread at twice that
     // rate (idle blocks are cheap, a thread looping over several pairs is not)

@@ -106,7 +106,8 @@ int32_t ldx_set_tuning(ldx_ctx *ctx, int32_t key, int32_t value);
  * [192+g] bits landed / [256+g] operand stage free (widener) / [320+g] widening stores issued, for its
  * first 48 pipeline stages g; [7] kernel entry, [56] all roles done; every CTA c < 192 also records its life
  * cycle at [512 + 8c + k], k = 0 entry, 1 prologue done, 2 first accumulator ready, 3 first epilogue done,
- * 4 all roles done, 5 SM id.  stamps8 (may be NULL, else 2048 entries) receives the last recording. */
+ * 4 all roles done, 5 SM id, 6/7 settlement barrier reached / passed (single-wave kernel), at [2048 + 2c] deferred
+ * pairs settled, at [2432 + c] their number.  stamps8 (may be NULL, else 4096 entries) receives the last recording. */
 int32_t ldx_debug_trace(ldx_ctx *ctx, int32_t enable, uint64_t *stamps8);
 /* Dominant-kernel timing for roofline reports: while enabled, every all-pairs kernel
  * (triangle_mma_kernel / triangle_popc_kernel) and window kernel launch is bracketed by CUDA events
@@ -212,7 +213,7 @@ int32_t ldx_triangle_rows(ldx_store *store, const int64_t *rows, int64_t v, int6
 /* ---------------------------------------------------------------- device-resident variants
  * Same kernels, but outputs stay in HBM (caller-allocated device memory) and the call only
  * enqueues work on the ctx stream.  ldx_resolve() then finishes the rounding of the (very rare)
- * pairs whose r2 sits within 1e-10 of a rounding tie -- there the reference's libm pow decides
+ * pairs whose r2 * 10^4 sits within 1e-9 of a rounding tie -- there the reference's libm pow decides
  * the last digit -- and must be called before the outputs are consumed (it synchronises).
  * Index arrays (rows, q_row, ...) are HOST arrays; pinned ones must stay valid until the next
  * ldx_synchronize()/ldx_resolve().

@@ -159,12 +159,12 @@ extern "C" int32_t ldx_debug_trace(ldx_ctx *ctx, int32_t enable, uint64_t *stamp
     LDX_REQUIRE(ctx, "ctx is NULL");
     LDX_CUDA(cudaSetDevice(ctx->device));
     if (enable && !ctx->d_trace) {
-        LDX_CUDA(cudaMalloc(&ctx->d_trace, 2048 * sizeof(unsigned long long)));
-        LDX_CUDA(cudaMemset(ctx->d_trace, 0, 2048 * sizeof(unsigned long long)));
+        LDX_CUDA(cudaMalloc(&ctx->d_trace, 4096 * sizeof(unsigned long long)));
+        LDX_CUDA(cudaMemset(ctx->d_trace, 0, 4096 * sizeof(unsigned long long)));
     }
     if (stamps8 && ctx->d_trace) {
         LDX_CUDA(cudaStreamSynchronize(ctx->stream));
-        LDX_CUDA(cudaMemcpy(stamps8, ctx->d_trace, 2048 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        LDX_CUDA(cudaMemcpy(stamps8, ctx->d_trace, 4096 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     }
     if (!enable && ctx->d_trace) { cudaFree(ctx->d_trace); ctx->d_trace = nullptr; }
     return LDX_OK;
@@ -231,7 +231,7 @@ extern "C" int32_t ldx_launch_count(ldx_ctx *ctx, int64_t *n_out) {
 // ------------------------------------------------------------------------------------------
 // Near-tie settlement.  The kernels compute d*d; CPython computes pow(d, 2.0) (calc_ld.py:87),
 // which glibc rounds differently for ~0.1% of inputs (1 ulp).  That can only change the printed
-// value when r2*10^4 is within an ulp of k + 0.5; the kernels flag a far wider band (1e-6) and
+// value when r2*10^4 is within an ulp of k + 0.5; the kernels flag a far wider band (1e-9) and
 // the few flagged pairs are re-evaluated here from their integer counts with the real libm pow.
 // gcc folds pow(x, 2.0) into x*x, hence the volatile pointer.
 static double (*volatile libm_pow)(double, double) = pow;

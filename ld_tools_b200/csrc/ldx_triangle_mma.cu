@@ -333,7 +333,7 @@ struct MmaArgs {
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) :: "memory"); return t; }
 // diagnostics: per-CTA life-cycle stamps at trace[512 + 8 * cta + k] (k: 0 entry, 1 prologue done, 2 first accumulator ready,
-// 3 first epilogue done, 4 all roles done, 5 SM id)
+// 3 first epilogue done, 4 all roles done, 5 SM id, 6/7 settlement barrier reached / passed; trace[2048 + 2 * cta]: settled)
 #define LDX_CTA_STAMP(k) do { if (TRACE && A.trace && blockIdx.x < 192) A.trace[512 + 8 * blockIdx.x + (k)] = gtime(); } while (0)
 
 constexpr int N_WIDEN_WARPS = 16, N_EPI_WARPS = 8;  // wideners: four teams of 4 warps, team k takes pipeline stages g = k mod 4
@@ -540,6 +540,12 @@ triangle_mma_kernel(const MmaArgs A) {
     const uint32_t tmem_full = bit_empty + 8 * Cfg::BIT_STAGES, tmem_empty = tmem_full + 16;
     uint32_t *tmem_ptr_s = reinterpret_cast<uint32_t *>(bars + Cfg::N_BARS);
     volatile int *abort_s = reinterpret_cast<volatile int *>(tmem_ptr_s + 1);
+    // single-wave kernel: CTA-wide list of deferred pairs.  It lives in the operand stages, which are free once the
+    // tile's accumulator is complete (every writer has waited for tmem_full first).
+    uint32_t *pool_cnt = tmem_ptr_s + 2;
+    uint4 *pool = reinterpret_cast<uint4 *>(op_s);
+    constexpr uint32_t POOL_CAP = Cfg::OP_STAGES * Cfg::OP_BYTES / 16;
+    constexpr int POOL_THREADS = 32 * (N_WIDEN_WARPS + N_EPI_WARPS);      // wideners + epilogue warps settle the list together
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kc_count = A.kc_count;
@@ -555,6 +561,7 @@ triangle_mma_kernel(const MmaArgs A) {
         for (int s = 0; s < Cfg::BIT_STAGES; ++s) { mbar_init(bit_full + 8 * s, 1); mbar_init(bit_empty + 8 * s, TEAM_WARPS); }
         for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + 8 * s, 1); mbar_init(tmem_empty + 8 * s, (PAIR ? 2 : 1) * N_EPI_WARPS); }
         *abort_s = 0;
+        if (SINGLE) *pool_cnt = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // one warp allocates TMEM (power-of-two columns >= 32) and later frees it
@@ -576,6 +583,12 @@ triangle_mma_kernel(const MmaArgs A) {
     // the tile list is uploaded by the host (and cached), not written by the preceding kernel: the first tile's
     // coordinates can be fetched while that kernel is still running
     const int2 first_tile = SINGLE && unit < A.n_tiles ? A.tiles[unit] : make_int2(0, 0);
+    if (SINGLE && threadIdx.x == 32) {
+        // the near-tie list is touched by a handful of pairs per call: without this the first of them pays a DRAM
+        // round trip for the counter and one for the record on the kernel's critical path
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(A.fix.count));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(A.fix.recs));
+    }
     pdl_launch_dependents();                                            // deferred-pairs kernel: launch latency hidden behind this grid
     pdl_wait();                                                         // bit panels / frequencies come from the gather kernel
     if (TRACE && A.trace && blockIdx.x == 0 && threadIdx.x == 0) A.trace[0] = gtime();   // prologue done
@@ -674,17 +687,18 @@ triangle_mma_kernel(const MmaArgs A) {
         const uint32_t op_full_leader = PAIR ? mapa_u32(op_full, 0) : 0u;     // pair: everybody reports to rank 0's barrier
         const uint32_t g_end = my_tiles * (uint32_t)ks_count;
         static_assert(Cfg::OP_STAGES == WIDEN_TEAMS, "one operand stage per team");
+        bool dead = false;            // single-wave kernel: an aborted warp still meets the others at the settlement barrier
         {
             for (uint32_t g = (uint32_t)team; g < g_end; g += WIDEN_TEAMS) {
                 const uint32_t sb = g % Cfg::BIT_STAGES, itb = g / Cfg::BIT_STAGES;
                 const uint32_t so = (uint32_t)team, ito = g / Cfg::OP_STAGES;
-                if (!mbar_wait(bit_full + 8 * sb, itb & 1, abort_s, A.error_flag)) goto done;
+                if (!mbar_wait(bit_full + 8 * sb, itb & 1, abort_s, A.error_flag)) { if (SINGLE) { dead = true; break; } goto done; }
                 if (TRACE && A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[192 + g] = gtime();
                 const uint4 *bsrc = reinterpret_cast<const uint4 *>(bit_s + sb * Cfg::BIT_BYTES);
                 uint4 ba[Cfg::CH];
 #pragma unroll
                 for (int c = 0; c < Cfg::CH; ++c) ba[c] = bsrc[c * MMA_M + wt];
-                if (!mbar_wait(op_empty + 8 * so, (ito & 1) ^ 1, abort_s, A.error_flag)) goto done;
+                if (!mbar_wait(op_empty + 8 * so, (ito & 1) ^ 1, abort_s, A.error_flag)) { if (SINGLE) { dead = true; break; } goto done; }
                 tc_fence_after();
                 if (TRACE && A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[256 + g] = gtime();
                 if (!(TRACE && (A.dbg & 1)))
@@ -725,7 +739,7 @@ triangle_mma_kernel(const MmaArgs A) {
                 if (TRACE && A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[8 + g] = gtime();
             }
         }
-        if (SINGLE && N == 128 && !PAIR && A.help && my_tiles) {
+        if (SINGLE && N == 128 && !PAIR && A.help && my_tiles && !dead) {
             // ===== single wave: this CTA's only tile has no successor to widen for.  Widener warp (quadrant, team)
             // takes the epilogue of rows 16..31 of its TMEM quadrant x columns 32*team..+31 -- the same arithmetic
             // as the epilogue warps below (which then do rows 0..15 only), with the column records formed on the
@@ -747,9 +761,9 @@ triangle_mma_kernel(const MmaArgs A) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { cn1[2 * k] = A.freq_rows[cg0 + 8 * k + 2 * lr].n1; cn1[2 * k + 1] = A.freq_rows[cg0 + 8 * k + 2 * lr + 1].n1; }
             }
-            if (!mbar_wait(tmem_full, 0, abort_s, A.error_flag, 64)) goto done;
+            dead = !mbar_wait(tmem_full, 0, abort_s, A.error_flag, 64);
             tc_fence_after();
-            if (mine) {
+            if (mine && !dead) {
                 const int32_t aNa = n1a * Nn, cNa = Nn * Nn - aNa, aNb = n1b * Nn, cNb = Nn * Nn - aNb;
                 const float faa = __int2float_rn(n1a * (Nn - n1a)), fab = __int2float_rn(n1b * (Nn - n1b));
                 uint32_t *pa = A.packed + (ra * (ra - 1) / 2 - A.out_off + cg0 + 2 * lr);
@@ -776,12 +790,20 @@ triangle_mma_kernel(const MmaArgs A) {
                     if (v0) {
                         (g ? pb : pa)[8 * k] = s0 ? (acc[i] >> ACC_SHIFT) : w0;
                         if (WANT_N11) (g ? qb : qa)[8 * k] = (int32_t)(acc[i] >> ACC_SHIFT);
-                        slow |= (uint32_t)s0 << i;
+                        if (s0) {                  // deferred: onto the CTA's list (a full list: redone by this lane below)
+                            const uint32_t slot = atomicAdd(pool_cnt, 1u);
+                            if (slot < POOL_CAP) pool[slot] = make_uint4((uint32_t)row, (uint32_t)col, acc[i] >> ACC_SHIFT, 0u);
+                            else slow |= 1u << i;
+                        }
                     }
                     if (v1) {
                         (g ? pb : pa)[8 * k + 1] = s1 ? (acc[i + 1] >> ACC_SHIFT) : w1;
                         if (WANT_N11) (g ? qb : qa)[8 * k + 1] = (int32_t)(acc[i + 1] >> ACC_SHIFT);
-                        slow |= (uint32_t)s1 << (i + 1);
+                        if (s1) {
+                            const uint32_t slot = atomicAdd(pool_cnt, 1u);
+                            if (slot < POOL_CAP) pool[slot] = make_uint4((uint32_t)row, (uint32_t)(col + 1), acc[i + 1] >> ACC_SHIFT, 0u);
+                            else slow |= 1u << (i + 1);
+                        }
                     }
                 }
                 while (slow) {
@@ -792,9 +814,26 @@ triangle_mma_kernel(const MmaArgs A) {
                     const uint32_t n11 = ((i & 2) ? pb : pa)[8 * k + e];
                     settle_slow_pair(make_uint4((uint32_t)row, (uint32_t)col, n11, 0u), A.freq_rows, A.fc, m_shift, thres, A.packed, A.out_off, A.fix);
                 }
-                __threadfence();
             }
             tc_fence_before();
+        }
+        if (SINGLE) {
+            // the CTA's deferred pairs (about 1% of the tile), one per thread over the wideners and the epilogue warps:
+            // one pass of the fp64 chain.  bar.sync orders every warp's provisional stores before the settled words.
+            if (warp == FIRST_WIDEN_WARP && lane == 0) LDX_CTA_STAMP(6);         // first widener warp at the settlement barrier
+            asm volatile("bar.sync 1, %0;" :: "n"(POOL_THREADS) : "memory");
+            if (warp == FIRST_WIDEN_WARP && lane == 0) LDX_CTA_STAMP(7);         // ... past it (all 24 warps arrived)
+            if (warp == FIRST_WIDEN_WARP && lane == 0 && TRACE && A.trace && blockIdx.x < 192) A.trace[2048 + 2 * 192 + blockIdx.x] = *pool_cnt;
+            if (!dead) {
+                const uint32_t m_shift = A.measure == LDX_MEASURE_R2 ? 0u : (uint32_t)LDX_DP_SHIFT;
+                const uint32_t thres = A.has_thres ? (uint32_t)A.thres_e4 : 0u;
+                const uint32_t total = min(*pool_cnt, POOL_CAP);
+                for (uint32_t j = threadIdx.x - 32 * FIRST_WIDEN_WARP; j < total; j += POOL_THREADS)
+                    settle_slow_pair(pool[j], A.freq_rows, A.fc, m_shift, thres, A.packed, A.out_off, A.fix);
+            }
+            if (warp == FIRST_WIDEN_WARP && lane == 0 && TRACE && A.trace && blockIdx.x < 192) A.trace[512 + 8 * 192 + 2 * blockIdx.x] = gtime();       // settled
+            // no fence here: thread 0's fence after the CTA-wide barrier below is cumulative over everything the
+            // barrier made it observe (the pattern of a grid-wide sync)
         }
     } else {
         // ===== epilogue.  Warp w may only touch TMEM lanes 32*(w%4) .. +31.  Accumulators are read with
@@ -934,24 +973,20 @@ triangle_mma_kernel(const MmaArgs A) {
             if (ew == 0 && lane == 0 && tl == 0) LDX_CTA_STAMP(3);
         }
         if (SINGLE) {
-            // Single wave: no follow-up kernel.  The eight warps pool their deferred pairs (about 1% of the tile,
-            // unevenly spread) and settle them one pair per thread: one pass of the fp64 chain instead of one per
-            // 32 entries of the fullest warp.  bar.sync orders the warps' provisional stores before the settled words.
-            constexpr int WARP_WORDS = 32 * EPI_PITCH + SLOW_BUF * 4;
+            // Single wave: no follow-up kernel.  This warp's buffered pairs go onto the CTA's list (what does not
+            // fit is settled right here), then everybody settles the list: see the wideners' side above.
             __syncwarp();
-            if (lane == 0) stage[0] = slow_cnt;
-            asm volatile("bar.sync 1, %0;" :: "n"(32 * N_EPI_WARPS) : "memory");
-            uint32_t total = 0;
-#pragma unroll
-            for (int w = 0; w < N_EPI_WARPS; ++w) total += epi_s[w * WARP_WORDS];
-            for (uint32_t j = (uint32_t)(ew * 32 + lane); j < total; j += 32 * N_EPI_WARPS) {
-                uint32_t k = j;
-                int w = 0;
-                while (k >= epi_s[w * WARP_WORDS]) { k -= epi_s[w * WARP_WORDS]; ++w; }
-                const uint4 e = reinterpret_cast<const uint4 *>(epi_s + w * WARP_WORDS + 32 * EPI_PITCH)[k];
-                settle_slow_pair(e, A.freq_rows, A.fc, m_shift, thres, A.packed, A.out_off, A.fix);
+            uint32_t base = 0;
+            if (lane == 0 && slow_cnt) base = atomicAdd(pool_cnt, slow_cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (uint32_t i = lane; i < slow_cnt; i += 32) {
+                if (base + i < POOL_CAP) pool[base + i] = sbuf[i];
+                else settle_slow_pair(sbuf[i], A.freq_rows, A.fc, m_shift, thres, A.packed, A.out_off, A.fix);
             }
-            __threadfence();                      // results and fix-up records visible before the completion record
+            asm volatile("bar.sync 1, %0;" :: "n"(POOL_THREADS) : "memory");
+            const uint32_t total = min(*pool_cnt, POOL_CAP);
+            for (uint32_t j = threadIdx.x - 32 * FIRST_WIDEN_WARP; j < total; j += POOL_THREADS)
+                settle_slow_pair(pool[j], A.freq_rows, A.fc, m_shift, thres, A.packed, A.out_off, A.fix);
         } else {
             flush_slow<false>(A, sbuf, slow_cnt, lane, m_shift, thres);
         }

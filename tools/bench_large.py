@@ -63,21 +63,25 @@ def main():
             pps = n_pairs / best
             print(f"V={v} tile={tile} {best * 1e3:.3f} ms  {pps:.3e} pairs/s  int8 frac {pps * 2 * args.n_hap / peak_i8:.3f}", flush=True)
             if args.trace and engine == ENGINE_MMA:
-                s = np.zeros(2048, dtype=np.uint64)
+                s = np.zeros(4096, dtype=np.uint64)
                 ctx._lib.ldx_debug_trace(ctx._h, 1, ptr(s))
                 s = s.astype(np.int64)
                 t0 = s[0]
                 print("  kernel entry %.2f us before the prologue's end; all roles done at %.2f us" % ((t0 - s[7]) / 1e3, (s[56] - t0) / 1e3))
                 print("  tile stamps (us after prologue): " + " ".join("%.2f" % ((x - t0) / 1e3) for x in s[1:7] if x))
-                c = s[512:512 + 8 * 192].reshape(192, 8)
+                c = np.concatenate([s[512:512 + 8 * 192].reshape(192, 8), s[2048:2048 + 2 * 192].reshape(192, 2)], axis=1)
                 c = c[c[:, 0] > 0]
                 if len(c):
                     e0 = c[:, 0].min()
-                    print("  per-CTA life cycle (us after the first CTA's entry): entry / prologue done / accumulator ready / epilogue done / all done")
+                    cols = [0, 1, 2, 3, 6, 7, 8, 4] if c[:, 6].max() > 0 else [0, 1, 2, 3, 4]
+                    print("  per-CTA life cycle (us after the first CTA's entry): entry / prologue done / accumulator ready / epilogue done / "
+                          + ("barrier reached / passed / settled / " if len(cols) > 5 else "") + "all done")
                     for q in (0, 10, 50, 90, 100):
-                        print("    p%-3d  %s" % (q, "  ".join("%6.2f" % (np.percentile(c[:, k] - e0, q) / 1e3) for k in range(5))))
-                    last = int(np.argmax(c[:, 4]))
-                    print("    slowest CTA %d on SM %d: %s" % (last, c[last, 5], "  ".join("%6.2f" % ((c[last, k] - e0) / 1e3) for k in range(5))))
+                        print("    p%-3d  %s" % (q, "  ".join("%6.2f" % (np.percentile(c[:, k] - e0, q) / 1e3) for k in cols)))
+                    pc = s[2048 + 2 * 192:2048 + 3 * 192][:len(c)]
+                    print("    deferred pairs per CTA: min %d median %d max %d (CTA %d)" % (pc.min(), np.median(pc), pc.max(), int(np.argmax(pc))))
+                    for last in np.argsort(c[:, 4])[-3:]:
+                        print("    slow CTA %d on SM %d: %s" % (last, c[last, 5], "  ".join("%6.2f" % ((c[last, k] - e0) / 1e3) for k in cols)))
                 for g in range(0, 48, 1):
                     if not s[64 + g]:
                         break

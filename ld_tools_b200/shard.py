@@ -12,6 +12,8 @@ The path shards into independent units with no exchange during compute:
   sides and scans the queries whose position falls into the slab.  The kept hits (variable length)
   are the only thing exchanged: one all_gather of counts, one of padded records (NCCL on GPU
   tensors, gloo on CPU tensors in the tests).
+  A whole-genome job (one store per chromosome) is cut the same way across chromosome boundaries
+  (genome_pieces): a rank holds, per chromosome it touches, only the rows its queries' windows reach.
 * ld_lite: replicas only.
 """
 import numpy as np
@@ -111,6 +113,37 @@ def area_slabs(pos0, end0_max_len, q_row, q_pos, flank, world):
             row_begin = row_end = own_begin
         out.append({"row_begin": row_begin, "row_end": row_end, "own_begin": own_begin, "own_end": own_end,
                     "queries": mine})
+    return out
+
+
+def genome_pieces(chroms, world):
+    """Region sharding of a whole-genome ld_area job (one store per chromosome, ld_area.py:152 loops over them).
+
+    chroms: per chromosome a dict with the position-sorted query arrays q_row, lo, hi (window_bounds()).  The
+    genome-wide query list, ordered by (chromosome, position), is cut into `world` contiguous pieces with equal
+    candidate-pair counts.  -> per rank a list of dicts, one per chromosome the rank touches:
+
+        chrom               index into chroms
+        qa, qb              the rank's queries of that chromosome: q_row[qa:qb]
+        row_begin, row_end  the chromosome rows the rank must hold (slab + halo of its queries' windows)
+    """
+    work = np.concatenate([np.asarray(ch["hi"], dtype=np.int64) - np.asarray(ch["lo"], dtype=np.int64) for ch in chroms]).astype(np.float64)
+    first = np.concatenate([[0], np.cumsum([len(ch["q_row"]) for ch in chroms])]).astype(np.int64)
+    cum = np.concatenate([[0.0], np.cumsum(work)])
+    cuts = [int(np.searchsorted(cum, cum[-1] * k / world, side="left")) for k in range(world)] + [len(work)]
+    out = []
+    for k in range(world):
+        a, b = cuts[k], max(cuts[k + 1], cuts[k])
+        pieces = []
+        for c, ch in enumerate(chroms):
+            qa, qb = int(max(a, first[c]) - first[c]), int(min(b, first[c + 1]) - first[c])
+            if qb <= qa:
+                continue
+            q_row, lo, hi = np.asarray(ch["q_row"]), np.asarray(ch["lo"]), np.asarray(ch["hi"])
+            pieces.append({"chrom": c, "qa": qa, "qb": qb,
+                           "row_begin": int(min(lo[qa:qb].min(), q_row[qa:qb].min())),
+                           "row_end": int(max(hi[qa:qb].max(), q_row[qa:qb].max() + 1))})
+        out.append(pieces)
     return out
 
 

@@ -127,6 +127,38 @@ def test_area_slabs_reproduce_the_unsharded_scan(world):
         assert max(s["row_end"] - s["row_begin"] for s in slabs) < len(job["pos0"])
 
 
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_genome_pieces_partition_a_multi_chromosome_job(world):
+    """BASELINE configs[4] in miniature: the genome-wide query list is cut across chromosome boundaries; every
+    query lands on exactly one rank, whose row range of that chromosome covers the query's whole window."""
+    rng = np.random.default_rng(world)
+    chroms = []
+    for c, nv in enumerate([5000, 1200, 3100, 40]):
+        pos0 = np.sort(rng.integers(0, 40 * nv, size=nv))
+        q_row = np.sort(rng.choice(nv, max(1, nv // 50), replace=False))
+        lo, hi, _, _ = shard.window_bounds(pos0, 1, pos0[q_row] + 1, 2000)
+        chroms.append({"q_row": q_row, "lo": lo, "hi": hi})
+    plan = shard.genome_pieces(chroms, world)
+    assert len(plan) == world
+    seen = [np.zeros(len(ch["q_row"]), dtype=int) for ch in chroms]
+    work = []
+    for pieces in plan:
+        w = 0
+        assert [p["chrom"] for p in pieces] == sorted(p["chrom"] for p in pieces)      # contiguous in genome order
+        for p in pieces:
+            ch = chroms[p["chrom"]]
+            seen[p["chrom"]][p["qa"]:p["qb"]] += 1
+            assert p["row_begin"] <= ch["lo"][p["qa"]:p["qb"]].min() and p["row_end"] >= ch["hi"][p["qa"]:p["qb"]].max()
+            assert p["row_begin"] <= ch["q_row"][p["qa"]] and p["row_end"] > ch["q_row"][p["qb"] - 1]
+            w += int((ch["hi"] - ch["lo"])[p["qa"]:p["qb"]].sum())
+        work.append(w)
+    assert all((s == 1).all() for s in seen)
+    total = sum(int((ch["hi"] - ch["lo"]).sum()) for ch in chroms)
+    assert sum(work) == total
+    biggest = max(int((ch["hi"] - ch["lo"]).max()) for ch in chroms)
+    assert max(work) <= total / world + biggest                                         # balanced to within one window
+
+
 def test_window_bounds_match_reference_flank_rule():
     pos0 = np.array([9, 99, 100, 149, 150, 151, 400], dtype=np.int64)
     lo, hi, ws, we = shard.window_bounds(pos0, 3, np.array([150, 5]), 50)

@@ -112,23 +112,17 @@ def main():
         q_row = np.sort(rng.choice(nv, nq, replace=False)).astype(np.int64)
         lo, hi, ws, we = shard.window_bounds(pos0, 1, pos0[q_row].astype(np.int64) + 1, args.flank)
         chroms.append({"nv": nv, "pos0": pos0, "q_row": q_row, "lo": lo, "hi": hi, "ws": ws, "we": we})
-    work = np.concatenate([ch["hi"] - ch["lo"] for ch in chroms]).astype(np.float64)
-    q_chrom = np.concatenate([np.full(len(ch["q_row"]), c) for c, ch in enumerate(chroms)])
     q_first = np.concatenate([[0], np.cumsum([len(ch["q_row"]) for ch in chroms])])
-    cum = np.concatenate([[0.0], np.cumsum(work)])
-    cuts = [int(np.searchsorted(cum, cum[-1] * k / world, side="left")) for k in range(world)] + [len(work)]
-    a, b = cuts[rank], cuts[rank + 1]
+    my_pieces = shard.genome_pieces(chroms, world)[rank]
     plan_s = time.perf_counter() - t_plan
 
     # ---- this rank's pieces: per chromosome the queries [qa, qb) and the rows their windows reach
     t_build = time.perf_counter()
     pieces = []
     store_bytes = 0
-    for c in sorted(set(q_chrom[a:b].tolist())):
+    for pc in my_pieces:
+        c, qa, qb, rb, re = pc["chrom"], pc["qa"], pc["qb"], pc["row_begin"], pc["row_end"]
         ch = chroms[c]
-        qa, qb = max(a, q_first[c]) - q_first[c], min(b, q_first[c + 1]) - q_first[c]
-        rb = int(min(ch["lo"][qa:qb].min(), ch["q_row"][qa]))
-        re = int(max(ch["hi"][qa:qb].max(), ch["q_row"][qb - 1] + 1))
         st = Store(ctx, re - rb, n_hap)
         planes = torch.as_tensor(_DevView(st.planes_ptr, (re - rb) * st.stride_words), device=dev).view(re - rb, st.stride_words)
         fill_rows(torch, dev, planes, st.stride_words, n_hap, c, rb, re)

@@ -50,6 +50,22 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0, "source": "fallback"}
 
 
+def ncu_traffic(profile_name):
+    """DRAM bytes (read + write) of one launch of the dominant kernel, from the committed summary of an
+    `ncu --set full` capture of this same command (profiles/, written by tools/ncu_summarize.py); None if absent."""
+    units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        total = 0.0
+        with open(os.path.join(ROOT, "profiles", profile_name)) as fh:
+            for line in fh:
+                f = line.split()
+                if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    total += float(f[1]) * units[f[2]]
+        return total or None
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------- CPU baseline
 _W = {}
 
@@ -326,7 +342,7 @@ def run_ours(args, rank, world, local_rank):
         roof = {"bound": "popc", "achieved": n_pairs * POPC_PER_PAIR / kern_s / 1e12, "peak": peak,
                 "unit": "TPOPC32/s", "peak_source": "148 SM x 16 POPC/clk x clocks.max.sm"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["traffic"] = None
+    roof["traffic"] = ncu_traffic("r01_ncu_full_mma_v10_v2000.txt") if used_mma else None     # bytes per launch (L2-resident operands)
     roof["kernel"] = "triangle_mma_kernel" if used_mma else "triangle_popc_kernel"
     roof["kernel_ms"] = kern_s * 1e3
     roof["kernel_launches_timed"] = int(dom_launches)
@@ -479,7 +495,7 @@ def run_area(args, rank, world, local_rank):
     row_bytes = st.stride_words * 8
     kern_s = dom_ms * 1e-3 / max(dom_n, 1)
     roof = {"bound": "hbm", "achieved": scanned * row_bytes / kern_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "peak_source": f"{peaks['source']} copy bandwidth", "traffic": None, "kernel": "window_kernel", "kernel_ms": kern_s * 1e3,
+            "peak_source": f"{peaks['source']} copy bandwidth", "traffic": ncu_traffic("r01_ncu_full_window_configs2.txt"), "kernel": "window_kernel", "kernel_ms": kern_s * 1e3,
             "kernel_launches_timed": int(dom_n),
             "algorithmic_per_launch": f"{scanned} pairs x {row_bytes} B (one candidate row each; query plane and mask in registers)"}
     roof["frac"] = roof["achieved"] / roof["peak"]

@@ -150,6 +150,10 @@ extern "C" int32_t ldx_set_tuning(ldx_ctx *ctx, int32_t key, int32_t value) {
             LDX_REQUIRE(value >= 2, "minimum variant count must be >= 2");
             ctx->mma_min_v = value;
             return LDX_OK;
+        case LDX_TUNE_DEFER_CAP:
+            LDX_REQUIRE(value >= 0, "deferred-pair list capacity must be >= 0");
+            ctx->defer_cap = value;
+            return LDX_OK;
         default:
             return set_error(LDX_ERR_ARG, "unknown tuning key");
     }

@@ -322,6 +322,7 @@ struct MmaArgs {
     // single-wave calls (at most one tile per CTA): no follow-up kernel -- every epilogue warp settles its own deferred
     // pairs and the last CTA publishes the completion record (counters = d_fix_count, see slow_pairs_kernel)
     int inline_settle; uint32_t *counters; volatile uint32_t *mailbox; uint32_t seq;
+    uint32_t pool_cap;           // single-wave calls: capacity of the CTA-wide list (tests shrink it to force the overflow paths)
     int help;                    // single-wave calls: the wideners, idle once the K loop is done, take half of the epilogue
     uint32_t *packed; int32_t *n11;
     FixupSink fix;
@@ -544,7 +545,7 @@ triangle_mma_kernel(const MmaArgs A) {
     // tile's accumulator is complete (every writer has waited for tmem_full first).
     uint32_t *pool_cnt = tmem_ptr_s + 2;
     uint4 *pool = reinterpret_cast<uint4 *>(op_s);
-    constexpr uint32_t POOL_CAP = Cfg::OP_STAGES * Cfg::OP_BYTES / 16;
+    const uint32_t POOL_CAP = min((uint32_t)(Cfg::OP_STAGES * Cfg::OP_BYTES / 16), A.pool_cap);
     constexpr int POOL_THREADS = 32 * (N_WIDEN_WARPS + N_EPI_WARPS);      // wideners + epilogue warps settle the list together
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1159,7 +1160,9 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t 
     }
     A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity, ctx->fix_tag};
     A.error_flag = reinterpret_cast<int32_t *>(ctx->d_fix_count + 1);
-    A.slow = d_slow; A.slow_count = ctx->d_fix_count + 2; A.slow_cap = (uint32_t)slow_cap64;
+    A.slow = d_slow; A.slow_count = ctx->d_fix_count + 2;
+    A.slow_cap = ctx->defer_cap ? (uint32_t)std::min<uint64_t>(slow_cap64, (uint64_t)ctx->defer_cap) : (uint32_t)slow_cap64;
+    A.pool_cap = ctx->defer_cap ? (uint32_t)ctx->defer_cap : 0xffffffffu;
     A.trace = ctx->d_trace;
     A.dbg = getenv("LDX_DEBUG_MMA") ? atoi(getenv("LDX_DEBUG_MMA")) : 0;
     // one wave of tiles (e.g. the 2,000-variant workload: 136 tiles on 148 SMs): a follow-up kernel for ~1% of the

@@ -348,6 +348,29 @@ def test_triangle_mma_bit_exact_vs_popcount_and_oracle(ctx, tile_n, n_var, n_hap
     st.close()
 
 
+@pytest.mark.parametrize("n_var,n_hap", [(700, 5008), (2000, 198), (2000, 5008), (2500, 5008), (2500, 198)])
+def test_triangle_mma_deferred_list_overflow_is_settled_in_place(ctx, n_var, n_hap):
+    """Pairs the single-precision screen cannot settle go onto a list (CTA-wide in the single-wave kernel, <= 148
+    tiles; global for the follow-up kernel otherwise).  With the list capped at 3 entries nearly all of them take
+    the overflow paths -- settled by the lane / warp that found them -- and the result must not change."""
+    from ld_tools_b200._lib import TUNE_DEFER_CAP
+    from ld_tools_b200.engine import ENGINE_MMA, ENGINE_POPC, threshold_e4
+    st, planes, mask = make_store(ctx, n_var, n_hap, seed=900 + n_var)
+    rows = np.arange(n_var)
+    t = threshold_e4(0.3)
+    ref_packed, ref_n11 = st.triangle(rows, measure="d_prime", thres_e4_=t, engine=ENGINE_POPC, want_n11=True)
+    ctx.set_tuning(TUNE_DEFER_CAP, 3)
+    try:
+        packed, n11 = st.triangle(rows, measure="d_prime", thres_e4_=t, engine=ENGINE_MMA, want_n11=True)
+        plain, _ = st.triangle(rows, engine=ENGINE_MMA)
+    finally:
+        ctx.set_tuning(TUNE_DEFER_CAP, 0)
+    assert (n11 == ref_n11).all()
+    assert (packed == ref_packed).all()
+    assert (plain == (ref_packed & ~np.uint32(0x40000000))).all()
+    st.close()
+
+
 def test_triangle_mma_full_size_and_threshold(ctx):
     from ld_tools_b200.engine import BELOW_THRES, ENGINE_MMA, r2_e4, threshold_e4
     st, planes, mask = make_store(ctx, 2000, 5008, seed=2)

@@ -158,6 +158,13 @@ int32_t ldx_store_pack_gt(ldx_store *store, int64_t first_row, int64_t n_rows, c
 /* Load / read back ready-made planes (host, [n_rows][stride_words] uint64). */
 int32_t ldx_store_upload(ldx_store *store, int64_t first_row, int64_t n_rows, const uint64_t *planes);
 int32_t ldx_store_download(const ldx_store *store, int64_t first_row, int64_t n_rows, uint64_t *planes);
+/* The on-disk form of a store: what replaces the reference's per-run tabix/pysam access to <chrom>.vcf.gz
+ * (prep_intgen_data.py:138-177 builds its cache once; so does this).  One file = 64-byte header
+ * {"LDXSTOR1", n_variants, n_hap, stride_words, annotated} + the planes + (if annotated) pos0 | end0 | idnum |
+ * eligible, all little-endian, streamed through pinned staging in 64 MiB pieces.  The sample mask is per run
+ * and not saved.  ldx_store_load creates the store; a truncated or foreign file is LDX_ERR_ARG. */
+int32_t ldx_store_save(const ldx_store *store, const char *path);
+int32_t ldx_store_load(ldx_ctx *ctx, const char *path, ldx_store **store_out);
 
 /* Select samples: mask[stride_words] (host).  Runs the per-variant count kernel (K2):
  * n1[v] = popcount(mask & plane[v]) (calc_ld.py:37,39), N = popcount(mask) (calc_ld.py:31), and

@@ -56,6 +56,8 @@ SIGNATURES = {
     "ldx_store_pack_gt": [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _i32, _vp],
     "ldx_store_upload": [_vp, _i64, _i64, _vp],
     "ldx_store_download": [_vp, _i64, _i64, _vp],
+    "ldx_store_save": [_vp, C.c_char_p],
+    "ldx_store_load": [_vp, C.c_char_p, _P(_vp)],
     "ldx_store_set_mask": [_vp, _vp],
     "ldx_store_counts": [_vp, _vp, _vp, _P(_i32)],
     "ldx_store_subset": [_vp, _vp, _i32, _P(_vp)],

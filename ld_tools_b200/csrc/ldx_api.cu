@@ -637,6 +637,101 @@ extern "C" int32_t ldx_store_set_annotations(ldx_store *s, const int32_t *pos0, 
     return LDX_OK;
 }
 
+// ------------------------------------------------------------------------------------------ store files
+namespace {
+struct StoreFileHeader {
+    char magic[8];
+    int64_t n_variants;
+    int32_t n_hap, stride_words, annotated, reserved[9];
+};
+static_assert(sizeof(StoreFileHeader) == 64, "store file header");
+constexpr size_t FILE_PIECE = 64u << 20;
+
+struct Staging {            // pinned bounce buffer + FILE, released on every exit path
+    void *buf = nullptr;
+    FILE *fh = nullptr;
+    ~Staging() { if (buf) cudaFreeHost(buf); if (fh) fclose(fh); }
+};
+
+int stream_out(ldx_ctx *ctx, Staging &st, const void *dev, size_t bytes) {
+    for (size_t off = 0; off < bytes; off += FILE_PIECE) {
+        const size_t n = std::min(FILE_PIECE, bytes - off);
+        LDX_CUDA(cudaMemcpyAsync(st.buf, (const uint8_t *)dev + off, n, cudaMemcpyDeviceToHost, ctx->stream));
+        LDX_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (fwrite(st.buf, 1, n, st.fh) != n) return ldx::set_error(LDX_ERR_STATE, "store file: write failed");
+    }
+    return LDX_OK;
+}
+int stream_in(ldx_ctx *ctx, Staging &st, void *dev, size_t bytes) {
+    for (size_t off = 0; off < bytes; off += FILE_PIECE) {
+        const size_t n = std::min(FILE_PIECE, bytes - off);
+        if (fread(st.buf, 1, n, st.fh) != n) return ldx::set_error(LDX_ERR_ARG, "store file: truncated");
+        LDX_CUDA(cudaMemcpyAsync((uint8_t *)dev + off, st.buf, n, cudaMemcpyHostToDevice, ctx->stream));
+        LDX_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return LDX_OK;
+}
+}  // namespace
+
+extern "C" int32_t ldx_store_save(const ldx_store *s, const char *path) {
+    LDX_REQUIRE(s && path, "NULL argument");
+    ldx_ctx *ctx = s->ctx;
+    LDX_CUDA(cudaSetDevice(ctx->device));
+    Staging st;
+    LDX_CUDA(cudaMallocHost(&st.buf, FILE_PIECE));
+    st.fh = fopen(path, "wb");
+    if (!st.fh) return set_error(LDX_ERR_ARG, std::string("store file: cannot create ") + path);
+    StoreFileHeader h = {};
+    std::memcpy(h.magic, "LDXSTOR1", 8);
+    h.n_variants = s->n_variants; h.n_hap = s->n_hap; h.stride_words = s->stride_words; h.annotated = s->annotated ? 1 : 0;
+    if (fwrite(&h, sizeof h, 1, st.fh) != 1) return set_error(LDX_ERR_STATE, "store file: write failed");
+    const size_t n = (size_t)s->n_variants;
+    LDX_TRY(stream_out(ctx, st, s->d_planes, n * s->stride_words * sizeof(uint64_t)));
+    if (s->annotated) {
+        LDX_TRY(stream_out(ctx, st, s->d_pos0, n * 4));
+        LDX_TRY(stream_out(ctx, st, s->d_end0, n * 4));
+        LDX_TRY(stream_out(ctx, st, s->d_idnum, n * 8));
+        LDX_TRY(stream_out(ctx, st, s->d_eligible, n));
+    }
+    if (fflush(st.fh) != 0) return set_error(LDX_ERR_STATE, "store file: write failed");
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_store_load(ldx_ctx *ctx, const char *path, ldx_store **store_out) {
+    LDX_REQUIRE(ctx && path && store_out, "NULL argument");
+    *store_out = nullptr;
+    LDX_CUDA(cudaSetDevice(ctx->device));
+    Staging st;
+    st.fh = fopen(path, "rb");
+    if (!st.fh) return set_error(LDX_ERR_ARG, std::string("store file: cannot open ") + path);
+    StoreFileHeader h;
+    if (fread(&h, sizeof h, 1, st.fh) != 1 || std::memcmp(h.magic, "LDXSTOR1", 8) != 0)
+        return set_error(LDX_ERR_ARG, "store file: not an ldx store (bad magic)");
+    LDX_REQUIRE(h.n_variants >= 0 && h.n_variants < (1ll << 31) && h.n_hap > 0 && h.n_hap <= (1 << 24), "store file: bad header");
+    LDX_CUDA(cudaMallocHost(&st.buf, FILE_PIECE));
+    ldx_store *s = nullptr;
+    LDX_TRY(ldx_store_create(ctx, h.n_variants, h.n_hap, &s));
+    int rc = s->stride_words == h.stride_words ? (int)LDX_OK : set_error(LDX_ERR_ARG, "store file: row pitch of another library version");
+    const size_t n = (size_t)s->n_variants;
+    if (rc == LDX_OK) rc = stream_in(ctx, st, s->d_planes, n * s->stride_words * sizeof(uint64_t));
+    if (rc == LDX_OK && h.annotated) {
+        const size_t nv = std::max<size_t>(n, 1);
+        cudaError_t e = cudaMalloc(&s->d_pos0, nv * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_end0, nv * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_idnum, nv * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_eligible, nv);
+        if (e != cudaSuccess) { cudaGetLastError(); rc = set_error(LDX_ERR_NOMEM, "store file: annotation allocation failed"); }
+        if (rc == LDX_OK) rc = stream_in(ctx, st, s->d_pos0, n * 4);
+        if (rc == LDX_OK) rc = stream_in(ctx, st, s->d_end0, n * 4);
+        if (rc == LDX_OK) rc = stream_in(ctx, st, s->d_idnum, n * 8);
+        if (rc == LDX_OK) rc = stream_in(ctx, st, s->d_eligible, n);
+        if (rc == LDX_OK) s->annotated = true;
+    }
+    if (rc != LDX_OK) { ldx_store_destroy(s); return rc; }
+    *store_out = s;
+    return LDX_OK;
+}
+
 // ------------------------------------------------------------------------------------------ pairs
 extern "C" int32_t ldx_pairs(ldx_store *s, const int64_t *ia, const int64_t *ib, int64_t n, int32_t *n11,
                              double *d, double *dprime, double *r2, uint32_t *packed) {

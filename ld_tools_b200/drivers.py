@@ -21,7 +21,7 @@ import sqlite3
 import numpy as np
 
 from .engine import Context, Store, dprime_value, measure_value, r2_value, threshold_e4
-from ._lib import BELOW_THRES
+from ._lib import BELOW_THRES, LdxError
 
 RS_RE = re.compile(r"rs\d+$")
 
@@ -70,9 +70,75 @@ def gender_tuple(gend_names):
 
 # --------------------------------------------------------------------------- VCF ingest (one pass per chromosome)
 class ChromData:
-    """One <chrom>.vcf.gz read once: annotations on the host, genotypes as a bit-plane store in HBM."""
+    """One <chrom>.vcf.gz read once: annotations on the host, genotypes as a bit-plane store in HBM.
 
-    def __init__(self, ctx, vcf_path):
+    The packed store is also kept on disk next to the VCF (<chrom>.vcf.gz.ldxstore: planes + window annotations,
+    written by ldx_store_save; <chrom>.vcf.gz.ldxmeta.npz: the text columns the writers print), the way the
+    reference keeps its conversion.db / tabix indices there (prep_intgen_data.py:138-182): later runs skip the
+    inflate + parse + GPU packing and load 632 B per variant instead of 10 KB of text.  A cache whose recorded VCF
+    size or mtime differs from the file's is rebuilt; LDX_NO_STORE_CACHE=1 (or cache=False) ignores it."""
+
+    CACHE_VERSION = 1
+
+    def __init__(self, ctx, vcf_path, cache=True):
+        cache = cache and not os.environ.get("LDX_NO_STORE_CACHE")
+        if not (cache and self._load_cache(ctx, vcf_path)):
+            self._ingest(ctx, vcf_path)
+            if cache:
+                self._save_cache(vcf_path)
+        self.n_variants, self.n_samples = len(self.pos), len(self.samples)
+        self.max_ref_len = int((self.end0 - self.pos0).max()) if self.n_variants else 1
+        self.col_of = {n: i for i, n in enumerate(self.samples)}
+        self._row_of = {}
+        for k, (p, i) in enumerate(zip(self.pos.tolist(), self.ids)):
+            self._row_of.setdefault((p, i), k)            # first record wins, as the drivers' `break` does
+
+    # ---- cache
+    @staticmethod
+    def _cache_paths(vcf_path):
+        return vcf_path + ".ldxstore", vcf_path + ".ldxmeta.npz"
+
+    def _load_cache(self, ctx, vcf_path):
+        store_path, meta_path = self._cache_paths(vcf_path)
+        if not (os.path.exists(store_path) and os.path.exists(meta_path)):
+            return False
+        try:
+            st = os.stat(vcf_path)
+            with np.load(meta_path) as z:
+                if [int(x) for x in z["source"]] != [self.CACHE_VERSION, st.st_size, st.st_mtime_ns]:
+                    return False
+                cols = {k: bytes(z[k]).decode().split("\n") if len(z[k]) else [] for k in ("samples", "ids", "refs", "alts", "vts")}
+                self.pos = z["pos"].astype(np.int64)
+                self.multi = z["multi"].astype(bool).tolist()
+            self.samples, self.ids, self.refs, self.alts, self.vts = (cols[k] for k in ("samples", "ids", "refs", "alts", "vts"))
+            if not (len(self.ids) == len(self.refs) == len(self.alts) == len(self.vts) == len(self.multi) == len(self.pos)):
+                return False
+            self.store = Store.load(ctx, store_path)
+        except (OSError, ValueError, KeyError, LdxError):
+            return False
+        if self.store.n_variants != len(self.pos) or self.store.n_hap != 2 * len(self.samples):
+            self.store.close()
+            return False
+        self.pos0 = (self.pos - 1).astype(np.int32)
+        self.end0 = (self.pos0 + np.asarray([len(r) for r in self.refs], dtype=np.int32)).astype(np.int32)
+        return True
+
+    def _save_cache(self, vcf_path):
+        store_path, meta_path = self._cache_paths(vcf_path)
+        try:
+            st = os.stat(vcf_path)
+            self.store.save(store_path)
+            blob = {k: np.frombuffer("\n".join(v).encode(), dtype=np.uint8)
+                    for k, v in (("samples", self.samples), ("ids", self.ids), ("refs", self.refs), ("alts", self.alts), ("vts", self.vts))}
+            tmp = meta_path + ".tmp.npz"
+            np.savez(tmp, source=np.array([self.CACHE_VERSION, st.st_size, st.st_mtime_ns], dtype=np.int64), pos=self.pos,
+                     multi=np.asarray(self.multi, dtype=np.uint8), **blob)
+            os.replace(tmp, meta_path)                     # the meta file appears last and atomically: it validates the pair
+        except (OSError, LdxError):
+            pass                                           # a read-only data directory: work without the cache
+
+    # ---- first run: the VCF itself
+    def _ingest(self, ctx, vcf_path):
         with gzip.open(vcf_path, "rb") as fh:
             raw = fh.read()
         buf = np.frombuffer(raw, dtype=np.uint8)
@@ -101,25 +167,21 @@ class ChromData:
             self.vts.append(vt[0] if vt else "")
             self.multi.append("MULTI_ALLELIC" in info)
             gt_off.append(p)
-        self.n_variants, self.n_samples = len(self.pos), len(self.samples)
+        n_variants, n_samples = len(self.pos), len(self.samples)
         self.pos = np.asarray(self.pos, dtype=np.int64)
         self.pos0 = (self.pos - 1).astype(np.int32)
         self.end0 = (self.pos0 + np.asarray([len(r) for r in self.refs], dtype=np.int32)).astype(np.int32)
-        self.max_ref_len = int((self.end0 - self.pos0).max()) if self.n_variants else 1
         elig = np.array([bool(RS_RE.match(i)) and not m for i, m in zip(self.ids, self.multi)], dtype=np.uint8)
         # same-id test of ld_area.py:222 on integers: rs number, or a unique negative for non-rs ids
         idnum = np.array([int(i[2:]) if RS_RE.match(i) else -1 - k for k, i in enumerate(self.ids)], dtype=np.int64)
-        self.store = Store(ctx, self.n_variants, 2 * self.n_samples)
-        status = self.store.pack_gt(0, buf, self.n_samples, row_off=np.asarray(gt_off, dtype=np.int64))
+        self.store = Store(ctx, n_variants, 2 * n_samples)
+        status = self.store.pack_gt(0, buf, n_samples, row_off=np.asarray(gt_off, dtype=np.int64))
         if (status.astype(bool) & elig.astype(bool)).any():              # rows no driver ever pairs may be anything
             bad = int(np.flatnonzero(status.astype(bool) & elig.astype(bool))[0])
+            self.store.close()
             raise ValueError(f"{vcf_path}: record {self.ids[bad]} is not phased diploid biallelic (chrX/Y and "
                              "missing calls are outside the engine's domain, reference README.md:72)")
         self.store.set_annotations(self.pos0, self.end0, idnum, elig)
-        self.col_of = {n: i for i, n in enumerate(self.samples)}
-        self._row_of = {}
-        for k, (p, i) in enumerate(zip(self.pos.tolist(), self.ids)):
-            self._row_of.setdefault((p, i), k)            # first record wins, as the drivers' `break` does
 
     def select_samples(self, sample_names):
         """The mask plane of the chosen samples; names absent from the VCF are skipped like the

@@ -5,6 +5,7 @@ turns status codes into exceptions and decodes the packed result words into the 
 the reference returns (int `0` vs float, calc_ld.py:68-69/:89-90; round(x, 4), calc_ld.py:94-97).
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -190,6 +191,16 @@ class Store:
     def upload(self, first_row, planes):
         planes = np.ascontiguousarray(planes, dtype="<u8")
         check(self._lib.ldx_store_upload(self._h, int(first_row), planes.shape[0], ptr(planes)))
+
+    def save(self, path):
+        """Planes + annotations to one file (ldx_store_save): built once per chromosome, like the reference's cache."""
+        check(self._lib.ldx_store_save(self._h, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, ctx, path):
+        h = C.c_void_p()
+        check(ctx._lib.ldx_store_load(ctx._h, os.fsencode(path), C.byref(h)))
+        return cls(ctx, 0, 0, _handle=h)
 
     def download(self, first_row=0, n_rows=None):
         n_rows = self.n_variants - first_row if n_rows is None else n_rows

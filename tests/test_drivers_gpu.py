@@ -91,3 +91,55 @@ def test_ld_lite_printout_identical(data, ctx, name, extra):
         text = drivers.ld_lite(a, b, intgen, ctx=ctx, **kw)
         with open(os.path.join(GOLD, name, f"pair{k}.txt")) as fh:
             assert text + "\n" == fh.read()
+
+
+def test_store_cache_round_trip_and_staleness(data, ctx, monkeypatch):
+    """The packed store kept next to the VCF (ldx_store_save / ldx_store_load + the text columns): a second run
+    loads it instead of re-reading the VCF and sees exactly the same data; a VCF that changed invalidates it."""
+    import numpy as np
+    from ld_tools_b200 import drivers
+    root, intgen, srcs = data
+    vcf = os.path.join(intgen, "22.vcf.gz")
+    paths = drivers.ChromData._cache_paths(vcf)
+    for p in paths:
+        if os.path.exists(p):
+            os.remove(p)
+    fresh = drivers.ChromData(ctx, vcf, cache=False)
+    assert not any(os.path.exists(p) for p in paths)
+    first = drivers.ChromData(ctx, vcf)                      # ingests and writes the cache
+    assert all(os.path.exists(p) for p in paths)
+    ingests = []
+    real_ingest = drivers.ChromData._ingest
+    monkeypatch.setattr(drivers.ChromData, "_ingest", lambda self, c, p: (ingests.append(p), real_ingest(self, c, p))[1])
+    cached = drivers.ChromData(ctx, vcf)                     # must come from the cache
+    assert ingests == []
+    for cd in (first, cached):
+        assert (cd.store.download() == fresh.store.download()).all()
+        assert cd.samples == fresh.samples and cd.ids == fresh.ids and cd.refs == fresh.refs and cd.alts == fresh.alts
+        assert cd.vts == fresh.vts and list(cd.multi) == list(fresh.multi)
+        assert (cd.pos == fresh.pos).all() and (cd.pos0 == fresh.pos0).all() and (cd.end0 == fresh.end0).all()
+        assert cd.max_ref_len == fresh.max_ref_len and cd.n_samples == fresh.n_samples
+    # the annotations travelled with the planes: the same window scan on both
+    names = fresh.samples[::3]
+    q = np.flatnonzero([bool(drivers.RS_RE.match(i)) and not m for i, m in zip(fresh.ids, fresh.multi)])[5:25]
+    from ld_tools_b200 import shard
+    lo, hi, ws, we = shard.window_bounds(fresh.pos0, fresh.max_ref_len, fresh.pos[q], 3000)
+    hits = []
+    for cd in (fresh, cached):
+        cd.select_samples(names)
+        hits.append(cd.store.window(q, lo, hi, ws, we, "r_square", 0)[0])
+    assert len(hits[0]) > 0 and (hits[0] == hits[1]).all()
+    # a VCF with another mtime: the cache is stale and the file is read again
+    st = os.stat(vcf)
+    os.utime(vcf, ns=(st.st_atime_ns, st.st_mtime_ns + 1_000_000_000))
+    again = drivers.ChromData(ctx, vcf)
+    assert ingests == [vcf]
+    assert (again.store.download() == fresh.store.download()).all()
+    # a truncated store file is refused (and rebuilt), never half-loaded
+    with open(paths[0], "r+b") as fh:
+        fh.truncate(os.path.getsize(paths[0]) // 2)
+    rebuilt = drivers.ChromData(ctx, vcf)
+    assert ingests == [vcf, vcf]
+    assert (rebuilt.store.download() == fresh.store.download()).all()
+    for cd in (fresh, first, cached, again, rebuilt):
+        cd.close()

@@ -155,6 +155,33 @@ int32_t ldx_store_planes_ptr(const ldx_store *store, void **dev_ptr_out);
 int32_t ldx_store_pack_gt(ldx_store *store, int64_t first_row, int64_t n_rows, const uint8_t *text,
                           int64_t text_bytes, const int64_t *row_off, int64_t row_pitch,
                           int32_t n_samples, uint8_t *row_status);
+/* ---------------------------------------------------------------- VCF text -> store, on the GPU
+ * Replaces the per-record pysam access of the drivers (rec.pos / .id / .ref / .info / .samples[..]['GT'],
+ * ld_area.py:215-235, ld_triangle.py:128-186) and the Python per-line loop an ingest would otherwise need.
+ * `text` = a whole decompressed VCF (host memory; '##' / '#CHROM' lines are skipped, every other line is a
+ * record: nine tab-separated fixed columns, then n_samples "a|b" genotype columns).  One upload; kernels
+ * build the newline index, parse every line (POS, len(REF), the rs number, the MULTI_ALLELIC INFO key),
+ * write the window annotations (pos0, end0, idnum, eligible = rs\d+$ and not MULTI_ALLELIC,
+ * ld_area.py:222-225) into a NEW store and bit-pack the genotypes (K1).  rows_out[rows_cap] receives one
+ * record per variant in file order (= store row); *n_rows_out = their number (LDX_ERR_CAPACITY if > rows_cap).
+ * status: bit 0 = a genotype outside {0|0,0|1,1|0,1|1} (packed with non-'1' as 0), bit 1 = fewer than 9 + n_samples
+ * columns (row kept, all-reference, not eligible), bit 2 = POS is not a number. */
+typedef struct ldx_vcf_row {
+    int64_t line_off;                 /* byte offset of the line in the text */
+    int64_t idnum;                    /* digits of an rs\d+ ID, else -1 - row */
+    int32_t gt_off, id_off, ref_off, alt_off, info_off, fmt_off;   /* field starts, relative to line_off */
+    int32_t pos;                      /* POS, 1-based */
+    int32_t ref_len;                  /* len(REF): the record covers [pos - 1, pos - 1 + ref_len) (pysam fetch overlap) */
+    uint8_t status, eligible, multi, pad[5];
+} ldx_vcf_row;
+int32_t ldx_store_ingest_vcf(ldx_ctx *ctx, const uint8_t *text, int64_t text_bytes, int32_t n_samples,
+                             ldx_store **store_out, ldx_vcf_row *rows_out, int64_t rows_cap, int64_t *n_rows_out);
+/* Host helper: the fixed columns of every record back to back (record r = out[off_out[r], off_out[r+1]); off_out has
+ * n_rows + 1 entries), so that the caller can drop the text and still print ID / REF / ALT / INFO of the rows it
+ * reports.  out == NULL: only off_out is filled (size query). */
+int32_t ldx_vcf_copy_prefixes(const uint8_t *text, int64_t text_bytes, const ldx_vcf_row *rows, int64_t n_rows,
+                              uint8_t *out, int64_t out_cap, int64_t *off_out);
+
 /* Load / read back ready-made planes (host, [n_rows][stride_words] uint64). */
 int32_t ldx_store_upload(ldx_store *store, int64_t first_row, int64_t n_rows, const uint64_t *planes);
 int32_t ldx_store_download(const ldx_store *store, int64_t first_row, int64_t n_rows, uint64_t *planes);

@@ -16,6 +16,9 @@ TUNE_MMA_TILE_N, TUNE_MMA_MIN_V, TUNE_MMA_PAIR, TUNE_DEFER_CAP = 1, 2, 3, 4
 R2_MASK, R2_INT0, DP_SHIFT, DP_MASK, BELOW_THRES, DP_INT0 = 0x3FFF, 0x8000, 16, 0x3FFF0000, 0x40000000, 0x80000000
 
 HIT_DTYPE = np.dtype([("query", "<i4"), ("row", "<i4"), ("n11", "<i4"), ("packed", "<u4")])
+VCF_ROW_DTYPE = np.dtype([("line_off", "<i8"), ("idnum", "<i8"), ("gt_off", "<i4"), ("id_off", "<i4"), ("ref_off", "<i4"),
+                          ("alt_off", "<i4"), ("info_off", "<i4"), ("fmt_off", "<i4"), ("pos", "<i4"), ("ref_len", "<i4"),
+                          ("status", "u1"), ("eligible", "u1"), ("multi", "u1"), ("pad", "u1", (5,))])
 LD_RESULT_DTYPE = np.dtype([
     ("n_hap", "<i8"), ("n_11", "<i8"), ("n_a1", "<i8"), ("n_a0", "<i8"), ("n_b1", "<i8"), ("n_b0", "<i8"),
     ("d", "<f8"), ("dprime", "<f8"), ("r2", "<f8"), ("p_a", "<f8"), ("p_b", "<f8"),
@@ -54,6 +57,8 @@ SIGNATURES = {
     "ldx_store_shape": [_vp, _P(_i64), _P(_i32), _P(_i32)],
     "ldx_store_planes_ptr": [_vp, _P(_vp)],
     "ldx_store_pack_gt": [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _i32, _vp],
+    "ldx_store_ingest_vcf": [_vp, _vp, _i64, _i32, _P(_vp), _vp, _i64, _P(_i64)],
+    "ldx_vcf_copy_prefixes": [_vp, _i64, _vp, _i64, _vp, _i64, _vp],
     "ldx_store_upload": [_vp, _i64, _i64, _vp],
     "ldx_store_download": [_vp, _i64, _i64, _vp],
     "ldx_store_save": [_vp, C.c_char_p],

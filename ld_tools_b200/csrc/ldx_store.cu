@@ -39,6 +39,11 @@ pack_gt_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row
     const int n_words_data = (2 * n_samples + 63) / 64;
     for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
         const int64_t off = row_off ? row_off[r] : r * row_pitch;
+        if (off < 0) {                               // a row without genotype text (ldx_store_ingest_vcf: malformed line): all reference
+            for (int w = threadIdx.x; w < stride_words; w += PACK_THREADS) planes[r * (int64_t)stride_words + w] = 0;
+            if (threadIdx.x == 0 && status) status[r] = 0;
+            continue;                                // block-uniform
+        }
         const int64_t aligned = off & ~15ll;
         const int skew = (int)(off - aligned);
         const int n_gran = (int)((skew + row_bytes + 15) >> 4);

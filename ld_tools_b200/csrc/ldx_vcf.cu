@@ -1,0 +1,308 @@
+// ldx_vcf.cu -- GPU-side indexing of decompressed VCF text (the ingest path).
+//
+// The reference reaches a record's fields through pysam, one record at a time: rec.pos / rec.id / rec.ref /
+// rec.info / rec.samples[name]['GT'] (ld_area.py:215-235, ld_triangle.py:128-186, prep_intgen_data.py:163-177).
+// Here the whole decompressed <chrom>.vcf is uploaded once and four small kernels do what a per-line host loop
+// would: (1) newline index, (2) one thread per line finds the nine fixed columns and parses what the fused
+// ld_area filters need -- POS, len(REF), the rs number, the MULTI_ALLELIC key -- (3) the records are compacted
+// and their annotations written straight into the store, (4) K1 (pack_gt_kernel) bit-packs the genotype
+// columns from the same device copy of the text.  The host gets back one fixed-size record per variant (field
+// offsets included, so that the text columns the writers print can be sliced lazily).
+//
+// All of it is byte work bound by the one pass over the text (10 KB per 2504-sample variant): the upload over
+// PCIe is the limit, not the kernels.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "ldx_internal.h"
+
+#define LDX_TRY(expr) do { int rc__ = (expr); if (rc__ != LDX_OK) return rc__; } while (0)
+#define LDX_REQUIRE(cond, msg) do { if (!(cond)) return ldx::set_error(LDX_ERR_ARG, msg); } while (0)
+
+namespace ldx {
+
+constexpr int NL_THREADS = 256, NL_BYTES_PER_THREAD = 64, NL_BLOCK_BYTES = NL_THREADS * NL_BYTES_PER_THREAD;
+
+__device__ __forceinline__ int count_nl_64(const uint8_t *__restrict__ text, int64_t begin, int64_t n) {
+    int c = 0;
+    if (begin + NL_BYTES_PER_THREAD <= n) {                 // whole 64-byte run: four 16-byte loads (begin is 64-aligned)
+        const uint4 *p = reinterpret_cast<const uint4 *>(text + begin);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint4 v = __ldg(p + g);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t x = w[k] ^ 0x0a0a0a0au;        // zero byte <=> newline
+                c += __popc(((x - 0x01010101u) & ~x & 0x80808080u));
+            }
+        }
+        // the borrow trick can flag the byte above a true zero byte (0x01 after 0x00): recount exactly when anything was found
+        if (c) {
+            c = 0;
+            for (int i = 0; i < NL_BYTES_PER_THREAD; ++i) c += text[begin + i] == '\n';
+        }
+    } else {
+        for (int64_t i = begin; i < n; ++i) c += text[i] == '\n';
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(NL_THREADS)
+count_newlines_kernel(const uint8_t *__restrict__ text, int64_t n, uint32_t *__restrict__ block_counts) {
+    using BlockReduce = cub::BlockReduce<int, NL_THREADS>;
+    __shared__ typename BlockReduce::TempStorage tmp;
+    const int64_t begin = (int64_t)blockIdx.x * NL_BLOCK_BYTES + (int64_t)threadIdx.x * NL_BYTES_PER_THREAD;
+    const int c = begin < n ? count_nl_64(text, begin, n) : 0;
+    const int total = BlockReduce(tmp).Sum(c);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)total;
+}
+
+__global__ void __launch_bounds__(NL_THREADS)
+write_newlines_kernel(const uint8_t *__restrict__ text, int64_t n, const uint32_t *__restrict__ block_base, int64_t *__restrict__ nl) {
+    using BlockScan = cub::BlockScan<int, NL_THREADS>;
+    __shared__ typename BlockScan::TempStorage tmp;
+    const int64_t begin = (int64_t)blockIdx.x * NL_BLOCK_BYTES + (int64_t)threadIdx.x * NL_BYTES_PER_THREAD;
+    const int c = begin < n ? count_nl_64(text, begin, n) : 0;
+    int base;
+    BlockScan(tmp).ExclusiveSum(c, base);
+    if (c) {
+        int64_t *out = nl + block_base[blockIdx.x] + base;
+        const int64_t end = begin + NL_BYTES_PER_THREAD < n ? begin + NL_BYTES_PER_THREAD : n;
+        for (int64_t i = begin; i < end; ++i)
+            if (text[i] == '\n') *out++ = i;
+    }
+}
+
+// One thread per line.  Line k is text[start, end) with start = nl[k-1] + 1, end = nl[k] (the newline).
+__global__ void __launch_bounds__(256)
+parse_lines_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ nl, int64_t n_lines, int32_t n_samples,
+                   ldx_vcf_row *__restrict__ tmp_rows, uint32_t *__restrict__ is_rec) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_lines) return;
+    const int64_t start = k ? nl[k - 1] + 1 : 0;
+    int64_t end = nl[k];
+    if (end > start && text[end - 1] == '\r') --end;
+    if (end <= start || text[start] == '#') { is_rec[k] = 0; return; }
+    ldx_vcf_row r;
+    r.line_off = start;
+    r.idnum = -1;
+    r.status = 0; r.eligible = 0; r.multi = 0;
+    r.pad[0] = r.pad[1] = r.pad[2] = r.pad[3] = r.pad[4] = 0;
+    int32_t field_off[10];
+    int nf = 1;
+    field_off[0] = 0;
+    for (int64_t i = start; i < end && nf < 10; ++i)
+        if (text[i] == '\t') field_off[nf++] = (int32_t)(i + 1 - start);
+    const int64_t need = nf == 10 ? (int64_t)field_off[9] + 4ll * n_samples - 1 : 0;
+    if (nf < 10 || need > end - start) {
+        // not a full record line: kept as a row (the drivers' row numbering follows the file) and flagged
+        r.status = 2;
+        for (int f = nf; f < 10; ++f) field_off[f] = (int32_t)(end - start);
+    }
+    r.id_off = field_off[2]; r.ref_off = field_off[3]; r.alt_off = field_off[4]; r.info_off = field_off[7];
+    r.fmt_off = field_off[8]; r.gt_off = field_off[9];
+    // POS
+    int64_t pos = 0;
+    for (int32_t i = field_off[1]; i < field_off[2] - 1; ++i) {
+        const uint8_t c = text[start + i];
+        if (c < '0' || c > '9' || pos > 214748363) { pos = 0; r.status |= 4; break; }
+        pos = pos * 10 + (c - '0');
+    }
+    r.pos = (int32_t)pos;
+    r.ref_len = max(field_off[4] - 1 - field_off[3], 0);
+    // ID: rs\d+$ (ld_area.py:223, prep_intgen_data.py:166)
+    {
+        const int32_t a = field_off[2], b = field_off[3] - 1;
+        bool rs = b - a >= 3 && b - a <= 20 && text[start + a] == 'r' && text[start + a + 1] == 's';
+        int64_t num = 0;
+        for (int32_t i = a + 2; rs && i < b; ++i) {
+            const uint8_t c = text[start + i];
+            if (c < '0' || c > '9') rs = false; else num = num * 10 + (c - '0');
+        }
+        if (rs) r.idnum = num;
+        r.eligible = rs ? 1 : 0;
+    }
+    // INFO: the MULTI_ALLELIC key (ld_area.py:224 `'MULTI_ALLELIC' in rec.info`): a ';'-delimited key, with or without a value
+    {
+        const char key[] = "MULTI_ALLELIC";
+        const int32_t a = field_off[7], b = field_off[8] - 1;
+        bool at_key = true;
+        for (int32_t i = a; i < b; ++i) {
+            if (at_key && b - i >= 13) {
+                bool m = true;
+                for (int j = 0; j < 13; ++j) m &= text[start + i + j] == (uint8_t)key[j];
+                if (m && (i + 13 == b || text[start + i + 13] == ';' || text[start + i + 13] == '=')) { r.multi = 1; break; }
+            }
+            at_key = text[start + i] == ';';
+        }
+        if (r.multi || r.status) r.eligible = 0;
+    }
+    tmp_rows[k] = r;
+    is_rec[k] = 1;
+}
+
+// Record lines -> dense rows; the window annotations go straight into the store's device arrays.
+__global__ void __launch_bounds__(256)
+compact_rows_kernel(const ldx_vcf_row *__restrict__ tmp_rows, const uint32_t *__restrict__ is_rec, const uint32_t *__restrict__ rec_index,
+                    int64_t n_lines, ldx_vcf_row *__restrict__ rows, int64_t *__restrict__ gt_abs, int32_t *__restrict__ pos0,
+                    int32_t *__restrict__ end0, int64_t *__restrict__ idnum, uint8_t *__restrict__ eligible) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_lines || !is_rec[k]) return;
+    const int64_t row = rec_index[k];
+    ldx_vcf_row r = tmp_rows[k];
+    if (r.idnum < 0) r.idnum = -1 - row;                       // unique per row: never equal to a query's id (ld_area.py:222)
+    rows[row] = r;
+    gt_abs[row] = (r.status & 2) ? -1 : r.line_off + r.gt_off;
+    pos0[row] = r.pos - 1;
+    end0[row] = r.pos - 1 + r.ref_len;
+    idnum[row] = r.idnum;
+    eligible[row] = r.eligible;
+}
+
+// pack status (bit 0) and zeroed planes of malformed rows
+__global__ void __launch_bounds__(256)
+merge_status_kernel(ldx_vcf_row *__restrict__ rows, const uint8_t *__restrict__ pack_status, int64_t n_rows) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_rows && !(rows[r].status & 2)) rows[r].status |= pack_status[r] & 1;
+}
+
+int launch_pack_gt(ldx_ctx *ctx, const uint8_t *d_text, const int64_t *d_row_off, int64_t row_pitch, int64_t n_rows, int32_t n_samples,
+                   uint64_t *d_planes_first, int32_t stride_words, uint8_t *d_status);
+
+struct DevBuf {                 // scratch of one ingest call, freed on every exit path
+    std::vector<void *> p;
+    ~DevBuf() { for (void *q : p) cudaFree(q); }
+    template <typename T> int get(T **out, size_t n) {
+        void *q = nullptr;
+        if (cudaMalloc(&q, std::max<size_t>(n * sizeof(T), 16)) != cudaSuccess) { cudaGetLastError(); return set_error(LDX_ERR_NOMEM, "vcf ingest: device scratch allocation failed"); }
+        p.push_back(q);
+        *out = reinterpret_cast<T *>(q);
+        return LDX_OK;
+    }
+};
+
+}  // namespace ldx
+
+using namespace ldx;
+
+extern "C" int32_t ldx_store_ingest_vcf(ldx_ctx *ctx, const uint8_t *text, int64_t text_bytes, int32_t n_samples,
+                                        ldx_store **store_out, ldx_vcf_row *rows_out, int64_t rows_cap, int64_t *n_rows_out) {
+    LDX_REQUIRE(ctx && text && store_out && n_rows_out, "NULL argument");
+    LDX_REQUIRE(text_bytes > 0 && n_samples > 0 && n_samples <= (1 << 23), "bad text size or sample count");
+    LDX_REQUIRE(rows_cap >= 0 && (rows_out || rows_cap == 0), "bad rows buffer");
+    *store_out = nullptr; *n_rows_out = 0;
+    LDX_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevBuf scratch;
+    // ---- the text, once, with a final newline and slack for K1's aligned 16-byte loads
+    const bool add_nl = text[text_bytes - 1] != '\n';
+    const int64_t n = text_bytes + (add_nl ? 1 : 0);
+    uint8_t *d_text = nullptr;
+    LDX_TRY(scratch.get(&d_text, (size_t)n + 64));
+    LDX_CUDA(cudaMemcpyAsync(d_text, text, (size_t)text_bytes, cudaMemcpyHostToDevice, st));
+    LDX_CUDA(cudaMemsetAsync(d_text + text_bytes, '\n', (size_t)(n - text_bytes) + 64, st));
+    // ---- newline index
+    const int64_t n_blocks = (n + NL_BLOCK_BYTES - 1) / NL_BLOCK_BYTES;
+    LDX_REQUIRE(n_blocks < (1ll << 31), "vcf ingest: text too large for one call");
+    uint32_t *d_counts = nullptr, *d_base = nullptr;
+    LDX_TRY(scratch.get(&d_counts, (size_t)n_blocks + 1));
+    LDX_TRY(scratch.get(&d_base, (size_t)n_blocks + 1));
+    LDX_CUDA(cudaMemsetAsync(d_counts + n_blocks, 0, sizeof(uint32_t), st));
+    count_newlines_kernel<<<(unsigned)n_blocks, NL_THREADS, 0, st>>>(d_text, n, d_counts);
+    ctx->launches++;
+    LDX_CUDA(cudaGetLastError());
+    size_t cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, d_counts, d_base, (int)(n_blocks + 1), st);
+    size_t cub_bytes2 = 0;
+    void *d_cub;
+    {   // one temp block serves both scans (the second is over lines: sized below once their number is known)
+        LDX_TRY(scratch.get(reinterpret_cast<uint8_t **>(&d_cub), cub_bytes));
+    }
+    LDX_CUDA(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_counts, d_base, (int)(n_blocks + 1), st));
+    uint32_t n_lines32 = 0;
+    LDX_CUDA(cudaMemcpyAsync(&n_lines32, d_base + n_blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    LDX_CUDA(cudaStreamSynchronize(st));
+    const int64_t n_lines = n_lines32;
+    LDX_REQUIRE(n_lines > 0 && n_lines < (1ll << 31), "vcf ingest: no lines");
+    int64_t *d_nl;
+    LDX_TRY(scratch.get(&d_nl, (size_t)n_lines));
+    write_newlines_kernel<<<(unsigned)n_blocks, NL_THREADS, 0, st>>>(d_text, n, d_base, d_nl);
+    ctx->launches++;
+    LDX_CUDA(cudaGetLastError());
+    // ---- per-line parse, record numbering
+    ldx_vcf_row *d_tmp;
+    uint32_t *d_isrec, *d_recidx;
+    LDX_TRY(scratch.get(&d_tmp, (size_t)n_lines));
+    LDX_TRY(scratch.get(&d_isrec, (size_t)n_lines + 1));
+    LDX_TRY(scratch.get(&d_recidx, (size_t)n_lines + 1));
+    LDX_CUDA(cudaMemsetAsync(d_isrec + n_lines, 0, sizeof(uint32_t), st));
+    const unsigned lgrid = (unsigned)((n_lines + 255) / 256);
+    parse_lines_kernel<<<lgrid, 256, 0, st>>>(d_text, d_nl, n_lines, n_samples, d_tmp, d_isrec);
+    ctx->launches++;
+    LDX_CUDA(cudaGetLastError());
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes2, d_isrec, d_recidx, (int)(n_lines + 1), st);
+    void *d_cub2;
+    LDX_TRY(scratch.get(reinterpret_cast<uint8_t **>(&d_cub2), cub_bytes2));
+    LDX_CUDA(cub::DeviceScan::ExclusiveSum(d_cub2, cub_bytes2, d_isrec, d_recidx, (int)(n_lines + 1), st));
+    uint32_t n_rec32 = 0;
+    LDX_CUDA(cudaMemcpyAsync(&n_rec32, d_recidx + n_lines, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    LDX_CUDA(cudaStreamSynchronize(st));
+    const int64_t n_rec = n_rec32;
+    *n_rows_out = n_rec;
+    if (n_rec > rows_cap) return set_error(LDX_ERR_CAPACITY, "vcf ingest: rows buffer too small");
+    // ---- the store, its annotations, the genotype planes
+    ldx_store *s = nullptr;
+    LDX_TRY(ldx_store_create(ctx, n_rec, 2 * n_samples, &s));
+    int rc = LDX_OK;
+    {
+        const size_t nv = (size_t)std::max<int64_t>(n_rec, 1);
+        cudaError_t e = cudaMalloc(&s->d_pos0, nv * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_end0, nv * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_idnum, nv * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_eligible, nv);
+        if (e != cudaSuccess) { cudaGetLastError(); rc = set_error(LDX_ERR_NOMEM, "vcf ingest: annotation allocation failed"); }
+    }
+    ldx_vcf_row *d_rows = nullptr; int64_t *d_gt = nullptr; uint8_t *d_status = nullptr;
+    if (rc == LDX_OK) rc = scratch.get(&d_rows, (size_t)n_rec);
+    if (rc == LDX_OK) rc = scratch.get(&d_gt, (size_t)n_rec);
+    if (rc == LDX_OK) rc = scratch.get(&d_status, (size_t)n_rec);
+    if (rc == LDX_OK && n_rec > 0) {
+        compact_rows_kernel<<<lgrid, 256, 0, st>>>(d_tmp, d_isrec, d_recidx, n_lines, d_rows, d_gt, s->d_pos0, s->d_end0, s->d_idnum, s->d_eligible);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = set_error(LDX_ERR_CUDA, "vcf ingest: compact launch failed");
+    }
+    if (rc == LDX_OK && n_rec > 0) rc = launch_pack_gt(ctx, d_text, d_gt, 0, n_rec, n_samples, s->d_planes, s->stride_words, d_status);   // rows with offset -1: zeros
+    if (rc == LDX_OK && n_rec > 0) {
+        merge_status_kernel<<<(unsigned)((n_rec + 255) / 256), 256, 0, st>>>(d_rows, d_status, n_rec);
+        ctx->launches++;
+        if (cudaMemcpyAsync(rows_out, d_rows, sizeof(ldx_vcf_row) * (size_t)n_rec, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            rc = cuda_fail(cudaGetLastError(), "vcf ingest: rows download");
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == LDX_OK) rc = cuda_fail(cudaGetLastError(), "vcf ingest");
+    if (rc != LDX_OK) { ldx_store_destroy(s); return rc; }
+    s->annotated = true;
+    *store_out = s;
+    return LDX_OK;
+}
+
+/* Host helper: the nine fixed columns of every record, back to back (record r = out[off[r], off[r+1])), so that the
+ * caller can drop the multi-gigabyte text and still print ID / REF / ALT / INFO of the rows it reports. */
+extern "C" int32_t ldx_vcf_copy_prefixes(const uint8_t *text, int64_t text_bytes, const ldx_vcf_row *rows, int64_t n_rows,
+                                         uint8_t *out, int64_t out_cap, int64_t *off_out) {
+    LDX_REQUIRE(text && (rows || n_rows == 0) && off_out && n_rows >= 0, "bad argument");
+    int64_t total = 0;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        off_out[r] = total;
+        LDX_REQUIRE(rows[r].line_off >= 0 && rows[r].gt_off >= 0 && rows[r].line_off + rows[r].gt_off <= text_bytes, "row outside the text");
+        total += rows[r].gt_off;
+    }
+    off_out[n_rows] = total;
+    if (!out) return LDX_OK;                                     // size query
+    if (total > out_cap) return set_error(LDX_ERR_CAPACITY, "prefix buffer too small");
+    for (int64_t r = 0; r < n_rows; ++r) std::memcpy(out + off_out[r], text + rows[r].line_off, (size_t)rows[r].gt_off);
+    return LDX_OK;
+}

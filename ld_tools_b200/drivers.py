@@ -21,7 +21,7 @@ import sqlite3
 import numpy as np
 
 from .engine import Context, Store, dprime_value, measure_value, r2_value, threshold_e4
-from ._lib import BELOW_THRES, LdxError
+from ._lib import BELOW_THRES, VCF_ROW_DTYPE, LdxError
 
 RS_RE = re.compile(r"rs\d+$")
 
@@ -69,6 +69,32 @@ def gender_tuple(gend_names):
 
 
 # --------------------------------------------------------------------------- VCF ingest (one pass per chromosome)
+class _Column:
+    """One text column of the records (ID, REF, ALT or the VT key of INFO), sliced on demand from the fixed columns
+    the ingest kept: only the rows a driver reports are ever decoded."""
+
+    def __init__(self, cd, field, vt=False):
+        self.cd, self.field, self.vt = cd, field, vt
+
+    def __len__(self):
+        return self.cd.rows.shape[0]
+
+    def __getitem__(self, k):
+        cd = self.cd
+        if k < 0:
+            k += len(self)
+        a = int(cd._off[k]) + int(cd.rows[self.field][k])
+        b = cd._blob.find(b"\t", a, int(cd._off[k + 1]))
+        text = cd._blob[a:b if b >= 0 else int(cd._off[k + 1])].decode()
+        if not self.vt:
+            return text
+        vt = [x[3:] for x in text.split(";") if x.startswith("VT=")]        # ld_area.py:233 rec.info['VT']
+        return vt[0] if vt else ""
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self)))
+
+
 class ChromData:
     """One <chrom>.vcf.gz read once: annotations on the host, genotypes as a bit-plane store in HBM.
 
@@ -78,7 +104,7 @@ class ChromData:
     inflate + parse + GPU packing and load 632 B per variant instead of 10 KB of text.  A cache whose recorded VCF
     size or mtime differs from the file's is rebuilt; LDX_NO_STORE_CACHE=1 (or cache=False) ignores it."""
 
-    CACHE_VERSION = 1
+    CACHE_VERSION = 2
 
     def __init__(self, ctx, vcf_path, cache=True):
         cache = cache and not os.environ.get("LDX_NO_STORE_CACHE")
@@ -107,20 +133,18 @@ class ChromData:
             with np.load(meta_path) as z:
                 if [int(x) for x in z["source"]] != [self.CACHE_VERSION, st.st_size, st.st_mtime_ns]:
                     return False
-                cols = {k: bytes(z[k]).decode().split("\n") if len(z[k]) else [] for k in ("samples", "ids", "refs", "alts", "vts")}
-                self.pos = z["pos"].astype(np.int64)
-                self.multi = z["multi"].astype(bool).tolist()
-            self.samples, self.ids, self.refs, self.alts, self.vts = (cols[k] for k in ("samples", "ids", "refs", "alts", "vts"))
-            if not (len(self.ids) == len(self.refs) == len(self.alts) == len(self.vts) == len(self.multi) == len(self.pos)):
+                samples = bytes(z["samples"]).decode().split("\n") if len(z["samples"]) else []
+                rows = np.frombuffer(bytes(z["rows"]), dtype=VCF_ROW_DTYPE).copy()
+                blob, off = bytes(z["blob"]), z["off"].astype(np.int64)
+            if off.shape[0] != rows.shape[0] + 1 or (rows.shape[0] and int(off[-1]) != len(blob)):
                 return False
             self.store = Store.load(ctx, store_path)
         except (OSError, ValueError, KeyError, LdxError):
             return False
-        if self.store.n_variants != len(self.pos) or self.store.n_hap != 2 * len(self.samples):
+        if self.store.n_variants != rows.shape[0] or self.store.n_hap != 2 * len(samples):
             self.store.close()
             return False
-        self.pos0 = (self.pos - 1).astype(np.int32)
-        self.end0 = (self.pos0 + np.asarray([len(r) for r in self.refs], dtype=np.int32)).astype(np.int32)
+        self._set_columns(samples, rows, blob, off)
         return True
 
     def _save_cache(self, vcf_path):
@@ -128,60 +152,48 @@ class ChromData:
         try:
             st = os.stat(vcf_path)
             self.store.save(store_path)
-            blob = {k: np.frombuffer("\n".join(v).encode(), dtype=np.uint8)
-                    for k, v in (("samples", self.samples), ("ids", self.ids), ("refs", self.refs), ("alts", self.alts), ("vts", self.vts))}
             tmp = meta_path + ".tmp.npz"
-            np.savez(tmp, source=np.array([self.CACHE_VERSION, st.st_size, st.st_mtime_ns], dtype=np.int64), pos=self.pos,
-                     multi=np.asarray(self.multi, dtype=np.uint8), **blob)
+            np.savez(tmp, source=np.array([self.CACHE_VERSION, st.st_size, st.st_mtime_ns], dtype=np.int64),
+                     samples=np.frombuffer("\n".join(self.samples).encode(), dtype=np.uint8),
+                     rows=np.frombuffer(self.rows.tobytes(), dtype=np.uint8), blob=np.frombuffer(self._blob, dtype=np.uint8),
+                     off=self._off)
             os.replace(tmp, meta_path)                     # the meta file appears last and atomically: it validates the pair
         except (OSError, LdxError):
             pass                                           # a read-only data directory: work without the cache
 
-    # ---- first run: the VCF itself
+    def _set_columns(self, samples, rows, blob, off):
+        """rows: one VCF_ROW_DTYPE record per variant (parsed on the GPU); blob/off: the records' fixed columns."""
+        self.samples, self.rows, self._blob, self._off = samples, rows, blob, off
+        self.pos = rows["pos"].astype(np.int64)
+        self.pos0 = (self.pos - 1).astype(np.int32)
+        self.end0 = (self.pos0 + rows["ref_len"]).astype(np.int32)
+        self.multi = rows["multi"].astype(bool)
+        self.ids, self.refs, self.alts = _Column(self, "id_off"), _Column(self, "ref_off"), _Column(self, "alt_off")
+        self.vts = _Column(self, "info_off", vt=True)
+
+    # ---- first run: the VCF itself.  The host only inflates the file and reads the #CHROM line; splitting lines and
+    #      fields, parsing POS / ID / REF / INFO and packing the genotypes all happen on the GPU (ldx_store_ingest_vcf).
     def _ingest(self, ctx, vcf_path):
         with gzip.open(vcf_path, "rb") as fh:
             raw = fh.read()
-        buf = np.frombuffer(raw, dtype=np.uint8)
-        nl = np.flatnonzero(buf == 10)
-        starts = np.concatenate([[0], nl[:-1] + 1]) if len(nl) else np.zeros(0, np.int64)
-        self.samples, self.pos, self.ids, self.refs, self.alts, self.vts, self.multi = [], [], [], [], [], [], []
-        gt_off = []
-        for s, e in zip(starts.tolist(), nl.tolist()):
-            if raw[s:s + 2] == b"##":
-                continue
-            if raw[s:s + 1] == b"#":
-                self.samples = raw[s:e].decode().split("\t")[9:]
-                continue
-            # the nine fixed columns; the GT columns stay bytes for the GPU packer
-            p, fields = s, []
-            for _ in range(9):
-                q = raw.index(b"\t", p, e)
-                fields.append(raw[p:q])
-                p = q + 1
-            info = fields[7].decode().split(";")
-            self.pos.append(int(fields[1]))
-            self.ids.append(fields[2].decode())
-            self.refs.append(fields[3].decode())
-            self.alts.append(fields[4].decode())
-            vt = [x[3:] for x in info if x.startswith("VT=")]
-            self.vts.append(vt[0] if vt else "")
-            self.multi.append("MULTI_ALLELIC" in info)
-            gt_off.append(p)
-        n_variants, n_samples = len(self.pos), len(self.samples)
-        self.pos = np.asarray(self.pos, dtype=np.int64)
-        self.pos0 = (self.pos - 1).astype(np.int32)
-        self.end0 = (self.pos0 + np.asarray([len(r) for r in self.refs], dtype=np.int32)).astype(np.int32)
-        elig = np.array([bool(RS_RE.match(i)) and not m for i, m in zip(self.ids, self.multi)], dtype=np.uint8)
-        # same-id test of ld_area.py:222 on integers: rs number, or a unique negative for non-rs ids
-        idnum = np.array([int(i[2:]) if RS_RE.match(i) else -1 - k for k, i in enumerate(self.ids)], dtype=np.int64)
-        self.store = Store(ctx, n_variants, 2 * n_samples)
-        status = self.store.pack_gt(0, buf, n_samples, row_off=np.asarray(gt_off, dtype=np.int64))
-        if (status.astype(bool) & elig.astype(bool)).any():              # rows no driver ever pairs may be anything
-            bad = int(np.flatnonzero(status.astype(bool) & elig.astype(bool))[0])
+        h = 0 if raw.startswith(b"#CHROM") else raw.find(b"\n#CHROM") + 1
+        if h == 0 and not raw.startswith(b"#CHROM"):
+            raise ValueError(f"{vcf_path}: no #CHROM header line")
+        e = raw.find(b"\n", h)
+        samples = raw[h:e if e >= 0 else len(raw)].decode().rstrip("\r").split("\t")[9:]
+        if not samples:
+            raise ValueError(f"{vcf_path}: no sample columns")
+        self.store, rows = Store.ingest_vcf(ctx, raw, len(samples), rows_cap=raw.count(b"\n") + 1)
+        bad = np.flatnonzero((rows["status"] != 0) & ((rows["eligible"] != 0) | ((rows["status"] & 6) != 0)))
+        if len(bad):                                                       # rows no driver ever pairs may be anything
+            k = int(bad[0])
+            line = raw[rows["line_off"][k]:rows["line_off"][k] + 60].decode(errors="replace")
             self.store.close()
-            raise ValueError(f"{vcf_path}: record {self.ids[bad]} is not phased diploid biallelic (chrX/Y and "
+            raise ValueError(f"{vcf_path}: record {k} ({line!r}...) is not a phased diploid biallelic VCF row (chrX/Y and "
                              "missing calls are outside the engine's domain, reference README.md:72)")
-        self.store.set_annotations(self.pos0, self.end0, idnum, elig)
+        blob, off = Store.vcf_fixed_columns(ctx._lib, raw, rows)
+        self._set_columns(samples, rows, blob.tobytes(), off)
+
 
     def select_samples(self, sample_names):
         """The mask plane of the chosen samples; names absent from the VCF are skipped like the

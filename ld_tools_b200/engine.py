@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (BELOW_THRES, DP_INT0, DP_MASK, DP_SHIFT, ENGINE_AUTO, ENGINE_MMA, ENGINE_POPC,  # noqa: F401
-                   HIT_DTYPE, LD_RESULT_DTYPE, MEASURE_DPRIME, MEASURE_R2, R2_INT0, R2_MASK, LdxError,
+                   HIT_DTYPE, LD_RESULT_DTYPE, MEASURE_DPRIME, MEASURE_R2, R2_INT0, R2_MASK, VCF_ROW_DTYPE, LdxError,
                    check, ptr)
 
 MEASURES = {"r_square": MEASURE_R2, "d_prime": MEASURE_DPRIME}   # the CLI's -l choices
@@ -191,6 +191,30 @@ class Store:
     def upload(self, first_row, planes):
         planes = np.ascontiguousarray(planes, dtype="<u8")
         check(self._lib.ldx_store_upload(self._h, int(first_row), planes.shape[0], ptr(planes)))
+
+    @classmethod
+    def ingest_vcf(cls, ctx, text, n_samples, rows_cap=None):
+        """A whole decompressed VCF (bytes-like) -> (store with planes + window annotations, one VCF_ROW_DTYPE
+        record per variant), everything parsed and packed on the GPU (ldx_store_ingest_vcf)."""
+        buf = np.frombuffer(text, dtype=np.uint8)
+        if rows_cap is None:
+            rows_cap = int(np.count_nonzero(buf == 10)) + 1
+        rows = np.zeros(max(rows_cap, 1), dtype=VCF_ROW_DTYPE)
+        h, n = C.c_void_p(), C.c_int64()
+        check(ctx._lib.ldx_store_ingest_vcf(ctx._h, ptr(buf), buf.shape[0], int(n_samples), C.byref(h), ptr(rows), int(rows_cap),
+                                            C.byref(n)))
+        return cls(ctx, 0, 0, _handle=h), rows[:n.value]
+
+    @staticmethod
+    def vcf_fixed_columns(lib, text, rows):
+        """(blob, off): the nine fixed columns of every record back to back, record r = blob[off[r]:off[r+1]]."""
+        buf = np.frombuffer(text, dtype=np.uint8)
+        rows = np.ascontiguousarray(rows, dtype=VCF_ROW_DTYPE)
+        off = np.zeros(rows.shape[0] + 1, dtype=np.int64)
+        check(lib.ldx_vcf_copy_prefixes(ptr(buf), buf.shape[0], ptr(rows), rows.shape[0], None, 0, ptr(off)))
+        blob = np.zeros(max(int(off[-1]), 1), dtype=np.uint8)
+        check(lib.ldx_vcf_copy_prefixes(ptr(buf), buf.shape[0], ptr(rows), rows.shape[0], ptr(blob), blob.shape[0], ptr(off)))
+        return blob[:int(off[-1])], off
 
     def save(self, path):
         """Planes + annotations to one file (ldx_store_save): built once per chromosome, like the reference's cache."""

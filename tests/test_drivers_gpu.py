@@ -115,8 +115,8 @@ def test_store_cache_round_trip_and_staleness(data, ctx, monkeypatch):
     assert ingests == []
     for cd in (first, cached):
         assert (cd.store.download() == fresh.store.download()).all()
-        assert cd.samples == fresh.samples and cd.ids == fresh.ids and cd.refs == fresh.refs and cd.alts == fresh.alts
-        assert cd.vts == fresh.vts and list(cd.multi) == list(fresh.multi)
+        assert cd.samples == fresh.samples and list(cd.ids) == list(fresh.ids) and list(cd.refs) == list(fresh.refs)
+        assert list(cd.alts) == list(fresh.alts) and list(cd.vts) == list(fresh.vts) and list(cd.multi) == list(fresh.multi)
         assert (cd.pos == fresh.pos).all() and (cd.pos0 == fresh.pos0).all() and (cd.end0 == fresh.end0).all()
         assert cd.max_ref_len == fresh.max_ref_len and cd.n_samples == fresh.n_samples
     # the annotations travelled with the planes: the same window scan on both
@@ -143,3 +143,82 @@ def test_store_cache_round_trip_and_staleness(data, ctx, monkeypatch):
     assert (rebuilt.store.download() == fresh.store.download()).all()
     for cd in (fresh, first, cached, again, rebuilt):
         cd.close()
+
+
+def _host_parse(raw, n_samples):
+    """What the GPU ingest must reproduce, stated with Python string methods (the drivers' former per-line loop)."""
+    import re
+    rows = []
+    for line in raw.split(b"\n"):
+        line = line.rstrip(b"\r")
+        if not line or line.startswith(b"#"):
+            continue
+        f = line.split(b"\t")
+        ok = len(f) >= 9 + n_samples and len(b"\t".join(f[9:9 + n_samples])) >= 4 * n_samples - 1
+        pos = int(f[1]) if len(f) > 1 and f[1].isdigit() else 0
+        rid = f[2].decode() if len(f) > 2 else ""
+        keys = [x.split("=")[0] for x in (f[7].decode().split(";") if len(f) > 7 else [])]
+        rs = bool(re.match(r"rs\d+$", rid))
+        multi = "MULTI_ALLELIC" in keys
+        rows.append({"pos": pos, "id": rid, "ref": f[3].decode() if len(f) > 3 else "", "alt": f[4].decode() if len(f) > 4 else "",
+                     "rs": rs, "multi": multi, "ok": ok, "gts": f[9:9 + n_samples] if ok else None,
+                     "vt": ([x[3:] for x in f[7].decode().split(";") if x.startswith("VT=")] or [""])[0] if len(f) > 7 else ""})
+    return rows
+
+
+def _check_ingest(ctx, raw, n_samples):
+    import numpy as np
+    from ld_tools_b200 import Store
+    want = _host_parse(raw, n_samples)
+    st, rows = Store.ingest_vcf(ctx, raw, n_samples)
+    assert len(rows) == len(want) == st.n_variants
+    blob, off = Store.vcf_fixed_columns(ctx._lib, raw, rows)
+    blob = blob.tobytes()
+    planes = st.download() if len(want) else np.zeros((0, st.stride_words), dtype="<u8")
+    for k, (r, w) in enumerate(zip(rows, want)):
+        assert bool(r["status"] & 2) == (not w["ok"]), (k, r, w)
+        if not w["ok"]:
+            assert r["eligible"] == 0 and not planes[k].any()
+            continue
+        assert r["pos"] == w["pos"] and r["ref_len"] == len(w["ref"]) and bool(r["multi"]) == w["multi"]
+        assert bool(r["eligible"]) == (w["rs"] and not w["multi"])
+        assert r["idnum"] == (int(w["id"][2:]) if w["rs"] else -1 - k)
+        rec = blob[off[k]:off[k + 1]]
+        assert rec[r["id_off"]:r["ref_off"] - 1].decode() == w["id"] and rec[r["ref_off"]:r["alt_off"] - 1].decode() == w["ref"]
+        assert rec[r["alt_off"]:].split(b"\t")[0].decode() == w["alt"] and len(rec) == r["gt_off"]
+        bits = np.zeros(st.stride_words * 64, dtype=np.uint8)
+        bad = False
+        for s_i, g in enumerate(w["gts"]):
+            bad |= len(g) < 3 or g[0:1] not in (b"0", b"1") or g[2:3] not in (b"0", b"1") or g[1:2] != b"|"
+            bits[2 * s_i] = g[0:1] == b"1"
+            bits[2 * s_i + 1] = g[2:3] == b"1"
+        assert bool(r["status"] & 1) == bad, (k, w["gts"][:4])
+        assert (np.packbits(bits, bitorder="little").view("<u8") == planes[k]).all(), k
+    st.close()
+    return rows
+
+
+def test_gpu_vcf_ingest_matches_a_host_parse(data, ctx):
+    """ldx_store_ingest_vcf: newline index, field split, POS / rs number / MULTI_ALLELIC / len(REF) and the packed
+    genotypes, against a parse written with Python string methods -- on the synthetic chr22 and on hand-made corner cases."""
+    import gzip
+    root, intgen, srcs = data
+    with gzip.open(os.path.join(intgen, "22.vcf.gz"), "rb") as fh:
+        raw = fh.read()
+    hdr = [ln for ln in raw.split(b"\n") if ln.startswith(b"#CHROM")][0]
+    rows = _check_ingest(ctx, raw, len(hdr.split(b"\t")) - 9)
+    assert rows["eligible"].sum() > 0 and rows["multi"].sum() > 0 and (rows["idnum"] < 0).sum() > 0 and (rows["ref_len"] > 1).sum() > 0
+    gt = lambda s: "\t".join(s.split())                                                     # noqa: E731
+    fixed = "22\t{pos}\t{id}\t{ref}\t{alt}\t100\tPASS\t{info}\tGT\t"
+    lines = ["##fileformat=VCFv4.1", "##INFO=<ID=VT>", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\tB\tC",
+             fixed.format(pos=1, id="rs1", ref="A", alt="G", info="AC=1;VT=SNP") + gt("0|1 1|1 0|0"),
+             fixed.format(pos=248956422, id="rs4294967296", ref="ACGT", alt="A", info="VT=INDEL;MULTI_ALLELIC") + gt("1|0 0|0 1|1"),
+             fixed.format(pos=77, id="esv123", ref="A", alt="<CN0>", info="MULTI_ALLELIC=1;VT=SV") + gt("0|0 0|0 0|1"),
+             fixed.format(pos=78, id=".", ref="A", alt="C,T", info="XMULTI_ALLELIC;MULTI_ALLELICX;VT=SNP") + gt("1|1 1|1 1|1"),
+             fixed.format(pos=79, id="rs12x", ref="A", alt="C", info=".") + gt("0|1 .|1 0/1"),
+             fixed.format(pos=80, id="rs9", ref="A", alt="C", info="VT=SNP") + gt("0|1 1|0"),          # a column short
+             "22\t81\trs10\tA",                                                                    # truncated line
+             "",
+             fixed.format(pos=82, id="rs0011", ref="AT", alt="A", info="VT=INDEL;AF=0.5") + gt("1|1 0|1 1|0")]
+    for text in ("\n".join(lines) + "\n", "\n".join(lines), "\r\n".join(lines) + "\r\n", "\n".join(lines[:3]) + "\n"):
+        _check_ingest(ctx, text.encode(), 3)

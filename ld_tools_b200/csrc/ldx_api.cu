@@ -58,6 +58,15 @@ static int arena_get(ldx_ctx *ctx, int slot, size_t bytes, void **out) {
 }
 enum { S_IA = 0, S_IB, S_PACKED, S_N11, S_D, S_DP, S_R2, S_TEXT, S_ROWOFF, S_STATUS, S_HITS, S_MISC, S_ROWS };
 
+namespace ldx {
+// Arena blocks for code outside this file (ldx_vcf.cu): 0 = the text slot, 1 = row offsets, 2 = status.
+int scratch_get(ldx_ctx *ctx, int which, size_t bytes, void **out) {
+    static const int slot[3] = {S_TEXT, S_ROWOFF, S_STATUS};
+    if (which < 0 || which > 2) return set_error(LDX_ERR_ARG, "bad scratch block");
+    return arena_get(ctx, slot[which], bytes, out);
+}
+}  // namespace ldx
+
 // ------------------------------------------------------------------------------------------ lifecycle
 extern "C" int32_t ldx_abi_version(void) { return LDX_ABI_VERSION; }
 extern "C" const char *ldx_last_error(void) { return g_last_error.c_str(); }
@@ -115,6 +124,7 @@ extern "C" int32_t ldx_destroy(ldx_ctx *ctx) {
     if (ctx->d_fix_count) cudaFree(ctx->d_fix_count);
     if (ctx->h_fix_count) cudaFreeHost(ctx->h_fix_count);
     if (ctx->h_mailbox) cudaFreeHost((void *)ctx->h_mailbox);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->d_mma_ops) cudaFree(ctx->d_mma_ops);
     if (ctx->d_trace) cudaFree(ctx->d_trace);
     for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
@@ -647,11 +657,16 @@ struct StoreFileHeader {
 static_assert(sizeof(StoreFileHeader) == 64, "store file header");
 constexpr size_t FILE_PIECE = 64u << 20;
 
-struct Staging {            // pinned bounce buffer + FILE, released on every exit path
+struct Staging {            // the context's pinned bounce buffer + a FILE that is closed on every exit path
     void *buf = nullptr;
     FILE *fh = nullptr;
-    ~Staging() { if (buf) cudaFreeHost(buf); if (fh) fclose(fh); }
+    ~Staging() { if (fh) fclose(fh); }
 };
+int staging_buffer(ldx_ctx *ctx, Staging &st) {
+    if (!ctx->h_stage) LDX_CUDA(cudaMallocHost(&ctx->h_stage, FILE_PIECE));
+    st.buf = ctx->h_stage;
+    return LDX_OK;
+}
 
 int stream_out(ldx_ctx *ctx, Staging &st, const void *dev, size_t bytes) {
     for (size_t off = 0; off < bytes; off += FILE_PIECE) {
@@ -678,7 +693,7 @@ extern "C" int32_t ldx_store_save(const ldx_store *s, const char *path) {
     ldx_ctx *ctx = s->ctx;
     LDX_CUDA(cudaSetDevice(ctx->device));
     Staging st;
-    LDX_CUDA(cudaMallocHost(&st.buf, FILE_PIECE));
+    LDX_TRY(staging_buffer(ctx, st));
     st.fh = fopen(path, "wb");
     if (!st.fh) return set_error(LDX_ERR_ARG, std::string("store file: cannot create ") + path);
     StoreFileHeader h = {};
@@ -708,7 +723,7 @@ extern "C" int32_t ldx_store_load(ldx_ctx *ctx, const char *path, ldx_store **st
     if (fread(&h, sizeof h, 1, st.fh) != 1 || std::memcmp(h.magic, "LDXSTOR1", 8) != 0)
         return set_error(LDX_ERR_ARG, "store file: not an ldx store (bad magic)");
     LDX_REQUIRE(h.n_variants >= 0 && h.n_variants < (1ll << 31) && h.n_hap > 0 && h.n_hap <= (1 << 24), "store file: bad header");
-    LDX_CUDA(cudaMallocHost(&st.buf, FILE_PIECE));
+    LDX_TRY(staging_buffer(ctx, st));
     ldx_store *s = nullptr;
     LDX_TRY(ldx_store_create(ctx, h.n_variants, h.n_hap, &s));
     int rc = s->stride_words == h.stride_words ? (int)LDX_OK : set_error(LDX_ERR_ARG, "store file: row pitch of another library version");

@@ -172,16 +172,18 @@ merge_status_kernel(ldx_vcf_row *__restrict__ rows, const uint8_t *__restrict__ 
 
 int launch_pack_gt(ldx_ctx *ctx, const uint8_t *d_text, const int64_t *d_row_off, int64_t row_pitch, int64_t n_rows, int32_t n_samples,
                    uint64_t *d_planes_first, int32_t stride_words, uint8_t *d_status);
+int scratch_get(ldx_ctx *ctx, int which, size_t bytes, void **out);      // ldx_api.cu: block `which` (0..2) of the context's arena
 
-struct DevBuf {                 // scratch of one ingest call, freed on every exit path
-    std::vector<void *> p;
-    ~DevBuf() { for (void *q : p) cudaFree(q); }
-    template <typename T> int get(T **out, size_t n) {
-        void *q = nullptr;
-        if (cudaMalloc(&q, std::max<size_t>(n * sizeof(T), 16)) != cudaSuccess) { cudaGetLastError(); return set_error(LDX_ERR_NOMEM, "vcf ingest: device scratch allocation failed"); }
-        p.push_back(q);
-        *out = reinterpret_cast<T *>(q);
-        return LDX_OK;
+// Scratch comes from the context's arena (three blocks, one per phase: their sizes depend on counts only known after the
+// previous phase) -- cudaMalloc / cudaFree of a dozen buffers per call cost more than the kernels.
+struct Carve {
+    uint8_t *base = nullptr;
+    size_t off = 0;
+    static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
+    template <typename T> T *take(size_t n) {
+        T *p = reinterpret_cast<T *>(base + off);
+        off += pad(n * sizeof(T));
+        return p;
     }
 };
 
@@ -197,56 +199,48 @@ extern "C" int32_t ldx_store_ingest_vcf(ldx_ctx *ctx, const uint8_t *text, int64
     *store_out = nullptr; *n_rows_out = 0;
     LDX_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    DevBuf scratch;
-    // ---- the text, once, with a final newline and slack for K1's aligned 16-byte loads
+    // ---- phase 1: the text, once, with a final newline and slack for K1's aligned 16-byte loads; newline counts per block
     const bool add_nl = text[text_bytes - 1] != '\n';
     const int64_t n = text_bytes + (add_nl ? 1 : 0);
-    uint8_t *d_text = nullptr;
-    LDX_TRY(scratch.get(&d_text, (size_t)n + 64));
-    LDX_CUDA(cudaMemcpyAsync(d_text, text, (size_t)text_bytes, cudaMemcpyHostToDevice, st));
-    LDX_CUDA(cudaMemsetAsync(d_text + text_bytes, '\n', (size_t)(n - text_bytes) + 64, st));
-    // ---- newline index
     const int64_t n_blocks = (n + NL_BLOCK_BYTES - 1) / NL_BLOCK_BYTES;
     LDX_REQUIRE(n_blocks < (1ll << 31), "vcf ingest: text too large for one call");
-    uint32_t *d_counts = nullptr, *d_base = nullptr;
-    LDX_TRY(scratch.get(&d_counts, (size_t)n_blocks + 1));
-    LDX_TRY(scratch.get(&d_base, (size_t)n_blocks + 1));
+    size_t cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)(n_blocks + 1), st);
+    Carve c1;
+    LDX_TRY(scratch_get(ctx, 0, Carve::pad((size_t)n + 64) + 2 * Carve::pad(((size_t)n_blocks + 1) * 4) + Carve::pad(cub_bytes) + 256, (void **)&c1.base));
+    uint8_t *d_text = c1.take<uint8_t>((size_t)n + 64);
+    uint32_t *d_counts = c1.take<uint32_t>((size_t)n_blocks + 1), *d_base = c1.take<uint32_t>((size_t)n_blocks + 1);
+    void *d_cub = c1.take<uint8_t>(cub_bytes);
+    LDX_CUDA(cudaMemcpyAsync(d_text, text, (size_t)text_bytes, cudaMemcpyHostToDevice, st));
+    LDX_CUDA(cudaMemsetAsync(d_text + text_bytes, '\n', (size_t)(n - text_bytes) + 64, st));
     LDX_CUDA(cudaMemsetAsync(d_counts + n_blocks, 0, sizeof(uint32_t), st));
     count_newlines_kernel<<<(unsigned)n_blocks, NL_THREADS, 0, st>>>(d_text, n, d_counts);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
-    size_t cub_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, d_counts, d_base, (int)(n_blocks + 1), st);
-    size_t cub_bytes2 = 0;
-    void *d_cub;
-    {   // one temp block serves both scans (the second is over lines: sized below once their number is known)
-        LDX_TRY(scratch.get(reinterpret_cast<uint8_t **>(&d_cub), cub_bytes));
-    }
     LDX_CUDA(cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_counts, d_base, (int)(n_blocks + 1), st));
     uint32_t n_lines32 = 0;
     LDX_CUDA(cudaMemcpyAsync(&n_lines32, d_base + n_blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     LDX_CUDA(cudaStreamSynchronize(st));
     const int64_t n_lines = n_lines32;
     LDX_REQUIRE(n_lines > 0 && n_lines < (1ll << 31), "vcf ingest: no lines");
-    int64_t *d_nl;
-    LDX_TRY(scratch.get(&d_nl, (size_t)n_lines));
+    // ---- phase 2: newline positions, per-line parse, record numbering
+    size_t cub_bytes2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes2, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)(n_lines + 1), st);
+    Carve c2;
+    LDX_TRY(scratch_get(ctx, 1, Carve::pad((size_t)n_lines * 8) + Carve::pad((size_t)n_lines * sizeof(ldx_vcf_row)) +
+                                    2 * Carve::pad(((size_t)n_lines + 1) * 4) + Carve::pad(cub_bytes2) + 256, (void **)&c2.base));
+    int64_t *d_nl = c2.take<int64_t>((size_t)n_lines);
+    ldx_vcf_row *d_tmp = c2.take<ldx_vcf_row>((size_t)n_lines);
+    uint32_t *d_isrec = c2.take<uint32_t>((size_t)n_lines + 1), *d_recidx = c2.take<uint32_t>((size_t)n_lines + 1);
+    void *d_cub2 = c2.take<uint8_t>(cub_bytes2);
     write_newlines_kernel<<<(unsigned)n_blocks, NL_THREADS, 0, st>>>(d_text, n, d_base, d_nl);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
-    // ---- per-line parse, record numbering
-    ldx_vcf_row *d_tmp;
-    uint32_t *d_isrec, *d_recidx;
-    LDX_TRY(scratch.get(&d_tmp, (size_t)n_lines));
-    LDX_TRY(scratch.get(&d_isrec, (size_t)n_lines + 1));
-    LDX_TRY(scratch.get(&d_recidx, (size_t)n_lines + 1));
     LDX_CUDA(cudaMemsetAsync(d_isrec + n_lines, 0, sizeof(uint32_t), st));
     const unsigned lgrid = (unsigned)((n_lines + 255) / 256);
     parse_lines_kernel<<<lgrid, 256, 0, st>>>(d_text, d_nl, n_lines, n_samples, d_tmp, d_isrec);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
-    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes2, d_isrec, d_recidx, (int)(n_lines + 1), st);
-    void *d_cub2;
-    LDX_TRY(scratch.get(reinterpret_cast<uint8_t **>(&d_cub2), cub_bytes2));
     LDX_CUDA(cub::DeviceScan::ExclusiveSum(d_cub2, cub_bytes2, d_isrec, d_recidx, (int)(n_lines + 1), st));
     uint32_t n_rec32 = 0;
     LDX_CUDA(cudaMemcpyAsync(&n_rec32, d_recidx + n_lines, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -254,6 +248,13 @@ extern "C" int32_t ldx_store_ingest_vcf(ldx_ctx *ctx, const uint8_t *text, int64
     const int64_t n_rec = n_rec32;
     *n_rows_out = n_rec;
     if (n_rec > rows_cap) return set_error(LDX_ERR_CAPACITY, "vcf ingest: rows buffer too small");
+    // ---- phase 3: dense rows
+    Carve c3;
+    LDX_TRY(scratch_get(ctx, 2, Carve::pad((size_t)n_rec * sizeof(ldx_vcf_row)) + Carve::pad((size_t)n_rec * 8) + Carve::pad((size_t)n_rec) + 256,
+                        (void **)&c3.base));
+    ldx_vcf_row *d_rows = c3.take<ldx_vcf_row>((size_t)n_rec);
+    int64_t *d_gt = c3.take<int64_t>((size_t)n_rec);
+    uint8_t *d_status = c3.take<uint8_t>((size_t)n_rec);
     // ---- the store, its annotations, the genotype planes
     ldx_store *s = nullptr;
     LDX_TRY(ldx_store_create(ctx, n_rec, 2 * n_samples, &s));
@@ -266,10 +267,6 @@ extern "C" int32_t ldx_store_ingest_vcf(ldx_ctx *ctx, const uint8_t *text, int64
         if (e == cudaSuccess) e = cudaMalloc(&s->d_eligible, nv);
         if (e != cudaSuccess) { cudaGetLastError(); rc = set_error(LDX_ERR_NOMEM, "vcf ingest: annotation allocation failed"); }
     }
-    ldx_vcf_row *d_rows = nullptr; int64_t *d_gt = nullptr; uint8_t *d_status = nullptr;
-    if (rc == LDX_OK) rc = scratch.get(&d_rows, (size_t)n_rec);
-    if (rc == LDX_OK) rc = scratch.get(&d_gt, (size_t)n_rec);
-    if (rc == LDX_OK) rc = scratch.get(&d_status, (size_t)n_rec);
     if (rc == LDX_OK && n_rec > 0) {
         compact_rows_kernel<<<lgrid, 256, 0, st>>>(d_tmp, d_isrec, d_recidx, n_lines, d_rows, d_gt, s->d_pos0, s->d_end0, s->d_idnum, s->d_eligible);
         ctx->launches++;

@@ -176,6 +176,13 @@ typedef struct ldx_vcf_row {
 } ldx_vcf_row;
 int32_t ldx_store_ingest_vcf(ldx_ctx *ctx, const uint8_t *text, int64_t text_bytes, int32_t n_samples,
                              ldx_store **store_out, ldx_vcf_row *rows_out, int64_t rows_cap, int64_t *n_rows_out);
+/* Host side of the ingest: a whole .gz file -> malloc'ed text (*text_out; release it with ldx_free_host).  A BGZF file
+ * (what tabix indexes, prep_intgen_data.py:138: independent gzip members of <= 64 KiB announcing their sizes) is
+ * inflated by `threads` host threads in parallel (<= 0: all cores), every block straight into its final place, CRCs
+ * checked; any other gzip file (one stream or concatenated members) sequentially.  *was_bgzf_out may be NULL. */
+int32_t ldx_inflate_gz_file(const char *path, int32_t threads, uint8_t **text_out, int64_t *text_bytes_out,
+                            int32_t *was_bgzf_out);
+int32_t ldx_free_host(void *p);
 /* Host helper: the fixed columns of every record back to back (record r = out[off_out[r], off_out[r+1]); off_out has
  * n_rows + 1 entries), so that the caller can drop the text and still print ID / REF / ALT / INFO of the rows it
  * reports.  out == NULL: only off_out is filled (size query). */

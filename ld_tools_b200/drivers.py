@@ -12,7 +12,6 @@ golden files under tests/golden/drivers/ were produced by the UNMODIFIED referen
 
 There is no CPU path here: every LD number comes out of libldx.so.
 """
-import gzip
 import json
 import os
 import re
@@ -20,7 +19,7 @@ import sqlite3
 
 import numpy as np
 
-from .engine import Context, Store, dprime_value, measure_value, r2_value, threshold_e4
+from .engine import Context, HostText, Store, dprime_value, measure_value, r2_value, threshold_e4
 from ._lib import BELOW_THRES, VCF_ROW_DTYPE, LdxError
 
 RS_RE = re.compile(r"rs\d+$")
@@ -174,25 +173,27 @@ class ChromData:
     # ---- first run: the VCF itself.  The host only inflates the file and reads the #CHROM line; splitting lines and
     #      fields, parsing POS / ID / REF / INFO and packing the genotypes all happen on the GPU (ldx_store_ingest_vcf).
     def _ingest(self, ctx, vcf_path):
-        with gzip.open(vcf_path, "rb") as fh:
-            raw = fh.read()
-        h = 0 if raw.startswith(b"#CHROM") else raw.find(b"\n#CHROM") + 1
-        if h == 0 and not raw.startswith(b"#CHROM"):
-            raise ValueError(f"{vcf_path}: no #CHROM header line")
-        e = raw.find(b"\n", h)
-        samples = raw[h:e if e >= 0 else len(raw)].decode().rstrip("\r").split("\t")[9:]
+        host = HostText(vcf_path)                          # BGZF blocks inflated in parallel by the library
+        raw = host.array
+        head = raw[:1 << 24].tobytes()                     # the meta lines and the #CHROM line
+        h = 0 if head.startswith(b"#CHROM") else head.find(b"\n#CHROM") + 1
+        if h == 0 and not head.startswith(b"#CHROM"):
+            raise ValueError(f"{vcf_path}: no #CHROM header line in the first 16 MiB")
+        e = head.find(b"\n", h)
+        samples = head[h:e if e >= 0 else len(head)].decode().rstrip("\r").split("\t")[9:]
         if not samples:
             raise ValueError(f"{vcf_path}: no sample columns")
-        self.store, rows = Store.ingest_vcf(ctx, raw, len(samples), rows_cap=raw.count(b"\n") + 1)
+        self.store, rows = Store.ingest_vcf(ctx, raw, len(samples))
         bad = np.flatnonzero((rows["status"] != 0) & ((rows["eligible"] != 0) | ((rows["status"] & 6) != 0)))
         if len(bad):                                                       # rows no driver ever pairs may be anything
             k = int(bad[0])
-            line = raw[rows["line_off"][k]:rows["line_off"][k] + 60].decode(errors="replace")
+            line = raw[rows["line_off"][k]:rows["line_off"][k] + 60].tobytes().decode(errors="replace")
             self.store.close()
             raise ValueError(f"{vcf_path}: record {k} ({line!r}...) is not a phased diploid biallelic VCF row (chrX/Y and "
                              "missing calls are outside the engine's domain, reference README.md:72)")
         blob, off = Store.vcf_fixed_columns(ctx._lib, raw, rows)
         self._set_columns(samples, rows, blob.tobytes(), off)
+        host.close()
 
 
     def select_samples(self, sample_names):

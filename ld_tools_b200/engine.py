@@ -64,6 +64,27 @@ def _i64(a):
     return np.ascontiguousarray(a, dtype=np.int64)
 
 
+class HostText:
+    """A .gz file inflated by the library (ldx_inflate_gz_file: BGZF blocks in parallel on all host cores).
+    `.array` is a uint8 view of the C-owned text; it is released when this object goes away."""
+
+    def __init__(self, path, threads=0):
+        self._lib = _lib.load()
+        p, n, b = C.c_void_p(), C.c_int64(), C.c_int32()
+        check(self._lib.ldx_inflate_gz_file(os.fsencode(path), int(threads), C.byref(p), C.byref(n), C.byref(b)))
+        self._p, self.nbytes, self.was_bgzf = p, n.value, bool(b.value)
+        self.array = (np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value,)) if n.value
+                      else np.zeros(0, dtype=np.uint8))
+
+    def close(self):
+        if getattr(self, "_p", None) is not None:
+            self.array = None
+            self._lib.ldx_free_host(self._p)
+            self._p = None
+
+    __del__ = close
+
+
 class Context:
     """One CUDA context/stream of libldx.  Create it AFTER fork (see include/ldx.h)."""
 
@@ -197,13 +218,18 @@ class Store:
         """A whole decompressed VCF (bytes-like) -> (store with planes + window annotations, one VCF_ROW_DTYPE
         record per variant), everything parsed and packed on the GPU (ldx_store_ingest_vcf)."""
         buf = np.frombuffer(text, dtype=np.uint8)
-        if rows_cap is None:
-            rows_cap = int(np.count_nonzero(buf == 10)) + 1
-        rows = np.zeros(max(rows_cap, 1), dtype=VCF_ROW_DTYPE)
-        h, n = C.c_void_p(), C.c_int64()
-        check(ctx._lib.ldx_store_ingest_vcf(ctx._h, ptr(buf), buf.shape[0], int(n_samples), C.byref(h), ptr(rows), int(rows_cap),
-                                            C.byref(n)))
-        return cls(ctx, 0, 0, _handle=h), rows[:n.value]
+        if rows_cap is None:       # a record line holds at least 4 * n_samples - 1 genotype bytes; the rest are header lines
+            rows_cap = buf.shape[0] // max(4 * int(n_samples) - 1, 1) + 4096
+        while True:
+            rows = np.zeros(max(rows_cap, 1), dtype=VCF_ROW_DTYPE)
+            h, n = C.c_void_p(), C.c_int64()
+            rc = ctx._lib.ldx_store_ingest_vcf(ctx._h, ptr(buf), buf.shape[0], int(n_samples), C.byref(h), ptr(rows), int(rows_cap),
+                                               C.byref(n))
+            if rc == _lib.ERR_CAPACITY and n.value > rows_cap:       # many short (malformed) lines: now the count is known
+                rows_cap = n.value
+                continue
+            check(rc)
+            return cls(ctx, 0, 0, _handle=h), rows[:n.value]
 
     @staticmethod
     def vcf_fixed_columns(lib, text, rows):

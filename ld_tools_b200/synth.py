@@ -8,13 +8,48 @@ distance.  Haplotypes are mosaics of a small founder panel (Li-Stephens style co
 recombination switches), which yields realistic r2 >= 0.8 neighbourhoods and variants that are
 monomorphic inside a sub-population.
 """
-import gzip
 import os
 import sqlite3
 
 import numpy as np
 
 SEED = 20130502
+
+
+class BgzfWriter:
+    """Minimal BGZF writer (the block-gzip container htslib / tabix use): gzip members of at most 65,280 input
+    bytes, each with a 'BC' extra field holding its compressed size - 1, closed by the 28-byte empty EOF block."""
+
+    BLOCK = 65280
+
+    def __init__(self, path, level=1):
+        import zlib
+        self._z, self._fh, self._buf, self._level = zlib, open(path, "wb"), bytearray(), level
+
+    def _emit(self, chunk):
+        import struct
+        c = self._z.compressobj(self._level, self._z.DEFLATED, -15)
+        body = c.compress(bytes(chunk)) + c.flush()
+        self._fh.write(struct.pack("<BBBBIBBH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6) + b"BC" + struct.pack("<HH", 2, len(body) + 25))
+        self._fh.write(body + struct.pack("<II", self._z.crc32(bytes(chunk)) & 0xffffffff, len(chunk)))
+
+    def write(self, data):
+        self._buf += data
+        while len(self._buf) >= self.BLOCK:
+            self._emit(self._buf[:self.BLOCK])
+            del self._buf[:self.BLOCK]
+
+    def close(self):
+        if self._buf:
+            self._emit(self._buf)
+        self._emit(b"")
+        self._fh.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 # 1000G phase 3 super-population sizes (SURVEY.md 8d): AFR 661, AMR 347, EAS 504, EUR 503, SAS 489
 SUPER_POPS = [("AFR", 661, ["YRI", "LWK", "GWD", "MSL", "ESN", "ASW", "ACB"]),
@@ -170,7 +205,7 @@ def write_intgen_dir(path, panel, recs, haps, chrom="22"):
         fh.write("sample\tpop\tsuper_pop\tgender\n")
         for row in panel:
             fh.write("\t".join(row) + "\n")
-    with gzip.open(os.path.join(path, f"{chrom}.vcf.gz"), "wb", compresslevel=1) as fh:
+    with BgzfWriter(os.path.join(path, f"{chrom}.vcf.gz")) as fh:          # BGZF, like the real 1000G files (any gzip reader reads it)
         fh.write(b"##fileformat=VCFv4.1\n##source=ld_tools_b200.synth\n")
         fh.write(("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(names) + "\n").encode())
         for r, h in zip(recs, haps):

@@ -1026,11 +1026,12 @@ int triangle_mma_max_haplotypes() { return 8192; }
 
 template <int N, bool WANT_N11, bool THRES, bool TRACE, bool PAIR, bool SINGLE>
 static int launch_tiles_t(ldx_ctx *ctx, const MmaArgs &A) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};            // a function attribute is per device: a process may hold contexts on several
+    const int dv = ctx->device & 63;
+    if (!attr_set[dv]) {
         LDX_CUDA(cudaFuncSetAttribute(triangle_mma_kernel<N, WANT_N11, THRES, TRACE, PAIR, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)MmaCfg<N, PAIR>::SMEM));
-        attr_set = true;
+        attr_set[dv] = true;
     }
     // persistent: one CTA per SM; a pair kernel runs sm_count / 2 clusters of two
     const int units = PAIR ? ctx->sm_count / 2 : ctx->sm_count;

@@ -143,10 +143,11 @@ int launch_triangle_popc(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t
     const int64_t n_tiles = A.n_tiles_side * (A.n_tiles_side + 1) / 2 - A.tile_begin;
     if (n_tiles > 0x7fffffffll) return set_error(LDX_ERR_ARG, "triangle: too many tiles for one launch");
     const size_t smem = (size_t)2 * TRI_TILE * TRI_PITCH * sizeof(uint64_t);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};            // a function attribute is per device: a process may hold contexts on several
+    const int dv = ctx->device & 63;
+    if (!attr_set[dv]) {
         LDX_CUDA(cudaFuncSetAttribute(triangle_popc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set[dv] = true;
     }
     timing_begin(ctx);
     triangle_popc_kernel<<<(int)n_tiles, TRI_THREADS, smem, ctx->stream>>>(A);

@@ -371,6 +371,33 @@ def test_triangle_mma_deferred_list_overflow_is_settled_in_place(ctx, n_var, n_h
     st.close()
 
 
+@pytest.mark.parametrize("n_var,n_hap,sel_frac", [(513, 5008, None), (2000, 5008, 0.2), (2600, 5008, None), (2600, 198, None)])
+def test_triangle_mma_cta_pair_kernel_bit_exact(ctx, n_var, n_hap, sel_frac):
+    """LDX_TUNE_MMA_PAIR: 256 x 128 tiles on CTA pairs (tcgen05.mma.cta_group::2; the peer's wideners report to their own
+    barrier and forwarder warps relay each completed stage to the leader).  Same counts and words as the popcount engine,
+    for single-wave and multi-wave calls."""
+    from ld_tools_b200._lib import TUNE_MMA_PAIR, TUNE_MMA_TILE_N
+    from ld_tools_b200.engine import ENGINE_MMA, ENGINE_POPC, threshold_e4
+    st, planes, mask = make_store(ctx, n_var, n_hap, seed=1200 + n_var, sel_frac=sel_frac)
+    rows = np.random.default_rng(n_var).permutation(n_var)
+    t = threshold_e4(0.05)
+    ref_packed, ref_n11 = st.triangle(rows, thres_e4_=t, engine=ENGINE_POPC, want_n11=True)
+    ctx.set_tuning(TUNE_MMA_PAIR, 1)
+    ctx.set_tuning(TUNE_MMA_TILE_N, 128)
+    try:
+        packed, n11 = st.triangle(rows, thres_e4_=t, engine=ENGINE_MMA, want_n11=True)
+        plain, _ = st.triangle(rows, engine=ENGINE_MMA)
+        part, _ = st.triangle_rows(rows, 256, n_var, engine=ENGINE_MMA)
+    finally:
+        ctx.set_tuning(TUNE_MMA_PAIR, 0)
+        ctx.set_tuning(TUNE_MMA_TILE_N, 0)
+    assert (n11 == ref_n11).all()
+    assert (packed == ref_packed).all()
+    assert (plain == (ref_packed & ~np.uint32(0x40000000))).all()
+    assert (part == plain[256 * 255 // 2:]).all()
+    st.close()
+
+
 def test_triangle_mma_full_size_and_threshold(ctx):
     from ld_tools_b200.engine import BELOW_THRES, ENGINE_MMA, r2_e4, threshold_e4
     st, planes, mask = make_store(ctx, 2000, 5008, seed=2)

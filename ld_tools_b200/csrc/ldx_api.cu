@@ -292,14 +292,19 @@ static int collect_fixups(ldx_ctx *ctx, std::vector<FixupRec> &recs, bool use_ma
     recs.clear();
     uint32_t n, err;
     bool polled = false;
+    uint64_t record = 0;                       // {sequence number : 32, near-tie count : 24, error flag : 8}, see publish_record
     if (use_mailbox && ctx->seq != 0) {
         const uint32_t want = ctx->seq;
-        for (long spins = 0; spins < 200000000L; ++spins)
-            if (ctx->h_mailbox[0] == want) { polled = true; break; }
+        const volatile uint64_t *box = reinterpret_cast<const volatile uint64_t *>(ctx->h_mailbox);
+        for (long spins = 0; spins < 200000000L; ++spins) {
+            record = *box;
+            if ((uint32_t)record == want) { polled = true; break; }
+        }
     }
     if (polled) {
         std::atomic_thread_fence(std::memory_order_acquire);
-        n = ctx->h_mailbox[1]; err = ctx->h_mailbox[2];
+        n = (uint32_t)(record >> 32) & 0xffffffu; err = (uint32_t)(record >> 56);
+        if (n == 0xffffffu) n = ctx->fix_capacity + 1;      // saturated: reported as the overflow it is
     } else {
         // [0] = near-tie records appended, [1] = tcgen05 pipeline error flag
         LDX_CUDA(cudaMemcpyAsync(ctx->h_fix_count, ctx->d_fix_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));

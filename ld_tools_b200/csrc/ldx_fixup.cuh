@@ -23,4 +23,14 @@ __device__ __forceinline__ void fixup_append(const FixupSink &s, uint64_t out_in
     }
 }
 
+// The completion record of an enqueued call goes to pinned host memory as ONE aligned 64-bit store (single-copy atomic,
+// one PCIe write): sequence number in bits 0-31, near-tie count (saturated) in bits 32-55, error flag in bits 56-63.  The
+// host polls that word: it can never see a new sequence number with stale counts, and no system-wide fence has to sit
+// between payload and flag on the kernel's critical path (it cost the last CTA of the single-wave kernel ~2.4 us).
+__device__ __forceinline__ void publish_record(volatile uint32_t *mailbox, uint32_t seq, uint32_t n_fix, uint32_t err) {
+    const unsigned long long w = (unsigned long long)seq | ((unsigned long long)(n_fix < 0xffffffu ? n_fix : 0xffffffu) << 32) |
+                                 ((unsigned long long)(err & 0xffu) << 56);
+    asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(mailbox), "l"(w) : "memory");
+}
+
 }  // namespace ldx

@@ -7,6 +7,7 @@
 //                          (calc_ld.py:37-44, :96-97; ld_area.py:188-189)
 //   subset_kernel          gather selected haplotype columns into a narrower store
 #include "ldx_internal.h"
+#include "ldx_fixup.cuh"
 
 namespace ldx {
 
@@ -185,13 +186,10 @@ int launch_subset(const ldx_store *src, const int32_t *d_sel, ldx_store *dst) {
 }
 
 // ------------------------------------------------------------------------------------------ mailbox
-// One thread copies {near-tie count, error flag} and the call's sequence number to pinned host
-// memory.  __threadfence_system() orders the payload before the sequence number.
+// One thread copies {near-tie count, error flag} and the call's sequence number to pinned host memory (one 64-bit
+// store, see publish_record).
 __global__ void publish_kernel(const uint32_t *__restrict__ fix_count, volatile uint32_t *mailbox, uint32_t seq) {
-    mailbox[1] = fix_count[0];
-    mailbox[2] = fix_count[1];
-    __threadfence_system();
-    mailbox[0] = seq;
+    publish_record(mailbox, seq, fix_count[0], fix_count[1]);
 }
 
 int launch_publish(ldx_ctx *ctx) {

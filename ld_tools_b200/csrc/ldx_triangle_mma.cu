@@ -507,12 +507,7 @@ slow_pairs_kernel(const uint4 *__restrict__ list, uint32_t *__restrict__ counter
             __threadfence();
             counters[3] = 0;
             counters[2] = 0;
-            if (mailbox) {
-                mailbox[1] = *(volatile uint32_t *)&counters[0];
-                mailbox[2] = *(volatile uint32_t *)&counters[1];
-                __threadfence_system();
-                mailbox[0] = seq;
-            }
+            if (mailbox) publish_record(mailbox, seq, *(volatile uint32_t *)&counters[0], *(volatile uint32_t *)&counters[1]);
         }
     }
 }
@@ -1001,12 +996,7 @@ done:
         if (ticket == gridDim.x - 1) {            // last CTA: what slow_pairs_kernel's last block does otherwise
             __threadfence();
             A.counters[3] = 0;
-            if (A.mailbox) {
-                A.mailbox[1] = *(volatile uint32_t *)&A.counters[0];
-                A.mailbox[2] = *(volatile uint32_t *)&A.counters[1];
-                __threadfence_system();
-                A.mailbox[0] = A.seq;
-            }
+            if (A.mailbox) publish_record(A.mailbox, A.seq, *(volatile uint32_t *)&A.counters[0], *(volatile uint32_t *)&A.counters[1]);
         }
     }
     if (TRACE && A.trace && blockIdx.x == 0 && threadIdx.x == 0) A.trace[56] = gtime();   // all roles done

@@ -17,6 +17,7 @@ from .engine import Context
 __all__ = ["calc_ld"]
 
 _ctx_by_pid = {}
+_CODE_TABLE = bytes([0, 1] + [255] * 254)          # byte value -> genotype code: 0 ref, 1 alt, anything else neither
 
 
 def _context():
@@ -34,6 +35,13 @@ def encode_genotypes(genotypes):
 
     Mirrors list.count(1) / list.count(0) (calc_ld.py:37-40): equality, not identity, so 1.0 and
     True count as 1; None, 2, '.' count as neither."""
+    if isinstance(genotypes, (list, tuple)):
+        # fast path for the drivers' lists of small ints (and bools): bytes() refuses anything else -- floats, None, '.',
+        # negative or > 255 -- and those take the general path below
+        try:
+            return np.frombuffer(bytes(genotypes).translate(_CODE_TABLE), dtype=np.uint8)
+        except (TypeError, ValueError):
+            pass
     arr = np.asarray(genotypes)
     if arr.dtype == object or arr.dtype.kind not in "biuf":
         arr = np.asarray(genotypes, dtype=object)

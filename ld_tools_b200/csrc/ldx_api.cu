@@ -65,6 +65,17 @@ int scratch_get(ldx_ctx *ctx, int which, size_t bytes, void **out) {
     if (which < 0 || which > 2) return set_error(LDX_ERR_ARG, "bad scratch block");
     return arena_get(ctx, slot[which], bytes, out);
 }
+// A whole-chromosome ingest leaves blocks as large as its text (tens of GB) in the grow-only arena: give those back.
+void scratch_trim(ldx_ctx *ctx, size_t keep_bytes) {
+    Arena *a = arena_of(ctx);
+    static const int slot[3] = {S_TEXT, S_ROWOFF, S_STATUS};
+    for (int k = 0; k < 3; ++k)
+        if (a->bytes[slot[k]] > keep_bytes) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(a->ptr[slot[k]]);
+            a->ptr[slot[k]] = nullptr; a->bytes[slot[k]] = 0;
+        }
+}
 }  // namespace ldx
 
 // ------------------------------------------------------------------------------------------ lifecycle
@@ -831,6 +842,46 @@ static int stage_window(ldx_store *s, const int64_t *q_row, const int64_t *lo, c
     return LDX_OK;
 }
 
+// Work list of the multi-query window kernel: queries sorted by (lo, hi); one record per 256-row block of the store that
+// some query needs, with the (contiguous, because the bounds are monotone) run of queries whose candidate range meets it;
+// the kernel cuts each run into groups of WINDOW_MQ.  O(blocks + queries) on the host.  Returns false when the bounds are not
+// monotone in that order (then the single-query kernel is used).
+static bool build_mq_blocks(const int64_t *lo, const int64_t *hi, int64_t nq, std::vector<int32_t> &order, std::vector<WindowMqBlock> &blocks,
+                            int64_t *n_items_out) {
+    order.clear(); blocks.clear();
+    *n_items_out = 0;
+    order.reserve((size_t)nq);
+    bool sorted = true;
+    for (int64_t k = 0; k < nq; ++k)
+        if (hi[k] > lo[k]) {
+            if (!order.empty() && (lo[k] < lo[order.back()] || (lo[k] == lo[order.back()] && hi[k] < hi[order.back()]))) sorted = false;
+            order.push_back((int32_t)k);
+        }
+    if (!sorted)
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return lo[a] != lo[b] ? lo[a] < lo[b] : hi[a] < hi[b]; });
+    const size_t n = order.size();
+    for (size_t k = 1; k < n; ++k)
+        if (hi[order[k]] < hi[order[k - 1]]) return false;
+    if (n == 0) return true;
+    const int64_t B = WINDOW_CHUNK;
+    blocks.reserve((size_t)((hi[order[n - 1]] - lo[order[0]]) / B + 2));
+    size_t a = 0, b = 0;
+    int64_t n_items = 0;
+    for (int64_t blk = lo[order[0]] / B; a < n;) {
+        const int64_t begin = blk * B, end = begin + B;
+        while (a < n && hi[order[a]] <= begin) ++a;                 // candidate ranges that end before this block
+        if (a == n) break;
+        if (lo[order[a]] >= end) { blk = lo[order[a]] / B; continue; }   // nobody needs this block: jump to the next needed one
+        if (b < a) b = a;
+        while (b < n && lo[order[b]] < end) ++b;                    // order[a .. b) meet the block
+        blocks.push_back(WindowMqBlock{begin, n_items, (int32_t)a, (int32_t)b});
+        n_items += (int64_t)((b - a + WINDOW_MQ - 1) / WINDOW_MQ);
+        ++blk;
+    }
+    *n_items_out = n_items;
+    return true;
+}
+
 extern "C" int32_t ldx_window_dev(ldx_store *s, const int64_t *q_row, const int64_t *lo, const int64_t *hi,
                                   const int32_t *win_start, const int32_t *win_end, int64_t nq,
                                   int32_t measure, int32_t thres_e4, ldx_hit *dev_hits, int64_t cap,
@@ -844,7 +895,28 @@ extern "C" int32_t ldx_window_dev(ldx_store *s, const int64_t *q_row, const int6
     // dev_n_hits: [0] hits, [1] pairs scanned
     LDX_CUDA(cudaMemsetAsync(dev_n_hits, 0, 2 * sizeof(int64_t), ctx->stream));
     if (nq == 0 || n_chunks == 0) return LDX_OK;
+    // Several queries with overlapping windows (the usual ld_area job): the multi-query kernel loads every store row once
+    // per WINDOW_MQ queries instead of once per query.  LDX_WINDOW_MQ=0 forces the single-query kernel.
+    static const bool mq_off = getenv("LDX_WINDOW_MQ") && atoi(getenv("LDX_WINDOW_MQ")) == 0;
+    std::vector<int32_t> order;
+    std::vector<WindowMqBlock> blocks;
+    int64_t n_items = 0;
+    const bool use_mq = !mq_off && nq >= 2 && window_mq_supported(s) && build_mq_blocks(lo, hi, nq, order, blocks, &n_items) &&
+                        n_items < 0x7fffffffll && n_items * WINDOW_MQ < 3 * n_chunks;   // else: the windows barely overlap
     LDX_TRY(begin_dev_call(ctx));
+    if (use_mq) {
+        std::vector<WindowMqQuery> sorted(order.size());
+        for (size_t k = 0; k < order.size(); ++k) { const int32_t q = order[k]; sorted[k] = WindowMqQuery{q, q_row[q], lo[q], hi[q]}; }
+        uint8_t *blk;
+        const size_t blk_bytes = blocks.size() * sizeof(WindowMqBlock), srt_bytes = sorted.size() * sizeof(WindowMqQuery);
+        LDX_TRY(arena_get(ctx, S_IB, blk_bytes + srt_bytes + 64, (void **)&blk));
+        LDX_CUDA(cudaMemcpyAsync(blk, blocks.data(), blk_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        LDX_CUDA(cudaMemcpyAsync(blk + blk_bytes, sorted.data(), srt_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        LDX_CUDA(cudaStreamSynchronize(ctx->stream));   // blocks / sorted are locals
+        LDX_TRY(launch_window_mq(s, arr[0], arr[1], arr[2], (const int32_t *)arr[4], (const int32_t *)arr[5], nq, blk, (int64_t)blocks.size(),
+                                 blk + blk_bytes, reinterpret_cast<unsigned int *>(blk + blk_bytes + srt_bytes), measure, thres_e4, dev_hits, cap,
+                                 reinterpret_cast<unsigned long long *>(dev_n_hits)));
+    } else
     LDX_TRY(launch_window(s, arr[0], arr[1], arr[2], (const int32_t *)arr[4], (const int32_t *)arr[5], arr[3], nq,
                           n_chunks, measure, thres_e4, dev_hits, cap, reinterpret_cast<unsigned long long *>(dev_n_hits)));
     ++ctx->seq;

@@ -130,5 +130,12 @@ void timing_begin(ldx_ctx *ctx);
 void timing_end(ldx_ctx *ctx);
 
 constexpr int WINDOW_CHUNK = 256;   // rows per work item of the window kernel
+constexpr int WINDOW_MQ = 4;        // queries per work item of the multi-query window kernel (ldx_window.cu: MQ)
+struct WindowMqBlock { int64_t base, first_item; int32_t a, b; };   // = ldx::MqBlock (ldx_window.cu)
+struct WindowMqQuery { int64_t q, qrow, lo, hi; };                  // = ldx::MqQuery
+bool window_mq_supported(const ldx_store *s);
+int launch_window_mq(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, const int64_t *d_hi, const int32_t *d_ws, const int32_t *d_we,
+                     int64_t nq, const void *d_blocks, int64_t n_blocks, const void *d_sorted, unsigned int *d_next, int measure, int thres_e4,
+                     ldx_hit *d_hits, int64_t cap, unsigned long long *d_counters);
 
 }  // namespace ldx

@@ -173,6 +173,7 @@ merge_status_kernel(ldx_vcf_row *__restrict__ rows, const uint8_t *__restrict__ 
 int launch_pack_gt(ldx_ctx *ctx, const uint8_t *d_text, const int64_t *d_row_off, int64_t row_pitch, int64_t n_rows, int32_t n_samples,
                    uint64_t *d_planes_first, int32_t stride_words, uint8_t *d_status);
 int scratch_get(ldx_ctx *ctx, int which, size_t bytes, void **out);      // ldx_api.cu: block `which` (0..2) of the context's arena
+void scratch_trim(ldx_ctx *ctx, size_t keep_bytes);                      // ... and: free those blocks if larger than keep_bytes
 
 // Scratch comes from the context's arena (three blocks, one per phase: their sizes depend on counts only known after the
 // previous phase) -- cudaMalloc / cudaFree of a dozen buffers per call cost more than the kernels.
@@ -280,6 +281,7 @@ extern "C" int32_t ldx_store_ingest_vcf(ldx_ctx *ctx, const uint8_t *text, int64
             rc = cuda_fail(cudaGetLastError(), "vcf ingest: rows download");
     }
     if (cudaStreamSynchronize(st) != cudaSuccess && rc == LDX_OK) rc = cuda_fail(cudaGetLastError(), "vcf ingest");
+    scratch_trim(ctx, (size_t)256 << 20);      // the text of a whole chromosome does not stay behind in the arena
     if (rc != LDX_OK) { ldx_store_destroy(s); return rc; }
     s->annotated = true;
     *store_out = s;

@@ -68,6 +68,185 @@ __device__ __forceinline__ bool screen_below(int32_t n11, int32_t N, int32_t n1a
     return __fadd_rn(x, err) < t_minus;      // false for NaN: falls to the exact path
 }
 
+// The per-row tail of both window kernels: thread `tid` owns store row `row` of query q (row >= the query's lo by
+// construction; rows at or beyond `hi` are not candidates).  Filters, single-precision screen, exact finalisation, rounded
+// threshold, and the warp-aggregated append of the kept pair.  Every thread of the warp must call it.
+__device__ __forceinline__ void row_epilogue(const WindowArgs &A, int64_t q, int64_t qrow, int64_t row, int64_t hi, int n11, int tid,
+                                             unsigned long long &scanned) {
+    bool pass = false;
+    uint32_t packed = 0;
+    if (row < hi) {
+        const int32_t ws = A.win_start[q], we = A.win_end[q];
+        const bool scan = A.pos0[row] < we && A.end0[row] > ws      // fetch overlap, ld_area.py:215-217
+                          && A.eligible[row]                           // rs\d+$ and not MULTI_ALLELIC, :223-224
+                          && A.idnum[row] != A.idnum[qrow];            // :222
+        if (scan) ++scanned;
+        if (scan && !(A.screen_t > 0.0f && screen_below(n11, A.n_sel, A.freq[qrow].n1, A.freq[row].n1, A.measure, A.screen_t, A.screen_g))) {
+            const VarFreq fa = A.freq[qrow], fb = A.freq[row];         // var_1 = query, var_2 = row (:242)
+            const PairFinal f = finalise_pair(n11, fa, fb, A.fc);
+            packed = f.packed;
+            int32_t m = measure_e4(packed, A.measure);
+            if (A.measure == LDX_MEASURE_R2 && (packed & LDX_R2_NEARTIE)) ++m;   // keep; host settles the tie
+            pass = m >= A.thres_e4;                                    // rounded value, :248
+        }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+    if (ballot) {
+        const int lane = tid & 31;
+        unsigned long long slot0 = 0;
+        if (lane == __ffs(ballot) - 1) slot0 = atomicAdd(A.counters, (unsigned long long)__popc(ballot));
+        slot0 = __shfl_sync(0xffffffffu, slot0, __ffs(ballot) - 1);
+        if (pass) {
+            const unsigned long long slot = slot0 + __popc(ballot & ((1u << lane) - 1));
+            if ((int64_t)slot < A.cap) {
+                // ldx_hit = {query, row, n11, packed}: one 16-byte store
+                *reinterpret_cast<uint4 *>(A.hits + slot) =
+                    make_uint4((uint32_t)q, (uint32_t)row, (uint32_t)n11, packed);
+                if (packed & LDX_R2_NEARTIE)
+                    fixup_append(A.fix, slot, n11, A.freq[qrow].n1, A.freq[row].n1, packed);
+            }
+        }
+    }
+}
+
+// 8 x 8 transpose-reduce over the lanes of a group: in, cnt[i] = this lane's partial count of row i; out, the total of row
+// i = lane8.
+__device__ __forceinline__ int transpose_reduce8(int (&cnt)[8], int lane8) {
+    {
+        const bool up = lane8 & 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int send = up ? cnt[i] : cnt[i + 4];
+            const int keep = up ? cnt[i + 4] : cnt[i];
+            cnt[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool up = lane8 & 2;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int send = up ? cnt[i] : cnt[i + 2];
+            const int keep = up ? cnt[i + 2] : cnt[i];
+            cnt[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+    }
+    const bool up = lane8 & 1;
+    const int send = up ? cnt[0] : cnt[1];
+    const int keep = up ? cnt[1] : cnt[0];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+// ------------------------------------------------------------------------------------------ multi-query kernel
+// The single-query kernel above reads every candidate row once PER QUERY: 9 TB/s of L2 traffic at configs[2], three
+// quarters of what the L2 slices deliver, with the POPC pipe 57% busy.  Windows of neighbouring queries overlap almost
+// completely (+/-500 kb windows of queries ~35 kb apart), so this kernel turns the loop inside out: a work item is a
+// 256-row block of the store and up to MQ queries whose windows cover it; the block's rows are loaded once into registers
+// and counted against all MQ query planes, which sit (mask folded in) in shared memory.  L2 traffic per pair drops by MQ
+// and the POPC pipe becomes the limit.  Needs the queries sorted with monotone window bounds (the host checks).
+constexpr int MQ = 4;
+// One record per 256-row block that some query needs: rows base .. base+255, met by the queries at sorted positions
+// a .. b-1 (MqQuery records); the kernel walks them in groups of MQ.
+struct MqBlock { int64_t base, first_item; int32_t a, b; };
+struct MqQuery { int64_t q, qrow, lo, hi; };               // query index of the call, its store row, its candidate range
+
+template <int NG, bool L1ROWS>
+__global__ void __launch_bounds__(WIN_THREADS, 2)
+window_mq_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int64_t n_blocks, const MqQuery *__restrict__ sorted,
+                 unsigned int *__restrict__ next_block, int64_t n_rows) {
+    // double-buffered per group of queries: their planes (mask folded in) and their records
+    __shared__ uint4 qs[2][MQ][NG * 8];
+    __shared__ int64_t s_q[2][MQ], s_qrow[2][MQ], s_lo[2][MQ], s_hi[2][MQ];
+    __shared__ unsigned int s_j;
+    constexpr int PL = MQ * NG * 8;                         // threads that fetch one 16-byte granule of one query plane each
+    static_assert(PL <= WIN_THREADS, "plane loaders");
+    const int tid = threadIdx.x, lane8 = tid & 7, group = tid >> 3;
+    const int k_pl = tid / (NG * 8), g_pl = tid % (NG * 8);
+    unsigned long long scanned = 0;
+    for (;;) {
+        // blocks cost one pass per group of queries that meets them (1 .. ~10): handed out dynamically
+        if (tid == 0) s_j = atomicAdd(next_block, 1u);
+        __syncthreads();
+        const unsigned int j = s_j;
+        if (j >= n_blocks) break;
+        const MqBlock blk = blocks[j];
+        const int n_groups = (blk.b - blk.a + MQ - 1) / MQ;
+        // ---- the block's first group, synchronously; the store row of the second group's plane granule for later
+        if (tid < MQ) {
+            const MqQuery m = sorted[min(blk.a + tid, blk.b - 1)];
+            s_q[0][tid] = m.q; s_qrow[0][tid] = m.qrow; s_lo[0][tid] = m.lo; s_hi[0][tid] = blk.a + tid < blk.b ? m.hi : 0;
+        }
+        int64_t qrow_next = 0;
+        if (tid < PL) {
+            const int64_t qrow0 = sorted[min(blk.a + k_pl, blk.b - 1)].qrow;
+            const uint4 x = ldg_u4(A.planes + qrow0 * A.stride_u4 + g_pl), m = __ldg(A.mask + g_pl);
+            qs[0][k_pl][g_pl] = make_uint4(x.x & m.x, x.y & m.y, x.z & m.z, x.w & m.w);
+            qrow_next = sorted[min(blk.a + MQ + k_pl, blk.b - 1)].qrow;
+        }
+        __syncthreads();
+        for (int g = 0; g < n_groups; ++g) {
+            const int cur = g & 1, q0 = blk.a + g * MQ, nq = min(MQ, blk.b - q0);
+            // ---- the NEXT group's plane granule and records, requested now and parked in shared memory after this
+            //      group's work: single independent loads (the host pre-sorted the records), so nobody stalls on them
+            uint4 nx = make_uint4(0, 0, 0, 0), mk = nx;
+            MqQuery mnext = {0, 0, 0, 0};
+            const bool more = g + 1 < n_groups;
+            int64_t qrow_next2 = 0;
+            if (more && tid < PL) {
+                nx = ldg_u4(A.planes + qrow_next * A.stride_u4 + g_pl); mk = __ldg(A.mask + g_pl);
+                qrow_next2 = sorted[min(q0 + 2 * MQ + k_pl, blk.b - 1)].qrow;
+            }
+            if (more && tid < MQ) mnext = sorted[min(q0 + MQ + tid, blk.b - 1)];
+            // ---- counting: group of lanes covers rows base + 8 * group + i, each loaded once for all queries of this pass
+            int cnt[MQ][8];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+                const int64_t r0 = blk.base + group * 8 + i, r1 = r0 + 1;
+                const uint4 *p0 = A.planes + (r0 < n_rows ? r0 : n_rows - 1) * A.stride_u4 + lane8;
+                const uint4 *p1 = A.planes + (r1 < n_rows ? r1 : n_rows - 1) * A.stride_u4 + lane8;
+                uint4 x0[NG], x1[NG];
+#pragma unroll
+                for (int jj = 0; jj < NG; ++jj) {
+                    x0[jj] = L1ROWS ? ldg_u4(p0 + jj * 8) : ldg_u4_stream(p0 + jj * 8);
+                    x1[jj] = L1ROWS ? ldg_u4(p1 + jj * 8) : ldg_u4_stream(p1 + jj * 8);
+                }
+#pragma unroll
+                for (int k = 0; k < MQ; ++k) {
+                    int c0 = 0, c1 = 0;
+                    if (k < nq) {                           // block-uniform
+#pragma unroll
+                        for (int jj = 0; jj < NG; ++jj) {
+                            const uint4 qm = qs[cur][k][jj * 8 + lane8];
+                            c0 += popc_and_u4(x0[jj], qm); c1 += popc_and_u4(x1[jj], qm);
+                        }
+                    }
+                    cnt[k][i] = c0; cnt[k][i + 1] = c1;
+                }
+            }
+            // ---- per query: transpose-reduce, then thread t owns row base + t
+#pragma unroll
+            for (int k = 0; k < MQ; ++k) {
+                if (k < nq) {                               // block-uniform
+                    const int n11 = transpose_reduce8(cnt[k], lane8);
+                    const int64_t row = blk.base + tid;
+                    // rows before the query's lo are not candidates either: hi = 0 switches the row off
+                    row_epilogue(A, s_q[cur][k], s_qrow[cur][k], row, row >= s_lo[cur][k] ? s_hi[cur][k] : 0, n11, tid, scanned);
+                }
+            }
+            if (more) {
+                if (tid < PL) qs[cur ^ 1][k_pl][g_pl] = make_uint4(nx.x & mk.x, nx.y & mk.y, nx.z & mk.z, nx.w & mk.w);
+                if (tid < MQ) {
+                    s_q[cur ^ 1][tid] = mnext.q; s_qrow[cur ^ 1][tid] = mnext.qrow; s_lo[cur ^ 1][tid] = mnext.lo;
+                    s_hi[cur ^ 1][tid] = q0 + MQ + tid < blk.b ? mnext.hi : 0;
+                }
+            }
+            qrow_next = qrow_next2;
+            __syncthreads();
+        }
+    }
+    for (int o = 16; o; o >>= 1) scanned += __shfl_xor_sync(0xffffffffu, scanned, o);
+    if ((tid & 31) == 0 && scanned) atomicAdd(A.counters + 1, scanned);
+}
+
 template <int NG>   // NG = 16-byte granules per lane per row; 0 = runtime loop
 __global__ void __launch_bounds__(WIN_THREADS, 3)
 window_kernel(const WindowArgs A) {
@@ -127,68 +306,10 @@ window_kernel(const WindowArgs A) {
             }
         }
         // ---- transpose-reduce over the 8 lanes: lane l ends with the total of row i = l
-        {
-            const bool up = lane8 & 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int send = up ? cnt[i] : cnt[i + 4];
-                const int keep = up ? cnt[i + 4] : cnt[i];
-                cnt[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-        }
-        {
-            const bool up = lane8 & 2;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int send = up ? cnt[i] : cnt[i + 2];
-                const int keep = up ? cnt[i + 2] : cnt[i];
-                cnt[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
-        }
-        int n11;
-        {
-            const bool up = lane8 & 1;
-            const int send = up ? cnt[0] : cnt[1];
-            const int keep = up ? cnt[1] : cnt[0];
-            n11 = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-        }
+        const int n11 = transpose_reduce8(cnt, lane8);
 
         // ---- epilogue: thread t owns row base + t
-        const int64_t row = base + tid;
-        bool pass = false;
-        uint32_t packed = 0;
-        if (row < hi) {
-            const int32_t ws = A.win_start[q], we = A.win_end[q];
-            const bool scan = A.pos0[row] < we && A.end0[row] > ws      // fetch overlap, ld_area.py:215-217
-                              && A.eligible[row]                           // rs\d+$ and not MULTI_ALLELIC, :223-224
-                              && A.idnum[row] != A.idnum[qrow];            // :222
-            if (scan) ++scanned;
-            if (scan && !(A.screen_t > 0.0f && screen_below(n11, A.n_sel, A.freq[qrow].n1, A.freq[row].n1, A.measure, A.screen_t, A.screen_g))) {
-                const VarFreq fa = A.freq[qrow], fb = A.freq[row];         // var_1 = query, var_2 = row (:242)
-                const PairFinal f = finalise_pair(n11, fa, fb, A.fc);
-                packed = f.packed;
-                int32_t m = measure_e4(packed, A.measure);
-                if (A.measure == LDX_MEASURE_R2 && (packed & LDX_R2_NEARTIE)) ++m;   // keep; host settles the tie
-                pass = m >= A.thres_e4;                                    // rounded value, :248
-            }
-        }
-        const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-        if (ballot) {
-            const int lane = tid & 31;
-            unsigned long long slot0 = 0;
-            if (lane == __ffs(ballot) - 1) slot0 = atomicAdd(A.counters, (unsigned long long)__popc(ballot));
-            slot0 = __shfl_sync(0xffffffffu, slot0, __ffs(ballot) - 1);
-            if (pass) {
-                const unsigned long long slot = slot0 + __popc(ballot & ((1u << lane) - 1));
-                if ((int64_t)slot < A.cap) {
-                    // ldx_hit = {query, row, n11, packed}: one 16-byte store
-                    *reinterpret_cast<uint4 *>(A.hits + slot) =
-                        make_uint4((uint32_t)q, (uint32_t)row, (uint32_t)n11, packed);
-                    if (packed & LDX_R2_NEARTIE)
-                        fixup_append(A.fix, slot, n11, A.freq[qrow].n1, A.freq[row].n1, packed);
-                }
-            }
-        }
+        row_epilogue(A, q, qrow, base + tid, hi, n11, tid, scanned);
     }
     // pairs scanned (for the bench's pairs/s figure): one atomic per warp
     for (int o = 16; o; o >>= 1) scanned += __shfl_xor_sync(0xffffffffu, scanned, o);
@@ -212,6 +333,67 @@ static int launch_window_ng(ldx_ctx *ctx, const WindowArgs &A) {
     ctx->launches++;
     LDX_LAUNCHED(ctx, "window_kernel");
     return LDX_OK;
+}
+
+template <int NG>
+static int launch_window_mq_ng(ldx_ctx *ctx, const WindowArgs &A, const MqBlock *d_blocks, int64_t n_blocks, const MqQuery *d_sorted,
+                               unsigned int *d_next, int64_t n_rows) {
+    static int per_sm = 0;
+    static const bool l1rows = !(getenv("LDX_WINDOW_MQ_L1") && atoi(getenv("LDX_WINDOW_MQ_L1")) == 0);
+    if (!per_sm) {
+        LDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, window_mq_kernel<NG, true>, WIN_THREADS, 0));
+        if (per_sm < 1) per_sm = 1;
+    }
+    int64_t grid = (int64_t)ctx->sm_count * per_sm;
+    if (grid > n_blocks) grid = n_blocks;
+    LDX_CUDA(cudaMemsetAsync(d_next, 0, sizeof(unsigned int), ctx->stream));
+    timing_begin(ctx);
+    if (l1rows) window_mq_kernel<NG, true><<<(int)grid, WIN_THREADS, 0, ctx->stream>>>(A, d_blocks, n_blocks, d_sorted, d_next, n_rows);
+    else window_mq_kernel<NG, false><<<(int)grid, WIN_THREADS, 0, ctx->stream>>>(A, d_blocks, n_blocks, d_sorted, d_next, n_rows);
+    timing_end(ctx);
+    ctx->launches++;
+    LDX_LAUNCHED(ctx, "window_mq_kernel");
+    return LDX_OK;
+}
+
+static void fill_window_args(ldx_store *s, WindowArgs &A, const int64_t *d_qrow, const int64_t *d_lo, const int64_t *d_hi, const int32_t *d_ws,
+                             const int32_t *d_we, int64_t nq, int measure, int thres_e4, ldx_hit *d_hits, int64_t cap, unsigned long long *d_counters) {
+    ldx_ctx *ctx = s->ctx;
+    A.planes = reinterpret_cast<const uint4 *>(s->d_planes);
+    A.mask = reinterpret_cast<const uint4 *>(s->d_mask);
+    A.stride_u4 = s->stride_words / 2;
+    A.freq = s->d_freq; A.fc = s->fc;
+    A.pos0 = s->d_pos0; A.end0 = s->d_end0; A.idnum = s->d_idnum; A.eligible = s->d_eligible;
+    A.q_row = d_qrow; A.lo = d_lo; A.hi = d_hi; A.win_start = d_ws; A.win_end = d_we;
+    A.chunk_prefix = nullptr; A.nq = nq; A.n_chunks = 0;
+    A.measure = measure; A.thres_e4 = thres_e4;
+    A.n_sel = s->n_sel;
+    const double n = (double)s->n_sel, g = 1.0e4 * 16.0 * 1.1102230246251565e-16 * n * n;
+    A.screen_g = (float)(g + 1.0e-4);
+    A.screen_t = (s->n_sel <= 8192 && thres_e4 > 0) ? (float)((double)thres_e4 - 0.5 - 1.0e-3) : 0.0f;
+    A.hits = d_hits; A.cap = cap; A.counters = d_counters;
+    A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity, ctx->fix_tag};
+}
+
+bool window_mq_supported(const ldx_store *s) { const int ng = s->stride_words / 16; return ng == 1 || ng == 2 || ng == 5; }
+
+// d_blocks: MqBlock records, d_sorted: MqQuery records in sorted order (WindowMqBlock / WindowMqQuery on the host side);
+// d_next: one word of device scratch for the dynamic block counter
+int launch_window_mq(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, const int64_t *d_hi, const int32_t *d_ws, const int32_t *d_we,
+                     int64_t nq, const void *d_blocks, int64_t n_blocks, const void *d_sorted, unsigned int *d_next, int measure, int thres_e4,
+                     ldx_hit *d_hits, int64_t cap, unsigned long long *d_counters) {
+    if (n_blocks <= 0) return LDX_OK;
+    static_assert(sizeof(MqBlock) == sizeof(WindowMqBlock) && sizeof(MqQuery) == sizeof(WindowMqQuery), "host and device work-list records");
+    WindowArgs A;
+    fill_window_args(s, A, d_qrow, d_lo, d_hi, d_ws, d_we, nq, measure, thres_e4, d_hits, cap, d_counters);
+    const MqBlock *blocks = reinterpret_cast<const MqBlock *>(d_blocks);
+    const MqQuery *sorted = reinterpret_cast<const MqQuery *>(d_sorted);
+    switch (A.stride_u4 / 8) {
+        case 1: return launch_window_mq_ng<1>(s->ctx, A, blocks, n_blocks, sorted, d_next, s->n_variants);
+        case 2: return launch_window_mq_ng<2>(s->ctx, A, blocks, n_blocks, sorted, d_next, s->n_variants);
+        case 5: return launch_window_mq_ng<5>(s->ctx, A, blocks, n_blocks, sorted, d_next, s->n_variants);
+        default: return set_error(LDX_ERR_STATE, "multi-query window kernel: unsupported row pitch");
+    }
 }
 
 int launch_window(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, const int64_t *d_hi,

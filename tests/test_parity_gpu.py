@@ -305,6 +305,46 @@ def test_window_matches_oracle_full_scan(ctx, measure, thres):
     st.close()
 
 
+@pytest.mark.parametrize("n_hap,thres", [(5008, 0.0), (5008, 0.3), (198, 0.2), (1006, 0.05)])
+def test_window_many_overlapping_queries_any_order(ctx, n_hap, thres):
+    """The multi-query window kernel's territory: hundreds of queries whose windows cover a large part of the store and
+    each other, passed in arbitrary order, with repeated queries and an empty candidate range among them; kept rows,
+    counts and packed words per query against the oracle's full scan."""
+    from ld_tools_b200.engine import threshold_e4
+    n_var = 2500
+    st, planes, mask, pos0, end0, idnum, elig = annotated_store(ctx, n_var, n_hap, seed=41 + n_hap)
+    rng = np.random.default_rng(n_hap)
+    q_rows = rng.choice(np.flatnonzero(elig), 300, replace=True)              # unsorted, with repeats
+    flank = 20000                                                              # ~1000 of the 2500 rows per window
+    pos = pos0 + 1
+    low = np.maximum(pos[q_rows] - flank, 0)
+    high = pos[q_rows] + flank
+    max_len = int((end0 - pos0).max())
+    lo = np.searchsorted(pos0, low - max_len, side="left")
+    hi = np.searchsorted(pos0, high, side="left")
+    hi[7] = lo[7]                                                              # one query without candidates
+    hits, scanned = st.window(q_rows, lo, hi, low, high, "r_square", threshold_e4(thres))
+    total = 0
+    for k, q in enumerate(q_rows):
+        rows, res = ld_oracle.window(planes, mask, n_hap, pos0, end0, idnum, elig, q, low[k], high[k], 0, thres, lo=int(lo[k]), hi=int(hi[k]))
+        mine = hits[hits["query"] == k]
+        assert mine["row"].tolist() == rows.tolist(), (k, q)
+        assert (mine["n11"] == res["n_11"]).all() and (mine["packed"] == ld_oracle.packed_of(res)).all()
+        total += len(rows)
+    assert len(hits) == total and total > 0
+    if thres == 0.0:
+        assert scanned == len(hits)
+    # windows of different widths: the bounds are no longer monotone and the single-query kernel takes over -- same answers
+    hi2 = hi.copy()
+    hi2[::3] = np.minimum(lo[::3] + 40, hi[::3])
+    hits2, _ = st.window(q_rows, lo, hi2, low, high, "r_square", threshold_e4(thres))
+    for k in (0, 3, 4, 150, 299):
+        rows, res = ld_oracle.window(planes, mask, n_hap, pos0, end0, idnum, elig, q_rows[k], low[k], high[k], 0, thres, lo=int(lo[k]), hi=int(hi2[k]))
+        mine = hits2[hits2["query"] == k]
+        assert mine["row"].tolist() == rows.tolist() and (mine["packed"] == ld_oracle.packed_of(res)).all()
+    st.close()
+
+
 def test_window_edge_cases(ctx):
     from ld_tools_b200.engine import threshold_e4
     st, planes, mask, pos0, end0, idnum, elig = annotated_store(ctx, 600, 198, seed=44)

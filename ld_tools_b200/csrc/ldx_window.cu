@@ -136,6 +136,42 @@ __device__ __forceinline__ int transpose_reduce8(int (&cnt)[8], int lane8) {
     return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
+// ------------------------------------------------------------------------------------------ carry-save popcount
+// popcount(x & q) over a lane's 20 words (5008 haplotypes: five 16-byte granules per lane) with 6 POPC instead of 20.  POPC
+// issues on the XU pipe at 16 lanes/clk/SM, LOP3 on the ALU pipe at 64: a carry-save adder (sum = a^b^c, carry = maj(a,b,c),
+// two LOP3) turns three words of weight w into one of weight w and one of weight 2w, and a tree of 14 of them leaves
+// 2 + 1 + 2 + 1 words of weight 1, 2, 4, 8 (Harley-Seal).  48 LOP3 + 6 POPC: bound by the ALU pipe at ~26 clk per (row, query)
+// and lane group instead of 40 on the XU pipe.
+__device__ __forceinline__ void csa(uint32_t &h, uint32_t &l, uint32_t a, uint32_t b, uint32_t c) {
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(l) : "r"(a), "r"(b), "r"(c));      // a ^ b ^ c
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(h) : "r"(a), "r"(b), "r"(c));      // majority
+}
+__device__ __forceinline__ int popc_and_20(const uint4 (&x)[5], const uint4 *__restrict__ q, int lane8) {
+    uint32_t w[20];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const uint4 m = q[j * 8 + lane8];
+        w[4 * j] = x[j].x & m.x; w[4 * j + 1] = x[j].y & m.y; w[4 * j + 2] = x[j].z & m.z; w[4 * j + 3] = x[j].w & m.w;
+    }
+    uint32_t o[8], t[9], f[4], e, hh, ll;
+    // weight 1: 20 words -> 2
+#pragma unroll
+    for (int k = 0; k < 6; ++k) csa(t[k], o[k], w[3 * k], w[3 * k + 1], w[3 * k + 2]);
+    o[6] = w[18]; o[7] = w[19];
+    csa(t[6], o[0], o[0], o[1], o[2]);
+    csa(t[7], o[1], o[3], o[4], o[5]);
+    csa(t[8], o[0], o[0], o[1], o[6]);              // weight-1 words left: o[0], o[7]
+    // weight 2: 9 words -> 1
+    csa(f[0], t[0], t[0], t[1], t[2]);
+    csa(f[1], t[1], t[3], t[4], t[5]);
+    csa(f[2], t[2], t[6], t[7], t[8]);
+    csa(f[3], t[0], t[0], t[1], t[2]);              // weight-2 word left: t[0]
+    // weight 4: 4 words -> 2, weight 8: 1
+    csa(e, f[0], f[0], f[1], f[2]);                 // weight-4 words left: f[0], f[3]
+    (void)hh; (void)ll;
+    return __popc(o[0]) + __popc(o[7]) + 2 * __popc(t[0]) + 4 * (__popc(f[0]) + __popc(f[3])) + 8 * __popc(e);
+}
+
 // ------------------------------------------------------------------------------------------ multi-query kernel
 // The single-query kernel above reads every candidate row once PER QUERY: 9 TB/s of L2 traffic at configs[2], three
 // quarters of what the L2 slices deliver, with the POPC pipe 57% busy.  Windows of neighbouring queries overlap almost
@@ -213,10 +249,15 @@ window_mq_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int64_t
                 for (int k = 0; k < MQ; ++k) {
                     int c0 = 0, c1 = 0;
                     if (k < nq) {                           // block-uniform
+                        if (NG == 5) {
+                            c0 = popc_and_20(reinterpret_cast<const uint4 (&)[5]>(x0), &qs[cur][k][0], lane8);
+                            c1 = popc_and_20(reinterpret_cast<const uint4 (&)[5]>(x1), &qs[cur][k][0], lane8);
+                        } else {
 #pragma unroll
-                        for (int jj = 0; jj < NG; ++jj) {
-                            const uint4 qm = qs[cur][k][jj * 8 + lane8];
-                            c0 += popc_and_u4(x0[jj], qm); c1 += popc_and_u4(x1[jj], qm);
+                            for (int jj = 0; jj < NG; ++jj) {
+                                const uint4 qm = qs[cur][k][jj * 8 + lane8];
+                                c0 += popc_and_u4(x0[jj], qm); c1 += popc_and_u4(x1[jj], qm);
+                            }
                         }
                     }
                     cnt[k][i] = c0; cnt[k][i + 1] = c1;

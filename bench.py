@@ -525,9 +525,11 @@ def run_area(args, rank, world, local_rank):
     row_bytes = st.stride_words * 8
     kern_s = dom_ms * 1e-3 / max(dom_n, 1)
     roof = {"bound": "hbm", "achieved": scanned * row_bytes / kern_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "peak_source": f"{peaks['source']} copy bandwidth", "traffic": ncu_traffic("r01_ncu_full_window_configs2.txt"), "kernel": "window_kernel", "kernel_ms": kern_s * 1e3,
+            "peak_source": f"{peaks['source']} copy bandwidth", "traffic": ncu_traffic("r01_ncu_full_window_mq_configs2.txt"), "kernel": "window_mq_kernel",
+            "kernel_ms": kern_s * 1e3,
             "kernel_launches_timed": int(dom_n),
-            "algorithmic_per_launch": f"{scanned} pairs x {row_bytes} B (one candidate row each; query plane and mask in registers)"}
+            "algorithmic_per_launch": f"{scanned} pairs x {row_bytes} B (one candidate row per pair; the multi-query kernel loads a row once per "
+                                      f"four queries and re-reads it from L1 for the other groups, hence frac > 1)"}
     roof["frac"] = roof["achieved"] / roof["peak"]
     line = {"metric": "variant pairs/sec (r2+D', 5008 haplotypes)", "value": scanned * world * args.steps / (step_ms * 1e-3),
             "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms / args.steps,

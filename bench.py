@@ -443,7 +443,7 @@ def run_area(args, rank, world, local_rank):
     import torch.distributed as dist
     from ld_tools_b200 import Context, Store, shard
     from ld_tools_b200.engine import threshold_e4
-    from ld_tools_b200.synth import random_planes
+    from ld_tools_b200.synth import fill_store_grouped
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -456,9 +456,7 @@ def run_area(args, rank, world, local_rank):
     rng = np.random.default_rng(77 + rank)
     nv = AREA_VARIANTS
     st = Store(ctx, nv, N_HAP)
-    for a in range(0, nv, 100_000):                                   # built in slabs: bounded host memory
-        b = min(a + 100_000, nv)
-        st.upload(a, random_planes(b - a, N_HAP, seed=1000 * rank + a))
+    fill_store_grouped(st, dev, 22 + rank, 0, nv)                     # generated on the GPU: groups of 8 neighbours in LD
     pos0 = np.sort(rng.integers(16_050_000, 51_200_000, size=nv)).astype(np.int32)
     end0 = pos0 + 1
     st.set_annotations(pos0, end0, np.arange(nv, dtype=np.int64), np.ones(nv, np.uint8))

@@ -155,6 +155,52 @@ def random_planes(n_variants, n_hap, seed=SEED, density=None):
 
 
 # ---------------------------------------------------------------------------------------------
+# Large stores generated ON the GPU (benchmarks at chromosome / genome scale)
+# ---------------------------------------------------------------------------------------------
+GEN_BLOCK = 1 << 18        # rows per generator block: the seed depends on (chromosome, block) only
+GEN_GROUP = 8              # neighbours sharing a base pattern
+
+
+class _DevView:
+    """A raw device address as a CUDA array: torch.as_tensor() wraps it without a copy."""
+
+    def __init__(self, addr, n_words):
+        self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (addr, False), "version": 3}
+
+
+def fill_store_grouped(store, dev, chrom, row_begin, row_end):
+    """Fill `store` (holding chromosome rows row_begin..row_end-1) on the GPU, straight into its planes.
+
+    Variants come in groups of 8 neighbours sharing a base pattern (alt frequency 1/4) with 1/64 of the haplotypes
+    flipped independently: neighbours are in strong LD (r2 ~ 0.85), everything else is not, so an r2 >= 0.8 filter keeps
+    a few pairs per query, as on real data.  The generator is seeded per (chromosome, 2^18-row block): every rank of a
+    sharded job sees the same genome whatever rows it holds."""
+    import torch
+    n_rows, stride, n_hap = row_end - row_begin, store.stride_words, store.n_hap
+    planes = torch.as_tensor(_DevView(store.planes_ptr, n_rows * stride), device=dev).view(n_rows, stride)
+    words = (n_hap + 63) // 64
+
+    def rnd(n, g):      # n x stride uniformly random 64-bit words (two int32 draws per word)
+        return torch.randint(-(1 << 31), 1 << 31, (n, 2 * stride), generator=g, device=dev, dtype=torch.int32).view(torch.int64)
+
+    for b in range(row_begin // GEN_BLOCK, (row_end + GEN_BLOCK - 1) // GEN_BLOCK):
+        g = torch.Generator(device=dev)
+        g.manual_seed(1_000_003 * (chrom + 1) + b)
+        base = rnd(GEN_BLOCK // GEN_GROUP, g) & rnd(GEN_BLOCK // GEN_GROUP, g)
+        noise = rnd(GEN_BLOCK, g)
+        for _ in range(5):
+            noise &= rnd(GEN_BLOCK, g)
+        rows = base.repeat_interleave(GEN_GROUP, dim=0) ^ noise
+        rows[:, words:] = 0
+        if n_hap & 63:
+            rows[:, words - 1] &= (1 << (n_hap & 63)) - 1
+        a, e = max(b * GEN_BLOCK, row_begin), min((b + 1) * GEN_BLOCK, row_end)
+        planes[a - row_begin:e - row_begin] = rows[a - b * GEN_BLOCK:e - b * GEN_BLOCK]
+        del base, noise, rows
+    torch.cuda.synchronize()
+
+
+# ---------------------------------------------------------------------------------------------
 # 1000G-format files: <dir>/<chrom>.vcf.gz, integrated_call_samples panel, conversion.db
 # ---------------------------------------------------------------------------------------------
 

@@ -36,40 +36,6 @@ sys.path.insert(0, ROOT)
 # GRCh38 autosome lengths (Mb), chr1..chr22
 CHR_MB = [248.96, 242.19, 198.30, 190.21, 181.54, 170.81, 159.35, 145.14, 138.39, 133.80, 135.09,
           133.28, 114.36, 107.04, 101.99, 90.34, 83.26, 80.37, 58.62, 64.44, 46.71, 50.82]
-BLOCK = 1 << 18            # rows per generator block
-GROUP = 8                  # neighbours sharing a base pattern
-
-
-class _DevView:
-    """A raw device address as a CUDA array: torch.as_tensor() wraps it without a copy."""
-
-    def __init__(self, addr, n_words):
-        self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (addr, False), "version": 3}
-
-
-def fill_rows(torch, dev, planes, stride, n_hap, chrom, row_begin, row_end):
-    """planes: int64 tensor view [rows, stride] of a store holding chromosome rows row_begin..row_end-1."""
-    words = (n_hap + 63) // 64
-
-    def rnd(n, g):      # n x stride uniformly random 64-bit words (two int32 draws per word)
-        return torch.randint(-(1 << 31), 1 << 31, (n, 2 * stride), generator=g, device=dev, dtype=torch.int32).view(torch.int64)
-
-    for b in range(row_begin // BLOCK, (row_end + BLOCK - 1) // BLOCK):
-        g = torch.Generator(device=dev)
-        g.manual_seed(1_000_003 * (chrom + 1) + b)
-        base = rnd(BLOCK // GROUP, g) & rnd(BLOCK // GROUP, g)
-        noise = rnd(BLOCK, g)
-        for _ in range(5):
-            noise &= rnd(BLOCK, g)
-        rows = base.repeat_interleave(GROUP, dim=0) ^ noise
-        rows[:, words:] = 0
-        if n_hap & 63:
-            rows[:, words - 1] &= (1 << (n_hap & 63)) - 1
-        a, e = max(b * BLOCK, row_begin), min((b + 1) * BLOCK, row_end)
-        planes[a - row_begin:e - row_begin] = rows[a - b * BLOCK:e - b * BLOCK]
-        del base, noise, rows
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--variants", type=int, default=80_000_000)
@@ -85,6 +51,7 @@ def main():
     from ld_tools_b200 import Context, Store, shard
     from ld_tools_b200._lib import BELOW_THRES, HIT_DTYPE, R2_MASK
     from ld_tools_b200.engine import threshold_e4
+    from ld_tools_b200.synth import fill_store_grouped
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -124,8 +91,7 @@ def main():
         c, qa, qb, rb, re = pc["chrom"], pc["qa"], pc["qb"], pc["row_begin"], pc["row_end"]
         ch = chroms[c]
         st = Store(ctx, re - rb, n_hap)
-        planes = torch.as_tensor(_DevView(st.planes_ptr, (re - rb) * st.stride_words), device=dev).view(re - rb, st.stride_words)
-        fill_rows(torch, dev, planes, st.stride_words, n_hap, c, rb, re)
+        fill_store_grouped(st, dev, c, rb, re)
         torch.cuda.synchronize()
         pos0 = ch["pos0"][rb:re]
         st.set_annotations(pos0, pos0 + 1, (np.int64(c) << 32) + np.arange(rb, re, dtype=np.int64), np.ones(re - rb, np.uint8))

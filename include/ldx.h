@@ -99,8 +99,10 @@ int32_t ldx_synchronize(ldx_ctx *ctx);
  *   LDX_TUNE_MMA_MIN_V   LDX_ENGINE_AUTO uses the tcgen05 engine from this many variants (256)
  *   LDX_TUNE_MMA_PAIR    1 = 256 x 128 tiles on CTA pairs (tcgen05.mma.cta_group::2), 0 = one CTA per 128 x 128 tile
  *   LDX_TUNE_DEFER_CAP   capacity of the tcgen05 engine's deferred-pair lists (0 = sized from the pair count); a
- *                        small value forces the overflow paths (pairs settled in place) -- for tests */
-enum { LDX_TUNE_MMA_TILE_N = 1, LDX_TUNE_MMA_MIN_V = 2, LDX_TUNE_MMA_PAIR = 3, LDX_TUNE_DEFER_CAP = 4 };
+ *                        small value forces the overflow paths (pairs settled in place) -- for tests
+ *   LDX_TUNE_WINDOW_MQ   1 (default) = window scans of several queries with monotone candidate ranges use the multi-query
+ *                        kernel (a store row is loaded once per four queries); 0 = always one query per pass */
+enum { LDX_TUNE_MMA_TILE_N = 1, LDX_TUNE_MMA_MIN_V = 2, LDX_TUNE_MMA_PAIR = 3, LDX_TUNE_DEFER_CAP = 4, LDX_TUNE_WINDOW_MQ = 5 };
 int32_t ldx_set_tuning(ldx_ctx *ctx, int32_t key, int32_t value);
 /* Diagnostics: with enable != 0 the tcgen05 all-pairs kernel's first CTA records %globaltimer
  * stamps (ns): [0] prologue done, [1]/[2] accumulator ready / epilogue done of its 1st tile,

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libldx.so")
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_EMPTY, ERR_CAPACITY, ERR_STATE, ERR_DATA = 0, -1, -2, -3, -4, -5, -6, -7
 MEASURE_R2, MEASURE_DPRIME = 0, 1
 ENGINE_AUTO, ENGINE_POPC, ENGINE_MMA = 0, 1, 2
-TUNE_MMA_TILE_N, TUNE_MMA_MIN_V, TUNE_MMA_PAIR, TUNE_DEFER_CAP = 1, 2, 3, 4
+TUNE_MMA_TILE_N, TUNE_MMA_MIN_V, TUNE_MMA_PAIR, TUNE_DEFER_CAP, TUNE_WINDOW_MQ = 1, 2, 3, 4, 5
 R2_MASK, R2_INT0, DP_SHIFT, DP_MASK, BELOW_THRES, DP_INT0 = 0x3FFF, 0x8000, 16, 0x3FFF0000, 0x40000000, 0x80000000
 
 HIT_DTYPE = np.dtype([("query", "<i4"), ("row", "<i4"), ("n11", "<i4"), ("packed", "<u4")])

@@ -171,6 +171,10 @@ extern "C" int32_t ldx_set_tuning(ldx_ctx *ctx, int32_t key, int32_t value) {
             LDX_REQUIRE(value >= 2, "minimum variant count must be >= 2");
             ctx->mma_min_v = value;
             return LDX_OK;
+        case LDX_TUNE_WINDOW_MQ:
+            LDX_REQUIRE(value == 0 || value == 1, "window multi-query mode must be 0 or 1");
+            ctx->window_mq = value;
+            return LDX_OK;
         case LDX_TUNE_DEFER_CAP:
             LDX_REQUIRE(value >= 0, "deferred-pair list capacity must be >= 0");
             ctx->defer_cap = value;
@@ -901,7 +905,7 @@ extern "C" int32_t ldx_window_dev(ldx_store *s, const int64_t *q_row, const int6
     std::vector<int32_t> order;
     std::vector<WindowMqBlock> blocks;
     int64_t n_items = 0;
-    const bool use_mq = !mq_off && nq >= 2 && window_mq_supported(s) && build_mq_blocks(lo, hi, nq, order, blocks, &n_items) &&
+    const bool use_mq = !mq_off && ctx->window_mq && nq >= 2 && window_mq_supported(s) && build_mq_blocks(lo, hi, nq, order, blocks, &n_items) &&
                         n_items < 0x7fffffffll && n_items * WINDOW_MQ < 3 * n_chunks;   // else: the windows barely overlap
     LDX_TRY(begin_dev_call(ctx));
     if (use_mq) {

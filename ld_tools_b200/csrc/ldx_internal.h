@@ -54,6 +54,7 @@ struct ldx_ctx {
     std::vector<int64_t> rows_cache;      // host copy of the variant list last staged on the device
     unsigned long long *d_trace = nullptr;   // diagnostics: globaltimer stamps written by the tcgen05 kernel
     void *h_stage = nullptr;              // pinned bounce buffer of the store files (allocated on first use)
+    int window_mq = 1;                    // LDX_TUNE_WINDOW_MQ: 0 = ld_area scans always use the one-query-per-pass kernel
     int defer_cap = 0;                    // LDX_TUNE_DEFER_CAP: capacity of the deferred-pair lists (0 = sized from the pair count)
     int mma_min_v = 256;                  // ENGINE_AUTO uses the tcgen05 engine from this many variants
     // dominant-kernel timing (ldx_kernel_timing): CUDA event pairs around the all-pairs / window kernel

@@ -345,6 +345,63 @@ def test_window_many_overlapping_queries_any_order(ctx, n_hap, thres):
     st.close()
 
 
+def test_window_full_size_properties(ctx):
+    """BASELINE configs[2] at full size: 1,000 queries, +/-500 kb, r2 >= 0.8, 503 of 2504 samples, 1.1 M variants x 5008
+    haplotypes (31 M candidate pairs; the store is generated on the GPU with neighbours in LD).  Properties that need no
+    CPU reference at this size: (1) the multi-query and the one-query kernels keep exactly the same pairs with the same
+    words; (2) a store of just the selected haplotype columns (ldx_store_subset) gives the same pairs, counts and words as
+    the mask over the full store; (3) a second run is identical; and a seeded sample of queries is checked against the
+    oracle's finalisation of numpy popcounts."""
+    import torch
+    from ld_tools_b200 import Store, shard
+    from ld_tools_b200._lib import TUNE_WINDOW_MQ
+    from ld_tools_b200.engine import threshold_e4
+    from ld_tools_b200.synth import fill_store_grouped
+    nv, n_hap, flank = 1_100_000, 5008, 500_000
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(2024)
+    st = Store(ctx, nv, n_hap)
+    fill_store_grouped(st, dev, 22, 0, nv)
+    pos0 = np.sort(rng.integers(16_050_000, 51_200_000, size=nv)).astype(np.int32)
+    st.set_annotations(pos0, pos0 + 1, np.arange(nv, dtype=np.int64), np.ones(nv, np.uint8))
+    samples = np.sort(rng.choice(n_hap // 2, 503, replace=False))
+    hap_idx = np.sort(np.concatenate([2 * samples, 2 * samples + 1]))
+    st.select_haplotypes(hap_idx)
+    q_row = np.sort(rng.choice(nv, 1000, replace=False)).astype(np.int64)
+    lo, hi, ws, we = shard.window_bounds(pos0, 1, pos0[q_row].astype(np.int64) + 1, flank)
+    t = threshold_e4(0.8)
+    hits_mq, scanned_mq = st.window(q_row, lo, hi, ws, we, "r_square", t)
+    again, _ = st.window(q_row, lo, hi, ws, we, "r_square", t)
+    ctx.set_tuning(TUNE_WINDOW_MQ, 0)
+    try:
+        hits_1q, scanned_1q = st.window(q_row, lo, hi, ws, we, "r_square", t)
+    finally:
+        ctx.set_tuning(TUNE_WINDOW_MQ, 1)
+    assert scanned_mq == scanned_1q == int((hi - lo).sum()) - 1000          # every candidate but the query itself
+    assert len(hits_mq) > 1000 and (hits_mq == hits_1q).all() and (hits_mq == again).all()
+    sub = st.subset(hap_idx)
+    hits_sub, scanned_sub = sub.window(q_row, lo, hi, ws, we, "r_square", t)
+    assert scanned_sub == scanned_mq and (hits_sub == hits_mq).all()
+    # a sample of queries against numpy popcounts + the oracle's finalisation
+    words = (n_hap + 63) // 64
+    bits = np.zeros(st.stride_words * 64, dtype=np.uint8)
+    bits[hap_idx] = 1
+    mask = np.packbits(bits, bitorder="little").view("<u8")[:words]
+    for k in rng.choice(1000, 4, replace=False):
+        a, b, q = int(lo[k]), int(hi[k]), int(q_row[k])
+        win = st.download(a, b - a)[:, :words] & mask
+        qrow = st.download(q, 1)[0, :words] & mask
+        n1 = np.bitwise_count(win).sum(axis=1).astype(np.int32)
+        n11 = np.bitwise_count(win & qrow[None, :]).sum(axis=1).astype(np.int32)
+        want = ld_oracle.packed_words(1006, n11, np.full(b - a, int(np.bitwise_count(qrow).sum()), np.int32), n1)
+        keep = ((want & 0x3FFF) >= t) & (np.arange(a, b) != q)
+        got = hits_mq[hits_mq["query"] == k]
+        assert got["row"].tolist() == (np.flatnonzero(keep) + a).tolist()
+        assert (got["n11"] == n11[keep]).all() and (got["packed"] == want[keep]).all()
+    sub.close()
+    st.close()
+
+
 def test_window_edge_cases(ctx):
     from ld_tools_b200.engine import threshold_e4
     st, planes, mask, pos0, end0, idnum, elig = annotated_store(ctx, 600, 198, seed=44)

@@ -97,7 +97,8 @@ int32_t ldx_synchronize(ldx_ctx *ctx);
 /* Tuning knobs (benchmarks/tests; defaults are chosen per call):
  *   LDX_TUNE_MMA_TILE_N  column width of the tcgen05 all-pairs tile: 0 = heuristic, 64 or 128
  *   LDX_TUNE_MMA_MIN_V   LDX_ENGINE_AUTO uses the tcgen05 engine from this many variants (256)
- *   LDX_TUNE_MMA_PAIR    1 = 256 x 128 tiles on CTA pairs (tcgen05.mma.cta_group::2), 0 = one CTA per 128 x 128 tile
+ *   LDX_TUNE_MMA_PAIR    1 = 256 x 128 tiles on CTA pairs (tcgen05.mma.cta_group::2), 0 = one CTA per 128 x 128 tile,
+ *                        -1 (default) = pairs for calls of more than one wave of tiles
  *   LDX_TUNE_DEFER_CAP   capacity of the tcgen05 engine's deferred-pair lists (0 = sized from the pair count); a
  *                        small value forces the overflow paths (pairs settled in place) -- for tests
  *   LDX_TUNE_WINDOW_MQ   1 (default) = window scans of several queries with monotone candidate ranges use the multi-query

@@ -118,7 +118,7 @@ extern "C" int32_t ldx_init(int32_t device, ldx_ctx **ctx_out) {
     if (e == cudaSuccess) { for (int i = 0; i < 4; ++i) ctx->h_mailbox[i] = 0; e = cudaHostGetDevicePointer((void **)&ctx->d_mailbox, (void *)ctx->h_mailbox, 0); }
     if (e != cudaSuccess) { ldx_destroy(ctx); return cuda_fail(e, "ldx_init"); }
     ctx->stream = ctx->own_stream;
-    if (const char *e = getenv("LDX_MMA_PAIR")) ctx->mma_pair = atoi(e) != 0;    // default of LDX_TUNE_MMA_PAIR
+    if (const char *e = getenv("LDX_MMA_PAIR")) ctx->mma_pair = atoi(e) < 0 ? -1 : atoi(e) != 0;    // default of LDX_TUNE_MMA_PAIR
     *ctx_out = ctx;
     return LDX_OK;
 }
@@ -164,7 +164,7 @@ extern "C" int32_t ldx_set_tuning(ldx_ctx *ctx, int32_t key, int32_t value) {
             ctx->mma_tile_n = value;
             return LDX_OK;
         case LDX_TUNE_MMA_PAIR:
-            LDX_REQUIRE(value == 0 || value == 1, "pair mode must be 0 or 1");
+            LDX_REQUIRE(value >= -1 && value <= 1, "pair mode must be -1 (auto), 0 or 1");
             ctx->mma_pair = value;
             return LDX_OK;
         case LDX_TUNE_MMA_MIN_V:

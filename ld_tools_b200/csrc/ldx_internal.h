@@ -43,7 +43,7 @@ struct ldx_ctx {
     int mma_tiles_n = 0;
     int64_t mma_tiles_begin = 0;
     bool mma_tiles_pair = false;
-    int mma_pair = 0;                     // LDX_TUNE_MMA_PAIR: 256 x 128 tiles on CTA pairs (tcgen05 cta_group::2)
+    int mma_pair = -1;                    // LDX_TUNE_MMA_PAIR: 256 x 128 tiles on CTA pairs (tcgen05 cta_group::2): 0 off, 1 on, -1 auto
     const void *mma_tiles_ptr = nullptr;  // where in d_mma_ops that list lives (depends on the haplotype count too)
     // completion mailbox: pinned, device-mapped {seq, near-tie count, error flag}; a 1-thread kernel
     // publishes it after each *_dev call so that ldx_resolve() can poll host memory instead of

@@ -136,8 +136,15 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// Arrive on a barrier of the pair's other CTA.  What the arrive announces -- operand bytes in THIS CTA's shared and tensor
+// memory -- has been completed by the caller's tcgen05.wait::st / fence.proxy.async / __syncwarp before this point, and it is
+// consumed in place (the pair's MMA reads each CTA's operands from that CTA's own memories).  A cluster-scope RELEASE here
+// made the arriving thread wait ~0.6 us for a fence it does not need, once per stage and warp, on every team's critical
+// path: the pair kernel ran slower than the single-CTA one (2.39 vs 2.10 ms at 32,768 variants).  A CTA-scope fence plus a
+// relaxed cluster-scope arrive: 1.89 ms.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void umma_i8_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -1073,7 +1080,15 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t 
     int n_tile = ctx->mma_tile_n;
     if (n_tile == 0) n_tile = v <= 1024 ? 64 : 128;
     // CTA pairs (256 x 128 tiles, cta_group::2): a quarter less widening work per result
-    const bool pair = ctx->mma_pair && n_tile == 128 && row_begin % (2 * MMA_M) == 0 && ctx->sm_count % 2 == 0;
+    // mma_pair: 0 off, 1 on, -1 (default) on for multi-wave calls -- a one-wave call has nothing to overlap the pair's longer
+    // prologue and signalling with
+    bool pair = ctx->mma_pair != 0 && n_tile == 128 && row_begin % (2 * MMA_M) == 0 && ctx->sm_count % 2 == 0;
+    if (pair && ctx->mma_pair < 0) {
+        size_t single_cta_tiles = 0;
+        for (int64_t bi = row_begin / MMA_M; bi < (v + MMA_M - 1) / MMA_M; ++bi)
+            single_cta_tiles += (size_t)((std::min<int64_t>(bi * MMA_M + MMA_M - 1, v - 1) + n_tile - 1) / n_tile);
+        pair = single_cta_tiles > (size_t)ctx->sm_count;
+    }
     const int64_t ph = pair ? 2 * MMA_M : MMA_M;             // tile height
     // ---- tile list (cached): every 128 x N tile holding at least one pair with row > col, row-panel major
     const size_t bits_bytes = (size_t)panels * kc_count * 128 * sizeof(uint4);

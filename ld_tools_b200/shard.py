@@ -20,7 +20,7 @@ import numpy as np
 
 from ._lib import HIT_DTYPE
 
-TRI_ALIGN = 128          # row ranges start on tcgen05 row-panel boundaries (include/ldx.h: ldx_triangle_rows)
+TRI_ALIGN = 256          # row ranges start on the CTA-pair kernel's 256-row panels (ldx_triangle_rows itself needs 128)
 
 
 def tri(r):
@@ -33,12 +33,16 @@ def triangle_row_ranges(v, world, align=TRI_ALIGN, tile=128):
     """[(begin, end)] * world covering rows 0..v, begin % align == 0, balanced by tile count.
 
     Cost model: the all-pairs kernel works in 128 x 128 tiles and a tile costs the same K loop
-    whether it is full or cut by the diagonal, so row panel b (rows 128b..128b+127) costs b + 1
-    tiles.  Boundaries are the panel indices where the cumulative cost crosses k / world."""
+    whether it is full or cut by the diagonal, so the 128-row panel s costs s + 1 tiles.  Boundaries
+    are the `align`-row panel indices where the cumulative cost crosses k / world."""
     v, world = int(v), int(world)
-    assert world >= 1 and align % tile == 0 or tile % align == 0
-    n_panels = (v + tile - 1) // tile
-    cost = np.arange(1, n_panels + 1, dtype=np.float64)                 # tiles of each row panel
+    assert world >= 1 and align % tile == 0
+    sub = align // tile                                                  # 128-row panels per boundary unit
+    n_sub = (v + tile - 1) // tile
+    n_panels = (n_sub + sub - 1) // sub
+    sub_cost = np.arange(1, n_panels * sub + 1, dtype=np.float64)
+    sub_cost[n_sub:] = 0.0                                               # panels beyond the matrix
+    cost = sub_cost.reshape(n_panels, sub).sum(axis=1) if n_panels else np.zeros(0)
     cum = np.concatenate([[0.0], np.cumsum(cost)])
     bounds = [0]
     for k in range(1, world):
@@ -50,9 +54,8 @@ def triangle_row_ranges(v, world, align=TRI_ALIGN, tile=128):
         b = min(max(b, bounds[-1]), n_panels)
         bounds.append(b)
     bounds.append(n_panels)
-    rows = [min(b * tile, v) for b in bounds]
+    rows = [min(b * align, v - v % align) for b in bounds]               # interior boundaries stay aligned even past the end
     rows[-1] = v
-    rows = [r - r % align if i not in (0, world) else r for i, r in enumerate(rows)]
     return [(rows[k], rows[k + 1]) for k in range(world)]
 
 

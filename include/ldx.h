@@ -279,6 +279,27 @@ int32_t ldx_window_dev(ldx_store *store, const int64_t *q_row, const int64_t *lo
                        int64_t *dev_n_hits);
 int32_t ldx_resolve(ldx_ctx *ctx, int64_t *n_fixed_out);
 
+/* ---------------------------------------------------------------- matrix text
+ * Replaces the table writer's body loop, ld_triangle.py:356-360: `'\t'.join(map(str, ld_two_dim[row]))` for
+ * matrix rows row_begin .. row_end-1 of a v x v matrix, formatted on the GPU from the packed words.
+ * `packed` is what ldx_triangle_rows[_dev] produced for the same row range (entry 0 = pair (row_begin, 0));
+ * it is a device pointer with LDX_TEXT_PACKED_ON_DEVICE in flags, else a host array.  Line r is
+ *     prefixes[prefix_off[r] .. prefix_off[r+1])  +  cells 0..v-1 joined by '\t'  +  '\n'
+ * (prefix_off has v+1 entries, indexed by absolute matrix row; the reference's prefix is rsID '\t' position '\t').
+ * Cell (r, c): c >= r -> "0" (the matrix starts as int zeros, :114; only row > col is filled, :150); LDX_BELOW_THRES or the measure's INT0 flag
+ * -> "0" (:223-225, calc_ld.py:68-90); otherwise str(k / 10000.0) exactly as Python prints it ("0.0", "0.5",
+ * "0.8125", "1.0").  text[cap] (device memory with LDX_TEXT_OUT_ON_DEVICE) receives *n_bytes bytes; when
+ * cap is too small the call returns LDX_ERR_CAPACITY with *n_bytes = the size needed (cap = 0 is a size query;
+ * 7 * v * (row_end - row_begin) + the prefix bytes always suffices).  Pending *_dev calls are resolved first.
+ * With ldx_kernel_timing enabled the text kernel's launches are counted like the all-pairs kernels'. */
+enum { LDX_TEXT_PACKED_ON_DEVICE = 1, LDX_TEXT_OUT_ON_DEVICE = 2 };
+int32_t ldx_triangle_text(ldx_ctx *ctx, const uint32_t *packed, int64_t v, int64_t row_begin, int64_t row_end,
+                          int32_t measure, const char *prefixes, const int64_t *prefix_off, int32_t flags,
+                          char *text, int64_t cap, int64_t *n_bytes);
+/* Host helper (no device needed): str(value_e4 / 10000.0) for 0 <= value_e4 < 20000 as the kernels print it,
+ * NUL-padded to 8 bytes -- the same digit arithmetic, exposed so that it can be checked against Python's str(). */
+int32_t ldx_format_e4(int32_t value_e4, char *out8);
+
 #ifdef __cplusplus
 }
 #endif

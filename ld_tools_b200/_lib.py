@@ -13,6 +13,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_EMPTY, ERR_CAPACITY, ERR_STATE, ERR_DATA =
 MEASURE_R2, MEASURE_DPRIME = 0, 1
 ENGINE_AUTO, ENGINE_POPC, ENGINE_MMA = 0, 1, 2
 TUNE_MMA_TILE_N, TUNE_MMA_MIN_V, TUNE_MMA_PAIR, TUNE_DEFER_CAP, TUNE_WINDOW_MQ = 1, 2, 3, 4, 5
+TEXT_PACKED_ON_DEVICE, TEXT_OUT_ON_DEVICE = 1, 2
 R2_MASK, R2_INT0, DP_SHIFT, DP_MASK, BELOW_THRES, DP_INT0 = 0x3FFF, 0x8000, 16, 0x3FFF0000, 0x40000000, 0x80000000
 
 HIT_DTYPE = np.dtype([("query", "<i4"), ("row", "<i4"), ("n11", "<i4"), ("packed", "<u4")])
@@ -77,6 +78,8 @@ SIGNATURES = {
     "ldx_triangle_rows_dev": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp],
     "ldx_window_dev": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp],
     "ldx_resolve": [_vp, _P(_i64)],
+    "ldx_triangle_text": [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _i32, _vp, _i64, _P(_i64)],
+    "ldx_format_e4": [_i32, _vp],
 }
 
 _lib = None

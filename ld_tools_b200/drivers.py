@@ -19,10 +19,11 @@ import sqlite3
 
 import numpy as np
 
-from .engine import Context, HostText, Store, dprime_value, measure_value, r2_value, threshold_e4
-from ._lib import BELOW_THRES, VCF_ROW_DTYPE, LdxError
+from .engine import Context, HostText, Store, dprime_value, r2_value, threshold_e4, tri_index
+from ._lib import VCF_ROW_DTYPE, LdxError
 
 RS_RE = re.compile(r"rs\d+$")
+TEXT_SLAB_BYTES = 256 << 20          # matrix text is formatted and written in slabs of at most this many bytes
 
 
 # --------------------------------------------------------------------------- conversion.db helpers
@@ -323,16 +324,15 @@ def ld_triangle(src_dir_path, intgen_dir_path, trg_top_dir_path=None, meta_lines
                 rows = np.array([cd.row_of(p, i) for p, i in var_rows], dtype=np.int64)
                 packed, _ = cd.store.triangle(rows, measure=ld_measure, thres_e4_=t_e4)      # :133-230 in one call
                 tab = "\t"
-                with open(os.path.join(trg_dir, f"{base}_chr{chrom}_{ld_measure[0]}.tsv"), "w") as fh:   # :351-360
-                    fh.write(f"##General\tinfo:\t{ld_measure}\tchr{chrom}\t{tab.join(pops)}\t{tab.join(gends)}\n\n")
-                    fh.write("rsIDs\t\t" + "\t".join(ids) + "\n")
-                    fh.write("\tPositions\t" + "\t".join(poss) + "\n")
-                    for r in range(v):
-                        cells = []
-                        for c in range(v):
-                            w = packed[r * (r - 1) // 2 + c] if c < r else None
-                            cells.append("0" if w is None or (w & BELOW_THRES) else str(measure_value(w, ld_measure)))
-                        fh.write(ids[r] + "\t" + poss[r] + "\t" + "\t".join(cells) + "\n")
+                with open(os.path.join(trg_dir, f"{base}_chr{chrom}_{ld_measure[0]}.tsv"), "wb") as fh:  # :351-360
+                    fh.write((f"##General\tinfo:\t{ld_measure}\tchr{chrom}\t{tab.join(pops)}\t{tab.join(gends)}\n\n"
+                              + "rsIDs\t\t" + "\t".join(ids) + "\n" + "\tPositions\t" + "\t".join(poss) + "\n").encode())
+                    # the V lines of V cells (:356-360) are formatted on the GPU, a slab of rows at a time
+                    prefixes = [(i + "\t" + p + "\t").encode() for i, p in zip(ids, poss)]
+                    slab = max(1, TEXT_SLAB_BYTES // (7 * v))
+                    for r0 in range(0, v, slab):
+                        r1 = min(v, r0 + slab)
+                        fh.write(ctx.triangle_text(packed[tri_index(r0, 0):tri_index(r1, 0)], v, ld_measure, prefixes, r0, r1).data)
     finally:
         for cd in chrom_cache.values():
             cd.close()

@@ -56,6 +56,16 @@ def measure_value(word, measure):
     return r2_value(word) if measure in ("r_square", MEASURE_R2) else dprime_value(word)
 
 
+FORMAT_CELL_MAX = 7       # bytes of the longest matrix cell with its separator ("1.6383" + tab)
+
+
+def format_e4(value_e4):
+    """str(value_e4 / 10000.0) as libldx prints it (ldx_format_e4: host code, no device needed)."""
+    buf = C.create_string_buffer(8)
+    check(_lib.load().ldx_format_e4(int(value_e4), buf))
+    return buf.value.decode("ascii")
+
+
 def _measure_code(measure):
     return MEASURES[measure] if isinstance(measure, str) else int(measure)
 
@@ -136,6 +146,35 @@ class Context:
         n = C.c_int64()
         check(self._lib.ldx_resolve(self._h, C.byref(n)))
         return n.value
+
+    def triangle_text(self, packed, v, measure, prefixes, row_begin=0, row_end=None, out=None, dev_text=0):
+        """The body lines of ld_triangle's table (ld_triangle.py:356-360), formatted on the GPU.
+        `packed`: the words of matrix rows row_begin..row_end-1 -- a uint32 numpy array or a raw device address
+        (int).  `prefixes`: one bytes object per matrix row (all v of them; the reference's is rsID + tab +
+        position + tab).  -> uint8 array of the text (a view of `out` when given); with `dev_text` = (device
+        address, capacity) the text stays in HBM and the byte count is returned."""
+        row_end = v if row_end is None else row_end
+        assert len(prefixes) == v
+        blob = np.frombuffer(b"".join(prefixes) + b"\0", dtype=np.uint8)
+        off = np.zeros(v + 1, dtype=np.int64)
+        np.cumsum([len(p) for p in prefixes], out=off[1:])
+        flags, pk = 0, None
+        if isinstance(packed, (int, np.integer)):
+            flags, p_packed = _lib.TEXT_PACKED_ON_DEVICE, C.c_void_p(int(packed))
+        else:
+            pk = np.ascontiguousarray(packed, dtype=np.uint32)
+            assert pk.shape[0] == tri_index(row_end, 0) - tri_index(row_begin, 0)
+            p_packed = ptr(pk)
+        n = C.c_int64()
+        args = (self._h, p_packed, int(v), int(row_begin), int(row_end), _measure_code(measure), ptr(blob), ptr(off))
+        if dev_text:
+            check(self._lib.ldx_triangle_text(*args, flags | _lib.TEXT_OUT_ON_DEVICE, C.c_void_p(dev_text[0]),
+                                              int(dev_text[1]), C.byref(n)))
+            return n.value
+        if out is None:
+            out = np.empty(FORMAT_CELL_MAX * v * (row_end - row_begin) + int(off[row_end] - off[row_begin]), dtype=np.uint8)
+        check(self._lib.ldx_triangle_text(*args, flags, ptr(out), out.shape[0], C.byref(n)))
+        return out[:n.value]
 
     def finalise_counts(self, n_hap, n11, n1a, n1b):
         """calc_ld.py:33-97 for arrays of counts.  -> dict(d, dprime, r2, packed)."""

@@ -80,3 +80,12 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(text), f"{os.path.join(dirpath, f)} references the oracle"
+
+
+def test_format_e4_is_python_str(lib_path):
+    """ldx_format_e4 (host code; the digit arithmetic the matrix text kernel uses for a cell) against Python's
+    str() of the value the result word stands for, for every representable k = round(x, 4) * 10^4."""
+    from ld_tools_b200.engine import format_e4
+    for k in range(20000):
+        assert format_e4(k) == str(k / 10000.0), k
+        assert k / 10000.0 == round(k / 10000.0, 4)

@@ -5,10 +5,12 @@ tests/golden/calc_ld_golden.json holds outputs of the unmodified reference calc_
 is replayed through (1) the pure-Python port and (2) the C restatement.  Bit-exact, no
 tolerance: both run the same IEEE operations and the same libm pow as the reference.
 """
+import os
+
 import numpy as np
 import pytest
 
-from conftest import decode_genotypes, decode_raw
+from conftest import ROOT, decode_genotypes, decode_raw
 from oracle import calc_ld_port, ld_oracle
 
 KEYS = ("r_square", "d_prime", "var_1_alt_freq", "var_2_alt_freq")
@@ -149,3 +151,31 @@ def test_pack_gt_text():
     buf[offs[4] + 4 * 5 + 1] = ord("/")      # unphased
     _, status = ld_oracle.pack_gt(buf, np.array(offs), n_samples)
     assert status.tolist() == [0, 0, 1, 0, 1, 0]
+
+
+def test_table_port_reproduces_reference_tables():
+    """The table writer port (oracle/table_port.py, ld_triangle.py:114,:150,:223-230,:356-360) against the .tsv
+    files the unmodified reference driver wrote: cells parsed back to the objects they print, lines re-created."""
+    import glob
+    from oracle import table_port
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "drivers", "triangle_*", "*", "*.tsv")))
+    assert len(files) >= 2
+    for path in files:
+        with open(path) as fh:
+            lines = fh.read().split("\n")
+        assert lines[0].startswith("##General\tinfo:") and lines[1] == "" and lines[-1] == ""
+        ids, poss = lines[2].split("\t")[2:], lines[3].split("\t")[2:]
+        body = lines[4:-1]
+        v = len(ids)
+        assert len(body) == v and len(poss) == v
+        cells = [ln.split("\t")[2:] for ln in body]
+        assert all(len(row) == v for row in cells)
+        assert all(cells[r][c] == "0" for r in range(v) for c in range(r, v))       # :150: only row > col is filled
+        objs = [[0 if t == "0" else float(t) for t in row] for row in cells]
+        assert any(isinstance(x, float) for row in objs for x in row)
+        text = table_port.matrix_body(lambda r, c: objs[r][c], v, ids, poss)
+        assert text == "\n".join(body) + "\n"
+        # every float cell is a round(x, 4) value printed by str(): at most four decimals, no exponent
+        for row in cells:
+            for t in row:
+                assert t == "0" or (t == str(round(float(t), 4)) and "e" not in t)

@@ -647,3 +647,86 @@ def test_several_device_resident_calls_one_resolve(ctx):
     packed, _ = st.triangle(np.arange(200))
     assert (packed == ld_oracle.packed_of(ld_oracle.triangle(planes, mask, n_hap, np.arange(200)))).all()
     st.close()
+
+
+# ------------------------------------------------------------------ matrix text (ld_triangle.py:351-360 on the GPU)
+def _python_body(packed, v, measure, prefixes, row_begin=0, row_end=None):
+    """The same lines from the decoded words, with Python's own str() per cell."""
+    from ld_tools_b200.engine import BELOW_THRES, measure_value, tri_index
+    row_end = v if row_end is None else row_end
+    out = []
+    for r in range(row_begin, row_end):
+        base = tri_index(r, 0) - tri_index(row_begin, 0)
+        cells = ["0" if (c >= r or packed[base + c] & BELOW_THRES) else str(measure_value(packed[base + c], measure))
+                 for c in range(v)]
+        out.append(prefixes[r] + "\t".join(cells).encode() + b"\n")
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("n_hap,measure,thres", [(198, "r_square", None), (198, "d_prime", 0.3), (1006, "r_square", 0.05),
+                                                 (14, "d_prime", None)])
+def test_triangle_text_matches_reference_writer(ctx, n_hap, measure, thres):
+    """ldx_triangle_text against the reference's writer restated (oracle/table_port.py), fed with the dicts the
+    oracle's calc_ld returns for every pair: int 0 vs 0.0, the rounded threshold, row > col only, str() per cell."""
+    from oracle import table_port
+    from ld_tools_b200.engine import ENGINE_POPC, threshold_e4
+    n_var = 75
+    st, planes, mask = make_store(ctx, n_var, n_hap, seed=300 + n_hap)
+    rows = np.random.default_rng(n_hap).permutation(n_var)
+    res = ld_oracle.triangle(planes, mask, n_hap, rows)
+    vals = [ld_oracle.as_reference_dict(x)[measure] for x in res]
+    ids = [f"rs{1000 + 7 * k}" for k in range(n_var)]
+    poss = [str(16050000 + 913 * k) for k in range(n_var)]
+    want = table_port.matrix_body(lambda r, c: vals[r * (r - 1) // 2 + c], n_var, ids, poss, thres).encode()
+    packed, _ = st.triangle(rows, measure=measure, thres_e4_=None if thres is None else threshold_e4(thres), engine=ENGINE_POPC)
+    prefixes = [(i + "\t" + p + "\t").encode() for i, p in zip(ids, poss)]
+    got = ctx.triangle_text(packed, n_var, measure, prefixes)
+    assert got.tobytes() == want
+    st.close()
+
+
+def test_triangle_text_full_size_slabs_and_device_words(ctx):
+    """configs[1] shape (2,000 x 2,000 cells): host words = device words = slabs concatenated = Python's str() per cell;
+    exact size query; empty prefixes; a matrix wider than one 2,048-cell chunk."""
+    import torch
+    from ld_tools_b200 import _lib
+    from ld_tools_b200.engine import threshold_e4, tri_index
+    v = 2500
+    st, planes, mask = make_store(ctx, v, 1006, seed=77)
+    rows = np.arange(v)
+    prefixes = [b"rs%d\t%d\t" % (3 * k + 1, 17000000 + 41 * k) if k % 97 else b"" for k in range(v)]
+    for measure, thres in (("r_square", None), ("d_prime", 0.9)):
+        packed, _ = st.triangle(rows, measure=measure, thres_e4_=None if thres is None else threshold_e4(thres))
+        want = _python_body(packed, v, measure, prefixes)
+        whole = ctx.triangle_text(packed, v, measure, prefixes)
+        assert whole.tobytes() == want
+        # the same words left in HBM by the device-resident call, text kept in HBM too
+        dev = torch.zeros(packed.shape[0], dtype=torch.int32, device="cuda:0")
+        torch.cuda.synchronize()
+        st.triangle_dev(rows, dev.data_ptr(), measure=measure, thres_e4_=None if thres is None else threshold_e4(thres))
+        text_dev = torch.zeros(len(want) + 5, dtype=torch.uint8, device="cuda:0")
+        torch.cuda.synchronize()
+        n = ctx.triangle_text(dev.data_ptr(), v, measure, prefixes, dev_text=(text_dev.data_ptr(), text_dev.numel()))
+        assert n == len(want) and text_dev[:n].cpu().numpy().tobytes() == want and int(text_dev[n:].sum()) == 0
+        # slabs of rows (unaligned boundaries) concatenate to the whole text
+        parts = []
+        for r0, r1 in ((0, 1), (1, 2), (2, 701), (701, 2499), (2499, 2500)):
+            parts.append(ctx.triangle_text(packed[tri_index(r0, 0):tri_index(r1, 0)], v, measure, prefixes, r0, r1).tobytes())
+        assert b"".join(parts) == want
+        # size query / too-small buffer
+        with pytest.raises(_lib.LdxError) as e:
+            ctx.triangle_text(packed, v, measure, prefixes, out=np.zeros(len(want) - 1, dtype=np.uint8))
+        assert e.value.code == _lib.ERR_CAPACITY
+        exact = np.zeros(len(want), dtype=np.uint8)
+        assert ctx.triangle_text(packed, v, measure, prefixes, out=exact).tobytes() == want
+    st.close()
+
+
+def test_triangle_text_tiny_matrices(ctx):
+    for v in (1, 2, 3):
+        st, planes, mask = make_store(ctx, 8, 198, seed=v)
+        packed, _ = st.triangle(np.arange(v))
+        prefixes = [b"a\t1\t"] * v
+        assert ctx.triangle_text(packed, v, "r_square", prefixes).tobytes() == _python_body(packed, v, "r_square", prefixes)
+        st.close()
+    assert ctx.triangle_text(np.zeros(0, np.uint32), 5, "r_square", [b""] * 5, 2, 2).shape[0] == 0

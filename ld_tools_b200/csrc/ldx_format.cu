@@ -70,9 +70,29 @@ matrix_line_bytes_kernel(const uint32_t *__restrict__ packed, int64_t v, int64_t
     }
 }
 
-// Pass 2: the text.  A CTA formats one line in chunks of 2,048 cells: every thread builds its eight cells in registers,
-// a block scan places them, the chunk is assembled in shared memory at the alignment it will have in global memory and
-// copied out with 16-byte stores.
+// One cell into the chunk buffer: up to six text bytes, then the tab at dst[n].  With `exact` false the six byte stores are
+// unconditional -- what they write beyond the cell's length lands in LATER cells of the same thread (the caller checks
+// that dst + 6 stays inside the thread's own bytes) and is overwritten by them in program order; cells at the end of a
+// thread's run must not touch the neighbour's bytes and take the predicated form.
+__device__ __forceinline__ unsigned char *put_cell(unsigned char *dst, uint32_t lo, uint32_t hi, int n, bool exact) {
+    if (!exact) {
+        dst[0] = (unsigned char)lo; dst[1] = (unsigned char)(lo >> 8); dst[2] = (unsigned char)(lo >> 16);
+        dst[3] = (unsigned char)(lo >> 24); dst[4] = (unsigned char)hi; dst[5] = (unsigned char)(hi >> 8);
+    } else {
+        dst[0] = (unsigned char)lo;
+        if (n > 1) { dst[1] = (unsigned char)(lo >> 8); dst[2] = (unsigned char)(lo >> 16); }       // a float has at least "0.0"
+        if (n > 3) dst[3] = (unsigned char)(lo >> 24);
+        if (n > 4) dst[4] = (unsigned char)hi;
+        if (n > 5) dst[5] = (unsigned char)(hi >> 8);
+    }
+    dst[n] = '\t';
+    return dst + n + 1;
+}
+
+// Pass 2: the text.  A CTA formats one line.  Cells left of the diagonal, in chunks of 2,048: every thread builds its
+// eight cells in registers, a block scan places them, the chunk is assembled in shared memory at the alignment it will
+// have in global memory and copied out with 16-byte stores.  The diagonal and everything right of it is the constant
+// pattern "0\t0\t...0\n", stored directly.
 __global__ void __launch_bounds__(FMT_THREADS)
 matrix_text_kernel(const uint32_t *__restrict__ packed, int64_t v, int64_t row_begin, int64_t n_lines, int measure,
                    const char *__restrict__ prefixes, const int64_t *__restrict__ prefix_off,
@@ -88,31 +108,29 @@ matrix_text_kernel(const uint32_t *__restrict__ packed, int64_t v, int64_t row_b
         for (int64_t i = tid; i < plen; i += FMT_THREADS) out[i] = prefixes[p0 + i];
         int64_t pos = plen;
         const uint32_t *__restrict__ words = packed + (tri64(r) - tri64(row_begin));
-        for (int64_t cb = 0; cb < v; cb += FMT_CHUNK) {
-            uint64_t s[FMT_CELLS_PER_THREAD];
+        for (int64_t cb = 0; cb < r; cb += FMT_CHUNK) {
+            uint32_t lo[FMT_CELLS_PER_THREAD], hi[FMT_CELLS_PER_THREAD];
             int len[FMT_CELLS_PER_THREAD], mine = 0;
             const int64_t c0 = cb + (int64_t)tid * FMT_CELLS_PER_THREAD;
 #pragma unroll
             for (int k = 0; k < FMT_CELLS_PER_THREAD; ++k) {
-                const int64_t c = c0 + k;
-                if (c >= v) { len[k] = 0; s[k] = 0; continue; }
-                int n = 1;
-                uint64_t t = '0';
-                if (c < r) t = text_of_word(__ldg(words + c), measure, &n);
-                const uint64_t sep = c + 1 == v ? '\n' : '\t';
-                s[k] = (t & ((1ull << (8 * n)) - 1)) | (sep << (8 * n));
-                len[k] = n + 1;
-                mine += n + 1;
+                len[k] = 0; lo[k] = 0; hi[k] = 0;
+                if (c0 + k < r) {
+                    int n;
+                    const uint64_t t = text_of_word(__ldg(words + c0 + k), measure, &n);
+                    lo[k] = (uint32_t)t; hi[k] = (uint32_t)(t >> 32);
+                    len[k] = n;
+                    mine += n + 1;
+                }
             }
             int off, total;
             Scan(tmp).ExclusiveSum(mine, off, total);
             const int shift = (int)(reinterpret_cast<uintptr_t>(out + pos) & 15);
             unsigned char *dst = buf + shift + off;
+            const unsigned char *const end = dst + mine;             // where this thread's bytes stop and its neighbour's start
 #pragma unroll
-            for (int k = 0; k < FMT_CELLS_PER_THREAD; ++k) {
-                uint64_t t = s[k];
-                for (int b = 0; b < len[k]; ++b) { *dst++ = (unsigned char)t; t >>= 8; }
-            }
+            for (int k = 0; k < FMT_CELLS_PER_THREAD; ++k)
+                if (len[k]) dst = put_cell(dst, lo[k], hi[k], len[k], k + 1 == FMT_CELLS_PER_THREAD || dst + 6 > end);
             __syncthreads();
             char *g = out + pos;
             const int head = shift ? min(16 - shift, total) : 0;
@@ -125,6 +143,20 @@ matrix_text_kernel(const uint32_t *__restrict__ packed, int64_t v, int64_t row_b
             if (tid < total - done) g[done + tid] = (char)buf[shift + done + tid];
             pos += total;
             __syncthreads();
+        }
+        // cells r .. v-1: "0\t" each, the last one "0\n"
+        {
+            char *g = out + pos;
+            const int64_t total = 2 * (v - r);
+            const int shift = (int)(reinterpret_cast<uintptr_t>(g) & 15);
+            const int64_t head = shift ? min((int64_t)(16 - shift), total - 1) : 0;
+            if (tid < head) g[tid] = (tid & 1) ? '\t' : '0';
+            const int64_t nvec = (total - 1 - head) >> 4;                                // the final byte is never part of a vector
+            const uint32_t w = (head & 1) ? 0x30093009u : 0x09300930u;
+            uint4 *gv = reinterpret_cast<uint4 *>(g + head);
+            for (int64_t i = tid; i < nvec; i += FMT_THREADS) gv[i] = make_uint4(w, w, w, w);
+            const int64_t done = head + (nvec << 4);
+            if (tid < total - done) g[done + tid] = done + tid == total - 1 ? '\n' : (((done + tid) & 1) ? '\t' : '0');
         }
     }
 }

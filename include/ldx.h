@@ -296,6 +296,13 @@ enum { LDX_TEXT_PACKED_ON_DEVICE = 1, LDX_TEXT_OUT_ON_DEVICE = 2 };
 int32_t ldx_triangle_text(ldx_ctx *ctx, const uint32_t *packed, int64_t v, int64_t row_begin, int64_t row_end,
                           int32_t measure, const char *prefixes, const int64_t *prefix_off, int32_t flags,
                           char *text, int64_t cap, int64_t *n_bytes);
+/* ldx_triangle_rows_dev + ldx_resolve + ldx_triangle_text in one call: the pairs of matrix rows row_begin..row_end-1
+ * (row_begin a multiple of 128) are computed into the ctx's scratch and only their text leaves the GPU -- what
+ * `ld_triangle -o table` needs (ld_triangle.py:133-230 and :356-360 together).  flags: 0 or LDX_TEXT_OUT_ON_DEVICE. */
+int32_t ldx_triangle_table(ldx_store *store, const int64_t *rows, int64_t v, int64_t row_begin, int64_t row_end,
+                           int32_t measure, int32_t has_thres, int32_t thres_e4, int32_t engine,
+                           const char *prefixes, const int64_t *prefix_off, int32_t flags,
+                           char *text, int64_t cap, int64_t *n_bytes);
 /* Host helper (no device needed): str(value_e4 / 10000.0) for 0 <= value_e4 < 20000 as the kernels print it,
  * NUL-padded to 8 bytes -- the same digit arithmetic, exposed so that it can be checked against Python's str(). */
 int32_t ldx_format_e4(int32_t value_e4, char *out8);

@@ -79,6 +79,7 @@ SIGNATURES = {
     "ldx_window_dev": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp],
     "ldx_resolve": [_vp, _P(_i64)],
     "ldx_triangle_text": [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _i32, _vp, _i64, _P(_i64)],
+    "ldx_triangle_table": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _P(_i64)],
     "ldx_format_e4": [_i32, _vp],
 }
 

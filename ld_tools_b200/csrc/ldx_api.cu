@@ -1059,6 +1059,27 @@ extern "C" int32_t ldx_triangle(ldx_store *s, const int64_t *rows, int64_t v, in
     return ldx_triangle_rows(s, rows, v, 0, v, measure, has_thres, thres_e4, engine, packed, n11);
 }
 
+// The all-pairs call and the table writer in one: the words of matrix rows row_begin..row_end-1 go to the ctx's scratch,
+// are settled there, and only their text crosses PCIe.
+extern "C" int32_t ldx_triangle_table(ldx_store *s, const int64_t *rows, int64_t v, int64_t row_begin, int64_t row_end,
+                                      int32_t measure, int32_t has_thres, int32_t thres_e4, int32_t engine,
+                                      const char *prefixes, const int64_t *prefix_off, int32_t flags,
+                                      char *text, int64_t cap, int64_t *n_bytes) {
+    LDX_REQUIRE(s && n_bytes, "NULL argument");
+    *n_bytes = 0;
+    LDX_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= v, "bad row range");
+    LDX_REQUIRE((flags & ~LDX_TEXT_OUT_ON_DEVICE) == 0, "bad flags");
+    ldx_ctx *ctx = s->ctx;
+    const int64_t n_pairs = (row_end > 1 ? row_end * (row_end - 1) / 2 : 0) - (row_begin > 1 ? row_begin * (row_begin - 1) / 2 : 0);
+    uint32_t *d_pk = nullptr;
+    LDX_TRY(settle_before_host_call(ctx));
+    LDX_TRY(arena_get(ctx, S_PACKED, sizeof(uint32_t) * (size_t)std::max<int64_t>(n_pairs, 1), (void **)&d_pk));
+    LDX_TRY(ldx_triangle_rows_dev(s, rows, v, row_begin, row_end, measure, has_thres, thres_e4, engine, d_pk, nullptr));
+    // ldx_triangle_text resolves the pending call (near-ties settled into d_pk) before it reads the words
+    return ldx_triangle_text(ctx, d_pk, v, row_begin, row_end, measure, prefixes, prefix_off, flags | LDX_TEXT_PACKED_ON_DEVICE,
+                             text, cap, n_bytes);
+}
+
 // ------------------------------------------------------------------------------------------ resolve
 __global__ void scatter_words_kernel(uint8_t *base, const uint64_t *__restrict__ byte_off, const uint32_t *__restrict__ words, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -19,7 +19,7 @@ import sqlite3
 
 import numpy as np
 
-from .engine import Context, HostText, Store, dprime_value, r2_value, threshold_e4, tri_index
+from .engine import Context, HostText, Store, dprime_value, r2_value, threshold_e4
 from ._lib import VCF_ROW_DTYPE, LdxError
 
 RS_RE = re.compile(r"rs\d+$")
@@ -322,17 +322,16 @@ def ld_triangle(src_dir_path, intgen_dir_path, trg_top_dir_path=None, meta_lines
                 ids = [i for _, i in var_rows]
                 v = len(ids)
                 rows = np.array([cd.row_of(p, i) for p, i in var_rows], dtype=np.int64)
-                packed, _ = cd.store.triangle(rows, measure=ld_measure, thres_e4_=t_e4)      # :133-230 in one call
                 tab = "\t"
                 with open(os.path.join(trg_dir, f"{base}_chr{chrom}_{ld_measure[0]}.tsv"), "wb") as fh:  # :351-360
                     fh.write((f"##General\tinfo:\t{ld_measure}\tchr{chrom}\t{tab.join(pops)}\t{tab.join(gends)}\n\n"
                               + "rsIDs\t\t" + "\t".join(ids) + "\n" + "\tPositions\t" + "\t".join(poss) + "\n").encode())
-                    # the V lines of V cells (:356-360) are formatted on the GPU, a slab of rows at a time
+                    # the double loop (:133-230) and the V lines of V cells (:356-360): all-pairs kernel, settlement and
+                    # the writer in one library call per slab of rows; only text leaves the GPU
                     prefixes = [(i + "\t" + p + "\t").encode() for i, p in zip(ids, poss)]
-                    slab = max(1, TEXT_SLAB_BYTES // (7 * v))
+                    slab = max(256, TEXT_SLAB_BYTES // (7 * v) // 256 * 256)
                     for r0 in range(0, v, slab):
-                        r1 = min(v, r0 + slab)
-                        fh.write(ctx.triangle_text(packed[tri_index(r0, 0):tri_index(r1, 0)], v, ld_measure, prefixes, r0, r1).data)
+                        fh.write(cd.store.triangle_table(rows, prefixes, ld_measure, t_e4, row_begin=r0, row_end=min(v, r0 + slab)).data)
     finally:
         for cd in chrom_cache.values():
             cd.close()

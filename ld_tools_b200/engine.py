@@ -397,6 +397,26 @@ class Store:
                                           int(engine), ptr(packed), ptr(n11)))
         return packed, n11
 
+    def triangle_table(self, rows, prefixes, measure="r_square", thres_e4_=None, engine=ENGINE_AUTO, row_begin=0,
+                       row_end=None, out=None):
+        """Matrix rows row_begin..row_end-1 (row_begin % 128 == 0) of ld_triangle's table as text: all-pairs kernel,
+        settlement and the writer (ld_triangle.py:133-230, :356-360) in one library call; the words never leave HBM.
+        `prefixes`: one bytes object per matrix row.  -> uint8 array (a view of `out` when given)."""
+        rows = _i64(rows)
+        v = rows.shape[0]
+        row_end = v if row_end is None else row_end
+        assert len(prefixes) == v
+        blob = np.frombuffer(b"".join(prefixes) + b"\0", dtype=np.uint8)
+        off = np.zeros(v + 1, dtype=np.int64)
+        np.cumsum([len(p) for p in prefixes], out=off[1:])
+        if out is None:
+            out = np.empty(FORMAT_CELL_MAX * v * (row_end - row_begin) + int(off[row_end] - off[row_begin]), dtype=np.uint8)
+        n = C.c_int64()
+        check(self._lib.ldx_triangle_table(self._h, ptr(rows), v, int(row_begin), int(row_end), _measure_code(measure),
+                                           int(thres_e4_ is not None), int(thres_e4_ or 0), int(engine), ptr(blob), ptr(off),
+                                           0, ptr(out), out.shape[0], C.byref(n)))
+        return out[:n.value]
+
     def triangle_rows_dev(self, rows, row_begin, row_end, dev_packed, dev_n11=0, measure="r_square", thres_e4_=None,
                           engine=ENGINE_AUTO):
         rows = _i64(rows)

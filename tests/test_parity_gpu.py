@@ -730,3 +730,23 @@ def test_triangle_text_tiny_matrices(ctx):
         assert ctx.triangle_text(packed, v, "r_square", prefixes).tobytes() == _python_body(packed, v, "r_square", prefixes)
         st.close()
     assert ctx.triangle_text(np.zeros(0, np.uint32), 5, "r_square", [b""] * 5, 2, 2).shape[0] == 0
+
+
+@pytest.mark.parametrize("n_var,n_hap,measure,thres", [(700, 198, "r_square", None), (700, 5008, "d_prime", 0.4),
+                                                        (130, 1006, "r_square", 0.02), (1, 198, "r_square", None)])
+def test_triangle_table_is_triangle_plus_text(ctx, n_var, n_hap, measure, thres):
+    """ldx_triangle_table (all-pairs kernel + settlement + writer, words never leave HBM) = the two separate calls,
+    whole and in slabs of 256 rows; small haplotype counts make near-ties (settled on the host) common."""
+    from ld_tools_b200.engine import threshold_e4
+    st, planes, mask = make_store(ctx, max(n_var, 8), n_hap, seed=500 + n_var + n_hap)
+    rows = np.random.default_rng(n_var).permutation(max(n_var, 8))[:n_var]
+    t = None if thres is None else threshold_e4(thres)
+    prefixes = [b"rs%d\t%d\t" % (k, 5 * k) for k in range(n_var)]
+    packed, _ = st.triangle(rows, measure=measure, thres_e4_=t)
+    want = ctx.triangle_text(packed, n_var, measure, prefixes).tobytes()
+    assert want == _python_body(packed, n_var, measure, prefixes)
+    assert st.triangle_table(rows, prefixes, measure, t).tobytes() == want
+    parts = [st.triangle_table(rows, prefixes, measure, t, row_begin=r0, row_end=min(n_var, r0 + 256)).tobytes()
+             for r0 in range(0, n_var, 256)]
+    assert b"".join(parts) == want
+    st.close()

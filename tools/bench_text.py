@@ -68,6 +68,10 @@ def main():
         k_ms /= max(k_n, 1)
         host = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
         ms_host = timed(lambda: ctx.triangle_text(dev.data_ptr(), v, "r_square", prefixes, out=host), 3)
+        # ---- store -> text on the host in one call (all-pairs kernel + settlement + writer + the copy of the text)
+        two_calls = host[:n].tobytes()
+        same = st.triangle_table(rows, prefixes, out=host).tobytes() == two_calls
+        ms_table = timed(lambda: st.triangle_table(rows, prefixes, out=host), 3)
         # ---- the reference's writer on a bounded sample of rows (one host core), and parity on those rows
         packed = dev.cpu().numpy().view(np.uint32)
         sample = sorted(set(np.linspace(0, v - 1, num=min(v, 200 if v <= 4000 else 24), dtype=np.int64).tolist()))
@@ -85,7 +89,7 @@ def main():
                     "device_call_ms": ms_dev, "text_kernel_ms": k_ms, "text_kernel_launches_timed": int(k_n),
                     "text_kernel_GBps": bytes_k / k_ms / 1e6, "hbm_peak_GBps": hbm, "frac_of_hbm_peak": bytes_k / k_ms / 1e6 / hbm,
                     "cells_per_s_device": v * v / ms_dev * 1e3, "to_host_call_ms": ms_host, "cells_per_s_to_host": v * v / ms_host * 1e3,
-                    "text_GBps_to_host": n / ms_host / 1e6,
+                    "text_GBps_to_host": n / ms_host / 1e6, "triangle_table_call_ms": ms_table, "triangle_table_equals_two_calls": same,
                     "python_writer_cells_per_s_1core": len(sample) * v / py_s, "python_rows_sampled": len(sample),
                     "sample_rows_identical": bool(ok)})
         print(json.dumps(out[-1]), flush=True)

@@ -41,10 +41,16 @@ __host__ __device__ __forceinline__ uint64_t text_of_e4(uint32_t k, int *len) {
 }
 
 // A matrix cell given its result word: "0" for the reference's int 0 (threshold, monomorphic, d' == 0), else the float.
-__device__ __forceinline__ uint64_t text_of_word(uint32_t w, int measure, int *len) {
-    const bool int0 = (w & LDX_BELOW_THRES) || (w & (measure == LDX_MEASURE_R2 ? LDX_R2_INT0 : LDX_DP_INT0));
-    if (int0) { *len = 1; return '0'; }
-    return text_of_e4(measure == LDX_MEASURE_R2 ? (w & LDX_R2_MASK) : ((w & LDX_DP_MASK) >> LDX_DP_SHIFT), len);
+// Branch-free (the digits are computed for every word and dropped for an int 0): the lanes of a warp never diverge on
+// the data and the eight words of a thread can be loaded ahead of their use.  dp_shift = 0 / 16 and int0_mask select
+// the measure.
+__device__ __forceinline__ void text_of_word(uint32_t w, int dp_shift, uint32_t int0_mask, uint32_t *lo, uint32_t *hi, int *len) {
+    int n;
+    const uint64_t t = text_of_e4((w >> dp_shift) & LDX_R2_MASK, &n);
+    const bool int0 = (w & int0_mask) != 0;
+    *lo = int0 ? (uint32_t)'0' : (uint32_t)t;
+    *hi = int0 ? 0u : (uint32_t)(t >> 32);
+    *len = int0 ? 1 : n;
 }
 
 __device__ __forceinline__ int64_t tri64(int64_t r) { return r * (r - 1) / 2; }
@@ -55,13 +61,16 @@ matrix_line_bytes_kernel(const uint32_t *__restrict__ packed, int64_t v, int64_t
                          const int64_t *__restrict__ prefix_off, int64_t *__restrict__ line_bytes) {
     using Reduce = cub::BlockReduce<int, FMT_THREADS>;
     __shared__ typename Reduce::TempStorage tmp;
+    const int dp_shift = measure == LDX_MEASURE_R2 ? 0 : LDX_DP_SHIFT;
+    const uint32_t int0_mask = LDX_BELOW_THRES | (measure == LDX_MEASURE_R2 ? LDX_R2_INT0 : LDX_DP_INT0);
     for (int64_t l = blockIdx.x; l < n_lines; l += gridDim.x) {
         const int64_t r = row_begin + l;
         const uint32_t *__restrict__ words = packed + (tri64(r) - tri64(row_begin));
         int sum = 0;
-        for (int64_t c = threadIdx.x; c < r; c += FMT_THREADS) {
+        for (int c = threadIdx.x; c < (int)r; c += FMT_THREADS) {
+            uint32_t lo, hi;
             int len;
-            text_of_word(__ldg(words + c), measure, &len);
+            text_of_word(__ldg(words + c), dp_shift, int0_mask, &lo, &hi, &len);
             sum += len + 1;
         }
         const int total = Reduce(tmp).Sum(sum);
@@ -101,6 +110,8 @@ matrix_text_kernel(const uint32_t *__restrict__ packed, int64_t v, int64_t row_b
     __shared__ typename Scan::TempStorage tmp;
     __shared__ __align__(16) unsigned char buf[FMT_CHUNK * FMT_CELL_MAX + 32];
     const int tid = threadIdx.x;
+    const int dp_shift = measure == LDX_MEASURE_R2 ? 0 : LDX_DP_SHIFT;
+    const uint32_t int0_mask = LDX_BELOW_THRES | (measure == LDX_MEASURE_R2 ? LDX_R2_INT0 : LDX_DP_INT0);
     for (int64_t l = blockIdx.x; l < n_lines; l += gridDim.x) {
         const int64_t r = row_begin + l;
         char *out = text + line_off[l];
@@ -108,20 +119,18 @@ matrix_text_kernel(const uint32_t *__restrict__ packed, int64_t v, int64_t row_b
         for (int64_t i = tid; i < plen; i += FMT_THREADS) out[i] = prefixes[p0 + i];
         int64_t pos = plen;
         const uint32_t *__restrict__ words = packed + (tri64(r) - tri64(row_begin));
-        for (int64_t cb = 0; cb < r; cb += FMT_CHUNK) {
-            uint32_t lo[FMT_CELLS_PER_THREAD], hi[FMT_CELLS_PER_THREAD];
+        for (int cb = 0; cb < (int)r; cb += FMT_CHUNK) {
+            uint32_t w[FMT_CELLS_PER_THREAD], lo[FMT_CELLS_PER_THREAD], hi[FMT_CELLS_PER_THREAD];
             int len[FMT_CELLS_PER_THREAD], mine = 0;
-            const int64_t c0 = cb + (int64_t)tid * FMT_CELLS_PER_THREAD;
+            const int c0 = cb + tid * FMT_CELLS_PER_THREAD;
+            const int n_valid = min(max((int)r - c0, 0), FMT_CELLS_PER_THREAD);       // this thread's cells left of the diagonal
+#pragma unroll
+            for (int k = 0; k < FMT_CELLS_PER_THREAD; ++k) w[k] = k < n_valid ? __ldg(words + c0 + k) : 0u;
 #pragma unroll
             for (int k = 0; k < FMT_CELLS_PER_THREAD; ++k) {
-                len[k] = 0; lo[k] = 0; hi[k] = 0;
-                if (c0 + k < r) {
-                    int n;
-                    const uint64_t t = text_of_word(__ldg(words + c0 + k), measure, &n);
-                    lo[k] = (uint32_t)t; hi[k] = (uint32_t)(t >> 32);
-                    len[k] = n;
-                    mine += n + 1;
-                }
+                text_of_word(w[k], dp_shift, int0_mask, &lo[k], &hi[k], &len[k]);
+                if (k >= n_valid) len[k] = 0;
+                mine += k < n_valid ? len[k] + 1 : 0;
             }
             int off, total;
             Scan(tmp).ExclusiveSum(mine, off, total);

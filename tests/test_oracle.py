@@ -179,3 +179,29 @@ def test_table_port_reproduces_reference_tables():
         for row in cells:
             for t in row:
                 assert t == "0" or (t == str(round(float(t), 4)) and "e" not in t)
+
+
+@pytest.mark.parametrize("n_hap,measure,thres", [(14, "d_prime", None), (198, "r_square", 0.3), (1006, "d_prime", 0.9)])
+def test_packed_words_print_like_the_reference_objects(n_hap, measure, thres):
+    """Host-side decode of the result word (engine.measure_value + BELOW_THRES) feeds str() the same objects the
+    reference's matrix holds: table text from the words = table text from the oracle's calc_ld dicts."""
+    from oracle import table_port
+    from ld_tools_b200.engine import BELOW_THRES, measure_value, threshold_e4
+    from ld_tools_b200.synth import synth_haplotypes
+    v = 40
+    planes = ld_oracle.pack_bits(synth_haplotypes(v, n_hap, seed=n_hap))
+    mask = ld_oracle.mask_from_haplotypes(np.arange(n_hap), n_hap)
+    res = ld_oracle.triangle(planes, mask, n_hap, np.arange(v))
+    vals = [ld_oracle.as_reference_dict(x)[measure] for x in res]
+    ids, poss = [f"rs{k}" for k in range(v)], [str(100 + k) for k in range(v)]
+    want = table_port.matrix_body(lambda r, c: vals[r * (r - 1) // 2 + c], v, ids, poss, thres)
+    words = ld_oracle.packed_of(res)
+    if thres is not None:
+        shift = 0 if measure == "r_square" else 16
+        words = words | np.where(((words >> shift) & 0x3FFF) < threshold_e4(thres), np.uint32(BELOW_THRES), np.uint32(0))
+    lines = []
+    for r in range(v):
+        cells = ["0" if (c >= r or words[r * (r - 1) // 2 + c] & BELOW_THRES) else str(measure_value(words[r * (r - 1) // 2 + c], measure))
+                 for c in range(v)]
+        lines.append(ids[r] + "\t" + poss[r] + "\t" + "\t".join(cells) + "\n")
+    assert "".join(lines) == want

@@ -66,8 +66,19 @@ matrix_line_bytes_kernel(const uint32_t *__restrict__ packed, int64_t v, int64_t
     for (int64_t l = blockIdx.x; l < n_lines; l += gridDim.x) {
         const int64_t r = row_begin + l;
         const uint32_t *__restrict__ words = packed + (tri64(r) - tri64(row_begin));
-        int sum = 0;
-        for (int c = threadIdx.x; c < (int)r; c += FMT_THREADS) {
+        int sum = 0, c = threadIdx.x;
+        for (; c + 3 * FMT_THREADS < (int)r; c += 4 * FMT_THREADS) {           // four loads in flight per thread
+            uint32_t w[4], lo, hi;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w[k] = __ldg(words + c + k * FMT_THREADS);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int len;
+                text_of_word(w[k], dp_shift, int0_mask, &lo, &hi, &len);
+                sum += len + 1;
+            }
+        }
+        for (; c < (int)r; c += FMT_THREADS) {
             uint32_t lo, hi;
             int len;
             text_of_word(__ldg(words + c), dp_shift, int0_mask, &lo, &hi, &len);

@@ -11,8 +11,9 @@
 //                              trailing zeros dropped and at least one fractional digit: "0.0", "0.5", "0.8125", "1.0".
 // Line r = prefix[r] (rsID '\t' position '\t', supplied by the caller) + the cells joined by '\t' + '\n'.
 //
-// Byte work bound by HBM: 4 B read per lower-triangle cell, 2..7 B written per cell.  Two passes over the words
-// (line lengths, then the text) with a device-wide scan of the line lengths in between.
+// Byte work: 4 B read per lower-triangle cell, 2..7 B written per cell, two passes over the words (line lengths, then
+// the text) with a device-wide scan of the line lengths in between.  HBM is the roofline by bytes (0.37 of the measured
+// peak at 20,000 x 20,000 cells); what the text kernel is bound by is the byte stores into shared memory.
 #include <algorithm>
 #include <cstring>
 

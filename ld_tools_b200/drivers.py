@@ -329,9 +329,11 @@ def ld_triangle(src_dir_path, intgen_dir_path, trg_top_dir_path=None, meta_lines
                     # the double loop (:133-230) and the V lines of V cells (:356-360): all-pairs kernel, settlement and
                     # the writer in one library call per slab of rows; only text leaves the GPU
                     prefixes = [(i + "\t" + p + "\t").encode() for i, p in zip(ids, poss)]
-                    slab = max(256, TEXT_SLAB_BYTES // (7 * v) // 256 * 256)
+                    slab = min(v, max(256, TEXT_SLAB_BYTES // (7 * v) // 256 * 256))
+                    buf = np.empty(7 * v * slab + sum(map(len, prefixes)), dtype=np.uint8)        # one buffer for every slab
                     for r0 in range(0, v, slab):
-                        fh.write(cd.store.triangle_table(rows, prefixes, ld_measure, t_e4, row_begin=r0, row_end=min(v, r0 + slab)).data)
+                        fh.write(cd.store.triangle_table(rows, prefixes, ld_measure, t_e4, row_begin=r0, row_end=min(v, r0 + slab),
+                                                         out=buf).data)
     finally:
         for cd in chrom_cache.values():
             cd.close()

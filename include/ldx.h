@@ -102,8 +102,11 @@ int32_t ldx_synchronize(ldx_ctx *ctx);
  *   LDX_TUNE_DEFER_CAP   capacity of the tcgen05 engine's deferred-pair lists (0 = sized from the pair count); a
  *                        small value forces the overflow paths (pairs settled in place) -- for tests
  *   LDX_TUNE_WINDOW_MQ   1 (default) = window scans of several queries with monotone candidate ranges use the multi-query
- *                        kernel (a store row is loaded once per four queries); 0 = always one query per pass */
-enum { LDX_TUNE_MMA_TILE_N = 1, LDX_TUNE_MMA_MIN_V = 2, LDX_TUNE_MMA_PAIR = 3, LDX_TUNE_DEFER_CAP = 4, LDX_TUNE_WINDOW_MQ = 5 };
+ *                        kernel (a store row is loaded once per four queries); 0 = always one query per pass
+ *   LDX_TUNE_MMA_DIRECT  -1 / 1 (default) = a one-wave all-pairs call whose rows[] are contiguous store rows reads the planes
+ *                        through a TMA tensor map (no gather kernel, no operand scratch); 0 = always gather */
+enum { LDX_TUNE_MMA_TILE_N = 1, LDX_TUNE_MMA_MIN_V = 2, LDX_TUNE_MMA_PAIR = 3, LDX_TUNE_DEFER_CAP = 4, LDX_TUNE_WINDOW_MQ = 5,
+       LDX_TUNE_MMA_DIRECT = 6 };
 int32_t ldx_set_tuning(ldx_ctx *ctx, int32_t key, int32_t value);
 /* Diagnostics: with enable != 0 the tcgen05 all-pairs kernel's first CTA records %globaltimer
  * stamps (ns): [0] prologue done, [1]/[2] accumulator ready / epilogue done of its 1st tile,
@@ -278,6 +281,23 @@ int32_t ldx_window_dev(ldx_store *store, const int64_t *q_row, const int64_t *lo
                        int32_t measure, int32_t thres_e4, ldx_hit *dev_hits, int64_t cap,
                        int64_t *dev_n_hits);
 int32_t ldx_resolve(ldx_ctx *ctx, int64_t *n_fixed_out);
+/* Several independent variant sets in ONE launch of the all-pairs engine.  The reference's unit of work is one matrix per
+ * (source file, chromosome) (ld_triangle.py:80-88; its own fan-out over them is the process pool of :406-408); a
+ * 2,000-variant matrix alone is a single wave of tiles on 148 SMs and is bound by launch, pipeline-fill and drain
+ * latencies, a batch of them is not.  Set k is the lower triangle of rows[0..v) of its store (as ldx_triangle_dev:
+ * v*(v-1)/2 words into dev_packed, dev_n11 may be NULL).  Sets that share the haplotype count and the number of selected
+ * haplotypes (e.g. the chromosomes of one sample selection) go into the same launch, up to 32 per launch; anything else
+ * falls back to one ldx_triangle_dev call per set.  Enqueue only: ldx_resolve() as for the other *_dev calls.
+ * rows[] arrays are HOST arrays. */
+typedef struct {
+    ldx_store *store;
+    const int64_t *rows;
+    int64_t v;
+    uint32_t *dev_packed;
+    int32_t *dev_n11;
+} ldx_triangle_set;
+int32_t ldx_triangle_batch_dev(ldx_ctx *ctx, const ldx_triangle_set *sets, int32_t n_sets, int32_t measure,
+                               int32_t has_thres, int32_t thres_e4, int32_t engine);
 
 /* ---------------------------------------------------------------- matrix text
  * Replaces the table writer's body loop, ld_triangle.py:356-360: `'\t'.join(map(str, ld_two_dim[row]))` for

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libldx.so")
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_EMPTY, ERR_CAPACITY, ERR_STATE, ERR_DATA = 0, -1, -2, -3, -4, -5, -6, -7
 MEASURE_R2, MEASURE_DPRIME = 0, 1
 ENGINE_AUTO, ENGINE_POPC, ENGINE_MMA = 0, 1, 2
-TUNE_MMA_TILE_N, TUNE_MMA_MIN_V, TUNE_MMA_PAIR, TUNE_DEFER_CAP, TUNE_WINDOW_MQ = 1, 2, 3, 4, 5
+TUNE_MMA_TILE_N, TUNE_MMA_MIN_V, TUNE_MMA_PAIR, TUNE_DEFER_CAP, TUNE_WINDOW_MQ, TUNE_MMA_DIRECT = 1, 2, 3, 4, 5, 6
 TEXT_PACKED_ON_DEVICE, TEXT_OUT_ON_DEVICE = 1, 2
 R2_MASK, R2_INT0, DP_SHIFT, DP_MASK, BELOW_THRES, DP_INT0 = 0x3FFF, 0x8000, 16, 0x3FFF0000, 0x40000000, 0x80000000
 
@@ -20,6 +20,7 @@ HIT_DTYPE = np.dtype([("query", "<i4"), ("row", "<i4"), ("n11", "<i4"), ("packed
 VCF_ROW_DTYPE = np.dtype([("line_off", "<i8"), ("idnum", "<i8"), ("gt_off", "<i4"), ("id_off", "<i4"), ("ref_off", "<i4"),
                           ("alt_off", "<i4"), ("info_off", "<i4"), ("fmt_off", "<i4"), ("pos", "<i4"), ("ref_len", "<i4"),
                           ("status", "u1"), ("eligible", "u1"), ("multi", "u1"), ("pad", "u1", (5,))])
+TRIANGLE_SET_DTYPE = np.dtype([("store", "<u8"), ("rows", "<u8"), ("v", "<i8"), ("dev_packed", "<u8"), ("dev_n11", "<u8")])   # ldx_triangle_set
 LD_RESULT_DTYPE = np.dtype([
     ("n_hap", "<i8"), ("n_11", "<i8"), ("n_a1", "<i8"), ("n_a0", "<i8"), ("n_b1", "<i8"), ("n_b0", "<i8"),
     ("d", "<f8"), ("dprime", "<f8"), ("r2", "<f8"), ("p_a", "<f8"), ("p_b", "<f8"),
@@ -78,6 +79,7 @@ SIGNATURES = {
     "ldx_triangle_rows_dev": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp],
     "ldx_window_dev": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp],
     "ldx_resolve": [_vp, _P(_i64)],
+    "ldx_triangle_batch_dev": [_vp, _vp, _i32, _i32, _i32, _i32, _i32],
     "ldx_triangle_text": [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _i32, _vp, _i64, _P(_i64)],
     "ldx_triangle_table": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _P(_i64)],
     "ldx_format_e4": [_i32, _vp],

@@ -175,6 +175,10 @@ extern "C" int32_t ldx_set_tuning(ldx_ctx *ctx, int32_t key, int32_t value) {
             LDX_REQUIRE(value == 0 || value == 1, "window multi-query mode must be 0 or 1");
             ctx->window_mq = value;
             return LDX_OK;
+        case LDX_TUNE_MMA_DIRECT:
+            LDX_REQUIRE(value >= -1 && value <= 1, "direct mode must be -1 (auto), 0 or 1");
+            ctx->mma_direct = value;
+            return LDX_OK;
         case LDX_TUNE_DEFER_CAP:
             LDX_REQUIRE(value >= 0, "deferred-pair list capacity must be >= 0");
             ctx->defer_cap = value;
@@ -475,7 +479,9 @@ extern "C" int32_t ldx_store_create(ldx_ctx *ctx, int64_t n_variants, int32_t n_
     cudaError_t e = cudaMalloc(&s->d_planes, nv * s->stride_words * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMemsetAsync(s->d_planes, 0, nv * s->stride_words * sizeof(uint64_t), ctx->stream);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_mask, s->stride_words * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_freq, nv * sizeof(VarFreq));
+    // STORE_FREQ_PAD zeroed records past the last variant: the tcgen05 engine's direct mode reads whole 128-row tiles
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_freq, (nv + STORE_FREQ_PAD) * sizeof(VarFreq));
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_freq, 0, (nv + STORE_FREQ_PAD) * sizeof(VarFreq), ctx->stream);
     if (e != cudaSuccess) { ldx_store_destroy(s); cudaGetLastError(); return set_error(LDX_ERR_NOMEM, std::string("store device allocation: ") + cudaGetErrorString(e)); }
     *store_out = s;
     return LDX_OK;
@@ -485,6 +491,7 @@ extern "C" int32_t ldx_store_destroy(ldx_store *s) {
     if (!s) return LDX_OK;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
+    s->ctx->rows_cache_valid = false;          // a staged variant list validated against this store means nothing to the next one
     cudaFree(s->d_planes); cudaFree(s->d_mask); cudaFree(s->d_freq);
     cudaFree(s->d_pos0); cudaFree(s->d_end0); cudaFree(s->d_idnum); cudaFree(s->d_eligible);
     delete s;
@@ -975,23 +982,51 @@ extern "C" int32_t ldx_window(ldx_store *s, const int64_t *q_row, const int64_t 
 }
 
 // ------------------------------------------------------------------------------------------ triangle
-static int stage_rows(ldx_store *s, const int64_t *rows, int64_t v, int64_t **d_rows_out) {
-    LDX_TRY(require_mask(s));
-    LDX_REQUIRE(v >= 0 && v < (1ll << 31) && (v == 0 || rows), "bad rows");
-    if (v == 0) { *d_rows_out = nullptr; return LDX_OK; }
-    ldx_ctx *ctx = s->ctx;
+// The variant lists of a call (one per set), concatenated, on the device.  Repeated calls with the same lists for the same
+// stores (the usual case) skip validation and the upload: the cache key records which store (and how many rows of it) every
+// list was checked against.  contiguous[k] (may be NULL) = rows[k] is first, first + 1, ...
+struct RowList { ldx_store *s; const int64_t *rows; int64_t v; };
+static int stage_rows(ldx_ctx *ctx, const RowList *lists, int n, int64_t **d_rows_out, int64_t *offsets, bool *contiguous) {
+    int64_t total = 0;
+    for (int k = 0; k < n; ++k) {
+        LDX_TRY(require_mask(lists[k].s));
+        LDX_REQUIRE(lists[k].s->ctx == ctx, "store of another context");
+        LDX_REQUIRE(lists[k].v >= 0 && lists[k].v < (1ll << 31) && (lists[k].v == 0 || lists[k].rows), "bad rows");
+        offsets[k] = total;
+        total += lists[k].v;
+    }
+    *d_rows_out = nullptr;
+    if (total == 0) { for (int k = 0; k < n && contiguous; ++k) contiguous[k] = false; return LDX_OK; }
     LDX_CUDA(cudaSetDevice(ctx->device));
     Arena *a = arena_of(ctx);
     void *before = a->ptr[S_ROWS];
-    LDX_TRY(arena_get(ctx, S_ROWS, sizeof(int64_t) * (size_t)v, (void **)d_rows_out));
-    // repeated calls on the same variant list (the usual case) skip validation and the upload
-    const bool same = before == a->ptr[S_ROWS] && (int64_t)ctx->rows_cache.size() == v &&
-                      std::memcmp(ctx->rows_cache.data(), rows, sizeof(int64_t) * (size_t)v) == 0;
-    if (same) return LDX_OK;
-    ctx->rows_cache.clear();
-    for (int64_t k = 0; k < v; ++k) LDX_REQUIRE(rows[k] >= 0 && rows[k] < s->n_variants, "rows[] outside the store");
-    ctx->rows_cache.assign(rows, rows + v);
-    LDX_CUDA(cudaMemcpyAsync(*d_rows_out, ctx->rows_cache.data(), sizeof(int64_t) * (size_t)v, cudaMemcpyHostToDevice, ctx->stream));
+    LDX_TRY(arena_get(ctx, S_ROWS, sizeof(int64_t) * (size_t)total, (void **)d_rows_out));
+    std::vector<int64_t> key;
+    key.reserve(3 * (size_t)n);
+    for (int k = 0; k < n; ++k) { key.push_back((int64_t)reinterpret_cast<intptr_t>(lists[k].s)); key.push_back(lists[k].s->n_variants); key.push_back(lists[k].v); }
+    bool same = ctx->rows_cache_valid && before == a->ptr[S_ROWS] && (int64_t)ctx->rows_cache.size() == total && ctx->rows_cache_key == key;
+    for (int k = 0; k < n && same; ++k)
+        same = lists[k].v == 0 || std::memcmp(ctx->rows_cache.data() + offsets[k], lists[k].rows, sizeof(int64_t) * (size_t)lists[k].v) == 0;
+    if (!same) {
+        ctx->rows_cache_valid = false;
+        for (int k = 0; k < n; ++k)
+            for (int64_t i = 0; i < lists[k].v; ++i)
+                LDX_REQUIRE(lists[k].rows[i] >= 0 && lists[k].rows[i] < lists[k].s->n_variants, "rows[] outside the store");
+        ctx->rows_cache.resize((size_t)total);
+        for (int k = 0; k < n; ++k)
+            if (lists[k].v) std::memcpy(ctx->rows_cache.data() + offsets[k], lists[k].rows, sizeof(int64_t) * (size_t)lists[k].v);
+        // the host copy stays alive (and unchanged) until the next staging, which the stream orders after this copy's consumers
+        LDX_CUDA(cudaMemcpyAsync(*d_rows_out, ctx->rows_cache.data(), sizeof(int64_t) * (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->rows_cache_key = key;
+        ctx->rows_cache_contig.assign((size_t)n, 0);
+        for (int k = 0; k < n; ++k) {
+            bool c = lists[k].v > 0;
+            for (int64_t i = 1; i < lists[k].v && c; ++i) c = lists[k].rows[i] == lists[k].rows[0] + i;
+            ctx->rows_cache_contig[(size_t)k] = c ? 1 : 0;
+        }
+        ctx->rows_cache_valid = true;                 // only now: a failed copy must not leave a cache that claims an upload
+    }
+    for (int k = 0; k < n && contiguous; ++k) contiguous[k] = ctx->rows_cache_contig[(size_t)k] != 0;
     return LDX_OK;
 }
 
@@ -1002,10 +1037,13 @@ extern "C" int32_t ldx_triangle_rows_dev(ldx_store *s, const int64_t *rows, int6
     LDX_REQUIRE(engine >= LDX_ENGINE_AUTO && engine <= LDX_ENGINE_MMA, "bad engine");
     LDX_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= v, "bad row range");
     LDX_REQUIRE(row_begin % 128 == 0, "row_begin must be a multiple of 128");
-    int64_t *d_rows;
-    LDX_TRY(stage_rows(s, rows, v, &d_rows));
-    if (row_end < 2 || row_begin == row_end) return LDX_OK;
+    LDX_REQUIRE(s, "store is NULL");
     ldx_ctx *ctx = s->ctx;
+    int64_t *d_rows, off = 0;
+    bool contiguous = false;
+    const RowList list = {s, rows, v};
+    LDX_TRY(stage_rows(ctx, &list, 1, &d_rows, &off, &contiguous));
+    if (row_end < 2 || row_begin == row_end) return LDX_OK;
     if (engine == LDX_ENGINE_MMA && !triangle_mma_available())
         return set_error(LDX_ERR_ARG, "the tcgen05 engine is not available in this build");
     const bool use_mma = engine == LDX_ENGINE_MMA || (engine == LDX_ENGINE_AUTO && triangle_mma_available() && row_end >= ctx->mma_min_v &&
@@ -1013,12 +1051,65 @@ extern "C" int32_t ldx_triangle_rows_dev(ldx_store *s, const int64_t *rows, int6
     // rows[] staging is consumed by the kernel on the same stream (stage_rows keeps a host copy alive)
     const uint32_t seq = ctx->seq + 1 ? ctx->seq + 1 : 1;     // 0 means "nothing published"
     LDX_TRY(begin_dev_call(ctx));
-    int rc = use_mma ? launch_triangle_mma(s, d_rows, row_end, row_begin, measure, has_thres, thres_e4, dev_packed, dev_n11, seq)
-                     : launch_triangle_popc(s, d_rows, row_end, row_begin, measure, has_thres, thres_e4, dev_packed, dev_n11);
+    int rc;
+    if (use_mma) {
+        const MmaSetDesc d = {s, 0, row_end, row_begin, dev_packed, dev_n11, ctx->fix_tag, rows[0], contiguous};
+        rc = launch_triangle_mma(ctx, &d, 1, d_rows, measure, has_thres, thres_e4, seq);
+    } else rc = launch_triangle_popc(s, d_rows, row_end, row_begin, measure, has_thres, thres_e4, dev_packed, dev_n11);
     LDX_TRY(rc);
     ctx->seq = seq;
     if (!use_mma) LDX_TRY(launch_publish(ctx));
     end_dev_call(ctx, 1, dev_packed, s->fc.n_hap, measure, has_thres, thres_e4);
+    return LDX_OK;
+}
+
+// Several variant sets -- the reference's unit of work is one matrix per (source file, chromosome), ld_triangle.py:80-88 and
+// :406-408 -- in ONE persistent launch of the tcgen05 engine: a 2,000-variant matrix is a single wave of tiles, bound by
+// launch, pipeline-fill and drain latencies; a batch of them keeps every SM busy across sets.
+extern "C" int32_t ldx_triangle_batch_dev(ldx_ctx *ctx, const ldx_triangle_set *sets, int32_t n_sets, int32_t measure,
+                                          int32_t has_thres, int32_t thres_e4, int32_t engine) {
+    LDX_REQUIRE(ctx && (sets || n_sets == 0) && n_sets >= 0, "bad set list");
+    LDX_REQUIRE(measure == LDX_MEASURE_R2 || measure == LDX_MEASURE_DPRIME, "bad measure");
+    LDX_REQUIRE(engine >= LDX_ENGINE_AUTO && engine <= LDX_ENGINE_MMA, "bad engine");
+    for (int32_t k = 0; k < n_sets; ++k) {
+        LDX_REQUIRE(sets[k].store && sets[k].store->ctx == ctx, "every store of a batch must belong to the calling context");
+        LDX_REQUIRE(sets[k].v >= 0 && (sets[k].dev_packed || sets[k].v < 2), "bad set");
+    }
+    for (int32_t first = 0; first < n_sets;) {
+        // a launch takes the sets that follow with the same haplotype count and selection size, up to MMA_MAX_SETS
+        const ldx_store *s0 = sets[first].store;
+        int32_t n = 1;
+        while (first + n < n_sets && n < MMA_MAX_SETS && sets[first + n].store->n_hap == s0->n_hap && sets[first + n].store->n_sel == s0->n_sel &&
+               sets[first + n].store->mask_set && s0->mask_set) ++n;
+        int64_t v_max = sets[first].v;
+        for (int32_t k = 1; k < n; ++k) v_max = std::max(v_max, sets[first + k].v);
+        const bool use_mma = n > 1 && s0->mask_set && (engine == LDX_ENGINE_MMA || (engine == LDX_ENGINE_AUTO && triangle_mma_available() && v_max >= 2 &&
+                                                                                     s0->n_sel <= triangle_mma_max_haplotypes()));
+        if (!use_mma) {          // a lone set or too many haplotypes: the single-set path chooses its engine itself
+            for (int32_t k = 0; k < n; ++k)
+                LDX_TRY(ldx_triangle_dev(sets[first + k].store, sets[first + k].rows, sets[first + k].v, measure, has_thres, thres_e4, engine,
+                                         sets[first + k].dev_packed, sets[first + k].dev_n11));
+            first += n;
+            continue;
+        }
+        RowList lists[MMA_MAX_SETS];
+        int64_t offs[MMA_MAX_SETS];
+        for (int32_t k = 0; k < n; ++k) lists[k] = RowList{sets[first + k].store, sets[first + k].rows, sets[first + k].v};
+        int64_t *d_rows;
+        LDX_TRY(stage_rows(ctx, lists, n, &d_rows, offs, nullptr));
+        MmaSetDesc desc[MMA_MAX_SETS];
+        if (ctx->pending_q.size() + (size_t)n >= 4096) LDX_TRY(resolve_pending(ctx, nullptr));
+        for (int32_t k = 0; k < n; ++k) {
+            const ldx_triangle_set &t = sets[first + k];
+            LDX_TRY(begin_dev_call(ctx));
+            desc[k] = MmaSetDesc{t.store, offs[k], t.v, 0, t.dev_packed, t.dev_n11, ctx->fix_tag, 0, false};
+            end_dev_call(ctx, 1, t.dev_packed, t.store->fc.n_hap, measure, has_thres, thres_e4);
+        }
+        const uint32_t seq = ctx->seq + 1 ? ctx->seq + 1 : 1;
+        LDX_TRY(launch_triangle_mma(ctx, desc, n, d_rows, measure, has_thres, thres_e4, seq));
+        ctx->seq = seq;
+        first += n;
+    }
     return LDX_OK;
 }
 

@@ -39,19 +39,25 @@ struct ldx_ctx {
     void *d_mma_ops = nullptr;
     size_t mma_ops_bytes = 0;
     int mma_tile_n = 0;                   // tcgen05 tile width override (0 = heuristic)
-    int64_t mma_tiles_v = -1;             // tile list cached in d_mma_ops: built for this (v, N)
-    int mma_tiles_n = 0;
-    int64_t mma_tiles_begin = 0;
-    bool mma_tiles_pair = false;
+    // tile list cached in d_mma_ops: the key is everything the list depends on -- {tile width, pair mode, then per set
+    // (v, row_begin)} -- plus the place in the scratch block it was uploaded to (depends on the haplotype count too)
+    std::vector<int64_t> mma_tiles_key;
+    const void *mma_tiles_ptr = nullptr;
     int mma_pair = -1;                    // LDX_TUNE_MMA_PAIR: 256 x 128 tiles on CTA pairs (tcgen05 cta_group::2): 0 off, 1 on, -1 auto
-    const void *mma_tiles_ptr = nullptr;  // where in d_mma_ops that list lives (depends on the haplotype count too)
+    int mma_direct = -1;                  // LDX_TUNE_MMA_DIRECT: one-wave calls on contiguous store rows read the planes through a
+                                          // TMA tensor map (no gather kernel): 0 off, 1 / -1 (default) on
     // completion mailbox: pinned, device-mapped {seq, near-tie count, error flag}; a 1-thread kernel
     // publishes it after each *_dev call so that ldx_resolve() can poll host memory instead of
     // paying a stream synchronisation (tens of microseconds) per call
     volatile uint32_t *h_mailbox = nullptr;
     uint32_t *d_mailbox = nullptr;
     uint32_t seq = 0;
-    std::vector<int64_t> rows_cache;      // host copy of the variant list last staged on the device
+    // host copy of the variant list(s) last staged on the device, and what it was validated against: the same list may
+    // arrive for another (smaller) store on the same ctx, and must then be bounds-checked again
+    std::vector<int64_t> rows_cache;
+    std::vector<int64_t> rows_cache_key;  // per set {store address, its n_variants, v}
+    std::vector<char> rows_cache_contig;  // per set: rows[k] == rows[0] + k
+    bool rows_cache_valid = false;
     unsigned long long *d_trace = nullptr;   // diagnostics: globaltimer stamps written by the tcgen05 kernel
     void *h_stage = nullptr;              // pinned bounce buffer of the store files (allocated on first use)
     int window_mq = 1;                    // LDX_TUNE_WINDOW_MQ: 0 = ld_area scans always use the one-query-per-pass kernel
@@ -82,7 +88,12 @@ struct ldx_store {
     int64_t *d_idnum = nullptr;
     uint8_t *d_eligible = nullptr;
     bool annotated = false;
+    // TMA tensor map of the planes ([n_variants][stride_words * 2] uint32, box 8 x 128), encoded on first use by the
+    // tcgen05 engine's direct mode (ldx_triangle_mma.cu); 128 bytes, 64-byte aligned as the driver requires
+    alignas(64) unsigned char tmap[128] = {};
+    bool tmap_ready = false;
 };
+constexpr int64_t STORE_FREQ_PAD = 512;   // zeroed VarFreq entries past the last variant: the all-pairs kernels read whole tiles
 
 namespace ldx {
 
@@ -120,9 +131,17 @@ int launch_window(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, cons
 // row_begin .. v-1 (row_begin a multiple of 128); output index 0 is pair (row_begin, 0).
 int launch_triangle_popc(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t row_begin, int measure, int has_thres,
                          int thres_e4, uint32_t *d_packed, int32_t *d_n11);
-// publish_seq != 0: the engine's last kernel also publishes the completion record for that sequence number
-int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t row_begin, int measure, int has_thres,
-                        int thres_e4, uint32_t *d_packed, int32_t *d_n11, uint32_t publish_seq);
+// The tcgen05 engine works on up to MMA_MAX_SETS variant sets per launch (ldx_triangle_batch_dev): set k is the first v
+// entries of d_rows + rows_off and emits rows row_begin .. v-1 (row_begin = 0 unless n_sets == 1) into d_packed / d_n11;
+// fix_tag is ORed into the out_index of its near-tie records.  All sets share the haplotype and selected-haplotype counts.
+// contiguous: rows[k] == rows[0] + k (set 0 of a single-set call; host knowledge from stage_rows) -> direct mode may apply.
+// publish_seq != 0: the engine's last kernel also publishes the completion record for that sequence number.
+constexpr int MMA_MAX_SETS = 32;
+struct MmaSetDesc {
+    ldx_store *s; int64_t rows_off; int64_t v, row_begin; uint32_t *d_packed; int32_t *d_n11; uint64_t fix_tag; int64_t row0; bool contiguous;
+};
+int launch_triangle_mma(ldx_ctx *ctx, const MmaSetDesc *sets, int n_sets, const int64_t *d_rows, int measure, int has_thres,
+                        int thres_e4, uint32_t publish_seq);
 bool triangle_mma_available();
 int triangle_mma_max_haplotypes();
 int launch_publish(ldx_ctx *ctx);   // enqueue the mailbox update for ctx->seq

@@ -1,12 +1,22 @@
 // ldx_triangle_mma.cu -- K5: all-pairs (alt, alt) haplotype counts as an EXACT int8 Gram matrix
 // on the 5th-generation tensor cores (tcgen05.mma kind::i8, int32 accumulators in TMEM), with the
-// fp64 D / D' / r2 finalisation fused into the epilogue.
+// D / D' / r2 finalisation fused into the epilogue.
 //
 // Replaces the double loop at ld_triangle.py:133-230 (var_1 = row variant, var_2 = column
 // variant, ld_triangle.py:193); the counting step is calc_ld.py:30-32 for 128 x N pairs at once:
 //     n11[r][c] = sum_h  a[r][h] * a[c][h],   a[v][h] = (plane[v] & mask) bit h
 // Operand bytes are 0 or a power of two chosen so that every (alt, alt) product is 2^7 (see
-// widen4): the int32 accumulator holds n11 * 128 exactly; the epilogue shifts it back.  The counts equal the popcount engine's bit for bit (tests/test_parity_gpu.py).
+// widen4): the int32 accumulator holds the count * 128 exactly; the epilogue shifts it back.
+//
+// MINOR-ALLELE ENCODING.  The operands are not the alt bits themselves: a variant whose alt allele is the
+// major one under the mask (2 * n1 > N) enters with its bits complemented (under the mask), so that every
+// operand row has at most N/2 bits set.  r2 and |D'| of calc_ld.py:50-90 do not change when an allele is
+// relabelled (D changes sign), and with counts <= N/2 every integer the screening arithmetic of the epilogue
+// needs -- n11' * N, n1a' * n1b', Dn, the D' bound -- is below 2^24 (N <= 5792; one rounding up to N = 8192)
+// and therefore EXACT in single precision: the epilogue runs on FFMA2 / FMUL2 alone, no integer multiply-add
+// chain and no int -> float conversion of Dn (see fast_pair2).  The exact path (finalise_pair, the reference's
+// own operation sequence in fp64) gets the true counts back: true_n11().  Results equal the popcount engine's
+// bit for bit (tests/test_parity_gpu.py).
 //
 // Data movement is designed around the L2: the operands stay BIT-PACKED in global memory/L2
 // (16 B per variant per 128-haplotype chunk, gathered once per call by gather_bits_kernel, O(V))
@@ -15,30 +25,38 @@
 // both the tensor and the fp64 pipe under 14% busy.  Bit-packed operands cut that traffic 8x and
 // keep a 100k-variant operand set (64 MB) resident in the 126 MB L2.
 //
-// Persistent, warp-specialised CTAs (one per SM, 18 warps), each looping over 128 x N tiles of
-// the lower triangle:
+// Persistent, warp-specialised CTAs (one per SM, 28 warps), each looping over 128 x N tiles of
+// the lower triangle(s) -- one launch takes up to MMA_MAX_SETS independent variant sets (ldx_triangle_batch_dev):
 //   warp 0      producer: cp.async.bulk (UBLKCP, the TMA engine's linear mode) brings the tiles'
 //               bit blocks (2 KB per 128 variants per chunk) into an 8-deep shared-memory ring;
 //               completion is counted on mbarriers (complete_tx).  Runs ahead across tiles.
-//   warps 2-9   wideners: each thread turns one variant-row of a chunk (128 bits) into 128 operand
-//               bytes, written straight into the 128-byte-swizzled tile tcgen05 reads (LOP on the
-//               ALU pipe + IMAD on the FMA pipe, one 16-byte STS per 16 haplotypes), then
-//               fence.proxy.async + mbarrier arrive.  3-deep operand ring.
-//   warp 1      MMA issuer: one elected lane issues 4 x tcgen05.mma (K = 32 each) per chunk,
+//               DIRECT mode (one-wave calls on contiguous store rows): no gather kernel at all -- the
+//               producer reads 128-row x 32-byte boxes of the store's planes through a TMA tensor map
+//               (cp.async.bulk.tensor.2d, UTMALDG) and the wideners apply mask, allele flip and bit reversal.
+//   warps 4-19  wideners: each thread turns one variant-row of a stage (256 bits) into operand bytes: the row
+//               operand straight into TENSOR MEMORY (tcgen05.st), the column operand into the 128-byte-swizzled
+//               shared-memory tile tcgen05 reads, then fence.proxy.async + mbarrier arrive.  Four teams, one
+//               operand stage each.
+//   warp 1      MMA issuer: one elected lane issues 8 x tcgen05.mma (K = 32 each) per stage,
 //               tcgen05.commit's the operand stage back to the wideners and, per tile, the TMEM
 //               accumulator to the epilogue; owns the TMEM allocation (2 accumulators of N columns).
-//   warps 10-17 epilogue: tcgen05.ld the int32 counts (lane = row variant, column = column
-//               variant), calc_ld.py:33-97 in fp64 (ldx_common.cuh, branch-free so that the 16
-//               pairs of a chunk interleave), transpose through shared memory and store rows of
-//               packed results coalesced.  Works on accumulator t while the tensor pipe fills t+1.
+//   warps 20-27 epilogue: tcgen05.ld the int32 counts (16 lanes x 256 bits: a lane owns two row variants and
+//               eight column variants per load), screen them in single precision, store the packed words
+//               straight from registers.  Works on accumulator t while the tensor pipe fills t+1.
 //
-// Roofline: int8 tensor pipe, 2 * n_hap int8 ops per pair; co-bounds are the fp64 epilogue
-// (~45 fp64 instructions per pair) and the widening ALU work ((128 + N) rows per 128 * N pairs).
+// Roofline: int8 tensor pipe, 2 * n_hap int8 ops per pair; co-bounds are the epilogue's instruction issue
+// and the widening ALU work ((128 + N) rows per 128 * N pairs).
+#include <cuda.h>
+
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "ldx_internal.h"
 #include "ldx_fixup.cuh"
+
+#define LDX_TRY(expr) do { int rc__ = (expr); if (rc__ != LDX_OK) return rc__; } while (0)
 
 namespace ldx {
 
@@ -107,6 +125,12 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// One box of a 2-D tensor map (direct mode: 128 store rows x 32 bytes of their planes) -> dense shared-memory tile.
+// Rows beyond the tensor are zero-filled and still count towards complete_tx.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, int32_t x, int32_t y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(x), "r"(y) : "memory");
 }
 // One lane of a fully converged warp; the surrounding control flow stays warp-uniform so that the
 // compiler keeps descriptors/addresses in uniform registers (issuing tcgen05/bulk-copy instructions
@@ -218,36 +242,48 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 }
 
 // ------------------------------------------------------------------------------------------ gather
-// Store rows (gathered through rows[], masked) -> chunk-blocked bit panels:
+// Store rows (gathered through rows[], masked, minor-allele encoded) -> chunk-blocked bit panels:
 //   bits[panel][chunk][row 0..127][16 B],  panel = matrix_row / 128,  chunk = haplotype / 128
 // so that the 128 rows of one pipeline stage are ONE contiguous 2 KB block (one bulk copy).
-// A second copy with each byte bit-reversed feeds the column operand.
+// A second copy with each byte bit-reversed feeds the column operand.  The variant sets of a launch sit one after
+// the other in this row space, each padded to whole 256-row panels: matrix row r of set k is global row base_row + r.
+struct GatherSet {
+    const uint64_t *planes, *mask; const VarFreq *freq; const int64_t *rows;
+    int64_t v, v_pad, base_row; int32_t stride_words, n_sel;
+};
+struct GatherArgs {
+    GatherSet set[MMA_MAX_SETS];
+    int32_t kc_count; uint4 *bits, *bits_rev; VarFreq *freq_rows;
+};
+
+__device__ __forceinline__ uint32_t brev_bytes(uint32_t x) { return __byte_perm(__brev(x), 0, 0x0123); }   // every BYTE bit-reversed
+
 __global__ void __launch_bounds__(256)
-gather_bits_kernel(const uint64_t *__restrict__ planes, const uint64_t *__restrict__ mask, int32_t stride_words,
-                   const int64_t *__restrict__ rows, int64_t v, int64_t v_pad, int32_t kc_count,
-                   const VarFreq *__restrict__ freq, uint4 *__restrict__ bits, uint4 *__restrict__ bits_rev,
-                   VarFreq *__restrict__ freq_rows) {
+gather_bits_kernel(const __grid_constant__ GatherArgs G) {
     pdl_launch_dependents();                                            // the all-pairs kernel may start its prologue
     pdl_wait();                                                         // the scratch is still read by the previous call's kernels
+    const GatherSet &S = G.set[blockIdx.z];
     const int kc = blockIdx.y;
-    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;          // matrix row
-    if (r >= v_pad) return;
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;          // matrix row of this set
+    if (r >= S.v_pad) return;
+    const int64_t gr = S.base_row + r;                                  // row in the launch's row space
     uint4 out = make_uint4(0, 0, 0, 0);
-    if (r < v) {
-        const int64_t srow = rows[r];
-        const uint4 x = __ldg(reinterpret_cast<const uint4 *>(planes + srow * stride_words) + kc);
-        const uint4 m = __ldg(reinterpret_cast<const uint4 *>(mask) + kc);
-        out = make_uint4(x.x & m.x, x.y & m.y, x.z & m.z, x.w & m.w);
-        if (kc == 0) freq_rows[r] = freq[srow];
+    if (r < S.v) {
+        const int64_t srow = S.rows[r];
+        const uint4 x = __ldg(reinterpret_cast<const uint4 *>(S.planes + srow * S.stride_words) + kc);
+        const uint4 m = __ldg(reinterpret_cast<const uint4 *>(S.mask) + kc);
+        const VarFreq f = S.freq[srow];
+        const uint32_t flip = 2 * f.n1 > S.n_sel ? 0xffffffffu : 0u;    // alt is the major allele: operand = ref bits
+        out = make_uint4((x.x ^ flip) & m.x, (x.y ^ flip) & m.y, (x.z ^ flip) & m.z, (x.w ^ flip) & m.w);
+        if (kc == 0) G.freq_rows[gr] = f;                               // the TRUE counts: true_n11() undoes the flip
     } else if (kc == 0) {
         VarFreq z; z.p = 0.0; z.q = 0.0; z.pq = 0.0; z.n1 = 0; z.p_e4 = 0;
-        freq_rows[r] = z;
+        G.freq_rows[gr] = z;
     }
-    const int64_t o = ((r >> 7) * kc_count + kc) * 128 + (r & 127);
-    bits[o] = out;
+    const int64_t o = ((gr >> 7) * G.kc_count + kc) * 128 + (gr & 127);
+    G.bits[o] = out;
     // the same bits with every BYTE bit-reversed: the column operand's source (see widen_row)
-    bits_rev[o] = make_uint4(__byte_perm(__brev(out.x), 0, 0x0123), __byte_perm(__brev(out.y), 0, 0x0123),
-                             __byte_perm(__brev(out.z), 0, 0x0123), __byte_perm(__brev(out.w), 0, 0x0123));
+    G.bits_rev[o] = make_uint4(brev_bytes(out.x), brev_bytes(out.y), brev_bytes(out.z), brev_bytes(out.w));
 }
 
 // ------------------------------------------------------------------------------------------ widen
@@ -287,56 +323,73 @@ constexpr int ACC_SHIFT = 7;   // 2^p * 2^(7-p) = 2^7 per (alt, alt) haplotype
 
 // ------------------------------------------------------------------------------------------ screening arithmetic
 // The epilogue's fast path.  With complete biallelic data every quantity of calc_ld.py:33-90 is a
-// ratio of small integers:
-//     Dn = n11*N - n1a*n1b                  d  = Dn / N^2                       (calc_ld.py:50)
-//     m  = Dn > 0 ? min(n1a*n0b, n0a*n1b)   D' = |Dn| / m                       (calc_ld.py:63-76)
-//                 : min(n1a*n1b, n0a*n0b)
-//     den = n1a*n0a*n1b*n0b                 r2 = Dn^2 / den                     (calc_ld.py:86-88)
-// Dn and m are formed exactly in int32 (N <= 8192: |Dn| <= 2^26, m <= 2^24).  x = value * 10^4 is
-// then evaluated in SINGLE precision -- the epilogue is bound by instruction issue, and an fp32
-// chain is half the instructions of an fp64 one -- with a relative error below SCREEN_C_* * 2^-24:
-//     fD = RN(|Dn|) (1 rounding), fm = m and n1a*n0a, n1b*n0b exact (<= 2^24),
-//     x_dp = (fD * 1e4) * rcp(fm)                : 3 roundings + rcp.approx (<= 2^-23)  -> 6 u
-//     x_r2 = ((fD * 1e4) * fD) * rcp(da * dc)    : 6 roundings + rcp.approx            -> 9 u
+// ratio of small integers.  In the minor-allele encoding (a' = min(n1a, N - n1a) <= N/2, likewise c',
+// n11' = the accumulator's count; relabelling an allele leaves r2 and |D'| unchanged):
+//     Dn = n11'*N - a'*c'                     |d| = |Dn| / N^2                    (calc_ld.py:50)
+//     m  = Dn > 0 ? N*min(a', c') - a'*c'     D'  = |Dn| / m                      (calc_ld.py:63-76)
+//                 : a'*c'                          [min(a'c', a0'c0') = a'c' because a0' >= a', c0' >= c']
+//     den = (a'*a0') * (c'*c0')               r2  = Dn^2 / den                    (calc_ld.py:86-88)
+// a'*c' <= N^2/4, n11'*N <= N^2/2, a'*a0' <= N^2/4: for N <= 5792 every one of these integers is below 2^24 and the
+// single-precision FMAs that form them are EXACT; up to N = 8192 Dn and the positive bound may be rounded once
+// (an FMA rounds the exact value), which the error budget below already carries.  x = value * 10^4:
+//     fD = fma(n11', N, -a'c')                      exact, or 1 rounding (sign and zero test always exact)
+//     x_dp = (fD * 1e4) * rcp(m)                    : fD 1 + mul 1 + m 1 + rcp.approx 2 + mul 1 = 6 u, u = 2^-24
+//     x_r2 = ((fD * 1e4) * ra) * (fD * rc)          : (2 + 2 + 1) + (1 + 2 + 1) + 1 = 10 u, ra = rcp(a'a0'), rc = rcp(c'c0')
 // The reference rounds ITS OWN fp64 chain, whose distance from the exact ratio is bounded by the
 // cancellation in f11 - p1*p2: |x_ref - x_exact| <= 10^4 * 16 * 2^-53 * N^2 for r2 (half of that for
 // D').  Whenever x is farther than both bounds together (+1e-5) from every k + 1/2, Python's
 // round(x_ref, 4) and the rounding of x agree, and the packed word is final.  Otherwise -- and when
 // Dn == 0 for two polymorphic variants, where only the reference's own rounding errors decide
 // between int 0 and 0.0 -- `slow` is set and the pair is redone with the reference's operation
-// sequence in fp64 (finalise_pair, slow_pairs_kernel): about 1% of the pairs.
+// sequence in fp64 on the TRUE counts (finalise_pair, slow_pairs_kernel): about 1% of the pairs.
 // Monomorphic variants (den == 0) need no arithmetic: d is exactly 0 and the bound is exactly 0 in
 // the reference as well (calc_ld.py:68-69, :89-90): both int-0 flags.
 constexpr float SCREEN_U = 5.9604644775390625e-08f;      // 2^-24
-constexpr float SCREEN_C_DP = 7.0f * SCREEN_U;            // 6 u proven + 1 u slack
-constexpr float SCREEN_C_R2 = 10.0f * SCREEN_U;           // 9 u proven + 1 u slack
+constexpr float SCREEN_C_DP = 8.0f * SCREEN_U;            // 6 u proven + 2 u slack
+constexpr float SCREEN_C_R2 = 12.0f * SCREEN_U;           // 10 u proven + 2 u slack
 constexpr float ROUND_MAGIC = 12582912.0f;                // 1.5 * 2^23: x + MAGIC has ulp 1 for 0 <= x < 2^22
 __device__ __forceinline__ float rcp_approx(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// The (alt, alt) count of the TRUE alleles from the count n11p of the minor-allele operands (a_t, b_t: true alt counts):
+// a flipped row contributes its ref haplotypes, so  |~a & b| = b_t - n11,  |a & ~b| = a_t - n11,  |~a & ~b| = N - a_t - b_t + n11.
+__device__ __forceinline__ int32_t true_n11(int32_t n11p, int32_t a_t, int32_t b_t, int32_t N) {
+    const bool fa = 2 * a_t > N, fb = 2 * b_t > N;
+    return fa ? (fb ? n11p - N + a_t + b_t : b_t - n11p) : (fb ? a_t - n11p : n11p);
+}
 // ------------------------------------------------------------------------------------------ GEMM + epilogue
+// One variant set of a launch: its place in the launch's row space and its outputs.
+struct SetRec {
+    int64_t base_row;            // first row of the set in bits / freq_rows (a multiple of 256)
+    int64_t v;                   // variants
+    int64_t out_off;             // packed index of the first pair of the call's row range: outputs are relative to it
+    uint32_t *packed; int32_t *n11;
+    uint64_t fix_tag;            // ORed into the out_index of the set's near-tie records (FIX_TAG_SHIFT)
+};
 struct MmaArgs {
     const uint4 *bits, *bits_rev; int32_t kc_count;
     const VarFreq *freq_rows; FinalCtx fc;
-    const int2 *tiles; int32_t n_tiles;
-    int64_t v; int measure, has_thres, thres_e4;
-    int64_t out_off;             // packed index of the first pair of the call's row range: outputs are relative to it
+    const int4 *tiles; int32_t n_tiles;      // {row panel, column block (both in the launch's row space), set, -}
+    int measure, has_thres, thres_e4;
     int32_t n_sel;               // N = selected haplotypes
     float lim_dp, lim_r2;        // 0.5 - guard band of the screening arithmetic at x = 0 (see fast_pair2)
-    uint4 *slow; uint32_t *slow_count; uint32_t slow_cap;   // deferred pairs {row, col, n11, -} for slow_pairs_kernel
+    uint4 *slow; uint32_t *slow_count; uint32_t slow_cap;   // deferred pairs {row, col, n11', set} for slow_pairs_kernel
     // single-wave calls (at most one tile per CTA): no follow-up kernel -- every epilogue warp settles its own deferred
     // pairs and the last CTA publishes the completion record (counters = d_fix_count, see slow_pairs_kernel)
     int inline_settle; uint32_t *counters; volatile uint32_t *mailbox; uint32_t seq;
     uint32_t pool_cap;           // single-wave calls: capacity of the CTA-wide list (tests shrink it to force the overflow paths)
     int help;                    // single-wave calls: the wideners, idle once the K loop is done, take half of the epilogue
-    uint32_t *packed; int32_t *n11;
     FixupSink fix;
     int32_t *error_flag;
     unsigned long long *trace;   // optional [512]: globaltimer stamps of CTA 0 (diagnostics)
     int dbg;                     // diagnostics build only (LDX_DEBUG_MMA; results invalid): 1 skip row-operand widening,
                                  // 2 skip column-operand widening, 4 skip the epilogue arithmetic, 8 skip the MMAs
+    // direct mode: the planes of the store itself through a TMA tensor map; matrix row r = store row row0 + r
+    const uint4 *mask; int32_t row0;
+    alignas(64) CUtensorMap tmap;
+    SetRec set[MMA_MAX_SETS];    // single-wave kernels work on set[0]
 };
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) :: "memory"); return t; }
@@ -361,13 +414,27 @@ static_assert(MMA_THREADS * REGS_LAUNCH <= 65536, "register file");
 constexpr int SLOW_BUF = 64;                                           // deferred pairs buffered per epilogue warp
 constexpr int EPI_PITCH = 16;                                          // words per parked row (rare path: bank conflicts do not matter)
 
-// Per column variant, what the screening arithmetic of the epilogue needs (one 16-byte broadcast load per pair).
-struct __align__(16) ColRec {
-    float prod;      // n1 * (N - n1), exact (<= 2^24)
-    int32_t n1;      // alt alleles under the mask
-    int32_t n1N;     // n1 * N
-    int32_t pad;
+// Per PAIR of neighbouring column variants (2j, 2j + 1), what the screening arithmetic of the epilogue needs, laid out as
+// the packed f32x2 operands fast_pair2 uses: one 16-byte load per two pairs and no register shuffling.
+struct __align__(16) ColPair {
+    float n1f[2];    // c' = min(n1, N - n1): the minor-allele counts, exact
+    float rc[2];     // rcp.approx(c' * (N - c')); +inf for a monomorphic variant
 };
+__device__ __forceinline__ float minor_f(int32_t n1t, int32_t Nn) { return __int2float_rn(min(n1t, Nn - n1t)); }
+__device__ __forceinline__ float rcp_nn(int32_t n1t, int32_t Nn) {         // 1 / (c' * c0'): the product is exact (<= 2^24)
+    const int32_t c = min(n1t, Nn - n1t);
+    return rcp_approx(__int2float_rn(c * (Nn - c)));
+}
+// The same per row variant of an epilogue lane, packed once per pass.
+struct RowP { uint64_t na2, ra2; float n1f; };    // {-a', -a'}, {ra, ra}, a'
+__device__ __forceinline__ RowP make_rowp(int32_t n1t, int32_t Nn) {
+    RowP p;
+    p.n1f = minor_f(n1t, Nn);
+    const float ra = rcp_nn(n1t, Nn);
+    asm("mov.b64 %0, {%1, %1};" : "=l"(p.na2) : "f"(-p.n1f));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(p.ra2) : "f"(ra));
+    return p;
+}
 
 // PAIR: two CTAs of a cluster work on one 256 x N tile with tcgen05.mma.cta_group::2; each widens its own 128
 // row variants (TMEM) and HALF of the column variants (N/2 rows of the shared-memory operand, which the
@@ -390,7 +457,7 @@ template <int N, bool PAIR = false> struct MmaCfg {
     static constexpr int N_BARS = 2 * OP_STAGES + 2 * BIT_STAGES + 4;
     static constexpr int EPI_BYTES = N_EPI_WARPS * (32 * EPI_PITCH * 4 + SLOW_BUF * 16);   // staging + deferred-pair buffer per warp
     static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)OP_STAGES * OP_BYTES + (size_t)BIT_STAGES * BIT_BYTES +
-                                   N_EPI_WARPS * (N / 2) * sizeof(ColRec) + EPI_BYTES + N_BARS * 8 + 64;
+                                   N_EPI_WARPS * (N / 4) * sizeof(ColPair) + EPI_BYTES + N_BARS * 8 + 64;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static_assert(!PAIR || (N == 128 && CH == 2), "the pair kernel splits the column widening as 64 rows x 2 chunks");
 };
@@ -404,46 +471,66 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; a
 __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
-// Pairs (row, column j) and (row, column j + 1): the screening arithmetic described above.  The bound m carries the
-// sign of Dn (m = -min(n1a*n1b, n0a*n0b) for Dn <= 0), so that Dn / m is |D'| without an absolute value --
-// the packed instructions have no operand modifiers.
+// What fast_pair2 needs about the call, packed for the f32x2 instructions once per warp.
+struct ScreenK {
+    uint64_t Ns2;        // {N / 128, N / 128}: the accumulator holds n11' * 128 (exactly representable: a power-of-two scale)
+    uint64_t N2;         // {N, N}
+    float lim_dp, lim_r2;
+    uint32_t m_shift, thres;
+};
+__device__ __forceinline__ ScreenK make_screen(const MmaArgs &A) {
+    ScreenK K;
+    K.m_shift = A.measure == LDX_MEASURE_R2 ? 0u : (uint32_t)LDX_DP_SHIFT;
+    K.thres = A.has_thres ? (uint32_t)A.thres_e4 : 0u;      // rounded values are >= 0: 0 flags nothing
+    const float nf = __int2float_rn(A.n_sel);
+    K.Ns2 = pk2(nf * 0.0078125f, nf * 0.0078125f); K.N2 = pk2(nf, nf);
+    K.lim_dp = A.lim_dp; K.lim_r2 = A.lim_r2;
+    return K;
+}
+
+// Pairs (row, column 2j) and (row, column 2j + 1): the screening arithmetic described above.  The bound m carries the
+// sign of Dn (m = -a'c' for Dn <= 0), so that Dn / m is |D'| without an absolute value -- the packed instructions have no
+// operand modifiers.  A monomorphic variant shows as ra * rc = +inf (rcp.approx(0) = +inf; the product of two finite
+// reciprocals is at most 1).
 template <bool THRES>
-__device__ __forceinline__ void fast_pair2(uint32_t acc0, uint32_t acc1, int32_t Nn, int32_t n1a, int32_t aN, int32_t cN, float fa,
-                                           const ColRec &c0, const ColRec &c1, float lim_dp, float lim_r2, uint32_t m_shift,
-                                           uint32_t thres, uint32_t &w0, uint32_t &w1, bool &slow0, bool &slow1) {
-    const int32_t P0 = n1a * c0.n1, P1 = n1a * c1.n1;
-    const int32_t Dn0 = (int32_t)(acc0 >> ACC_SHIFT) * Nn - P0, Dn1 = (int32_t)(acc1 >> ACC_SHIFT) * Nn - P1;
-    const int32_t mp0 = min(aN, c0.n1N) - P0, mp1 = min(aN, c1.n1N) - P1;            //  min(n1a*n0b, n0a*n1b)
-    const int32_t mn0 = max(0, c0.n1N - cN) - P0, mn1 = max(0, c1.n1N - cN) - P1;    // -min(n1a*n1b, n0a*n0b)
-    const int32_t m0 = Dn0 > 0 ? mp0 : mn0, m1 = Dn1 > 0 ? mp1 : mn1;
-    const uint64_t fD = pk2(__int2float_rn(Dn0), __int2float_rn(Dn1));
-    const uint64_t den = mul2(pk2(fa, fa), pk2(c0.prod, c1.prod));
-    float den0, den1;
-    upk2(den, den0, den1);
-    const uint64_t R1 = pk2(rcp_approx(__int2float_rn(m0)), rcp_approx(__int2float_rn(m1)));    // m is exact in fp32
-    const uint64_t R2 = pk2(rcp_approx(den0), rcp_approx(den1));                                  // inf when monomorphic: masked below
+__device__ __forceinline__ void fast_pair2(uint32_t acc0, uint32_t acc1, const ScreenK &K, const RowP &R, const ColPair &C,
+                                           uint32_t &w0, uint32_t &w1, bool &slow0, bool &slow1) {
+    const uint64_t cn = pk2(C.n1f[0], C.n1f[1]);
+    const uint64_t accf = pk2(__int2float_rn((int32_t)acc0), __int2float_rn((int32_t)acc1));   // n11' * 128 <= 2^19: exact
+    const uint64_t nP = mul2(R.na2, cn);                                            // -a'c': exact (<= 2^24)
+    const uint64_t fD = fma2(accf, K.Ns2, nP);                                     // Dn = n11'*N - a'c'
+    const uint64_t mp = fma2(K.N2, pk2(fminf(R.n1f, C.n1f[0]), fminf(R.n1f, C.n1f[1])), nP);   // N*min(a', c') - a'c' > 0
+    float d0, d1, mp0, mp1, np0, np1;
+    upk2(fD, d0, d1); upk2(mp, mp0, mp1); upk2(nP, np0, np1);
+    const uint64_t R1 = pk2(rcp_approx(d0 > 0.0f ? mp0 : np0), rcp_approx(d1 > 0.0f ? mp1 : np1));
+    const uint64_t rinv = mul2(R.ra2, pk2(C.rc[0], C.rc[1]));                     // 1 / den; +inf <=> a monomorphic variant
     const uint64_t D4 = mul2(fD, pk2(1.0e4f, 1.0e4f));
     const uint64_t x_dp = mul2(D4, R1);
-    const uint64_t x_r2 = mul2(mul2(D4, fD), R2);
+    const uint64_t x_r2 = mul2(mul2(D4, fD), rinv);
     const uint64_t magic = pk2(ROUND_MAGIC, ROUND_MAGIC), nmagic = pk2(-ROUND_MAGIC, -ROUND_MAGIC), neg1 = pk2(-1.0f, -1.0f);
     const uint64_t t_dp = add2(x_dp, magic), t_r2 = add2(x_r2, magic);
     const uint64_t f_dp = fma2(add2(t_dp, nmagic), neg1, x_dp);          // exact: x - nearest integer
     const uint64_t f_r2 = fma2(add2(t_r2, nmagic), neg1, x_r2);
-    const uint64_t l_dp = fma2(x_dp, pk2(-SCREEN_C_DP, -SCREEN_C_DP), pk2(lim_dp, lim_dp));   // guard band grows with x
-    const uint64_t l_r2 = fma2(x_r2, pk2(-SCREEN_C_R2, -SCREEN_C_R2), pk2(lim_r2, lim_r2));
-    float td0, td1, tr0, tr1, fd0, fd1, fr0, fr1, ld0, ld1, lr0, lr1;
+    const uint64_t l_dp = fma2(x_dp, pk2(-SCREEN_C_DP, -SCREEN_C_DP), pk2(K.lim_dp, K.lim_dp));   // guard band grows with x
+    const uint64_t l_r2 = fma2(x_r2, pk2(-SCREEN_C_R2, -SCREEN_C_R2), pk2(K.lim_r2, K.lim_r2));
+    float td0, td1, tr0, tr1, fd0, fd1, fr0, fr1, ld0, ld1, lr0, lr1, ri0, ri1;
     upk2(t_dp, td0, td1); upk2(t_r2, tr0, tr1); upk2(f_dp, fd0, fd1); upk2(f_r2, fr0, fr1); upk2(l_dp, ld0, ld1); upk2(l_r2, lr0, lr1);
-    const bool mono0 = den0 == 0.0f, mono1 = den1 == 0.0f;
-    // !(<=) rather than (>): a NaN from an unforeseen input must fall to the exact path, never pass
-    slow0 = (bool)((uint32_t)!mono0 & ((uint32_t)!(fabsf(fd0) <= ld0) | (uint32_t)!(fabsf(fr0) <= lr0) | (uint32_t)(Dn0 == 0)));
-    slow1 = (bool)((uint32_t)!mono1 & ((uint32_t)!(fabsf(fd1) <= ld1) | (uint32_t)!(fabsf(fr1) <= lr1) | (uint32_t)(Dn1 == 0)));
-    uint32_t a = (uint32_t)__float_as_int(td0) * 65536u + ((uint32_t)__float_as_int(tr0) - 0x4B400000u);
-    uint32_t b = (uint32_t)__float_as_int(td1) * 65536u + ((uint32_t)__float_as_int(tr1) - 0x4B400000u);
+    upk2(rinv, ri0, ri1);
+    const float inf = __int_as_float(0x7f800000);
+    const bool mono0 = ri0 == inf, mono1 = ri1 == inf;
+    // (<=) with everything else falling through: a NaN from an unforeseen input must take the exact path, never pass
+    const bool fine0 = (fabsf(fd0) <= ld0) && (fabsf(fr0) <= lr0) && (d0 != 0.0f);
+    const bool fine1 = (fabsf(fd1) <= ld1) && (fabsf(fr1) <= lr1) && (d1 != 0.0f);
+    slow0 = !(fine0 || mono0);
+    slow1 = !(fine1 || mono1);
+    // x + MAGIC has the rounded integer k (< 2^14) in its low mantissa bits: word = k_dp << 16 | k_r2 is one byte permute
+    uint32_t a = __byte_perm((uint32_t)__float_as_int(tr0), (uint32_t)__float_as_int(td0), 0x5410);
+    uint32_t b = __byte_perm((uint32_t)__float_as_int(tr1), (uint32_t)__float_as_int(td1), 0x5410);
     a = mono0 ? (LDX_DP_INT0 | LDX_R2_INT0) : a;
     b = mono1 ? (LDX_DP_INT0 | LDX_R2_INT0) : b;
     if (THRES) {
-        a |= (((a >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;
-        b |= (((b >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;
+        a |= (((a >> K.m_shift) & LDX_R2_MASK) < K.thres) ? LDX_BELOW_THRES : 0u;
+        b |= (((b >> K.m_shift) & LDX_R2_MASK) < K.thres) ? LDX_BELOW_THRES : 0u;
     }
     w0 = a; w1 = b;
 }
@@ -452,18 +539,23 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 
-// One deferred pair {row, col, n11, -} redone with the reference's own operation sequence (finalise_pair).
-__device__ __forceinline__ void settle_slow_pair(const uint4 e, const VarFreq *__restrict__ freq_rows, const FinalCtx &fc,
-                                                 uint32_t m_shift, uint32_t thres, uint32_t *__restrict__ packed, int64_t out_off,
-                                                 const FixupSink &fix) {
+// One deferred pair {row, col, n11', set} (row / col relative to the set) redone with the reference's own operation
+// sequence (finalise_pair) on the true counts.
+__device__ __forceinline__ void settle_slow_pair(const uint4 e, const MmaArgs &A, uint32_t m_shift, uint32_t thres) {
+    const SetRec &S = A.set[e.w];
     const int64_t r = e.x, col = e.y;
-    const VarFreq fa = freq_rows[r], fb = freq_rows[col];
-    const PairFinal f = finalise_pair((int32_t)e.z, fa, fb, fc);       // var_1 = row, var_2 = column
+    const VarFreq fa = A.freq_rows[S.base_row + r], fb = A.freq_rows[S.base_row + col];
+    const int32_t n11 = true_n11((int32_t)e.z, fa.n1, fb.n1, A.n_sel);
+    const PairFinal f = finalise_pair(n11, fa, fb, A.fc);              // var_1 = row, var_2 = column
     uint32_t w = f.packed;
     w |= (((w >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;
-    const uint64_t idx = (uint64_t)(r * (r - 1) / 2 + col - out_off);
-    if (w & LDX_R2_NEARTIE) fixup_append(fix, idx, (int32_t)e.z, fa.n1, fb.n1, w);
-    packed[idx] = w;
+    const uint64_t idx = (uint64_t)(r * (r - 1) / 2 + col - S.out_off);
+    if (w & LDX_R2_NEARTIE) {
+        FixupSink fx = A.fix;
+        fx.tag = S.fix_tag;
+        fixup_append(fx, idx, n11, fa.n1, fb.n1, w);
+    }
+    S.packed[idx] = w;
 }
 
 // Warp-collective: move a warp's buffered deferred pairs to the global list.  Returns the new count (0).
@@ -476,7 +568,7 @@ __device__ __forceinline__ uint32_t flush_slow(const MmaArgs &A, const uint4 *sb
     if (cnt == 0) return 0;
     __syncwarp();
     if (SINGLE) {          // warp-uniform: one deferred pair per lane, right here
-        for (uint32_t i = lane; i < cnt; i += 32) settle_slow_pair(sbuf[i], A.freq_rows, A.fc, m_shift, thres, A.packed, A.out_off, A.fix);
+        for (uint32_t i = lane; i < cnt; i += 32) settle_slow_pair(sbuf[i], A, m_shift, thres);
         __syncwarp();
         return 0;
     }
@@ -485,7 +577,7 @@ __device__ __forceinline__ uint32_t flush_slow(const MmaArgs &A, const uint4 *sb
     base = __shfl_sync(0xffffffffu, base, 0);
     for (uint32_t i = lane; i < cnt; i += 32) {
         if (base + i < A.slow_cap) A.slow[base + i] = sbuf[i];
-        else settle_slow_pair(sbuf[i], A.freq_rows, A.fc, m_shift, thres, A.packed, A.out_off, A.fix);
+        else settle_slow_pair(sbuf[i], A, m_shift, thres);
     }
     __syncwarp();
     return 0;
@@ -495,17 +587,16 @@ __device__ __forceinline__ uint32_t flush_slow(const MmaArgs &A, const uint4 *sb
 // block to finish publishes the call's completion record (near-tie count, error flag, sequence number)
 // to the host mailbox.
 __global__ void __launch_bounds__(256)
-slow_pairs_kernel(const uint4 *__restrict__ list, uint32_t *__restrict__ counters /* d_fix_count */, uint32_t cap,
-                  const VarFreq *__restrict__ freq_rows, FinalCtx fc, int measure, int has_thres, int thres_e4,
-                  uint32_t *__restrict__ packed, int64_t out_off, FixupSink fix, volatile uint32_t *mailbox, uint32_t seq) {
+slow_pairs_kernel(const __grid_constant__ MmaArgs A) {
     pdl_launch_dependents();
     pdl_wait();                                                 // everything below depends on the all-pairs kernel
+    uint32_t *counters = A.counters;
     const uint32_t total = counters[2];
-    const uint32_t n = total < cap ? total : cap;              // the rest was settled in the epilogue (flush_slow)
-    const uint32_t m_shift = measure == LDX_MEASURE_R2 ? 0u : (uint32_t)LDX_DP_SHIFT;
-    const uint32_t thres = has_thres ? (uint32_t)thres_e4 : 0u;
+    const uint32_t n = total < A.slow_cap ? total : A.slow_cap;    // the rest was settled in the epilogue (flush_slow)
+    const uint32_t m_shift = A.measure == LDX_MEASURE_R2 ? 0u : (uint32_t)LDX_DP_SHIFT;
+    const uint32_t thres = A.has_thres ? (uint32_t)A.thres_e4 : 0u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        settle_slow_pair(list[i], freq_rows, fc, m_shift, thres, packed, out_off, fix);
+        settle_slow_pair(A.slow[i], A, m_shift, thres);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -514,7 +605,7 @@ slow_pairs_kernel(const uint4 *__restrict__ list, uint32_t *__restrict__ counter
             __threadfence();
             counters[3] = 0;
             counters[2] = 0;
-            if (mailbox) publish_record(mailbox, seq, *(volatile uint32_t *)&counters[0], *(volatile uint32_t *)&counters[1]);
+            if (A.mailbox) publish_record(A.mailbox, A.seq, *(volatile uint32_t *)&counters[0], *(volatile uint32_t *)&counters[1]);
         }
     }
 }
@@ -522,10 +613,13 @@ slow_pairs_kernel(const uint4 *__restrict__ list, uint32_t *__restrict__ counter
 // SINGLE: the call is one wave of tiles (every CTA has exactly one): deferred pairs are settled in this kernel, the last CTA
 // publishes the completion record, and the wideners share the epilogue.  The multi-wave instantiation carries none of that
 // code: its hot loops are sensitive to every change in register allocation and code layout.
-template <int N, bool WANT_N11, bool THRES, bool TRACE, bool PAIR, bool SINGLE>
+// DIRECT (single-wave, one CTA per 128 x 128 tile only): no gather kernel ran; the producer reads the store's planes through
+// the tensor map in A.tmap and the wideners apply mask, minor-allele flip and the column operand's bit reversal.
+template <int N, bool THRES, bool TRACE, bool PAIR, bool SINGLE, bool DIRECT>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
-triangle_mma_kernel(const MmaArgs A) {
+triangle_mma_kernel(const __grid_constant__ MmaArgs A) {
     using Cfg = MmaCfg<N, PAIR>;
+    static_assert(!DIRECT || (SINGLE && !PAIR && N == 128), "direct mode: one CTA per 128 x 128 tile of a one-wave call");
     // work units: a CTA (tile = 128 x N), or a CTA pair (tile = 256 x N, this CTA owns rows 128 * rank ...)
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -535,8 +629,8 @@ triangle_mma_kernel(const MmaArgs A) {
     uint8_t *smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);      // swizzle-128B needs 1 KB alignment
     uint8_t *op_s = smem;                                                        // [OP_STAGES][N][128 B] column operand
     uint8_t *bit_s = smem + Cfg::OP_STAGES * Cfg::OP_BYTES;                      // [BIT_STAGES][ROWS][16 B]
-    ColRec *col_s = reinterpret_cast<ColRec *>(bit_s + Cfg::BIT_STAGES * Cfg::BIT_BYTES);   // [N_EPI_WARPS][N / 2]: private to each epilogue warp
-    uint32_t *epi_s = reinterpret_cast<uint32_t *>(col_s + N_EPI_WARPS * (N / 2));  // [N_EPI_WARPS][32][EPI_PITCH]
+    ColPair *col_s = reinterpret_cast<ColPair *>(bit_s + Cfg::BIT_STAGES * Cfg::BIT_BYTES);   // [N_EPI_WARPS][N / 4]: private to each epilogue warp
+    uint32_t *epi_s = reinterpret_cast<uint32_t *>(col_s + N_EPI_WARPS * (N / 4));  // [N_EPI_WARPS][32][EPI_PITCH]
     uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(epi_s) + Cfg::EPI_BYTES);
     const uint32_t op_full = smem_u32(bars), op_empty = op_full + 8 * Cfg::OP_STAGES;
     const uint32_t bit_full = op_empty + 8 * Cfg::OP_STAGES, bit_empty = bit_full + 8 * Cfg::BIT_STAGES;
@@ -566,6 +660,7 @@ triangle_mma_kernel(const MmaArgs A) {
         *abort_s = 0;
         if (SINGLE) *pool_cnt = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (DIRECT) asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&A.tmap)) : "memory");
     }
     if (warp == 1) {   // one warp allocates TMEM (power-of-two columns >= 32) and later frees it
         if (PAIR) {
@@ -585,7 +680,7 @@ triangle_mma_kernel(const MmaArgs A) {
     const uint32_t tmem_base = *tmem_ptr_s;
     // the tile list is uploaded by the host (and cached), not written by the preceding kernel: the first tile's
     // coordinates can be fetched while that kernel is still running
-    const int2 first_tile = SINGLE && unit < A.n_tiles ? A.tiles[unit] : make_int2(0, 0);
+    const int4 first_tile = SINGLE && unit < A.n_tiles ? A.tiles[unit] : make_int4(0, 0, 0, 0);
     if (SINGLE && threadIdx.x == 32) {
         // the near-tie list is touched by a handful of pairs per call: without this the first of them pays a DRAM
         // round trip for the counter and one for the record on the kernel's critical path
@@ -605,7 +700,7 @@ triangle_mma_kernel(const MmaArgs A) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         uint32_t g = 0;
         for (int t = unit; t < A.n_tiles; t += n_units) {
-            const int2 tile = SINGLE ? first_tile : A.tiles[t];
+            const int4 tile = SINGLE ? first_tile : A.tiles[t];
             const int64_t c0 = (int64_t)tile.y * N + (PAIR ? rank * Cfg::NB : 0);      // pair: this CTA's half of the columns
             const uint4 *a_src = A.bits + (int64_t)(PAIR ? tile.x * 2 + rank : tile.x) * kc_count * 128;
             for (int ks = 0; ks < ks_count; ++ks, ++g) {
@@ -617,6 +712,11 @@ triangle_mma_kernel(const MmaArgs A) {
                 if (elect_one()) {
                     if (TRACE && A.trace && blockIdx.x == 0 && g < 48) A.trace[128 + g] = gtime();
                     mbar_arrive_expect_tx(bar, Cfg::BIT_BYTES);
+                    if (DIRECT) {
+                        // [128 rows][32 B] of the row variants, then of the column variants, straight from the store
+                        tma_load_2d(dst, &A.tmap, kc * 4, A.row0 + tile.x * MMA_M, bar);
+                        tma_load_2d(dst + MMA_M * 16 * Cfg::CH, &A.tmap, kc * 4, A.row0 + (int32_t)c0, bar);
+                    } else {
                     bulk_g2s(dst, a_src + (int64_t)kc * 128, Cfg::CH * MMA_M * 16, bar);       // [CH][128] rows
 #pragma unroll
                     for (int part = 0; part < Cfg::B_PARTS; ++part) {
@@ -629,6 +729,7 @@ triangle_mma_kernel(const MmaArgs A) {
 #pragma unroll
                             for (int c = 0; c < Cfg::CH; ++c) bulk_g2s(b_dst + c * Cfg::B_ROWS * 16, b_src + c * 128, Cfg::B_ROWS * 16, bar);
                         }
+                    }
                     }
                 }
                 __syncwarp();
@@ -691,16 +792,34 @@ triangle_mma_kernel(const MmaArgs A) {
         const uint32_t g_end = my_tiles * (uint32_t)ks_count;
         static_assert(Cfg::OP_STAGES == WIDEN_TEAMS, "one operand stage per team");
         bool dead = false;            // single-wave kernel: an aborted warp still meets the others at the settlement barrier
+        // direct mode: this thread's row and column variant enter complemented when their alt allele is the major one
+        uint32_t flip_a = 0, flip_b = 0;
+        if (DIRECT && my_tiles) {
+            flip_a = 2 * A.freq_rows[(int64_t)first_tile.x * MMA_M + wt].n1 > A.n_sel ? 0xffffffffu : 0u;
+            flip_b = 2 * A.freq_rows[(int64_t)first_tile.y * N + wt].n1 > A.n_sel ? 0xffffffffu : 0u;
+        }
         {
             for (uint32_t g = (uint32_t)team; g < g_end; g += WIDEN_TEAMS) {
                 const uint32_t sb = g % Cfg::BIT_STAGES, itb = g / Cfg::BIT_STAGES;
                 const uint32_t so = (uint32_t)team, ito = g / Cfg::OP_STAGES;
+                uint4 mk[Cfg::CH];
+                if (DIRECT) {                   // the mask words of this stage's haplotypes (one tile: stage g is chunk pair g)
+#pragma unroll
+                    for (int c = 0; c < Cfg::CH; ++c) mk[c] = __ldg(A.mask + g * Cfg::CH + c);
+                }
                 if (!mbar_wait(bit_full + 8 * sb, itb & 1, abort_s, A.error_flag)) { if (SINGLE) { dead = true; break; } goto done; }
                 if (TRACE && A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[192 + g] = gtime();
                 const uint4 *bsrc = reinterpret_cast<const uint4 *>(bit_s + sb * Cfg::BIT_BYTES);
-                uint4 ba[Cfg::CH];
+                uint4 ba[Cfg::CH], bb[Cfg::CH];
 #pragma unroll
-                for (int c = 0; c < Cfg::CH; ++c) ba[c] = bsrc[c * MMA_M + wt];
+                for (int c = 0; c < Cfg::CH; ++c) {
+                    if (DIRECT) {               // [128 rows][CH x 16 B] per operand, as the tensor map's box lands
+                        const uint4 x = bsrc[wt * Cfg::CH + c], y = bsrc[(MMA_M + wt) * Cfg::CH + c];
+                        ba[c] = make_uint4((x.x ^ flip_a) & mk[c].x, (x.y ^ flip_a) & mk[c].y, (x.z ^ flip_a) & mk[c].z, (x.w ^ flip_a) & mk[c].w);
+                        bb[c] = make_uint4(brev_bytes((y.x ^ flip_b) & mk[c].x), brev_bytes((y.y ^ flip_b) & mk[c].y),
+                                           brev_bytes((y.z ^ flip_b) & mk[c].z), brev_bytes((y.w ^ flip_b) & mk[c].w));
+                    } else ba[c] = bsrc[c * MMA_M + wt];
+                }
                 if (!mbar_wait(op_empty + 8 * so, (ito & 1) ^ 1, abort_s, A.error_flag)) { if (SINGLE) { dead = true; break; } goto done; }
                 tc_fence_after();
                 if (TRACE && A.trace && blockIdx.x == 0 && g < 48 && wt == 0) A.trace[256 + g] = gtime();
@@ -716,7 +835,12 @@ triangle_mma_kernel(const MmaArgs A) {
                     tmem_st32(tmem_base + Cfg::TMEM_A0 + so * Cfg::A_COLS + c * (KCHUNK / 4) + tmem_lane, v);
                 }
                 uint8_t *ops = op_s + so * Cfg::OP_BYTES;
-                if (PAIR) {
+                if (DIRECT) {
+                    if (!(TRACE && (A.dbg & 2))) {
+#pragma unroll
+                        for (int c = 0; c < Cfg::CH; ++c) expand_row<true>(ops + c * (N * KCHUNK) + wt * KCHUNK, wt & 7, bb[c]);
+                    }
+                } else if (PAIR) {
                     // 64 column variants x 2 chunks over the team's 128 threads: one row-chunk each
                     const int brow = wt & 63, c = wt >> 6;
                     if (!(TRACE && (A.dbg & 2)))
@@ -748,15 +872,15 @@ triangle_mma_kernel(const MmaArgs A) {
             // as the epilogue warps below (which then do rows 0..15 only), with the column records formed on the
             // fly.  A pair the screen cannot settle leaves its count in the result word and is redone by the lane
             // that found it (finalise_pair); a lane's own store is visible to its own later load.
+            const SetRec &S = A.set[0];
             const int quad = warp & 3, lq = lane >> 2, lr = lane & 3;
-            const uint32_t m_shift = A.measure == LDX_MEASURE_R2 ? 0u : (uint32_t)LDX_DP_SHIFT;
-            const uint32_t thres = A.has_thres ? (uint32_t)A.thres_e4 : 0u;
+            const ScreenK K = make_screen(A);
             const int32_t Nn = A.n_sel;
-            const int64_t r0 = (int64_t)(PAIR ? first_tile.x * 2 + rank : first_tile.x) * MMA_M, c0 = (int64_t)first_tile.y * N;
+            const int64_t r0 = (int64_t)first_tile.x * MMA_M, c0 = (int64_t)first_tile.y * N;
             const int64_t rmin = r0 + quad * 32 + 16;
             const int cb = team * 32;
             const int64_t cg0 = c0 + cb;
-            const bool mine = N == 128 && rmin < A.v && cg0 < rmin + 15 && cg0 < A.v && !(TRACE && (A.dbg & 4));   // warp-uniform
+            const bool mine = N == 128 && rmin < S.v && cg0 < rmin + 15 && cg0 < S.v && !(TRACE && (A.dbg & 4));   // warp-uniform
             const int64_t ra = rmin + lq, rb = ra + 8;
             int32_t n1a = 0, n1b = 0, cn1[8];
             if (mine) {                             // the counts this lane needs, fetched while the tensor pipe finishes
@@ -767,12 +891,11 @@ triangle_mma_kernel(const MmaArgs A) {
             dead = !mbar_wait(tmem_full, 0, abort_s, A.error_flag, 64);
             tc_fence_after();
             if (mine && !dead) {
-                const int32_t aNa = n1a * Nn, cNa = Nn * Nn - aNa, aNb = n1b * Nn, cNb = Nn * Nn - aNb;
-                const float faa = __int2float_rn(n1a * (Nn - n1a)), fab = __int2float_rn(n1b * (Nn - n1b));
-                uint32_t *pa = A.packed + (ra * (ra - 1) / 2 - A.out_off + cg0 + 2 * lr);
-                uint32_t *pb = A.packed + (rb * (rb - 1) / 2 - A.out_off + cg0 + 2 * lr);
-                int32_t *qa = WANT_N11 ? A.n11 + (ra * (ra - 1) / 2 - A.out_off + cg0 + 2 * lr) : nullptr;
-                int32_t *qb = WANT_N11 ? A.n11 + (rb * (rb - 1) / 2 - A.out_off + cg0 + 2 * lr) : nullptr;
+                const RowP Ra = make_rowp(n1a, Nn), Rb = make_rowp(n1b, Nn);
+                uint32_t *pa = S.packed + (ra * (ra - 1) / 2 - S.out_off + cg0 + 2 * lr);
+                uint32_t *pb = S.packed + (rb * (rb - 1) / 2 - S.out_off + cg0 + 2 * lr);
+                int32_t *qa = S.n11 ? S.n11 + (ra * (ra - 1) / 2 - S.out_off + cg0 + 2 * lr) : nullptr;
+                int32_t *qb = S.n11 ? S.n11 + (rb * (rb - 1) / 2 - S.out_off + cg0 + 2 * lr) : nullptr;
                 uint32_t acc[16];
                 tmem_ld16x256(tmem_base + ((uint32_t)(quad * 32 + 16) << 16) + (uint32_t)cb, acc);
                 uint32_t slow = 0;
@@ -780,19 +903,17 @@ triangle_mma_kernel(const MmaArgs A) {
                 for (int i = 0; i < 16; i += 2) {
                     const int k = i >> 2, g = (i >> 1) & 1;
                     const int64_t col = cg0 + 8 * k + 2 * lr;
-                    ColRec cr0, cr1;
-                    cr0.n1 = cn1[2 * k]; cr1.n1 = cn1[2 * k + 1];
-                    cr0.n1N = cr0.n1 * Nn; cr1.n1N = cr1.n1 * Nn;
-                    cr0.prod = __int2float_rn(cr0.n1 * (Nn - cr0.n1)); cr1.prod = __int2float_rn(cr1.n1 * (Nn - cr1.n1));
+                    ColPair cp;
+                    cp.n1f[0] = minor_f(cn1[2 * k], Nn); cp.n1f[1] = minor_f(cn1[2 * k + 1], Nn);
+                    cp.rc[0] = rcp_nn(cn1[2 * k], Nn); cp.rc[1] = rcp_nn(cn1[2 * k + 1], Nn);
                     uint32_t w0, w1;
                     bool s0, s1;
-                    fast_pair2<THRES>(acc[i], acc[i + 1], Nn, g ? n1b : n1a, g ? aNb : aNa, g ? cNb : cNa, g ? fab : faa, cr0, cr1,
-                                      A.lim_dp, A.lim_r2, m_shift, thres, w0, w1, s0, s1);
+                    fast_pair2<THRES>(acc[i], acc[i + 1], K, g ? Rb : Ra, cp, w0, w1, s0, s1);
                     const int64_t row = g ? rb : ra;
-                    const bool v0 = row < A.v && col < row, v1 = row < A.v && col + 1 < row;
+                    const bool v0 = row < S.v && col < row, v1 = row < S.v && col + 1 < row;
                     if (v0) {
                         (g ? pb : pa)[8 * k] = s0 ? (acc[i] >> ACC_SHIFT) : w0;
-                        if (WANT_N11) (g ? qb : qa)[8 * k] = (int32_t)(acc[i] >> ACC_SHIFT);
+                        if (qa) (g ? qb : qa)[8 * k] = true_n11((int32_t)(acc[i] >> ACC_SHIFT), g ? n1b : n1a, cn1[2 * k], Nn);
                         if (s0) {                  // deferred: onto the CTA's list (a full list: redone by this lane below)
                             const uint32_t slot = atomicAdd(pool_cnt, 1u);
                             if (slot < POOL_CAP) pool[slot] = make_uint4((uint32_t)row, (uint32_t)col, acc[i] >> ACC_SHIFT, 0u);
@@ -801,7 +922,7 @@ triangle_mma_kernel(const MmaArgs A) {
                     }
                     if (v1) {
                         (g ? pb : pa)[8 * k + 1] = s1 ? (acc[i + 1] >> ACC_SHIFT) : w1;
-                        if (WANT_N11) (g ? qb : qa)[8 * k + 1] = (int32_t)(acc[i + 1] >> ACC_SHIFT);
+                        if (qa) (g ? qb : qa)[8 * k + 1] = true_n11((int32_t)(acc[i + 1] >> ACC_SHIFT), g ? n1b : n1a, cn1[2 * k + 1], Nn);
                         if (s1) {
                             const uint32_t slot = atomicAdd(pool_cnt, 1u);
                             if (slot < POOL_CAP) pool[slot] = make_uint4((uint32_t)row, (uint32_t)(col + 1), acc[i + 1] >> ACC_SHIFT, 0u);
@@ -814,8 +935,8 @@ triangle_mma_kernel(const MmaArgs A) {
                     slow &= slow - 1;
                     const int k = i >> 2, e = i & 1;
                     const int64_t row = (i & 2) ? rb : ra, col = cg0 + 8 * k + 2 * lr + e;
-                    const uint32_t n11 = ((i & 2) ? pb : pa)[8 * k + e];
-                    settle_slow_pair(make_uint4((uint32_t)row, (uint32_t)col, n11, 0u), A.freq_rows, A.fc, m_shift, thres, A.packed, A.out_off, A.fix);
+                    const uint32_t n11p = ((i & 2) ? pb : pa)[8 * k + e];
+                    settle_slow_pair(make_uint4((uint32_t)row, (uint32_t)col, n11p, 0u), A, K.m_shift, K.thres);
                 }
             }
             tc_fence_before();
@@ -832,7 +953,7 @@ triangle_mma_kernel(const MmaArgs A) {
                 const uint32_t thres = A.has_thres ? (uint32_t)A.thres_e4 : 0u;
                 const uint32_t total = min(*pool_cnt, POOL_CAP);
                 for (uint32_t j = threadIdx.x - 32 * FIRST_WIDEN_WARP; j < total; j += POOL_THREADS)
-                    settle_slow_pair(pool[j], A.freq_rows, A.fc, m_shift, thres, A.packed, A.out_off, A.fix);
+                    settle_slow_pair(pool[j], A, m_shift, thres);
             }
             if (warp == FIRST_WIDEN_WARP && lane == 0 && TRACE && A.trace && blockIdx.x < 192) A.trace[512 + 8 * 192 + 2 * blockIdx.x] = gtime();       // settled
             // no fence here: thread 0's fence after the CTA-wide barrier below is cumulative over everything the
@@ -853,28 +974,35 @@ triangle_mma_kernel(const MmaArgs A) {
         uint4 *sbuf = reinterpret_cast<uint4 *>(stage + 32 * EPI_PITCH);
         uint32_t slow_cnt = 0;                                    // warp-uniform: entries buffered in sbuf
         const uint32_t lanemask_lt = (1u << lane) - 1u;
-        const uint32_t m_shift = A.measure == LDX_MEASURE_R2 ? 0u : (uint32_t)LDX_DP_SHIFT;
-        const uint32_t thres = A.has_thres ? (uint32_t)A.thres_e4 : 0u;      // rounded values are >= 0: 0 flags nothing
         const int32_t Nn = A.n_sel;
-        const float lim_dp = A.lim_dp, lim_r2 = A.lim_r2;
+        const ScreenK K = make_screen(A);
+        const uint32_t m_shift = K.m_shift, thres = K.thres;
         uint32_t tl = 0;
         const uint32_t tmem_empty_leader = PAIR ? mapa_u32(tmem_empty, 0) : 0u;
         for (int t = unit; t < A.n_tiles; t += n_units, ++tl) {
             const uint32_t buf = tl % Cfg::ACC_BUFS;
-            const int2 tile = SINGLE ? first_tile : A.tiles[t];
-            const int64_t r0 = (int64_t)(PAIR ? tile.x * 2 + rank : tile.x) * MMA_M, c0 = (int64_t)tile.y * N;
+            const int4 tile = SINGLE ? first_tile : A.tiles[t];
+            const SetRec &S = A.set[SINGLE ? 0 : tile.z];
+            // rows / columns in the launch's row space (operands, frequencies) and relative to the set (outputs)
+            const int64_t r0g = (int64_t)(PAIR ? tile.x * 2 + rank : tile.x) * MMA_M, c0g = (int64_t)tile.y * N;
+            const int64_t base = SINGLE ? 0 : S.base_row, v = S.v;
+            const int64_t r0 = r0g - base, c0 = c0g - base;
+            uint32_t *const packed = S.packed; int32_t *const n11o = S.n11; const int64_t out_off = S.out_off;
             // the column variants this warp works on (its half of the tile's columns): a private copy per warp costs
             // a few redundant loads and saves a barrier across the eight epilogue warps on every tile
-            ColRec *cols = col_s + ew * (N / 2) - half * (N / 2);         // indexed by the column's offset in the tile
+            ColPair *cols = col_s + ew * (N / 4) - half * (N / 4);        // indexed by HALF the column's offset in the tile
             __syncwarp();                                                 // the previous tile's readers are done
-            for (int i = half * (N / 2) + lane; i < (half + 1) * (N / 2); i += 32) {
-                const int32_t n1 = A.freq_rows[c0 + i].n1;
-                ColRec cr; cr.n1 = n1; cr.n1N = n1 * Nn; cr.prod = __int2float_rn(n1 * (Nn - n1)); cr.pad = 0;
-                cols[i] = cr;
+            {
+                float *cf = reinterpret_cast<float *>(cols);              // column i: n1f at [4 * (i / 2) + (i & 1)], rc two floats on
+                for (int i = half * (N / 2) + lane; i < (half + 1) * (N / 2); i += 32) {
+                    const int32_t n1t = A.freq_rows[c0g + i].n1;
+                    cf[4 * (i >> 1) + (i & 1)] = minor_f(n1t, Nn);
+                    cf[4 * (i >> 1) + (i & 1) + 2] = rcp_nn(n1t, Nn);
+                }
             }
             __syncwarp();
             // the first pass's row counts, fetched before the wait (freq_rows is padded to whole tiles)
-            const int32_t n1a_first = SINGLE ? A.freq_rows[r0 + quad * 32 + lq].n1 : 0, n1b_first = SINGLE ? A.freq_rows[r0 + quad * 32 + lq + 8].n1 : 0;
+            const int32_t n1a_first = SINGLE ? A.freq_rows[r0g + quad * 32 + lq].n1 : 0, n1b_first = SINGLE ? A.freq_rows[r0g + quad * 32 + lq + 8].n1 : 0;
             if (!mbar_wait(tmem_full + 8 * buf, (tl / Cfg::ACC_BUFS) & 1, abort_s, A.error_flag, 128)) {
                 if (SINGLE) break;            // aborted: still meet the other epilogue warps at the barrier below
                 goto done;
@@ -885,23 +1013,22 @@ triangle_mma_kernel(const MmaArgs A) {
             const int h_end = SINGLE && N == 128 && !PAIR && A.help ? 1 : 2;     // single wave: rows 16..31 of the quadrant belong to the wideners
 #pragma unroll 1
             for (int h = 0; h < h_end; ++h) {
-                const int64_t rmin = r0 + quad * 32 + 16 * h;    // this pass: rows rmin .. rmin + 15
-                if (rmin >= A.v || (TRACE && (A.dbg & 4))) break; // warp-uniform
-                // the lane's two row variants: n1a, n1a*N, N^2 - n1a*N, n1a*n0a
+                const int64_t rmin = r0 + quad * 32 + 16 * h;    // this pass: rows rmin .. rmin + 15 of the set
+                if (rmin >= v || (TRACE && (A.dbg & 4))) break;  // warp-uniform
+                // the lane's two row variants
                 const int64_t ra = rmin + lq, rb = ra + 8;
-                const int32_t n1a = SINGLE && h == 0 ? n1a_first : A.freq_rows[ra].n1, n1b = SINGLE && h == 0 ? n1b_first : A.freq_rows[rb].n1;
-                const int32_t aNa = n1a * Nn, cNa = Nn * Nn - aNa, aNb = n1b * Nn, cNb = Nn * Nn - aNb;
-                const float faa = __int2float_rn(n1a * (Nn - n1a)), fab = __int2float_rn(n1b * (Nn - n1b));
+                const int32_t n1a = SINGLE && h == 0 ? n1a_first : A.freq_rows[base + ra].n1, n1b = SINGLE && h == 0 ? n1b_first : A.freq_rows[base + rb].n1;
+                const RowP Ra = make_rowp(n1a, Nn), Rb = make_rowp(n1b, Nn);
                 // result words of (row, column c0 + 2 lr + j) live at p?[j]
-                uint32_t *pa = A.packed + (ra * (ra - 1) / 2 - A.out_off + c0 + 2 * lr);
-                uint32_t *pb = A.packed + (rb * (rb - 1) / 2 - A.out_off + c0 + 2 * lr);
-                int32_t *qa = WANT_N11 ? A.n11 + (ra * (ra - 1) / 2 - A.out_off + c0 + 2 * lr) : nullptr;
-                int32_t *qb = WANT_N11 ? A.n11 + (rb * (rb - 1) / 2 - A.out_off + c0 + 2 * lr) : nullptr;
+                uint32_t *pa = packed + (ra * (ra - 1) / 2 - out_off + c0 + 2 * lr);
+                uint32_t *pb = packed + (rb * (rb - 1) / 2 - out_off + c0 + 2 * lr);
+                int32_t *qa = n11o ? n11o + (ra * (ra - 1) / 2 - out_off + c0 + 2 * lr) : nullptr;
+                int32_t *qb = n11o ? n11o + (rb * (rb - 1) / 2 - out_off + c0 + 2 * lr) : nullptr;
                 const uint32_t tmem_acc = tmem_base + buf * N + ((uint32_t)(quad * 32 + 16 * h) << 16);
 #pragma unroll 1
                 for (int cb = half * (N / 2); cb < (half + 1) * (N / 2); cb += 32) {
                     const int64_t cg0 = c0 + cb;                  // first column of this load
-                    if (cg0 >= rmin + 15 || cg0 >= A.v) break;    // warp-uniform: nothing below the diagonal
+                    if (cg0 >= rmin + 15 || cg0 >= v) break;      // warp-uniform: nothing below the diagonal
                     uint32_t acc[16];
                     tmem_ld16x256(tmem_acc + (uint32_t)cb, acc);
                     uint32_t word[16];
@@ -909,19 +1036,18 @@ triangle_mma_kernel(const MmaArgs A) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 2) {                 // registers i, i + 1: same row, adjacent columns
                         const int k = i >> 2, g = (i >> 1) & 1;
-                        const ColRec cr0 = cols[cb + 8 * k + 2 * lr], cr1 = cols[cb + 8 * k + 2 * lr + 1];
+                        const ColPair cp = cols[(cb >> 1) + 4 * k + lr];
                         bool s0, s1;
-                        fast_pair2<THRES>(acc[i], acc[i + 1], Nn, g ? n1b : n1a, g ? aNb : aNa, g ? cNb : cNa, g ? fab : faa, cr0, cr1,
-                                          lim_dp, lim_r2, m_shift, thres, word[i], word[i + 1], s0, s1);
-                        slow |= ((uint32_t)s0 << i) | ((uint32_t)s1 << (i + 1));
+                        fast_pair2<THRES>(acc[i], acc[i + 1], K, g ? Rb : Ra, cp, word[i], word[i + 1], s0, s1);
+                        if (s0) slow |= 1u << i;
+                        if (s1) slow |= 2u << i;
                     }
-                    const bool interior = cg0 + 32 <= rmin && rmin + 15 < A.v;   // warp-uniform: every pair is below the diagonal
+                    const bool interior = cg0 + 32 <= rmin && rmin + 15 < v;   // warp-uniform: every pair is below the diagonal
                     if (interior) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int k = i >> 2, g = (i >> 1) & 1, e = i & 1;
                             (g ? pb : pa)[cb + 8 * k + e] = word[i];
-                            if (WANT_N11) (g ? qb : qa)[cb + 8 * k + e] = (int32_t)(acc[i] >> ACC_SHIFT);
                         }
                     } else {
                         uint32_t valid = 0;
@@ -929,13 +1055,21 @@ triangle_mma_kernel(const MmaArgs A) {
                         for (int i = 0; i < 16; ++i) {
                             const int k = i >> 2, g = (i >> 1) & 1, e = i & 1;
                             const int64_t row = g ? rb : ra, col = cg0 + 8 * k + 2 * lr + e;
-                            if (row < A.v && col < row) {         // only pairs of the triangle exist
+                            if (row < v && col < row) {           // only pairs of the triangle exist
                                 valid |= 1u << i;
                                 (g ? pb : pa)[cb + 8 * k + e] = word[i];
-                                if (WANT_N11) (g ? qb : qa)[cb + 8 * k + e] = (int32_t)(acc[i] >> ACC_SHIFT);
                             }
                         }
                         slow &= valid;
+                    }
+                    if (n11o) {                                   // warp-uniform; the counts are a diagnostic / test output
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int k = i >> 2, g = (i >> 1) & 1, e = i & 1;
+                            const int64_t row = g ? rb : ra, col = cg0 + 8 * k + 2 * lr + e;
+                            if (row < v && col < row)
+                                (g ? qb : qa)[cb + 8 * k + e] = true_n11((int32_t)(acc[i] >> ACC_SHIFT), g ? n1b : n1a, A.freq_rows[base + col].n1, Nn);
+                        }
                     }
                     // Rare (about 1% of the pairs): a screened value sits next to a rounding boundary, or D
                     // is exactly 0 for two polymorphic variants.  Those pairs are not redone here -- one lane
@@ -960,7 +1094,7 @@ triangle_mma_kernel(const MmaArgs A) {
                                 slow &= slow - 1;
                                 const uint32_t a = stage[lane * EPI_PITCH + i];
                                 const int64_t row = (i & 2) ? rb : ra, col = cg0 + 8 * (i >> 2) + 2 * lr + (i & 1);
-                                sbuf[slow_cnt + __popc(bal & lanemask_lt)] = make_uint4((uint32_t)row, (uint32_t)col, a >> ACC_SHIFT, 0u);
+                                sbuf[slow_cnt + __popc(bal & lanemask_lt)] = make_uint4((uint32_t)row, (uint32_t)col, a >> ACC_SHIFT, SINGLE ? 0u : (uint32_t)tile.z);
                             }
                             slow_cnt += __popc(bal);
                             __syncwarp();
@@ -984,12 +1118,12 @@ triangle_mma_kernel(const MmaArgs A) {
             base = __shfl_sync(0xffffffffu, base, 0);
             for (uint32_t i = lane; i < slow_cnt; i += 32) {
                 if (base + i < POOL_CAP) pool[base + i] = sbuf[i];
-                else settle_slow_pair(sbuf[i], A.freq_rows, A.fc, m_shift, thres, A.packed, A.out_off, A.fix);
+                else settle_slow_pair(sbuf[i], A, m_shift, thres);
             }
             asm volatile("bar.sync 1, %0;" :: "n"(POOL_THREADS) : "memory");
             const uint32_t total = min(*pool_cnt, POOL_CAP);
             for (uint32_t j = threadIdx.x - 32 * FIRST_WIDEN_WARP; j < total; j += POOL_THREADS)
-                settle_slow_pair(pool[j], A.freq_rows, A.fc, m_shift, thres, A.packed, A.out_off, A.fix);
+                settle_slow_pair(pool[j], A, m_shift, thres);
         } else {
             flush_slow<false>(A, sbuf, slow_cnt, lane, m_shift, thres);
         }
@@ -1021,12 +1155,12 @@ bool triangle_mma_available() { return true; }
 // haplotypes fewer than 1% of the pairs are deferred; beyond it ENGINE_AUTO uses the popcount engine.
 int triangle_mma_max_haplotypes() { return 8192; }
 
-template <int N, bool WANT_N11, bool THRES, bool TRACE, bool PAIR, bool SINGLE>
+template <int N, bool THRES, bool TRACE, bool PAIR, bool SINGLE, bool DIRECT>
 static int launch_tiles_t(ldx_ctx *ctx, const MmaArgs &A) {
     static bool attr_set[64] = {};            // a function attribute is per device: a process may hold contexts on several
     const int dv = ctx->device & 63;
     if (!attr_set[dv]) {
-        LDX_CUDA(cudaFuncSetAttribute(triangle_mma_kernel<N, WANT_N11, THRES, TRACE, PAIR, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        LDX_CUDA(cudaFuncSetAttribute(triangle_mma_kernel<N, THRES, TRACE, PAIR, SINGLE, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)MmaCfg<N, PAIR>::SMEM));
         attr_set[dv] = true;
     }
@@ -1043,148 +1177,215 @@ static int launch_tiles_t(ldx_ctx *ctx, const MmaArgs &A) {
         attr[1].id = cudaLaunchAttributeClusterDimension;
         attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = PAIR ? 2 : 1;
-        LDX_CUDA(cudaLaunchKernelEx(&cfg, triangle_mma_kernel<N, WANT_N11, THRES, TRACE, PAIR, SINGLE>, A));
+        LDX_CUDA(cudaLaunchKernelEx(&cfg, triangle_mma_kernel<N, THRES, TRACE, PAIR, SINGLE, DIRECT>, A));
     }
     timing_end(ctx);
     ctx->launches++;
     LDX_LAUNCHED(ctx, "triangle_mma_kernel");
     return LDX_OK;
 }
-template <int N, bool PAIR, bool SINGLE>
+template <int N, bool PAIR, bool SINGLE, bool DIRECT>
 static int launch_tiles_s(ldx_ctx *ctx, const MmaArgs &A) {
-    if (A.trace && !A.has_thres && !A.n11) return launch_tiles_t<N, false, false, true, PAIR, SINGLE>(ctx, A);   // diagnostics build of the kernel
-    if (A.has_thres) return A.n11 ? launch_tiles_t<N, true, true, false, PAIR, SINGLE>(ctx, A) : launch_tiles_t<N, false, true, false, PAIR, SINGLE>(ctx, A);
-    return A.n11 ? launch_tiles_t<N, true, false, false, PAIR, SINGLE>(ctx, A) : launch_tiles_t<N, false, false, false, PAIR, SINGLE>(ctx, A);
-}
-template <int N, bool PAIR>
-static int launch_tiles(ldx_ctx *ctx, const MmaArgs &A) {
-    return A.inline_settle ? launch_tiles_s<N, PAIR, true>(ctx, A) : launch_tiles_s<N, PAIR, false>(ctx, A);
+    if (A.trace && !A.has_thres && N == 128) return launch_tiles_t<N, false, N == 128, PAIR, SINGLE, DIRECT>(ctx, A);   // diagnostics build of the kernel
+    return A.has_thres ? launch_tiles_t<N, true, false, PAIR, SINGLE, DIRECT>(ctx, A) : launch_tiles_t<N, false, false, PAIR, SINGLE, DIRECT>(ctx, A);
 }
 
-int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t row_begin, int measure, int has_thres,
-                        int thres_e4, uint32_t *d_packed, int32_t *d_n11, uint32_t publish_seq) {
-    if (v < 2) return LDX_OK;
-    if (row_begin % MMA_M) return set_error(LDX_ERR_ARG, "tcgen05 engine: row_begin must be a multiple of 128");
-    ldx_ctx *ctx = s->ctx;
-    if (s->n_sel > triangle_mma_max_haplotypes())
+// The planes of a store as a 2-D tensor ([n_variants][stride_words * 2] uint32), box = 8 words (32 B: one pipeline stage's two
+// haplotype chunks) x 128 rows.  Encoded once per store through the driver entry point (no link-time libcuda dependency).
+static int ensure_tensor_map(ldx_store *s) {
+    if (s->tmap_ready) return LDX_OK;
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            cudaGetLastError();
+            return set_error(LDX_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        }
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    static_assert(sizeof(CUtensorMap) == sizeof(s->tmap), "tensor map size");
+    const cuuint64_t dims[2] = {(cuuint64_t)s->stride_words * 2, (cuuint64_t)std::max<int64_t>(s->n_variants, 1)};
+    const cuuint64_t strides[1] = {(cuuint64_t)s->stride_words * 8};
+    const cuuint32_t box[2] = {8, (cuuint32_t)MMA_M}, estr[2] = {1, 1};
+    const CUresult r = encode(reinterpret_cast<CUtensorMap *>(s->tmap), CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, s->d_planes, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(LDX_ERR_CUDA, "cuTensorMapEncodeTiled failed for the store's planes");
+    s->tmap_ready = true;
+    return LDX_OK;
+}
+
+int launch_triangle_mma(ldx_ctx *ctx, const MmaSetDesc *sets, int n_sets, const int64_t *d_rows, int measure, int has_thres,
+                        int thres_e4, uint32_t publish_seq) {
+    if (n_sets < 1 || n_sets > MMA_MAX_SETS) return set_error(LDX_ERR_ARG, "tcgen05 engine: 1..32 variant sets per launch");
+    ldx_store *s0 = sets[0].s;
+    int64_t v_max = 0;
+    for (int k = 0; k < n_sets; ++k) {
+        const MmaSetDesc &d = sets[k];
+        if (d.s->ctx != ctx) return set_error(LDX_ERR_ARG, "tcgen05 engine: every store of a launch must belong to the calling context");
+        if (d.s->n_hap != s0->n_hap || d.s->n_sel != s0->n_sel || d.s->stride_words != s0->stride_words)
+            return set_error(LDX_ERR_ARG, "tcgen05 engine: the variant sets of one launch must share the haplotype count and the number of selected haplotypes");
+        if (d.row_begin % MMA_M) return set_error(LDX_ERR_ARG, "tcgen05 engine: row_begin must be a multiple of 128");
+        if (n_sets > 1 && d.row_begin != 0) return set_error(LDX_ERR_ARG, "tcgen05 engine: row ranges are for single-set calls");
+        if (!d.d_packed) return set_error(LDX_ERR_ARG, "tcgen05 engine: the packed output is required");
+        v_max = std::max(v_max, d.v);
+    }
+    if (v_max < 2) return LDX_OK;
+    if (s0->n_sel > triangle_mma_max_haplotypes())
         return set_error(LDX_ERR_ARG, "tcgen05 engine: more than 8192 selected haplotypes (use LDX_ENGINE_POPC or LDX_ENGINE_AUTO)");
-    if (!d_packed) return set_error(LDX_ERR_ARG, "tcgen05 engine: the packed output is required");
-    if (s->n_hap > (1 << 23)) return set_error(LDX_ERR_ARG, "tcgen05 engine: more than 2^23 haplotypes would overflow the int32 accumulator");
+    if (s0->n_hap > (1 << 23)) return set_error(LDX_ERR_ARG, "tcgen05 engine: more than 2^23 haplotypes would overflow the int32 accumulator");
     // 128-haplotype chunks, rounded up to whole pipeline stages of two (rows are 128 B multiples,
     // i.e. a multiple of 8 chunks, so the padding chunk is inside the row and zero)
-    const int kc_count = ((s->n_hap + KCHUNK - 1) / KCHUNK + 1) / 2 * 2;
-    const int64_t v_pad = (v + 255) / 256 * 256;
-    const int64_t panels = v_pad / MMA_M;
+    const int kc_count = ((s0->n_hap + KCHUNK - 1) / KCHUNK + 1) / 2 * 2;
+    // the launch's row space: the sets one after the other, each padded to whole 256-row panels
+    int64_t base_row[MMA_MAX_SETS], total_rows = 0;
+    for (int k = 0; k < n_sets; ++k) { base_row[k] = total_rows; total_rows += (sets[k].v + 255) / 256 * 256; }
+    const int64_t panels = total_rows / MMA_M;
     // tile width: narrow tiles give every SM several tiles to overlap for small matrices, wide
     // tiles amortise the widening work for large ones
     int n_tile = ctx->mma_tile_n;
-    if (n_tile == 0) n_tile = v <= 1024 ? 64 : 128;
+    if (n_tile == 0) n_tile = (n_sets == 1 && v_max <= 1024) ? 64 : 128;
     // CTA pairs (256 x 128 tiles, cta_group::2): a quarter less widening work per result
     // mma_pair: 0 off, 1 on, -1 (default) on for multi-wave calls -- a one-wave call has nothing to overlap the pair's longer
     // prologue and signalling with
-    bool pair = ctx->mma_pair != 0 && n_tile == 128 && row_begin % (2 * MMA_M) == 0 && ctx->sm_count % 2 == 0;
-    if (pair && ctx->mma_pair < 0) {
-        size_t single_cta_tiles = 0;
-        for (int64_t bi = row_begin / MMA_M; bi < (v + MMA_M - 1) / MMA_M; ++bi)
-            single_cta_tiles += (size_t)((std::min<int64_t>(bi * MMA_M + MMA_M - 1, v - 1) + n_tile - 1) / n_tile);
-        pair = single_cta_tiles > (size_t)ctx->sm_count;
-    }
+    bool pair = ctx->mma_pair != 0 && n_tile == 128 && sets[0].row_begin % (2 * MMA_M) == 0 && ctx->sm_count % 2 == 0;
+    auto count_tiles = [&](int64_t ph) {
+        size_t n = 0;
+        for (int k = 0; k < n_sets; ++k)
+            for (int64_t bi = sets[k].row_begin / ph; bi < (sets[k].v + ph - 1) / ph; ++bi)
+                n += (size_t)((std::min<int64_t>(bi * ph + ph - 1, sets[k].v - 1) + n_tile - 1) / n_tile);
+        return n;
+    };
+    if (pair && ctx->mma_pair < 0) pair = count_tiles(MMA_M) > (size_t)ctx->sm_count;
     const int64_t ph = pair ? 2 * MMA_M : MMA_M;             // tile height
-    // ---- tile list (cached): every 128 x N tile holding at least one pair with row > col, row-panel major
-    const size_t bits_bytes = (size_t)panels * kc_count * 128 * sizeof(uint4);
-    const size_t freq_bytes = (size_t)v_pad * sizeof(VarFreq);
-    size_t n_tiles = 0;
-    for (int64_t bi = row_begin / ph; bi < (v + ph - 1) / ph; ++bi) {
-        const int64_t rmax = std::min<int64_t>(bi * ph + ph - 1, v - 1);
-        n_tiles += (size_t)((rmax + n_tile - 1) / n_tile);
-    }
+    const size_t n_tiles = count_tiles(ph);
     if (n_tiles == 0) return LDX_OK;
     if (n_tiles > 0x7fffffffull) return set_error(LDX_ERR_ARG, "tcgen05 engine: too many tiles");
-    const size_t tile_bytes = (n_tiles * sizeof(int2) + 15) / 16 * 16;
+    // one wave of tiles (e.g. the 2,000-variant workload: 136 tiles on 148 SMs): a follow-up kernel for ~1% of the
+    // pairs costs more (launch boundary + its own tail) than settling them in the epilogue warps
+    static const int inline_env = getenv("LDX_INLINE_SETTLE") ? atoi(getenv("LDX_INLINE_SETTLE")) : -1;
+    const bool one_wave = n_tiles <= (size_t)(pair ? ctx->sm_count / 2 : ctx->sm_count);
+    const bool single = n_sets == 1 && (inline_env >= 0 ? inline_env != 0 && one_wave : one_wave);
+    // direct mode: a one-wave call on contiguous store rows needs no gathered copy of the operands at all
+    static const int direct_env = getenv("LDX_MMA_DIRECT") ? atoi(getenv("LDX_MMA_DIRECT")) : -1;
+    const bool direct = single && !pair && n_tile == 128 && sets[0].contiguous && (direct_env >= 0 ? direct_env != 0 : ctx->mma_direct != 0) &&
+                        sets[0].row0 + total_rows < (1ll << 31);
+    // ---- scratch: bit panels (both operand forms), frequencies, tile list, deferred-pair list
+    const size_t bits_bytes = direct ? 0 : (size_t)panels * kc_count * 128 * sizeof(uint4);
+    const size_t freq_bytes = direct ? 0 : (size_t)total_rows * sizeof(VarFreq);
+    const size_t tile_bytes = (n_tiles * sizeof(int4) + 15) / 16 * 16;
     // deferred-pair list: the guard band defers < 1% of the pairs (triangle_mma_max_haplotypes)
-    const uint64_t n_pairs = (uint64_t)v * (uint64_t)(v - 1) / 2 - (uint64_t)row_begin * (uint64_t)(row_begin > 0 ? row_begin - 1 : 0) / 2;
+    uint64_t n_pairs = 0;
+    for (int k = 0; k < n_sets; ++k) {
+        const uint64_t v = (uint64_t)sets[k].v, rb = (uint64_t)sets[k].row_begin;
+        if (v >= 2) n_pairs += v * (v - 1) / 2 - rb * (rb > 0 ? rb - 1 : 0) / 2;
+    }
     const uint64_t slow_cap64 = n_pairs / 64 + 65536;
     if (slow_cap64 > 0xffffffffull) return set_error(LDX_ERR_ARG, "tcgen05 engine: too many pairs for one call");
-    const size_t slow_bytes = (size_t)slow_cap64 * sizeof(uint4);
+    const size_t slow_bytes = single ? 0 : (size_t)slow_cap64 * sizeof(uint4);
     const size_t need = 2 * bits_bytes + freq_bytes + tile_bytes + slow_bytes + 1024;
     if (ctx->mma_ops_bytes < need) {
         if (ctx->d_mma_ops) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_mma_ops); ctx->d_mma_ops = nullptr; ctx->mma_ops_bytes = 0; }
         if (cudaMalloc(&ctx->d_mma_ops, need) != cudaSuccess) { cudaGetLastError(); return set_error(LDX_ERR_NOMEM, "tcgen05 operand scratch allocation failed"); }
         ctx->mma_ops_bytes = need;
-        ctx->mma_tiles_v = -1;
+        ctx->mma_tiles_key.clear();
     }
     uint8_t *base = reinterpret_cast<uint8_t *>(ctx->d_mma_ops);
     uint4 *d_bits = reinterpret_cast<uint4 *>(base), *d_bits_rev = reinterpret_cast<uint4 *>(base + bits_bytes);
     VarFreq *d_freq_rows = reinterpret_cast<VarFreq *>(base + 2 * bits_bytes);
-    int2 *d_tiles = reinterpret_cast<int2 *>(base + 2 * bits_bytes + freq_bytes);
+    int4 *d_tiles = reinterpret_cast<int4 *>(base + 2 * bits_bytes + freq_bytes);
     uint4 *d_slow = reinterpret_cast<uint4 *>(base + 2 * bits_bytes + freq_bytes + tile_bytes);
-    if (ctx->mma_tiles_v != v || ctx->mma_tiles_n != n_tile || ctx->mma_tiles_begin != row_begin || ctx->mma_tiles_ptr != d_tiles ||
-        ctx->mma_tiles_pair != pair) {
-        // the list depends on (v, row_begin, N) only; its PLACE in the scratch block also on the haplotype count
-        // Longest tiles first is not needed (all tiles cost the same K loop); the list is ordered so
-        // that the tiles a wave of CTAs works on share row panels and neighbouring column blocks in L2.
-        std::vector<int2> tiles;
+    // ---- tile list (cached): every tile holding at least one pair with row > col, set by set, row-panel major, in the launch's
+    // row space.  All tiles cost the same K loop; the order keeps the tiles a wave of CTAs works on in neighbouring panels in L2.
+    std::vector<int64_t> key;
+    key.reserve(2 + 2 * (size_t)n_sets);
+    key.push_back(n_tile); key.push_back(pair ? 1 : 0);
+    for (int k = 0; k < n_sets; ++k) { key.push_back(sets[k].v); key.push_back(sets[k].row_begin); }
+    if (ctx->mma_tiles_ptr != d_tiles || ctx->mma_tiles_key != key) {
+        std::vector<int4> tiles;
         tiles.reserve(n_tiles);
-        for (int64_t bi = row_begin / ph; bi < (v + ph - 1) / ph; ++bi) {
-            const int64_t rmax = std::min<int64_t>(bi * ph + ph - 1, v - 1);
-            for (int64_t bj = 0; bj * n_tile < rmax; ++bj) tiles.push_back(make_int2((int)bi, (int)bj));
+        for (int k = 0; k < n_sets; ++k) {
+            const int64_t pb = base_row[k] / ph, cb = base_row[k] / n_tile;
+            for (int64_t bi = sets[k].row_begin / ph; bi < (sets[k].v + ph - 1) / ph; ++bi) {
+                const int64_t rmax = std::min<int64_t>(bi * ph + ph - 1, sets[k].v - 1);
+                for (int64_t bj = 0; bj * n_tile < rmax; ++bj) tiles.push_back(make_int4((int)(pb + bi), (int)(cb + bj), k, 0));
+            }
         }
-        LDX_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), n_tiles * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+        LDX_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), n_tiles * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
         LDX_CUDA(cudaStreamSynchronize(ctx->stream));   // `tiles` is a local
-        ctx->mma_tiles_v = v; ctx->mma_tiles_n = n_tile; ctx->mma_tiles_begin = row_begin; ctx->mma_tiles_ptr = d_tiles; ctx->mma_tiles_pair = pair;
+        ctx->mma_tiles_key = key; ctx->mma_tiles_ptr = d_tiles;
     }
 
-    dim3 ggrid((unsigned)((v_pad + 255) / 256), (unsigned)kc_count);
-    {
+    if (!direct) {
+        GatherArgs G;
+        memset(&G, 0, sizeof G);
+        for (int k = 0; k < n_sets; ++k) {
+            GatherSet &g = G.set[k];
+            g.planes = sets[k].s->d_planes; g.mask = sets[k].s->d_mask; g.freq = sets[k].s->d_freq; g.rows = d_rows + sets[k].rows_off;
+            g.v = sets[k].v; g.v_pad = (sets[k].v + 255) / 256 * 256; g.base_row = base_row[k];
+            g.stride_words = sets[k].s->stride_words; g.n_sel = sets[k].s->n_sel;
+        }
+        G.kc_count = kc_count; G.bits = d_bits; G.bits_rev = d_bits_rev; G.freq_rows = d_freq_rows;
+        const int64_t v_pad_max = (v_max + 255) / 256 * 256;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = ggrid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+        cfg.gridDim = dim3((unsigned)(v_pad_max / 256), (unsigned)kc_count, (unsigned)n_sets); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        LDX_CUDA(cudaLaunchKernelEx(&cfg, gather_bits_kernel, (const uint64_t *)s->d_planes, (const uint64_t *)s->d_mask, (int32_t)s->stride_words,
-                                    (const int64_t *)d_rows, (int64_t)v, (int64_t)v_pad, (int32_t)kc_count, (const VarFreq *)s->d_freq, d_bits, d_bits_rev,
-                                    d_freq_rows));
+        LDX_CUDA(cudaLaunchKernelEx(&cfg, gather_bits_kernel, G));
+        ctx->launches++;
+        LDX_LAUNCHED(ctx, "gather_bits_kernel");
     }
-    ctx->launches++;
-    LDX_LAUNCHED(ctx, "gather_bits_kernel");
 
     MmaArgs A;
-    A.bits = d_bits; A.bits_rev = d_bits_rev; A.kc_count = kc_count; A.freq_rows = d_freq_rows; A.fc = s->fc; A.tiles = d_tiles;
+    memset(&A, 0, sizeof A);
+    A.bits = d_bits; A.bits_rev = d_bits_rev; A.kc_count = kc_count; A.freq_rows = d_freq_rows; A.fc = s0->fc; A.tiles = d_tiles;
     A.n_tiles = (int32_t)n_tiles;
-    A.v = v; A.measure = measure; A.has_thres = has_thres; A.thres_e4 = thres_e4;
-    A.out_off = row_begin * (row_begin - 1) / 2;
-    A.packed = d_packed; A.n11 = d_n11;
-    A.n_sel = s->n_sel;
-    {   // guard band of the screening arithmetic (see fast_pair2).  Its fp32 half needs m and n1*n0 exact
+    A.measure = measure; A.has_thres = has_thres; A.thres_e4 = thres_e4;
+    for (int k = 0; k < n_sets; ++k) {
+        SetRec &r = A.set[k];
+        r.base_row = base_row[k]; r.v = sets[k].v; r.out_off = sets[k].row_begin * (sets[k].row_begin - 1) / 2;
+        r.packed = sets[k].d_packed; r.n11 = sets[k].d_n11; r.fix_tag = sets[k].fix_tag;
+    }
+    A.n_sel = s0->n_sel;
+    {   // guard band of the screening arithmetic (see fast_pair2).  Its fp32 half needs the minor-allele products exact
         // (<= 2^24, i.e. N <= 8192); should a caller ever get past the check above with more, every pair
         // takes the exact path.
-        const double n = (double)s->n_sel, g = 1.0e4 * 16.0 * 1.1102230246251565e-16 * n * n;
-        const bool ok = s->n_sel <= 8192;
+        const double n = (double)s0->n_sel, g = 1.0e4 * 16.0 * 1.1102230246251565e-16 * n * n;
+        const bool ok = s0->n_sel <= 8192;
         A.lim_r2 = ok ? (float)(0.5 - (g + 1.0e-5)) : -1.0f;
         A.lim_dp = ok ? (float)(0.5 - (0.5 * g + 1.0e-5)) : -1.0f;
     }
-    A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity, ctx->fix_tag};
+    A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity, sets[0].fix_tag};
     A.error_flag = reinterpret_cast<int32_t *>(ctx->d_fix_count + 1);
     A.slow = d_slow; A.slow_count = ctx->d_fix_count + 2;
     A.slow_cap = ctx->defer_cap ? (uint32_t)std::min<uint64_t>(slow_cap64, (uint64_t)ctx->defer_cap) : (uint32_t)slow_cap64;
     A.pool_cap = ctx->defer_cap ? (uint32_t)ctx->defer_cap : 0xffffffffu;
     A.trace = ctx->d_trace;
     A.dbg = getenv("LDX_DEBUG_MMA") ? atoi(getenv("LDX_DEBUG_MMA")) : 0;
-    // one wave of tiles (e.g. the 2,000-variant workload: 136 tiles on 148 SMs): a follow-up kernel for ~1% of the
-    // pairs costs more (launch boundary + its own tail) than settling them in the epilogue warps
-    static const int inline_env = getenv("LDX_INLINE_SETTLE") ? atoi(getenv("LDX_INLINE_SETTLE")) : -1;
-    A.inline_settle = inline_env >= 0 ? inline_env : (n_tiles <= (size_t)(pair ? ctx->sm_count / 2 : ctx->sm_count) ? 1 : 0);
+    A.inline_settle = single ? 1 : 0;
     A.counters = ctx->d_fix_count; A.mailbox = publish_seq ? ctx->d_mailbox : nullptr; A.seq = publish_seq;
-    A.help = A.inline_settle && n_tile == 128 && !pair && !getenv("LDX_NO_HELP");
-    int rc;
-    switch (n_tile) {
-        case 64: rc = launch_tiles<64, false>(ctx, A); break;
-        case 128: rc = pair ? launch_tiles<128, true>(ctx, A) : launch_tiles<128, false>(ctx, A); break;
-        default: return set_error(LDX_ERR_ARG, "tcgen05 tile width must be 64 or 128");
+    A.help = single && n_tile == 128 && !pair && !getenv("LDX_NO_HELP");
+    if (direct) {
+        LDX_TRY(ensure_tensor_map(s0));
+        memcpy(&A.tmap, s0->tmap, sizeof A.tmap);
+        A.mask = reinterpret_cast<const uint4 *>(s0->d_mask);
+        A.row0 = (int32_t)sets[0].row0;
+        A.freq_rows = s0->d_freq + sets[0].row0;          // padded by STORE_FREQ_PAD zeroed entries: whole tiles may be read
+        A.bits = A.bits_rev = nullptr;
     }
+    int rc;
+    if (n_tile == 64) rc = single ? launch_tiles_s<64, false, true, false>(ctx, A) : launch_tiles_s<64, false, false, false>(ctx, A);
+    else if (n_tile == 128) {
+        if (direct) rc = launch_tiles_s<128, false, true, true>(ctx, A);
+        else if (pair) rc = single ? launch_tiles_s<128, true, true, false>(ctx, A) : launch_tiles_s<128, true, false, false>(ctx, A);
+        else rc = single ? launch_tiles_s<128, false, true, false>(ctx, A) : launch_tiles_s<128, false, false, false>(ctx, A);
+    } else return set_error(LDX_ERR_ARG, "tcgen05 tile width must be 64 or 128");
     if (rc != LDX_OK) return rc;
-    if (A.inline_settle) return LDX_OK;
+    if (single) return LDX_OK;
     // deferred pairs + completion record (d_fix_count: [0] near-ties, [1] error flag, [2] deferred pairs, [3] ticket)
     // ~1% of the pairs are deferred and each costs a long, serial fp64 chain: one pair per thread at twice that
     // rate (idle blocks are cheap, a thread looping over several pairs is not)
@@ -1196,9 +1397,7 @@ int launch_triangle_mma(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t 
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        LDX_CUDA(cudaLaunchKernelEx(&cfg, slow_pairs_kernel, (const uint4 *)d_slow, ctx->d_fix_count, A.slow_cap, (const VarFreq *)d_freq_rows, s->fc,
-                                    (int)measure, (int)has_thres, (int)thres_e4, d_packed, A.out_off, A.fix,
-                                    (volatile uint32_t *)(publish_seq ? ctx->d_mailbox : nullptr), publish_seq));
+        LDX_CUDA(cudaLaunchKernelEx(&cfg, slow_pairs_kernel, A));
     }
     ctx->launches++;
     LDX_LAUNCHED(ctx, "slow_pairs_kernel");

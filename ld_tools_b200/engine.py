@@ -11,8 +11,8 @@ import numpy as np
 
 from . import _lib
 from ._lib import (BELOW_THRES, DP_INT0, DP_MASK, DP_SHIFT, ENGINE_AUTO, ENGINE_MMA, ENGINE_POPC,  # noqa: F401
-                   HIT_DTYPE, LD_RESULT_DTYPE, MEASURE_DPRIME, MEASURE_R2, R2_INT0, R2_MASK, VCF_ROW_DTYPE, LdxError,
-                   check, ptr)
+                   HIT_DTYPE, LD_RESULT_DTYPE, MEASURE_DPRIME, MEASURE_R2, R2_INT0, R2_MASK, TRIANGLE_SET_DTYPE, VCF_ROW_DTYPE,
+                   LdxError, check, ptr)
 
 MEASURES = {"r_square": MEASURE_R2, "d_prime": MEASURE_DPRIME}   # the CLI's -l choices
 
@@ -146,6 +146,18 @@ class Context:
         n = C.c_int64()
         check(self._lib.ldx_resolve(self._h, C.byref(n)))
         return n.value
+
+    def triangle_batch_dev(self, sets, measure="r_square", thres_e4_=None, engine=ENGINE_AUTO):
+        """Several variant sets in ONE launch of the all-pairs engine (ldx_triangle_batch_dev).  `sets`: iterable of
+        (store, rows, dev_packed[, dev_n11]) with raw device addresses; enqueue only -- call resolve() after."""
+        rec = np.zeros(len(sets), dtype=TRIANGLE_SET_DTYPE)
+        keep = []                                              # the row arrays must outlive the call
+        for k, t in enumerate(sets):
+            rows = _i64(t[1])
+            keep.append(rows)
+            rec[k] = (t[0]._h.value, rows.ctypes.data, rows.shape[0], int(t[2]), int(t[3]) if len(t) > 3 and t[3] else 0)
+        check(self._lib.ldx_triangle_batch_dev(self._h, ptr(rec), len(sets), _measure_code(measure), int(thres_e4_ is not None),
+                                               int(thres_e4_ or 0), int(engine)))
 
     def triangle_text(self, packed, v, measure, prefixes, row_begin=0, row_end=None, out=None, dev_text=0):
         """The body lines of ld_triangle's table (ld_triangle.py:356-360), formatted on the GPU.

@@ -6,6 +6,7 @@ import os
 import numpy as np
 
 N_SAMPLES, N_VARIANTS, SEED = 120, 520, 77
+N_TRIANGLE_BIG = 320
 
 
 def build_dataset(root):
@@ -54,6 +55,15 @@ def build_dataset(root):
     srcs["triangle"] = d
     srcs["lite_pairs"] = [(addressable[start + 1], addressable[start + 4]), (addressable[3], addressable[-2]),
                           (addressable[start + 10], addressable[start + 11])]
+    # ld_triangle source large enough for the tcgen05 engine (LDX_ENGINE_AUTO uses it from 256 variants up): 320 variants of the
+    # chromosome in shuffled order.  Its own generator: the draws above (and the goldens made from them) do not move.
+    d = os.path.join(root, "src_triangle_big")
+    os.makedirs(d)
+    rng_big = np.random.default_rng(SEED + 1000)
+    with open(os.path.join(d, "region.txt"), "w") as fh:
+        for k in rng_big.permutation(len(addressable))[:N_TRIANGLE_BIG]:
+            fh.write(addressable[k] + "\n")
+    srcs["triangle_big"] = d
     return intgen, srcs
 
 
@@ -67,6 +77,11 @@ AREA_CASES = [
 TRIANGLE_CASES = [
     ("triangle_r2", ["-o", "table"]),
     ("triangle_dp_thres_sas_male", ["-o", "table", "-l", "d_prime", "-z", "0.5", "-e", "sas", "-g", "male"]),
+]
+# 320 variants: files in -> tcgen05 all-pairs kernel -> settlement -> text kernel -> file out, against the reference's own file
+TRIANGLE_BIG_CASES = [
+    ("triangle_big_r2", ["-o", "table"]),
+    ("triangle_big_dp_thres_eur", ["-o", "table", "-l", "d_prime", "-z", "0.4", "-e", "eur"]),
 ]
 LITE_CASES = [("lite_all", []), ("lite_eur", ["-e", "eur"])]
 

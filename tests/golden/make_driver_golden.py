@@ -51,6 +51,12 @@ def main():
         run_ref("ld_triangle.py", ["-S", srcs["triangle"], "-D", intgen, "-t", trg, "-f", "-p", "1"] + extra, work)
         shutil.copytree(trg, os.path.join(OUT, name))
         index[name] = sorted(dc.read_tree(trg))
+    for name, extra in dc.TRIANGLE_BIG_CASES:
+        trg = os.path.join(work, "out_" + name)
+        os.makedirs(trg)
+        run_ref("ld_triangle.py", ["-S", srcs["triangle_big"], "-D", intgen, "-t", trg, "-f", "-p", "1"] + extra, work)
+        shutil.copytree(trg, os.path.join(OUT, name))
+        index[name] = sorted(dc.read_tree(trg))
     for name, extra in dc.LITE_CASES:
         os.makedirs(os.path.join(OUT, name))
         for k, (a, b) in enumerate(srcs["lite_pairs"]):

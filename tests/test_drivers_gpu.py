@@ -81,6 +81,73 @@ def test_ld_triangle_table_identical(data, ctx, tmp_path, name, extra):
     assert assert_same_tree(str(tmp_path), name) == 1
 
 
+@pytest.mark.parametrize("tile_n", [0, 128])
+@pytest.mark.parametrize("name,extra", dc.TRIANGLE_BIG_CASES)
+def test_ld_triangle_320_variants_through_the_tensor_core_engine(data, ctx, tmp_path, name, extra, tile_n):
+    """320 variants >= the 256 from which LDX_ENGINE_AUTO takes the tcgen05 engine: VCF -> store -> all-pairs kernel (64-wide
+    tiles by default, 128-wide forced) -> settlement -> text kernel -> .tsv, byte for byte the UNMODIFIED reference driver's
+    file (ld_triangle.py:133-230, :351-360)."""
+    from ld_tools_b200 import drivers
+    from ld_tools_b200._lib import TUNE_MMA_TILE_N
+    root, intgen, srcs = data
+    kw = parse(extra, "triangle")
+    kw.pop("matrix_type")
+    launches0 = ctx.launch_count
+    timing0 = ctx.kernel_timing(True)
+    ctx.set_tuning(TUNE_MMA_TILE_N, tile_n)
+    try:
+        drivers.ld_triangle(srcs["triangle_big"], intgen, trg_top_dir_path=str(tmp_path), ctx=ctx, **kw)
+    finally:
+        ctx.set_tuning(TUNE_MMA_TILE_N, 0)
+    ms, n_allpairs = ctx.kernel_timing(False)
+    assert n_allpairs >= 1 and ctx.launch_count > launches0
+    assert assert_same_tree(str(tmp_path), name) == 1
+
+
+def _pool_worker(args):
+    """Runs in a forked multiprocessing.Pool worker: the drop-in calc_ld creates its context lazily, after the fork."""
+    import os
+    from ld_tools_b200 import calc_ld
+    g1, g2 = args
+    return os.getpid(), calc_ld(g1, g2)
+
+
+def test_calc_ld_from_forked_pool_workers():
+    """The reference fans out with multiprocessing.Pool (ld_area.py:336-339, ld_triangle.py:406-408; start method fork on
+    Linux): the drop-in calc_ld must work in forked workers whose parent has NOT touched CUDA through libldx -- and, in a
+    parent that has (this test process), in spawned workers.  Results equal the oracle's, object for object."""
+    import multiprocessing as mp
+    import subprocess
+    import numpy as np
+    from oracle import calc_ld_port
+    rng = np.random.default_rng(5)
+    jobs = []
+    for _ in range(12):
+        n = int(rng.integers(2, 400))
+        jobs.append((list(map(int, rng.integers(0, 2, n))), list(map(int, rng.integers(0, 2, n)))))
+    jobs.append(([0, 1, None, 1], [1, 1, 0, None]))
+    want = [calc_ld_port.calc_ld(a, b) for a, b in jobs]
+    # (1) a fresh parent that forks before anything initialises CUDA: exactly the reference's situation
+    code = ("import sys, json, multiprocessing as mp\n"
+            "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import test_drivers_gpu as t\n"
+            "jobs = json.loads(sys.stdin.read())\n"
+            "with mp.get_context('fork').Pool(2) as pool:\n"
+            "    out = pool.map(t._pool_worker, [tuple(j) for j in jobs])\n"
+            "print(json.dumps([[p, [[k, repr(v)] for k, v in d.items()]] for p, d in out]))\n") % (os.path.dirname(HERE), HERE)
+    r = subprocess.run([sys.executable, "-c", code], input=json.dumps(jobs), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = json.loads(r.stdout.strip().splitlines()[-1])
+    assert len({p for p, _ in got}) >= 1 and os.getpid() not in {p for p, _ in got}
+    for (_, d), w in zip(got, want):
+        assert d == [[k, repr(v)] for k, v in w.items()]
+    # (2) spawned workers of a parent that already holds a CUDA context
+    with mp.get_context("spawn").Pool(2) as pool:
+        out = pool.map(_pool_worker, jobs)
+    for (_, d), w in zip(out, want):
+        assert list(d) == list(w) and all(type(d[k]) is type(w[k]) and d[k] == w[k] for k in w)
+
+
 @pytest.mark.parametrize("name,extra", dc.LITE_CASES)
 def test_ld_lite_printout_identical(data, ctx, name, extra):
     from ld_tools_b200 import drivers

@@ -7,7 +7,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libldx.so")
+# LDX_LIB: another build of the same ABI (A/B timing of kernel variants); the default is the in-tree library
+LIB_PATH = os.environ.get("LDX_LIB") or os.path.join(_HERE, "lib", "libldx.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_EMPTY, ERR_CAPACITY, ERR_STATE, ERR_DATA = 0, -1, -2, -3, -4, -5, -6, -7
 MEASURE_R2, MEASURE_DPRIME = 0, 1

@@ -397,6 +397,13 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 // 3 first epilogue done, 4 all roles done, 5 SM id, 6/7 settlement barrier reached / passed; trace[2048 + 2 * cta]: settled)
 #define LDX_CTA_STAMP(k) do { if (TRACE && A.trace && blockIdx.x < 192) A.trace[512 + 8 * blockIdx.x + (k)] = gtime(); } while (0)
 
+// Measured alternatives to this split (A/B runs of library builds on one box, tools/gpu_call_ab.sh; 32,768 variants, this
+// build 1.82-1.85 ms): three widener teams + twelve epilogue warps at 96 registers 2.23 ms (three teams no longer keep the
+// tensor pipe fed, although ncu shows the sixteen wideners waiting for more than half of their time and the eight epilogue
+// warps busy for 95% of theirs, profiles/r02_ncu_source_pair_v16384.txt); deferred-pair entries that carry the true counts
+// (no frequency loads in the settlement) 1.98 ms; the epilogue as a loop over 16 x 32 work units with the row counts
+// prefetched 1.89-2.01 ms.  The epilogue loop is latency-bound and at the edge of the instruction cache: small changes in
+// code layout move it by 5-10%.
 constexpr int N_WIDEN_WARPS = 16, N_EPI_WARPS = 8;  // wideners: four teams of 4 warps, team k takes pipeline stages g = k mod 4
 constexpr int WIDEN_TEAMS = 4, TEAM_WARPS = N_WIDEN_WARPS / WIDEN_TEAMS;
 // Warp roles, aligned to warpgroups (4 warps) so that setmaxnreg can move registers between them:

@@ -115,9 +115,11 @@ class ChromData:
         self.n_variants, self.n_samples = len(self.pos), len(self.samples)
         self.max_ref_len = int((self.end0 - self.pos0).max()) if self.n_variants else 1
         self.col_of = {n: i for i, n in enumerate(self.samples)}
-        self._row_of = {}
-        for k, (p, i) in enumerate(zip(self.pos.tolist(), self.ids)):
-            self._row_of.setdefault((p, i), k)            # first record wins, as the drivers' `break` does
+        # (pos, id) -> row is resolved on demand (row_of): a position lookup plus an ID comparison of the few records at that
+        # position, so that a chromosome with millions of rows costs nothing up front.  Needs ascending positions (every tabix-
+        # indexed VCF has them); a file without gets the exhaustive map.
+        self._sorted = bool(self.n_variants < 2 or (np.diff(self.pos) >= 0).all())
+        self._row_map = None
 
     # ---- cache
     @staticmethod
@@ -151,8 +153,10 @@ class ChromData:
         store_path, meta_path = self._cache_paths(vcf_path)
         try:
             st = os.stat(vcf_path)
-            self.store.save(store_path)
-            tmp = meta_path + ".tmp.npz"
+            tmp_store = store_path + f".tmp{os.getpid()}"
+            self.store.save(tmp_store)
+            os.replace(tmp_store, store_path)                # readers see the old file or the whole new one, never half of it
+            tmp = meta_path + f".tmp{os.getpid()}.npz"
             np.savez(tmp, source=np.array([self.CACHE_VERSION, st.st_size, st.st_mtime_ns], dtype=np.int64),
                      samples=np.frombuffer("\n".join(self.samples).encode(), dtype=np.uint8),
                      rows=np.frombuffer(self.rows.tobytes(), dtype=np.uint8), blob=np.frombuffer(self._blob, dtype=np.uint8),
@@ -205,7 +209,20 @@ class ChromData:
         self.n1, self.p_e4, self.n_hap_sel = self.store.counts()
 
     def row_of(self, pos, rs_id):
-        return self._row_of[(int(pos), rs_id)]
+        """Store row of the first record with this position and ID (the drivers `break` at the first match, ld_area.py:150-159)."""
+        pos = int(pos)
+        if self._sorted:
+            k = int(np.searchsorted(self.pos, pos, side="left"))
+            while k < self.n_variants and self.pos[k] == pos:
+                if self.ids[k] == rs_id:
+                    return k
+                k += 1
+            raise KeyError((pos, rs_id))
+        if self._row_map is None:
+            self._row_map = {}
+            for k, (p, i) in enumerate(zip(self.pos.tolist(), self.ids)):
+                self._row_map.setdefault((p, i), k)
+        return self._row_map[(pos, rs_id)]
 
     def close(self):
         self.store.close()
@@ -370,7 +387,7 @@ def ld_lite(rs_id_1, rs_id_2, intgen_dir_path, gend_names="both", pop_names="all
         first_alt = lambda r: cd.alts[r].split(",")[0]                        # noqa: E731  (intgen_rec.alts[0], :116)
         return tabulate([["chrom", chrom, chrom], ["hg38_pos", pos1, pos2],
                          ["alleles", cd.refs[r1] + "/" + first_alt(r1), cd.refs[r2] + "/" + first_alt(r2)],
-                         ["type", cd.vts[r1], cd.vts[r2]],
+                         ["type", cd.vts[r1].split(",")[0], cd.vts[r2].split(",")[0]],      # intgen_rec.info['VT'][0], ld_lite.py:118,131
                          ["alt_freq", cd.p_e4[r1] / 10000.0, cd.p_e4[r2] / 10000.0]],
                         headers=[tabulate([["r2", r2_value(w)], ["D'", dprime_value(w)], ["abs_dist", abs(pos1 - pos2)]],
                                           tablefmt="fancy_grid", disable_numparse=True),

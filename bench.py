@@ -22,7 +22,8 @@ Printed JSON (one line, rank 0):
   steady_state  the same kernel on a 32,768-variant set (221 tiles per SM instead of one)
   ld_area       BASELINE configs[2] through the window kernel (1,000 queries, +/-500 kb, r2 >= 0.8, EUR subset store)
   sharded       north_star (3) at this N: configs[3] (100,000-variant triangle, row-range sharded, strong scaling) and
-                configs[2] region-sharded with halos, the kept pairs gathered over NCCL inside the timed region
+                configs[4] (genome-scale ld_area: 50,000 queries over 80 M variants) region-sharded with halos, the kept pairs
+                gathered over NCCL and sorted on the device inside the timed region
   cpu_baseline  the reference algorithm (pure-Python port, oracle/calc_ld_port.py) on the host cores
 """
 import argparse
@@ -782,72 +783,113 @@ def leg_area(env, subset=True, steps=5, warmup=3):
     return out
 
 
-def leg_sharded_area(env, reps=3):
-    """configs[2] region-sharded (north_star (3)): slabs balanced by candidate pairs, each rank holding its slab plus the halo its
-    queries' windows reach; the kept pairs are gathered with NCCL (shard.gather_hits) inside the timed region.  Strong scaling."""
+# GRCh38 autosome lengths (Mb), chr1..chr22
+CHR_MB = [248.96, 242.19, 198.30, 190.21, 181.54, 170.81, 159.35, 145.14, 138.39, 133.80, 135.09,
+          133.28, 114.36, 107.04, 101.99, 90.34, 83.26, 80.37, 58.62, 64.44, 46.71, 50.82]
+
+
+def leg_sharded_genome(env, n_variants=80_000_000, n_queries=50_000, flank=1_000_000, reps=3, check=3):
+    """BASELINE configs[4] (north_star (3)): genome-scale ld_area, region-sharded.  The genome-wide query list, ordered by
+    (chromosome, position), is cut into `world` pieces with equal candidate-pair counts (shard.genome_pieces); a rank holds,
+    per chromosome it touches, only the rows its queries' windows reach (slab + halo) and makes one ldx_window_dev call per
+    piece.  The kept pairs are re-numbered job-wide ON THE DEVICE, gathered with NCCL (shard.gather_hits_tensor: counts,
+    padded records) and sorted by (query, row) on the device -- all inside the timed region.  Strong scaling."""
     torch, ctx, stream, dev = env.torch, env.ctx, env.stream, env.dev
-    from ld_tools_b200 import shard
+    from ld_tools_b200 import Store, shard
     from ld_tools_b200._lib import BELOW_THRES, HIT_DTYPE
     from ld_tools_b200.engine import threshold_e4
-    job = area_job()
-    slab = shard.area_slabs(job["pos0"], 1, job["q_row"], job["pos0"][job["q_row"]].astype(np.int64) + 1, AREA_FLANK, env.world)[env.rank]
-    rb, re = slab["row_begin"], slab["row_end"]
-    st = build_area_store(env, job, rb, max(re, rb + 1))
-    idx = slab["queries"]
-    q, lo, hi = shard.rebase_queries(slab, job["q_row"], job["lo"], job["hi"])
-    ws, we = job["ws"][idx], job["we"][idx]
+    from ld_tools_b200.synth import fill_store_grouped
     thres = threshold_e4(0.8)
-    cap = 64 * max(len(idx), 1) + 65536
-    d_hits = torch.empty(cap * 4, dtype=torch.int32, device=dev)
-    d_cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    tot_mb = sum(CHR_MB)
+    chroms = []
+    for c, mb in enumerate(CHR_MB):              # the job, identically on every rank
+        nv = int(round(n_variants * mb / tot_mb))
+        nq = max(1, int(round(n_queries * mb / tot_mb)))
+        rng = np.random.default_rng(9000 + c)
+        pos0 = np.sort(rng.integers(10_000, int(mb * 1e6), size=nv, dtype=np.int64)).astype(np.int32)
+        q_row = np.sort(rng.choice(nv, nq, replace=False)).astype(np.int64)
+        lo, hi, ws, we = shard.window_bounds(pos0, 1, pos0[q_row].astype(np.int64) + 1, flank)
+        chroms.append({"nv": nv, "pos0": pos0, "q_row": q_row, "lo": lo, "hi": hi, "ws": ws, "we": we})
+    q_first = np.concatenate([[0], np.cumsum([len(ch["q_row"]) for ch in chroms])])
+    t_build = time.perf_counter()
+    pieces, store_bytes, cap_total = [], 0, 0
+    for pc in shard.genome_pieces(chroms, env.world)[env.rank]:
+        c, qa, qb, rb, re = pc["chrom"], pc["qa"], pc["qb"], pc["row_begin"], pc["row_end"]
+        ch = chroms[c]
+        st = Store(ctx, re - rb, N_HAP)
+        fill_store_grouped(st, dev, c, rb, re)
+        pos0 = ch["pos0"][rb:re]
+        st.set_annotations(pos0, pos0 + 1, (np.int64(c) << 32) + np.arange(rb, re, dtype=np.int64), np.ones(re - rb, np.uint8))
+        st.set_mask(full_mask(st.stride_words))
+        cap = 64 * (qb - qa) + 65536
+        pieces.append({"chrom": c, "st": st, "rb": rb, "qa": qa, "qb": qb, "cap": cap, "off": cap_total,
+                       "q": ch["q_row"][qa:qb] - rb, "lo": ch["lo"][qa:qb] - rb, "hi": ch["hi"][qa:qb] - rb, "ws": ch["ws"][qa:qb], "we": ch["we"][qa:qb]})
+        cap_total += cap
+        store_bytes += (re - rb) * st.stride_words * 8
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t_build
+    d_hits = torch.empty((max(cap_total, 1), 4), dtype=torch.int32, device=dev)
+    d_cnt = torch.zeros((max(len(pieces), 1), 2), dtype=torch.int64, device=dev)
 
-    def job_once():
-        if len(idx):
-            st.window_dev(q, lo, hi, ws, we, "r_square", thres, d_hits.data_ptr(), cap, d_cnt.data_ptr())
-            ctx.resolve()
-            n_found = int(d_cnt[0].item())
-            h = d_hits[:4 * min(n_found, cap)].cpu().numpy().view(HIT_DTYPE)
-            h = h[(h["packed"] & BELOW_THRES) == 0]
-        else:
-            h = np.zeros(0, dtype=HIT_DTYPE)
-        t_g = time.perf_counter()
-        allh = shard.gather_hits(shard.globalise_hits(h, slab), device=dev) if env.world > 1 else h[np.lexsort((h["row"], h["query"]))]
-        return h, allh, time.perf_counter() - t_g
-    job_once()
-    times, scan_ms, gathers = [], [], []
+    def job():
+        for k, p in enumerate(pieces):
+            p["st"].window_dev(p["q"], p["lo"], p["hi"], p["ws"], p["we"], "r_square", thres, d_hits[p["off"]:].data_ptr(), p["cap"], d_cnt[k].data_ptr())
+        ctx.resolve()                                            # near-tie pairs settled (hits the exact rounding rejects get BELOW_THRES)
+        g0 = env.event()
+        g0.record(stream)
+        counts = d_cnt[:, 0].tolist() if pieces else []
+        parts = []
+        for k, p in enumerate(pieces):                           # job-wide numbering, on the device
+            h = d_hits[p["off"]:p["off"] + min(int(counts[k]), p["cap"])]
+            h = h[(h[:, 3] & BELOW_THRES) == 0]
+            h = h + torch.tensor([p["qa"] + int(q_first[p["chrom"]]), p["rb"], 0, 0], dtype=torch.int32, device=dev)
+            parts.append(h)
+        mine = torch.cat(parts) if parts else torch.zeros((0, 4), dtype=torch.int32, device=dev)
+        allh = shard.gather_hits_tensor(mine)
+        return mine, allh, g0
+    job()
+    times, gathers = [], []
     for _ in range(reps):
         env.barrier()
         e0, e1 = env.event(), env.event()
-        t0 = time.perf_counter()
         e0.record(stream)
-        local_hits, allh, g_s = job_once()
+        mine, allh, g0 = job()
         e1.record(stream)
         env.barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3            # the gather's host side (counts, padding, sort) is part of the job
-        m = env.max_over_ranks([wall_ms, g_s * 1e3])
+        m = env.max_over_ranks([float(e0.elapsed_time(e1)), float(g0.elapsed_time(e1))])
         times.append(m[0]); gathers.append(m[1])
-    scanned = int(d_cnt.cpu()[1]) if len(idx) else 0
-    tot = torch.tensor([scanned], dtype=torch.int64, device=dev)
+    scanned = int(d_cnt[:, 1].sum().item()) if pieces else 0
+    overflow = sum(max(0, int(n) - p["cap"]) for n, p in zip(d_cnt[:, 0].tolist(), pieces)) if pieces else 0
+    # parity: whole windows of a few of this rank's queries against numpy popcounts + the oracle's finalisation
+    ok = overflow == 0
+    mine_np = mine.cpu().numpy().reshape(-1).view(HIT_DTYPE)
+    rng = np.random.default_rng(500 + env.rank)
+    for _ in range(check if pieces else 0):
+        p = pieces[int(rng.integers(len(pieces)))]
+        local = mine_np[(mine_np["query"] >= p["qa"] + q_first[p["chrom"]]) & (mine_np["query"] < p["qb"] + q_first[p["chrom"]])].copy()
+        local["query"] -= p["qa"] + q_first[p["chrom"]]
+        local["row"] -= p["rb"]
+        ok &= check_area_queries(p["st"], local, p["q"], p["lo"], p["hi"], thres, 1, rng, N_HAP)
+    ok = env.min_flag(ok)
+    tot = torch.tensor([scanned, store_bytes], dtype=torch.int64, device=dev)
+    per_rank = torch.zeros(env.world, dtype=torch.int64, device=dev)
+    per_rank[env.rank] = scanned
     if env.world > 1:
         env.dist.all_reduce(tot)
-    ok = True
-    if len(idx):
-        ok = check_area_queries(st, local_hits, q, lo, hi, thres, 2, np.random.default_rng(900 + env.rank), st.n_hap)
-    ok = env.min_flag(ok)
-    per_rank = [0] * env.world
-    per_rank[env.rank] = scanned
-    pr = torch.tensor(per_rank, dtype=torch.int64, device=dev)
-    if env.world > 1:
-        env.dist.all_reduce(pr)
+        env.dist.all_reduce(per_rank)
     best = min(times)
-    out = {"workload": "BASELINE configs[2] region-sharded: " + AREA_WORKLOAD, "scaling": "strong", "ms": best, "ms_all": [round(x, 3) for x in times],
-           "value": int(tot.item()) / (best * 1e-3), "unit": "pairs/s", "pairs_scanned": int(tot.item()), "pairs_per_rank": pr.tolist(),
-           "kept_pairs": int(allh.shape[0]), "gather_hits_ms": min(gathers),
-           "collective": "NCCL all_gather of the kept-pair counts and of the padded 16-byte records (shard.gather_hits), inside the timed region",
-           "timed": "host wall clock around window scan + D2H of the rank's hits + gather, max over ranks (the gather ends on the host)",
-           "store_rows_of_rank0": [int(rb), int(re)], "parity_windows_ok": ok}
+    out = {"workload": f"BASELINE configs[4]: genome-scale ld_area, {sum(len(ch['q_row']) for ch in chroms)} queries over synthetic chr1-22 "
+                       f"({sum(ch['nv'] for ch in chroms)} variants x {N_HAP} haplotypes), +/-{flank} bp, r2 >= 0.8, region-sharded with halos",
+           "scaling": "strong", "ms": best, "ms_all": [round(x, 3) for x in times], "value": int(tot[0].item()) / (best * 1e-3), "unit": "pairs/s",
+           "pairs_scanned": int(tot[0].item()), "pairs_per_rank": per_rank.tolist(), "kept_pairs": int(allh.shape[0]),
+           "gather_ms": min(gathers), "store_GB_total": round(int(tot[1].item()) / 1e9, 2), "build_s": build_s,
+           "collective": "NCCL all_gather of the kept-pair counts and of the padded 16-byte records (shard.gather_hits_tensor), device sort by (query, row); "
+                         "inside the timed region, reported separately as gather_ms (renumbering + collective + sort)",
+           "timed": "CUDA events on the launching stream around window scans + ldx_resolve + renumbering + gather + sort, max over ranks",
+           "parity_windows_ok": ok}
+    for p in pieces:
+        p["st"].close()
     del d_hits
-    st.close()
     return out
 
 
@@ -866,7 +908,7 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_area:
         legs["ld_area"] = leg_area(env)
     if not args.no_sharded:
-        legs["sharded"] = {"n_gpus": world, "triangle_configs3": leg_sharded_triangle(env), "ld_area_configs2": leg_sharded_area(env)}
+        legs["sharded"] = {"n_gpus": world, "triangle_configs3": leg_sharded_triangle(env), "ld_area_genome_configs4": leg_sharded_genome(env)}
     line = {"metric": METRIC, "value": tri["value"], "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tri["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -924,7 +966,7 @@ def main():
     ap.add_argument("--no-steady", action="store_true", help="skip the 32,768-variant steady-state leg")
     ap.add_argument("--no-batched", action="store_true", help="skip the batched leg")
     ap.add_argument("--no-area", action="store_true", help="skip the ld_area (configs[2]) leg")
-    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded legs (configs[3] row ranges, configs[2] regions)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded legs (configs[3] row ranges, configs[4] regions)")
     ap.add_argument("--area-full-store", action="store_true", help="--workload ld_area: scan the 640-byte rows under a mask instead of the subset store")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -189,3 +189,29 @@ def gather_hits(hits, group=None, device=None):
     rec = [p[:c].cpu().numpy().reshape(-1).view(HIT_DTYPE) for p, c in zip(parts, counts) if c]
     allh = np.concatenate(rec) if rec else np.zeros(0, dtype=HIT_DTYPE)
     return allh[np.lexsort((allh["row"], allh["query"]))]
+
+
+def gather_hits_tensor(local, group=None):
+    """The same collective with the records left where they are: `local` is an int32 tensor [n, 4] (ldx_hit records as
+    {query, row, n11, packed}) on the rank's CUDA device (NCCL) or on the CPU (gloo); returns every rank's records
+    concatenated and sorted by (query, row) as a tensor on the same device.  One all_gather of the counts, one of the
+    records padded to the longest list, one device sort: nothing but the counts crosses to the host."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    local = local.reshape(-1, 4).contiguous()
+    if world > 1:
+        n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        counts = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(counts, n, group=group)
+        counts = torch.cat(counts).tolist()                    # the one host synchronisation of the gather
+        cap = max(max(counts), 1)
+        buf = torch.zeros((cap, 4), dtype=torch.int32, device=local.device)
+        buf[:local.shape[0]] = local
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf, group=group)
+        allh = torch.cat([p[:c] for p, c in zip(parts, counts)])
+    else:
+        allh = local
+    key = (allh[:, 0].to(torch.int64) << 32) | allh[:, 1].to(torch.int64)
+    return allh[torch.argsort(key)]

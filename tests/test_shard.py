@@ -178,6 +178,12 @@ def _gloo_worker(rank, world, port, tmpdir):
     mine = rank_hits(job, slabs[rank])
     allh = shard.gather_hits(mine)
     np.save(os.path.join(tmpdir, f"hits_{rank}.npy"), allh)
+    # the tensor form of the same collective (what bench.py times on NCCL): records stay tensors, sorted by (query, row)
+    import torch
+    from ld_tools_b200._lib import HIT_DTYPE
+    local = torch.from_numpy(np.ascontiguousarray(mine).view(np.int32).reshape(-1, 4).copy())      # rank_hits: already job-wide numbering
+    ten = shard.gather_hits_tensor(local).numpy().reshape(-1).view(HIT_DTYPE)
+    np.save(os.path.join(tmpdir, f"hits_tensor_{rank}.npy"), ten)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -196,3 +202,4 @@ def test_gather_hits_world2_gloo(tmp_path):
     for rank in range(2):
         got = np.load(os.path.join(str(tmp_path), f"hits_{rank}.npy"))
         assert (got == want).all()
+        assert (np.load(os.path.join(str(tmp_path), f"hits_tensor_{rank}.npy")) == want).all()

@@ -124,6 +124,10 @@ int32_t ldx_debug_trace(ldx_ctx *ctx, int32_t enable, uint64_t *stamps8);
  * recorded event. */
 int32_t ldx_kernel_timing(ldx_ctx *ctx, int32_t enable, double *ms_out, int64_t *launches_out);
 int32_t ldx_sm_count(ldx_ctx *ctx, int32_t *n_out);
+/* Device memory for the outputs of the *_dev entry points, for callers that have no CUDA allocator of their own (the drivers
+ * of ld_tools_b200/drivers.py: packed words of a batch of matrices that only ldx_triangle_text reads).  256-byte aligned. */
+int32_t ldx_dev_alloc(ldx_ctx *ctx, int64_t bytes, void **dev_ptr_out);
+int32_t ldx_dev_free(ldx_ctx *ctx, void *dev_ptr);
 /* Kernels launched by this ctx since creation (bench.py's gpu_launches claim). */
 int32_t ldx_launch_count(ldx_ctx *ctx, int64_t *n_out);
 
@@ -323,6 +327,22 @@ int32_t ldx_triangle_table(ldx_store *store, const int64_t *rows, int64_t v, int
                            int32_t measure, int32_t has_thres, int32_t thres_e4, int32_t engine,
                            const char *prefixes, const int64_t *prefix_off, int32_t flags,
                            char *text, int64_t cap, int64_t *n_bytes);
+/* ---------------------------------------------------------------- ld_area rows
+ * Replaces the per-hit writer of ld_area.py:252-283 for all queries of a window scan at once.  hits[n_hits] as ldx_window
+ * returned them (sorted by (query, row)); q_row[nq] = the queries' store rows (the dist column, :272); blob / blob_off / rows =
+ * the records' fixed columns and field offsets (ldx_vcf_copy_prefixes, ldx_store_ingest_vcf; n_rows of them); the alt_freq
+ * column is p_e4[row] (ldx_store_counts: var_2_alt_freq of calc_ld.py:97 for complete genotypes) unless alt_e4_of_hit[n_hits]
+ * gives it per hit.  Host code, `threads` host threads (<= 0: all cores).  Query k's text is out[query_off[k], query_off[k+1])
+ * (query_off has nq + 1 entries; *n_bytes = query_off[nq]; LDX_ERR_CAPACITY with the size needed when cap is too small):
+ *   LDX_AREA_TSV    one line per hit: pos, rsID, ref, alt, type, alt_freq, r2, D', dist joined by tabs (str() of each, :264-274)
+ *   LDX_AREA_JSON   per hit the element json.dump(trg_obj, fh, indent=4) writes (:275-283) preceded by its ",\n    " separator:
+ *                   the caller writes json.dumps([meta, query], indent=4)[:-2], the chunk, then "\n]"
+ *   LDX_AREA_RSIDS  one rsID per line (:258-260) */
+enum { LDX_AREA_TSV = 0, LDX_AREA_JSON = 1, LDX_AREA_RSIDS = 2 };
+int32_t ldx_area_format(const ldx_hit *hits, int64_t n_hits, const int64_t *q_row, int64_t nq, const uint8_t *blob,
+                        const int64_t *blob_off, const ldx_vcf_row *rows, int64_t n_rows, const int32_t *p_e4,
+                        const int32_t *alt_e4_of_hit, int32_t format, int32_t threads, char *out, int64_t cap,
+                        int64_t *n_bytes, int64_t *query_off);
 /* Host helper (no device needed): str(value_e4 / 10000.0) for 0 <= value_e4 < 20000 as the kernels print it,
  * NUL-padded to 8 bytes -- the same digit arithmetic, exposed so that it can be checked against Python's str(). */
 int32_t ldx_format_e4(int32_t value_e4, char *out8);

@@ -15,6 +15,7 @@ MEASURE_R2, MEASURE_DPRIME = 0, 1
 ENGINE_AUTO, ENGINE_POPC, ENGINE_MMA = 0, 1, 2
 TUNE_MMA_TILE_N, TUNE_MMA_MIN_V, TUNE_MMA_PAIR, TUNE_DEFER_CAP, TUNE_WINDOW_MQ, TUNE_MMA_DIRECT = 1, 2, 3, 4, 5, 6
 TEXT_PACKED_ON_DEVICE, TEXT_OUT_ON_DEVICE = 1, 2
+AREA_TSV, AREA_JSON, AREA_RSIDS = 0, 1, 2
 R2_MASK, R2_INT0, DP_SHIFT, DP_MASK, BELOW_THRES, DP_INT0 = 0x3FFF, 0x8000, 16, 0x3FFF0000, 0x40000000, 0x80000000
 
 HIT_DTYPE = np.dtype([("query", "<i4"), ("row", "<i4"), ("n11", "<i4"), ("packed", "<u4")])
@@ -52,6 +53,8 @@ SIGNATURES = {
     "ldx_set_tuning": [_vp, _i32, _i32],
     "ldx_kernel_timing": [_vp, _i32, _P(C.c_double), _P(_i64)],
     "ldx_sm_count": [_vp, _P(_i32)],
+    "ldx_dev_alloc": [_vp, _i64, _P(_vp)],
+    "ldx_dev_free": [_vp, _vp],
     "ldx_launch_count": [_vp, _P(_i64)],
     "ldx_calc_ld_lists": [_vp, _vp, _i64, _vp, _i64, _vp],
     "ldx_finalise_counts": [_vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
@@ -84,6 +87,7 @@ SIGNATURES = {
     "ldx_triangle_text": [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _i32, _vp, _i64, _P(_i64)],
     "ldx_triangle_table": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _P(_i64)],
     "ldx_format_e4": [_i32, _vp],
+    "ldx_area_format": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _P(_i64), _vp],
 }
 
 _lib = None

@@ -255,6 +255,26 @@ extern "C" int32_t ldx_sm_count(ldx_ctx *ctx, int32_t *n_out) {
     return LDX_OK;
 }
 
+extern "C" int32_t ldx_dev_alloc(ldx_ctx *ctx, int64_t bytes, void **dev_ptr_out) {
+    LDX_REQUIRE(ctx && dev_ptr_out && bytes >= 0, "bad argument");
+    *dev_ptr_out = nullptr;
+    LDX_CUDA(cudaSetDevice(ctx->device));
+    if (cudaMalloc(dev_ptr_out, (size_t)std::max<int64_t>(bytes, 256)) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(LDX_ERR_NOMEM, "device allocation failed");
+    }
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_dev_free(ldx_ctx *ctx, void *dev_ptr) {
+    LDX_REQUIRE(ctx, "ctx is NULL");
+    if (!dev_ptr) return LDX_OK;
+    LDX_CUDA(cudaSetDevice(ctx->device));
+    LDX_CUDA(cudaStreamSynchronize(ctx->stream));          // enqueued kernels may still write it
+    LDX_CUDA(cudaFree(dev_ptr));
+    return LDX_OK;
+}
+
 extern "C" int32_t ldx_launch_count(ldx_ctx *ctx, int64_t *n_out) {
     LDX_REQUIRE(ctx && n_out, "NULL argument");
     *n_out = ctx->launches;

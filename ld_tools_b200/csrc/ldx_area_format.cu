@@ -1,0 +1,192 @@
+// ldx_area_format.cu -- the ld_area writers at scale (second half).
+//
+// Replaces the per-hit Python of ld_area.py:252-283: for every kept (query, opposing variant) pair one line
+// of `'\t'.join(map(str, oppos_var_ann))` (:273-274), one element of the JSON list json.dump(..., indent=4) writes
+// (:275-283), or one rsID line (:258-260).  Host code (the records' text columns live on the host; the GPU's part of the
+// job -- the window scan -- already returned 16 bytes per kept pair): every query's rows are formatted by one of `threads`
+// host threads straight into its place in the caller's buffer, after a sizing pass of the same code over a counting sink.
+// At -z 0 configs[2] emits ~3 x 10^7 rows; the Python loop it replaces (four text slices and a list per hit) ran at
+// ~3 x 10^5 rows/s.
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "ldx_internal.h"
+
+#define LDX_REQUIRE(cond, msg) do { if (!(cond)) return ldx::set_error(LDX_ERR_ARG, msg); } while (0)
+
+namespace {
+
+struct CountSink {
+    int64_t n = 0;
+    void put(const char *, size_t len) { n += (int64_t)len; }
+    void ch(char) { ++n; }
+};
+struct WriteSink {
+    char *p;
+    void put(const char *s, size_t len) { std::memcpy(p, s, len); p += len; }
+    void ch(char c) { *p++ = c; }
+};
+
+// str(int) for the positions and distances
+template <class S> void put_int(S &s, int64_t v) {
+    char buf[24];
+    int n = 0;
+    const bool neg = v < 0;
+    uint64_t u = neg ? (uint64_t)(-(v + 1)) + 1 : (uint64_t)v;
+    do { buf[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (neg) buf[n++] = '-';
+    while (n) s.ch(buf[--n]);
+}
+
+// str(k / 10000.0): the digit arithmetic of ldx_format_e4 (csrc/ldx_format.cu), NUL-padded to 8 bytes
+template <class S> void put_e4(S &s, int32_t e4) {
+    char b[8];
+    ldx_format_e4(e4, b);
+    s.put(b, strnlen(b, 8));
+}
+
+// the rounded measure as Python prints the object calc_ld returned: the int 0 or a float (calc_ld.py:68-69, :89-90, :94-95)
+template <class S> void put_r2(S &s, uint32_t w) { if (w & LDX_R2_INT0) s.ch('0'); else put_e4(s, (int32_t)(w & LDX_R2_MASK)); }
+template <class S> void put_dp(S &s, uint32_t w) { if (w & LDX_DP_INT0) s.ch('0'); else put_e4(s, (int32_t)((w & LDX_DP_MASK) >> LDX_DP_SHIFT)); }
+
+struct Field { const char *p; size_t n; };
+
+#define PUT_LIT(sink, lit) (sink).put(lit, sizeof(lit) - 1)
+
+// json.dumps of a str (ensure_ascii=True): quotes, backslash, control characters, non-ASCII as \uXXXX (UTF-8 decoded)
+template <class S> void put_json_str(S &s, Field f) {
+    static const char hex[] = "0123456789abcdef";
+    auto u16 = [&](uint32_t x) { const char u[6] = {'\\', 'u', hex[(x >> 12) & 15], hex[(x >> 8) & 15], hex[(x >> 4) & 15], hex[x & 15]}; s.put(u, 6); };
+    s.ch('"');
+    for (size_t i = 0; i < f.n; ++i) {
+        const unsigned char c = (unsigned char)f.p[i];
+        if (c == '"') PUT_LIT(s, "\\\"");
+        else if (c == '\\') PUT_LIT(s, "\\\\");
+        else if (c == '\n') PUT_LIT(s, "\\n");
+        else if (c == '\r') PUT_LIT(s, "\\r");
+        else if (c == '\t') PUT_LIT(s, "\\t");
+        else if (c == '\b') PUT_LIT(s, "\\b");
+        else if (c == '\f') PUT_LIT(s, "\\f");
+        else if (c < 0x20) u16(c);
+        else if (c < 0x80) s.ch((char)c);                         // DEL included: json.dumps prints it as is
+        else {
+            uint32_t cp = 0xfffd;                                 // a malformed sequence: what errors='replace' would give
+            const int extra = c >= 0xf0 ? 3 : c >= 0xe0 ? 2 : c >= 0xc0 ? 1 : 0;
+            if (extra > 0 && i + (size_t)extra < f.n) {
+                cp = c & (0x3f >> extra);
+                for (int k = 1; k <= extra; ++k) cp = (cp << 6) | ((unsigned char)f.p[i + (size_t)k] & 0x3f);
+                i += (size_t)extra;
+            }
+            if (cp >= 0x10000) { cp -= 0x10000; u16(0xd800 + (cp >> 10)); u16(0xdc00 + (cp & 0x3ff)); }
+            else u16(cp);
+        }
+    }
+    s.ch('"');
+}
+
+struct Table {
+    const uint8_t *blob; const int64_t *off; const ldx_vcf_row *rows; const int32_t *p_e4;
+    Field col(int64_t r, int32_t field_off) const {               // a fixed column: from its offset to the next tab
+        const char *rec = reinterpret_cast<const char *>(blob + off[r]);
+        const size_t len = (size_t)(off[r + 1] - off[r]);
+        size_t a = (size_t)field_off, b = a;
+        while (b < len && rec[b] != '\t') ++b;
+        return Field{rec + a, b - a};
+    }
+    Field vt(int64_t r) const {                                   // ','.join(rec.info['VT']): the VT key of INFO, verbatim
+        const Field info = col(r, rows[r].info_off);
+        size_t i = 0;
+        while (i < info.n) {
+            size_t e = i;
+            while (e < info.n && info.p[e] != ';') ++e;
+            if (e - i >= 3 && info.p[i] == 'V' && info.p[i + 1] == 'T' && info.p[i + 2] == '=') return Field{info.p + i + 3, e - i - 3};
+            i = e + 1;
+        }
+        return Field{info.p, 0};
+    }
+};
+
+template <class S> void format_hit(S &s, const Table &T, const ldx_hit &h, int64_t qrow, int32_t alt_e4, int format) {
+    const int64_t r = h.row;
+    const Field id = T.col(r, T.rows[r].id_off);
+    if (format == LDX_AREA_RSIDS) { s.put(id.p, id.n); s.ch('\n'); return; }                      // ld_area.py:258-260
+    const Field ref = T.col(r, T.rows[r].ref_off), alt = T.col(r, T.rows[r].alt_off), vt = T.vt(r);
+    const int64_t pos = T.rows[r].pos, dist = (int64_t)T.rows[r].pos - (int64_t)T.rows[qrow].pos;   // :272
+    if (format == LDX_AREA_TSV) {                                                                  // :264-274
+        put_int(s, pos); s.ch('\t'); s.put(id.p, id.n); s.ch('\t'); s.put(ref.p, ref.n); s.ch('\t'); s.put(alt.p, alt.n); s.ch('\t');
+        s.put(vt.p, vt.n); s.ch('\t'); put_e4(s, alt_e4); s.ch('\t'); put_r2(s, h.packed); s.ch('\t'); put_dp(s, h.packed); s.ch('\t');
+        put_int(s, dist); s.ch('\n');
+        return;
+    }
+    // one element of the list json.dump(trg_obj, ..., indent=4) writes (:275-283), with the separator that precedes it
+    PUT_LIT(s, ",\n    {\n        \"hg38_pos\": "); put_int(s, pos);
+    PUT_LIT(s, ",\n        \"rsID\": "); put_json_str(s, id);
+    PUT_LIT(s, ",\n        \"ref\": "); put_json_str(s, ref);
+    PUT_LIT(s, ",\n        \"alt\": "); put_json_str(s, alt);
+    PUT_LIT(s, ",\n        \"type\": "); put_json_str(s, vt);
+    PUT_LIT(s, ",\n        \"alt_freq\": "); put_e4(s, alt_e4);
+    PUT_LIT(s, ",\n        \"r2\": "); put_r2(s, h.packed);
+    PUT_LIT(s, ",\n        \"D'\": "); put_dp(s, h.packed);
+    PUT_LIT(s, ",\n        \"dist\": "); put_int(s, dist);
+    PUT_LIT(s, "\n    }");
+}
+
+}  // namespace
+
+extern "C" int32_t ldx_area_format(const ldx_hit *hits, int64_t n_hits, const int64_t *q_row, int64_t nq, const uint8_t *blob,
+                                   const int64_t *blob_off, const ldx_vcf_row *rows, int64_t n_rows, const int32_t *p_e4,
+                                   const int32_t *alt_e4_of_hit, int32_t format, int32_t threads, char *out, int64_t cap,
+                                   int64_t *n_bytes, int64_t *query_off) {
+    LDX_REQUIRE(n_bytes && query_off && q_row && blob && blob_off && rows && (p_e4 || alt_e4_of_hit), "NULL argument");
+    LDX_REQUIRE(n_hits >= 0 && nq >= 0 && n_rows >= 0 && (hits || n_hits == 0) && (out || cap == 0), "bad sizes");
+    LDX_REQUIRE(format == LDX_AREA_TSV || format == LDX_AREA_JSON || format == LDX_AREA_RSIDS, "bad format");
+    *n_bytes = 0;
+    // the hits of query k: [first[k], first[k + 1]) -- they arrive sorted by (query, row)
+    std::vector<int64_t> first((size_t)nq + 1, 0);
+    for (int64_t i = 0; i < n_hits; ++i) {
+        LDX_REQUIRE(hits[i].query >= 0 && hits[i].query < nq && hits[i].row >= 0 && hits[i].row < n_rows, "hit outside the query / row tables");
+        LDX_REQUIRE(i == 0 || hits[i].query >= hits[i - 1].query, "hits must be sorted by query");
+        first[(size_t)hits[i].query + 1]++;
+    }
+    for (int64_t k = 0; k < nq; ++k) {
+        LDX_REQUIRE(q_row[k] >= 0 && q_row[k] < n_rows, "q_row outside the row table");
+        first[(size_t)k + 1] += first[(size_t)k];
+    }
+    const Table T{blob, blob_off, rows, p_e4};
+    const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(threads > 0 ? threads : (int)std::thread::hardware_concurrency(), std::max<int64_t>(1, n_hits / 4096)));
+    auto for_queries = [&](auto &&body) {                         // dynamic chunks of queries over the threads
+        std::atomic<int64_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                const int64_t k0 = next.fetch_add(16);
+                if (k0 >= nq) break;
+                for (int64_t k = k0; k < std::min(nq, k0 + 16); ++k) body(k);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_thr; ++t) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+    };
+    auto alt_of = [&](int64_t i) { return alt_e4_of_hit ? alt_e4_of_hit[i] : p_e4[hits[i].row]; };   // var_2_alt_freq, calc_ld.py:97
+    // ---- pass 1: sizes
+    for_queries([&](int64_t k) {
+        CountSink c;
+        for (int64_t i = first[(size_t)k]; i < first[(size_t)k + 1]; ++i) format_hit(c, T, hits[i], q_row[k], alt_of(i), format);
+        query_off[k + 1] = c.n;
+    });
+    query_off[0] = 0;
+    for (int64_t k = 0; k < nq; ++k) query_off[k + 1] += query_off[k];
+    *n_bytes = query_off[nq];
+    if (*n_bytes > cap) return ldx::set_error(LDX_ERR_CAPACITY, "area text buffer too small");
+    // ---- pass 2: every query's rows straight into their place
+    for_queries([&](int64_t k) {
+        WriteSink w{out + query_off[k]};
+        for (int64_t i = first[(size_t)k]; i < first[(size_t)k + 1]; ++i) format_hit(w, T, hits[i], q_row[k], alt_of(i), format);
+    });
+    return LDX_OK;
+}

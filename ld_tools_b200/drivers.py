@@ -168,6 +168,7 @@ class ChromData:
     def _set_columns(self, samples, rows, blob, off):
         """rows: one VCF_ROW_DTYPE record per variant (parsed on the GPU); blob/off: the records' fixed columns."""
         self.samples, self.rows, self._blob, self._off = samples, rows, blob, off
+        self._blob_arr = np.frombuffer(blob, dtype=np.uint8) if len(blob) else np.zeros(1, dtype=np.uint8)
         self.pos = rows["pos"].astype(np.int64)
         self.pos0 = (self.pos - 1).astype(np.int32)
         self.end0 = (self.pos0 + rows["ref_len"]).astype(np.int32)
@@ -202,11 +203,19 @@ class ChromData:
 
 
     def select_samples(self, sample_names):
-        """The mask plane of the chosen samples; names absent from the VCF are skipped like the
-        reference's `except KeyError: continue` (ld_area.py:184-187)."""
+        """The haplotypes of the chosen samples; names absent from the VCF are skipped like the reference's
+        `except KeyError: continue` (ld_area.py:184-187).  When they are at most half of the store's columns the selected
+        columns are gathered into a narrower store once (ldx_store_subset: e.g. 1006 of 5008 haplotypes -> 128-byte rows
+        instead of 640-byte rows under a mask) and every scan of this run reads that: `self.scan`."""
         cols = np.array([self.col_of[n] for n in sample_names if n in self.col_of], dtype=np.int64)
-        self.store.select_haplotypes(np.concatenate([2 * cols, 2 * cols + 1]))
-        self.n1, self.p_e4, self.n_hap_sel = self.store.counts()
+        hap = np.sort(np.concatenate([2 * cols, 2 * cols + 1]))
+        if getattr(self, "scan", None) is not None and self.scan is not self.store:
+            self.scan.close()
+        self.store.select_haplotypes(hap)
+        self.scan = self.store
+        if 0 < len(hap) <= self.store.n_hap // 2 and not os.environ.get("LDX_NO_SUBSET_STORE"):
+            self.scan = self.store.subset(hap)
+        self.n1, self.p_e4, self.n_hap_sel = self.scan.counts()
 
     def row_of(self, pos, rs_id):
         """Store row of the first record with this position and ID (the drivers `break` at the first match, ld_area.py:150-159)."""
@@ -225,6 +234,9 @@ class ChromData:
         return self._row_map[(pos, rs_id)]
 
     def close(self):
+        if getattr(self, "scan", None) is not None and self.scan is not self.store:
+            self.scan.close()
+        self.scan = None
         self.store.close()
 
 
@@ -237,125 +249,296 @@ def _ucsc(key, val):
     return f"{key}={val}"
 
 
+# --------------------------------------------------------------------------- fan-out over devices
+def _device_list(devices):
+    """None -> the current device; an int N -> devices 0..N-1; else the list itself."""
+    if devices is None:
+        return [-1]
+    if isinstance(devices, int):
+        return list(range(devices))
+    return list(devices)
+
+
+class _Worker:
+    """One device of a job: its context and the chromosomes it has loaded.  The reference fans its jobs out with
+    multiprocessing.Pool over source files (ld_area.py:320-342, ld_triangle.py:390-411); here the unit is finer -- a
+    (source file, chromosome) table, or a slab of one table's queries / matrix rows -- and the workers are threads, one per
+    GPU (the library calls release the GIL)."""
+
+    def __init__(self, device, ctx, intgen_dir_path, sample_names):
+        self.device, self.ctx, self.own = device, ctx, ctx is None
+        self.intgen_dir_path, self.sample_names = intgen_dir_path, sample_names
+        self.chroms = {}
+
+    def chrom(self, chrom):
+        if self.ctx is None:
+            self.ctx = Context(self.device)
+        if chrom not in self.chroms:
+            cd = self.chroms[chrom] = ChromData(self.ctx, os.path.join(self.intgen_dir_path, f"{chrom}.vcf.gz"))
+            cd.select_samples(self.sample_names)
+        return self.chroms[chrom]
+
+    def close(self):
+        for cd in self.chroms.values():
+            cd.close()
+        if self.own and self.ctx is not None:
+            self.ctx.close()
+
+
+def _run_on_devices(workers, jobs_per_worker, fn):
+    """fn(worker, job) for every job of every worker, one thread per worker; the first exception is re-raised."""
+    import threading
+    errors = []
+
+    def run(w, jobs):
+        try:
+            for job in jobs:
+                fn(w, job)
+        except BaseException as e:      # noqa: BLE001 -- re-raised in the caller's thread
+            errors.append(e)
+    if len(workers) == 1:
+        run(workers[0], jobs_per_worker[0])
+    else:
+        ths = [threading.Thread(target=run, args=(w, j)) for w, j in zip(workers, jobs_per_worker)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+    if errors:
+        raise errors[0]
+
+
 # --------------------------------------------------------------------------- ld_area
 def ld_area(src_dir_path, intgen_dir_path, trg_top_dir_path=None, meta_lines_quan=0, gend_names="both", pop_names="all",
-            flank_size=100000, ld_thres_measure="r_square", ld_low_thres=0.8, trg_file_type="tsv", ctx=None):
+            flank_size=100000, ld_thres_measure="r_square", ld_low_thres=0.8, trg_file_type="tsv", ctx=None, devices=None):
     """ld_area.py as a function: same arguments as its CLI (cli/ld_area_cli_en.py:36-60), same output
-    tree (<src>_in_LD/<chrom>/<rsID>_chr<chrom>_<m>_<thres>.<ext>, ld_area.py:82-84,160)."""
-    own = ctx is None
-    ctx = ctx or Context()
+    tree (<src>_in_LD/<chrom>/<rsID>_chr<chrom>_<m>_<thres>.<ext>, ld_area.py:82-84,160).
+    devices: the GPUs of the job (None = the current one, N = the first N, or a list).  With several, the (source file,
+    chromosome) tables are dealt to them by chromosome, and a lone table's queries are cut into slabs balanced by candidate
+    pairs (region sharding: every query's file is written by the device that scanned it, nothing is exchanged)."""
+    from . import shard
+    from ._lib import AREA_JSON, AREA_RSIDS, AREA_TSV
+    from .engine import area_format
     src_dir_path, intgen_dir_path = os.path.normpath(src_dir_path), os.path.normpath(intgen_dir_path)
     trg_top = src_dir_path if trg_top_dir_path is None else os.path.normpath(trg_top_dir_path)
     convdb = os.path.join(intgen_dir_path, "conversion.db")
     gends, pops = gender_tuple(gend_names), tuple(pop_names.upper().split(","))
     sample_names = get_sample_names(gends, pops, convdb)
     ext = trg_file_type if trg_file_type in ("tsv", "json") else "txt"
+    fmt = {"tsv": AREA_TSV, "json": AREA_JSON}.get(trg_file_type, AREA_RSIDS)
     meta_keys = ["chr", "gends", "pops", "each_flank", f"{ld_thres_measure}_thres"]
     header_row = ["hg38_pos", "rsID", "ref", "alt", "type", "alt_freq", "r2", "D'", "dist"]
     t_e4 = threshold_e4(ld_low_thres)
-    chrom_cache = {}
+    devs = _device_list(devices)
+    workers = [_Worker(d, ctx if k == 0 else None, intgen_dir_path, sample_names) for k, d in enumerate(devs)]
+    # ---- the tables of the job (host work: the source files and conversion.db), directories made as the reference makes them
+    tables = []
+    for src_file_name in os.listdir(src_dir_path):
+        data_by_chrs = create_src_dict(src_dir_path, src_file_name, meta_lines_quan, convdb)
+        trg_dir = os.path.join(trg_top, f"{src_file_name.rsplit('.', maxsplit=1)[0]}_in_LD")
+        for chrom, var_rows in data_by_chrs.items():
+            chr_dir = os.path.join(trg_dir, chrom)
+            os.makedirs(chr_dir)                                             # ld_area.py:123 (not exist_ok)
+            tables.append({"chrom": chrom, "var_rows": var_rows, "chr_dir": chr_dir})
+    chrom_order = {c: k for k, c in enumerate(dict.fromkeys(t["chrom"] for t in tables))}
+    jobs = [[] for _ in workers]
+    if len(workers) > 1 and len(chrom_order) == 1 and len(tables) == 1:
+        for k in range(len(workers)):                                        # one table: its queries in slabs, one per device
+            jobs[k].append(dict(tables[0], slab=(k, len(workers))))
+    else:
+        for t in tables:                                                     # a chromosome's store lives on one device
+            jobs[chrom_order[t["chrom"]] % len(workers)].append(t)
+
+    def run_table(w, t):
+        chrom, var_rows, chr_dir = t["chrom"], t["var_rows"], t["chr_dir"]
+        cd = w.chrom(chrom)
+        meta_vals = [chrom, gends, pops, flank_size, ld_low_thres]
+        ucsc = "##" + " ".join(map(_ucsc, meta_keys, meta_vals))
+        # ---- every query of the table in ONE window scan (ld_area.py:152-249)
+        q_row = np.array([cd.row_of(p, i) for p, i in var_rows], dtype=np.int64)
+        q_pos = cd.pos[q_row]
+        ws = np.maximum(q_pos - flank_size, 0)                        # :174-176
+        we = q_pos + flank_size                                       # :177
+        lo = np.searchsorted(cd.pos0, ws - cd.max_ref_len, side="right")
+        hi = np.maximum(np.searchsorted(cd.pos0, we, side="left"), lo)
+        mine = np.arange(len(q_row))
+        if "slab" in t:                                               # this device's share of the queries, by candidate pairs
+            k, n = t["slab"]
+            order = np.argsort(q_row, kind="stable")
+            cum = np.concatenate([[0], np.cumsum((hi - lo)[order])])
+            cuts = np.searchsorted(cum, cum[-1] * np.arange(n + 1) / n, side="left")
+            cuts[0], cuts[-1] = 0, len(order)
+            mine = np.sort(order[cuts[k]:max(cuts[k + 1], cuts[k])])
+            if not len(mine):
+                return
+        hits, _ = cd.scan.window(q_row[mine], lo[mine], hi[mine], ws[mine], we[mine], ld_thres_measure, t_e4)
+        # ---- the writers (:200-283): the rows of every query from the library, headers and the query's own line from here
+        text, qoff = area_format(w.ctx._lib, hits, q_row[mine], cd._blob_arr, cd._off, cd.rows, cd.p_e4, fmt)
+        for j, k in enumerate(mine):
+            if qoff[j + 1] == qoff[j]:
+                continue                                             # empty result: file removed, :291-292
+            qr = int(q_row[k])
+            q_id = cd.ids[qr]
+            q_ann = [int(cd.pos[qr]), q_id, cd.refs[qr], cd.alts[qr], cd.vts[qr], cd.p_e4[qr] / 10000.0] + ["quer"] * 3
+            path = os.path.join(chr_dir, f"{q_id}_chr{chrom}_{ld_thres_measure[0]}_{str(ld_low_thres)}.{ext}")
+            body = text[qoff[j]:qoff[j + 1]].data
+            with open(path, "wb") as fh:
+                if trg_file_type == "rsids":                          # :201-204, :258-260
+                    fh.write((ucsc + "\n#rsID\n" + q_id + "\n").encode())
+                    fh.write(body)
+                elif trg_file_type == "tsv":                          # :205-208, :273-274
+                    fh.write((ucsc + "\n#" + "\t".join(header_row) + "\n" + "\t".join(map(str, q_ann)) + "\n").encode())
+                    fh.write(body)
+                else:                                                 # :209-211, :275-283
+                    head = json.dumps([dict(zip(meta_keys, meta_vals)), dict(zip(header_row, q_ann))], indent=4)
+                    fh.write(head[:-2].encode())                      # ... without the closing "\n]"
+                    fh.write(body)
+                    fh.write(b"\n]")
     try:
-        for src_file_name in os.listdir(src_dir_path):
-            data_by_chrs = create_src_dict(src_dir_path, src_file_name, meta_lines_quan, convdb)
-            trg_dir = os.path.join(trg_top, f"{src_file_name.rsplit('.', maxsplit=1)[0]}_in_LD")
-            for chrom, var_rows in data_by_chrs.items():
-                chr_dir = os.path.join(trg_dir, chrom)
-                os.makedirs(chr_dir)                                         # ld_area.py:123 (not exist_ok)
-                if chrom not in chrom_cache:
-                    cd = chrom_cache[chrom] = ChromData(ctx, os.path.join(intgen_dir_path, f"{chrom}.vcf.gz"))
-                    cd.select_samples(sample_names)
-                cd = chrom_cache[chrom]
-                meta_vals = [chrom, gends, pops, flank_size, ld_low_thres]
-                ucsc = "##" + " ".join(map(_ucsc, meta_keys, meta_vals))
-                # ---- every query of the chromosome in ONE window scan (ld_area.py:152-249)
-                q_row = np.array([cd.row_of(p, i) for p, i in var_rows], dtype=np.int64)
-                q_pos = cd.pos[q_row]
-                ws = np.maximum(q_pos - flank_size, 0)                        # :174-176
-                we = q_pos + flank_size                                       # :177
-                lo = np.searchsorted(cd.pos0, ws - cd.max_ref_len, side="right")
-                hi = np.maximum(np.searchsorted(cd.pos0, we, side="left"), lo)
-                hits, _ = cd.store.window(q_row, lo, hi, ws, we, ld_thres_measure, t_e4)
-                bounds = np.searchsorted(hits["query"], np.arange(len(q_row) + 1))
-                for k, (pos, rs_id) in enumerate(var_rows):
-                    mine = hits[bounds[k]:bounds[k + 1]]
-                    if not len(mine):
-                        continue                                             # empty result: file removed, :291-292
-                    qr = int(q_row[k])
-                    q_ann = [int(cd.pos[qr]), cd.ids[qr], cd.refs[qr], cd.alts[qr], cd.vts[qr], cd.p_e4[qr] / 10000.0] + ["quer"] * 3
-                    path = os.path.join(chr_dir, f"{cd.ids[qr]}_chr{chrom}_{ld_thres_measure[0]}_{str(ld_low_thres)}.{ext}")
-                    rows = []
-                    for h in mine:
-                        r = int(h["row"])
-                        rows.append([int(cd.pos[r]), cd.ids[r], cd.refs[r], cd.alts[r], cd.vts[r], cd.p_e4[r] / 10000.0,
-                                     r2_value(h["packed"]), dprime_value(h["packed"]), int(cd.pos[r] - cd.pos[qr])])   # :264-272
-                    with open(path, "w") as fh:
-                        if trg_file_type == "rsids":                          # :201-204, :258-260
-                            fh.write(ucsc + "\n#rsID\n" + cd.ids[qr] + "\n")
-                            fh.writelines(r[1] + "\n" for r in rows)
-                        elif trg_file_type == "tsv":                          # :205-208, :273-274
-                            fh.write(ucsc + "\n#" + "\t".join(header_row) + "\n")
-                            fh.write("\t".join(map(str, q_ann)) + "\n")
-                            fh.writelines("\t".join(map(str, r)) + "\n" for r in rows)
-                        else:                                                 # :209-211, :275-283
-                            obj = [dict(zip(meta_keys, meta_vals)), dict(zip(header_row, q_ann))]
-                            obj += [dict(zip(header_row, r)) for r in rows]
-                            json.dump(obj, fh, indent=4)
+        _run_on_devices(workers, jobs, run_table)
     finally:
-        for cd in chrom_cache.values():
-            cd.close()
-        if own:
-            ctx.close()
+        for w in workers:
+            w.close()
 
 
 # --------------------------------------------------------------------------- ld_triangle (table output)
+BATCH_MAX_VARIANTS = 8192            # matrices up to this size go into one batched launch per device (ldx_triangle_batch_dev)
+BATCH_MAX_BYTES = 4 << 30            # ... as long as their packed words fit this much device memory
+
+
 def ld_triangle(src_dir_path, intgen_dir_path, trg_top_dir_path=None, meta_lines_quan=0, gend_names="both", pop_names="all",
-                ld_measure="r_square", ld_low_thres=None, ctx=None):
+                ld_measure="r_square", ld_low_thres=None, ctx=None, devices=None):
     """ld_triangle.py -o table as a function (cli/ld_triangle_cli_en.py:40-74).  The heatmap outputs are
-    Plotly rendering, out of scope; the matrix they draw is this one."""
-    own = ctx is None
-    ctx = ctx or Context()
+    Plotly rendering, out of scope; the matrix they draw is this one.
+    devices: as for ld_area.  The (source file, chromosome) matrices are dealt to the devices by chromosome; on each device
+    the small ones are computed by ONE batched launch (a 2,000-variant matrix alone is a single wave of tiles) and a large
+    one slab by slab; a lone large matrix is cut into row slabs that the devices take in turn while the file is written in
+    order."""
     src_dir_path, intgen_dir_path = os.path.normpath(src_dir_path), os.path.normpath(intgen_dir_path)
     trg_top = src_dir_path if trg_top_dir_path is None else os.path.normpath(trg_top_dir_path)
     convdb = os.path.join(intgen_dir_path, "conversion.db")
     gends, pops = gender_tuple(gend_names), tuple(pop_names.upper().split(","))
     sample_names = get_sample_names(gends, pops, convdb)
     t_e4 = None if ld_low_thres is None else threshold_e4(ld_low_thres)
-    chrom_cache = {}
+    devs = _device_list(devices)
+    workers = [_Worker(d, ctx if k == 0 else None, intgen_dir_path, sample_names) for k, d in enumerate(devs)]
+    tab = "\t"
+    tables = []
+    for src_file_name in os.listdir(src_dir_path):
+        data_by_chrs = create_src_dict(src_dir_path, src_file_name, meta_lines_quan, convdb)
+        base = src_file_name.rsplit(".", maxsplit=1)[0]
+        trg_dir = os.path.join(trg_top, f"{base}_LD_matr")
+        for chrom, var_rows in data_by_chrs.items():
+            if len(var_rows) < 2:                                        # ld_triangle.py:80
+                continue
+            os.makedirs(trg_dir, exist_ok=True)
+            var_rows.sort(key=lambda row: row[0])                        # :88 (stable)
+            tables.append({"chrom": chrom, "var_rows": var_rows, "path": os.path.join(trg_dir, f"{base}_chr{chrom}_{ld_measure[0]}.tsv")})
+    chrom_order = {c: k for k, c in enumerate(dict.fromkeys(t["chrom"] for t in tables))}
+
+    def prepare(w, t):
+        cd = w.chrom(t["chrom"])
+        poss = [str(p) for p, _ in t["var_rows"]]
+        ids = [i for _, i in t["var_rows"]]
+        t["v"] = len(ids)
+        t["rows"] = np.array([cd.row_of(p, i) for p, i in t["var_rows"]], dtype=np.int64)
+        t["head"] = (f"##General\tinfo:\t{ld_measure}\tchr{t['chrom']}\t{tab.join(pops)}\t{tab.join(gends)}\n\n"
+                     + "rsIDs\t\t" + "\t".join(ids) + "\n" + "\tPositions\t" + "\t".join(poss) + "\n").encode()       # :351-355
+        t["prefixes"] = [(i + "\t" + p + "\t").encode() for i, p in zip(ids, poss)]
+        return cd
+
+    def slab_rows(v):
+        return min(v, max(256, TEXT_SLAB_BYTES // (7 * v) // 256 * 256))
+
+    def write_slabbed(w, t, cd):
+        """The double loop (:133-230) and the V lines of V cells (:356-360): all-pairs kernel, settlement and the writer in one
+        library call per slab of rows; only text leaves the GPU."""
+        v, slab = t["v"], slab_rows(t["v"])
+        buf = np.empty(7 * v * slab + sum(map(len, t["prefixes"])), dtype=np.uint8)        # one buffer for every slab
+        with open(t["path"], "wb") as fh:
+            fh.write(t["head"])
+            for r0 in range(0, v, slab):
+                fh.write(cd.scan.triangle_table(t["rows"], t["prefixes"], ld_measure, t_e4, row_begin=r0, row_end=min(v, r0 + slab), out=buf).data)
+
+    def run_device(w, mine):
+        """A device's tables: the small matrices in batched launches, the large ones slab by slab."""
+        small, group, group_bytes = [], [], 0
+        for t in mine:
+            cd = prepare(w, t)
+            if t["v"] > BATCH_MAX_VARIANTS:
+                write_slabbed(w, t, cd)
+                continue
+            nbytes = 4 * (t["v"] * (t["v"] - 1) // 2)
+            if group and group_bytes + nbytes > BATCH_MAX_BYTES:
+                small.append(group)
+                group, group_bytes = [], 0
+            group.append((t, cd))
+            group_bytes += nbytes
+        if group:
+            small.append(group)
+        for group in small:
+            if len(group) == 1:                                          # nothing to batch with: the one-call path (direct mode applies)
+                write_slabbed(w, group[0][0], group[0][1])
+                continue
+            addrs = [w.ctx.dev_alloc(4 * (t["v"] * (t["v"] - 1) // 2)) for t, _ in group]
+            try:
+                w.ctx.triangle_batch_dev([(cd.scan, t["rows"], a) for (t, cd), a in zip(group, addrs)], measure=ld_measure, thres_e4_=t_e4)
+                w.ctx.resolve()
+                for (t, cd), a in zip(group, addrs):
+                    with open(t["path"], "wb") as fh:
+                        fh.write(t["head"])
+                        fh.write(w.ctx.triangle_text(a, t["v"], ld_measure, t["prefixes"]).data)
+            finally:
+                for a in addrs:
+                    w.ctx.dev_free(a)
+
+    def run_shared(ws, t):
+        """One large matrix over several devices: 256-aligned row slabs balanced by pair count, taken by the devices in turn;
+        every device formats its slabs' text and the file is written in slab order."""
+        import queue
+        import threading
+        cds = [prepare(w, t) for w in ws]
+        v = t["v"]
+        from . import shard
+        n_slabs = max(len(ws), min(4 * len(ws), (v + 255) // 256))
+        ranges = [r for r in shard.triangle_row_ranges(v, n_slabs) if r[1] > r[0]]
+        done = [queue.Queue(maxsize=2) for _ in ws]
+        errors = []
+
+        def produce(k):
+            try:
+                for j in range(k, len(ranges), len(ws)):
+                    r0, r1 = ranges[j]
+                    done[k].put(cds[k].scan.triangle_table(t["rows"], t["prefixes"], ld_measure, t_e4, row_begin=r0, row_end=r1).tobytes())
+            except BaseException as e:      # noqa: BLE001
+                errors.append(e)
+                done[k].put(None)
+        ths = [threading.Thread(target=produce, args=(k,)) for k in range(len(ws))]
+        for th in ths:
+            th.start()
+        with open(t["path"], "wb") as fh:
+            fh.write(t["head"])
+            for j in range(len(ranges)):
+                text = done[j % len(ws)].get()
+                if text is None:
+                    break
+                fh.write(text)
+        for th in ths:
+            th.join()
+        if errors:
+            raise errors[0]
+
     try:
-        for src_file_name in os.listdir(src_dir_path):
-            data_by_chrs = create_src_dict(src_dir_path, src_file_name, meta_lines_quan, convdb)
-            base = src_file_name.rsplit(".", maxsplit=1)[0]
-            trg_dir = os.path.join(trg_top, f"{base}_LD_matr")
-            for chrom, var_rows in data_by_chrs.items():
-                if len(var_rows) < 2:                                        # ld_triangle.py:80
-                    continue
-                os.makedirs(trg_dir, exist_ok=True)
-                var_rows.sort(key=lambda row: row[0])                        # :88 (stable)
-                if chrom not in chrom_cache:
-                    cd = chrom_cache[chrom] = ChromData(ctx, os.path.join(intgen_dir_path, f"{chrom}.vcf.gz"))
-                    cd.select_samples(sample_names)
-                cd = chrom_cache[chrom]
-                poss = [str(p) for p, _ in var_rows]
-                ids = [i for _, i in var_rows]
-                v = len(ids)
-                rows = np.array([cd.row_of(p, i) for p, i in var_rows], dtype=np.int64)
-                tab = "\t"
-                with open(os.path.join(trg_dir, f"{base}_chr{chrom}_{ld_measure[0]}.tsv"), "wb") as fh:  # :351-360
-                    fh.write((f"##General\tinfo:\t{ld_measure}\tchr{chrom}\t{tab.join(pops)}\t{tab.join(gends)}\n\n"
-                              + "rsIDs\t\t" + "\t".join(ids) + "\n" + "\tPositions\t" + "\t".join(poss) + "\n").encode())
-                    # the double loop (:133-230) and the V lines of V cells (:356-360): all-pairs kernel, settlement and
-                    # the writer in one library call per slab of rows; only text leaves the GPU
-                    prefixes = [(i + "\t" + p + "\t").encode() for i, p in zip(ids, poss)]
-                    slab = min(v, max(256, TEXT_SLAB_BYTES // (7 * v) // 256 * 256))
-                    buf = np.empty(7 * v * slab + sum(map(len, prefixes)), dtype=np.uint8)        # one buffer for every slab
-                    for r0 in range(0, v, slab):
-                        fh.write(cd.store.triangle_table(rows, prefixes, ld_measure, t_e4, row_begin=r0, row_end=min(v, r0 + slab),
-                                                         out=buf).data)
+        if len(workers) > 1 and len(tables) == 1 and len(tables[0]["var_rows"]) > BATCH_MAX_VARIANTS:
+            run_shared(workers, tables[0])
+        else:
+            jobs = [[] for _ in workers]
+            for t in tables:
+                jobs[chrom_order[t["chrom"]] % len(workers)].append(t)
+            _run_on_devices(workers, [[j] for j in jobs], run_device)
     finally:
-        for cd in chrom_cache.values():
-            cd.close()
-        if own:
-            ctx.close()
+        for w in workers:
+            w.close()
 
 
 # --------------------------------------------------------------------------- ld_lite
@@ -382,7 +565,7 @@ def ld_lite(rs_id_1, rs_id_2, intgen_dir_path, gend_names="both", pop_names="all
     try:
         cd.select_samples(get_sample_names(gender_tuple(gend_names), tuple(pop_names.upper().split(",")), convdb))
         r1, r2 = cd.row_of(pos1, rs_id_1), cd.row_of(pos2, rs_id_2)
-        out = cd.store.pairs([r1], [r2], raw=False)
+        out = cd.scan.pairs([r1], [r2], raw=False)
         w = out["packed"][0]
         first_alt = lambda r: cd.alts[r].split(",")[0]                        # noqa: E731  (intgen_rec.alts[0], :116)
         return tabulate([["chrom", chrom, chrom], ["hg38_pos", pos1, pos2],

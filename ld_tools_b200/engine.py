@@ -74,6 +74,30 @@ def _i64(a):
     return np.ascontiguousarray(a, dtype=np.int64)
 
 
+def area_format(lib, hits, q_row, blob, blob_off, rows, p_e4, fmt, alt_e4_of_hit=None, threads=0):
+    """The ld_area writers' body rows for all queries of a window scan (ldx_area_format: host code in libldx, all cores).
+    hits: HIT_DTYPE array sorted by (query, row); rows / blob / blob_off: the records' field offsets and fixed columns
+    (Store.ingest_vcf, Store.vcf_fixed_columns); p_e4: round(alt freq, 4) * 10^4 per store row.
+    -> (uint8 array of the text, int64 query_off[nq + 1]): query k's rows are text[query_off[k]:query_off[k + 1]]."""
+    hits = np.ascontiguousarray(hits, dtype=HIT_DTYPE)
+    q_row = _i64(q_row)
+    rows = np.ascontiguousarray(rows, dtype=VCF_ROW_DTYPE)
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    blob_off = _i64(blob_off)
+    p_e4 = np.ascontiguousarray(p_e4, dtype=np.int32)
+    alt = None if alt_e4_of_hit is None else np.ascontiguousarray(alt_e4_of_hit, dtype=np.int32)
+    qoff = np.zeros(q_row.shape[0] + 1, dtype=np.int64)
+    n = C.c_int64()
+    args = (ptr(hits), hits.shape[0], ptr(q_row), q_row.shape[0], ptr(blob), ptr(blob_off), ptr(rows), rows.shape[0], ptr(p_e4), ptr(alt),
+            int(fmt), int(threads))
+    rc = lib.ldx_area_format(*args, None, 0, C.byref(n), ptr(qoff))          # size query
+    if rc not in (_lib.OK, _lib.ERR_CAPACITY):
+        check(rc)
+    out = np.empty(max(n.value, 1), dtype=np.uint8)
+    check(lib.ldx_area_format(*args, ptr(out), out.shape[0], C.byref(n), ptr(qoff)))
+    return out[:n.value], qoff
+
+
 class HostText:
     """A .gz file inflated by the library (ldx_inflate_gz_file: BGZF blocks in parallel on all host cores).
     `.array` is a uint8 view of the C-owned text; it is released when this object goes away."""
@@ -141,6 +165,16 @@ class Context:
         n = C.c_int64()
         check(self._lib.ldx_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def dev_alloc(self, nbytes):
+        """Raw device memory (an address) for the outputs of the *_dev calls; release it with dev_free()."""
+        p = C.c_void_p()
+        check(self._lib.ldx_dev_alloc(self._h, int(nbytes), C.byref(p)))
+        return p.value
+
+    def dev_free(self, addr):
+        if addr and getattr(self, "_h", None):
+            check(self._lib.ldx_dev_free(self._h, C.c_void_p(addr)))
 
     def resolve(self):
         n = C.c_int64()

@@ -104,6 +104,58 @@ def test_ld_triangle_320_variants_through_the_tensor_core_engine(data, ctx, tmp_
     assert assert_same_tree(str(tmp_path), name) == 1
 
 
+@pytest.mark.parametrize("name,extra", [dc.AREA_CASES[0], dc.AREA_CASES[1]])
+def test_ld_area_fan_out_over_devices_same_tree(data, tmp_path, name, extra):
+    """devices=[0, 0]: two workers (own contexts; on a multi-GPU box they would be two GPUs) share the job's tables by
+    chromosome -- here one chromosome, two source files -- and, for a lone table, its queries in slabs.  Same output tree."""
+    import shutil
+    from ld_tools_b200 import drivers
+    root, intgen, srcs = data
+    kw = parse(extra, "area")
+    drivers.ld_area(srcs["area"], intgen, trg_top_dir_path=str(tmp_path / "two"), devices=[0, 0], **kw)
+    assert_same_tree(str(tmp_path / "two"), name)
+    # a lone table: region sharding of its queries over three workers
+    one = tmp_path / "src_one"
+    os.makedirs(one)
+    shutil.copy(os.path.join(srcs["area"], "gwas_hits.tsv"), one)
+    drivers.ld_area(str(one), intgen, trg_top_dir_path=str(tmp_path / "slabs"), devices=[0, 0, 0], **kw)
+    want = {k: v for k, v in dc.read_tree(os.path.join(GOLD, name)).items() if k.startswith("gwas_hits_in_LD")}
+    got = dc.read_tree(str(tmp_path / "slabs"))
+    assert sorted(got) == sorted(want) and all(got[k] == want[k] for k in want)
+
+
+def test_ld_triangle_batched_tables_and_shared_matrix(data, ctx, tmp_path, monkeypatch):
+    """Several (source file, chromosome) matrices of one run go through ONE batched launch (ldx_triangle_batch_dev) and the
+    text kernel; a lone large matrix is cut into row slabs over the devices.  Both must write the files the one-table path
+    writes -- which the goldens pin to the reference."""
+    import numpy as np
+    from ld_tools_b200 import drivers
+    root, intgen, srcs = data
+    with open(os.path.join(srcs["triangle_big"], "region.txt")) as fh:
+        ids = fh.read().split()
+    many = tmp_path / "src_many"
+    os.makedirs(many)
+    rng = np.random.default_rng(8)
+    for k, n in enumerate((300, 40, 2, 129)):
+        with open(many / f"set{k}.txt", "w") as fh:
+            fh.write("\n".join(rng.permutation(ids)[:n]) + "\n")
+    launches0 = ctx.launch_count
+    drivers.ld_triangle(str(many), intgen, trg_top_dir_path=str(tmp_path / "batched"), ld_measure="d_prime", ld_low_thres=0.3, ctx=ctx)
+    batched_launches = ctx.launch_count - launches0
+    monkeypatch.setattr(drivers, "BATCH_MAX_VARIANTS", 1)                # every table alone, slab path
+    drivers.ld_triangle(str(many), intgen, trg_top_dir_path=str(tmp_path / "single"), ld_measure="d_prime", ld_low_thres=0.3, ctx=ctx)
+    a, b = dc.read_tree(str(tmp_path / "batched")), dc.read_tree(str(tmp_path / "single"))
+    assert len(a) == 4 and sorted(a) == sorted(b) and all(a[k] == b[k] for k in a)
+    assert batched_launches <= 4 + 3 * 4                                 # gather + all-pairs + deferred pairs (+ scatter), then 3 text kernels per table
+    # the 320-variant golden table as a "large" matrix shared by three workers
+    name, extra = dc.TRIANGLE_BIG_CASES[1]
+    kw = parse(extra, "triangle")
+    kw.pop("matrix_type")
+    monkeypatch.setattr(drivers, "BATCH_MAX_VARIANTS", 100)
+    drivers.ld_triangle(srcs["triangle_big"], intgen, trg_top_dir_path=str(tmp_path / "shared"), devices=[0, 0, 0], **kw)
+    assert assert_same_tree(str(tmp_path / "shared"), name) == 1
+
+
 def _pool_worker(args):
     """Runs in a forked multiprocessing.Pool worker: the drop-in calc_ld creates its context lazily, after the fork."""
     import os

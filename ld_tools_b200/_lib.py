@@ -87,7 +87,7 @@ SIGNATURES = {
     "ldx_triangle_text": [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _i32, _vp, _i64, _P(_i64)],
     "ldx_triangle_table": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _P(_i64)],
     "ldx_format_e4": [_i32, _vp],
-    "ldx_area_format": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _P(_i64), _vp],
+    "ldx_area_format": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _P(_vp), _P(_i64), _vp],
 }
 
 _lib = None

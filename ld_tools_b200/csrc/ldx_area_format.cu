@@ -110,61 +110,119 @@ struct Table {
     }
 };
 
-template <class S> void format_hit(S &s, const Table &T, const ldx_hit &h, int64_t qrow, int32_t alt_e4, int format) {
-    const int64_t r = h.row;
+// ---- the part of a row that depends on the opposing variant alone, formatted once per variant of the call (a variant sits in
+// the windows of ~30 queries at configs[2]): TSV "pos\tid\tref\talt\ttype\t", JSON the element up to `"alt_freq": `
+template <class S> void format_row_prefix(S &s, const Table &T, int64_t r, int format) {
     const Field id = T.col(r, T.rows[r].id_off);
-    if (format == LDX_AREA_RSIDS) { s.put(id.p, id.n); s.ch('\n'); return; }                      // ld_area.py:258-260
+    if (format == LDX_AREA_RSIDS) { s.put(id.p, id.n); s.ch('\n'); return; }                      // ld_area.py:258-260: the whole line
     const Field ref = T.col(r, T.rows[r].ref_off), alt = T.col(r, T.rows[r].alt_off), vt = T.vt(r);
-    const int64_t pos = T.rows[r].pos, dist = (int64_t)T.rows[r].pos - (int64_t)T.rows[qrow].pos;   // :272
     if (format == LDX_AREA_TSV) {                                                                  // :264-274
-        put_int(s, pos); s.ch('\t'); s.put(id.p, id.n); s.ch('\t'); s.put(ref.p, ref.n); s.ch('\t'); s.put(alt.p, alt.n); s.ch('\t');
-        s.put(vt.p, vt.n); s.ch('\t'); put_e4(s, alt_e4); s.ch('\t'); put_r2(s, h.packed); s.ch('\t'); put_dp(s, h.packed); s.ch('\t');
-        put_int(s, dist); s.ch('\n');
+        put_int(s, T.rows[r].pos); s.ch('\t'); s.put(id.p, id.n); s.ch('\t'); s.put(ref.p, ref.n); s.ch('\t'); s.put(alt.p, alt.n); s.ch('\t');
+        s.put(vt.p, vt.n); s.ch('\t');
         return;
     }
     // one element of the list json.dump(trg_obj, ..., indent=4) writes (:275-283), with the separator that precedes it
-    PUT_LIT(s, ",\n    {\n        \"hg38_pos\": "); put_int(s, pos);
+    PUT_LIT(s, ",\n    {\n        \"hg38_pos\": "); put_int(s, T.rows[r].pos);
     PUT_LIT(s, ",\n        \"rsID\": "); put_json_str(s, id);
     PUT_LIT(s, ",\n        \"ref\": "); put_json_str(s, ref);
     PUT_LIT(s, ",\n        \"alt\": "); put_json_str(s, alt);
     PUT_LIT(s, ",\n        \"type\": "); put_json_str(s, vt);
-    PUT_LIT(s, ",\n        \"alt_freq\": "); put_e4(s, alt_e4);
-    PUT_LIT(s, ",\n        \"r2\": "); put_r2(s, h.packed);
-    PUT_LIT(s, ",\n        \"D'\": "); put_dp(s, h.packed);
-    PUT_LIT(s, ",\n        \"dist\": "); put_int(s, dist);
-    PUT_LIT(s, "\n    }");
+    PUT_LIT(s, ",\n        \"alt_freq\": ");
 }
+
+// str(k / 10000.0) for every k a packed word can hold, built once per process: 8 bytes of text + its length
+struct E4Table {
+    char txt[20001][8];
+    uint8_t len[20001];
+    E4Table() {
+        for (int k = 0; k <= 20000; ++k) {
+            if (ldx_format_e4(k, txt[k]) != LDX_OK) std::memset(txt[k], 0, 8);
+            len[k] = (uint8_t)strnlen(txt[k], 8);
+        }
+    }
+};
+const E4Table &e4_table() { static const E4Table t; return t; }
+
+struct HitFormatter {
+    const Table &T; const E4Table &E; int format;
+    const uint32_t *pre_len; const uint64_t *pre_off; const char *pre_txt;          // per store row: its prefix text (touched rows only)
+    // the rounded measures as Python prints the objects calc_ld returned: the int 0 or a float (calc_ld.py:68-69, :89-90, :94-95)
+    static int r2_e4(uint32_t w) { return (w & LDX_R2_INT0) ? -1 : (int)(w & LDX_R2_MASK); }
+    static int dp_e4(uint32_t w) { return (w & LDX_DP_INT0) ? -1 : (int)((w & LDX_DP_MASK) >> LDX_DP_SHIFT); }
+    size_t e4_len(int k) const { return k < 0 ? 1 : E.len[k]; }
+    static size_t int_len(int64_t v) { size_t n = v < 0 ? 2 : 1; uint64_t u = v < 0 ? (uint64_t)(-(v + 1)) + 1 : (uint64_t)v; while (u >= 10) { u /= 10; ++n; } return n; }
+    char *put_e4(char *p, int k) const { if (k < 0) { *p++ = '0'; return p; } std::memcpy(p, E.txt[k], 8); return p + E.len[k]; }
+    static char *put_int(char *p, int64_t v) {
+        char buf[24];
+        int n = 0;
+        const bool neg = v < 0;
+        uint64_t u = neg ? (uint64_t)(-(v + 1)) + 1 : (uint64_t)v;
+        do { buf[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+        if (neg) *p++ = '-';
+        while (n) *p++ = buf[--n];
+        return p;
+    }
+    size_t size(const ldx_hit &h, int64_t qrow, int32_t alt_e4) const {
+        const size_t a = pre_len[h.row];
+        if (format == LDX_AREA_RSIDS) return a;
+        const int64_t dist = (int64_t)T.rows[h.row].pos - (int64_t)T.rows[qrow].pos;                // :272
+        const size_t vals = e4_len(alt_e4) + e4_len(r2_e4(h.packed)) + e4_len(dp_e4(h.packed)) + int_len(dist);
+        return a + vals + (format == LDX_AREA_TSV ? 4 : sizeof(",\n        \"r2\": ") - 1 + sizeof(",\n        \"D'\": ") - 1 + sizeof(",\n        \"dist\": ") - 1 + sizeof("\n    }") - 1);
+    }
+    // NOTE: writes up to 7 bytes past the end of a value (8-byte copies of the e4 texts); the caller's buffer has that slack
+    char *write(char *p, const ldx_hit &h, int64_t qrow, int32_t alt_e4) const {
+        std::memcpy(p, pre_txt + pre_off[h.row], pre_len[h.row]);
+        p += pre_len[h.row];
+        if (format == LDX_AREA_RSIDS) return p;
+        const int64_t dist = (int64_t)T.rows[h.row].pos - (int64_t)T.rows[qrow].pos;
+        if (format == LDX_AREA_TSV) {
+            p = put_e4(p, alt_e4); *p++ = '\t'; p = put_e4(p, r2_e4(h.packed)); *p++ = '\t'; p = put_e4(p, dp_e4(h.packed)); *p++ = '\t';
+            p = put_int(p, dist); *p++ = '\n';
+            return p;
+        }
+#define LIT(x) do { std::memcpy(p, x, sizeof(x) - 1); p += sizeof(x) - 1; } while (0)
+        p = put_e4(p, alt_e4); LIT(",\n        \"r2\": "); p = put_e4(p, r2_e4(h.packed)); LIT(",\n        \"D'\": "); p = put_e4(p, dp_e4(h.packed));
+        LIT(",\n        \"dist\": "); p = put_int(p, dist); LIT("\n    }");
+#undef LIT
+        return p;
+    }
+};
 
 }  // namespace
 
 extern "C" int32_t ldx_area_format(const ldx_hit *hits, int64_t n_hits, const int64_t *q_row, int64_t nq, const uint8_t *blob,
                                    const int64_t *blob_off, const ldx_vcf_row *rows, int64_t n_rows, const int32_t *p_e4,
-                                   const int32_t *alt_e4_of_hit, int32_t format, int32_t threads, char *out, int64_t cap,
+                                   const int32_t *alt_e4_of_hit, int32_t format, int32_t threads, char **text_out,
                                    int64_t *n_bytes, int64_t *query_off) {
-    LDX_REQUIRE(n_bytes && query_off && q_row && blob && blob_off && rows && (p_e4 || alt_e4_of_hit), "NULL argument");
-    LDX_REQUIRE(n_hits >= 0 && nq >= 0 && n_rows >= 0 && (hits || n_hits == 0) && (out || cap == 0), "bad sizes");
+    LDX_REQUIRE(text_out && n_bytes && query_off && q_row && blob && blob_off && rows && (p_e4 || alt_e4_of_hit), "NULL argument");
+    LDX_REQUIRE(n_hits >= 0 && nq >= 0 && n_rows >= 0 && (hits || n_hits == 0), "bad sizes");
     LDX_REQUIRE(format == LDX_AREA_TSV || format == LDX_AREA_JSON || format == LDX_AREA_RSIDS, "bad format");
-    *n_bytes = 0;
+    *n_bytes = 0; *text_out = nullptr;
     // the hits of query k: [first[k], first[k + 1]) -- they arrive sorted by (query, row)
     std::vector<int64_t> first((size_t)nq + 1, 0);
+    std::vector<uint8_t> touched((size_t)n_rows, 0);
     for (int64_t i = 0; i < n_hits; ++i) {
         LDX_REQUIRE(hits[i].query >= 0 && hits[i].query < nq && hits[i].row >= 0 && hits[i].row < n_rows, "hit outside the query / row tables");
         LDX_REQUIRE(i == 0 || hits[i].query >= hits[i - 1].query, "hits must be sorted by query");
+        LDX_REQUIRE(!alt_e4_of_hit || (alt_e4_of_hit[i] >= 0 && alt_e4_of_hit[i] <= 20000), "alt_e4_of_hit out of range");
         first[(size_t)hits[i].query + 1]++;
+        touched[(size_t)hits[i].row] = 1;
     }
     for (int64_t k = 0; k < nq; ++k) {
         LDX_REQUIRE(q_row[k] >= 0 && q_row[k] < n_rows, "q_row outside the row table");
         first[(size_t)k + 1] += first[(size_t)k];
     }
+    if (!alt_e4_of_hit)
+        for (int64_t r = 0; r < n_rows; ++r) LDX_REQUIRE(!touched[(size_t)r] || (p_e4[r] >= 0 && p_e4[r] <= 20000), "p_e4 out of range");
     const Table T{blob, blob_off, rows, p_e4};
     const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(threads > 0 ? threads : (int)std::thread::hardware_concurrency(), std::max<int64_t>(1, n_hits / 4096)));
-    auto for_queries = [&](auto &&body) {                         // dynamic chunks of queries over the threads
+    auto parallel = [&](int64_t n, int64_t chunk, auto &&body) {   // dynamic chunks of [0, n) over the threads
         std::atomic<int64_t> next{0};
         auto work = [&]() {
             for (;;) {
-                const int64_t k0 = next.fetch_add(16);
-                if (k0 >= nq) break;
-                for (int64_t k = k0; k < std::min(nq, k0 + 16); ++k) body(k);
+                const int64_t k0 = next.fetch_add(chunk);
+                if (k0 >= n) break;
+                for (int64_t k = k0; k < std::min(n, k0 + chunk); ++k) body(k);
             }
         };
         std::vector<std::thread> pool;
@@ -172,21 +230,53 @@ extern "C" int32_t ldx_area_format(const ldx_hit *hits, int64_t n_hits, const in
         work();
         for (auto &t : pool) t.join();
     };
-    auto alt_of = [&](int64_t i) { return alt_e4_of_hit ? alt_e4_of_hit[i] : p_e4[hits[i].row]; };   // var_2_alt_freq, calc_ld.py:97
-    // ---- pass 1: sizes
-    for_queries([&](int64_t k) {
+    // ---- every touched variant's prefix, once: sizes, offsets, text
+    std::vector<uint32_t> pre_len((size_t)n_rows, 0);
+    std::vector<uint64_t> pre_off((size_t)n_rows + 1, 0);
+    parallel(n_rows, 4096, [&](int64_t r) {
+        if (!touched[(size_t)r]) return;
         CountSink c;
-        for (int64_t i = first[(size_t)k]; i < first[(size_t)k + 1]; ++i) format_hit(c, T, hits[i], q_row[k], alt_of(i), format);
-        query_off[k + 1] = c.n;
+        format_row_prefix(c, T, r, format);
+        pre_len[(size_t)r] = (uint32_t)c.n;
+    });
+    for (int64_t r = 0; r < n_rows; ++r) pre_off[(size_t)r + 1] = pre_off[(size_t)r] + pre_len[(size_t)r];
+    std::vector<char> pre_txt((size_t)pre_off[(size_t)n_rows] + 8);
+    parallel(n_rows, 4096, [&](int64_t r) {
+        if (!touched[(size_t)r]) return;
+        WriteSink w{pre_txt.data() + pre_off[(size_t)r]};
+        format_row_prefix(w, T, r, format);
+    });
+    const HitFormatter F{T, e4_table(), format, pre_len.data(), pre_off.data(), pre_txt.data()};
+    auto alt_of = [&](int64_t i) { return alt_e4_of_hit ? alt_e4_of_hit[i] : p_e4[hits[i].row]; };   // var_2_alt_freq, calc_ld.py:97
+    // ---- pass 1: sizes (table look-ups only)
+    parallel(nq, 16, [&](int64_t k) {
+        int64_t n = 0;
+        for (int64_t i = first[(size_t)k]; i < first[(size_t)k + 1]; ++i) n += (int64_t)F.size(hits[i], q_row[k], alt_of(i));
+        query_off[k + 1] = n;
     });
     query_off[0] = 0;
     for (int64_t k = 0; k < nq; ++k) query_off[k + 1] += query_off[k];
-    *n_bytes = query_off[nq];
-    if (*n_bytes > cap) return ldx::set_error(LDX_ERR_CAPACITY, "area text buffer too small");
-    // ---- pass 2: every query's rows straight into their place
-    for_queries([&](int64_t k) {
-        WriteSink w{out + query_off[k]};
-        for (int64_t i = first[(size_t)k]; i < first[(size_t)k + 1]; ++i) format_hit(w, T, hits[i], q_row[k], alt_of(i), format);
+    char *out = static_cast<char *>(std::malloc((size_t)query_off[nq] + 16));
+    if (!out) return ldx::set_error(LDX_ERR_NOMEM, "area text allocation failed");
+    // ---- pass 2: every query's rows into their place.  The values are copied as whole 8-byte table entries (up to 7 bytes past
+    // their end), so a row is built in a small buffer and copied out exactly: no byte outside the query's range is touched.
+    parallel(nq, 1, [&](int64_t k) {
+        char row[4096];
+        char *dst = out + query_off[k];
+        for (int64_t i = first[(size_t)k]; i < first[(size_t)k + 1]; ++i) {
+            const size_t need = F.size(hits[i], q_row[k], alt_of(i));
+            if (need + 8 <= sizeof row) {
+                F.write(row, hits[i], q_row[k], alt_of(i));
+                std::memcpy(dst, row, need);
+            } else {                                               // a record with very long alleles: through a heap buffer
+                std::vector<char> big(need + 8);
+                F.write(big.data(), hits[i], q_row[k], alt_of(i));
+                std::memcpy(dst, big.data(), need);
+            }
+            dst += need;
+        }
     });
+    *text_out = out;
+    *n_bytes = query_off[nq];
     return LDX_OK;
 }

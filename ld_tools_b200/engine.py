@@ -87,15 +87,39 @@ def area_format(lib, hits, q_row, blob, blob_off, rows, p_e4, fmt, alt_e4_of_hit
     p_e4 = np.ascontiguousarray(p_e4, dtype=np.int32)
     alt = None if alt_e4_of_hit is None else np.ascontiguousarray(alt_e4_of_hit, dtype=np.int32)
     qoff = np.zeros(q_row.shape[0] + 1, dtype=np.int64)
-    n = C.c_int64()
-    args = (ptr(hits), hits.shape[0], ptr(q_row), q_row.shape[0], ptr(blob), ptr(blob_off), ptr(rows), rows.shape[0], ptr(p_e4), ptr(alt),
-            int(fmt), int(threads))
-    rc = lib.ldx_area_format(*args, None, 0, C.byref(n), ptr(qoff))          # size query
-    if rc not in (_lib.OK, _lib.ERR_CAPACITY):
-        check(rc)
-    out = np.empty(max(n.value, 1), dtype=np.uint8)
-    check(lib.ldx_area_format(*args, ptr(out), out.shape[0], C.byref(n), ptr(qoff)))
-    return out[:n.value], qoff
+    n, p = C.c_int64(), C.c_void_p()
+    check(lib.ldx_area_format(ptr(hits), hits.shape[0], ptr(q_row), q_row.shape[0], ptr(blob), ptr(blob_off), ptr(rows), rows.shape[0], ptr(p_e4),
+                              ptr(alt), int(fmt), int(threads), C.byref(p), C.byref(n), ptr(qoff)))
+    return _lib_text(lib, p, n.value), qoff
+
+
+class _Allocation:
+    """Host memory malloc'ed by the library, released with ldx_free_host when the last array viewing it goes away."""
+
+    def __init__(self, lib, p):
+        self.lib, self.p = lib, p
+
+    def __del__(self):
+        if self.p is not None and self.p.value:
+            self.lib.ldx_free_host(self.p)
+        self.p = None
+
+
+class _LibText(np.ndarray):
+    """uint8 view of library-owned text; slices of it keep the allocation alive."""
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, "_owner", None)
+
+
+def _lib_text(lib, p, nbytes):
+    owner = _Allocation(lib, p)
+    if not nbytes:
+        return np.zeros(0, dtype=np.uint8)
+    out = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,)).view(_LibText)
+    out._owner = owner
+    return out
 
 
 class HostText:

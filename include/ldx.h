@@ -20,6 +20,13 @@
  *   of the variant's row.  Row pitch = ceil(n_hap/64) rounded up to 16 words (128 B); pad bits
  *   are zero.  5008 haplotypes -> 79 words -> 640-byte rows.  A *mask* plane selects the
  *   haplotypes of the chosen samples (get_sample_names.py:17-31); N = popcount(mask).
+ *   Genotype rows that are not complete phased diploid 0/1 rows -- a missing call ('.', in N but in neither allele count),
+ *   a haploid sample (one list element), an allele code other than 0 / 1, unphased '/' -- are kept with two more planes
+ *   (slot present, allele == 0) and every pair with such a variant is computed from explicit counts with the pairing's own N,
+ *   exactly as calc_ld.py:30-40 treats the lists the drivers build with `+= rec.samples[name]['GT']`, including zip()'s
+ *   position-by-position pairing of lists of unequal ploidy.  A store's common ploidy pattern (e.g. "males haploid" on chrX)
+ *   stays on the fast paths: it is folded into the mask.  Rounded values beyond 1.6383 (possible only with many non-0/1
+ *   entries) saturate the 14-bit fields.
  *
  * Packed pair result (uint32) -- the reference's rounded outputs (calc_ld.py:94-95) as integers:
  *   bits  0..13  round(r2, 4) * 10^4          (0..10000)
@@ -160,8 +167,10 @@ int32_t ldx_store_planes_ptr(const ldx_store *store, void **dev_ptr_out);
 /* GPU bit-packing of VCF genotype text (kernel K1).  `text` is host memory holding, for each of
  * n_rows variants, n_samples fields "a|b" each followed by one separator byte, starting at
  * byte row_off[i] (row_off == NULL: row i starts at i * row_pitch).  Rows land at store rows
- * first_row...  row_status[i] (may be NULL) = 0 ok, 1 = a field outside the phased diploid
- * biallelic alphabet {0|0, 0|1, 1|0, 1|1} (such rows are packed with non-'1' alleles as 0). */
+ * first_row...  row_status[i] (may be NULL): bit 0 = a field outside the phased diploid biallelic alphabet {0|0, 0|1, 1|0,
+ * 1|1}: the row was parsed again in full ("a", "a|b", "a/b" with a, b = '.' or a number; sub-fields after ':' ignored; the
+ * row ends at its newline) and takes the general route; bit 3 = not even that parser takes it (more than two alleles in a
+ * field, an empty field, fewer than n_samples fields): its planes are undefined and callers should refuse the file. */
 int32_t ldx_store_pack_gt(ldx_store *store, int64_t first_row, int64_t n_rows, const uint8_t *text,
                           int64_t text_bytes, const int64_t *row_off, int64_t row_pitch,
                           int32_t n_samples, uint8_t *row_status);
@@ -174,8 +183,9 @@ int32_t ldx_store_pack_gt(ldx_store *store, int64_t first_row, int64_t n_rows, c
  * write the window annotations (pos0, end0, idnum, eligible = rs\d+$ and not MULTI_ALLELIC,
  * ld_area.py:222-225) into a NEW store and bit-pack the genotypes (K1).  rows_out[rows_cap] receives one
  * record per variant in file order (= store row); *n_rows_out = their number (LDX_ERR_CAPACITY if > rows_cap).
- * status: bit 0 = a genotype outside {0|0,0|1,1|0,1|1} (packed with non-'1' as 0), bit 1 = fewer than 9 + n_samples
- * columns (row kept, all-reference, not eligible), bit 2 = POS is not a number. */
+ * status: bit 0 = a genotype field outside {0|0,0|1,1|0,1|1} (the row was parsed in full and takes the general route, see
+ * ldx_store_pack_gt), bit 1 = fewer than 9 + n_samples columns (row kept, all-reference, not eligible), bit 2 = POS is not a
+ * number, bit 3 = a genotype field no parser takes (more than two alleles, empty). */
 typedef struct ldx_vcf_row {
     int64_t line_off;                 /* byte offset of the line in the text */
     int64_t idnum;                    /* digits of an rs\d+ ID, else -1 - row */
@@ -216,6 +226,11 @@ int32_t ldx_store_load(ldx_ctx *ctx, const char *path, ldx_store **store_out);
 int32_t ldx_store_set_mask(ldx_store *store, const uint64_t *mask);
 /* n1_out[n_variants], p_e4_out[n_variants] = round(n1/N, 4)*10^4 (ld_area.py:188-189); any may be NULL. */
 int32_t ldx_store_counts(const ldx_store *store, int32_t *n1_out, int32_t *p_e4_out, int32_t *n_hap_sel_out);
+/* Per-row facts of the general route under the current selection (any pointer may be NULL): n1_out[v] = the variant's alt
+ * count, len_out[v] = the length of its own genotype list (calc_ld.py:31 for the variant alone: N for a complete row),
+ * kind_out[v] = -1 for a row on the fast paths, >= 0 or -2 for a row of the general route; *n_general_out = how many of those
+ * the store has.  The alt frequency calc_ld reports for var_2 of a pair (a, b) is round(n1[b] / min(len[a], len[b]), 4). */
+int32_t ldx_store_row_counts(const ldx_store *store, int32_t *n1_out, int32_t *len_out, int32_t *kind_out, int64_t *n_general_out);
 /* New store holding only the selected haplotype columns (sel[k] = source haplotype of new
  * haplotype k), mask = all ones: 5x less HBM traffic for a 503-sample subset. */
 int32_t ldx_store_subset(const ldx_store *store, const int32_t *sel, int32_t n_sel, ldx_store **store_out);

@@ -74,6 +74,7 @@ SIGNATURES = {
     "ldx_store_set_mask": [_vp, _vp],
     "ldx_store_counts": [_vp, _vp, _vp, _P(_i32)],
     "ldx_store_subset": [_vp, _vp, _i32, _P(_vp)],
+    "ldx_store_row_counts": [_vp, _vp, _vp, _vp, _P(_i64)],
     "ldx_store_set_annotations": [_vp, _vp, _vp, _vp, _vp],
     "ldx_pairs": [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "ldx_window": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _P(_i64), _P(_i64)],

@@ -387,8 +387,35 @@ static int settle_before_host_call(ldx_ctx *ctx) {
     return ctx->pending_q.empty() ? (int)LDX_OK : resolve_pending(ctx, nullptr);
 }
 
+// The general route's finalisation (ldx_common.cuh::finalise_general) on the host, with the real libm pow: calc_ld.py:33-97 from
+// explicit counts.
+static uint32_t host_finalise_general(const FixupRec &r, double *r2_raw) {
+    if (r2_raw) *r2_raw = 0.0;
+    if (r.n_pair <= 0) return LDX_DP_INT0 | LDX_R2_INT0;
+    const double N = (double)r.n_pair;
+    const double f11 = (double)r.n11 / N;
+    const double pa = (double)r.n1a / N, qa = (double)r.n0a / N, pb = (double)r.n1b / N, qb = (double)r.n0b / N;
+    const double t = pa * pb;
+    const double d = f11 - t;
+    double bound;
+    if (d >= 0.0) { const double x = pa * qb, y = qa * pb; bound = (y < x) ? y : x; }
+    else { const double x = -t, y = -(qa * qb); bound = (y > x) ? y : x; }
+    if (bound == 0.0) return LDX_DP_INT0 | LDX_R2_INT0;
+    const double dp = d / bound;
+    uint32_t word = ((uint32_t)std::fmin(host_round4_e4(dp), 16383.0)) << LDX_DP_SHIFT;      // the 14-bit fields saturate (finalise_general)
+    if (dp != 0.0) {
+        const double r2 = libm_pow(d, 2.0) / (((pa * qa) * pb) * qb);
+        if (r2_raw) *r2_raw = r2;
+        word |= (uint32_t)std::fmin(host_round4_e4(r2), 16383.0);
+    } else word |= LDX_R2_INT0;
+    return word;
+}
+static uint32_t host_finalise_rec(const FixupRec &r, double N, double *r2_raw) {
+    return r.n_pair != 0 ? host_finalise_general(r, r2_raw) : host_finalise_packed(N, r.n11, r.n1a, r.n1b, r2_raw);
+}
+
 static uint32_t settle_word(const FixupRec &r, double N, int measure, int has_thres, int thres_e4) {
-    uint32_t w = host_finalise_packed(N, r.n11, r.n1a, r.n1b, nullptr);
+    uint32_t w = host_finalise_rec(r, N, nullptr);
     if (has_thres && word_measure(w, measure) < thres_e4) w |= LDX_BELOW_THRES;
     return w;
 }
@@ -476,7 +503,7 @@ extern "C" int32_t ldx_finalise_counts(ldx_ctx *ctx, int32_t n_hap, const int32_
     LDX_TRY(collect_fixups(ctx, recs));   // synchronises
     for (const FixupRec &r : recs) {
         double r2_exact;
-        const uint32_t w = host_finalise_packed(fc.n_hap, r.n11, r.n1a, r.n1b, &r2_exact);
+        const uint32_t w = host_finalise_rec(r, fc.n_hap, &r2_exact);
         if (packed) packed[r.out_index] = w;
         if (r2) r2[r.out_index] = r2_exact;
     }
@@ -499,6 +526,16 @@ extern "C" int32_t ldx_store_create(ldx_ctx *ctx, int64_t n_variants, int32_t n_
     cudaError_t e = cudaMalloc(&s->d_planes, nv * s->stride_words * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMemsetAsync(s->d_planes, 0, nv * s->stride_words * sizeof(uint64_t), ctx->stream);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_mask, s->stride_words * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_mask_user, s->stride_words * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_common, s->stride_words * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_all_slots, s->stride_words * sizeof(uint64_t));
+    if (e == cudaSuccess) {
+        // the common presence pattern of a fresh store: every one of the n_hap slots (complete diploid rows)
+        s->h_common.assign((size_t)s->stride_words, 0);
+        for (int h = 0; h < n_hap; ++h) s->h_common[(size_t)(h >> 6)] |= 1ull << (h & 63);
+        e = cudaMemcpy(s->d_all_slots, s->h_common.data(), s->stride_words * sizeof(uint64_t), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(s->d_common, s->h_common.data(), s->stride_words * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    }
     // STORE_FREQ_PAD zeroed records past the last variant: the tcgen05 engine's direct mode reads whole 128-row tiles
     if (e == cudaSuccess) e = cudaMalloc(&s->d_freq, (nv + STORE_FREQ_PAD) * sizeof(VarFreq));
     if (e == cudaSuccess) e = cudaMemsetAsync(s->d_freq, 0, (nv + STORE_FREQ_PAD) * sizeof(VarFreq), ctx->stream);
@@ -513,6 +550,8 @@ extern "C" int32_t ldx_store_destroy(ldx_store *s) {
     cudaStreamSynchronize(s->ctx->stream);
     s->ctx->rows_cache_valid = false;          // a staged variant list validated against this store means nothing to the next one
     cudaFree(s->d_planes); cudaFree(s->d_mask); cudaFree(s->d_freq);
+    cudaFree(s->d_mask_user); cudaFree(s->d_common); cudaFree(s->d_all_slots); cudaFree(s->d_kind); cudaFree(s->d_aux); cudaFree(s->d_gen);
+    cudaFree(s->d_row_len); cudaFree(s->d_row_n1);
     cudaFree(s->d_pos0); cudaFree(s->d_end0); cudaFree(s->d_idnum); cudaFree(s->d_eligible);
     delete s;
     return LDX_OK;
@@ -544,30 +583,35 @@ extern "C" int32_t ldx_store_pack_gt(ldx_store *s, int64_t first_row, int64_t n_
     LDX_TRY(check_rows(s, first_row, n_rows));
     LDX_REQUIRE(text && text_bytes > 0, "text is empty");
     LDX_REQUIRE(n_samples > 0 && 2 * n_samples == s->n_hap, "n_samples does not match the store (n_hap = 2 * n_samples)");
-    const int64_t row_bytes = 4ll * n_samples - 1;   // the last separator need not exist
+    // a row of plain diploid fields is 4 * n_samples - 1 bytes (the last separator need not exist); haploid fields make it shorter
+    const int64_t row_bytes = 4ll * n_samples - 1, min_bytes = 2ll * n_samples - 1;
     if (row_off) {
         for (int64_t i = 0; i < n_rows; ++i)
-            LDX_REQUIRE(row_off[i] >= 0 && row_off[i] + row_bytes <= text_bytes, "row_off outside text");
+            LDX_REQUIRE(row_off[i] >= 0 && row_off[i] + min_bytes <= text_bytes, "row_off outside text");
     } else {
-        LDX_REQUIRE(row_pitch >= row_bytes && (n_rows == 0 || (n_rows - 1) * row_pitch + row_bytes <= text_bytes), "row_pitch/text_bytes mismatch");
+        LDX_REQUIRE(row_pitch >= min_bytes && (n_rows == 0 || (n_rows - 1) * row_pitch + min_bytes <= text_bytes), "row_pitch/text_bytes mismatch");
     }
     if (n_rows == 0) return LDX_OK;
     ldx_ctx *ctx = s->ctx;
     LDX_CUDA(cudaSetDevice(ctx->device));
     uint8_t *d_text, *d_status; int64_t *d_off = nullptr;
-    LDX_TRY(arena_get(ctx, S_TEXT, (size_t)text_bytes + 64, (void **)&d_text));
+    LDX_TRY(arena_get(ctx, S_TEXT, (size_t)text_bytes + (size_t)row_bytes + 64, (void **)&d_text));   // the fast kernel reads a whole plain row from every offset
     LDX_TRY(arena_get(ctx, S_STATUS, (size_t)n_rows, (void **)&d_status));
     LDX_CUDA(cudaMemcpyAsync(d_text, text, (size_t)text_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    LDX_CUDA(cudaMemsetAsync(d_text + text_bytes, '\n', (size_t)row_bytes + 64, ctx->stream));
     if (row_off) {
         LDX_TRY(arena_get(ctx, S_ROWOFF, sizeof(int64_t) * (size_t)n_rows, (void **)&d_off));
         LDX_CUDA(cudaMemcpyAsync(d_off, row_off, sizeof(int64_t) * (size_t)n_rows, cudaMemcpyHostToDevice, ctx->stream));
     }
     LDX_TRY(launch_pack_gt(ctx, d_text, d_off, row_pitch, n_rows, n_samples,
                            s->d_planes + first_row * s->stride_words, s->stride_words, d_status));
-    if (row_status)
-        LDX_CUDA(cudaMemcpyAsync(row_status, d_status, (size_t)n_rows, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint8_t> h_status((size_t)n_rows);
+    LDX_CUDA(cudaMemcpyAsync(h_status.data(), d_status, (size_t)n_rows, cudaMemcpyDeviceToHost, ctx->stream));
     LDX_CUDA(cudaStreamSynchronize(ctx->stream));
     s->mask_set = false;   // counts are stale
+    // rows with a field outside the plain alphabet: parsed again in full (haploid, missing, other codes, '/'), general route
+    LDX_TRY(store_pack_general(s, first_row, n_rows, d_text, text_bytes, d_off, row_pitch, n_samples, h_status.data()));
+    if (row_status) std::memcpy(row_status, h_status.data(), (size_t)n_rows);
     return LDX_OK;
 }
 
@@ -596,20 +640,25 @@ extern "C" int32_t ldx_store_download(const ldx_store *s, int64_t first_row, int
 
 extern "C" int32_t ldx_store_set_mask(ldx_store *s, const uint64_t *mask) {
     LDX_REQUIRE(s && mask, "NULL argument");
-    std::vector<uint64_t> m(s->stride_words, 0);
+    LDX_CUDA(cudaSetDevice(s->ctx->device));
+    if (s->classify_dirty) LDX_TRY(store_classify_rows(s));       // rows were packed since: the common pattern and every row's kind
+    // the selection as given (general rows use it with their own presence planes), and folded with the store's common
+    // presence pattern (all slots unless e.g. the males of chrX are haploid): the mask of the fast paths, N = its popcount
+    std::vector<uint64_t> m(s->stride_words, 0), mu(s->stride_words, 0);
     int64_t n_sel = 0;
     for (int w = 0; w < s->words; ++w) {
         uint64_t x = mask[w];
         if (w == s->words - 1 && (s->n_hap & 63)) x &= (1ull << (s->n_hap & 63)) - 1;   // ignore pad bits
-        m[w] = x;
-        n_sel += __builtin_popcountll(x);
+        mu[w] = x;
+        m[w] = x & s->h_common[(size_t)w];
+        n_sel += __builtin_popcountll(m[w]);
     }
     if (n_sel == 0) return set_error(LDX_ERR_EMPTY, "division by zero");   // empty sample selection, calc_ld.py:33
-    LDX_CUDA(cudaSetDevice(s->ctx->device));
     s->n_sel = (int32_t)n_sel;
     LDX_TRY(make_final_ctx(n_sel, &s->fc));
     LDX_CUDA(cudaMemcpyAsync(s->d_mask, m.data(), sizeof(uint64_t) * s->stride_words, cudaMemcpyHostToDevice, s->ctx->stream));
-    LDX_CUDA(cudaStreamSynchronize(s->ctx->stream));   // m goes out of scope
+    LDX_CUDA(cudaMemcpyAsync(s->d_mask_user, mu.data(), sizeof(uint64_t) * s->stride_words, cudaMemcpyHostToDevice, s->ctx->stream));
+    LDX_CUDA(cudaStreamSynchronize(s->ctx->stream));   // m, mu go out of scope
     LDX_TRY(launch_variant_freq(s));
     s->mask_set = true;
     return LDX_OK;
@@ -633,7 +682,27 @@ extern "C" int32_t ldx_store_counts(const ldx_store *s, int32_t *n1_out, int32_t
             if (n1_out) n1_out[v] = f[v].n1;
             if (p_e4_out) p_e4_out[v] = f[v].p_e4;
         }
+        if (n1_out && s->d_row_n1)            // general rows carry a code in VarFreq.n1: their true counts are kept by K2
+            LDX_CUDA(cudaMemcpy(n1_out, s->d_row_n1, sizeof(int32_t) * (size_t)s->n_variants, cudaMemcpyDeviceToHost));
     }
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_store_row_counts(const ldx_store *s, int32_t *n1_out, int32_t *len_out, int32_t *kind_out, int64_t *n_general_out) {
+    LDX_TRY(require_mask(s));
+    if (n_general_out) *n_general_out = s->n_nonsimple;
+    if (s->n_variants == 0) return LDX_OK;
+    LDX_CUDA(cudaSetDevice(s->ctx->device));
+    const size_t n = (size_t)s->n_variants;
+    if (kind_out) {
+        if (s->d_kind) LDX_CUDA(cudaMemcpy(kind_out, s->d_kind, 4 * n, cudaMemcpyDeviceToHost));
+        else for (size_t v = 0; v < n; ++v) kind_out[v] = -1;
+    }
+    if (len_out) {
+        if (s->d_row_len) LDX_CUDA(cudaMemcpy(len_out, s->d_row_len, 4 * n, cudaMemcpyDeviceToHost));
+        else for (size_t v = 0; v < n; ++v) len_out[v] = s->n_sel;
+    }
+    if (n1_out) LDX_TRY(ldx_store_counts(s, n1_out, nullptr, nullptr));
     return LDX_OK;
 }
 
@@ -642,6 +711,7 @@ extern "C" int32_t ldx_store_subset(const ldx_store *src, const int32_t *sel, in
     LDX_REQUIRE(n_sel > 0, "empty selection");
     for (int32_t k = 0; k < n_sel; ++k) LDX_REQUIRE(sel[k] >= 0 && sel[k] < src->n_hap, "sel[] outside the source haplotypes");
     ldx_ctx *ctx = src->ctx;
+    if (src->classify_dirty) LDX_TRY(store_classify_rows(const_cast<ldx_store *>(src)));      // the common pattern is about to be copied
     ldx_store *dst = nullptr;
     LDX_TRY(ldx_store_create(ctx, src->n_variants, n_sel, &dst));
     int32_t *d_sel;
@@ -649,6 +719,19 @@ extern "C" int32_t ldx_store_subset(const ldx_store *src, const int32_t *sel, in
     if (rc == LDX_OK && cudaMemcpyAsync(d_sel, sel, sizeof(int32_t) * (size_t)n_sel, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
         rc = cuda_fail(cudaGetLastError(), "subset: copy sel");
     if (rc == LDX_OK) rc = launch_subset(src, d_sel, dst);
+    if (rc == LDX_OK && !src->aux_rows.empty()) {
+        // rows of the general route: their present / ref planes and the store's common pattern through the same column gather
+        const int64_t n_aux = (int64_t)src->aux_rows.size();
+        if (cudaMalloc(&dst->d_aux, (size_t)n_aux * 2 * dst->stride_words * sizeof(uint64_t)) != cudaSuccess) { cudaGetLastError(); rc = set_error(LDX_ERR_NOMEM, "subset: aux planes"); }
+        if (rc == LDX_OK) {
+            dst->aux_capacity = n_aux;
+            dst->aux_rows = src->aux_rows;
+            rc = launch_subset_planes(ctx, src->d_aux, src->stride_words, d_sel, n_sel, 2 * n_aux, dst->d_aux, dst->stride_words);
+        }
+        if (rc == LDX_OK) rc = launch_subset_planes(ctx, src->d_common, src->stride_words, d_sel, n_sel, 1, dst->d_common, dst->stride_words);
+        dst->common_loaded = true;                      // the source's pattern restricted to the columns, not the subset's own middle row
+        dst->classify_dirty = true;
+    }
     if (rc == LDX_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "subset: sync");
     if (rc == LDX_OK && src->annotated) {
         const size_t nv = (size_t)src->n_variants;
@@ -744,8 +827,13 @@ extern "C" int32_t ldx_store_save(const ldx_store *s, const char *path) {
     st.fh = fopen(path, "wb");
     if (!st.fh) return set_error(LDX_ERR_ARG, std::string("store file: cannot create ") + path);
     StoreFileHeader h = {};
-    std::memcpy(h.magic, "LDXSTOR1", 8);
+    // rows with aux planes (the general route) make it a version-2 file: reserved[0] = their number; the section follows the
+    // annotations as {row of every aux slot (int64), the slots' present / ref planes}.  kind[] and the common presence pattern
+    // are re-derived when the loaded store's samples are selected, exactly as after an ingest.
+    const int64_t n_aux = (int64_t)s->aux_rows.size();
+    std::memcpy(h.magic, n_aux ? "LDXSTOR2" : "LDXSTOR1", 8);
     h.n_variants = s->n_variants; h.n_hap = s->n_hap; h.stride_words = s->stride_words; h.annotated = s->annotated ? 1 : 0;
+    h.reserved[0] = (int32_t)n_aux;
     if (fwrite(&h, sizeof h, 1, st.fh) != 1) return set_error(LDX_ERR_STATE, "store file: write failed");
     const size_t n = (size_t)s->n_variants;
     LDX_TRY(stream_out(ctx, st, s->d_planes, n * s->stride_words * sizeof(uint64_t)));
@@ -754,6 +842,10 @@ extern "C" int32_t ldx_store_save(const ldx_store *s, const char *path) {
         LDX_TRY(stream_out(ctx, st, s->d_end0, n * 4));
         LDX_TRY(stream_out(ctx, st, s->d_idnum, n * 8));
         LDX_TRY(stream_out(ctx, st, s->d_eligible, n));
+    }
+    if (n_aux) {
+        if (fwrite(s->aux_rows.data(), sizeof(int64_t), (size_t)n_aux, st.fh) != (size_t)n_aux) return set_error(LDX_ERR_STATE, "store file: write failed");
+        LDX_TRY(stream_out(ctx, st, s->d_aux, (size_t)n_aux * 2 * s->stride_words * sizeof(uint64_t)));
     }
     if (fflush(st.fh) != 0) return set_error(LDX_ERR_STATE, "store file: write failed");
     return LDX_OK;
@@ -767,8 +859,10 @@ extern "C" int32_t ldx_store_load(ldx_ctx *ctx, const char *path, ldx_store **st
     st.fh = fopen(path, "rb");
     if (!st.fh) return set_error(LDX_ERR_ARG, std::string("store file: cannot open ") + path);
     StoreFileHeader h;
-    if (fread(&h, sizeof h, 1, st.fh) != 1 || std::memcmp(h.magic, "LDXSTOR1", 8) != 0)
+    if (fread(&h, sizeof h, 1, st.fh) != 1 || (std::memcmp(h.magic, "LDXSTOR1", 8) != 0 && std::memcmp(h.magic, "LDXSTOR2", 8) != 0))
         return set_error(LDX_ERR_ARG, "store file: not an ldx store (bad magic)");
+    const int64_t n_aux = h.magic[7] == '2' ? h.reserved[0] : 0;
+    LDX_REQUIRE(n_aux >= 0 && n_aux <= h.n_variants, "store file: bad header");
     LDX_REQUIRE(h.n_variants >= 0 && h.n_variants < (1ll << 31) && h.n_hap > 0 && h.n_hap <= (1 << 24), "store file: bad header");
     LDX_TRY(staging_buffer(ctx, st));
     ldx_store *s = nullptr;
@@ -788,6 +882,17 @@ extern "C" int32_t ldx_store_load(ldx_ctx *ctx, const char *path, ldx_store **st
         if (rc == LDX_OK) rc = stream_in(ctx, st, s->d_idnum, n * 8);
         if (rc == LDX_OK) rc = stream_in(ctx, st, s->d_eligible, n);
         if (rc == LDX_OK) s->annotated = true;
+    }
+    if (rc == LDX_OK && n_aux) {
+        s->aux_rows.resize((size_t)n_aux);
+        if (fread(s->aux_rows.data(), sizeof(int64_t), (size_t)n_aux, st.fh) != (size_t)n_aux) rc = set_error(LDX_ERR_ARG, "store file: truncated");
+        for (int64_t k = 0; k < n_aux && rc == LDX_OK; ++k)
+            if (s->aux_rows[(size_t)k] < -1 || s->aux_rows[(size_t)k] >= s->n_variants) rc = set_error(LDX_ERR_ARG, "store file: bad aux section");
+        if (rc == LDX_OK && cudaMalloc(&s->d_aux, (size_t)n_aux * 2 * s->stride_words * sizeof(uint64_t)) != cudaSuccess) {
+            cudaGetLastError(); rc = set_error(LDX_ERR_NOMEM, "store file: aux planes");
+        }
+        if (rc == LDX_OK) { s->aux_capacity = n_aux; rc = stream_in(ctx, st, s->d_aux, (size_t)n_aux * 2 * s->stride_words * sizeof(uint64_t)); }
+        s->classify_dirty = true;
     }
     if (rc != LDX_OK) { ldx_store_destroy(s); return rc; }
     *store_out = s;
@@ -826,7 +931,7 @@ extern "C" int32_t ldx_pairs(ldx_store *s, const int64_t *ia, const int64_t *ib,
     LDX_TRY(collect_fixups(ctx, recs));   // synchronises
     for (const FixupRec &r : recs) {
         double r2_exact;
-        const uint32_t w = host_finalise_packed(s->fc.n_hap, r.n11, r.n1a, r.n1b, &r2_exact);
+        const uint32_t w = host_finalise_rec(r, s->fc.n_hap, &r2_exact);
         if (packed) packed[r.out_index] = w;
         if (r2) r2[r.out_index] = r2_exact;
     }

@@ -19,6 +19,17 @@ __device__ __forceinline__ void fixup_append(const FixupSink &s, uint64_t out_in
     if (slot < s.capacity) {
         FixupRec r;
         r.out_index = out_index | s.tag; r.n11 = n11; r.n1a = n1a; r.n1b = n1b; r.packed = packed;
+        r.n_pair = 0; r.n0a = 0; r.n0b = 0; r.pad = 0;
+        s.recs[slot] = r;
+    }
+}
+// The same for a pair of the general route: the host needs all six counts (n_pair != 0 marks the record).
+__device__ __forceinline__ void fixup_append_general(const FixupSink &s, uint64_t out_index, const GenCounts &c, uint32_t packed) {
+    const uint32_t slot = atomicAdd(s.count, 1u);
+    if (slot < s.capacity) {
+        FixupRec r;
+        r.out_index = out_index | s.tag; r.n11 = c.n11; r.n1a = c.n1a; r.n1b = c.n1b; r.packed = packed;
+        r.n_pair = c.n_pair; r.n0a = c.n0a; r.n0b = c.n0b; r.pad = 0;
         s.recs[slot] = r;
     }
 }

@@ -88,6 +88,24 @@ struct ldx_store {
     int64_t *d_idnum = nullptr;
     uint8_t *d_eligible = nullptr;
     bool annotated = false;
+    // Variants that are not complete phased diploid 0/1 rows with the store's common ploidy pattern (see
+    // "the general route" in ldx_common.cuh).  kind[v]: -1 simple, g >= 0 = index of its aux planes, -2 = all slots present and
+    // 0/1 without aux planes (only when the common pattern is not all-diploid).  All null / zero for a store without such rows.
+    int32_t *d_kind = nullptr;            // [n_variants]
+    uint64_t *d_aux = nullptr;            // [n_general][2][stride_words]: present, ref
+    int64_t n_general = 0;                // rows with aux planes
+    int64_t n_nonsimple = 0;              // rows with kind != -1
+    uint64_t *d_common = nullptr;         // [stride_words] the common presence pattern (all 2 * n_samples slots unless told otherwise)
+    uint64_t *d_all_slots = nullptr;      // [stride_words] n_hap ones
+    uint64_t *d_mask_user = nullptr;      // [stride_words] the selection as given (d_mask = selection & common pattern)
+    ldx::GenStore *d_gen = nullptr;       // device copy of the pointers above, for the kernels' general route
+    std::vector<int64_t> aux_rows;        // host: aux slot k holds the planes of row aux_rows[k] (-1: slot abandoned)
+    int64_t aux_capacity = 0;             // slots allocated in d_aux
+    bool classify_dirty = false;          // rows were (re)packed since kind[] / the common pattern were last derived
+    bool common_loaded = false;           // the common pattern came with a store file / a subset: do not re-derive it
+    std::vector<uint64_t> h_common;       // host copy of d_common (ldx_store_set_mask folds it into the selection)
+    int32_t *d_row_len = nullptr;         // [n_variants] K2: len of the variant's own genotype list under the selection (calc_ld.py:31)
+    int32_t *d_row_n1 = nullptr;          // [n_variants] K2: its alt count under the selection (the true one, also for general rows)
     // TMA tensor map of the planes ([n_variants][stride_words * 2] uint32, box 8 x 128), encoded on first use by the
     // tcgen05 engine's direct mode (ldx_triangle_mma.cu); 128 bytes, 64-byte aligned as the driver requires
     alignas(64) unsigned char tmap[128] = {};
@@ -116,7 +134,22 @@ int launch_pack_gt(ldx_ctx *ctx, const uint8_t *d_text, const int64_t *d_row_off
                    int64_t n_rows, int32_t n_samples, uint64_t *d_planes_first, int32_t stride_words,
                    uint8_t *d_status);
 int launch_variant_freq(ldx_store *s);
+// GT text of rows whose fields are not all plain "a|b" with a, b in {0, 1} (K1's status bit 0): any ploidy <= 2, '.' and other
+// allele codes, '/' or '|', sub-fields after ':'.  d_rows_idx[n] = the rows (relative to d_planes_first), d_row_off their GT
+// text offsets; writes the alt plane, and present / ref planes into d_aux_out[k] (k = position in d_rows_idx);
+// d_status_out[k] bit 3 = a field with more than two alleles or a row that ends early.
+int launch_pack_gt_general(ldx_ctx *ctx, const uint8_t *d_text, int64_t text_bytes, const int64_t *d_row_off, int64_t row_pitch, const int64_t *d_rows_idx,
+                           int64_t n, int32_t n_samples, uint64_t *d_planes_first, int32_t stride_words, uint64_t *d_aux_out, uint8_t *d_status_out);
+// After parsing: the common presence pattern and kind[] of every row (s->aux_rows says which rows have aux planes).
+int store_classify_rows(ldx_store *s);
+// Host side of K1 for rows the fast kernel flagged (status bit 0): aux slots, the general parser, bookkeeping.  d_status / h_status:
+// the fast kernel's per-row status on the device / host (n_rows of them); h_status gets bit 3 for rows even the general parser rejects.
+int store_pack_general(ldx_store *s, int64_t first_row, int64_t n_rows, const uint8_t *d_text, int64_t text_bytes, const int64_t *d_row_off,
+                       int64_t row_pitch, int32_t n_samples, uint8_t *h_status);
+int store_publish_gen(ldx_store *s);      // (re)build d_gen after the pointers changed
 int launch_subset(const ldx_store *src, const int32_t *d_sel, ldx_store *dst);
+int launch_subset_planes(ldx_ctx *ctx, const uint64_t *d_src, int32_t src_stride, const int32_t *d_sel, int32_t n_sel, int64_t n_rows, uint64_t *d_dst,
+                         int32_t dst_stride);
 int launch_pairs(ldx_store *s, const int64_t *d_ia, const int64_t *d_ib, int64_t n, int32_t *d_n11,
                  double *d_d, double *d_dp, double *d_r2, uint32_t *d_packed);
 int launch_finalise_counts(ldx_ctx *ctx, const ldx::FinalCtx &fc, const int32_t *d_n11, const int32_t *d_n1a,

@@ -16,7 +16,8 @@ __global__ void __launch_bounds__(PAIRS_THREADS)
 pairs_kernel(const uint4 *__restrict__ planes, const uint4 *__restrict__ mask, int32_t stride_u4,
              const VarFreq *__restrict__ freq, FinalCtx fc, const int64_t *__restrict__ ia,
              const int64_t *__restrict__ ib, int64_t n, int32_t *__restrict__ o_n11, double *__restrict__ o_d,
-             double *__restrict__ o_dp, double *__restrict__ o_r2, uint32_t *__restrict__ o_packed, FixupSink fix) {
+             double *__restrict__ o_dp, double *__restrict__ o_r2, uint32_t *__restrict__ o_packed, FixupSink fix,
+             const GenStore *__restrict__ gen) {
     const int sub = threadIdx.x & 7;
     const int64_t group0 = ((int64_t)blockIdx.x * PAIRS_THREADS + threadIdx.x) >> 3;
     const int64_t n_groups = ((int64_t)gridDim.x * PAIRS_THREADS) >> 3;
@@ -37,6 +38,19 @@ pairs_kernel(const uint4 *__restrict__ planes, const uint4 *__restrict__ mask, i
         cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
         if (sub == 0 && valid) {
             const VarFreq fa = freq[ra], fb = freq[rb];
+            if (gen && (fa.n1 | fb.n1) < 0) {                 // a variant of the general route: explicit counts, the pairing's own N
+                const GenCounts c = general_pair_counts(*gen, ra, fa.n1, rb, fb.n1);
+                const GenFinal g = finalise_general(c);
+                if (o_n11) o_n11[k] = c.n11;
+                if (o_d) o_d[k] = g.d;
+                if (o_dp) o_dp[k] = g.dprime;
+                if (o_r2) o_r2[k] = g.r2;
+                if (o_packed) {
+                    o_packed[k] = g.packed;
+                    if (g.packed & LDX_R2_NEARTIE) fixup_append_general(fix, (uint64_t)k, c, g.packed);
+                }
+                continue;
+            }
             const PairFinal f = finalise_pair(cnt, fa, fb, fc);
             if (o_n11) o_n11[k] = cnt;
             if (o_d) o_d[k] = f.d;
@@ -60,7 +74,7 @@ int launch_pairs(ldx_store *s, const int64_t *d_ia, const int64_t *d_ib, int64_t
     pairs_kernel<<<(int)blocks, PAIRS_THREADS, 0, ctx->stream>>>(
         reinterpret_cast<const uint4 *>(s->d_planes), reinterpret_cast<const uint4 *>(s->d_mask),
         s->stride_words / 2, s->d_freq, s->fc, d_ia, d_ib, n, d_n11, d_d, d_dp, d_r2, d_packed,
-        FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity, ctx->fix_tag});
+        FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity, ctx->fix_tag}, s->n_nonsimple > 0 ? s->d_gen : nullptr);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
     return LDX_OK;

@@ -132,6 +132,31 @@ variant_freq_kernel(const uint4 *__restrict__ planes, const uint4 *__restrict__ 
     }
 }
 
+// One thread per variant, after variant_freq_kernel: rows of the general route get their coded record.
+__global__ void __launch_bounds__(256)
+general_freq_kernel(const GenStore *__restrict__ G, const int32_t *__restrict__ kind, int64_t n_variants, int32_t n_sel, VarFreq *__restrict__ freq,
+                    int32_t *__restrict__ row_len, int32_t *__restrict__ row_n1) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_variants) return;
+    const int32_t k = kind[v];
+    if (k == -1) { row_len[v] = n_sel; row_n1[v] = freq[v].n1; return; }
+    const int32_t code = k >= 0 ? -1 - k : GEN_FULL;
+    int32_t len = 0, n1 = 0;
+    for (int w = 0; w < G->words; ++w) {
+        uint64_t present, alt, ref;
+        gen_row_word(*G, v, code, w, present, alt, ref);
+        len += __popcll(present); n1 += __popcll(alt);
+    }
+    VarFreq f;
+    f.n1 = code; f.p = 0.0; f.q = 0.0; f.pq = 0.0; f.p_e4 = 0;
+    if (len > 0) {
+        bool tie;
+        f.p_e4 = (int32_t)round4_e4_wide(__ddiv_rn((double)n1, (double)len), tie);
+    }
+    freq[v] = f;
+    row_len[v] = len; row_n1[v] = n1;
+}
+
 int launch_variant_freq(ldx_store *s) {
     if (s->n_variants <= 0) return LDX_OK;
     ldx_ctx *ctx = s->ctx;
@@ -146,6 +171,21 @@ int launch_variant_freq(ldx_store *s) {
         s->stride_words / 2, s->n_variants, s->fc, s->d_freq);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
+    if (s->n_nonsimple > 0) {
+        // rows of the general route: their own list length and allele counts under the selection (calc_ld.py:31, :37-40 for
+        // the variant alone), the coded VarFreq.n1 that sends every pair with them down the general route, and
+        // round(alt freq, 4) of their OWN list (ld_area.py:188-189)
+        const size_t nv = (size_t)s->n_variants;
+        if (!s->d_row_len) LDX_CUDA(cudaMalloc(&s->d_row_len, nv * sizeof(int32_t)));
+        if (!s->d_row_n1) LDX_CUDA(cudaMalloc(&s->d_row_n1, nv * sizeof(int32_t)));
+        general_freq_kernel<<<(unsigned)((s->n_variants + 255) / 256), 256, 0, ctx->stream>>>(s->d_gen, s->d_kind, s->n_variants, s->n_sel, s->d_freq,
+                                                                                              s->d_row_len, s->d_row_n1);
+        ctx->launches++;
+        LDX_CUDA(cudaGetLastError());
+    } else {
+        if (s->d_row_len) { cudaFree(s->d_row_len); s->d_row_len = nullptr; }
+        if (s->d_row_n1) { cudaFree(s->d_row_n1); s->d_row_n1 = nullptr; }
+    }
     return LDX_OK;
 }
 
@@ -180,6 +220,20 @@ int launch_subset(const ldx_store *src, const int32_t *d_sel, ldx_store *dst) {
     if (blocks > cap) blocks = cap;
     subset_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(src->d_planes, src->stride_words, d_sel, dst->n_hap,
                                                          src->n_variants, dst->d_planes, dst->stride_words);
+    ctx->launches++;
+    LDX_CUDA(cudaGetLastError());
+    return LDX_OK;
+}
+
+// the same gather for any [n_rows][src_stride] block of planes (aux planes, the common pattern)
+int launch_subset_planes(ldx_ctx *ctx, const uint64_t *d_src, int32_t src_stride, const int32_t *d_sel, int32_t n_sel, int64_t n_rows, uint64_t *d_dst,
+                         int32_t dst_stride) {
+    if (n_rows <= 0) return LDX_OK;
+    const int64_t total = n_rows * dst_stride;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    subset_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(d_src, src_stride, d_sel, n_sel, n_rows, d_dst, dst_stride);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
     return LDX_OK;

@@ -367,6 +367,9 @@ struct SetRec {
     int64_t out_off;             // packed index of the first pair of the call's row range: outputs are relative to it
     uint32_t *packed; int32_t *n11;
     uint64_t fix_tag;            // ORed into the out_index of the set's near-tie records (FIX_TAG_SHIFT)
+    // the general route (variants with missing calls / haploid samples / other codes, ldx_common.cuh): the set's store and the
+    // store rows of its matrix rows (rows == nullptr: store row = row0 + matrix row); gen == nullptr: the store has none
+    const GenStore *gen; const int64_t *rows; int64_t row0;
 };
 struct MmaArgs {
     const uint4 *bits, *bits_rev; int32_t kc_count;
@@ -430,7 +433,9 @@ struct __align__(16) ColPair {
 __device__ __forceinline__ float minor_f(int32_t n1t, int32_t Nn) { return __int2float_rn(min(n1t, Nn - n1t)); }
 __device__ __forceinline__ float rcp_nn(int32_t n1t, int32_t Nn) {         // 1 / (c' * c0'): the product is exact (<= 2^24)
     const int32_t c = min(n1t, Nn - n1t);
-    return rcp_approx(__int2float_rn(c * (Nn - c)));
+    // a variant of the general route (coded, negative count): NaN, so that the screen of every pair with it fails and the pair
+    // is deferred to settle_slow_pair, which takes the general route
+    return n1t < 0 ? __int_as_float(0x7fc00000) : rcp_approx(__int2float_rn(c * (Nn - c)));
 }
 // The same per row variant of an epilogue lane, packed once per pass.
 struct RowP { uint64_t na2, ra2; float n1f; };    // {-a', -a'}, {ra, ra}, a'
@@ -552,11 +557,25 @@ __device__ __forceinline__ void settle_slow_pair(const uint4 e, const MmaArgs &A
     const SetRec &S = A.set[e.w];
     const int64_t r = e.x, col = e.y;
     const VarFreq fa = A.freq_rows[S.base_row + r], fb = A.freq_rows[S.base_row + col];
+    const uint64_t idx = (uint64_t)(r * (r - 1) / 2 + col - S.out_off);
+    if ((fa.n1 | fb.n1) < 0 && S.gen) {                                // a variant of the general route: explicit counts from the store's planes
+        const int64_t sa = S.rows ? S.rows[r] : S.row0 + r, sb = S.rows ? S.rows[col] : S.row0 + col;
+        const GenCounts c = general_pair_counts(*S.gen, sa, fa.n1, sb, fb.n1);
+        uint32_t w = finalise_general(c).packed;
+        w |= (((w >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;
+        if (w & LDX_R2_NEARTIE) {
+            FixupSink fx = A.fix;
+            fx.tag = S.fix_tag;
+            fixup_append_general(fx, idx, c, w);
+        }
+        S.packed[idx] = w;
+        if (S.n11) S.n11[idx] = c.n11;
+        return;
+    }
     const int32_t n11 = true_n11((int32_t)e.z, fa.n1, fb.n1, A.n_sel);
     const PairFinal f = finalise_pair(n11, fa, fb, A.fc);              // var_1 = row, var_2 = column
     uint32_t w = f.packed;
     w |= (((w >> m_shift) & LDX_R2_MASK) < thres) ? LDX_BELOW_THRES : 0u;
-    const uint64_t idx = (uint64_t)(r * (r - 1) / 2 + col - S.out_off);
     if (w & LDX_R2_NEARTIE) {
         FixupSink fx = A.fix;
         fx.tag = S.fix_tag;
@@ -1356,6 +1375,8 @@ int launch_triangle_mma(ldx_ctx *ctx, const MmaSetDesc *sets, int n_sets, const 
         SetRec &r = A.set[k];
         r.base_row = base_row[k]; r.v = sets[k].v; r.out_off = sets[k].row_begin * (sets[k].row_begin - 1) / 2;
         r.packed = sets[k].d_packed; r.n11 = sets[k].d_n11; r.fix_tag = sets[k].fix_tag;
+        r.gen = sets[k].s->n_nonsimple > 0 ? sets[k].s->d_gen : nullptr;
+        r.rows = d_rows + sets[k].rows_off; r.row0 = sets[k].row0;
     }
     A.n_sel = s0->n_sel;
     {   // guard band of the screening arithmetic (see fast_pair2).  Its fp32 half needs the minor-allele products exact
@@ -1383,6 +1404,7 @@ int launch_triangle_mma(ldx_ctx *ctx, const MmaSetDesc *sets, int n_sets, const 
         A.row0 = (int32_t)sets[0].row0;
         A.freq_rows = s0->d_freq + sets[0].row0;          // padded by STORE_FREQ_PAD zeroed entries: whole tiles may be read
         A.bits = A.bits_rev = nullptr;
+        A.set[0].rows = nullptr;                          // store row = row0 + matrix row
     }
     int rc;
     if (n_tile == 64) rc = single ? launch_tiles_s<64, false, true, false>(ctx, A) : launch_tiles_s<64, false, false, false>(ctx, A);

@@ -32,6 +32,7 @@ struct TriArgs {
     int measure, has_thres, thres_e4;
     uint32_t *packed; int32_t *n11;
     FixupSink fix;
+    const GenStore *gen;           // the general route, or nullptr
 };
 
 __device__ __forceinline__ void tile_coords(int64_t t, int64_t &bi, int64_t &bj) {
@@ -112,10 +113,21 @@ triangle_popc_kernel(const TriArgs A) {
             const int64_t c = c0 + tx * 4 + j;
             if (c >= r) continue;
             const VarFreq fb = fb_s[tx * 4 + j];
+            const int64_t o = rbase + c;
+            if (A.gen && (fa.n1 | fb.n1) < 0) {               // a variant of the general route
+                const GenCounts gc = general_pair_counts(*A.gen, ra_s[ty * 4 + i], fa.n1, rb_s[tx * 4 + j], fb.n1);
+                uint32_t word = finalise_general(gc).packed;
+                if (A.has_thres && measure_e4(word, A.measure) < A.thres_e4) word |= LDX_BELOW_THRES;
+                if (A.packed) {
+                    A.packed[o] = word;
+                    if (word & LDX_R2_NEARTIE) fixup_append_general(A.fix, (uint64_t)o, gc, word);
+                }
+                if (A.n11) A.n11[o] = gc.n11;
+                continue;
+            }
             const PairFinal f = finalise_pair(cnt[i][j], fa, fb, A.fc);   // var_1 = row, var_2 = col
             uint32_t word = f.packed;
             if (A.has_thres && measure_e4(word, A.measure) < A.thres_e4) word |= LDX_BELOW_THRES;
-            const int64_t o = rbase + c;
             if (A.packed) {
                 A.packed[o] = word;
                 if (word & LDX_R2_NEARTIE) fixup_append(A.fix, (uint64_t)o, cnt[i][j], fa.n1, fb.n1, word);
@@ -137,6 +149,7 @@ int launch_triangle_popc(ldx_store *s, const int64_t *d_rows, int64_t v, int64_t
     A.measure = measure; A.has_thres = has_thres; A.thres_e4 = thres_e4;
     A.packed = d_packed; A.n11 = d_n11;
     A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity, ctx->fix_tag};
+    A.gen = s->n_nonsimple > 0 ? s->d_gen : nullptr;
     const int64_t bi_begin = row_begin / TRI_TILE;
     A.tile_begin = bi_begin * (bi_begin + 1) / 2;
     A.out_off = row_begin * (row_begin - 1) / 2;

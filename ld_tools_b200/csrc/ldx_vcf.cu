@@ -97,7 +97,9 @@ parse_lines_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
     field_off[0] = 0;
     for (int64_t i = start; i < end && nf < 10; ++i)
         if (text[i] == '\t') field_off[nf++] = (int32_t)(i + 1 - start);
-    const int64_t need = nf == 10 ? (int64_t)field_off[9] + 4ll * n_samples - 1 : 0;
+    // a record line has the nine fixed columns and n_samples genotype fields of at least one character each (plain diploid
+    // fields take 4 * n_samples - 1 bytes; haploid ones are shorter: K1 sorts that out)
+    const int64_t need = nf == 10 ? (int64_t)field_off[9] + 2ll * n_samples - 1 : 0;
     if (nf < 10 || need > end - start) {
         // not a full record line: kept as a row (the drivers' row numbering follows the file) and flagged
         r.status = 2;
@@ -165,9 +167,11 @@ compact_rows_kernel(const ldx_vcf_row *__restrict__ tmp_rows, const uint32_t *__
 
 // pack status (bit 0) and zeroed planes of malformed rows
 __global__ void __launch_bounds__(256)
-merge_status_kernel(ldx_vcf_row *__restrict__ rows, const uint8_t *__restrict__ pack_status, int64_t n_rows) {
+merge_status_kernel(ldx_vcf_row *__restrict__ rows, const uint8_t *__restrict__ pack_status, int64_t n_rows, uint8_t *__restrict__ eligible) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n_rows && !(rows[r].status & 2)) rows[r].status |= pack_status[r] & 1;
+    if (r >= n_rows || (rows[r].status & 2)) return;
+    rows[r].status |= pack_status[r] & 9;      // bit 0: not plain "a|b" fields (general route), bit 3: no parser takes the genotypes
+    if (pack_status[r] & 8) { rows[r].eligible = 0; eligible[r] = 0; }      // kept as a row, never paired by a window scan
 }
 
 int launch_pack_gt(ldx_ctx *ctx, const uint8_t *d_text, const int64_t *d_row_off, int64_t row_pitch, int64_t n_rows, int32_t n_samples,
@@ -208,12 +212,13 @@ extern "C" int32_t ldx_store_ingest_vcf(ldx_ctx *ctx, const uint8_t *text, int64
     size_t cub_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)(n_blocks + 1), st);
     Carve c1;
-    LDX_TRY(scratch_get(ctx, 0, Carve::pad((size_t)n + 64) + 2 * Carve::pad(((size_t)n_blocks + 1) * 4) + Carve::pad(cub_bytes) + 256, (void **)&c1.base));
-    uint8_t *d_text = c1.take<uint8_t>((size_t)n + 64);
+    LDX_TRY(scratch_get(ctx, 0, Carve::pad((size_t)n + 4 * (size_t)n_samples + 64) + 2 * Carve::pad(((size_t)n_blocks + 1) * 4) + Carve::pad(cub_bytes) + 256, (void **)&c1.base));
+    const size_t text_slack = (size_t)4 * n_samples + 64;      // K1's fast kernel reads a whole plain row from every genotype offset
+    uint8_t *d_text = c1.take<uint8_t>((size_t)n + text_slack);
     uint32_t *d_counts = c1.take<uint32_t>((size_t)n_blocks + 1), *d_base = c1.take<uint32_t>((size_t)n_blocks + 1);
     void *d_cub = c1.take<uint8_t>(cub_bytes);
     LDX_CUDA(cudaMemcpyAsync(d_text, text, (size_t)text_bytes, cudaMemcpyHostToDevice, st));
-    LDX_CUDA(cudaMemsetAsync(d_text + text_bytes, '\n', (size_t)(n - text_bytes) + 64, st));
+    LDX_CUDA(cudaMemsetAsync(d_text + text_bytes, '\n', (size_t)(n - text_bytes) + text_slack, st));
     LDX_CUDA(cudaMemsetAsync(d_counts + n_blocks, 0, sizeof(uint32_t), st));
     count_newlines_kernel<<<(unsigned)n_blocks, NL_THREADS, 0, st>>>(d_text, n, d_counts);
     ctx->launches++;
@@ -275,7 +280,16 @@ extern "C" int32_t ldx_store_ingest_vcf(ldx_ctx *ctx, const uint8_t *text, int64
     }
     if (rc == LDX_OK && n_rec > 0) rc = launch_pack_gt(ctx, d_text, d_gt, 0, n_rec, n_samples, s->d_planes, s->stride_words, d_status);   // rows with offset -1: zeros
     if (rc == LDX_OK && n_rec > 0) {
-        merge_status_kernel<<<(unsigned)((n_rec + 255) / 256), 256, 0, st>>>(d_rows, d_status, n_rec);
+        // rows with a field outside the plain "a|b" alphabet: parsed again in full, aux planes, the general route (ldx_general.cu)
+        std::vector<uint8_t> h_status((size_t)n_rec);
+        if (cudaMemcpyAsync(h_status.data(), d_status, (size_t)n_rec, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+            rc = cuda_fail(cudaGetLastError(), "vcf ingest: genotype status");
+        if (rc == LDX_OK) rc = store_pack_general(s, 0, n_rec, d_text, n, d_gt, 0, n_samples, h_status.data());
+        if (rc == LDX_OK && cudaMemcpyAsync(d_status, h_status.data(), (size_t)n_rec, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "vcf ingest: status");
+        if (rc == LDX_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "vcf ingest: status");      // h_status is a local
+    }
+    if (rc == LDX_OK && n_rec > 0) {
+        merge_status_kernel<<<(unsigned)((n_rec + 255) / 256), 256, 0, st>>>(d_rows, d_status, n_rec, s->d_eligible);
         ctx->launches++;
         if (cudaMemcpyAsync(rows_out, d_rows, sizeof(ldx_vcf_row) * (size_t)n_rec, cudaMemcpyDeviceToHost, st) != cudaSuccess)
             rc = cuda_fail(cudaGetLastError(), "vcf ingest: rows download");

@@ -36,6 +36,7 @@ struct WindowArgs {
                                    // reference chain's own error bound; screen_t <= 0 switches the screen off
     ldx_hit *hits; int64_t cap; unsigned long long *counters;   // [0] hits, [1] pairs scanned
     FixupSink fix;
+    const GenStore *gen;           // the general route (variants with missing calls / haploid samples / other codes), or nullptr
 };
 
 // Single-precision screen of the rounded-threshold test (ld_area.py:248).  Almost every candidate of a
@@ -71,16 +72,27 @@ __device__ __forceinline__ bool screen_below(int32_t n11, int32_t N, int32_t n1a
 // The per-row tail of both window kernels: thread `tid` owns store row `row` of query q (row >= the query's lo by
 // construction; rows at or beyond `hi` are not candidates).  Filters, single-precision screen, exact finalisation, rounded
 // threshold, and the warp-aggregated append of the kept pair.  Every thread of the warp must call it.
-__device__ __forceinline__ void row_epilogue(const WindowArgs &A, int64_t q, int64_t qrow, int64_t row, int64_t hi, int n11, int tid,
+__device__ __forceinline__ void row_epilogue(const WindowArgs &A, int64_t q, int64_t qrow, int64_t row, int64_t hi, int n11_in, int tid,
                                              unsigned long long &scanned) {
+    int n11 = n11_in;
     bool pass = false;
     uint32_t packed = 0;
+    GenCounts gc;
+    gc.n_pair = 0;                                                      // != 0: the pair took the general route
     if (row < hi) {
         const int32_t ws = A.win_start[q], we = A.win_end[q];
         const bool scan = A.pos0[row] < we && A.end0[row] > ws      // fetch overlap, ld_area.py:215-217
                           && A.eligible[row]                           // rs\d+$ and not MULTI_ALLELIC, :223-224
                           && A.idnum[row] != A.idnum[qrow];            // :222
         if (scan) ++scanned;
+        if (scan && A.gen && (A.freq[qrow].n1 | A.freq[row].n1) < 0) {          // a variant of the general route: rare, one thread does it all
+            gc = general_pair_counts(*A.gen, qrow, A.freq[qrow].n1, row, A.freq[row].n1);     // var_1 = query, var_2 = row (:242)
+            packed = finalise_general(gc).packed;
+            n11 = gc.n11;
+            int32_t m = measure_e4(packed, A.measure);
+            if (A.measure == LDX_MEASURE_R2 && (packed & LDX_R2_NEARTIE)) ++m;
+            pass = m >= A.thres_e4;
+        } else
         if (scan && !(A.screen_t > 0.0f && screen_below(n11, A.n_sel, A.freq[qrow].n1, A.freq[row].n1, A.measure, A.screen_t, A.screen_g))) {
             const VarFreq fa = A.freq[qrow], fb = A.freq[row];         // var_1 = query, var_2 = row (:242)
             const PairFinal f = finalise_pair(n11, fa, fb, A.fc);
@@ -102,8 +114,10 @@ __device__ __forceinline__ void row_epilogue(const WindowArgs &A, int64_t q, int
                 // ldx_hit = {query, row, n11, packed}: one 16-byte store
                 *reinterpret_cast<uint4 *>(A.hits + slot) =
                     make_uint4((uint32_t)q, (uint32_t)row, (uint32_t)n11, packed);
-                if (packed & LDX_R2_NEARTIE)
-                    fixup_append(A.fix, slot, n11, A.freq[qrow].n1, A.freq[row].n1, packed);
+                if (packed & LDX_R2_NEARTIE) {
+                    if (gc.n_pair != 0) fixup_append_general(A.fix, slot, gc, packed);
+                    else fixup_append(A.fix, slot, n11, A.freq[qrow].n1, A.freq[row].n1, packed);
+                }
             }
         }
     }
@@ -414,6 +428,7 @@ static void fill_window_args(ldx_store *s, WindowArgs &A, const int64_t *d_qrow,
     A.screen_t = (s->n_sel <= 8192 && thres_e4 > 0) ? (float)((double)thres_e4 - 0.5 - 1.0e-3) : 0.0f;
     A.hits = d_hits; A.cap = cap; A.counters = d_counters;
     A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity, ctx->fix_tag};
+    A.gen = s->n_nonsimple > 0 ? s->d_gen : nullptr;
 }
 
 bool window_mq_supported(const ldx_store *s) { const int ng = s->stride_words / 16; return ng == 1 || ng == 2 || ng == 5; }
@@ -460,6 +475,7 @@ int launch_window(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, cons
     }
     A.hits = d_hits; A.cap = cap; A.counters = d_counters;
     A.fix = FixupSink{ctx->d_fix, ctx->d_fix_count, ctx->fix_capacity, ctx->fix_tag};
+    A.gen = s->n_nonsimple > 0 ? s->d_gen : nullptr;
     switch (A.stride_u4 / 8) {
         case 1: return launch_window_ng<1>(ctx, A);
         case 2: return launch_window_ng<2>(ctx, A);

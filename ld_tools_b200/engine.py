@@ -393,6 +393,15 @@ class Store:
         check(self._lib.ldx_store_counts(self._h, ptr(n1), ptr(p_e4), C.byref(n)))
         return n1, p_e4, n.value
 
+    def row_counts(self):
+        """-> (n1, own list length, kind, number of general-route rows) per variant under the current selection."""
+        n1 = np.zeros(self.n_variants, dtype=np.int32)
+        ln = np.zeros(self.n_variants, dtype=np.int32)
+        kind = np.zeros(self.n_variants, dtype=np.int32)
+        ng = C.c_int64()
+        check(self._lib.ldx_store_row_counts(self._h, ptr(n1), ptr(ln), ptr(kind), C.byref(ng)))
+        return n1, ln, kind, ng.value
+
     def subset(self, hap_idx):
         sel = np.ascontiguousarray(hap_idx, dtype=np.int32)
         h = C.c_void_p()

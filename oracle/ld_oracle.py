@@ -138,9 +138,10 @@ def packed_words(n_hap, n_11, n_a1, n_b1):
 def packed_of(res):
     """Packed words of an array of ldo_result records."""
     res = np.atleast_1d(res)
-    w = np.where(res["r2_is_int0"] != 0, 0x8000, np.rint(res["r2_rounded"] * 10000.0).astype(np.int64))
+    # the 14-bit fields of the engine's word saturate at 1.6383 (reachable only with entries that are neither 0 nor 1)
+    w = np.where(res["r2_is_int0"] != 0, 0x8000, np.minimum(np.rint(res["r2_rounded"] * 10000.0), 16383).astype(np.int64))
     w = w | np.where(res["dprime_is_int0"] != 0, 0x80000000,
-                     np.rint(res["dprime_rounded"] * 10000.0).astype(np.int64) << 16)
+                     np.minimum(np.rint(res["dprime_rounded"] * 10000.0), 16383).astype(np.int64) << 16)
     return w.astype(np.uint32)
 
 

@@ -346,8 +346,9 @@ int32_t ldx_triangle_table(ldx_store *store, const int64_t *rows, int64_t v, int
  * Replaces the per-hit writer of ld_area.py:252-283 for all queries of a window scan at once.  hits[n_hits] as ldx_window
  * returned them (sorted by (query, row)); q_row[nq] = the queries' store rows (the dist column, :272); blob / blob_off / rows =
  * the records' fixed columns and field offsets (ldx_vcf_copy_prefixes, ldx_store_ingest_vcf; n_rows of them); the alt_freq
- * column is p_e4[row] (ldx_store_counts: var_2_alt_freq of calc_ld.py:97 for complete genotypes) unless alt_e4_of_hit[n_hits]
- * gives it per hit.  Host code, `threads` host threads (<= 0: all cores).  *text_out is allocated by the library (release it
+ * column is p_e4[row] (ldx_store_counts: var_2_alt_freq of calc_ld.py:97 for complete genotypes).  overrides (may be NULL):
+ * [n_hits][3] = {alt_freq, r2, D'} * 10^4 per hit, each < 0 = "as above": for the general route, where the alt frequency belongs
+ * to the PAIR (n1 / len(zip(...))) and a pairing of lists of unequal ploidy can exceed the packed word's 1.6383.  Host code, `threads` host threads (<= 0: all cores).  *text_out is allocated by the library (release it
  * with ldx_free_host); query k's text is (*text_out)[query_off[k], query_off[k+1]) (query_off has nq + 1 entries; *n_bytes =
  * query_off[nq]):
  *   LDX_AREA_TSV    one line per hit: pos, rsID, ref, alt, type, alt_freq, r2, D', dist joined by tabs (str() of each, :264-274)
@@ -357,7 +358,7 @@ int32_t ldx_triangle_table(ldx_store *store, const int64_t *rows, int64_t v, int
 enum { LDX_AREA_TSV = 0, LDX_AREA_JSON = 1, LDX_AREA_RSIDS = 2 };
 int32_t ldx_area_format(const ldx_hit *hits, int64_t n_hits, const int64_t *q_row, int64_t nq, const uint8_t *blob,
                         const int64_t *blob_off, const ldx_vcf_row *rows, int64_t n_rows, const int32_t *p_e4,
-                        const int32_t *alt_e4_of_hit, int32_t format, int32_t threads, char **text_out,
+                        const int32_t *overrides, int32_t format, int32_t threads, char **text_out,
                         int64_t *n_bytes, int64_t *query_off);
 /* Host helper (no device needed): str(value_e4 / 10000.0) for 0 <= value_e4 < 20000 as the kernels print it,
  * NUL-padded to 8 bytes -- the same digit arithmetic, exposed so that it can be checked against Python's str(). */

@@ -149,9 +149,25 @@ struct HitFormatter {
     // the rounded measures as Python prints the objects calc_ld returned: the int 0 or a float (calc_ld.py:68-69, :89-90, :94-95)
     static int r2_e4(uint32_t w) { return (w & LDX_R2_INT0) ? -1 : (int)(w & LDX_R2_MASK); }
     static int dp_e4(uint32_t w) { return (w & LDX_DP_INT0) ? -1 : (int)((w & LDX_DP_MASK) >> LDX_DP_SHIFT); }
-    size_t e4_len(int k) const { return k < 0 ? 1 : E.len[k]; }
+    // beyond the table (values above 2.0: only a pairing of lists of unequal ploidy produces them): integer part, '.', the four
+    // decimals without trailing zeros but at least one -- what Python prints for the double nearest to k * 10^-4
+    static size_t big_len(int k) { int f = k % 10000, nd = 4; while (nd > 1 && f % 10 == 0) { f /= 10; --nd; } return int_len(k / 10000) + 1 + (size_t)nd; }
+    static char *put_big(char *p, int k) {
+        p = put_int(p, k / 10000);
+        *p++ = '.';
+        int f = k % 10000, nd = 4;
+        while (nd > 1 && f % 10 == 0) { f /= 10; --nd; }
+        for (int i = nd - 1; i >= 0; --i) { p[i] = (char)('0' + f % 10); f /= 10; }
+        return p + nd;
+    }
+    size_t e4_len(int k) const { return k < 0 ? 1 : k <= 20000 ? E.len[k] : big_len(k); }
     static size_t int_len(int64_t v) { size_t n = v < 0 ? 2 : 1; uint64_t u = v < 0 ? (uint64_t)(-(v + 1)) + 1 : (uint64_t)v; while (u >= 10) { u /= 10; ++n; } return n; }
-    char *put_e4(char *p, int k) const { if (k < 0) { *p++ = '0'; return p; } std::memcpy(p, E.txt[k], 8); return p + E.len[k]; }
+    char *put_e4(char *p, int k) const {
+        if (k < 0) { *p++ = '0'; return p; }
+        if (k > 20000) return put_big(p, k);
+        std::memcpy(p, E.txt[k], 8);
+        return p + E.len[k];
+    }
     static char *put_int(char *p, int64_t v) {
         char buf[24];
         int n = 0;
@@ -162,26 +178,29 @@ struct HitFormatter {
         while (n) *p++ = buf[--n];
         return p;
     }
-    size_t size(const ldx_hit &h, int64_t qrow, int32_t alt_e4) const {
+    // ov: optional per-hit overrides {alt_e4, r2_e4, dp_e4}, each < 0 = "as the tables / the packed word say"
+    static int pick(const int32_t *ov, int i, int dflt) { return ov && ov[i] >= 0 ? ov[i] : dflt; }
+    size_t size(const ldx_hit &h, int64_t qrow, int32_t alt_e4, const int32_t *ov) const {
         const size_t a = pre_len[h.row];
         if (format == LDX_AREA_RSIDS) return a;
         const int64_t dist = (int64_t)T.rows[h.row].pos - (int64_t)T.rows[qrow].pos;                // :272
-        const size_t vals = e4_len(alt_e4) + e4_len(r2_e4(h.packed)) + e4_len(dp_e4(h.packed)) + int_len(dist);
+        const size_t vals = e4_len(pick(ov, 0, alt_e4)) + e4_len(pick(ov, 1, r2_e4(h.packed))) + e4_len(pick(ov, 2, dp_e4(h.packed))) + int_len(dist);
         return a + vals + (format == LDX_AREA_TSV ? 4 : sizeof(",\n        \"r2\": ") - 1 + sizeof(",\n        \"D'\": ") - 1 + sizeof(",\n        \"dist\": ") - 1 + sizeof("\n    }") - 1);
     }
     // NOTE: writes up to 7 bytes past the end of a value (8-byte copies of the e4 texts); the caller's buffer has that slack
-    char *write(char *p, const ldx_hit &h, int64_t qrow, int32_t alt_e4) const {
+    char *write(char *p, const ldx_hit &h, int64_t qrow, int32_t alt_e4_in, const int32_t *ov) const {
         std::memcpy(p, pre_txt + pre_off[h.row], pre_len[h.row]);
         p += pre_len[h.row];
         if (format == LDX_AREA_RSIDS) return p;
         const int64_t dist = (int64_t)T.rows[h.row].pos - (int64_t)T.rows[qrow].pos;
+        const int alt_e4 = pick(ov, 0, alt_e4_in), r2v = pick(ov, 1, r2_e4(h.packed)), dpv = pick(ov, 2, dp_e4(h.packed));
         if (format == LDX_AREA_TSV) {
-            p = put_e4(p, alt_e4); *p++ = '\t'; p = put_e4(p, r2_e4(h.packed)); *p++ = '\t'; p = put_e4(p, dp_e4(h.packed)); *p++ = '\t';
+            p = put_e4(p, alt_e4); *p++ = '\t'; p = put_e4(p, r2v); *p++ = '\t'; p = put_e4(p, dpv); *p++ = '\t';
             p = put_int(p, dist); *p++ = '\n';
             return p;
         }
 #define LIT(x) do { std::memcpy(p, x, sizeof(x) - 1); p += sizeof(x) - 1; } while (0)
-        p = put_e4(p, alt_e4); LIT(",\n        \"r2\": "); p = put_e4(p, r2_e4(h.packed)); LIT(",\n        \"D'\": "); p = put_e4(p, dp_e4(h.packed));
+        p = put_e4(p, alt_e4); LIT(",\n        \"r2\": "); p = put_e4(p, r2v); LIT(",\n        \"D'\": "); p = put_e4(p, dpv);
         LIT(",\n        \"dist\": "); p = put_int(p, dist); LIT("\n    }");
 #undef LIT
         return p;
@@ -192,9 +211,9 @@ struct HitFormatter {
 
 extern "C" int32_t ldx_area_format(const ldx_hit *hits, int64_t n_hits, const int64_t *q_row, int64_t nq, const uint8_t *blob,
                                    const int64_t *blob_off, const ldx_vcf_row *rows, int64_t n_rows, const int32_t *p_e4,
-                                   const int32_t *alt_e4_of_hit, int32_t format, int32_t threads, char **text_out,
+                                   const int32_t *overrides, int32_t format, int32_t threads, char **text_out,
                                    int64_t *n_bytes, int64_t *query_off) {
-    LDX_REQUIRE(text_out && n_bytes && query_off && q_row && blob && blob_off && rows && (p_e4 || alt_e4_of_hit), "NULL argument");
+    LDX_REQUIRE(text_out && n_bytes && query_off && q_row && blob && blob_off && rows && p_e4, "NULL argument");
     LDX_REQUIRE(n_hits >= 0 && nq >= 0 && n_rows >= 0 && (hits || n_hits == 0), "bad sizes");
     LDX_REQUIRE(format == LDX_AREA_TSV || format == LDX_AREA_JSON || format == LDX_AREA_RSIDS, "bad format");
     *n_bytes = 0; *text_out = nullptr;
@@ -204,7 +223,6 @@ extern "C" int32_t ldx_area_format(const ldx_hit *hits, int64_t n_hits, const in
     for (int64_t i = 0; i < n_hits; ++i) {
         LDX_REQUIRE(hits[i].query >= 0 && hits[i].query < nq && hits[i].row >= 0 && hits[i].row < n_rows, "hit outside the query / row tables");
         LDX_REQUIRE(i == 0 || hits[i].query >= hits[i - 1].query, "hits must be sorted by query");
-        LDX_REQUIRE(!alt_e4_of_hit || (alt_e4_of_hit[i] >= 0 && alt_e4_of_hit[i] <= 20000), "alt_e4_of_hit out of range");
         first[(size_t)hits[i].query + 1]++;
         touched[(size_t)hits[i].row] = 1;
     }
@@ -212,8 +230,7 @@ extern "C" int32_t ldx_area_format(const ldx_hit *hits, int64_t n_hits, const in
         LDX_REQUIRE(q_row[k] >= 0 && q_row[k] < n_rows, "q_row outside the row table");
         first[(size_t)k + 1] += first[(size_t)k];
     }
-    if (!alt_e4_of_hit)
-        for (int64_t r = 0; r < n_rows; ++r) LDX_REQUIRE(!touched[(size_t)r] || (p_e4[r] >= 0 && p_e4[r] <= 20000), "p_e4 out of range");
+    for (int64_t r = 0; r < n_rows; ++r) LDX_REQUIRE(!touched[(size_t)r] || (p_e4[r] >= 0 && p_e4[r] <= 20000), "p_e4 out of range");
     const Table T{blob, blob_off, rows, p_e4};
     const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(threads > 0 ? threads : (int)std::thread::hardware_concurrency(), std::max<int64_t>(1, n_hits / 4096)));
     auto parallel = [&](int64_t n, int64_t chunk, auto &&body) {   // dynamic chunks of [0, n) over the threads
@@ -247,11 +264,12 @@ extern "C" int32_t ldx_area_format(const ldx_hit *hits, int64_t n_hits, const in
         format_row_prefix(w, T, r, format);
     });
     const HitFormatter F{T, e4_table(), format, pre_len.data(), pre_off.data(), pre_txt.data()};
-    auto alt_of = [&](int64_t i) { return alt_e4_of_hit ? alt_e4_of_hit[i] : p_e4[hits[i].row]; };   // var_2_alt_freq, calc_ld.py:97
+    auto alt_of = [&](int64_t i) { return p_e4[hits[i].row]; };                                      // var_2_alt_freq, calc_ld.py:97 (complete rows)
+    auto ov_of = [&](int64_t i) { return overrides ? overrides + 3 * i : nullptr; };
     // ---- pass 1: sizes (table look-ups only)
     parallel(nq, 16, [&](int64_t k) {
         int64_t n = 0;
-        for (int64_t i = first[(size_t)k]; i < first[(size_t)k + 1]; ++i) n += (int64_t)F.size(hits[i], q_row[k], alt_of(i));
+        for (int64_t i = first[(size_t)k]; i < first[(size_t)k + 1]; ++i) n += (int64_t)F.size(hits[i], q_row[k], alt_of(i), ov_of(i));
         query_off[k + 1] = n;
     });
     query_off[0] = 0;
@@ -264,13 +282,13 @@ extern "C" int32_t ldx_area_format(const ldx_hit *hits, int64_t n_hits, const in
         char row[4096];
         char *dst = out + query_off[k];
         for (int64_t i = first[(size_t)k]; i < first[(size_t)k + 1]; ++i) {
-            const size_t need = F.size(hits[i], q_row[k], alt_of(i));
+            const size_t need = F.size(hits[i], q_row[k], alt_of(i), ov_of(i));
             if (need + 8 <= sizeof row) {
-                F.write(row, hits[i], q_row[k], alt_of(i));
+                F.write(row, hits[i], q_row[k], alt_of(i), ov_of(i));
                 std::memcpy(dst, row, need);
             } else {                                               // a record with very long alleles: through a heap buffer
                 std::vector<char> big(need + 8);
-                F.write(big.data(), hits[i], q_row[k], alt_of(i));
+                F.write(big.data(), hits[i], q_row[k], alt_of(i), ov_of(i));
                 std::memcpy(dst, big.data(), need);
             }
             dst += need;

@@ -20,7 +20,9 @@ import sqlite3
 import numpy as np
 
 from .engine import Context, HostText, Store, dprime_value, r2_value, threshold_e4
-from ._lib import VCF_ROW_DTYPE, LdxError
+from ._lib import DP_INT0, DP_MASK, DP_SHIFT, R2_INT0, R2_MASK, VCF_ROW_DTYPE, LdxError
+
+R2_MASK_SAT = 16383                 # a 14-bit field of the packed word at its ceiling (general route only)
 
 RS_RE = re.compile(r"rs\d+$")
 TEXT_SLAB_BYTES = 256 << 20          # matrix text is formatted and written in slabs of at most this many bytes
@@ -190,13 +192,16 @@ class ChromData:
         if not samples:
             raise ValueError(f"{vcf_path}: no sample columns")
         self.store, rows = Store.ingest_vcf(ctx, raw, len(samples))
-        bad = np.flatnonzero((rows["status"] != 0) & ((rows["eligible"] != 0) | ((rows["status"] & 6) != 0)))
-        if len(bad):                                                       # rows no driver ever pairs may be anything
+        # status bit 0 (a genotype field that is not plain "a|b": haploid, missing, other codes, unphased) is fine: such rows
+        # take the engine's general route.  What no parser takes -- a line that is not a record, a POS that is not a number,
+        # a field with more than two alleles -- is refused by name.
+        bad = np.flatnonzero((rows["status"] & 14) != 0)
+        if len(bad):
             k = int(bad[0])
             line = raw[rows["line_off"][k]:rows["line_off"][k] + 60].tobytes().decode(errors="replace")
             self.store.close()
-            raise ValueError(f"{vcf_path}: record {k} ({line!r}...) is not a phased diploid biallelic VCF row (chrX/Y and "
-                             "missing calls are outside the engine's domain, reference README.md:72)")
+            raise ValueError(f"{vcf_path}: record {k} ({line!r}...) is not a VCF record this engine can read "
+                             f"(status {int(rows['status'][k])}: 2 = too few columns, 4 = POS, 8 = genotype fields)")
         blob, off = Store.vcf_fixed_columns(ctx._lib, raw, rows)
         self._set_columns(samples, rows, blob.tobytes(), off)
         host.close()
@@ -216,6 +221,23 @@ class ChromData:
         if 0 < len(hap) <= self.store.n_hap // 2 and not os.environ.get("LDX_NO_SUBSET_STORE"):
             self.scan = self.store.subset(hap)
         self.n1, self.p_e4, self.n_hap_sel = self.scan.counts()
+        # rows of the general route (missing calls, haploid samples ...): their own list lengths, for the alt frequencies calc_ld
+        # reports per PAIR (var_2_alt_freq = n1 / len(zip(...)), calc_ld.py:31,43,97)
+        self.row_n1, self.row_len, self.kind, self.n_general = self.scan.row_counts()
+
+    def pair_values_e4(self, row_a, row_b):
+        """(round(r2, 4), round(D', 4)) * 10^4 of calc_ld(var_1 = row_a, var_2 = row_b) from the engine's unrounded values, -1 for
+        the reference's int 0: for the pairs whose values do not fit the packed word's 14-bit fields (more than 1.6383: a
+        pairing of lists of unequal ploidy, e.g. a pseudo-autosomal with an X-specific variant)."""
+        out = self.scan.pairs([row_a], [row_b], raw=True)
+        w = int(out["packed"][0])
+        e4 = lambda x: int(round(round(float(x), 4) * 10000))                     # noqa: E731
+        return (-1 if w & R2_INT0 else e4(out["r2"][0])), (-1 if w & DP_INT0 else e4(out["dprime"][0]))
+
+    def pair_alt_e4(self, row_a, row_b):
+        """round(var_2_alt_freq, 4) * 10^4 of calc_ld(var_1 = row_a, var_2 = row_b): the alt count of b over the PAIRING's length."""
+        n = min(int(self.row_len[row_a]), int(self.row_len[row_b]))
+        return int(round(round(int(self.row_n1[row_b]) / n, 4) * 10000)) if n else 0
 
     def row_of(self, pos, rs_id):
         """Store row of the first record with this position and ID (the drivers `break` at the first match, ld_area.py:150-159)."""
@@ -373,7 +395,18 @@ def ld_area(src_dir_path, intgen_dir_path, trg_top_dir_path=None, meta_lines_qua
                 return
         hits, _ = cd.scan.window(q_row[mine], lo[mine], hi[mine], ws[mine], we[mine], ld_thres_measure, t_e4)
         # ---- the writers (:200-283): the rows of every query from the library, headers and the query's own line from here
-        text, qoff = area_format(w.ctx._lib, hits, q_row[mine], cd._blob_arr, cd._off, cd.rows, cd.p_e4, fmt)
+        overrides = None
+        if cd.n_general and len(hits):
+            # the general route: var_2_alt_freq belongs to the PAIR where one list is shorter (calc_ld.py:31,43), and such a
+            # pairing can produce values beyond the packed word's 1.6383: those come from the engine's unrounded values
+            overrides = np.full((len(hits), 3), -1, dtype=np.int32)
+            qr_of_hit = q_row[mine][hits["query"]]
+            for i in np.flatnonzero(cd.row_len[hits["row"]] != cd.row_len[qr_of_hit]):
+                overrides[i, 0] = cd.pair_alt_e4(int(qr_of_hit[i]), int(hits["row"][i]))
+            sat = ((hits["packed"] & R2_MASK) == R2_MASK_SAT) | (((hits["packed"] & DP_MASK) >> DP_SHIFT) == R2_MASK_SAT)
+            for i in np.flatnonzero(sat):
+                overrides[i, 1], overrides[i, 2] = cd.pair_values_e4(int(qr_of_hit[i]), int(hits["row"][i]))
+        text, qoff = area_format(w.ctx._lib, hits, q_row[mine], cd._blob_arr, cd._off, cd.rows, cd.p_e4, fmt, overrides=overrides)
         for j, k in enumerate(mine):
             if qoff[j + 1] == qoff[j]:
                 continue                                             # empty result: file removed, :291-292
@@ -450,6 +483,25 @@ def ld_triangle(src_dir_path, intgen_dir_path, trg_top_dir_path=None, meta_lines
     def slab_rows(v):
         return min(v, max(256, TEXT_SLAB_BYTES // (7 * v) // 256 * 256))
 
+    def exact_cells(cd, t, text, row_begin):
+        """Stores with general-route rows only: a cell printed as 1.6383 is a packed field at its ceiling (a pairing of lists of
+        unequal ploidy); its value comes from the engine's unrounded numbers instead.  -> the text, patched (bytes)."""
+        text = bytes(text)
+        if not cd.n_general or b"1.6383" not in text:
+            return text
+        lines = text.split(b"\n")
+        for k, line in enumerate(lines[:-1]):
+            if b"1.6383" not in line:
+                continue
+            cells = line.split(b"\t")
+            for c in range(2, len(cells)):
+                if cells[c] == b"1.6383":
+                    r2v, dpv = cd.pair_values_e4(int(t["rows"][row_begin + k]), int(t["rows"][c - 2]))      # var_1 = row, var_2 = column
+                    val = r2v if ld_measure == "r_square" else dpv
+                    cells[c] = str(val / 10000.0).encode() if val >= 0 else b"0"
+            lines[k] = b"\t".join(cells)
+        return b"\n".join(lines)
+
     def write_slabbed(w, t, cd):
         """The double loop (:133-230) and the V lines of V cells (:356-360): all-pairs kernel, settlement and the writer in one
         library call per slab of rows; only text leaves the GPU."""
@@ -458,7 +510,7 @@ def ld_triangle(src_dir_path, intgen_dir_path, trg_top_dir_path=None, meta_lines
         with open(t["path"], "wb") as fh:
             fh.write(t["head"])
             for r0 in range(0, v, slab):
-                fh.write(cd.scan.triangle_table(t["rows"], t["prefixes"], ld_measure, t_e4, row_begin=r0, row_end=min(v, r0 + slab), out=buf).data)
+                fh.write(exact_cells(cd, t, cd.scan.triangle_table(t["rows"], t["prefixes"], ld_measure, t_e4, row_begin=r0, row_end=min(v, r0 + slab), out=buf).data, r0))
 
     def run_device(w, mine):
         """A device's tables: the small matrices in batched launches, the large ones slab by slab."""
@@ -487,7 +539,7 @@ def ld_triangle(src_dir_path, intgen_dir_path, trg_top_dir_path=None, meta_lines
                 for (t, cd), a in zip(group, addrs):
                     with open(t["path"], "wb") as fh:
                         fh.write(t["head"])
-                        fh.write(w.ctx.triangle_text(a, t["v"], ld_measure, t["prefixes"]).data)
+                        fh.write(exact_cells(cd, t, w.ctx.triangle_text(a, t["v"], ld_measure, t["prefixes"]).data, 0))
             finally:
                 for a in addrs:
                     w.ctx.dev_free(a)
@@ -509,7 +561,7 @@ def ld_triangle(src_dir_path, intgen_dir_path, trg_top_dir_path=None, meta_lines
             try:
                 for j in range(k, len(ranges), len(ws)):
                     r0, r1 = ranges[j]
-                    done[k].put(cds[k].scan.triangle_table(t["rows"], t["prefixes"], ld_measure, t_e4, row_begin=r0, row_end=r1).tobytes())
+                    done[k].put(exact_cells(cds[k], t, cds[k].scan.triangle_table(t["rows"], t["prefixes"], ld_measure, t_e4, row_begin=r0, row_end=r1).data, r0))
             except BaseException as e:      # noqa: BLE001
                 errors.append(e)
                 done[k].put(None)
@@ -567,12 +619,17 @@ def ld_lite(rs_id_1, rs_id_2, intgen_dir_path, gend_names="both", pop_names="all
         r1, r2 = cd.row_of(pos1, rs_id_1), cd.row_of(pos2, rs_id_2)
         out = cd.scan.pairs([r1], [r2], raw=False)
         w = out["packed"][0]
+        r2_e4v, dp_e4v = (int(w) & R2_MASK), ((int(w) & DP_MASK) >> DP_SHIFT)
+        if cd.n_general and R2_MASK_SAT in (r2_e4v, dp_e4v):          # beyond the packed fields: from the unrounded values
+            r2_e4v, dp_e4v = cd.pair_values_e4(r1, r2)
+        r2_obj = 0 if (int(w) & R2_INT0) else r2_e4v / 10000.0
+        dp_obj = 0 if (int(w) & DP_INT0) else dp_e4v / 10000.0
         first_alt = lambda r: cd.alts[r].split(",")[0]                        # noqa: E731  (intgen_rec.alts[0], :116)
         return tabulate([["chrom", chrom, chrom], ["hg38_pos", pos1, pos2],
                          ["alleles", cd.refs[r1] + "/" + first_alt(r1), cd.refs[r2] + "/" + first_alt(r2)],
                          ["type", cd.vts[r1].split(",")[0], cd.vts[r2].split(",")[0]],      # intgen_rec.info['VT'][0], ld_lite.py:118,131
-                         ["alt_freq", cd.p_e4[r1] / 10000.0, cd.p_e4[r2] / 10000.0]],
-                        headers=[tabulate([["r2", r2_value(w)], ["D'", dprime_value(w)], ["abs_dist", abs(pos1 - pos2)]],
+                         ["alt_freq", cd.pair_alt_e4(r2, r1) / 10000.0, cd.pair_alt_e4(r1, r2) / 10000.0]],      # var_1 / var_2_alt_freq of the pair
+                        headers=[tabulate([["r2", r2_obj], ["D'", dp_obj], ["abs_dist", abs(pos1 - pos2)]],
                                           tablefmt="fancy_grid", disable_numparse=True),
                                  f"\n\n\n{rs_id_1}", f"\n\n\n{rs_id_2}"], tablefmt="fancy_grid")
     finally:

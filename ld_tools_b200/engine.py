@@ -74,7 +74,7 @@ def _i64(a):
     return np.ascontiguousarray(a, dtype=np.int64)
 
 
-def area_format(lib, hits, q_row, blob, blob_off, rows, p_e4, fmt, alt_e4_of_hit=None, threads=0):
+def area_format(lib, hits, q_row, blob, blob_off, rows, p_e4, fmt, overrides=None, threads=0):
     """The ld_area writers' body rows for all queries of a window scan (ldx_area_format: host code in libldx, all cores).
     hits: HIT_DTYPE array sorted by (query, row); rows / blob / blob_off: the records' field offsets and fixed columns
     (Store.ingest_vcf, Store.vcf_fixed_columns); p_e4: round(alt freq, 4) * 10^4 per store row.
@@ -85,7 +85,8 @@ def area_format(lib, hits, q_row, blob, blob_off, rows, p_e4, fmt, alt_e4_of_hit
     blob = np.ascontiguousarray(blob, dtype=np.uint8)
     blob_off = _i64(blob_off)
     p_e4 = np.ascontiguousarray(p_e4, dtype=np.int32)
-    alt = None if alt_e4_of_hit is None else np.ascontiguousarray(alt_e4_of_hit, dtype=np.int32)
+    alt = None if overrides is None else np.ascontiguousarray(overrides, dtype=np.int32).reshape(-1, 3)      # {alt_freq, r2, D'} * 10^4, < 0: default
+    assert alt is None or alt.shape[0] == hits.shape[0]
     qoff = np.zeros(q_row.shape[0] + 1, dtype=np.int64)
     n, p = C.c_int64(), C.c_void_p()
     check(lib.ldx_area_format(ptr(hits), hits.shape[0], ptr(q_row), q_row.shape[0], ptr(blob), ptr(blob_off), ptr(rows), rows.shape[0], ptr(p_e4),

@@ -242,9 +242,11 @@ def gt_row_text(h_row):
     return buf.tobytes()[:-1]
 
 
-def write_intgen_dir(path, panel, recs, haps, chrom="22"):
+def write_intgen_dir(path, panel, recs, haps, chrom="22", gt_text=None):
     """Write <path>/<chrom>.vcf.gz, the panel file and conversion.db as prep_intgen_data would
-    have left them (prep_intgen_data.py:51-63 samples table, :146-182 variants table + index)."""
+    have left them (prep_intgen_data.py:51-63 samples table, :146-182 variants table + index).
+    gt_text (optional): per variant the bytes of its genotype columns (tab-joined sample fields) instead of the plain
+    phased diploid text of `haps` -- haploid, missing, unphased ... fields."""
     os.makedirs(path, exist_ok=True)
     names = [p[0] for p in panel]
     with open(os.path.join(path, "integrated_call_samples_v3.20130502.ALL.panel"), "w") as fh:
@@ -254,11 +256,13 @@ def write_intgen_dir(path, panel, recs, haps, chrom="22"):
     with BgzfWriter(os.path.join(path, f"{chrom}.vcf.gz")) as fh:          # BGZF, like the real 1000G files (any gzip reader reads it)
         fh.write(b"##fileformat=VCFv4.1\n##source=ld_tools_b200.synth\n")
         fh.write(("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(names) + "\n").encode())
+        written = []
         for r, h in zip(recs, haps):
             ac = int(h.sum())
             info = f"AC={ac};AF={ac / len(h):.6g};AN={len(h)};VT={r['vt']}" + (";MULTI_ALLELIC" if r["multi"] else "")
             head = f"{r['chrom']}\t{r['pos']}\t{r['id']}\t{r['ref']}\t{r['alt']}\t100\tPASS\t{info}\tGT\t"
-            fh.write(head.encode() + gt_row_text(h) + b"\n")
+            fh.write(head.encode() + (gt_row_text(h) if gt_text is None else gt_text[len(written)]) + b"\n")
+            written.append(1)
     db = os.path.join(path, "conversion.db")
     if os.path.exists(db):
         os.remove(db)

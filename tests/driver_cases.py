@@ -67,6 +67,68 @@ def build_dataset(root):
     return intgen, srcs
 
 
+N_SAMPLES_X, N_VARIANTS_X = 90, 420
+
+
+def build_dataset_x(root):
+    """A chrX-shaped data set for the general route: males haploid outside two pseudo-autosomal blocks,
+    missing calls ('.', '.|.', '.|1'), a few unphased rows.  -> (intgen_dir, {name: src_dir}, lite pairs)."""
+    from ld_tools_b200.synth import conversion_rows, make_panel, make_records, synth_haplotypes, write_intgen_dir
+    panel = make_panel(N_SAMPLES_X, seed=SEED + 7)
+    male = np.array([p[3] == "male" for p in panel])
+    haps = synth_haplotypes(N_VARIANTS_X, 2 * N_SAMPLES_X, seed=SEED + 7, n_founders=16, switch_rate=0.01)
+    rng = np.random.default_rng(SEED + 8)
+    for i in range(8, N_VARIANTS_X):
+        if rng.random() < 0.35:
+            src = i - int(rng.integers(1, 8))
+            haps[i] = haps[src] ^ (rng.random(haps.shape[1]) < rng.choice([0.0, 0.01, 0.05])).astype(haps.dtype)
+    recs = make_records(N_VARIANTS_X, chrom="X", seed=SEED + 7, mean_gap=40)
+    gt_text = []
+    for v in range(N_VARIANTS_X):
+        a = haps[v]
+        par = v < 50 or v >= N_VARIANTS_X - 30                                   # PAR1 / PAR2: everybody diploid
+        fields = [f"{a[2 * s]}|{a[2 * s + 1]}" for s in range(N_SAMPLES_X)]
+        if not par:
+            for s in np.flatnonzero(male):
+                fields[s] = str(a[2 * s])
+        u = rng.random()
+        if u < 0.12:
+            for s in rng.choice(N_SAMPLES_X, int(rng.integers(1, 4)), replace=False):
+                fields[s] = "." if (not par and male[s]) else str(rng.choice([".|.", f".|{a[2 * s]}", f"{a[2 * s]}|."]))
+        elif u < 0.16:
+            fields = [f.replace("|", "/") for f in fields]
+        gt_text.append("\t".join(fields).encode())
+    intgen = os.path.join(root, "intgen_x")
+    write_intgen_dir(intgen, panel, recs, haps, chrom="X", gt_text=gt_text)
+    addressable = [r[2] for r in conversion_rows(recs)]
+    srcs = {}
+    d = os.path.join(root, "src_area_x")
+    os.makedirs(d)
+    with open(os.path.join(d, "hits_x.txt"), "w") as fh:
+        for k in rng.choice(len(addressable), 24, replace=False):
+            fh.write(addressable[k] + "\n")
+    srcs["area"] = d
+    d = os.path.join(root, "src_triangle_x")
+    os.makedirs(d)
+    with open(os.path.join(d, "region_x.txt"), "w") as fh:
+        for k in rng.permutation(len(addressable))[:280]:
+            fh.write(addressable[k] + "\n")
+    srcs["triangle"] = d
+    srcs["lite_pairs"] = [(addressable[3], addressable[10]), (addressable[20], addressable[200]), (addressable[150], addressable[151]),
+                          (addressable[-3], addressable[100])]
+    return intgen, srcs
+
+
+AREA_X_CASES = [
+    ("area_x_r2_tsv", ["-w", "3000", "-l", "r_square", "-z", "0.2", "-o", "tsv"]),
+    ("area_x_dp_json_male", ["-w", "2500", "-l", "d_prime", "-z", "0.8", "-o", "json", "-g", "male"]),
+]
+TRIANGLE_X_CASES = [
+    ("triangle_x_r2", ["-o", "table"]),
+    ("triangle_x_dp_thres_female", ["-o", "table", "-l", "d_prime", "-z", "0.3", "-g", "female"]),
+]
+LITE_X_CASES = [("lite_x_all", []), ("lite_x_afr", ["-e", "afr"])]
+
 # name, driver, extra CLI arguments (as the reference's argparse takes them)
 AREA_CASES = [
     ("area_r2_tsv", ["-m", "2", "-w", "2500", "-l", "r_square", "-z", "0.3", "-o", "tsv"]),

@@ -64,6 +64,22 @@ def main():
             with open(os.path.join(OUT, name, f"pair{k}.txt"), "w") as fh:
                 fh.write(text)
         index[name] = sorted(os.listdir(os.path.join(OUT, name)))
+    # ---- the chrX-shaped data set (haploid males, missing calls): the general route
+    intgen_x, srcs_x = dc.build_dataset_x(work)
+    for cases, script, key in ((dc.AREA_X_CASES, "ld_area.py", "area"), (dc.TRIANGLE_X_CASES, "ld_triangle.py", "triangle")):
+        for name, extra in cases:
+            trg = os.path.join(work, "out_" + name)
+            os.makedirs(trg)
+            run_ref(script, ["-S", srcs_x[key], "-D", intgen_x, "-t", trg, "-f", "-p", "1"] + extra, work)
+            shutil.copytree(trg, os.path.join(OUT, name))
+            index[name] = sorted(dc.read_tree(trg))
+    for name, extra in dc.LITE_X_CASES:
+        os.makedirs(os.path.join(OUT, name))
+        for k, (a, b) in enumerate(srcs_x["lite_pairs"]):
+            text = run_ref("ld_lite.py", [a, b, "-D", intgen_x, "-f"] + extra, work)
+            with open(os.path.join(OUT, name, f"pair{k}.txt"), "w") as fh:
+                fh.write(text)
+        index[name] = sorted(os.listdir(os.path.join(OUT, name)))
     with open(os.path.join(OUT, "index.json"), "w") as fh:
         json.dump(index, fh, indent=1, sort_keys=True)
     n = sum(len(v) for v in index.values())

@@ -93,11 +93,22 @@ def test_area_format_equals_python_writers(threads):
                 assert full.startswith(base[:-2]) and full.endswith("\n]")
                 want = full[len(base) - 2:-2]
             assert got == want, (fmt, k)
-    # per-hit alt frequencies override the per-row table
-    alt = rng.integers(0, 10001, size=len(hits)).astype(np.int32)
-    text, qoff = area_format(lib, hits, q_row, blob, off, rows, p_e4, AREA_TSV, alt_e4_of_hit=alt, threads=threads)
-    lines = text.tobytes().decode().split("\n")[:-1]
-    assert [ln.split("\t")[5] for ln in lines] == [str(a / 10000.0) for a in alt]
+    # per-hit overrides {alt_freq, r2, D'} (general route): any magnitude, < 0 = default
+    ov = np.full((len(hits), 3), -1, dtype=np.int32)
+    ov[:, 0] = rng.integers(0, 30001, size=len(hits))
+    big = rng.random(len(hits)) < 0.3
+    ov[big, 1] = rng.choice([16383, 16384, 20001, 89099, 100000, 1234500, 2147480000 // 10000 * 10000 + 7], size=int(big.sum()))
+    ov[big, 2] = rng.integers(0, 5_000_000, size=int(big.sum()))
+    for fmt in (AREA_TSV, AREA_JSON):
+        text, qoff = area_format(lib, hits, q_row, blob, off, rows, p_e4, fmt, overrides=ov, threads=threads)
+        if fmt == AREA_TSV:
+            cols = [ln.split("\t") for ln in text.tobytes().decode().split("\n")[:-1]]
+        else:
+            cols = [[None] * 5 + [c.split(": ")[1].rstrip(",") for c in el.split("\n")[6:9]] for el in text.tobytes().decode().split("\n    {")[1:]]
+        for h, o, c in zip(hits, ov, cols):
+            want = [str(o[0] / 10000.0), str(o[1] / 10000.0) if o[1] >= 0 else str(value(h["packed"], True)),
+                    str(o[2] / 10000.0) if o[2] >= 0 else str(value(h["packed"], False))]
+            assert c[5:8] == want, (fmt, c[5:8], want)
 
 
 def test_area_format_rejects_bad_input():

@@ -156,6 +156,52 @@ def test_ld_triangle_batched_tables_and_shared_matrix(data, ctx, tmp_path, monke
     assert assert_same_tree(str(tmp_path / "shared"), name) == 1
 
 
+# ------------------------------------------------------------------ the chrX-shaped data set: haploid males, missing calls
+@pytest.fixture(scope="module")
+def data_x(tmp_path_factory):
+    root = str(tmp_path_factory.mktemp("ldx_drivers_x"))
+    intgen, srcs = dc.build_dataset_x(root)
+    return root, intgen, srcs
+
+
+@pytest.mark.parametrize("name,extra", dc.AREA_X_CASES)
+def test_ld_area_chrx_general_route_tree_identical(data_x, ctx, tmp_path, name, extra):
+    """Males haploid outside the pseudo-autosomal blocks, missing calls, unphased rows: the unmodified reference pairs the
+    lists pysam hands it; the engine's general route must write the same files (alt_freq of a hit = var_2_alt_freq of the PAIR)."""
+    from ld_tools_b200 import drivers
+    root, intgen, srcs = data_x
+    drivers.ld_area(srcs["area"], intgen, trg_top_dir_path=str(tmp_path), ctx=ctx, **parse(extra, "area"))
+    assert assert_same_tree(str(tmp_path), name) > 3
+
+
+@pytest.mark.parametrize("tile_n", [0, 128])
+@pytest.mark.parametrize("name,extra", dc.TRIANGLE_X_CASES)
+def test_ld_triangle_chrx_general_route_table_identical(data_x, ctx, tmp_path, name, extra, tile_n):
+    from ld_tools_b200 import drivers
+    from ld_tools_b200._lib import TUNE_MMA_TILE_N
+    root, intgen, srcs = data_x
+    kw = parse(extra, "triangle")
+    kw.pop("matrix_type")
+    ctx.set_tuning(TUNE_MMA_TILE_N, tile_n)
+    try:
+        drivers.ld_triangle(srcs["triangle"], intgen, trg_top_dir_path=str(tmp_path), ctx=ctx, **kw)
+    finally:
+        ctx.set_tuning(TUNE_MMA_TILE_N, 0)
+    assert assert_same_tree(str(tmp_path), name) == 1
+
+
+@pytest.mark.parametrize("name,extra", dc.LITE_X_CASES)
+def test_ld_lite_chrx_printout_identical(data_x, ctx, name, extra):
+    from ld_tools_b200 import drivers
+    root, intgen, srcs = data_x
+    kw = parse(extra, "lite")
+    kw.pop("meta_lines_quan")
+    for k, (a, b) in enumerate(srcs["lite_pairs"]):
+        text = drivers.ld_lite(a, b, intgen, ctx=ctx, **kw)
+        with open(os.path.join(GOLD, name, f"pair{k}.txt")) as fh:
+            assert text + "\n" == fh.read(), (name, k)
+
+
 def _pool_worker(args):
     """Runs in a forked multiprocessing.Pool worker: the drop-in calc_ld creates its context lazily, after the fork."""
     import os

@@ -196,6 +196,15 @@ typedef struct ldx_vcf_row {
 } ldx_vcf_row;
 int32_t ldx_store_ingest_vcf(ldx_ctx *ctx, const uint8_t *text, int64_t text_bytes, int32_t n_samples,
                              ldx_store **store_out, ldx_vcf_row *rows_out, int64_t rows_cap, int64_t *n_rows_out);
+/* The whole ingest in one call, in bounded memory: <chrom>.vcf.gz (BGZF) is inflated slab by slab (`slab_bytes` of text at a
+ * time, <= 0: 256 MiB; `threads` host threads, <= 0: all cores) into one pinned buffer, every slab is cut at its last newline,
+ * indexed, parsed and packed on the GPU into the next rows of the store; the records and their fixed columns come back in
+ * tables allocated by the library (*rows_out [*n_rows_out], *blob_out, *blob_off_out [*n_rows_out + 1]: as ldx_store_ingest_vcf /
+ * ldx_vcf_copy_prefixes give them; line_off is file-wide; release each with ldx_free_host).  *text_bytes_out (may be NULL) = the
+ * size of the decompressed text.  A plain gzip file (no block table) is read at once. */
+int32_t ldx_store_ingest_vcf_file(ldx_ctx *ctx, const char *path, int32_t n_samples, int64_t slab_bytes, int32_t threads,
+                                  ldx_store **store_out, ldx_vcf_row **rows_out, int64_t *n_rows_out, uint8_t **blob_out,
+                                  int64_t **blob_off_out, int64_t *text_bytes_out);
 /* Host side of the ingest: a whole .gz file -> malloc'ed text (*text_out; release it with ldx_free_host).  A BGZF file
  * (what tabix indexes, prep_intgen_data.py:138: independent gzip members of <= 64 KiB announcing their sizes) is
  * inflated by `threads` host threads in parallel (<= 0: all cores), every block straight into its final place, CRCs

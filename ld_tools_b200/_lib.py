@@ -64,6 +64,7 @@ SIGNATURES = {
     "ldx_store_planes_ptr": [_vp, _P(_vp)],
     "ldx_store_pack_gt": [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _i32, _vp],
     "ldx_store_ingest_vcf": [_vp, _vp, _i64, _i32, _P(_vp), _vp, _i64, _P(_i64)],
+    "ldx_store_ingest_vcf_file": [_vp, C.c_char_p, _i32, _i64, _i32, _P(_vp), _P(_vp), _P(_i64), _P(_vp), _P(_vp), _P(_i64)],
     "ldx_vcf_copy_prefixes": [_vp, _i64, _vp, _i64, _vp, _i64, _vp],
     "ldx_inflate_gz_file": [C.c_char_p, _i32, _P(_vp), _P(_i64), _P(_i32)],
     "ldx_free_host": [_vp],

@@ -557,6 +557,54 @@ extern "C" int32_t ldx_store_destroy(ldx_store *s) {
     return LDX_OK;
 }
 
+namespace ldx {
+int store_alloc_annotations(ldx_store *s) {
+    const size_t nv = (size_t)std::max<int64_t>(s->n_variants, 1);
+    if (s->d_pos0) return LDX_OK;
+    cudaError_t e = cudaMalloc(&s->d_pos0, nv * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_end0, nv * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_idnum, nv * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_eligible, nv);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_error(LDX_ERR_NOMEM, "store: annotation allocation failed"); }
+    return LDX_OK;
+}
+
+// A store allocated for an upper bound of its rows keeps the first n_variants: smaller arrays when that frees a quarter or more.
+template <typename T> static int shrink_array(T *&p, size_t old_n, size_t new_n, size_t unit, cudaStream_t st) {
+    if (!p || new_n >= old_n) return LDX_OK;
+    T *q = nullptr;
+    if (cudaMalloc(&q, std::max<size_t>(new_n, 1) * unit) != cudaSuccess) { cudaGetLastError(); return LDX_OK; }   // keep the large one
+    if (new_n && cudaMemcpyAsync(q, p, new_n * unit, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { cudaGetLastError(); cudaFree(q); return LDX_OK; }
+    cudaStreamSynchronize(st);
+    cudaFree(p);
+    p = q;
+    return LDX_OK;
+}
+int store_shrink(ldx_store *s, int64_t n_variants) {
+    if (n_variants < 0 || n_variants > s->n_variants) return set_error(LDX_ERR_ARG, "store_shrink: bad row count");
+    const size_t old_n = (size_t)s->n_variants, new_n = (size_t)n_variants;
+    s->n_variants = n_variants;
+    s->mask_set = false;
+    s->tmap_ready = false;
+    if (new_n * 4 > old_n * 3) return LDX_OK;
+    cudaStream_t st = s->ctx->stream;
+    shrink_array(s->d_planes, old_n, new_n, (size_t)s->stride_words * sizeof(uint64_t), st);
+    shrink_array(s->d_pos0, old_n, new_n, 4, st); shrink_array(s->d_end0, old_n, new_n, 4, st);
+    shrink_array(s->d_idnum, old_n, new_n, 8, st); shrink_array(s->d_eligible, old_n, new_n, 1, st);
+    {   // frequency records: padded (STORE_FREQ_PAD zeroed entries past the last row)
+        VarFreq *q = nullptr;
+        if (cudaMalloc(&q, (std::max<size_t>(new_n, 1) + STORE_FREQ_PAD) * sizeof(VarFreq)) == cudaSuccess) {
+            cudaMemsetAsync(q, 0, (std::max<size_t>(new_n, 1) + STORE_FREQ_PAD) * sizeof(VarFreq), st);
+            cudaStreamSynchronize(st);
+            cudaFree(s->d_freq);
+            s->d_freq = q;
+        } else cudaGetLastError();
+    }
+    if (s->d_kind) { cudaFree(s->d_kind); s->d_kind = nullptr; s->classify_dirty = true; }
+    return LDX_OK;
+}
+}  // namespace ldx
+
 extern "C" int32_t ldx_store_shape(const ldx_store *s, int64_t *n_variants, int32_t *n_hap, int32_t *stride_words) {
     LDX_REQUIRE(s, "store is NULL");
     if (n_variants) *n_variants = s->n_variants;

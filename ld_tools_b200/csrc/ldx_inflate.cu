@@ -23,7 +23,7 @@
 
 namespace {
 
-struct Member { size_t in_off, in_len, out_off, out_len, data_off; };   // data_off: first deflate byte inside the member
+using Member = ldx::BgzfMember;       // {in_off, in_len, out_off, out_len, data_off}; data_off: first deflate byte inside the member
 
 // Parses one gzip member header at p[0..n).  Returns the header length (0 = not a gzip header) and, for a BGZF
 // member, its total size in *bsize (else 0).
@@ -68,6 +68,68 @@ bool inflate_member(const uint8_t *in, const Member &m, uint8_t *out) {
 }
 
 }  // namespace
+
+namespace ldx {
+
+// Walks the members of a BGZF file by their announced sizes.  false: not (entirely) BGZF.
+bool bgzf_scan(const uint8_t *in, size_t n, std::vector<BgzfMember> &members, size_t *total_out) {
+    members.clear();
+    size_t total = 0;
+    for (size_t off = 0; off < n;) {
+        size_t bsize = 0;
+        const size_t h = gzip_header(in + off, n - off, &bsize);
+        if (!h || !bsize || bsize < h + 8 || off + bsize > n) return false;
+        const uint8_t *t = in + off + bsize - 4;
+        const size_t isize = t[0] | (t[1] << 8) | (t[2] << 16) | ((size_t)t[3] << 24);
+        if (isize > (1u << 16)) return false;
+        members.push_back(BgzfMember{off, bsize, total, isize, h});
+        total += isize;
+        off += bsize;
+    }
+    *total_out = total;
+    return true;
+}
+
+// Members [first, last) inflated by `threads` host threads, member k to out + (members[k].out_off - members[first].out_off).
+bool bgzf_inflate_range(const uint8_t *in, const std::vector<BgzfMember> &members, size_t first, size_t last, uint8_t *out, int threads) {
+    if (first >= last) return true;
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min<int>(nt, 64));
+    nt = (int)std::min<size_t>((size_t)nt, std::max<size_t>((last - first) / 16, 1));
+    uint8_t *base = out - members[first].out_off;
+    std::atomic<size_t> next{first};
+    std::atomic<bool> failed{false};
+    auto work = [&]() {
+        for (;;) {
+            const size_t b = next.fetch_add(64);               // 64 members (<= 4 MiB of text) per grab
+            if (b >= last || failed.load()) return;
+            const size_t e = std::min(last, b + 64);
+            for (size_t k = b; k < e; ++k)
+                if (members[k].out_len && !inflate_member(in, members[k], base)) { failed.store(true); return; }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    return !failed.load();
+}
+
+int read_whole_file(const char *path, std::vector<uint8_t> &in) {
+    FILE *fh = fopen(path, "rb");
+    if (!fh) return set_error(LDX_ERR_ARG, std::string("cannot open ") + path);
+    fseek(fh, 0, SEEK_END);
+    const long sz = ftell(fh);
+    fseek(fh, 0, SEEK_SET);
+    if (sz < 0) { fclose(fh); return set_error(LDX_ERR_ARG, "cannot size the file"); }
+    in.resize((size_t)sz);
+    const size_t got = sz ? fread(in.data(), 1, (size_t)sz, fh) : 0;
+    fclose(fh);
+    if (got != (size_t)sz) return set_error(LDX_ERR_ARG, "short read");
+    return LDX_OK;
+}
+
+}  // namespace ldx
 
 /* Whole .gz file -> malloc'ed text (*text_out, free with ldx_free_host).  threads <= 0: all host cores.
  * *was_bgzf_out (may be NULL) = 1 when the file was a BGZF series inflated in parallel. */

@@ -182,6 +182,12 @@ int launch_publish(ldx_ctx *ctx);   // enqueue the mailbox update for ctx->seq
 void timing_begin(ldx_ctx *ctx);
 void timing_end(ldx_ctx *ctx);
 
+// BGZF pieces of the ingest path (ldx_inflate.cu), shared with the slab-wise file ingest (ldx_vcf.cu)
+struct BgzfMember { size_t in_off, in_len, out_off, out_len, data_off; };
+bool bgzf_scan(const uint8_t *in, size_t n, std::vector<BgzfMember> &members, size_t *total_out);
+bool bgzf_inflate_range(const uint8_t *in, const std::vector<BgzfMember> &members, size_t first, size_t last, uint8_t *out, int threads);
+int read_whole_file(const char *path, std::vector<uint8_t> &in);
+
 constexpr int WINDOW_CHUNK = 256;   // rows per work item of the window kernel
 constexpr int WINDOW_MQ = 4;        // queries per work item of the multi-query window kernel (ldx_window.cu: MQ)
 struct WindowMqBlock { int64_t base, first_item; int32_t a, b; };   // = ldx::MqBlock (ldx_window.cu)

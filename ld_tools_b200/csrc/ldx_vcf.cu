@@ -151,12 +151,12 @@ parse_lines_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
 __global__ void __launch_bounds__(256)
 compact_rows_kernel(const ldx_vcf_row *__restrict__ tmp_rows, const uint32_t *__restrict__ is_rec, const uint32_t *__restrict__ rec_index,
                     int64_t n_lines, ldx_vcf_row *__restrict__ rows, int64_t *__restrict__ gt_abs, int32_t *__restrict__ pos0,
-                    int32_t *__restrict__ end0, int64_t *__restrict__ idnum, uint8_t *__restrict__ eligible) {
+                    int32_t *__restrict__ end0, int64_t *__restrict__ idnum, uint8_t *__restrict__ eligible, int64_t row_base) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_lines || !is_rec[k]) return;
-    const int64_t row = rec_index[k];
+    const int64_t row = rec_index[k];                          // relative to this text's first record (store row = row_base + row)
     ldx_vcf_row r = tmp_rows[k];
-    if (r.idnum < 0) r.idnum = -1 - row;                       // unique per row: never equal to a query's id (ld_area.py:222)
+    if (r.idnum < 0) r.idnum = -1 - (row_base + row);          // unique per row: never equal to a query's id (ld_area.py:222)
     rows[row] = r;
     gt_abs[row] = (r.status & 2) ? -1 : r.line_off + r.gt_off;
     pos0[row] = r.pos - 1;
@@ -176,6 +176,8 @@ merge_status_kernel(ldx_vcf_row *__restrict__ rows, const uint8_t *__restrict__ 
 
 int launch_pack_gt(ldx_ctx *ctx, const uint8_t *d_text, const int64_t *d_row_off, int64_t row_pitch, int64_t n_rows, int32_t n_samples,
                    uint64_t *d_planes_first, int32_t stride_words, uint8_t *d_status);
+int store_alloc_annotations(ldx_store *s);                               // ldx_api.cu: pos0 / end0 / idnum / eligible of every row
+int store_shrink(ldx_store *s, int64_t n_variants);                      // ldx_api.cu: keep the first n_variants rows
 int scratch_get(ldx_ctx *ctx, int which, size_t bytes, void **out);      // ldx_api.cu: block `which` (0..2) of the context's arena
 void scratch_trim(ldx_ctx *ctx, size_t keep_bytes);                      // ... and: free those blocks if larger than keep_bytes
 
@@ -196,12 +198,12 @@ struct Carve {
 
 using namespace ldx;
 
-extern "C" int32_t ldx_store_ingest_vcf(ldx_ctx *ctx, const uint8_t *text, int64_t text_bytes, int32_t n_samples,
-                                        ldx_store **store_out, ldx_vcf_row *rows_out, int64_t rows_cap, int64_t *n_rows_out) {
-    LDX_REQUIRE(ctx && text && store_out && n_rows_out, "NULL argument");
-    LDX_REQUIRE(text_bytes > 0 && n_samples > 0 && n_samples <= (1 << 23), "bad text size or sample count");
-    LDX_REQUIRE(rows_cap >= 0 && (rows_out || rows_cap == 0), "bad rows buffer");
-    *store_out = nullptr; *n_rows_out = 0;
+// VCF text (whole lines) -> rows of a store.  *store_io == nullptr: a new store of exactly the text's records is created;
+// else the records land at rows row_base ... of the given (annotated, large enough) store.  rows_out[rows_cap] receives the
+// records (line_off relative to `text`).
+static int ingest_text(ldx_ctx *ctx, const uint8_t *text, int64_t text_bytes, int32_t n_samples, ldx_store **store_io, int64_t row_base,
+                       ldx_vcf_row *rows_out, int64_t rows_cap, int64_t *n_rows_out, bool trim_scratch) {
+    *n_rows_out = 0;
     LDX_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     // ---- phase 1: the text, once, with a final newline and slack for K1's aligned 16-byte loads; newline counts per block
@@ -228,7 +230,8 @@ extern "C" int32_t ldx_store_ingest_vcf(ldx_ctx *ctx, const uint8_t *text, int64
     LDX_CUDA(cudaMemcpyAsync(&n_lines32, d_base + n_blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     LDX_CUDA(cudaStreamSynchronize(st));
     const int64_t n_lines = n_lines32;
-    LDX_REQUIRE(n_lines > 0 && n_lines < (1ll << 31), "vcf ingest: no lines");
+    LDX_REQUIRE(n_lines < (1ll << 31), "vcf ingest: too many lines for one call");
+    if (n_lines == 0) return LDX_OK;
     // ---- phase 2: newline positions, per-line parse, record numbering
     size_t cub_bytes2 = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes2, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)(n_lines + 1), st);
@@ -262,45 +265,178 @@ extern "C" int32_t ldx_store_ingest_vcf(ldx_ctx *ctx, const uint8_t *text, int64
     int64_t *d_gt = c3.take<int64_t>((size_t)n_rec);
     uint8_t *d_status = c3.take<uint8_t>((size_t)n_rec);
     // ---- the store, its annotations, the genotype planes
-    ldx_store *s = nullptr;
-    LDX_TRY(ldx_store_create(ctx, n_rec, 2 * n_samples, &s));
+    ldx_store *s = *store_io;
+    const bool own_store = s == nullptr;
     int rc = LDX_OK;
-    {
-        const size_t nv = (size_t)std::max<int64_t>(n_rec, 1);
-        cudaError_t e = cudaMalloc(&s->d_pos0, nv * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&s->d_end0, nv * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&s->d_idnum, nv * 8);
-        if (e == cudaSuccess) e = cudaMalloc(&s->d_eligible, nv);
-        if (e != cudaSuccess) { cudaGetLastError(); rc = set_error(LDX_ERR_NOMEM, "vcf ingest: annotation allocation failed"); }
-    }
+    if (own_store) {
+        LDX_TRY(ldx_store_create(ctx, n_rec, 2 * n_samples, &s));
+        rc = store_alloc_annotations(s);
+    } else if (row_base + n_rec > s->n_variants) return set_error(LDX_ERR_CAPACITY, "vcf ingest: more records than the store has rows");
     if (rc == LDX_OK && n_rec > 0) {
-        compact_rows_kernel<<<lgrid, 256, 0, st>>>(d_tmp, d_isrec, d_recidx, n_lines, d_rows, d_gt, s->d_pos0, s->d_end0, s->d_idnum, s->d_eligible);
+        compact_rows_kernel<<<lgrid, 256, 0, st>>>(d_tmp, d_isrec, d_recidx, n_lines, d_rows, d_gt, s->d_pos0 + row_base, s->d_end0 + row_base,
+                                                   s->d_idnum + row_base, s->d_eligible + row_base, row_base);
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) rc = set_error(LDX_ERR_CUDA, "vcf ingest: compact launch failed");
     }
-    if (rc == LDX_OK && n_rec > 0) rc = launch_pack_gt(ctx, d_text, d_gt, 0, n_rec, n_samples, s->d_planes, s->stride_words, d_status);   // rows with offset -1: zeros
+    if (rc == LDX_OK && n_rec > 0)
+        rc = launch_pack_gt(ctx, d_text, d_gt, 0, n_rec, n_samples, s->d_planes + row_base * s->stride_words, s->stride_words, d_status);   // rows with offset -1: zeros
     if (rc == LDX_OK && n_rec > 0) {
         // rows with a field outside the plain "a|b" alphabet: parsed again in full, aux planes, the general route (ldx_general.cu)
         std::vector<uint8_t> h_status((size_t)n_rec);
         if (cudaMemcpyAsync(h_status.data(), d_status, (size_t)n_rec, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
             rc = cuda_fail(cudaGetLastError(), "vcf ingest: genotype status");
-        if (rc == LDX_OK) rc = store_pack_general(s, 0, n_rec, d_text, n, d_gt, 0, n_samples, h_status.data());
+        if (rc == LDX_OK) rc = store_pack_general(s, row_base, n_rec, d_text, n, d_gt, 0, n_samples, h_status.data());
         if (rc == LDX_OK && cudaMemcpyAsync(d_status, h_status.data(), (size_t)n_rec, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "vcf ingest: status");
         if (rc == LDX_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "vcf ingest: status");      // h_status is a local
     }
     if (rc == LDX_OK && n_rec > 0) {
-        merge_status_kernel<<<(unsigned)((n_rec + 255) / 256), 256, 0, st>>>(d_rows, d_status, n_rec, s->d_eligible);
+        merge_status_kernel<<<(unsigned)((n_rec + 255) / 256), 256, 0, st>>>(d_rows, d_status, n_rec, s->d_eligible + row_base);
         ctx->launches++;
         if (cudaMemcpyAsync(rows_out, d_rows, sizeof(ldx_vcf_row) * (size_t)n_rec, cudaMemcpyDeviceToHost, st) != cudaSuccess)
             rc = cuda_fail(cudaGetLastError(), "vcf ingest: rows download");
     }
     if (cudaStreamSynchronize(st) != cudaSuccess && rc == LDX_OK) rc = cuda_fail(cudaGetLastError(), "vcf ingest");
-    scratch_trim(ctx, (size_t)256 << 20);      // the text of a whole chromosome does not stay behind in the arena
-    if (rc != LDX_OK) { ldx_store_destroy(s); return rc; }
+    if (trim_scratch) scratch_trim(ctx, (size_t)256 << 20);      // the text of a whole chromosome does not stay behind in the arena
+    if (rc != LDX_OK) { if (own_store) ldx_store_destroy(s); return rc; }
     s->annotated = true;
+    s->mask_set = false;
+    *store_io = s;
+    return LDX_OK;
+}
+
+extern "C" int32_t ldx_store_ingest_vcf(ldx_ctx *ctx, const uint8_t *text, int64_t text_bytes, int32_t n_samples,
+                                        ldx_store **store_out, ldx_vcf_row *rows_out, int64_t rows_cap, int64_t *n_rows_out) {
+    LDX_REQUIRE(ctx && text && store_out && n_rows_out, "NULL argument");
+    LDX_REQUIRE(text_bytes > 0 && n_samples > 0 && n_samples <= (1 << 23), "bad text size or sample count");
+    LDX_REQUIRE(rows_cap >= 0 && (rows_out || rows_cap == 0), "bad rows buffer");
+    *store_out = nullptr;
+    ldx_store *s = nullptr;
+    LDX_TRY(ingest_text(ctx, text, text_bytes, n_samples, &s, 0, rows_out, rows_cap, n_rows_out, true));
+    if (!s) {                                  // a text without a single line: an empty store
+        LDX_TRY(ldx_store_create(ctx, 0, 2 * n_samples, &s));
+        const int rc = store_alloc_annotations(s);
+        if (rc != LDX_OK) { ldx_store_destroy(s); return rc; }
+        s->annotated = true;
+    }
     *store_out = s;
     return LDX_OK;
 }
+
+// ------------------------------------------------------------------------------------------ a whole <chrom>.vcf.gz, slab by slab
+// a real 1000 Genomes chromosome is ~65 GB of text (6.4 M records x 10 KB) for a 4 GB store; inflating it into
+// one host buffer and uploading it as one device buffer needs 65 GB of each.  Here the BGZF members are inflated in groups of
+// `slab_bytes` into ONE pinned host buffer, each slab is cut at its last newline (the partial line is carried over), indexed,
+// parsed and packed into the store at the next row, and its records' fixed columns are kept: host and device hold one slab of
+// text at a time.  The store is allocated for an upper bound of the record count (a record line has at least 2 * n_samples + 18
+// bytes) and trimmed to the rows found.
+extern "C" int32_t ldx_store_ingest_vcf_file(ldx_ctx *ctx, const char *path, int32_t n_samples, int64_t slab_bytes, int32_t threads,
+                                             ldx_store **store_out, ldx_vcf_row **rows_out, int64_t *n_rows_out, uint8_t **blob_out,
+                                             int64_t **blob_off_out, int64_t *text_bytes_out) {
+    LDX_REQUIRE(ctx && path && store_out && rows_out && n_rows_out && blob_out && blob_off_out, "NULL argument");
+    LDX_REQUIRE(n_samples > 0 && n_samples <= (1 << 23), "bad sample count");
+    *store_out = nullptr; *rows_out = nullptr; *n_rows_out = 0; *blob_out = nullptr; *blob_off_out = nullptr;
+    if (text_bytes_out) *text_bytes_out = 0;
+    if (slab_bytes <= 0) slab_bytes = (int64_t)256 << 20;
+    slab_bytes = std::max<int64_t>(slab_bytes, 4096);       // a line (or a BGZF member) that does not fit a slab is an error, not a hang
+    LDX_CUDA(cudaSetDevice(ctx->device));
+    std::vector<uint8_t> in;
+    LDX_TRY(read_whole_file(path, in));
+    std::vector<BgzfMember> members;
+    size_t total = 0;
+    const bool bgzf = !in.empty() && bgzf_scan(in.data(), in.size(), members, &total);
+    std::vector<ldx_vcf_row> rows;
+    std::vector<uint8_t> blob;
+    std::vector<int64_t> off(1, 0);
+    ldx_store *s = nullptr;
+    int rc = LDX_OK;
+    auto keep_columns = [&](const uint8_t *text, int64_t n_text, int64_t first, int64_t n_new, int64_t text_base) {
+        // the nine fixed columns of the new records (what the writers print), and their line offsets made file-wide
+        for (int64_t r = first; r < first + n_new; ++r) {
+            ldx_vcf_row &x = rows[(size_t)r];
+            if (x.line_off < 0 || x.line_off > n_text) return set_error(LDX_ERR_STATE, "vcf ingest: record outside its slab");
+            const int64_t len = std::max<int64_t>(0, std::min<int64_t>(x.gt_off, n_text - x.line_off));   // a refused record (status 2): what there is
+            blob.insert(blob.end(), text + x.line_off, text + x.line_off + len);
+            off.push_back((int64_t)blob.size());
+            x.line_off += text_base;
+        }
+        return (int)LDX_OK;
+    };
+    if (!bgzf) {
+        // plain gzip (one stream): no block table to cut by -- the whole text at once, as ldx_inflate_gz_file + ldx_store_ingest_vcf
+        uint8_t *text = nullptr; int64_t n_text = 0;
+        LDX_TRY(ldx_inflate_gz_file(path, threads, &text, &n_text, nullptr));
+        int64_t n_rec = 0;
+        if (n_text > 0) {
+            rows.resize((size_t)(n_text / std::max<int64_t>(2ll * n_samples + 18, 1) + 16));
+            rc = ingest_text(ctx, text, n_text, n_samples, &s, 0, rows.data(), (int64_t)rows.size(), &n_rec, true);
+            rows.resize((size_t)n_rec);
+            if (rc == LDX_OK) rc = keep_columns(text, n_text, 0, n_rec, 0);
+        }
+        std::free(text);
+        total = (size_t)n_text;
+    } else {
+        const int64_t min_line = 2ll * n_samples + 18;
+        const int64_t n_max = (int64_t)total / min_line + 16;
+        rc = ldx_store_create(ctx, n_max, 2 * n_samples, &s);
+        if (rc == LDX_OK) rc = store_alloc_annotations(s);
+        uint8_t *h_slab = nullptr;
+        const size_t slab_cap = (size_t)slab_bytes + (1u << 16) + 64;                 // + one member + the final newline
+        if (rc == LDX_OK && cudaMallocHost((void **)&h_slab, slab_cap) != cudaSuccess) { cudaGetLastError(); rc = set_error(LDX_ERR_NOMEM, "vcf ingest: pinned slab buffer"); }
+        int64_t carry = 0, row_base = 0, text_base = 0;               // text_base: file-wide offset of h_slab[0]
+        size_t m = 0;
+        while (rc == LDX_OK && (m < members.size() || carry > 0)) {
+            // the next group of members behind the carried-over partial line
+            size_t e = m;
+            int64_t fill = carry;
+            while (e < members.size() && fill + (int64_t)members[e].out_len <= (int64_t)slab_bytes) fill += (int64_t)members[e++].out_len;
+            if (e == m && m < members.size()) { rc = set_error(LDX_ERR_DATA, "vcf ingest: a line longer than the slab"); break; }
+            if (!bgzf_inflate_range(in.data(), members, m, e, h_slab + carry, threads)) { rc = set_error(LDX_ERR_ARG, "inflate: corrupt BGZF block (deflate error or CRC mismatch)"); break; }
+            const bool last = e == members.size();
+            int64_t cut = fill;
+            if (!last) {
+                while (cut > 0 && h_slab[cut - 1] != '\n') --cut;     // whole lines only; the rest is carried over
+                if (cut == 0) { rc = set_error(LDX_ERR_DATA, "vcf ingest: a line longer than the slab"); break; }
+            }
+            if (cut > 0) {
+                const size_t before = rows.size();
+                rows.resize(before + (size_t)(cut / min_line + 16));
+                int64_t n_rec = 0;
+                rc = ingest_text(ctx, h_slab, cut, n_samples, &s, row_base, rows.data() + before, (int64_t)(rows.size() - before), &n_rec, false);
+                rows.resize(before + (size_t)(rc == LDX_OK ? n_rec : 0));
+                if (rc == LDX_OK) rc = keep_columns(h_slab, cut, (int64_t)before, n_rec, text_base);
+                row_base += n_rec;
+            }
+            carry = fill - cut;
+            if (carry > 0) std::memmove(h_slab, h_slab + cut, (size_t)carry);
+            text_base += cut;
+            m = e;
+            if (last) { if (carry > 0) rc = set_error(LDX_ERR_STATE, "vcf ingest: text left over"); break; }
+        }
+        if (h_slab) cudaFreeHost(h_slab);
+        scratch_trim(ctx, (size_t)256 << 20);
+        if (rc == LDX_OK) rc = store_shrink(s, row_base);
+    }
+    if (rc == LDX_OK && !s) {
+        rc = ldx_store_create(ctx, 0, 2 * n_samples, &s);
+        if (rc == LDX_OK) rc = store_alloc_annotations(s);
+        if (rc == LDX_OK) s->annotated = true;
+    }
+    ldx_vcf_row *r_out = nullptr; uint8_t *b_out = nullptr; int64_t *o_out = nullptr;
+    if (rc == LDX_OK) {
+        r_out = static_cast<ldx_vcf_row *>(std::malloc(std::max<size_t>(rows.size() * sizeof(ldx_vcf_row), 1)));
+        b_out = static_cast<uint8_t *>(std::malloc(std::max<size_t>(blob.size(), 1)));
+        o_out = static_cast<int64_t *>(std::malloc(off.size() * sizeof(int64_t)));
+        if (!r_out || !b_out || !o_out) rc = set_error(LDX_ERR_NOMEM, "vcf ingest: host tables");
+    }
+    if (rc != LDX_OK) { std::free(r_out); std::free(b_out); std::free(o_out); if (s) ldx_store_destroy(s); return rc; }
+    std::memcpy(r_out, rows.data(), rows.size() * sizeof(ldx_vcf_row));
+    std::memcpy(b_out, blob.data(), blob.size());
+    std::memcpy(o_out, off.data(), off.size() * sizeof(int64_t));
+    *store_out = s; *rows_out = r_out; *n_rows_out = (int64_t)rows.size(); *blob_out = b_out; *blob_off_out = o_out;
+    if (text_bytes_out) *text_bytes_out = (int64_t)total;
+    return LDX_OK;
+}
+
 
 /* Host helper: the nine fixed columns of every record, back to back (record r = out[off[r], off[r+1])), so that the
  * caller can drop the multi-gigabyte text and still print ID / REF / ALT / INFO of the rows it reports. */

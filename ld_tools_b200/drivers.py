@@ -12,6 +12,7 @@ golden files under tests/golden/drivers/ were produced by the UNMODIFIED referen
 
 There is no CPU path here: every LD number comes out of libldx.so.
 """
+import gzip
 import json
 import os
 import re
@@ -179,11 +180,14 @@ class ChromData:
         self.vts = _Column(self, "info_off", vt=True)
 
     # ---- first run: the VCF itself.  The host only inflates the file and reads the #CHROM line; splitting lines and
-    #      fields, parsing POS / ID / REF / INFO and packing the genotypes all happen on the GPU (ldx_store_ingest_vcf).
-    def _ingest(self, ctx, vcf_path):
-        host = HostText(vcf_path)                          # BGZF blocks inflated in parallel by the library
-        raw = host.array
-        head = raw[:1 << 24].tobytes()                     # the meta lines and the #CHROM line
+    #      fields, parsing POS / ID / REF / INFO and packing the genotypes all happen on the GPU, one slab of text at a time
+    #      (ldx_store_ingest_vcf_file: a 1000 Genomes chromosome is ~65 GB of text for a 4 GB store).
+    SLAB_BYTES = int(os.environ.get("LDX_INGEST_SLAB_MB", "256")) << 20
+
+    @staticmethod
+    def _header_samples(vcf_path):
+        with gzip.open(vcf_path, "rb") as fh:              # the meta lines and the #CHROM line
+            head = fh.read(1 << 24)
         h = 0 if head.startswith(b"#CHROM") else head.find(b"\n#CHROM") + 1
         if h == 0 and not head.startswith(b"#CHROM"):
             raise ValueError(f"{vcf_path}: no #CHROM header line in the first 16 MiB")
@@ -191,21 +195,22 @@ class ChromData:
         samples = head[h:e if e >= 0 else len(head)].decode().rstrip("\r").split("\t")[9:]
         if not samples:
             raise ValueError(f"{vcf_path}: no sample columns")
-        self.store, rows = Store.ingest_vcf(ctx, raw, len(samples))
+        return samples
+
+    def _ingest(self, ctx, vcf_path):
+        samples = self._header_samples(vcf_path)
+        self.store, rows, blob, off, _ = Store.ingest_vcf_file(ctx, vcf_path, len(samples), slab_bytes=self.SLAB_BYTES)
         # status bit 0 (a genotype field that is not plain "a|b": haploid, missing, other codes, unphased) is fine: such rows
         # take the engine's general route.  What no parser takes -- a line that is not a record, a POS that is not a number,
         # a field with more than two alleles -- is refused by name.
         bad = np.flatnonzero((rows["status"] & 14) != 0)
         if len(bad):
             k = int(bad[0])
-            line = raw[rows["line_off"][k]:rows["line_off"][k] + 60].tobytes().decode(errors="replace")
+            line = blob[off[k]:off[k] + 60].tobytes().decode(errors="replace")
             self.store.close()
             raise ValueError(f"{vcf_path}: record {k} ({line!r}...) is not a VCF record this engine can read "
                              f"(status {int(rows['status'][k])}: 2 = too few columns, 4 = POS, 8 = genotype fields)")
-        blob, off = Store.vcf_fixed_columns(ctx._lib, raw, rows)
         self._set_columns(samples, rows, blob.tobytes(), off)
-        host.close()
-
 
     def select_samples(self, sample_names):
         """The haplotypes of the chosen samples; names absent from the VCF are skipped like the reference's

@@ -341,6 +341,22 @@ class Store:
             check(rc)
             return cls(ctx, 0, 0, _handle=h), rows[:n.value]
 
+    @classmethod
+    def ingest_vcf_file(cls, ctx, path, n_samples, slab_bytes=0, threads=0):
+        """<chrom>.vcf.gz -> (store, rows, blob, off, text_bytes) in bounded memory (ldx_store_ingest_vcf_file): the file is inflated,
+        parsed and packed `slab_bytes` of text at a time (0: 256 MiB), so neither the host nor the GPU ever holds the whole text.
+        rows: one VCF_ROW_DTYPE record per variant; blob/off: the records' fixed columns (as vcf_fixed_columns)."""
+        h, n, tb = C.c_void_p(), C.c_int64(), C.c_int64()
+        p_rows, p_blob, p_off = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        lib = ctx._lib
+        check(lib.ldx_store_ingest_vcf_file(ctx._h, os.fsencode(path), int(n_samples), int(slab_bytes), int(threads), C.byref(h),
+                                            C.byref(p_rows), C.byref(n), C.byref(p_blob), C.byref(p_off), C.byref(tb)))
+        nr = n.value
+        off = np.array(_lib_text(lib, p_off, (nr + 1) * 8).view(np.int64))
+        rows = np.array(_lib_text(lib, p_rows, nr * VCF_ROW_DTYPE.itemsize).view(VCF_ROW_DTYPE))      # an empty table is released at once
+        blob = _lib_text(lib, p_blob, int(off[-1]))
+        return cls(ctx, 0, 0, _handle=h), rows, blob, off, tb.value
+
     @staticmethod
     def vcf_fixed_columns(lib, text, rows):
         """(blob, off): the nine fixed columns of every record back to back, record r = blob[off[r]:off[r+1]]."""

@@ -387,3 +387,52 @@ def test_gpu_vcf_ingest_matches_a_host_parse(data, ctx):
              fixed.format(pos=82, id="rs0011", ref="AT", alt="A", info="VT=INDEL;AF=0.5") + gt("1|1 0|1 1|0")]
     for text in ("\n".join(lines) + "\n", "\n".join(lines), "\r\n".join(lines) + "\r\n", "\n".join(lines[:3]) + "\n"):
         _check_ingest(ctx, text.encode(), 3)
+
+
+@pytest.mark.parametrize("which", ["chr22", "chrX"])
+def test_slab_ingest_of_the_file_equals_the_whole_text_ingest(data, data_x, ctx, tmp_path, which):
+    """ldx_store_ingest_vcf_file with slabs of 4 KiB (dozens of slabs, every one cut inside a line and carried over) builds
+    the same store, record table and fixed columns as ldx_store_ingest_vcf on the whole text -- general-route rows included --
+    and the drivers' first-run path (ChromData._ingest) goes through it."""
+    import gzip
+    import numpy as np
+    from ld_tools_b200 import Store
+    from ld_tools_b200.drivers import ChromData
+    from ld_tools_b200.synth import BgzfWriter
+    intgen, name = (data[1], "22.vcf.gz") if which == "chr22" else (data_x[1], "X.vcf.gz")
+    with gzip.open(os.path.join(intgen, name), "rb") as fh:
+        raw = fh.read()
+    n_samples = len(ChromData._header_samples(os.path.join(intgen, name)))
+
+    class SmallBlocks(BgzfWriter):           # members of 1,500 bytes: a 4 KiB slab holds two of them and six or seven lines
+        BLOCK = 1500
+    path = str(tmp_path / name)
+    with SmallBlocks(path) as fh:
+        fh.write(raw)
+    assert len(raw) > 30 * 4096
+    whole, rows_w = Store.ingest_vcf(ctx, raw, n_samples)
+    blob_w, off_w = Store.vcf_fixed_columns(ctx._lib, raw, rows_w)
+    for slab in (4096, 30_000, 0):
+        st, rows, blob, off, text_bytes = Store.ingest_vcf_file(ctx, path, n_samples, slab_bytes=slab, threads=3)
+        assert text_bytes == len(raw) and st.n_variants == whole.n_variants == len(rows)
+        assert rows.tobytes() == rows_w.tobytes()                         # line_off is file-wide, idnum of unnamed records too
+        assert (off == off_w).all() and blob.tobytes() == blob_w.tobytes()
+        assert (st.download() == whole.download()).all()
+        st.select_all(); whole.select_all()
+        for a, b in zip(st.row_counts(), whole.row_counts()):
+            assert np.array_equal(a, b)
+        for a, b in zip(st.counts(), whole.counts()):
+            assert np.array_equal(a, b)
+        rows_all = np.arange(min(st.n_variants, 700), dtype=np.int64)
+        assert np.array_equal(st.triangle(rows_all, "r_square")[0], whole.triangle(rows_all, "r_square")[0])
+        q = np.arange(5, st.n_variants, 97, dtype=np.int64)
+        lo, hi = np.maximum(q - 150, 0), np.minimum(q + 150, st.n_variants)
+        ws, we = np.zeros(len(q), np.int32), np.full(len(q), 2**31 - 1, np.int32)
+        h1, _ = st.window(q, lo, hi, ws, we, "r_square", 2000)
+        h2, _ = whole.window(q, lo, hi, ws, we, "r_square", 2000)
+        assert np.array(h1).tobytes() == np.array(h2).tobytes() and len(h1) > 0
+        st.close()
+    whole.close()
+    cd = ChromData(ctx, path, cache=False)
+    assert cd.rows.tobytes() == rows_w.tobytes() and cd._blob == blob_w.tobytes()
+    cd.close()

@@ -286,7 +286,8 @@ def full_mask(stride_words):
 def leg_triangle(env, engine):
     torch, args, ctx, stream, dev = env.torch, env.args, env.ctx, env.stream, env.dev
     from ld_tools_b200 import Context, Store
-    from ld_tools_b200.engine import ENGINE_AUTO, ENGINE_MMA
+    from ld_tools_b200._lib import PAIR_HIT_DTYPE, R2_MASK
+    from ld_tools_b200.engine import ENGINE_AUTO, ENGINE_MMA, threshold_e4
     from ld_tools_b200.synth import pack_bits, synth_haplotypes
 
     # synthetic 1000G-shaped input: this rank's own 2,000-variant set
@@ -388,67 +389,88 @@ def leg_triangle(env, engine):
             l_ctx.set_stream(l_stream.cuda_stream)
             l_store = Store(l_ctx, N_VARIANTS, N_HAP)
         out_pin = torch.empty(n_pairs, dtype=torch.int32).pin_memory()
-        lanes.append({"ctx": l_ctx, "stream": l_stream, "store": l_store, "out_pin": out_pin, "out": out_pin.numpy().view(np.uint32)})
+        lanes.append({"ctx": l_ctx, "stream": l_stream, "store": l_store, "out_pin": out_pin, "out": out_pin.numpy().view(np.uint32),
+                      "out16": out_pin.numpy().view(np.uint16)[:n_pairs], "hits": np.zeros(1 << 16, dtype=PAIR_HIT_DTYPE), "n_hits": 0})
     e_each = max(args.e2e_steps // n_ctx, 3)
     e_steps = e_each * n_ctx
+    # the result forms a caller can ask for: 2 bytes per pair of the one measure the drivers print (the headline: ld_triangle.py:230
+    # only ever prints one), the 4-byte words with both measures, and -- with -z 0.8 -- only the pairs that pass
+    thres_z = threshold_e4(0.8)
+    forms = [("values16", e_each), ("packed32", max(e_each // 2, 3)), ("hits_z", max(e_each // 2, 3))]
     gate = threading.Barrier(n_ctx + 1)
-    ends = [env.event() for _ in lanes]
-    walls = [0.0] * n_ctx
+    ends = {f: [env.event() for _ in lanes] for f, _ in forms}
 
     def lane_main(k):
         lane = lanes[k]
+        st = lane["store"]
         torch.cuda.set_device(env.local_rank)
-        for phase_steps in (max(args.warmup // 2, 3), e_each):          # warm-up pass, then the timed pass
+        for form, n_steps in [(f, max(args.warmup // 2, 3)) for f, _ in forms] + forms:      # a warm-up pass of every form, then the timed passes
             gate.wait()
-            t0 = time.perf_counter()
-            for _ in range(phase_steps):
-                lane["store"].upload(0, planes_host)
-                lane["store"].set_mask(mask_np)
-                lane["store"].triangle(rows, engine=engine, out=lane["out"])
-            ends[k].record(lane["stream"])
-            walls[k] = time.perf_counter() - t0
+            for _ in range(n_steps):
+                st.upload(0, planes_host, wait=False)          # pinned source, enqueued; the step's one wait is in the result call
+                st.set_mask(mask_np)
+                if form == "values16":
+                    st.triangle_values(rows, "r_square", engine=engine, out=lane["out16"])
+                elif form == "packed32":
+                    st.triangle(rows, engine=engine, out=lane["out"])
+                else:
+                    lane["n_hits"] = len(st.triangle_hits(rows, "r_square", thres_z, engine=engine, out=lane["hits"]))
+            ends[form][k].record(lane["stream"])
             gate.wait()
 
     threads = [threading.Thread(target=lane_main, args=(k,)) for k in range(n_ctx)]
     for t in threads:
         t.start()
-    gate.wait(); gate.wait()                     # warm-up pass
-    env.barrier()
-    e0 = env.event()
-    e0.record(stream)
-    for s in (lane["stream"] for lane in lanes[1:]):
-        s.wait_event(e0)
-    t0 = time.perf_counter()
-    gate.wait(); gate.wait()                     # timed pass: every lane runs its steps
-    e2e_wall = time.perf_counter() - t0
+    for _ in forms:
+        gate.wait(); gate.wait()                 # warm-up passes
+    form_ms, form_wall = {}, {}
+    for form, _ in forms:
+        env.barrier()
+        e0 = env.event()
+        e0.record(stream)
+        for s_ in (lane["stream"] for lane in lanes[1:]):
+            s_.wait_event(e0)
+        t0 = time.perf_counter()
+        gate.wait(); gate.wait()                 # timed pass: every lane runs its steps
+        form_wall[form] = time.perf_counter() - t0
+        env.barrier()
+        form_ms[form] = max(float(e0.elapsed_time(e)) for e in ends[form])      # device clock, start of the first step to the end of the last copy
     for t in threads:
         t.join()
-    env.barrier()
-    e2e_ms = max(float(e0.elapsed_time(e)) for e in ends)      # device clock, start of the first step to the end of the last copy
+    e2e_ms, e2e_wall = form_ms["values16"], form_wall["values16"]
+    # the 2-byte values are the 4-byte words narrowed (checked on what the timed passes left in the lanes' buffers)
+    w32 = lanes[0]["out"].copy()
+    lanes[0]["store"].triangle_values(rows, "r_square", engine=engine, out=lanes[0]["out16"])
+    narrow_ok = bool((lanes[0]["out16"] == ((w32 & 0xBFFF) | ((w32 >> 16) & 0x4000)).astype(np.uint16)).all())
+    hits_ok = lanes[0]["n_hits"] == int(((w32 & R2_MASK) >= thres_z).sum())
+    lanes[0]["store"].triangle(rows, engine=engine, out=lanes[0]["out"])
 
-    # ---- what plain pinned D2H copies reach here, same run: every rank at once, three streams, 8 MB pieces
+    # ---- what plain pinned D2H copies reach here, same run: every rank at once, three streams, 4 MB pieces (the size of a step's result)
     probe_streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
-    probe_src = [torch.empty(n_pairs, dtype=torch.int32, device=dev) for _ in range(3)]
-    probe_dst = [lane_out for lane_out in (torch.empty(n_pairs, dtype=torch.int32).pin_memory() for _ in range(3))]
-    env.barrier()
-    p0, p1 = env.event(), env.event()
-    p0.record(stream)
-    for s in probe_streams:
-        s.wait_event(p0)
+    probe_src = [torch.empty(n_pairs // 2, dtype=torch.int32, device=dev) for _ in range(3)]
+    probe_dst = [torch.empty(n_pairs // 2, dtype=torch.int32).pin_memory() for _ in range(3)]
     probe_reps = 20
-    for _ in range(probe_reps):
-        for s, a, b in zip(probe_streams, probe_src, probe_dst):
-            with torch.cuda.stream(s):
-                b.copy_(a, non_blocking=True)
-    for s in probe_streams:
-        stream.wait_stream(s)
-    p1.record(stream)
+    for rep in range(2):                         # the first pass is the buffers' and streams' first use: untimed
+        torch.cuda.synchronize()
+        env.barrier()
+        p0 = [env.event() for _ in probe_streams]
+        p1 = [env.event() for _ in probe_streams]
+        for s, a in zip(probe_streams, p0):
+            a.record(s)
+        for _ in range(probe_reps):
+            for s, a, b in zip(probe_streams, probe_src, probe_dst):
+                with torch.cuda.stream(s):
+                    b.copy_(a, non_blocking=True)
+        for s, a in zip(probe_streams, p1):
+            a.record(s)
+        torch.cuda.synchronize()
+        probe_ms = max(float(a.elapsed_time(b)) for a, b in zip(p0, p1))
     env.barrier()
-    probe_ms = float(p0.elapsed_time(p1))
     clocks = sampler.stop()
 
     # ---- max over ranks
-    step_ms, kern_ms, e2e_ms, dom_ms, b2b_ms, probe_ms = env.max_over_ranks([step_ms, kern_ms, e2e_ms, dom_ms, b2b_ms, probe_ms])
+    step_ms, kern_ms, e2e_ms, dom_ms, b2b_ms, probe_ms, p32_ms, hz_ms = env.max_over_ranks(
+        [step_ms, kern_ms, e2e_ms, dom_ms, b2b_ms, probe_ms, form_ms["packed32"], form_ms["hits_z"]])
     world = env.world
     total_pairs = n_pairs * world
     value = total_pairs * args.steps / (step_ms * 1e-3)
@@ -477,7 +499,8 @@ def leg_triangle(env, engine):
     roof["algorithmic_per_launch"] = (f"{n_pairs} pairs x {OPS_PER_PAIR_I8} int8 ops" if used_mma
                                       else f"{n_pairs} pairs x {POPC_PER_PAIR} POPC32")
     h2d = int(planes_np.nbytes + mask_np.nbytes + rows.nbytes)
-    d2h = int(lanes[0]["out"].nbytes)
+    d2h = int(lanes[0]["out16"].nbytes)
+    other = {f: n * n_ctx for f, n in forms}
     out = {
         "value": value, "ms_per_step": step_ms / args.steps, "launches": int(launches), "clocks": clocks, "roofline": roof,
         "parity_selfcheck": same, "used_mma": used_mma, "n_pairs": n_pairs, "depth": depth,
@@ -487,10 +510,16 @@ def leg_triangle(env, engine):
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps,
                 "wall_s": e2e_wall, "contexts": n_ctx, "ms_per_step": e2e_ms / e_steps,
                 "d2h_gbs_per_gpu": d2h * e_each * n_ctx / (e2e_ms * 1e-3) / 1e9,
-                "d2h_probe": {"gbs_per_gpu": 3 * probe_reps * d2h / (probe_ms * 1e-3) / 1e9, "ranks_at_once": world,
-                              "what": "plain cudaMemcpyAsync D2H of 8 MB pinned buffers on three streams, every rank at the same time"},
-                "api": "Store.upload + Store.set_mask + Store.triangle (blocking host-buffer calls), one host thread per context, "
-                       "threads started before the timed region"},
+                "d2h_probe": {"gbs_per_gpu": 3 * probe_reps * probe_dst[0].numel() * 4 / (probe_ms * 1e-3) / 1e9, "ranks_at_once": world,
+                              "what": "plain cudaMemcpyAsync D2H of 4 MB pinned buffers on three streams, every rank at the same time"},
+                "api": "Store.upload(wait=False) + Store.set_mask + Store.triangle_values (ldx_triangle_values: 2 bytes per pair of the measure asked for; "
+                       "blocking host-buffer calls), one host thread per context, threads started before the timed region",
+                "narrow_equals_words": narrow_ok,
+                "packed32": {"value": total_pairs * other["packed32"] / (p32_ms * 1e-3), "unit": "pairs/s", "d2h_bytes_per_step": int(lanes[0]["out"].nbytes),
+                             "steps": other["packed32"], "api": "Store.triangle: 4-byte words with both measures (the round-1 e2e)"},
+                "hits_z": {"value": total_pairs * other["hits_z"] / (hz_ms * 1e-3), "unit": "pairs/s", "steps": other["hits_z"],
+                           "d2h_bytes_per_step": int(lanes[0]["n_hits"]) * 12 + 8, "hits_per_step": int(lanes[0]["n_hits"]), "hits_equal_words": hits_ok,
+                           "api": "Store.triangle_hits: -z 0.8, only the pairs that pass cross PCIe"}},
         "host": {"enqueue_us_per_step": 1e6 * host["enqueue_s"] / args.steps, "resolve_wait_us_per_step": 1e6 * host["resolve_s"] / args.steps,
                  "flush_us_per_step": 1e3 * flush_ms / args.steps},
     }
@@ -958,7 +987,7 @@ def main():
     ap.add_argument("--cpu-pairs-per-core", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline", type=int, default=32, help="device-resident calls in flight per ldx_resolve()")
-    ap.add_argument("--e2e-contexts", type=int, default=3,
+    ap.add_argument("--e2e-contexts", type=int, default=4,
                     help="independent contexts (stream + store + host thread) the end-to-end leg pipelines its steps over")
     ap.add_argument("--e2e-steps", type=int, default=240, help="steps of the end-to-end leg (all contexts together)")
     ap.add_argument("--batch-sets", type=int, default=16, help="variant sets per launch of the batched leg")

@@ -221,6 +221,9 @@ int32_t ldx_vcf_copy_prefixes(const uint8_t *text, int64_t text_bytes, const ldx
 /* Load / read back ready-made planes (host, [n_rows][stride_words] uint64). */
 int32_t ldx_store_upload(ldx_store *store, int64_t first_row, int64_t n_rows, const uint64_t *planes);
 int32_t ldx_store_download(const ldx_store *store, int64_t first_row, int64_t n_rows, uint64_t *planes);
+/* ldx_store_upload without the wait: the copy is enqueued on the context's stream.  A pinned `planes` buffer must stay unchanged
+ * until the next blocking call on this context (ldx_triangle*, ldx_window, ldx_synchronize ...). */
+int32_t ldx_store_upload_async(ldx_store *store, int64_t first_row, int64_t n_rows, const uint64_t *planes);
 /* The on-disk form of a store: what replaces the reference's per-run tabix/pysam access to <chrom>.vcf.gz
  * (prep_intgen_data.py:138-177 builds its cache once; so does this).  One file = 64-byte header
  * {"LDXSTOR1", n_variants, n_hap, stride_words, annotated} + the planes + (if annotated) pos0 | end0 | idnum |
@@ -286,6 +289,21 @@ int32_t ldx_triangle(ldx_store *store, const int64_t *rows, int64_t v, int32_t m
 int32_t ldx_triangle_rows(ldx_store *store, const int64_t *rows, int64_t v, int64_t row_begin,
                           int64_t row_end, int32_t measure, int32_t has_thres, int32_t thres_e4,
                           int32_t engine, uint32_t *packed, int32_t *n11);
+
+/* Narrow outputs of the same call, for callers that want the numbers on the host: every byte crosses PCIe, and the drivers only
+ * ever print ONE measure of a matrix (ld_triangle.py:230).
+ * ldx_triangle_values: 2 bytes per pair for the measure asked for -- bits 0..13 = round(value, 4) * 10^4, LDX_V16_BELOW = below the
+ * threshold (has_thres != 0), LDX_V16_INT0 = the reference prints the int 0 -- in the layout of ldx_triangle_rows.
+ * ldx_triangle_hits: with a threshold (-z), only the pairs that pass it, in matrix order (row > col, indices into rows[]); hits[cap],
+ * *n_hits = pairs found (LDX_ERR_CAPACITY if > cap, with *n_hits = the size needed). */
+#define LDX_V16_VALUE 0x3fffu
+#define LDX_V16_BELOW 0x4000u
+#define LDX_V16_INT0  0x8000u
+typedef struct ldx_pair_hit { int32_t row, col; uint32_t packed; } ldx_pair_hit;
+int32_t ldx_triangle_values(ldx_store *store, const int64_t *rows, int64_t v, int64_t row_begin, int64_t row_end, int32_t measure,
+                            int32_t has_thres, int32_t thres_e4, int32_t engine, uint16_t *values);
+int32_t ldx_triangle_hits(ldx_store *store, const int64_t *rows, int64_t v, int32_t measure, int32_t thres_e4, int32_t engine,
+                          ldx_pair_hit *hits, int64_t cap, int64_t *n_hits);
 
 /* ---------------------------------------------------------------- device-resident variants
  * Same kernels, but outputs stay in HBM (caller-allocated device memory) and the call only

@@ -19,6 +19,8 @@ AREA_TSV, AREA_JSON, AREA_RSIDS = 0, 1, 2
 R2_MASK, R2_INT0, DP_SHIFT, DP_MASK, BELOW_THRES, DP_INT0 = 0x3FFF, 0x8000, 16, 0x3FFF0000, 0x40000000, 0x80000000
 
 HIT_DTYPE = np.dtype([("query", "<i4"), ("row", "<i4"), ("n11", "<i4"), ("packed", "<u4")])
+PAIR_HIT_DTYPE = np.dtype([("row", "<i4"), ("col", "<i4"), ("packed", "<u4")])        # ldx_pair_hit
+V16_VALUE, V16_BELOW, V16_INT0 = 0x3fff, 0x4000, 0x8000                              # ldx_triangle_values
 VCF_ROW_DTYPE = np.dtype([("line_off", "<i8"), ("idnum", "<i8"), ("gt_off", "<i4"), ("id_off", "<i4"), ("ref_off", "<i4"),
                           ("alt_off", "<i4"), ("info_off", "<i4"), ("fmt_off", "<i4"), ("pos", "<i4"), ("ref_len", "<i4"),
                           ("status", "u1"), ("eligible", "u1"), ("multi", "u1"), ("pad", "u1", (5,))])
@@ -69,6 +71,7 @@ SIGNATURES = {
     "ldx_inflate_gz_file": [C.c_char_p, _i32, _P(_vp), _P(_i64), _P(_i32)],
     "ldx_free_host": [_vp],
     "ldx_store_upload": [_vp, _i64, _i64, _vp],
+    "ldx_store_upload_async": [_vp, _i64, _i64, _vp],
     "ldx_store_download": [_vp, _i64, _i64, _vp],
     "ldx_store_save": [_vp, C.c_char_p],
     "ldx_store_load": [_vp, C.c_char_p, _P(_vp)],
@@ -81,6 +84,8 @@ SIGNATURES = {
     "ldx_window": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _P(_i64), _P(_i64)],
     "ldx_triangle": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp],
     "ldx_triangle_dev": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp],
+    "ldx_triangle_values": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp],
+    "ldx_triangle_hits": [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _P(_i64)],
     "ldx_triangle_rows": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp],
     "ldx_triangle_rows_dev": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp],
     "ldx_window_dev": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp],

@@ -553,6 +553,8 @@ extern "C" int32_t ldx_store_destroy(ldx_store *s) {
     cudaFree(s->d_mask_user); cudaFree(s->d_common); cudaFree(s->d_all_slots); cudaFree(s->d_kind); cudaFree(s->d_aux); cudaFree(s->d_gen);
     cudaFree(s->d_row_len); cudaFree(s->d_row_n1);
     cudaFree(s->d_pos0); cudaFree(s->d_end0); cudaFree(s->d_idnum); cudaFree(s->d_eligible);
+    if (s->h_mask_stage) cudaFreeHost(s->h_mask_stage);
+    if (s->mask_staged) cudaEventDestroy(s->mask_staged);
     delete s;
     return LDX_OK;
 }
@@ -675,6 +677,19 @@ extern "C" int32_t ldx_store_upload(ldx_store *s, int64_t first_row, int64_t n_r
     return LDX_OK;
 }
 
+// The same without the wait: the copy is only enqueued (a pageable source is staged by the runtime before the call returns; a
+// pinned one is read by the copy engine later, so it must stay unchanged until the next blocking call on this context).
+extern "C" int32_t ldx_store_upload_async(ldx_store *s, int64_t first_row, int64_t n_rows, const uint64_t *planes) {
+    LDX_TRY(check_rows(s, first_row, n_rows));
+    LDX_REQUIRE(planes || n_rows == 0, "planes is NULL");
+    if (n_rows == 0) return LDX_OK;
+    LDX_CUDA(cudaSetDevice(s->ctx->device));
+    LDX_CUDA(cudaMemcpyAsync(s->d_planes + first_row * s->stride_words, planes,
+                             sizeof(uint64_t) * (size_t)n_rows * s->stride_words, cudaMemcpyHostToDevice, s->ctx->stream));
+    s->mask_set = false;
+    return LDX_OK;
+}
+
 extern "C" int32_t ldx_store_download(const ldx_store *s, int64_t first_row, int64_t n_rows, uint64_t *planes) {
     LDX_TRY(check_rows(s, first_row, n_rows));
     LDX_REQUIRE(planes || n_rows == 0, "planes is NULL");
@@ -692,7 +707,14 @@ extern "C" int32_t ldx_store_set_mask(ldx_store *s, const uint64_t *mask) {
     if (s->classify_dirty) LDX_TRY(store_classify_rows(s));       // rows were packed since: the common pattern and every row's kind
     // the selection as given (general rows use it with their own presence planes), and folded with the store's common
     // presence pattern (all slots unless e.g. the males of chrX are haploid): the mask of the fast paths, N = its popcount
-    std::vector<uint64_t> m(s->stride_words, 0), mu(s->stride_words, 0);
+    // staged in the store's own pinned buffer: the call enqueues two small copies and the count kernel and returns
+    const size_t sw = (size_t)s->stride_words;
+    if (!s->h_mask_stage) {
+        LDX_CUDA(cudaMallocHost((void **)&s->h_mask_stage, 2 * sw * sizeof(uint64_t)));
+        LDX_CUDA(cudaEventCreateWithFlags(&s->mask_staged, cudaEventDisableTiming));
+    } else LDX_CUDA(cudaEventSynchronize(s->mask_staged));         // the previous selection has left the buffer
+    uint64_t *m = s->h_mask_stage, *mu = s->h_mask_stage + sw;
+    std::memset(m, 0, 2 * sw * sizeof(uint64_t));
     int64_t n_sel = 0;
     for (int w = 0; w < s->words; ++w) {
         uint64_t x = mask[w];
@@ -704,9 +726,9 @@ extern "C" int32_t ldx_store_set_mask(ldx_store *s, const uint64_t *mask) {
     if (n_sel == 0) return set_error(LDX_ERR_EMPTY, "division by zero");   // empty sample selection, calc_ld.py:33
     s->n_sel = (int32_t)n_sel;
     LDX_TRY(make_final_ctx(n_sel, &s->fc));
-    LDX_CUDA(cudaMemcpyAsync(s->d_mask, m.data(), sizeof(uint64_t) * s->stride_words, cudaMemcpyHostToDevice, s->ctx->stream));
-    LDX_CUDA(cudaMemcpyAsync(s->d_mask_user, mu.data(), sizeof(uint64_t) * s->stride_words, cudaMemcpyHostToDevice, s->ctx->stream));
-    LDX_CUDA(cudaStreamSynchronize(s->ctx->stream));   // m, mu go out of scope
+    LDX_CUDA(cudaMemcpyAsync(s->d_mask, m, sizeof(uint64_t) * sw, cudaMemcpyHostToDevice, s->ctx->stream));
+    LDX_CUDA(cudaMemcpyAsync(s->d_mask_user, mu, sizeof(uint64_t) * sw, cudaMemcpyHostToDevice, s->ctx->stream));
+    LDX_CUDA(cudaEventRecord(s->mask_staged, s->ctx->stream));
     LDX_TRY(launch_variant_freq(s));
     s->mask_set = true;
     return LDX_OK;
@@ -1321,6 +1343,197 @@ extern "C" int32_t ldx_triangle(ldx_store *s, const int64_t *rows, int64_t v, in
                                 int32_t has_thres, int32_t thres_e4, int32_t engine, uint32_t *packed,
                                 int32_t *n11) {
     return ldx_triangle_rows(s, rows, v, 0, v, measure, has_thres, thres_e4, engine, packed, n11);
+}
+
+// ------------------------------------------------------------------------------------------ narrow outputs of the all-pairs call
+// The drivers only ever print ONE measure of a matrix (ld_triangle.py:230 picks the r_square or the d_prime key); a caller that
+// wants the numbers on the host pays PCIe for every byte, so: 2 bytes per pair for the measure asked for, or -- with a threshold
+// (-z) -- only the pairs that pass it.
+__global__ void narrow_values_kernel(const uint32_t *__restrict__ packed, uint16_t *__restrict__ out, int64_t n, int dprime) {
+    // bits 0..13 the value, bit 14 LDX_V16_BELOW, bit 15 LDX_V16_INT0 (the D' half of the word already has this shape)
+    const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i4 + 8 <= n && (reinterpret_cast<uintptr_t>(packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(packed + i4)), b = __ldcs(reinterpret_cast<const uint4 *>(packed + i4 + 4));
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t h[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) h[k] = dprime ? w[k] >> 16 : (w[k] & 0xbfffu) | ((w[k] >> 16) & 0x4000u);
+        *reinterpret_cast<uint4 *>(out + i4) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+    } else {
+        for (int64_t i = i4; i < n && i < i4 + 8; ++i) {
+            const uint32_t w = packed[i];
+            out[i] = (uint16_t)(dprime ? w >> 16 : (w & 0xbfffu) | ((w >> 16) & 0x4000u));
+        }
+    }
+}
+static inline uint16_t narrow_word(uint32_t w, int measure) {
+    return (uint16_t)(measure == LDX_MEASURE_DPRIME ? w >> 16 : (w & 0xbfffu) | ((w >> 16) & 0x4000u));
+}
+
+extern "C" int32_t ldx_triangle_values(ldx_store *s, const int64_t *rows, int64_t v, int64_t row_begin, int64_t row_end, int32_t measure,
+                                       int32_t has_thres, int32_t thres_e4, int32_t engine, uint16_t *values) {
+    LDX_REQUIRE(s && values, "NULL argument");
+    LDX_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= v, "bad row range");
+    ldx_ctx *ctx = s->ctx;
+    const int64_t n_pairs = (row_end > 1 ? row_end * (row_end - 1) / 2 : 0) - (row_begin > 1 ? row_begin * (row_begin - 1) / 2 : 0);
+    uint32_t *d_pk = nullptr; uint16_t *d_v16 = nullptr;
+    LDX_TRY(settle_before_host_call(ctx));
+    if (n_pairs) {
+        LDX_TRY(arena_get(ctx, S_PACKED, sizeof(uint32_t) * (size_t)n_pairs, (void **)&d_pk));
+        LDX_TRY(arena_get(ctx, S_N11, sizeof(uint16_t) * (size_t)n_pairs, (void **)&d_v16));
+    }
+    LDX_TRY(ldx_triangle_rows_dev(s, rows, v, row_begin, row_end, measure, has_thres, thres_e4, engine, d_pk, nullptr));
+    ctx->pending_q.clear();                // this call settles its own records below
+    if (!n_pairs) return LDX_OK;
+    narrow_values_kernel<<<(unsigned)((n_pairs + 2047) / 2048), 256, 0, ctx->stream>>>(d_pk, d_v16, n_pairs, measure == LDX_MEASURE_DPRIME);
+    ctx->launches++;
+    LDX_CUDA(cudaGetLastError());
+    LDX_CUDA(cudaMemcpyAsync(values, d_v16, sizeof(uint16_t) * (size_t)n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<FixupRec> recs;
+    LDX_TRY(collect_fixups(ctx, recs));   // synchronises
+    for (const FixupRec &r : recs) values[r.out_index & FIX_INDEX_MASK] = narrow_word(settle_word(r, s->fc.n_hap, measure, has_thres, thres_e4), measure);
+    return LDX_OK;
+}
+
+// The pairs that pass the threshold, in matrix order: flags counted per chunk of 4,096 words, one scan over the chunk counts,
+// then every chunk writes its survivors behind those of the chunks before it.
+constexpr int HIT_CHUNK = 4096, HIT_PER_THREAD = HIT_CHUNK / 256;
+__global__ void __launch_bounds__(256) count_passing_kernel(const uint32_t *__restrict__ packed, int64_t n, uint32_t *__restrict__ chunk_count) {
+    const int64_t base = (int64_t)blockIdx.x * HIT_CHUNK;
+    uint32_t c = 0;
+    for (int k = 0; k < HIT_PER_THREAD; ++k) {
+        const int64_t i = base + k * 256 + threadIdx.x;
+        if (i < n) c += !(packed[i] & LDX_BELOW_THRES);
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ uint32_t part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) chunk_count[blockIdx.x] = part[0] + part[1] + part[2] + part[3] + part[4] + part[5] + part[6] + part[7];
+}
+__global__ void __launch_bounds__(1024) scan_chunks_kernel(const uint32_t *__restrict__ chunk_count, int64_t n_chunks, int64_t *__restrict__ chunk_first,
+                                                            int64_t *__restrict__ total_out) {
+    __shared__ int64_t warp_sum[32];
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t b = 0; b < n_chunks; b += 1024) {
+        const int64_t i = b + threadIdx.x;
+        const int64_t x = i < n_chunks ? chunk_count[i] : 0;
+        int64_t incl = x;
+        for (int d = 1; d < 32; d <<= 1) { const int64_t y = __shfl_up_sync(0xffffffffu, incl, d); if ((threadIdx.x & 31) >= d) incl += y; }
+        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int64_t w = warp_sum[threadIdx.x];
+            for (int d = 1; d < 32; d <<= 1) { const int64_t y = __shfl_up_sync(0xffffffffu, w, d); if (threadIdx.x >= d) w += y; }
+            warp_sum[threadIdx.x] = w;                  // inclusive over warps
+        }
+        __syncthreads();
+        const int64_t before = carry + ((threadIdx.x >> 5) ? warp_sum[(threadIdx.x >> 5) - 1] : 0) + incl - x;
+        if (i < n_chunks) chunk_first[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+__global__ void __launch_bounds__(256) write_passing_kernel(const uint32_t *__restrict__ packed, int64_t n, const int64_t *__restrict__ chunk_first,
+                                                             ldx_pair_hit *__restrict__ hits, int64_t cap) {
+    // thread t owns words base + t*16 .. +15, so that the survivors leave in matrix order
+    const int64_t base = (int64_t)blockIdx.x * HIT_CHUNK + (int64_t)threadIdx.x * HIT_PER_THREAD;
+    uint32_t w[HIT_PER_THREAD], flags = 0;
+#pragma unroll
+    for (int k = 0; k < HIT_PER_THREAD; ++k) {
+        w[k] = base + k < n ? packed[base + k] : LDX_BELOW_THRES;
+        flags |= (uint32_t)!(w[k] & LDX_BELOW_THRES) << k;
+    }
+    const uint32_t mine = __popc(flags);
+    uint32_t incl = mine;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if ((threadIdx.x & 31) >= d) incl += y; }
+    __shared__ uint32_t warp_sum[8];
+    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t before = incl - mine;
+    for (int k = 0; k < (int)(threadIdx.x >> 5); ++k) before += warp_sum[k];
+    if (!flags) return;
+    int64_t at = chunk_first[blockIdx.x] + before;
+    // (row, col) of the first word: row = the largest r with r(r-1)/2 <= index
+    int64_t row = (int64_t)((1.0 + sqrt(1.0 + 8.0 * (double)base)) * 0.5);
+    while (row * (row - 1) / 2 > base) --row;
+    while ((row + 1) * row / 2 <= base) ++row;
+    int64_t col = base - row * (row - 1) / 2;
+#pragma unroll
+    for (int k = 0; k < HIT_PER_THREAD; ++k) {
+        if ((flags >> k) & 1u) {
+            if (at < cap) hits[at] = ldx_pair_hit{(int32_t)row, (int32_t)col, w[k]};
+            ++at;
+        }
+        if (++col == row) { ++row; col = 0; }
+    }
+}
+
+extern "C" int32_t ldx_triangle_hits(ldx_store *s, const int64_t *rows, int64_t v, int32_t measure, int32_t thres_e4, int32_t engine,
+                                     ldx_pair_hit *hits, int64_t cap, int64_t *n_hits) {
+    LDX_REQUIRE(s && n_hits && cap >= 0 && (hits || cap == 0), "bad argument");
+    *n_hits = 0;
+    ldx_ctx *ctx = s->ctx;
+    const int64_t n_pairs = v > 1 ? v * (v - 1) / 2 : 0;
+    LDX_TRY(settle_before_host_call(ctx));
+    if (!n_pairs) { const RowList list = {s, rows, v}; int64_t *d_rows, off; return stage_rows(ctx, &list, 1, &d_rows, &off, nullptr); }
+    const int64_t n_chunks = (n_pairs + HIT_CHUNK - 1) / HIT_CHUNK;
+    LDX_REQUIRE(n_chunks < (1ll << 31), "too many pairs for one call");
+    uint32_t *d_pk = nullptr, *d_count = nullptr; int64_t *d_first = nullptr; ldx_pair_hit *d_hits = nullptr;
+    LDX_TRY(arena_get(ctx, S_PACKED, sizeof(uint32_t) * (size_t)n_pairs, (void **)&d_pk));
+    LDX_TRY(arena_get(ctx, S_MISC, (size_t)n_chunks * 4 + 16, (void **)&d_count));
+    LDX_TRY(arena_get(ctx, S_ROWOFF, (size_t)(n_chunks + 1) * 8, (void **)&d_first));       // [n_chunks] = the total
+    LDX_TRY(arena_get(ctx, S_HITS, sizeof(ldx_pair_hit) * (size_t)std::max<int64_t>(cap, 1), (void **)&d_hits));
+    LDX_TRY(ldx_triangle_rows_dev(s, rows, v, 0, v, measure, 1, thres_e4, engine, d_pk, nullptr));
+    ctx->pending_q.clear();
+    count_passing_kernel<<<(unsigned)n_chunks, 256, 0, ctx->stream>>>(d_pk, n_pairs, d_count);
+    scan_chunks_kernel<<<1, 1024, 0, ctx->stream>>>(d_count, n_chunks, d_first, d_first + n_chunks);
+    write_passing_kernel<<<(unsigned)n_chunks, 256, 0, ctx->stream>>>(d_pk, n_pairs, d_first, d_hits, cap);
+    ctx->launches += 3;
+    LDX_CUDA(cudaGetLastError());
+    int64_t total = 0;
+    LDX_CUDA(cudaMemcpyAsync(&total, d_first + n_chunks, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<FixupRec> recs;
+    LDX_TRY(collect_fixups(ctx, recs));   // synchronises
+    const int64_t n_dev = std::min(total, cap);
+    if (n_dev) LDX_CUDA(cudaMemcpy(hits, d_hits, sizeof(ldx_pair_hit) * (size_t)n_dev, cudaMemcpyDeviceToHost));
+    // near-ties settled on the host may enter, leave or change the list
+    auto index_of = [](const ldx_pair_hit &h) { return (int64_t)h.row * (h.row - 1) / 2 + h.col; };
+    std::vector<std::pair<int64_t, uint32_t>> add;
+    std::vector<int64_t> drop;
+    for (const FixupRec &r : recs) {
+        const int64_t idx = (int64_t)(r.out_index & FIX_INDEX_MASK);
+        const uint32_t w = settle_word(r, s->fc.n_hap, measure, 1, thres_e4);
+        ldx_pair_hit *e = std::lower_bound(hits, hits + n_dev, idx, [&](const ldx_pair_hit &h, int64_t i) { return index_of(h) < i; });
+        const bool listed = e != hits + n_dev && index_of(*e) == idx;
+        if (listed && !(w & LDX_BELOW_THRES)) e->packed = w;
+        else if (listed) drop.push_back(idx);
+        else if (!(w & LDX_BELOW_THRES)) add.emplace_back(idx, w);
+    }
+    int64_t n_out = total;
+    if (total > cap) { *n_hits = total + (int64_t)add.size(); return set_error(LDX_ERR_CAPACITY, "hit buffer too small"); }
+    if (!drop.empty() || !add.empty()) {
+        std::vector<ldx_pair_hit> merged;
+        merged.reserve((size_t)n_dev + add.size());
+        std::sort(drop.begin(), drop.end());
+        for (int64_t k = 0; k < n_dev; ++k) if (!std::binary_search(drop.begin(), drop.end(), index_of(hits[k]))) merged.push_back(hits[k]);
+        for (const auto &a : add) {
+            int64_t row = (int64_t)((1.0 + std::sqrt(1.0 + 8.0 * (double)a.first)) * 0.5);
+            while (row * (row - 1) / 2 > a.first) --row;
+            while ((row + 1) * row / 2 <= a.first) ++row;
+            merged.push_back(ldx_pair_hit{(int32_t)row, (int32_t)(a.first - row * (row - 1) / 2), a.second});
+        }
+        std::sort(merged.begin(), merged.end(), [&](const ldx_pair_hit &a, const ldx_pair_hit &b) { return index_of(a) < index_of(b); });
+        n_out = (int64_t)merged.size();
+        if (n_out > cap) { *n_hits = n_out; return set_error(LDX_ERR_CAPACITY, "hit buffer too small"); }
+        std::copy(merged.begin(), merged.end(), hits);
+    }
+    *n_hits = n_out;
+    return LDX_OK;
 }
 
 // The all-pairs call and the table writer in one: the words of matrix rows row_begin..row_end-1 go to the ctx's scratch,

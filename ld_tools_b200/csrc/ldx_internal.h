@@ -104,6 +104,8 @@ struct ldx_store {
     bool classify_dirty = false;          // rows were (re)packed since kind[] / the common pattern were last derived
     bool common_loaded = false;           // the common pattern came with a store file / a subset: do not re-derive it
     std::vector<uint64_t> h_common;       // host copy of d_common (ldx_store_set_mask folds it into the selection)
+    uint64_t *h_mask_stage = nullptr;     // pinned [2][stride_words]: the masks on their way to the device (set_mask does not wait for them)
+    cudaEvent_t mask_staged = nullptr;    // recorded behind the copies out of h_mask_stage
     int32_t *d_row_len = nullptr;         // [n_variants] K2: len of the variant's own genotype list under the selection (calc_ld.py:31)
     int32_t *d_row_n1 = nullptr;          // [n_variants] K2: its alt count under the selection (the true one, also for general rows)
     // TMA tensor map of the planes ([n_variants][stride_words * 2] uint32, box 8 x 128), encoded on first use by the

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (BELOW_THRES, DP_INT0, DP_MASK, DP_SHIFT, ENGINE_AUTO, ENGINE_MMA, ENGINE_POPC,  # noqa: F401
-                   HIT_DTYPE, LD_RESULT_DTYPE, MEASURE_DPRIME, MEASURE_R2, R2_INT0, R2_MASK, TRIANGLE_SET_DTYPE, VCF_ROW_DTYPE,
+                   HIT_DTYPE, PAIR_HIT_DTYPE, LD_RESULT_DTYPE, MEASURE_DPRIME, MEASURE_R2, R2_INT0, R2_MASK, TRIANGLE_SET_DTYPE, VCF_ROW_DTYPE,
                    LdxError, check, ptr)
 
 MEASURES = {"r_square": MEASURE_R2, "d_prime": MEASURE_DPRIME}   # the CLI's -l choices
@@ -319,9 +319,11 @@ class Store:
                                           int(row_pitch), int(n_samples), ptr(status)))
         return status
 
-    def upload(self, first_row, planes):
+    def upload(self, first_row, planes, wait=True):
+        """wait=False: only enqueue the copy (ldx_store_upload_async); a pinned `planes` must stay unchanged until the next blocking call."""
         planes = np.ascontiguousarray(planes, dtype="<u8")
-        check(self._lib.ldx_store_upload(self._h, int(first_row), planes.shape[0], ptr(planes)))
+        fn = self._lib.ldx_store_upload if wait else self._lib.ldx_store_upload_async
+        check(fn(self._h, int(first_row), planes.shape[0], ptr(planes)))
 
     @classmethod
     def ingest_vcf(cls, ctx, text, n_samples, rows_cap=None):
@@ -492,6 +494,32 @@ class Store:
                                           _measure_code(measure), int(thres_e4_ is not None), int(thres_e4_ or 0),
                                           int(engine), ptr(packed), ptr(n11)))
         return packed, n11
+
+    def triangle_values(self, rows, measure="r_square", thres_e4_=None, engine=ENGINE_AUTO, row_begin=0, row_end=None, out=None):
+        """The same triangle as 2 bytes per pair for ONE measure (ldx_triangle_values): value * 10^4 in bits 0..13, V16_BELOW, V16_INT0."""
+        rows = _i64(rows)
+        row_end = rows.shape[0] if row_end is None else row_end
+        n_pairs = tri_index(row_end, 0) - tri_index(row_begin, 0)
+        out = np.zeros(n_pairs, dtype=np.uint16) if out is None else out
+        assert out.dtype == np.uint16 and out.shape[0] == n_pairs and out.flags.c_contiguous
+        check(self._lib.ldx_triangle_values(self._h, ptr(rows), rows.shape[0], int(row_begin), int(row_end), _measure_code(measure),
+                                            int(thres_e4_ is not None), int(thres_e4_ or 0), int(engine), ptr(out)))
+        return out
+
+    def triangle_hits(self, rows, measure, thres_e4_, engine=ENGINE_AUTO, cap=None, out=None):
+        """Only the pairs whose rounded measure passes the threshold (-z), in matrix order (ldx_triangle_hits) -> PAIR_HIT_DTYPE array."""
+        rows = _i64(rows)
+        cap = (1 << 16) if cap is None and out is None else (out.shape[0] if out is not None else cap)
+        while True:
+            hits = np.zeros(max(cap, 1), dtype=PAIR_HIT_DTYPE) if out is None else out
+            n = C.c_int64()
+            rc = self._lib.ldx_triangle_hits(self._h, ptr(rows), rows.shape[0], _measure_code(measure), int(thres_e4_), int(engine),
+                                             ptr(hits), int(cap), C.byref(n))
+            if rc == _lib.ERR_CAPACITY and out is None:
+                cap = int(n.value) + 1024
+                continue
+            check(rc)
+            return hits[:n.value]
 
     def triangle_table(self, rows, prefixes, measure="r_square", thres_e4_=None, engine=ENGINE_AUTO, row_begin=0,
                        row_end=None, out=None):

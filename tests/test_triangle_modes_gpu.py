@@ -177,3 +177,65 @@ def test_same_rows_for_a_smaller_store_are_checked_again(ctx):
     assert ok.shape[0] == 400 * 399 // 2
     big.close()
     small.close()
+
+
+# ------------------------------------------------------------------ narrow host outputs (ldx_triangle_values / ldx_triangle_hits)
+def _narrow(words, measure):
+    words = words.astype(np.uint32)
+    if measure == "d_prime":
+        return (words >> 16).astype(np.uint16)
+    return ((words & 0xBFFF) | ((words >> 16) & 0x4000)).astype(np.uint16)
+
+
+@pytest.mark.parametrize("n_var,n_hap", [(700, 198), (2000, 5008), (131, 70)])
+def test_two_byte_values_and_threshold_hit_lists_equal_the_packed_triangle(ctx, n_var, n_hap):
+    """2 bytes per pair of one measure, and only the pairs above a threshold, are the packed triangle narrowed / filtered --
+    with small haplotype counts (198) the near-ties settled on the host enter, leave and change both outputs."""
+    from ld_tools_b200._lib import BELOW_THRES, PAIR_HIT_DTYPE, V16_BELOW, V16_INT0, V16_VALUE
+    from ld_tools_b200.engine import ENGINE_AUTO, ENGINE_MMA, ENGINE_POPC, measure_value, threshold_e4, tri_index
+    if n_hap == 198:                                  # founder haplotypes: few distinct count tables, exact rounding ties among them
+        from ld_tools_b200 import Store
+        from ld_tools_b200.synth import synth_haplotypes
+        planes = ld_oracle.pack_bits(synth_haplotypes(n_var, n_hap, seed=12))
+        st = Store.from_planes(ctx, planes, n_hap)
+        st.select_all()
+    else:
+        st, planes, mask = mixed_frequency_store(ctx, n_var, n_hap, seed=n_var)
+    rng = np.random.default_rng(n_var)
+    rows = np.sort(rng.permutation(n_var)[: n_var - 3])
+    v = len(rows)
+    for measure, thres, engine in [("r_square", None, ENGINE_AUTO), ("d_prime", None, ENGINE_MMA), ("r_square", 0.2, ENGINE_MMA),
+                                   ("d_prime", 0.9, ENGINE_POPC), ("r_square", 0.0001, ENGINE_AUTO)]:
+        t = None if thres is None else threshold_e4(thres)
+        packed, _ = st.triangle(rows, measure, t, engine=engine)
+        vals = st.triangle_values(rows, measure, t, engine=engine)
+        assert vals.dtype == np.uint16 and (vals == _narrow(packed, measure)).all()
+        # the decoded number a caller prints is the same from either form
+        for i in rng.integers(0, len(vals), 50):
+            w16 = int(vals[i])
+            got = 0 if w16 & V16_INT0 else (w16 & V16_VALUE) / 10000
+            assert got == measure_value(int(packed[i]), measure) and bool(w16 & V16_BELOW) == bool(int(packed[i]) & BELOW_THRES)
+        if v > 256:                                   # a row range of the same triangle
+            part = st.triangle_values(rows, measure, t, engine=engine, row_begin=128, row_end=v - 5)
+            assert (part == vals[tri_index(128, 0):tri_index(v - 5, 0)]).all()
+        if t is not None:
+            hits = st.triangle_hits(rows, measure, t, engine=engine)
+            keep = np.flatnonzero((packed & BELOW_THRES) == 0)
+            r = np.floor((1 + np.sqrt(1 + 8.0 * keep)) / 2).astype(np.int64)
+            r -= (r * (r - 1) // 2 > keep)
+            r += ((r + 1) * r // 2 <= keep)
+            want = np.zeros(len(keep), dtype=PAIR_HIT_DTYPE)
+            want["row"], want["col"], want["packed"] = r, keep - r * (r - 1) // 2, packed[keep]
+            assert len(hits) == len(want) and hits.tobytes() == want.tobytes(), (measure, thres, len(hits), len(want))
+            assert len(want) > 0
+            small = np.zeros(max(len(want) - 1, 1), dtype=PAIR_HIT_DTYPE)        # a buffer one entry short says how many there are
+            with pytest.raises(Exception):
+                st.triangle_hits(rows, measure, t, engine=engine, out=small)
+    # near-ties did occur in the small-N case (otherwise the host-side patching above was not exercised)
+    if n_hap == 198:
+        import torch
+        out = torch.zeros(v * (v - 1) // 2, dtype=torch.int32, device="cuda:0")
+        st.triangle_dev(rows, out.data_ptr(), thres_e4_=threshold_e4(0.2))
+        assert ctx.resolve() > 0
+    assert len(st.triangle_values(rows[:1])) == 0 and len(st.triangle_hits(rows[:1], "r_square", 5000)) == 0
+    st.close()

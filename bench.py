@@ -794,11 +794,11 @@ def leg_area(env, subset=True, steps=5, warmup=3):
     pps = scanned / kern_s
     roof = {"bound": "int-alu/popc", "achieved": pps / 1e9, "peak": popc_peak_pairs / 1e9, "unit": "Gpairs/s",
             "frac": pps / popc_peak_pairs, "peak_source": f"148 SM x 16 POPC32/clk x {env.peaks['sm_max_mhz']:.0f} MHz / {popc32_per_pair} POPC32 per pair "
-            "(SURVEY 8d; the carry-save adder tree moves two thirds of the counting to the 64-lane ALU pipe, so frac may exceed 1)",
-            "kernel": "window_mq_kernel", "kernel_ms": kern_s * 1e3, "kernel_launches_timed": int(dom_n),
+            "(SURVEY 8d; the carry-save adders move half (128-byte rows) to two thirds (640-byte rows) of the counting to the 64-lane ALU pipe, so frac may exceed 1)",
+            "kernel": "window_rows1_kernel (+ mq_extend_kernel, inside the timed pair)" if row_bytes == 128 else "window_mq_kernel", "kernel_ms": kern_s * 1e3, "kernel_launches_timed": int(dom_n),
             "hbm_frac_if_every_pair_read_its_row": scanned * row_bytes / kern_s / 1e9 / env.peaks["hbm_gbs"],
             "hbm_frac_one_pass_over_the_store": st.n_variants * row_bytes / kern_s / 1e9 / env.peaks["hbm_gbs"],
-            "traffic": ncu_traffic(["r02_ncu_full_window_mq_subset_configs2.txt"] if subset else ["r01_ncu_full_window_mq_configs2.txt"]),
+            "traffic": ncu_traffic(["r02_ncu_full_window_rows1_configs2.txt"] if subset else ["r01_ncu_full_window_mq_configs2.txt"]),
             "algorithmic_per_launch": f"{scanned} pairs x {popc32_per_pair} POPC32 ({row_bytes}-byte rows)"}
     out = {"workload": AREA_WORKLOAD, "store": f"{'subset store' if subset else 'mask on the full store'}: {st.n_hap} haplotype columns, {row_bytes}-byte rows, "
            f"{st.n_variants * row_bytes / 1e6:.0f} MB", "value": scanned * env.world * steps / (step_ms * 1e-3), "unit": "pairs/s",

@@ -1115,13 +1115,14 @@ extern "C" int32_t ldx_window_dev(ldx_store *s, const int64_t *q_row, const int6
         for (size_t k = 0; k < order.size(); ++k) { const int32_t q = order[k]; sorted[k] = WindowMqQuery{q, q_row[q], lo[q], hi[q]}; }
         uint8_t *blk;
         const size_t blk_bytes = blocks.size() * sizeof(WindowMqBlock), srt_bytes = sorted.size() * sizeof(WindowMqQuery);
-        LDX_TRY(arena_get(ctx, S_IB, blk_bytes + srt_bytes + 64, (void **)&blk));
+        const size_t ext_off = (blk_bytes + srt_bytes + 64 + 15) & ~(size_t)15;
+        LDX_TRY(arena_get(ctx, S_IB, ext_off + sorted.size() * WINDOW_MQ_EXT_BYTES, (void **)&blk));
         LDX_CUDA(cudaMemcpyAsync(blk, blocks.data(), blk_bytes, cudaMemcpyHostToDevice, ctx->stream));
         LDX_CUDA(cudaMemcpyAsync(blk + blk_bytes, sorted.data(), srt_bytes, cudaMemcpyHostToDevice, ctx->stream));
         LDX_CUDA(cudaStreamSynchronize(ctx->stream));   // blocks / sorted are locals
         LDX_TRY(launch_window_mq(s, arr[0], arr[1], arr[2], (const int32_t *)arr[4], (const int32_t *)arr[5], nq, blk, (int64_t)blocks.size(),
-                                 blk + blk_bytes, reinterpret_cast<unsigned int *>(blk + blk_bytes + srt_bytes), measure, thres_e4, dev_hits, cap,
-                                 reinterpret_cast<unsigned long long *>(dev_n_hits)));
+                                 blk + blk_bytes, (int64_t)sorted.size(), blk + ext_off, reinterpret_cast<unsigned int *>(blk + blk_bytes + srt_bytes),
+                                 measure, thres_e4, dev_hits, cap, reinterpret_cast<unsigned long long *>(dev_n_hits)));
     } else
     LDX_TRY(launch_window(s, arr[0], arr[1], arr[2], (const int32_t *)arr[4], (const int32_t *)arr[5], arr[3], nq,
                           n_chunks, measure, thres_e4, dev_hits, cap, reinterpret_cast<unsigned long long *>(dev_n_hits)));

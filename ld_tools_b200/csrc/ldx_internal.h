@@ -196,7 +196,8 @@ struct WindowMqBlock { int64_t base, first_item; int32_t a, b; };   // = ldx::Mq
 struct WindowMqQuery { int64_t q, qrow, lo, hi; };                  // = ldx::MqQuery
 bool window_mq_supported(const ldx_store *s);
 int launch_window_mq(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, const int64_t *d_hi, const int32_t *d_ws, const int32_t *d_we,
-                     int64_t nq, const void *d_blocks, int64_t n_blocks, const void *d_sorted, unsigned int *d_next, int measure, int thres_e4,
-                     ldx_hit *d_hits, int64_t cap, unsigned long long *d_counters);
+                     int64_t nq, const void *d_blocks, int64_t n_blocks, const void *d_sorted, int64_t n_sorted, void *d_ext, unsigned int *d_next,
+                     int measure, int thres_e4, ldx_hit *d_hits, int64_t cap, unsigned long long *d_counters);
+constexpr size_t WINDOW_MQ_EXT_BYTES = 48;   // per sorted query: scratch for the row-per-thread kernel's records (ldx_window.cu: MqQueryX)
 
 }  // namespace ldx

@@ -72,28 +72,26 @@ __device__ __forceinline__ bool screen_below(int32_t n11, int32_t N, int32_t n1a
 // The per-row tail of both window kernels: thread `tid` owns store row `row` of query q (row >= the query's lo by
 // construction; rows at or beyond `hi` are not candidates).  Filters, single-precision screen, exact finalisation, rounded
 // threshold, and the warp-aggregated append of the kept pair.  Every thread of the warp must call it.
-__device__ __forceinline__ void row_epilogue(const WindowArgs &A, int64_t q, int64_t qrow, int64_t row, int64_t hi, int n11_in, int tid,
-                                             unsigned long long &scanned) {
+// The tail of a candidate pair that passed the filters (`scan`): general route or screen + exact finalisation, the rounded
+// threshold, and the warp-aggregated append.  n1q / n1r: VarFreq.n1 of the query and of the row.  Every thread of the warp calls it.
+template <typename Counter>
+__device__ __forceinline__ void pair_tail(const WindowArgs &A, int64_t q, int64_t qrow, int64_t row, bool scan, int n11_in, int32_t n1q, int32_t n1r,
+                                          int tid, Counter &scanned) {
     int n11 = n11_in;
     bool pass = false;
     uint32_t packed = 0;
     GenCounts gc;
     gc.n_pair = 0;                                                      // != 0: the pair took the general route
-    if (row < hi) {
-        const int32_t ws = A.win_start[q], we = A.win_end[q];
-        const bool scan = A.pos0[row] < we && A.end0[row] > ws      // fetch overlap, ld_area.py:215-217
-                          && A.eligible[row]                           // rs\d+$ and not MULTI_ALLELIC, :223-224
-                          && A.idnum[row] != A.idnum[qrow];            // :222
-        if (scan) ++scanned;
-        if (scan && A.gen && (A.freq[qrow].n1 | A.freq[row].n1) < 0) {          // a variant of the general route: rare, one thread does it all
-            gc = general_pair_counts(*A.gen, qrow, A.freq[qrow].n1, row, A.freq[row].n1);     // var_1 = query, var_2 = row (:242)
+    if (scan) {
+        ++scanned;
+        if (A.gen && (n1q | n1r) < 0) {                                 // a variant of the general route: rare, one thread does it all
+            gc = general_pair_counts(*A.gen, qrow, n1q, row, n1r);      // var_1 = query, var_2 = row (:242)
             packed = finalise_general(gc).packed;
             n11 = gc.n11;
             int32_t m = measure_e4(packed, A.measure);
             if (A.measure == LDX_MEASURE_R2 && (packed & LDX_R2_NEARTIE)) ++m;
             pass = m >= A.thres_e4;
-        } else
-        if (scan && !(A.screen_t > 0.0f && screen_below(n11, A.n_sel, A.freq[qrow].n1, A.freq[row].n1, A.measure, A.screen_t, A.screen_g))) {
+        } else if (!(A.screen_t > 0.0f && screen_below(n11, A.n_sel, n1q, n1r, A.measure, A.screen_t, A.screen_g))) {
             const VarFreq fa = A.freq[qrow], fb = A.freq[row];         // var_1 = query, var_2 = row (:242)
             const PairFinal f = finalise_pair(n11, fa, fb, A.fc);
             packed = f.packed;
@@ -116,11 +114,25 @@ __device__ __forceinline__ void row_epilogue(const WindowArgs &A, int64_t q, int
                     make_uint4((uint32_t)q, (uint32_t)row, (uint32_t)n11, packed);
                 if (packed & LDX_R2_NEARTIE) {
                     if (gc.n_pair != 0) fixup_append_general(A.fix, slot, gc, packed);
-                    else fixup_append(A.fix, slot, n11, A.freq[qrow].n1, A.freq[row].n1, packed);
+                    else fixup_append(A.fix, slot, n11, n1q, n1r, packed);
                 }
             }
         }
     }
+}
+
+__device__ __forceinline__ void row_epilogue(const WindowArgs &A, int64_t q, int64_t qrow, int64_t row, int64_t hi, int n11, int tid,
+                                             unsigned long long &scanned) {
+    bool scan = false;
+    int32_t n1q = 0, n1r = 0;
+    if (row < hi) {
+        const int32_t ws = A.win_start[q], we = A.win_end[q];
+        scan = A.pos0[row] < we && A.end0[row] > ws                    // fetch overlap, ld_area.py:215-217
+               && A.eligible[row]                                      // rs\d+$ and not MULTI_ALLELIC, :223-224
+               && A.idnum[row] != A.idnum[qrow];                       // :222
+        if (scan) { n1q = A.freq[qrow].n1; n1r = A.freq[row].n1; }
+    }
+    pair_tail(A, q, qrow, row, scan, n11, n1q, n1r, tid, scanned);
 }
 
 // 8 x 8 transpose-reduce over the lanes of a group: in, cnt[i] = this lane's partial count of row i; out, the total of row
@@ -302,6 +314,124 @@ window_mq_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int64_t
     if ((tid & 31) == 0 && scanned) atomicAdd(A.counters + 1, scanned);
 }
 
+// ------------------------------------------------------------------------------------------ 128-byte rows: one thread per row
+// A subset store (ldx_store_subset: e.g. the 1006 EUR haplotypes of configs[2]) has rows of 16 words.  With 8 lanes per row
+// the kernel above spends more instructions on the 8 x 8 transposes, the per-(row, query) filter loads and the re-loading of
+// the block's rows for every group of queries than on the 4 AND + POPC a lane has to do.  Here a thread OWNS a row for the
+// whole block: its 128 bytes and its filter columns (pos0, end0, eligible, idnum, n1) are loaded into registers once, every
+// query that meets the block is then one pass over registers against the query's plane in shared memory (broadcast reads), and
+// the count needs no reduction across lanes.  The popcount is carry-save per 8 words (4 POPC + 8 LOP3 instead of 8 POPC: POPC
+// issues at a quarter of the LOP3 rate), which balances the two pipes.  Per-query columns come in one 48-byte record each
+// (MqQueryX, filled by a small kernel before), so nothing in the inner loop waits on global memory.
+constexpr int RQ = 8;                                      // queries per group (their planes double-buffered in shared memory)
+struct MqQueryX { int64_t idnum; int32_t q, qrow, lo, hi, ws, we, n1, pad[3]; };
+static_assert(sizeof(MqQueryX) == WINDOW_MQ_EXT_BYTES, "three 16-byte loads");
+
+__global__ void mq_extend_kernel(const WindowArgs A, const MqQuery *__restrict__ sorted, int64_t n, MqQueryX *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const MqQuery m = sorted[i];
+    MqQueryX x;
+    x.idnum = A.idnum[m.qrow]; x.q = (int32_t)m.q; x.qrow = (int32_t)m.qrow; x.lo = (int32_t)m.lo; x.hi = (int32_t)m.hi;
+    x.ws = A.win_start[m.q]; x.we = A.win_end[m.q]; x.n1 = A.freq[m.qrow].n1; x.pad[0] = x.pad[1] = x.pad[2] = 0;
+    out[i] = x;
+}
+
+// popcount(x & q) over 8 words with 4 POPC: three carry-save adders leave two words of weight 1 and three of weight 2, a fourth
+// turns those into one of weight 2 and one of weight 4
+__device__ __forceinline__ int popc_and_8(const uint4 &xa, const uint4 &xb, const uint4 &qa, const uint4 &qb) {
+    uint32_t h0, l0, h1, l1, h2, l2, f, t;
+    csa(h0, l0, xa.x & qa.x, xa.y & qa.y, xa.z & qa.z);
+    csa(h1, l1, xa.w & qa.w, xb.x & qb.x, xb.y & qb.y);
+    csa(h2, l2, l0, l1, xb.z & qb.z);
+    csa(f, t, h0, h1, h2);
+    return __popc(l2) + __popc(xb.w & qb.w) + 2 * __popc(t) + 4 * __popc(f);
+}
+
+__global__ void __launch_bounds__(WIN_THREADS, 2)
+window_rows1_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int64_t n_blocks, const MqQueryX *__restrict__ ext,
+                    unsigned int *__restrict__ next_block, int64_t n_rows) {
+    __shared__ uint4 qs[2][RQ][8];
+    __shared__ uint4 s_rec[2][RQ][3];                        // MqQueryX records
+    __shared__ unsigned int s_j;
+    const int tid = threadIdx.x, k_pl = tid >> 3, g_pl = tid & 7;      // loader threads (tid < RQ * 8): granule g_pl of query k_pl
+    constexpr int PL = RQ * 8;
+    unsigned long long scanned_total = 0;
+    for (;;) {
+        if (tid == 0) s_j = atomicAdd(next_block, 1u);
+        __syncthreads();
+        const unsigned int j = s_j;
+        if (j >= n_blocks) break;
+        const MqBlock blk = blocks[j];
+        const int n_groups = (blk.b - blk.a + RQ - 1) / RQ;
+        // ---- this thread's row and its filter columns, once per block
+        const int64_t row = blk.base + tid;
+        const bool in_store = row < n_rows;
+        const int64_t rc = in_store ? row : n_rows - 1;
+        uint4 x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = ldg_u4(A.planes + rc * 8 + i);
+        const int32_t pos0 = A.pos0[rc], end0 = A.end0[rc], n1r = A.freq[rc].n1, row32 = (int32_t)row;
+        const int64_t idn = A.idnum[rc];
+        const bool elig = in_store && A.eligible[rc];
+        // ---- the block's first group of queries, synchronously; the store row of the second group's plane granule for later
+        int32_t qrow_next = 0;
+        if (tid < PL) {
+            const int32_t qrow0 = ext[min(blk.a + k_pl, blk.b - 1)].qrow;
+            const uint4 y = ldg_u4(A.planes + (int64_t)qrow0 * 8 + g_pl), m = __ldg(A.mask + g_pl);
+            qs[0][k_pl][g_pl] = make_uint4(y.x & m.x, y.y & m.y, y.z & m.z, y.w & m.w);
+            qrow_next = ext[min(blk.a + RQ + k_pl, blk.b - 1)].qrow;
+        }
+        if (tid < RQ * 3) s_rec[0][tid / 3][tid % 3] = __ldg(reinterpret_cast<const uint4 *>(ext + min(blk.a + tid / 3, blk.b - 1)) + tid % 3);
+        __syncthreads();
+        unsigned int scanned = 0;
+        for (int g = 0; g < n_groups; ++g) {
+            const int cur = g & 1, q0 = blk.a + g * RQ, nq = min(RQ, blk.b - q0);
+            // ---- the NEXT group's plane granules and records, requested now and parked in shared memory after this group's work
+            const bool more = g + 1 < n_groups;
+            uint4 nx = make_uint4(0, 0, 0, 0), mk = nx, rec_next = nx;
+            int32_t qrow_next2 = 0;
+            if (more && tid < PL) {
+                nx = ldg_u4(A.planes + (int64_t)qrow_next * 8 + g_pl); mk = __ldg(A.mask + g_pl);
+                qrow_next2 = ext[min(q0 + 2 * RQ + k_pl, blk.b - 1)].qrow;
+            }
+            if (more && tid < RQ * 3) rec_next = __ldg(reinterpret_cast<const uint4 *>(ext + min(q0 + RQ + tid / 3, blk.b - 1)) + tid % 3);
+            // ---- this group's queries against the row in registers, two at a time (independent chains for the scheduler)
+            for (int k = 0; k < nq; k += 2) {                          // nq is block-uniform
+                const bool two = k + 1 < nq;
+                const int k1 = two ? k + 1 : k;
+                int n11a = 0, n11b = 0;
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    n11a += popc_and_8(x[2 * h], x[2 * h + 1], qs[cur][k][2 * h], qs[cur][k][2 * h + 1]);
+                    n11b += popc_and_8(x[2 * h], x[2 * h + 1], qs[cur][k1][2 * h], qs[cur][k1][2 * h + 1]);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (u == 1 && !two) break;
+                    const int kk = u ? k1 : k;
+                    const uint4 r0 = s_rec[cur][kk][0], r1 = s_rec[cur][kk][1];        // {idnum lo, hi, q, qrow} {lo, hi, ws, we}
+                    const int32_t n1q = (int32_t)s_rec[cur][kk][2].x;
+                    const int64_t idq = (int64_t)(((unsigned long long)r0.y << 32) | r0.x);
+                    const bool scan = row32 >= (int32_t)r1.x && row32 < (int32_t)r1.y       // the query's candidate range
+                                      && pos0 < (int32_t)r1.w && end0 > (int32_t)r1.z       // fetch overlap, ld_area.py:215-217
+                                      && elig && idn != idq;                                // :223-224, :222
+                    pair_tail(A, (int64_t)(int32_t)r0.z, (int64_t)(int32_t)r0.w, row, scan, u ? n11b : n11a, n1q, n1r, tid, scanned);
+                }
+            }
+            if (more) {
+                if (tid < PL) qs[cur ^ 1][k_pl][g_pl] = make_uint4(nx.x & mk.x, nx.y & mk.y, nx.z & mk.z, nx.w & mk.w);
+                if (tid < RQ * 3) s_rec[cur ^ 1][tid / 3][tid % 3] = rec_next;
+            }
+            qrow_next = qrow_next2;
+            __syncthreads();
+        }
+        scanned_total += scanned;
+    }
+    for (int o = 16; o; o >>= 1) scanned_total += __shfl_xor_sync(0xffffffffu, scanned_total, o);
+    if ((tid & 31) == 0 && scanned_total) atomicAdd(A.counters + 1, scanned_total);
+}
+
 template <int NG>   // NG = 16-byte granules per lane per row; 0 = runtime loop
 __global__ void __launch_bounds__(WIN_THREADS, 3)
 window_kernel(const WindowArgs A) {
@@ -436,14 +566,33 @@ bool window_mq_supported(const ldx_store *s) { const int ng = s->stride_words / 
 // d_blocks: MqBlock records, d_sorted: MqQuery records in sorted order (WindowMqBlock / WindowMqQuery on the host side);
 // d_next: one word of device scratch for the dynamic block counter
 int launch_window_mq(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, const int64_t *d_hi, const int32_t *d_ws, const int32_t *d_we,
-                     int64_t nq, const void *d_blocks, int64_t n_blocks, const void *d_sorted, unsigned int *d_next, int measure, int thres_e4,
-                     ldx_hit *d_hits, int64_t cap, unsigned long long *d_counters) {
+                     int64_t nq, const void *d_blocks, int64_t n_blocks, const void *d_sorted, int64_t n_sorted, void *d_ext, unsigned int *d_next,
+                     int measure, int thres_e4, ldx_hit *d_hits, int64_t cap, unsigned long long *d_counters) {
     if (n_blocks <= 0) return LDX_OK;
     static_assert(sizeof(MqBlock) == sizeof(WindowMqBlock) && sizeof(MqQuery) == sizeof(WindowMqQuery), "host and device work-list records");
     WindowArgs A;
     fill_window_args(s, A, d_qrow, d_lo, d_hi, d_ws, d_we, nq, measure, thres_e4, d_hits, cap, d_counters);
     const MqBlock *blocks = reinterpret_cast<const MqBlock *>(d_blocks);
     const MqQuery *sorted = reinterpret_cast<const MqQuery *>(d_sorted);
+    static const bool rows1_off = getenv("LDX_WINDOW_ROWS1") && atoi(getenv("LDX_WINDOW_ROWS1")) == 0;
+    if (A.stride_u4 == 8 && d_ext && n_sorted > 0 && s->n_variants < (1ll << 31) && !rows1_off) {     // 128-byte rows: a thread per row
+        ldx_ctx *ctx = s->ctx;
+        MqQueryX *ext = reinterpret_cast<MqQueryX *>(d_ext);
+        static int per_sm = 0;
+        if (!per_sm) {
+            LDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, window_rows1_kernel, WIN_THREADS, 0));
+            if (per_sm < 1) per_sm = 1;
+        }
+        const int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count * per_sm, n_blocks);
+        LDX_CUDA(cudaMemsetAsync(d_next, 0, sizeof(unsigned int), ctx->stream));
+        timing_begin(ctx);
+        mq_extend_kernel<<<(unsigned)((n_sorted + 255) / 256), 256, 0, ctx->stream>>>(A, sorted, n_sorted, ext);
+        window_rows1_kernel<<<(int)grid, WIN_THREADS, 0, ctx->stream>>>(A, blocks, n_blocks, ext, d_next, s->n_variants);
+        timing_end(ctx);
+        ctx->launches += 2;
+        LDX_LAUNCHED(ctx, "window_rows1_kernel");
+        return LDX_OK;
+    }
     switch (A.stride_u4 / 8) {
         case 1: return launch_window_mq_ng<1>(s->ctx, A, blocks, n_blocks, sorted, d_next, s->n_variants);
         case 2: return launch_window_mq_ng<2>(s->ctx, A, blocks, n_blocks, sorted, d_next, s->n_variants);

@@ -402,6 +402,54 @@ def test_window_full_size_properties(ctx):
     st.close()
 
 
+@pytest.mark.parametrize("measure,thres", [("r_square", 0.05), ("d_prime", 0.95), ("r_square", 0.0), ("d_prime", 0.3)])
+def test_window_thread_per_row_kernel_equals_the_single_query_kernel(ctx, measure, thres):
+    """128-byte rows (a subset store, or any store of at most 1024 haplotypes) take the row-per-thread kernel
+    (window_rows1_kernel) when several queries overlap: same hits, same scanned count as the one-query-per-pass kernel and as
+    the masked full-width store -- with records that fail the filters (ineligible IDs, multi-allelic, the query's own ID at
+    another row, long REF alleles at the window edge), windows clipped at both ends of the store and query groups that do
+    not fill a group of 8."""
+    from ld_tools_b200._lib import TUNE_WINDOW_MQ
+    from ld_tools_b200.engine import threshold_e4
+    n_var, n_hap = 5000, 5008
+    st, planes, mask, pos0, end0, idnum, elig = annotated_store(ctx, n_var, n_hap, seed=71)
+    idnum = idnum.copy()
+    idnum[100:140:7] = idnum[120]                       # the query's ID again at other rows: skipped (ld_area.py:222)
+    st.set_annotations(pos0, end0, idnum, elig)
+    rng = np.random.default_rng(3)
+    sel = np.sort(rng.choice(n_hap, 1000, replace=False))
+    st.select_haplotypes(sel)
+    sub = st.subset(sel)
+    assert sub.stride_words == 16
+    q_rows = np.unique(np.concatenate([[0, 1, 120, n_var - 1], rng.choice(n_var, 61, replace=False)])).astype(np.int64)
+    pos = pos0.astype(np.int64) + 1
+    flank = 9000
+    max_len = int((end0 - pos0).max())
+    lo = np.searchsorted(pos0, np.maximum(pos[q_rows] - flank, 0) - max_len, side="left").astype(np.int64)
+    hi = np.searchsorted(pos0, pos[q_rows] + flank, side="left").astype(np.int64)
+    ws, we = np.maximum(pos[q_rows] - flank, 0).astype(np.int32), (pos[q_rows] + flank).astype(np.int32)
+    t = threshold_e4(thres)
+    want, scanned_want = st.window(q_rows, lo, hi, ws, we, measure, t)                  # full-width rows under the mask
+    got, scanned = sub.window(q_rows, lo, hi, ws, we, measure, t)                       # thread per row
+    ctx.set_tuning(TUNE_WINDOW_MQ, 0)
+    try:
+        one, scanned_one = sub.window(q_rows, lo, hi, ws, we, measure, t)               # one query per pass
+    finally:
+        ctx.set_tuning(TUNE_WINDOW_MQ, 1)
+    assert scanned == scanned_one == scanned_want and scanned > 0
+    assert len(got) > 0 and (got == one).all() and (got == want).all()
+    # and against the oracle (full-width planes under the selection mask) for a few queries
+    sel_mask = ld_oracle.mask_from_haplotypes(sel, n_hap)
+    mcode = 0 if measure == "r_square" else 1
+    for k in (0, 2, len(q_rows) - 1, len(q_rows) // 2, int(np.flatnonzero(q_rows == 120)[0])):
+        rows, res = ld_oracle.window(planes, sel_mask, n_hap, pos0, end0, idnum, elig, int(q_rows[k]), int(ws[k]), int(we[k]), mcode, thres,
+                                     lo=int(lo[k]), hi=int(hi[k]))
+        mine = got[got["query"] == k]
+        assert mine["row"].tolist() == rows.tolist() and (mine["n11"] == res["n_11"]).all() and (mine["packed"] == ld_oracle.packed_of(res)).all()
+    sub.close()
+    st.close()
+
+
 def test_window_edge_cases(ctx):
     from ld_tools_b200.engine import threshold_e4
     st, planes, mask, pos0, end0, idnum, elig = annotated_store(ctx, 600, 198, seed=44)

@@ -211,13 +211,28 @@ constexpr int MQ = 4;
 struct MqBlock { int64_t base, first_item; int32_t a, b; };
 struct MqQuery { int64_t q, qrow, lo, hi; };               // query index of the call, its store row, its candidate range
 
+// One 48-byte record per query with everything the per-pair filters need (filled by mq_extend_kernel before the scan), so that the
+// scan kernels' inner loops read shared memory and registers only.
+struct MqQueryX { int64_t idnum; int32_t q, qrow, lo, hi, ws, we, n1, pad[3]; };
+static_assert(sizeof(MqQueryX) == WINDOW_MQ_EXT_BYTES, "three 16-byte loads");
+
+__global__ void mq_extend_kernel(const WindowArgs A, const MqQuery *__restrict__ sorted, int64_t n, MqQueryX *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const MqQuery m = sorted[i];
+    MqQueryX x;
+    x.idnum = A.idnum[m.qrow]; x.q = (int32_t)m.q; x.qrow = (int32_t)m.qrow; x.lo = (int32_t)m.lo; x.hi = (int32_t)m.hi;
+    x.ws = A.win_start[m.q]; x.we = A.win_end[m.q]; x.n1 = A.freq[m.qrow].n1; x.pad[0] = x.pad[1] = x.pad[2] = 0;
+    out[i] = x;
+}
+
 template <int NG, bool L1ROWS>
 __global__ void __launch_bounds__(WIN_THREADS, 2)
-window_mq_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int64_t n_blocks, const MqQuery *__restrict__ sorted,
+window_mq_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int64_t n_blocks, const MqQueryX *__restrict__ sorted,
                  unsigned int *__restrict__ next_block, int64_t n_rows) {
     // double-buffered per group of queries: their planes (mask folded in) and their records
     __shared__ uint4 qs[2][MQ][NG * 8];
-    __shared__ int64_t s_q[2][MQ], s_qrow[2][MQ], s_lo[2][MQ], s_hi[2][MQ];
+    __shared__ uint4 s_rec[2][MQ][3];                        // MqQueryX records
     __shared__ unsigned int s_j;
     constexpr int PL = MQ * NG * 8;                         // threads that fetch one 16-byte granule of one query plane each
     static_assert(PL <= WIN_THREADS, "plane loaders");
@@ -232,11 +247,15 @@ window_mq_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int64_t
         if (j >= n_blocks) break;
         const MqBlock blk = blocks[j];
         const int n_groups = (blk.b - blk.a + MQ - 1) / MQ;
+        // ---- the row this thread owns in every epilogue of the block, and its filter columns: once per block
+        const int64_t row = blk.base + tid;
+        const bool in_store = row < n_rows;
+        const int64_t rc = in_store ? row : n_rows - 1;
+        const int32_t pos0 = A.pos0[rc], end0 = A.end0[rc], n1r = A.freq[rc].n1, row32 = (int32_t)row;
+        const int64_t idn = A.idnum[rc];
+        const bool elig = in_store && A.eligible[rc];
         // ---- the block's first group, synchronously; the store row of the second group's plane granule for later
-        if (tid < MQ) {
-            const MqQuery m = sorted[min(blk.a + tid, blk.b - 1)];
-            s_q[0][tid] = m.q; s_qrow[0][tid] = m.qrow; s_lo[0][tid] = m.lo; s_hi[0][tid] = blk.a + tid < blk.b ? m.hi : 0;
-        }
+        if (tid < MQ * 3) s_rec[0][tid / 3][tid % 3] = __ldg(reinterpret_cast<const uint4 *>(sorted + min(blk.a + tid / 3, blk.b - 1)) + tid % 3);
         int64_t qrow_next = 0;
         if (tid < PL) {
             const int64_t qrow0 = sorted[min(blk.a + k_pl, blk.b - 1)].qrow;
@@ -249,15 +268,14 @@ window_mq_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int64_t
             const int cur = g & 1, q0 = blk.a + g * MQ, nq = min(MQ, blk.b - q0);
             // ---- the NEXT group's plane granule and records, requested now and parked in shared memory after this
             //      group's work: single independent loads (the host pre-sorted the records), so nobody stalls on them
-            uint4 nx = make_uint4(0, 0, 0, 0), mk = nx;
-            MqQuery mnext = {0, 0, 0, 0};
+            uint4 nx = make_uint4(0, 0, 0, 0), mk = nx, rec_next = nx;
             const bool more = g + 1 < n_groups;
             int64_t qrow_next2 = 0;
             if (more && tid < PL) {
                 nx = ldg_u4(A.planes + qrow_next * A.stride_u4 + g_pl); mk = __ldg(A.mask + g_pl);
                 qrow_next2 = sorted[min(q0 + 2 * MQ + k_pl, blk.b - 1)].qrow;
             }
-            if (more && tid < MQ) mnext = sorted[min(q0 + MQ + tid, blk.b - 1)];
+            if (more && tid < MQ * 3) rec_next = __ldg(reinterpret_cast<const uint4 *>(sorted + min(q0 + MQ + tid / 3, blk.b - 1)) + tid % 3);
             // ---- counting: group of lanes covers rows base + 8 * group + i, each loaded once for all queries of this pass
             int cnt[MQ][8];
 #pragma unroll
@@ -294,17 +312,18 @@ window_mq_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int64_t
             for (int k = 0; k < MQ; ++k) {
                 if (k < nq) {                               // block-uniform
                     const int n11 = transpose_reduce8(cnt[k], lane8);
-                    const int64_t row = blk.base + tid;
-                    // rows before the query's lo are not candidates either: hi = 0 switches the row off
-                    row_epilogue(A, s_q[cur][k], s_qrow[cur][k], row, row >= s_lo[cur][k] ? s_hi[cur][k] : 0, n11, tid, scanned);
+                    const uint4 r0 = s_rec[cur][k][0], r1 = s_rec[cur][k][1];           // {idnum lo, hi, q, qrow} {lo, hi, ws, we}
+                    const int32_t n1q = (int32_t)s_rec[cur][k][2].x;
+                    const int64_t idq = (int64_t)(((unsigned long long)r0.y << 32) | r0.x);
+                    const bool scan = row32 >= (int32_t)r1.x && row32 < (int32_t)r1.y       // the query's candidate range
+                                      && pos0 < (int32_t)r1.w && end0 > (int32_t)r1.z       // fetch overlap, ld_area.py:215-217
+                                      && elig && idn != idq;                                // :223-224, :222
+                    pair_tail(A, (int64_t)(int32_t)r0.z, (int64_t)(int32_t)r0.w, row, scan, n11, n1q, n1r, tid, scanned);
                 }
             }
             if (more) {
                 if (tid < PL) qs[cur ^ 1][k_pl][g_pl] = make_uint4(nx.x & mk.x, nx.y & mk.y, nx.z & mk.z, nx.w & mk.w);
-                if (tid < MQ) {
-                    s_q[cur ^ 1][tid] = mnext.q; s_qrow[cur ^ 1][tid] = mnext.qrow; s_lo[cur ^ 1][tid] = mnext.lo;
-                    s_hi[cur ^ 1][tid] = q0 + MQ + tid < blk.b ? mnext.hi : 0;
-                }
+                if (tid < MQ * 3) s_rec[cur ^ 1][tid / 3][tid % 3] = rec_next;
             }
             qrow_next = qrow_next2;
             __syncthreads();
@@ -324,19 +343,6 @@ window_mq_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int64_t
 // issues at a quarter of the LOP3 rate), which balances the two pipes.  Per-query columns come in one 48-byte record each
 // (MqQueryX, filled by a small kernel before), so nothing in the inner loop waits on global memory.
 constexpr int RQ = 8;                                      // queries per group (their planes double-buffered in shared memory)
-struct MqQueryX { int64_t idnum; int32_t q, qrow, lo, hi, ws, we, n1, pad[3]; };
-static_assert(sizeof(MqQueryX) == WINDOW_MQ_EXT_BYTES, "three 16-byte loads");
-
-__global__ void mq_extend_kernel(const WindowArgs A, const MqQuery *__restrict__ sorted, int64_t n, MqQueryX *__restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const MqQuery m = sorted[i];
-    MqQueryX x;
-    x.idnum = A.idnum[m.qrow]; x.q = (int32_t)m.q; x.qrow = (int32_t)m.qrow; x.lo = (int32_t)m.lo; x.hi = (int32_t)m.hi;
-    x.ws = A.win_start[m.q]; x.we = A.win_end[m.q]; x.n1 = A.freq[m.qrow].n1; x.pad[0] = x.pad[1] = x.pad[2] = 0;
-    out[i] = x;
-}
-
 // popcount(x & q) over 8 words with 4 POPC: three carry-save adders leave two words of weight 1 and three of weight 2, a fourth
 // turns those into one of weight 2 and one of weight 4
 __device__ __forceinline__ int popc_and_8(const uint4 &xa, const uint4 &xb, const uint4 &qa, const uint4 &qb) {
@@ -521,7 +527,7 @@ static int launch_window_ng(ldx_ctx *ctx, const WindowArgs &A) {
 }
 
 template <int NG>
-static int launch_window_mq_ng(ldx_ctx *ctx, const WindowArgs &A, const MqBlock *d_blocks, int64_t n_blocks, const MqQuery *d_sorted,
+static int launch_window_mq_ng(ldx_ctx *ctx, const WindowArgs &A, const MqBlock *d_blocks, int64_t n_blocks, const MqQueryX *d_sorted,
                                unsigned int *d_next, int64_t n_rows) {
     static int per_sm = 0;
     static const bool l1rows = !(getenv("LDX_WINDOW_MQ_L1") && atoi(getenv("LDX_WINDOW_MQ_L1")) == 0);
@@ -531,8 +537,7 @@ static int launch_window_mq_ng(ldx_ctx *ctx, const WindowArgs &A, const MqBlock 
     }
     int64_t grid = (int64_t)ctx->sm_count * per_sm;
     if (grid > n_blocks) grid = n_blocks;
-    LDX_CUDA(cudaMemsetAsync(d_next, 0, sizeof(unsigned int), ctx->stream));
-    timing_begin(ctx);
+    // (the caller brackets the record kernel and this one with one timing pair)
     if (l1rows) window_mq_kernel<NG, true><<<(int)grid, WIN_THREADS, 0, ctx->stream>>>(A, d_blocks, n_blocks, d_sorted, d_next, n_rows);
     else window_mq_kernel<NG, false><<<(int)grid, WIN_THREADS, 0, ctx->stream>>>(A, d_blocks, n_blocks, d_sorted, d_next, n_rows);
     timing_end(ctx);
@@ -575,28 +580,31 @@ int launch_window_mq(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, c
     const MqBlock *blocks = reinterpret_cast<const MqBlock *>(d_blocks);
     const MqQuery *sorted = reinterpret_cast<const MqQuery *>(d_sorted);
     static const bool rows1_off = getenv("LDX_WINDOW_ROWS1") && atoi(getenv("LDX_WINDOW_ROWS1")) == 0;
-    if (A.stride_u4 == 8 && d_ext && n_sorted > 0 && s->n_variants < (1ll << 31) && !rows1_off) {     // 128-byte rows: a thread per row
-        ldx_ctx *ctx = s->ctx;
-        MqQueryX *ext = reinterpret_cast<MqQueryX *>(d_ext);
+    if (!d_ext || n_sorted <= 0 || s->n_variants >= (1ll << 31)) return set_error(LDX_ERR_STATE, "multi-query window kernel: no record scratch");
+    ldx_ctx *ctx = s->ctx;
+    MqQueryX *ext = reinterpret_cast<MqQueryX *>(d_ext);
+    LDX_CUDA(cudaMemsetAsync(d_next, 0, sizeof(unsigned int), ctx->stream));
+    timing_begin(ctx);                      // one pair around the record kernel and the scan kernel
+    mq_extend_kernel<<<(unsigned)((n_sorted + 255) / 256), 256, 0, ctx->stream>>>(A, sorted, n_sorted, ext);
+    ctx->launches++;
+    LDX_LAUNCHED(ctx, "mq_extend_kernel");
+    if (A.stride_u4 == 8 && !rows1_off) {     // 128-byte rows: a thread per row
         static int per_sm = 0;
         if (!per_sm) {
             LDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, window_rows1_kernel, WIN_THREADS, 0));
             if (per_sm < 1) per_sm = 1;
         }
         const int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count * per_sm, n_blocks);
-        LDX_CUDA(cudaMemsetAsync(d_next, 0, sizeof(unsigned int), ctx->stream));
-        timing_begin(ctx);
-        mq_extend_kernel<<<(unsigned)((n_sorted + 255) / 256), 256, 0, ctx->stream>>>(A, sorted, n_sorted, ext);
         window_rows1_kernel<<<(int)grid, WIN_THREADS, 0, ctx->stream>>>(A, blocks, n_blocks, ext, d_next, s->n_variants);
         timing_end(ctx);
-        ctx->launches += 2;
+        ctx->launches++;
         LDX_LAUNCHED(ctx, "window_rows1_kernel");
         return LDX_OK;
     }
     switch (A.stride_u4 / 8) {
-        case 1: return launch_window_mq_ng<1>(s->ctx, A, blocks, n_blocks, sorted, d_next, s->n_variants);
-        case 2: return launch_window_mq_ng<2>(s->ctx, A, blocks, n_blocks, sorted, d_next, s->n_variants);
-        case 5: return launch_window_mq_ng<5>(s->ctx, A, blocks, n_blocks, sorted, d_next, s->n_variants);
+        case 1: return launch_window_mq_ng<1>(ctx, A, blocks, n_blocks, ext, d_next, s->n_variants);
+        case 2: return launch_window_mq_ng<2>(ctx, A, blocks, n_blocks, ext, d_next, s->n_variants);
+        case 5: return launch_window_mq_ng<5>(ctx, A, blocks, n_blocks, ext, d_next, s->n_variants);
         default: return set_error(LDX_ERR_STATE, "multi-query window kernel: unsupported row pitch");
     }
 }

@@ -191,7 +191,7 @@ typedef struct ldx_vcf_row {
     int64_t idnum;                    /* digits of an rs\d+ ID, else -1 - row */
     int32_t gt_off, id_off, ref_off, alt_off, info_off, fmt_off;   /* field starts, relative to line_off */
     int32_t pos;                      /* POS, 1-based */
-    int32_t ref_len;                  /* len(REF): the record covers [pos - 1, pos - 1 + ref_len) (pysam fetch overlap) */
+    int32_t ref_len;                  /* the record covers [pos - 1, pos - 1 + ref_len) for the window fetch: len(REF), or INFO's END=<n> - (pos - 1) when it has one (htslib tbx.c) */
     uint8_t status, eligible, multi, pad[5];
 } ldx_vcf_row;
 int32_t ldx_store_ingest_vcf(ldx_ctx *ctx, const uint8_t *text, int64_t text_bytes, int32_t n_samples,

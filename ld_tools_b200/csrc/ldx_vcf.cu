@@ -143,6 +143,23 @@ parse_lines_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
         }
         if (r.multi || r.status) r.eligible = 0;
     }
+    // INFO: END=<n> extends the record's interval for the window fetch (ld_area.py:215-217 goes through the tabix index, and
+    // htslib's tbx.c takes a VCF record's end from INFO/END when it has one -- structural variants -- else from len(REF);
+    // an END at or before POS-1 is ignored there too).  ref_len carries the interval length either way.
+    {
+        const int32_t a = field_off[7], b = field_off[8] - 1;
+        bool at_key = true;
+        for (int32_t i = a; i + 4 < b + 1; ++i) {
+            if (at_key && text[start + i] == 'E' && text[start + i + 1] == 'N' && text[start + i + 2] == 'D' && text[start + i + 3] == '=') {
+                int64_t v = 0;
+                int32_t j = i + 4;
+                for (; j < b && text[start + j] >= '0' && text[start + j] <= '9' && v < 4000000000ll; ++j) v = v * 10 + (text[start + j] - '0');
+                if (j > i + 4 && v > pos - 1 && v - (pos - 1) < 2147483647ll && !(r.status & 4)) r.ref_len = (int32_t)(v - (pos - 1));
+                break;
+            }
+            at_key = text[start + i] == ';';
+        }
+    }
     tmp_rows[k] = r;
     is_rec[k] = 1;
 }

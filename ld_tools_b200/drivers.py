@@ -107,7 +107,7 @@ class ChromData:
     inflate + parse + GPU packing and load 632 B per variant instead of 10 KB of text.  A cache whose recorded VCF
     size or mtime differs from the file's is rebuilt; LDX_NO_STORE_CACHE=1 (or cache=False) ignores it."""
 
-    CACHE_VERSION = 2
+    CACHE_VERSION = 3           # 3: record intervals honour INFO/END
 
     def __init__(self, ctx, vcf_path, cache=True):
         cache = cache and not os.environ.get("LDX_NO_STORE_CACHE")
@@ -116,7 +116,10 @@ class ChromData:
             if cache:
                 self._save_cache(vcf_path)
         self.n_variants, self.n_samples = len(self.pos), len(self.samples)
-        self.max_ref_len = int((self.end0 - self.pos0).max()) if self.n_variants else 1
+        # the longest interval among the rows a scan can report (an ineligible structural variant's END= may span megabases: it is
+        # never a hit, so it must not widen every query's candidate range)
+        span = (self.end0 - self.pos0)[self.rows["eligible"] != 0]
+        self.max_ref_len = int(span.max()) if len(span) else 1
         self.col_of = {n: i for i, n in enumerate(self.samples)}
         # (pos, id) -> row is resolved on demand (row_of): a position lookup plus an ID comparison of the few records at that
         # position, so that a chromosome with millions of rows costs nothing up front.  Needs ascending positions (every tabix-

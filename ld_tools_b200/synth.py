@@ -259,7 +259,8 @@ def write_intgen_dir(path, panel, recs, haps, chrom="22", gt_text=None):
         written = []
         for r, h in zip(recs, haps):
             ac = int(h.sum())
-            info = f"AC={ac};AF={ac / len(h):.6g};AN={len(h)};VT={r['vt']}" + (";MULTI_ALLELIC" if r["multi"] else "")
+            info = (r.get("info_prefix", "") + f"AC={ac};AF={ac / len(h):.6g};AN={len(h)};VT={r['vt']}" + (";MULTI_ALLELIC" if r["multi"] else "")
+                    + r.get("info_suffix", ""))
             head = f"{r['chrom']}\t{r['pos']}\t{r['id']}\t{r['ref']}\t{r['alt']}\t100\tPASS\t{info}\tGT\t"
             fh.write(head.encode() + (gt_row_text(h) if gt_text is None else gt_text[len(written)]) + b"\n")
             written.append(1)

@@ -119,6 +119,56 @@ def build_dataset_x(root):
     return intgen, srcs
 
 
+def build_dataset_edge(root):
+    """Records placed on the edges of one query's window (ld_area.py:174-177: fetch(chrom, pos - flank, pos + flank), 0-based
+    half-open, overlap semantics of the tabix index): an indel straddling the left edge, one ending exactly at it, records at
+    high - 1 and high, structural-variant style records whose interval comes from INFO/END (first key, middle key, END equal to
+    the window start, CIEND without END).  All of them carry the query's haplotypes, so only the interval decides.
+    -> (intgen_dir, {"area": src_dir}, flank)"""
+    from ld_tools_b200.synth import conversion_rows, make_panel, make_records, synth_haplotypes, write_intgen_dir
+    n, n_s, flank = 240, 60, 500
+    panel = make_panel(n_s, seed=SEED + 21)
+    haps = synth_haplotypes(n, 2 * n_s, seed=SEED + 21, n_founders=12, switch_rate=0.02)
+    recs = make_records(n, chrom="7", start=1_000_000, mean_gap=30, seed=SEED + 21)
+    qi = next(i for i in range(118, n) if recs[i]["id"].startswith("rs") and not recs[i]["multi"] and len(recs[i]["ref"]) == 1
+              and 0.2 < haps[i].mean() < 0.8)
+    q = recs[qi]
+    low, high = q["pos"] - flank, q["pos"] + flank
+    crafted = [
+        dict(pos=low - 5, id="rs900001", ref="ACGTACGTACGT", alt="A", vt="INDEL"),                      # [low-6, low+6): straddles the left edge -> kept
+        dict(pos=low - 9, id="rs900002", ref="ACGTACGTAC", alt="A", vt="INDEL"),                        # [low-10, low): ends at the edge -> not fetched
+        dict(pos=high, id="rs900003", ref="A", alt="C", vt="SNP"),                                      # pos0 = high - 1 -> kept
+        dict(pos=high + 1, id="rs900004", ref="A", alt="C", vt="SNP"),                                  # pos0 = high -> not fetched
+        dict(pos=low - 300, id="rs900005", ref="A", alt="<CN0>", vt="SV", info_prefix=f"END={low + 20};"),          # END first in INFO -> kept
+        dict(pos=low - 250, id="rs900006", ref="A", alt="<CN0>", vt="SV", info_prefix=f"END={low};"),               # interval ends at the edge -> not fetched
+        dict(pos=low - 200, id="rs900007", ref="A", alt="<CN2>", vt="SV", info_prefix="CIEND=-50,400;"),            # no END key -> len(REF) -> not fetched
+        dict(pos=low - 150, id="rs900008", ref="AC", alt="A", vt="SV", info_suffix=f";CIEND=0,5;END={low + 1};SVLEN=-9"),   # END in the middle -> kept
+        dict(pos=high - 40, id="rs900009", ref="A", alt="<CN0>", vt="SV", info_prefix=f"END={high - 400};"),        # END before POS: ignored -> kept by len(REF)
+    ]
+    for c in crafted:
+        c.update(chrom="7", multi=False)
+    order = sorted(range(n + len(crafted)), key=lambda k: ((recs + crafted)[k]["pos"], k))
+    all_recs = [(recs + crafted)[k] for k in order]
+    all_haps = np.concatenate([haps, np.repeat(haps[qi:qi + 1], len(crafted), axis=0)])[order]
+    intgen = os.path.join(root, "intgen_edge")
+    write_intgen_dir(intgen, panel, all_recs, all_haps, chrom="7")
+    addressable = [r[2] for r in conversion_rows(all_recs)]
+    rng = np.random.default_rng(SEED + 22)
+    d = os.path.join(root, "src_area_edge")
+    os.makedirs(d)
+    with open(os.path.join(d, "edge.txt"), "w") as fh:
+        fh.write(q["id"] + "\n")
+        for k in rng.choice(len(addressable), 9, replace=False):
+            fh.write(addressable[k] + "\n")
+        fh.write("rs900005\n")                         # the END= record as a query: its own window is around its POS
+    return intgen, {"area": d}, {"query": q["id"], "kept": ["rs900001", "rs900003", "rs900005", "rs900008", "rs900009"],
+                                 "not_fetched": ["rs900002", "rs900004", "rs900006", "rs900007"]}
+
+
+AREA_EDGE_CASES = [
+    ("area_edge_r2_tsv", ["-w", "500", "-l", "r_square", "-z", "0.9", "-o", "tsv"]),
+    ("area_edge_dp_rsids", ["-w", "500", "-l", "d_prime", "-z", "0.9", "-o", "rsids", "-e", "eur,eas"]),
+]
 AREA_X_CASES = [
     ("area_x_r2_tsv", ["-w", "3000", "-l", "r_square", "-z", "0.2", "-o", "tsv"]),
     ("area_x_dp_json_male", ["-w", "2500", "-l", "d_prime", "-z", "0.8", "-o", "json", "-g", "male"]),

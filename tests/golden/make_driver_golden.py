@@ -80,6 +80,17 @@ def main():
             with open(os.path.join(OUT, name, f"pair{k}.txt"), "w") as fh:
                 fh.write(text)
         index[name] = sorted(os.listdir(os.path.join(OUT, name)))
+    # ---- records on the edges of a query's window, INFO/END intervals
+    intgen_e, srcs_e, expect = dc.build_dataset_edge(work)
+    for name, extra in dc.AREA_EDGE_CASES:
+        trg = os.path.join(work, "out_" + name)
+        os.makedirs(trg)
+        run_ref("ld_area.py", ["-S", srcs_e["area"], "-D", intgen_e, "-t", trg, "-f", "-p", "1"] + extra, work)
+        shutil.copytree(trg, os.path.join(OUT, name))
+        index[name] = sorted(dc.read_tree(trg))
+        # the crafted records decide by their intervals alone (they carry the query's haplotypes)
+        text = b"".join(v for k, v in dc.read_tree(trg).items() if expect["query"] in os.path.basename(k)).decode()
+        assert all(i in text for i in expect["kept"]) and not any(i in text for i in expect["not_fetched"]), (name, text[:2000])
     with open(os.path.join(OUT, "index.json"), "w") as fh:
         json.dump(index, fh, indent=1, sort_keys=True)
     n = sum(len(v) for v in index.values())

@@ -4,9 +4,22 @@ run in a container without pysam and serve as end-to-end oracles (tests/golden/m
 
 Surface: VariantFile(path) as a context manager; .fetch() and
 .fetch(chrom, start, end) with htslib's 0-based half-open OVERLAP semantics (a record is returned
-iff POS-1 < end and POS-1+rlen > start, rlen = len(REF)); record attributes id, chrom, pos (1-based),
+iff POS-1 < end and record_end > start; record_end = POS-1 + len(REF), or the value of INFO/END when the record
+has one greater than POS-1); record attributes id, chrom, pos (1-based),
 ref, alts (tuple), info (mapping; flags are keys; VT -> tuple of str), samples[name]['GT'] -> tuple of
 ints / None; tabix_index() is a no-op.  Nothing in ld_tools_b200/ imports this package.
+
+PROVENANCE.  Real pysam / htslib / tabix are not in this image and cannot be installed (no network), so these
+semantics are restated from htslib's published sources, not observed: the interval of a VCF line in a tabix index
+and in the iterator's per-line re-check is tbx.c:tbx_parse1, VCF preset -- begin = POS-1, end = begin + len(REF)
+(column 4), replaced by INFO's END=<n> when column 8 starts with "END=" or contains ";END=" and n > begin (an END
+at or before begin is warned about and ignored); the iterator returns a line iff end > region_start and begin <
+region_end.  GT decoding follows pysam's VariantRecordSample: alleles as ints, '.' -> None, one entry per allele of
+the call (so a haploid call is a 1-tuple), phasing separator '|' or '/'.  INFO flags are keys of rec.info.  Golden
+cases that pin the edge semantics the engine hard-codes: tests/golden/drivers/area_edge_* (an indel straddling the
+window's left edge, one ending exactly at it, records at high-1 / high, END= first and in the middle of INFO, END
+equal to the window start, CIEND= without END).  A maintainer with pysam installed can regenerate the same cases
+with tests/golden/make_driver_golden.py after removing tests/refshim from PYTHONPATH.
 """
 import gzip
 
@@ -39,6 +52,16 @@ class _Record:
                 self.info[item] = True
         self.samples = _Samples(names_to_col, f[9:])
         self.start, self.stop = self.pos - 1, self.pos - 1 + len(self.ref)
+        # tbx.c:tbx_parse1 (VCF preset): "END=" at the start of INFO, else ";END="
+        s = f[7]
+        k = 4 if s.startswith("END=") else (s.find(";END=") + 5 if ";END=" in s else -1)
+        if k >= 0:
+            digits = ""
+            while k < len(s) and s[k].isdigit():
+                digits += s[k]
+                k += 1
+            if digits and int(digits) > self.start:
+                self.stop = int(digits)
 
 
 class VariantFile:

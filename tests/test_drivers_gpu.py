@@ -174,6 +174,19 @@ def test_ld_area_chrx_general_route_tree_identical(data_x, ctx, tmp_path, name, 
     assert assert_same_tree(str(tmp_path), name) > 3
 
 
+@pytest.mark.parametrize("name,extra", dc.AREA_EDGE_CASES)
+def test_ld_area_window_edges_and_info_end_tree_identical(ctx, tmp_path_factory, tmp_path, name, extra):
+    """Records on the edges of a query's window and structural-variant records whose interval comes from INFO/END (the tabix
+    index's definition, see tests/refshim/pysam): an indel straddling the left edge is reported, one ending exactly at it is
+    not, pos0 = high - 1 is, pos0 = high is not, END= first or in the middle of INFO extends the record, CIEND= does not."""
+    from ld_tools_b200 import drivers
+    intgen, srcs, expect = dc.build_dataset_edge(str(tmp_path_factory.mktemp("ldx_drivers_edge")))
+    drivers.ld_area(srcs["area"], intgen, trg_top_dir_path=str(tmp_path), ctx=ctx, **parse(extra, "area"))
+    assert assert_same_tree(str(tmp_path), name) >= 2
+    mine = b"".join(v for k, v in dc.read_tree(str(tmp_path)).items() if expect["query"] + "_" in os.path.basename(k)).decode()
+    assert all(i in mine for i in expect["kept"]) and not any(i in mine for i in expect["not_fetched"])
+
+
 @pytest.mark.parametrize("tile_n", [0, 128])
 @pytest.mark.parametrize("name,extra", dc.TRIANGLE_X_CASES)
 def test_ld_triangle_chrx_general_route_table_identical(data_x, ctx, tmp_path, name, extra, tile_n):
@@ -325,7 +338,12 @@ def _host_parse(raw, n_samples):
         keys = [x.split("=")[0] for x in (f[7].decode().split(";") if len(f) > 7 else [])]
         rs = bool(re.match(r"rs\d+$", rid))
         multi = "MULTI_ALLELIC" in keys
-        rows.append({"pos": pos, "id": rid, "ref": f[3].decode() if len(f) > 3 else "", "alt": f[4].decode() if len(f) > 4 else "",
+        span = len(f[3]) if len(f) > 3 else 0
+        info = f[7].decode() if len(f) > 7 else ""
+        m = re.match(r"END=(\d+)", info) or re.search(r";END=(\d+)", info)
+        if m and int(m.group(1)) > pos - 1:
+            span = int(m.group(1)) - (pos - 1)
+        rows.append({"pos": pos, "id": rid, "ref": f[3].decode() if len(f) > 3 else "", "alt": f[4].decode() if len(f) > 4 else "", "span": span,
                      "rs": rs, "multi": multi, "ok": ok, "gts": f[9:9 + n_samples] if ok else None,
                      "vt": ([x[3:] for x in f[7].decode().split(";") if x.startswith("VT=")] or [""])[0] if len(f) > 7 else ""})
     return rows
@@ -345,7 +363,7 @@ def _check_ingest(ctx, raw, n_samples):
         if not w["ok"]:
             assert r["eligible"] == 0 and not planes[k].any()
             continue
-        assert r["pos"] == w["pos"] and r["ref_len"] == len(w["ref"]) and bool(r["multi"]) == w["multi"]
+        assert r["pos"] == w["pos"] and r["ref_len"] == w["span"] and bool(r["multi"]) == w["multi"]
         assert bool(r["eligible"]) == (w["rs"] and not w["multi"])
         assert r["idnum"] == (int(w["id"][2:]) if w["rs"] else -1 - k)
         rec = blob[off[k]:off[k + 1]]
@@ -381,6 +399,10 @@ def test_gpu_vcf_ingest_matches_a_host_parse(data, ctx):
              fixed.format(pos=77, id="esv123", ref="A", alt="<CN0>", info="MULTI_ALLELIC=1;VT=SV") + gt("0|0 0|0 0|1"),
              fixed.format(pos=78, id=".", ref="A", alt="C,T", info="XMULTI_ALLELIC;MULTI_ALLELICX;VT=SNP") + gt("1|1 1|1 1|1"),
              fixed.format(pos=79, id="rs12x", ref="A", alt="C", info=".") + gt("0|1 .|1 0/1"),
+             fixed.format(pos=500, id="rs21", ref="A", alt="<CN0>", info="END=1234;VT=SV") + gt("0|1 1|0 0|0"),     # interval from INFO/END
+             fixed.format(pos=501, id="rs22", ref="ACG", alt="A", info="CIEND=-5,5;VT=SV;END=2000;SVLEN=9") + gt("0|1 1|0 0|0"),
+             fixed.format(pos=502, id="rs23", ref="AC", alt="A", info="CIEND=0,9;XEND=7000;VT=SV") + gt("0|1 1|0 0|0"),    # no END key
+             fixed.format(pos=503, id="rs24", ref="AC", alt="A", info="VT=SV;END=400") + gt("0|1 1|0 0|0"),            # END before POS: ignored
              fixed.format(pos=80, id="rs9", ref="A", alt="C", info="VT=SNP") + gt("0|1 1|0"),          # a column short
              "22\t81\trs10\tA",                                                                    # truncated line
              "",

@@ -4,7 +4,8 @@
 
 Reads the report with `ncu -i REPORT --page raw --csv` and prints the metrics the DESIGN.md rooflines
 quote (duration, pipe utilisation, issue slots, DRAM bytes = roofline.traffic, L2 hit rate, launch shape)
-for the LAST launch whose name contains KERNEL_SUBSTRING.
+for the LAST launch whose name contains KERNEL_SUBSTRING (or, with a fourth argument "longest", the launch of that kernel
+with the longest duration -- the full-size one when a script also runs the kernel on small inputs).
 """
 import csv
 import io
@@ -49,6 +50,12 @@ def main():
     if not hit:
         sys.exit(f"no launch of a kernel matching {kernel!r} in {rep}")
     r = hit[-1]
+    if len(sys.argv) > 4 and sys.argv[4] == "longest":
+        def dur(x):
+            v, u = float(x[col["gpu__time_duration.sum"]]), units[col["gpu__time_duration.sum"]]
+            return v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(u.replace("second", "s").strip(), 1.0)
+        r = max(hit, key=dur)
+        header += f" [longest of {len(hit)} launches]"
     print("# " + header)
     print(f"{'Kernel Name':<90} {r[col['Kernel Name']]}")
     for m in METRICS:

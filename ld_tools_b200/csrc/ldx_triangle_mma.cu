@@ -388,7 +388,8 @@ struct MmaArgs {
     int32_t *error_flag;
     unsigned long long *trace;   // optional [512]: globaltimer stamps of CTA 0 (diagnostics)
     int dbg;                     // diagnostics build only (LDX_DEBUG_MMA; results invalid): 1 skip row-operand widening,
-                                 // 2 skip column-operand widening, 4 skip the epilogue arithmetic, 8 skip the MMAs
+                                 // 2 skip column-operand widening, 4 skip the whole epilogue, 8 skip the MMAs, 16 no result stores,
+                                 // 32 nobody is deferred, 64 no screening arithmetic (16 + 32 + 64: what is left is TMEM loads and set-up)
     // direct mode: the planes of the store itself through a TMA tensor map; matrix row r = store row row0 + r
     const uint4 *mask; int32_t row0;
     alignas(64) CUtensorMap tmap;
@@ -934,9 +935,12 @@ triangle_mma_kernel(const __grid_constant__ MmaArgs A) {
                     cp.rc[0] = rcp_nn(cn1[2 * k], Nn); cp.rc[1] = rcp_nn(cn1[2 * k + 1], Nn);
                     uint32_t w0, w1;
                     bool s0, s1;
+                    if (TRACE && (A.dbg & 64)) { w0 = acc[i] + cp.rc[0]; w1 = acc[i + 1]; s0 = s1 = false; }
+                    else
                     fast_pair2<THRES>(acc[i], acc[i + 1], K, g ? Rb : Ra, cp, w0, w1, s0, s1);
+                    if (TRACE && (A.dbg & 32)) s0 = s1 = false;
                     const int64_t row = g ? rb : ra;
-                    const bool v0 = row < S.v && col < row, v1 = row < S.v && col + 1 < row;
+                    const bool v0 = row < S.v && col < row && !(TRACE && (A.dbg & 16) && w0 != 0x12345678u), v1 = row < S.v && col + 1 < row && !(TRACE && (A.dbg & 16) && w1 != 0x12345678u);
                     if (v0) {
                         (g ? pb : pa)[8 * k] = s0 ? (acc[i] >> ACC_SHIFT) : w0;
                         if (qa) (g ? qb : qa)[8 * k] = true_n11((int32_t)(acc[i] >> ACC_SHIFT), g ? n1b : n1a, cn1[2 * k], Nn);
@@ -1036,6 +1040,7 @@ triangle_mma_kernel(const __grid_constant__ MmaArgs A) {
             tc_fence_after();
             if (TRACE && A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[1 + 2 * tl] = gtime();   // accumulator ready
             if (ew == 0 && lane == 0 && tl == 0) LDX_CTA_STAMP(2);
+            if (TRACE && A.trace && blockIdx.x == 1 && ew == 0 && lane == 0) A.trace[39] = gtime();
             const int h_end = SINGLE && N == 128 && !PAIR && A.help ? 1 : 2;     // single wave: rows 16..31 of the quadrant belong to the wideners
 #pragma unroll 1
             for (int h = 0; h < h_end; ++h) {
@@ -1056,7 +1061,9 @@ triangle_mma_kernel(const __grid_constant__ MmaArgs A) {
                     const int64_t cg0 = c0 + cb;                  // first column of this load
                     if (cg0 >= rmin + 15 || cg0 >= v) break;      // warp-uniform: nothing below the diagonal
                     uint32_t acc[16];
+                    if (TRACE && A.trace && blockIdx.x == 1 && ew == 0 && lane == 0) A.trace[40 + (cb >> 5) * 3] = gtime();     // before the load
                     tmem_ld16x256(tmem_acc + (uint32_t)cb, acc);
+                    if (TRACE && A.trace && blockIdx.x == 1 && ew == 0 && lane == 0) A.trace[41 + (cb >> 5) * 3] = gtime();     // accumulators in registers
                     uint32_t word[16];
                     uint32_t slow = 0;                            // bit i: pair i must be redone exactly
 #pragma unroll
@@ -1064,11 +1071,20 @@ triangle_mma_kernel(const __grid_constant__ MmaArgs A) {
                         const int k = i >> 2, g = (i >> 1) & 1;
                         const ColPair cp = cols[(cb >> 1) + 4 * k + lr];
                         bool s0, s1;
+                        if (TRACE && (A.dbg & 64)) { word[i] = acc[i] + cp.rc[0]; word[i + 1] = acc[i + 1]; s0 = s1 = false; }   // diagnostics: no screen arithmetic
+                        else
                         fast_pair2<THRES>(acc[i], acc[i + 1], K, g ? Rb : Ra, cp, word[i], word[i + 1], s0, s1);
                         if (s0) slow |= 1u << i;
                         if (s1) slow |= 2u << i;
                     }
+                    if (TRACE && (A.dbg & 32)) slow = 0;              // diagnostics: nobody is deferred
                     const bool interior = cg0 + 32 <= rmin && rmin + 15 < v;   // warp-uniform: every pair is below the diagonal
+                    if (TRACE && (A.dbg & 16)) {                      // diagnostics: no result stores (keep the values alive)
+                        uint32_t x = 0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) x ^= word[i];
+                        if (x == 0x12345678u) pa[0] = x;
+                    } else
                     if (interior) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
@@ -1103,6 +1119,7 @@ triangle_mma_kernel(const __grid_constant__ MmaArgs A) {
                     // but queued for slow_pairs_kernel, which runs after this kernel and overwrites their
                     // words.  The queue is per warp in shared memory (ballot compaction, no atomics) and is
                     // flushed to the global list when it fills up and at the end.
+                    if (TRACE && A.trace && blockIdx.x == 1 && ew == 0 && lane == 0) A.trace[42 + (cb >> 5) * 3] = gtime();     // words stored
                     if (__any_sync(0xffffffffu, slow != 0)) {
                         // a lane with flagged pairs parks its counts in shared memory and fetches them by index
                         if (slow) {
@@ -1134,6 +1151,7 @@ triangle_mma_kernel(const __grid_constant__ MmaArgs A) {
             if (lane == 0) { if (PAIR) mbar_arrive_remote(tmem_empty_leader + 8 * buf); else mbar_arrive(tmem_empty + 8 * buf); }
             if (TRACE && A.trace && blockIdx.x == 0 && ew == 0 && lane == 0 && tl < 3) A.trace[2 + 2 * tl] = gtime();       // epilogue of this tile done
             if (ew == 0 && lane == 0 && tl == 0) LDX_CTA_STAMP(3);
+            if (TRACE && A.trace && blockIdx.x == 1 && ew == 0 && lane == 0) A.trace[46] = gtime();
         }
         if (SINGLE) {
             // Single wave: no follow-up kernel.  This warp's buffered pairs go onto the CTA's list (what does not

@@ -69,6 +69,9 @@ def main():
                 t0 = s[0]
                 print("  kernel entry %.2f us before the prologue's end; all roles done at %.2f us" % ((t0 - s[7]) / 1e3, (s[56] - t0) / 1e3))
                 print("  tile stamps (us after prologue): " + " ".join("%.2f" % ((x - t0) / 1e3) for x in s[1:7] if x))
+                if s[39]:
+                    print("  CTA 1, epilogue warp 0 (us after its accumulator was ready): " + " ".join("%s %.2f" % (n, (s[k] - s[39]) / 1e3) for n, k in
+                          [("ld0>", 40), ("ld0<", 41), ("stored0", 42), ("ld1>", 43), ("ld1<", 44), ("stored1", 45), ("done", 46)] if s[k]))
                 c = np.concatenate([s[512:512 + 8 * 192].reshape(192, 8), s[2048:2048 + 2 * 192].reshape(192, 2)], axis=1)
                 c = c[c[:, 0] > 0]
                 if len(c):

@@ -874,7 +874,7 @@ def leg_sharded_genome(env, n_variants=80_000_000, n_queries=50_000, flank=1_000
             h = h + torch.tensor([p["qa"] + int(q_first[p["chrom"]]), p["rb"], 0, 0], dtype=torch.int32, device=dev)
             parts.append(h)
         mine = torch.cat(parts) if parts else torch.zeros((0, 4), dtype=torch.int32, device=dev)
-        allh = shard.gather_hits_tensor(mine)
+        allh = shard.gather_hits_tensor(mine, ranks_own_ordered_query_ranges=True)     # genome_pieces: contiguous query ranges in rank order
         return mine, allh, g0
     job()
     times, gathers = [], []
@@ -912,7 +912,8 @@ def leg_sharded_genome(env, n_variants=80_000_000, n_queries=50_000, flank=1_000
            "scaling": "strong", "ms": best, "ms_all": [round(x, 3) for x in times], "value": int(tot[0].item()) / (best * 1e-3), "unit": "pairs/s",
            "pairs_scanned": int(tot[0].item()), "pairs_per_rank": per_rank.tolist(), "kept_pairs": int(allh.shape[0]),
            "gather_ms": min(gathers), "store_GB_total": round(int(tot[1].item()) / 1e9, 2), "build_s": build_s,
-           "collective": "NCCL all_gather of the kept-pair counts and of the padded 16-byte records (shard.gather_hits_tensor), device sort by (query, row); "
+           "collective": "device sort of the rank's own records by (query, row), then NCCL all_gather of the kept-pair counts and of the padded 16-byte records "
+                         "(shard.gather_hits_tensor; ranks own ordered query ranges, so the concatenation is the sorted list); "
                          "inside the timed region, reported separately as gather_ms (renumbering + collective + sort)",
            "timed": "CUDA events on the launching stream around window scans + ldx_resolve + renumbering + gather + sort, max over ranks",
            "parity_windows_ok": ok}

@@ -191,15 +191,19 @@ def gather_hits(hits, group=None, device=None):
     return allh[np.lexsort((allh["row"], allh["query"]))]
 
 
-def gather_hits_tensor(local, group=None):
+def gather_hits_tensor(local, group=None, ranks_own_ordered_query_ranges=False):
     """The same collective with the records left where they are: `local` is an int32 tensor [n, 4] (ldx_hit records as
     {query, row, n11, packed}) on the rank's CUDA device (NCCL) or on the CPU (gloo); returns every rank's records
-    concatenated and sorted by (query, row) as a tensor on the same device.  One all_gather of the counts, one of the
-    records padded to the longest list, one device sort: nothing but the counts crosses to the host."""
+    concatenated and sorted by (query, row) as a tensor on the same device.  Every rank sorts ITS records (the work that
+    shrinks with the number of ranks), then one all_gather of the counts and one of the records padded to the longest list;
+    nothing but the counts crosses to the host.  ranks_own_ordered_query_ranges: rank r's queries all come before rank
+    r + 1's (genome_pieces, area_slabs) -- then the concatenation in rank order is the sorted list and no global sort runs."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     local = local.reshape(-1, 4).contiguous()
+    if local.shape[0] > 1:
+        local = local[torch.argsort((local[:, 0].to(torch.int64) << 32) | local[:, 1].to(torch.int64))]
     if world > 1:
         n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
         counts = [torch.zeros_like(n) for _ in range(world)]
@@ -211,7 +215,8 @@ def gather_hits_tensor(local, group=None):
         parts = [torch.empty_like(buf) for _ in range(world)]
         dist.all_gather(parts, buf, group=group)
         allh = torch.cat([p[:c] for p, c in zip(parts, counts)])
+        if not ranks_own_ordered_query_ranges:
+            allh = allh[torch.argsort((allh[:, 0].to(torch.int64) << 32) | allh[:, 1].to(torch.int64))]
     else:
         allh = local
-    key = (allh[:, 0].to(torch.int64) << 32) | allh[:, 1].to(torch.int64)
-    return allh[torch.argsort(key)]
+    return allh

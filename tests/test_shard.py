@@ -184,6 +184,15 @@ def _gloo_worker(rank, world, port, tmpdir):
     local = torch.from_numpy(np.ascontiguousarray(mine).view(np.int32).reshape(-1, 4).copy())      # rank_hits: already job-wide numbering
     ten = shard.gather_hits_tensor(local).numpy().reshape(-1).view(HIT_DTYPE)
     np.save(os.path.join(tmpdir, f"hits_tensor_{rank}.npy"), ten)
+    # With the queries numbered in position order (as genome_pieces numbers them), rank r's queries all come before rank
+    # r + 1's: the cheaper form -- every rank sorts its own records, no global sort -- returns the same list
+    pos_rank = torch.from_numpy(np.argsort(np.argsort(job["q_row"])).astype(np.int32))
+    renum = local.clone()
+    renum[:, 0] = pos_rank[local[:, 0].long()]
+    full = shard.gather_hits_tensor(renum)
+    shuffled = renum[torch.randperm(renum.shape[0], generator=torch.Generator().manual_seed(rank))]
+    fast = shard.gather_hits_tensor(shuffled, ranks_own_ordered_query_ranges=True)
+    assert torch.equal(full, fast) and full.shape[0] == ten.shape[0]
     dist.barrier()
     dist.destroy_process_group()
 

@@ -423,9 +423,6 @@ constexpr int FIRST_WIDEN_WARP = 4, FIRST_EPI_WARP = FIRST_WIDEN_WARP + N_WIDEN_
 constexpr int MMA_THREADS = 32 * (FIRST_EPI_WARP + N_EPI_WARPS);   // 896
 static_assert(MMA_THREADS * REGS_LAUNCH <= 65536, "register file");
 constexpr int SLOW_BUF = 64;                                           // deferred pairs buffered per epilogue warp
-#ifndef LDX_EPI_TSTORE
-#define LDX_EPI_TSTORE 0          // 1: result words leave through the warp's staging block, one row per store instruction
-#endif
 constexpr int EPI_PITCH = 16;                                          // words per parked row (rare path: bank conflicts do not matter)
 
 // Per PAIR of neighbouring column variants (2j, 2j + 1), what the screening arithmetic of the epilogue needs, laid out as
@@ -1087,41 +1084,6 @@ triangle_mma_kernel(const __grid_constant__ MmaArgs A) {
                         for (int i = 0; i < 16; ++i) x ^= word[i];
                         if (x == 0x12345678u) pa[0] = x;
                     } else
-#if LDX_EPI_TSTORE
-                    {
-                        // The lane's words belong to 2 rows x 8 column pairs; stored from here, one instruction touches 8 rows
-                        // (8 cache lines, 16 bytes each).  Through the warp's staging block ([16 rows][32 words], 8-byte
-                        // stores, columns swizzled by row against bank conflicts) every store instruction writes ONE row's
-                        // 128 contiguous bytes.
-                        __syncwarp();
-#pragma unroll
-                        for (int i = 0; i < 16; i += 2) {
-                            const int k = i >> 2, g = (i >> 1) & 1;
-                            *reinterpret_cast<uint2 *>(stage + (lq + 8 * g) * 32 + ((8 * k + 2 * lr) ^ ((lq & 3) << 3))) = make_uint2(word[i], word[i + 1]);
-                        }
-                        __syncwarp();
-                        const bool interior = cg0 + 32 <= rmin && rmin + 15 < v;   // warp-uniform: every pair is below the diagonal
-                        uint32_t *prow = packed + (rmin * (rmin - 1) / 2 - out_off + cg0 + lane);
-                        const int64_t col = cg0 + lane;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const uint32_t w = stage[j * 32 + (lane ^ ((j & 3) << 3))];
-                            if (interior || (rmin + j < v && col < rmin + j)) *prow = w;
-                            prow += rmin + j;                         // tri(r + 1) = tri(r) + r
-                        }
-                        if (!interior) {
-                            uint32_t valid = 0;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const int k = i >> 2, g = (i >> 1) & 1, e = i & 1;
-                                const int64_t row = g ? rb : ra, c = cg0 + 8 * k + 2 * lr + e;
-                                if (row < v && c < row) valid |= 1u << i;
-                            }
-                            slow &= valid;
-                        }
-                        __syncwarp();                                 // the staging block is reused by the deferred-pair hand-off below
-                    }
-#else
                     {
                     const bool interior = cg0 + 32 <= rmin && rmin + 15 < v;   // warp-uniform: every pair is below the diagonal
                     if (interior) {
@@ -1144,7 +1106,6 @@ triangle_mma_kernel(const __grid_constant__ MmaArgs A) {
                         slow &= valid;
                     }
                     }
-#endif
                     if (n11o) {                                   // warp-uniform; the counts are a diagnostic / test output
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {

@@ -12,32 +12,26 @@
 namespace ldx {
 
 // ------------------------------------------------------------------------------------------ K1
-// One CTA per variant row (grid-stride).  The row's text (4 bytes per sample, arbitrary byte
-// alignment inside the VCF line) is staged into shared memory with aligned 16-byte loads, then
-// each warp turns 32 samples into one 64-bit word: two ballots (allele slot 0 / slot 1) that one
-// lane bit-interleaves, because haplotype 2*s+a lives at bit 2*s+a.
+// One CTA per variant row (grid-stride).  The row's text (4 bytes per sample, arbitrary byte alignment inside the VCF line) is
+// staged into shared memory word by word.  A thread then takes FOUR samples: five words of the staged text, four
+// funnel shifts undo the row's byte skew, and one XOR against "0|0" per sample gives both allele bits and the validity test
+// (every other bit of the three bytes must be zero); its 8 haplotype bits go to a byte of the row's image in shared memory --
+// haplotype 2*s+a lives at bit 2*s+a, so a thread's byte IS byte s/4 of the row -- and the image leaves with coalesced 8-byte
+// stores.  ~9 instructions per sample (the first version: one sample per lane, three byte loads, two ballots and a bit
+// interleave per 32 samples, ~40).
 constexpr int PACK_THREADS = 256;
 
-__device__ __forceinline__ uint64_t spread_bits(uint32_t x) {   // bit i -> bit 2i
-    uint64_t v = x;
-    v = (v | (v << 16)) & 0x0000ffff0000ffffull;
-    v = (v | (v << 8)) & 0x00ff00ff00ff00ffull;
-    v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0full;
-    v = (v | (v << 2)) & 0x3333333333333333ull;
-    v = (v | (v << 1)) & 0x5555555555555555ull;
-    return v;
-}
+__host__ __device__ inline int pack_text_granules(int32_t n_samples) { return (int)((4ll * n_samples + 15 + 16) / 16 + 1); }
 
 __global__ void __launch_bounds__(PACK_THREADS)
 pack_gt_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_off, int64_t row_pitch,
                int64_t n_rows, int32_t n_samples, uint64_t *__restrict__ planes, int32_t stride_words,
                uint8_t *__restrict__ status) {
-    extern __shared__ uint4 stage[];                 // row text, 16-byte granules
+    extern __shared__ uint4 stage[];                 // row text, 16-byte granules; then the row's packed image
     __shared__ int s_bad;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_warps = PACK_THREADS / 32;
     const int64_t row_bytes = 4ll * n_samples;
-    const int n_words_data = (2 * n_samples + 63) / 64;
+    uint8_t *outb = reinterpret_cast<uint8_t *>(stage + pack_text_granules(n_samples));      // [stride_words * 8]
+    const int out_bytes = stride_words * 8, n_quads = (n_samples + 3) / 4;
     for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
         const int64_t off = row_off ? row_off[r] : r * row_pitch;
         if (off < 0) {                               // a row without genotype text (ldx_store_ingest_vcf: malformed line): all reference
@@ -45,35 +39,41 @@ pack_gt_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row
             if (threadIdx.x == 0 && status) status[r] = 0;
             continue;                                // block-uniform
         }
-        const int64_t aligned = off & ~15ll;
-        const int skew = (int)(off - aligned);
-        const int n_gran = (int)((skew + row_bytes + 15) >> 4);
-        const uint4 *src = reinterpret_cast<const uint4 *>(text + aligned);
+        // staged word by word from the row's 4-byte-aligned start (coalesced 128-byte requests), so that sample 4b begins in word
+        // 4b of the staging area: the consumer's 16-byte shared-memory loads are aligned and free of bank conflicts
+        const int skew = (int)(off & 3);
+        const int n_words = (int)((skew + row_bytes + 3) >> 2) + 1;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(text + (off - skew));
+        uint32_t *stage32 = reinterpret_cast<uint32_t *>(stage);
         if (threadIdx.x == 0) s_bad = 0;
-        for (int g = threadIdx.x; g < n_gran; g += PACK_THREADS) stage[g] = ldg_u4_stream(src + g);
+        for (int g = threadIdx.x; g < n_words; g += PACK_THREADS) stage32[g] = __ldcs(src + g);
         __syncthreads();
-        const uint8_t *row = reinterpret_cast<const uint8_t *>(stage) + skew;
-        uint64_t *out = planes + r * (int64_t)stride_words;
-        int bad = 0;
-        for (int w = warp; w < stride_words; w += n_warps) {
-            uint64_t word = 0;
-            if (w < n_words_data) {
-                const int s = w * 32 + lane;
-                uint32_t a0 = 0, a1 = 0;
-                if (s < n_samples) {
-                    const uint8_t c0 = row[4 * s], sep = row[4 * s + 1], c1 = row[4 * s + 2];
-                    a0 = c0 == '1'; a1 = c1 == '1';
-                    bad |= (c0 != '0' && c0 != '1') || (c1 != '0' && c1 != '1') || sep != '|';
+        const uint32_t *w32 = stage32;
+        const int q8 = skew * 8;
+        uint32_t bad = 0;
+        for (int b = threadIdx.x; b < out_bytes; b += PACK_THREADS) {
+            uint32_t byte = 0;
+            if (b < n_quads) {
+                const uint32_t *p = w32 + 4 * b;     // (the words past the row's end are slack of the staging area: masked below)
+                const uint4 x03 = *reinterpret_cast<const uint4 *>(p);
+                const uint32_t x0 = x03.x, x1 = x03.y, x2 = x03.z, x3 = x03.w, x4 = p[4];
+                const uint32_t v[4] = {__funnelshift_r(x0, x1, q8), __funnelshift_r(x1, x2, q8), __funnelshift_r(x2, x3, q8), __funnelshift_r(x3, x4, q8)};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t x = (v[j] ^ 0x00307c30u) & 0x00ffffffu;          // "0|0" -> 0: byte 0 / byte 2 = allele ^ '0', byte 1 = separator ^ '|'
+                    if (4 * b + j < n_samples) {
+                        bad |= x & 0x00fefffeu;
+                        byte |= (((x & 0xffu) == 1u ? 1u : 0u) | ((x >> 16) == 1u ? 2u : 0u)) << (2 * j);
+                    }
                 }
-                const uint32_t b0 = __ballot_sync(0xffffffffu, a0);
-                const uint32_t b1 = __ballot_sync(0xffffffffu, a1);
-                word = spread_bits(b0) | (spread_bits(b1) << 1);
             }
-            if (lane == 0) out[w] = word;            // pad words are written as zero
+            outb[b] = (uint8_t)byte;                 // pad bytes of the row are written as zero
         }
-        if (bad) atomicOr(&s_bad, 1);
+        if (__any_sync(0xffffffffu, bad != 0) && (threadIdx.x & 31) == 0) atomicOr(&s_bad, 1);
         __syncthreads();
-        if (threadIdx.x == 0 && status) status[r] = (uint8_t)s_bad;
+        uint64_t *out = planes + r * (int64_t)stride_words;
+        for (int w = threadIdx.x; w < stride_words; w += PACK_THREADS) out[w] = reinterpret_cast<const uint64_t *>(outb)[w];
+        if (threadIdx.x == 0 && status) status[r] = (uint8_t)(s_bad ? 1 : 0);
         __syncthreads();
     }
 }
@@ -82,15 +82,17 @@ int launch_pack_gt(ldx_ctx *ctx, const uint8_t *d_text, const int64_t *d_row_off
                    int64_t n_rows, int32_t n_samples, uint64_t *d_planes_first, int32_t stride_words,
                    uint8_t *d_status) {
     if (n_rows <= 0) return LDX_OK;
-    const size_t smem = ((size_t)4 * n_samples + 15 + 16) / 16 * 16 + 16;
+    const size_t smem = (size_t)pack_text_granules(n_samples) * 16 + (size_t)stride_words * 8;
     if (smem > 200 * 1024) return set_error(LDX_ERR_ARG, "pack_gt: row too long for shared memory");
     if (smem > 48 * 1024)
         LDX_CUDA(cudaFuncSetAttribute(pack_gt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t want = (int64_t)ctx->sm_count * 8;
     const int grid = (int)(n_rows < want ? n_rows : want);
+    timing_begin(ctx);
     pack_gt_kernel<<<grid, PACK_THREADS, smem, ctx->stream>>>(d_text, d_row_off, row_pitch, n_rows,
                                                                n_samples, d_planes_first, stride_words,
                                                                d_status);
+    timing_end(ctx);
     ctx->launches++;
     LDX_CUDA(cudaGetLastError());
     return LDX_OK;

@@ -7,9 +7,10 @@ cli/ld_triangle_cli_en.py:40-74 and cli/ld_lite_cli_en.py:37-49, so an existing 
     python -m ld_tools_b200 ld_area -S src -D intgen -f -w 500000 -z 0.8 -e eur
 
 -f (skip the download/verification of 1000 Genomes data) is accepted and implied: the network path of
-prep_intgen_data.py is out of scope (the upstream data is gone, reference README.md:1-2).  -p is accepted
-and ignored: one GPU call per chromosome replaces the per-file process pool.  ld_triangle writes the
-table output (-o table|both); the Plotly heatmap is out of scope.
+prep_intgen_data.py is out of scope (the upstream data is gone, reference README.md:1-2).  -p, the reference's
+number of parallel processes over source files, is the number of GPUs to fan the job's tables / matrices out to
+(at most those present; one worker thread and one context per GPU).  ld_triangle writes the table output
+(-o table|both); the Plotly heatmap is out of scope.
 """
 import argparse
 import datetime
@@ -52,14 +53,19 @@ def main(argv=None):
     common(li, with_src=False)
     args = ap.parse_args(argv)
     t0 = datetime.datetime.now()
+    devices = None
+    if args.tool != "ld_lite":
+        from .engine import device_count
+        n = min(max(args.max_proc_quan, 1), device_count())
+        devices = n if n > 1 else None
     if args.tool == "ld_area":
         drivers.ld_area(args.src_dir_path, args.intgen_dir_path, args.trg_top_dir_path, args.meta_lines_quan, args.gend_names,
-                        args.pop_names, args.flank_size, args.ld_thres_measure, args.ld_low_thres, args.trg_file_type)
+                        args.pop_names, args.flank_size, args.ld_thres_measure, args.ld_low_thres, args.trg_file_type, devices=devices)
     elif args.tool == "ld_triangle":
         if args.matrix_type == "heatmap":
             sys.exit("the Plotly heatmap output is out of scope of this engine: use -o table")
         drivers.ld_triangle(args.src_dir_path, args.intgen_dir_path, args.trg_top_dir_path, args.meta_lines_quan, args.gend_names,
-                            args.pop_names, args.ld_measure, args.ld_low_thres)
+                            args.pop_names, args.ld_measure, args.ld_low_thres, devices=devices)
     else:
         print(drivers.ld_lite(args.rs_id_1, args.rs_id_2, args.intgen_dir_path, args.gend_names, args.pop_names))
         return

@@ -58,13 +58,16 @@ pack_gt_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row
                 const uint4 x03 = *reinterpret_cast<const uint4 *>(p);
                 const uint32_t x0 = x03.x, x1 = x03.y, x2 = x03.z, x3 = x03.w, x4 = p[4];
                 const uint32_t v[4] = {__funnelshift_r(x0, x1, q8), __funnelshift_r(x1, x2, q8), __funnelshift_r(x2, x3, q8), __funnelshift_r(x3, x4, q8)};
+                // "0|0" -> 0: byte 0 / byte 2 = allele ^ '0', byte 1 = separator ^ '|'; a sample is plain iff nothing but bit 0 of bytes
+                // 0 and 2 is left.  (A row with any other sample is flagged and re-packed whole by the general kernel, so the bits
+                // taken from such a sample here do not matter.)
+                const int live = n_samples - 4 * b;          // >= 4 except in the row's last byte
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint32_t x = (v[j] ^ 0x00307c30u) & 0x00ffffffu;          // "0|0" -> 0: byte 0 / byte 2 = allele ^ '0', byte 1 = separator ^ '|'
-                    if (4 * b + j < n_samples) {
-                        bad |= x & 0x00fefffeu;
-                        byte |= (((x & 0xffu) == 1u ? 1u : 0u) | ((x >> 16) == 1u ? 2u : 0u)) << (2 * j);
-                    }
+                    uint32_t x = (v[j] ^ 0x00307c30u) & 0x00ffffffu;
+                    if (j >= live) x = 0;
+                    bad |= x & 0x00fefffeu;
+                    byte |= ((x & 1u) | ((x >> 15) & 2u)) << (2 * j);
                 }
             }
             outb[b] = (uint8_t)byte;                 // pad bytes of the row are written as zero

@@ -123,6 +123,13 @@ def _lib_text(lib, p, nbytes):
     return out
 
 
+def device_count():
+    """CUDA devices visible to the library (ldx_device_count): no context is created."""
+    n = C.c_int32()
+    check(_lib.load().ldx_device_count(C.byref(n)))
+    return n.value
+
+
 class HostText:
     """A .gz file inflated by the library (ldx_inflate_gz_file: BGZF blocks in parallel on all host cores).
     `.array` is a uint8 view of the C-owned text; it is released when this object goes away."""

@@ -458,3 +458,18 @@ def test_slab_ingest_of_the_file_equals_the_whole_text_ingest(data, data_x, ctx,
     cd = ChromData(ctx, path, cache=False)
     assert cd.rows.tobytes() == rows_w.tobytes() and cd._blob == blob_w.tobytes()
     cd.close()
+
+
+def test_command_line_front_end_writes_the_reference_tree(data, tmp_path, capsys):
+    """`python -m ld_tools_b200 ld_area ...` with the reference's own option letters (cli/ld_area_cli_en.py:36-60): the same
+    output tree as the function; -p picks the number of GPUs (1 here, or however many the box has)."""
+    from ld_tools_b200.__main__ import main
+    root, intgen, srcs = data
+    name, extra = dc.AREA_CASES[0]
+    main(["ld_area", "-S", srcs["area"], "-D", intgen, "-t", str(tmp_path), "-f", "-p", "2"] + extra)
+    assert "computation time" in capsys.readouterr().out
+    assert assert_same_tree(str(tmp_path), name) > 3
+    a, b = srcs["lite_pairs"][0]
+    main(["ld_lite", a, b, "-D", intgen, "-f"])
+    with open(os.path.join(GOLD, "lite_all", "pair0.txt")) as fh:
+        assert capsys.readouterr().out == fh.read()

@@ -201,7 +201,8 @@ int32_t ldx_store_ingest_vcf(ldx_ctx *ctx, const uint8_t *text, int64_t text_byt
  * indexed, parsed and packed on the GPU into the next rows of the store; the records and their fixed columns come back in
  * tables allocated by the library (*rows_out [*n_rows_out], *blob_out, *blob_off_out [*n_rows_out + 1]: as ldx_store_ingest_vcf /
  * ldx_vcf_copy_prefixes give them; line_off is file-wide; release each with ldx_free_host).  *text_bytes_out (may be NULL) = the
- * size of the decompressed text.  A plain gzip file (no block table) is read at once. */
+ * size of the decompressed text.  A plain gzip file (no block table) is read at once.  A slab smaller than a BGZF member or than
+ * a line grows to what the step needs (a line of more than 1 GiB is an error). */
 int32_t ldx_store_ingest_vcf_file(ldx_ctx *ctx, const char *path, int32_t n_samples, int64_t slab_bytes, int32_t threads,
                                   ldx_store **store_out, ldx_vcf_row **rows_out, int64_t *n_rows_out, uint8_t **blob_out,
                                   int64_t **blob_off_out, int64_t *text_bytes_out);

@@ -397,7 +397,7 @@ extern "C" int32_t ldx_store_ingest_vcf_file(ldx_ctx *ctx, const char *path, int
         rc = ldx_store_create(ctx, n_max, 2 * n_samples, &s);
         if (rc == LDX_OK) rc = store_alloc_annotations(s);
         uint8_t *h_slab = nullptr;
-        const size_t slab_cap = (size_t)slab_bytes + (1u << 16) + 64;                 // + one member + the final newline
+        size_t slab_cap = (size_t)slab_bytes + (1u << 16) + 64;                       // + one member + the final newline
         if (rc == LDX_OK && cudaMallocHost((void **)&h_slab, slab_cap) != cudaSuccess) { cudaGetLastError(); rc = set_error(LDX_ERR_NOMEM, "vcf ingest: pinned slab buffer"); }
         int64_t carry = 0, row_base = 0, text_base = 0;               // text_base: file-wide offset of h_slab[0]
         size_t m = 0;
@@ -406,13 +406,23 @@ extern "C" int32_t ldx_store_ingest_vcf_file(ldx_ctx *ctx, const char *path, int
             size_t e = m;
             int64_t fill = carry;
             while (e < members.size() && fill + (int64_t)members[e].out_len <= (int64_t)slab_bytes) fill += (int64_t)members[e++].out_len;
-            if (e == m && m < members.size()) { rc = set_error(LDX_ERR_DATA, "vcf ingest: a line longer than the slab"); break; }
+            if (e == m && m < members.size()) {
+                // not even one more member fits behind the carried-over text (a slab smaller than a member, or a line longer than
+                // the slab): the buffer grows to what this step needs, up to 1 GiB of text without a newline
+                const int64_t need = carry + (int64_t)members[m].out_len;
+                if (need > ((int64_t)1 << 30)) { rc = set_error(LDX_ERR_DATA, "vcf ingest: a line longer than 1 GiB"); break; }
+                uint8_t *bigger = nullptr;
+                if (cudaMallocHost((void **)&bigger, (size_t)need + (1u << 16) + 64) != cudaSuccess) { cudaGetLastError(); rc = set_error(LDX_ERR_NOMEM, "vcf ingest: pinned slab buffer"); break; }
+                if (carry > 0) std::memcpy(bigger, h_slab, (size_t)carry);
+                cudaFreeHost(h_slab);
+                h_slab = bigger; slab_cap = (size_t)need + (1u << 16) + 64; slab_bytes = need;
+                continue;
+            }
             if (!bgzf_inflate_range(in.data(), members, m, e, h_slab + carry, threads)) { rc = set_error(LDX_ERR_ARG, "inflate: corrupt BGZF block (deflate error or CRC mismatch)"); break; }
             const bool last = e == members.size();
             int64_t cut = fill;
             if (!last) {
-                while (cut > 0 && h_slab[cut - 1] != '\n') --cut;     // whole lines only; the rest is carried over
-                if (cut == 0) { rc = set_error(LDX_ERR_DATA, "vcf ingest: a line longer than the slab"); break; }
+                while (cut > 0 && h_slab[cut - 1] != '\n') --cut;     // whole lines only; the rest is carried over (cut == 0: all of it)
             }
             if (cut > 0) {
                 const size_t before = rows.size();

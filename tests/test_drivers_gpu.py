@@ -473,3 +473,58 @@ def test_command_line_front_end_writes_the_reference_tree(data, tmp_path, capsys
     main(["ld_lite", a, b, "-D", intgen, "-f"])
     with open(os.path.join(GOLD, "lite_all", "pair0.txt")) as fh:
         assert capsys.readouterr().out == fh.read()
+
+
+def test_slab_ingest_edge_cases(data, ctx, tmp_path):
+    """ldx_store_ingest_vcf_file at its edges: a file with no record, a last line without its newline, a plain (non-BGZF) gzip
+    file, CRLF line ends, and a slab smaller than a BGZF member or a line (the buffer grows)."""
+    import gzip
+    import numpy as np
+    from ld_tools_b200 import Store
+    from ld_tools_b200.synth import BgzfWriter
+    root, intgen, srcs = data
+    with gzip.open(os.path.join(intgen, "22.vcf.gz"), "rb") as fh:
+        raw = fh.read()
+    lines = raw.split(b"\n")
+    n_samples = len([ln for ln in lines if ln.startswith(b"#CHROM")][0].split(b"\t")) - 9
+    header = b"\n".join(ln for ln in lines if ln.startswith(b"#")) + b"\n"
+    body = [ln for ln in lines if ln and not ln.startswith(b"#")]
+
+    def write(name, text, bgzf=True):
+        path = str(tmp_path / name)
+        if bgzf:
+            with BgzfWriter(path) as fh:
+                fh.write(text)
+        else:
+            with gzip.open(path, "wb") as fh:
+                fh.write(text)
+        return path
+
+    whole, rows_w = Store.ingest_vcf(ctx, raw, n_samples)
+    planes_w = whole.download()
+    # no record at all
+    st, rows, blob, off, n_text = Store.ingest_vcf_file(ctx, write("empty.vcf.gz", header), n_samples)
+    assert st.n_variants == 0 and len(rows) == 0 and off.tolist() == [0] and n_text == len(header)
+    st.close()
+    # the last line without its newline; small slabs
+    text = header + b"\n".join(body)
+    st, rows, blob, off, n_text = Store.ingest_vcf_file(ctx, write("nonl.vcf.gz", text), n_samples, slab_bytes=5000)
+    assert st.n_variants == len(body) == whole.n_variants and (st.download() == planes_w).all() and n_text == len(text)
+    assert (rows["pos"] == rows_w["pos"]).all() and (rows["status"] == rows_w["status"]).all()
+    st.close()
+    # a plain gzip stream (no block table): read at once, same store
+    st, rows, blob, off, n_text = Store.ingest_vcf_file(ctx, write("plain.vcf.gz", raw, bgzf=False), n_samples, slab_bytes=5000)
+    assert st.n_variants == whole.n_variants and (st.download() == planes_w).all() and rows.tobytes() == rows_w.tobytes()
+    st.close()
+    # CRLF line ends
+    crlf = raw.replace(b"\n", b"\r\n")
+    st, rows, blob, off, n_text = Store.ingest_vcf_file(ctx, write("crlf.vcf.gz", crlf), n_samples, slab_bytes=7000)
+    assert st.n_variants == whole.n_variants and (st.download() == planes_w).all() and (rows["pos"] == rows_w["pos"]).all()
+    assert (rows["ref_len"] == rows_w["ref_len"]).all() and (rows["eligible"] == rows_w["eligible"]).all()
+    st.close()
+    # a slab smaller than a BGZF member and than a record line: the buffer grows to what a step needs
+    wide = header + b"\n".join(b + b"\t" + b"0|0\t" * 4000 for b in body[:3]) + b"\n"            # ~16 KB lines
+    st, rows, blob, off, n_text = Store.ingest_vcf_file(ctx, write("wide.vcf.gz", wide), n_samples, slab_bytes=4096)
+    assert st.n_variants == 3 and (st.download() == planes_w[:3]).all() and n_text == len(wide)
+    st.close()
+    whole.close()

@@ -66,6 +66,31 @@ def create_src_dict(src_dir_path, src_file_name, meta_lines_quan, convdb_path):
     return out
 
 
+def _reference_helpers():
+    """The reference's own backend/get_sample_names.py and backend/create_src_dict.py when its tree is importable (on sys.path,
+    or named by LD_TOOLS_REFERENCE): these two stay as they are in the reference, so the drivers prefer
+    the originals and keep the restatements above as the fallback.  -> (get_sample_names, create_src_dict)."""
+    import importlib
+    import sys
+    ref = os.environ.get("LD_TOOLS_REFERENCE")
+    added = False
+    try:
+        if ref and os.path.isfile(os.path.join(ref, "backend", "calc_ld.py")) and ref not in sys.path:
+            sys.path.insert(0, ref)
+            added = True
+        g = importlib.import_module("backend.get_sample_names")
+        c = importlib.import_module("backend.create_src_dict")
+        here = os.path.dirname(os.path.abspath(g.__file__))
+        if os.path.isfile(os.path.join(here, "calc_ld.py")) and os.path.dirname(os.path.abspath(c.__file__)) == here:
+            return g.get_sample_names, c.create_src_dict
+    except Exception:                                   # no such package, or somebody else's `backend`
+        pass
+    finally:
+        if added:
+            sys.path.remove(ref)
+    return get_sample_names, create_src_dict
+
+
 def gender_tuple(gend_names):
     """ld_area.py:47-52."""
     return ("male",) if gend_names == "male" else ("female",) if gend_names == "female" else ("male", "female")
@@ -353,7 +378,8 @@ def ld_area(src_dir_path, intgen_dir_path, trg_top_dir_path=None, meta_lines_qua
     trg_top = src_dir_path if trg_top_dir_path is None else os.path.normpath(trg_top_dir_path)
     convdb = os.path.join(intgen_dir_path, "conversion.db")
     gends, pops = gender_tuple(gend_names), tuple(pop_names.upper().split(","))
-    sample_names = get_sample_names(gends, pops, convdb)
+    ref_sample_names, ref_src_dict = _reference_helpers()
+    sample_names = ref_sample_names(gends, pops, convdb)
     ext = trg_file_type if trg_file_type in ("tsv", "json") else "txt"
     fmt = {"tsv": AREA_TSV, "json": AREA_JSON}.get(trg_file_type, AREA_RSIDS)
     meta_keys = ["chr", "gends", "pops", "each_flank", f"{ld_thres_measure}_thres"]
@@ -364,7 +390,7 @@ def ld_area(src_dir_path, intgen_dir_path, trg_top_dir_path=None, meta_lines_qua
     # ---- the tables of the job (host work: the source files and conversion.db), directories made as the reference makes them
     tables = []
     for src_file_name in os.listdir(src_dir_path):
-        data_by_chrs = create_src_dict(src_dir_path, src_file_name, meta_lines_quan, convdb)
+        data_by_chrs = ref_src_dict(src_dir_path, src_file_name, meta_lines_quan, convdb)
         trg_dir = os.path.join(trg_top, f"{src_file_name.rsplit('.', maxsplit=1)[0]}_in_LD")
         for chrom, var_rows in data_by_chrs.items():
             chr_dir = os.path.join(trg_dir, chrom)
@@ -459,14 +485,15 @@ def ld_triangle(src_dir_path, intgen_dir_path, trg_top_dir_path=None, meta_lines
     trg_top = src_dir_path if trg_top_dir_path is None else os.path.normpath(trg_top_dir_path)
     convdb = os.path.join(intgen_dir_path, "conversion.db")
     gends, pops = gender_tuple(gend_names), tuple(pop_names.upper().split(","))
-    sample_names = get_sample_names(gends, pops, convdb)
+    ref_sample_names, ref_src_dict = _reference_helpers()
+    sample_names = ref_sample_names(gends, pops, convdb)
     t_e4 = None if ld_low_thres is None else threshold_e4(ld_low_thres)
     devs = _device_list(devices)
     workers = [_Worker(d, ctx if k == 0 else None, intgen_dir_path, sample_names) for k, d in enumerate(devs)]
     tab = "\t"
     tables = []
     for src_file_name in os.listdir(src_dir_path):
-        data_by_chrs = create_src_dict(src_dir_path, src_file_name, meta_lines_quan, convdb)
+        data_by_chrs = ref_src_dict(src_dir_path, src_file_name, meta_lines_quan, convdb)
         base = src_file_name.rsplit(".", maxsplit=1)[0]
         trg_dir = os.path.join(trg_top, f"{base}_LD_matr")
         for chrom, var_rows in data_by_chrs.items():
@@ -623,7 +650,7 @@ def ld_lite(rs_id_1, rs_id_2, intgen_dir_path, gend_names="both", pop_names="all
     chrom, pos1, pos2 = info[0][0], info[0][1], info[1][1]
     cd = ChromData(ctx, os.path.join(intgen_dir_path, f"{chrom}.vcf.gz"))
     try:
-        cd.select_samples(get_sample_names(gender_tuple(gend_names), tuple(pop_names.upper().split(",")), convdb))
+        cd.select_samples(_reference_helpers()[0](gender_tuple(gend_names), tuple(pop_names.upper().split(",")), convdb))
         r1, r2 = cd.row_of(pos1, rs_id_1), cd.row_of(pos2, rs_id_2)
         out = cd.scan.pairs([r1], [r2], raw=False)
         w = out["packed"][0]

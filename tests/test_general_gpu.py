@@ -102,7 +102,7 @@ def store_from_rows(ctx, rows, n_samples, via="pack_gt"):
     return st, status
 
 
-@pytest.mark.parametrize("style,n_samples", [("autosome", 150), ("chrx", 97), ("chrx", 310)])
+@pytest.mark.parametrize("style,n_samples", [("autosome", 150), ("chrx", 97), ("chrx", 310), ("autosome", 700), ("chrx", 1100), ("autosome", 2504)])   # 128- / 256- / 384- / 640-byte rows
 def test_general_rows_all_kernels_equal_calc_ld_on_the_lists(ctx, style, n_samples):
     from ld_tools_b200._lib import TUNE_MMA_TILE_N
     from ld_tools_b200.engine import ENGINE_MMA, ENGINE_POPC, threshold_e4

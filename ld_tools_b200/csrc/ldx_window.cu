@@ -566,7 +566,7 @@ static void fill_window_args(ldx_store *s, WindowArgs &A, const int64_t *d_qrow,
     A.gen = s->n_nonsimple > 0 ? s->d_gen : nullptr;
 }
 
-bool window_mq_supported(const ldx_store *s) { const int ng = s->stride_words / 16; return ng == 1 || ng == 2 || ng == 5; }
+bool window_mq_supported(const ldx_store *s) { const int ng = s->stride_words / 16; return ng >= 1 && ng <= 5; }
 
 // d_blocks: MqBlock records, d_sorted: MqQuery records in sorted order (WindowMqBlock / WindowMqQuery on the host side);
 // d_next: one word of device scratch for the dynamic block counter
@@ -604,6 +604,8 @@ int launch_window_mq(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, c
     switch (A.stride_u4 / 8) {
         case 1: return launch_window_mq_ng<1>(ctx, A, blocks, n_blocks, ext, d_next, s->n_variants);
         case 2: return launch_window_mq_ng<2>(ctx, A, blocks, n_blocks, ext, d_next, s->n_variants);
+        case 3: return launch_window_mq_ng<3>(ctx, A, blocks, n_blocks, ext, d_next, s->n_variants);     // e.g. two super-populations gathered: 2049..3072 haplotypes
+        case 4: return launch_window_mq_ng<4>(ctx, A, blocks, n_blocks, ext, d_next, s->n_variants);
         case 5: return launch_window_mq_ng<5>(ctx, A, blocks, n_blocks, ext, d_next, s->n_variants);
         default: return set_error(LDX_ERR_STATE, "multi-query window kernel: unsupported row pitch");
     }

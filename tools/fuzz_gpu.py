@@ -45,7 +45,8 @@ def random_store(ctx, rng, n_var, n_hap):
 
 
 def fuzz_window(ctx, rng):
-    n_hap = int(rng.choice([int(rng.integers(2, 1025)), int(rng.integers(1025, 2049)), 5008, int(rng.integers(2, 300))]))
+    n_hap = int(rng.choice([int(rng.integers(2, 1025)), int(rng.integers(1025, 2049)), int(rng.integers(2049, 4097)), 5008, int(rng.integers(4097, 7000)),
+                            int(rng.integers(2, 300))]))
     n_var = int(rng.integers(50, 3000))
     st, planes, mask, sel = random_store(ctx, rng, n_var, n_hap)
     pos0 = np.sort(rng.integers(1000, 1000 + 40 * n_var, size=n_var)).astype(np.int32)

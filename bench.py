@@ -795,7 +795,7 @@ def leg_area(env, subset=True, steps=5, warmup=3):
     roof = {"bound": "int-alu/popc", "achieved": pps / 1e9, "peak": popc_peak_pairs / 1e9, "unit": "Gpairs/s",
             "frac": pps / popc_peak_pairs, "peak_source": f"148 SM x 16 POPC32/clk x {env.peaks['sm_max_mhz']:.0f} MHz / {popc32_per_pair} POPC32 per pair "
             "(SURVEY 8d; the carry-save adders move half (128-byte rows) to two thirds (640-byte rows) of the counting to the 64-lane ALU pipe, so frac may exceed 1)",
-            "kernel": "window_rows1_kernel (+ mq_extend_kernel, inside the timed pair)" if row_bytes == 128 else "window_mq_kernel", "kernel_ms": kern_s * 1e3, "kernel_launches_timed": int(dom_n),
+            "kernel": "window_rows1_kernel (+ mq_extend_kernel, inside the timed pair)" if row_bytes in (128, 256) else "window_mq_kernel (+ mq_extend_kernel)", "kernel_ms": kern_s * 1e3, "kernel_launches_timed": int(dom_n),
             "hbm_frac_if_every_pair_read_its_row": scanned * row_bytes / kern_s / 1e9 / env.peaks["hbm_gbs"],
             "hbm_frac_one_pass_over_the_store": st.n_variants * row_bytes / kern_s / 1e9 / env.peaks["hbm_gbs"],
             "traffic": ncu_traffic(["r02_ncu_full_window_rows1_configs2.txt"] if subset else ["r01_ncu_full_window_mq_configs2.txt"]),
@@ -959,6 +959,9 @@ def run_ours(args, rank, world, local_rank):
 
 def run_area(args, rank, world, local_rank):
     """--workload ld_area: configs[2] as the headline line (one chromosome per GPU: weak scaling)."""
+    global AREA_EUR_SAMPLES
+    if args.area_samples:
+        AREA_EUR_SAMPLES = args.area_samples
     env = Env(args, rank, world, local_rank)
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -998,6 +1001,7 @@ def main():
     ap.add_argument("--no-area", action="store_true", help="skip the ld_area (configs[2]) leg")
     ap.add_argument("--no-sharded", action="store_true", help="skip the sharded legs (configs[3] row ranges, configs[4] regions)")
     ap.add_argument("--area-full-store", action="store_true", help="--workload ld_area: scan the 640-byte rows under a mask instead of the subset store")
+    ap.add_argument("--area-samples", type=int, default=0, help="--workload ld_area: samples in the selection instead of the 503 of EUR (e.g. 661 = AFR: 256-byte rows)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

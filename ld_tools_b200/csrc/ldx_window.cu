@@ -354,14 +354,17 @@ __device__ __forceinline__ int popc_and_8(const uint4 &xa, const uint4 &xb, cons
     return __popc(l2) + __popc(xb.w & qb.w) + 2 * __popc(t) + 4 * __popc(f);
 }
 
+template <int NG>                                            // NG = 128-byte units per row (1: up to 1024 haplotypes, 2: up to 2048)
 __global__ void __launch_bounds__(WIN_THREADS, 2)
 window_rows1_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int64_t n_blocks, const MqQueryX *__restrict__ ext,
                     unsigned int *__restrict__ next_block, int64_t n_rows) {
-    __shared__ uint4 qs[2][RQ][8];
+    constexpr int GR = 8 * NG;                               // 16-byte granules per row
+    __shared__ uint4 qs[2][RQ][GR];
     __shared__ uint4 s_rec[2][RQ][3];                        // MqQueryX records
     __shared__ unsigned int s_j;
-    const int tid = threadIdx.x, k_pl = tid >> 3, g_pl = tid & 7;      // loader threads (tid < RQ * 8): granule g_pl of query k_pl
-    constexpr int PL = RQ * 8;
+    const int tid = threadIdx.x, k_pl = tid / GR, g_pl = tid % GR;     // loader threads (tid < RQ * GR): granule g_pl of query k_pl
+    constexpr int PL = RQ * GR;
+    static_assert(PL <= WIN_THREADS, "plane loaders");
     unsigned long long scanned_total = 0;
     for (;;) {
         if (tid == 0) s_j = atomicAdd(next_block, 1u);
@@ -374,9 +377,9 @@ window_rows1_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int6
         const int64_t row = blk.base + tid;
         const bool in_store = row < n_rows;
         const int64_t rc = in_store ? row : n_rows - 1;
-        uint4 x[8];
+        uint4 x[GR];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = ldg_u4(A.planes + rc * 8 + i);
+        for (int i = 0; i < GR; ++i) x[i] = ldg_u4(A.planes + rc * GR + i);
         const int32_t pos0 = A.pos0[rc], end0 = A.end0[rc], n1r = A.freq[rc].n1, row32 = (int32_t)row;
         const int64_t idn = A.idnum[rc];
         const bool elig = in_store && A.eligible[rc];
@@ -384,7 +387,7 @@ window_rows1_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int6
         int32_t qrow_next = 0;
         if (tid < PL) {
             const int32_t qrow0 = ext[min(blk.a + k_pl, blk.b - 1)].qrow;
-            const uint4 y = ldg_u4(A.planes + (int64_t)qrow0 * 8 + g_pl), m = __ldg(A.mask + g_pl);
+            const uint4 y = ldg_u4(A.planes + (int64_t)qrow0 * GR + g_pl), m = __ldg(A.mask + g_pl);
             qs[0][k_pl][g_pl] = make_uint4(y.x & m.x, y.y & m.y, y.z & m.z, y.w & m.w);
             qrow_next = ext[min(blk.a + RQ + k_pl, blk.b - 1)].qrow;
         }
@@ -398,7 +401,7 @@ window_rows1_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int6
             uint4 nx = make_uint4(0, 0, 0, 0), mk = nx, rec_next = nx;
             int32_t qrow_next2 = 0;
             if (more && tid < PL) {
-                nx = ldg_u4(A.planes + (int64_t)qrow_next * 8 + g_pl); mk = __ldg(A.mask + g_pl);
+                nx = ldg_u4(A.planes + (int64_t)qrow_next * GR + g_pl); mk = __ldg(A.mask + g_pl);
                 qrow_next2 = ext[min(q0 + 2 * RQ + k_pl, blk.b - 1)].qrow;
             }
             if (more && tid < RQ * 3) rec_next = __ldg(reinterpret_cast<const uint4 *>(ext + min(q0 + RQ + tid / 3, blk.b - 1)) + tid % 3);
@@ -408,7 +411,7 @@ window_rows1_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int6
                 const int k1 = two ? k + 1 : k;
                 int n11a = 0, n11b = 0;
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
+                for (int h = 0; h < 4 * NG; ++h) {
                     n11a += popc_and_8(x[2 * h], x[2 * h + 1], qs[cur][k][2 * h], qs[cur][k][2 * h + 1]);
                     n11b += popc_and_8(x[2 * h], x[2 * h + 1], qs[cur][k1][2 * h], qs[cur][k1][2 * h + 1]);
                 }
@@ -588,14 +591,17 @@ int launch_window_mq(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, c
     mq_extend_kernel<<<(unsigned)((n_sorted + 255) / 256), 256, 0, ctx->stream>>>(A, sorted, n_sorted, ext);
     ctx->launches++;
     LDX_LAUNCHED(ctx, "mq_extend_kernel");
-    if (A.stride_u4 == 8 && !rows1_off) {     // 128-byte rows: a thread per row
-        static int per_sm = 0;
-        if (!per_sm) {
-            LDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, window_rows1_kernel, WIN_THREADS, 0));
-            if (per_sm < 1) per_sm = 1;
+    if ((A.stride_u4 == 8 || A.stride_u4 == 16) && !rows1_off) {     // 128- and 256-byte rows: a thread per row
+        static int per_sm[2] = {0, 0};
+        const int w = A.stride_u4 == 16;
+        if (!per_sm[w]) {
+            if (w) LDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[w], window_rows1_kernel<2>, WIN_THREADS, 0));
+            else LDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[w], window_rows1_kernel<1>, WIN_THREADS, 0));
+            if (per_sm[w] < 1) per_sm[w] = 1;
         }
-        const int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count * per_sm, n_blocks);
-        window_rows1_kernel<<<(int)grid, WIN_THREADS, 0, ctx->stream>>>(A, blocks, n_blocks, ext, d_next, s->n_variants);
+        const int64_t grid = std::min<int64_t>((int64_t)ctx->sm_count * per_sm[w], n_blocks);
+        if (w) window_rows1_kernel<2><<<(int)grid, WIN_THREADS, 0, ctx->stream>>>(A, blocks, n_blocks, ext, d_next, s->n_variants);
+        else window_rows1_kernel<1><<<(int)grid, WIN_THREADS, 0, ctx->stream>>>(A, blocks, n_blocks, ext, d_next, s->n_variants);
         timing_end(ctx);
         ctx->launches++;
         LDX_LAUNCHED(ctx, "window_rows1_kernel");

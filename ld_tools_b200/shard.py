@@ -202,19 +202,22 @@ def gather_hits_tensor(local, group=None, ranks_own_ordered_query_ranges=False):
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     local = local.reshape(-1, 4).contiguous()
+    work = None
+    if world > 1:                                           # the counts travel while this rank sorts its records
+        n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        counts_t = torch.empty(world, dtype=torch.int64, device=local.device)
+        work = dist.all_gather_into_tensor(counts_t, n, group=group, async_op=True)
     if local.shape[0] > 1:
         local = local[torch.argsort((local[:, 0].to(torch.int64) << 32) | local[:, 1].to(torch.int64))]
     if world > 1:
-        n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-        counts = [torch.zeros_like(n) for _ in range(world)]
-        dist.all_gather(counts, n, group=group)
-        counts = torch.cat(counts).tolist()                    # the one host synchronisation of the gather
+        work.wait()
+        counts = counts_t.tolist()                             # the one host synchronisation of the gather
         cap = max(max(counts), 1)
         buf = torch.zeros((cap, 4), dtype=torch.int32, device=local.device)
         buf[:local.shape[0]] = local
-        parts = [torch.empty_like(buf) for _ in range(world)]
-        dist.all_gather(parts, buf, group=group)
-        allh = torch.cat([p[:c] for p, c in zip(parts, counts)])
+        parts = torch.empty((world * cap, 4), dtype=torch.int32, device=local.device)      # rank r's records at rows r * cap ...
+        dist.all_gather_into_tensor(parts, buf, group=group)
+        allh = torch.cat([parts[r * cap:r * cap + c] for r, c in enumerate(counts)])
         if not ranks_own_ordered_query_ranges:
             allh = allh[torch.argsort((allh[:, 0].to(torch.int64) << 32) | allh[:, 1].to(torch.int64))]
     else:

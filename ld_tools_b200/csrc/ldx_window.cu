@@ -74,9 +74,28 @@ __device__ __forceinline__ bool screen_below(int32_t n11, int32_t N, int32_t n1a
 // threshold, and the warp-aggregated append of the kept pair.  Every thread of the warp must call it.
 // The tail of a candidate pair that passed the filters (`scan`): general route or screen + exact finalisation, the rounded
 // threshold, and the warp-aggregated append.  n1q / n1r: VarFreq.n1 of the query and of the row.  Every thread of the warp calls it.
-template <typename Counter>
+// The r2 screen with the variants' halves of the denominator prepared beforehand: qa = 10^4 / (n1a * n0a) comes with the query's
+// record, rb = 1 / (n1b * n0b) is formed once per block by the thread that owns the row (0 for a monomorphic variant: x = 0, the
+// pair is dropped, as calc_ld's int 0 is below any positive threshold).  x = (Dn * Dn) * (qa * rb): two IMAD, one conversion,
+// three multiplications -- no reciprocal and no second conversion per pair.  Relative error: two rcp.approx (2^-23 each), the
+// roundings of 10^4 * rcp, qa * rb, Dn * Dn, the final product and of Dn itself (twice) = 10 * 2^-24, inside the same 12 * 2^-24
+// bound as screen_below.
+__device__ __forceinline__ bool screen_below_r2_pre(int32_t n11, int32_t N, int32_t n1a, int32_t n1b, float qa, float rb, float t_minus, float g) {
+    const float fD = __int2float_rn(n11 * N - n1a * n1b);
+    const float x = __fmul_rn(__fmul_rn(fD, fD), __fmul_rn(qa, rb));
+    return __fadd_rn(x, __fmaf_rn(x, 12.0f * 5.9604644775390625e-08f, g)) < t_minus;      // false for NaN: falls to the exact path
+}
+__device__ __forceinline__ float half_denominator_rcp(int32_t n1, int32_t N, float scale) {
+    const int32_t d = n1 * (N - n1);
+    if (n1 < 0 || d <= 0) return 0.0f;              // a general-route code or a monomorphic variant
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__int2float_rn(d)));
+    return __fmul_rn(scale, r);
+}
+
+template <bool PRE = false, typename Counter>
 __device__ __forceinline__ void pair_tail(const WindowArgs &A, int64_t q, int64_t qrow, int64_t row, bool scan, int n11_in, int32_t n1q, int32_t n1r,
-                                          int tid, Counter &scanned) {
+                                          int tid, Counter &scanned, float qa = 0.0f, float rb = 0.0f) {
     int n11 = n11_in;
     bool pass = false;
     uint32_t packed = 0;
@@ -91,7 +110,8 @@ __device__ __forceinline__ void pair_tail(const WindowArgs &A, int64_t q, int64_
             int32_t m = measure_e4(packed, A.measure);
             if (A.measure == LDX_MEASURE_R2 && (packed & LDX_R2_NEARTIE)) ++m;
             pass = m >= A.thres_e4;
-        } else if (!(A.screen_t > 0.0f && screen_below(n11, A.n_sel, n1q, n1r, A.measure, A.screen_t, A.screen_g))) {
+        } else if (!(A.screen_t > 0.0f && (PRE && A.measure == LDX_MEASURE_R2 ? screen_below_r2_pre(n11, A.n_sel, n1q, n1r, qa, rb, A.screen_t, A.screen_g)
+                                                                               : screen_below(n11, A.n_sel, n1q, n1r, A.measure, A.screen_t, A.screen_g)))) {
             const VarFreq fa = A.freq[qrow], fb = A.freq[row];         // var_1 = query, var_2 = row (:242)
             const PairFinal f = finalise_pair(n11, fa, fb, A.fc);
             packed = f.packed;
@@ -222,7 +242,8 @@ __global__ void mq_extend_kernel(const WindowArgs A, const MqQuery *__restrict__
     const MqQuery m = sorted[i];
     MqQueryX x;
     x.idnum = A.idnum[m.qrow]; x.q = (int32_t)m.q; x.qrow = (int32_t)m.qrow; x.lo = (int32_t)m.lo; x.hi = (int32_t)m.hi;
-    x.ws = A.win_start[m.q]; x.we = A.win_end[m.q]; x.n1 = A.freq[m.qrow].n1; x.pad[0] = x.pad[1] = x.pad[2] = 0;
+    x.ws = A.win_start[m.q]; x.we = A.win_end[m.q]; x.n1 = A.freq[m.qrow].n1; x.pad[1] = x.pad[2] = 0;
+    x.pad[0] = __float_as_int(half_denominator_rcp(x.n1, A.n_sel, 1.0e4f));      // the query's half of the r2 screen (screen_below_r2_pre)
     out[i] = x;
 }
 
@@ -254,6 +275,7 @@ window_mq_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int64_t
         const int32_t pos0 = A.pos0[rc], end0 = A.end0[rc], n1r = A.freq[rc].n1, row32 = (int32_t)row;
         const int64_t idn = A.idnum[rc];
         const bool elig = in_store && A.eligible[rc];
+        const float rb = half_denominator_rcp(n1r, A.n_sel, 1.0f);
         // ---- the block's first group, synchronously; the store row of the second group's plane granule for later
         if (tid < MQ * 3) s_rec[0][tid / 3][tid % 3] = __ldg(reinterpret_cast<const uint4 *>(sorted + min(blk.a + tid / 3, blk.b - 1)) + tid % 3);
         int64_t qrow_next = 0;
@@ -313,12 +335,13 @@ window_mq_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int64_t
                 if (k < nq) {                               // block-uniform
                     const int n11 = transpose_reduce8(cnt[k], lane8);
                     const uint4 r0 = s_rec[cur][k][0], r1 = s_rec[cur][k][1];           // {idnum lo, hi, q, qrow} {lo, hi, ws, we}
-                    const int32_t n1q = (int32_t)s_rec[cur][k][2].x;
+                    const uint4 r2 = s_rec[cur][k][2];                                  // {n1, qa, -, -}
+                    const int32_t n1q = (int32_t)r2.x;
                     const int64_t idq = (int64_t)(((unsigned long long)r0.y << 32) | r0.x);
                     const bool scan = row32 >= (int32_t)r1.x && row32 < (int32_t)r1.y       // the query's candidate range
                                       && pos0 < (int32_t)r1.w && end0 > (int32_t)r1.z       // fetch overlap, ld_area.py:215-217
                                       && elig && idn != idq;                                // :223-224, :222
-                    pair_tail(A, (int64_t)(int32_t)r0.z, (int64_t)(int32_t)r0.w, row, scan, n11, n1q, n1r, tid, scanned);
+                    pair_tail<true>(A, (int64_t)(int32_t)r0.z, (int64_t)(int32_t)r0.w, row, scan, n11, n1q, n1r, tid, scanned, __uint_as_float(r2.y), rb);
                 }
             }
             if (more) {
@@ -383,6 +406,7 @@ window_rows1_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int6
         const int32_t pos0 = A.pos0[rc], end0 = A.end0[rc], n1r = A.freq[rc].n1, row32 = (int32_t)row;
         const int64_t idn = A.idnum[rc];
         const bool elig = in_store && A.eligible[rc];
+        const float rb = half_denominator_rcp(n1r, A.n_sel, 1.0f);
         // ---- the block's first group of queries, synchronously; the store row of the second group's plane granule for later
         int32_t qrow_next = 0;
         if (tid < PL) {
@@ -420,12 +444,13 @@ window_rows1_kernel(const WindowArgs A, const MqBlock *__restrict__ blocks, int6
                     if (u == 1 && !two) break;
                     const int kk = u ? k1 : k;
                     const uint4 r0 = s_rec[cur][kk][0], r1 = s_rec[cur][kk][1];        // {idnum lo, hi, q, qrow} {lo, hi, ws, we}
-                    const int32_t n1q = (int32_t)s_rec[cur][kk][2].x;
+                    const uint4 r2 = s_rec[cur][kk][2];                                 // {n1, qa, -, -}
+                    const int32_t n1q = (int32_t)r2.x;
                     const int64_t idq = (int64_t)(((unsigned long long)r0.y << 32) | r0.x);
                     const bool scan = row32 >= (int32_t)r1.x && row32 < (int32_t)r1.y       // the query's candidate range
                                       && pos0 < (int32_t)r1.w && end0 > (int32_t)r1.z       // fetch overlap, ld_area.py:215-217
                                       && elig && idn != idq;                                // :223-224, :222
-                    pair_tail(A, (int64_t)(int32_t)r0.z, (int64_t)(int32_t)r0.w, row, scan, u ? n11b : n11a, n1q, n1r, tid, scanned);
+                    pair_tail<true>(A, (int64_t)(int32_t)r0.z, (int64_t)(int32_t)r0.w, row, scan, u ? n11b : n11a, n1q, n1r, tid, scanned, __uint_as_float(r2.y), rb);
                 }
             }
             if (more) {

@@ -798,3 +798,34 @@ def test_triangle_table_is_triangle_plus_text(ctx, n_var, n_hap, measure, thres)
              for r0 in range(0, n_var, 256)]
     assert b"".join(parts) == want
     st.close()
+
+
+def test_async_upload_and_no_wait_mask_give_the_same_results(ctx):
+    """ldx_store_upload_async + ldx_store_set_mask (which no longer waits for its own copies) + a blocking result call, repeated
+    with changing planes and masks from pinned and pageable memory: every step's result is that step's input's -- nothing is
+    read from a staging buffer that a later call has already overwritten."""
+    import torch
+    from ld_tools_b200 import Store
+    from ld_tools_b200.synth import random_planes
+    n_var, n_hap = 700, 1500
+    st = Store(ctx, n_var, n_hap)
+    rows = np.arange(n_var, dtype=np.int64)
+    rng = np.random.default_rng(5)
+    pinned = torch.empty((n_var, st.stride_words), dtype=torch.int64).pin_memory()
+    for step in range(6):
+        planes = random_planes(n_var, n_hap, seed=100 + step)
+        sel = np.sort(rng.choice(n_hap, int(rng.integers(200, n_hap)), replace=False))
+        mask = ld_oracle.mask_from_haplotypes(sel, n_hap)
+        if step % 2 == 0:
+            pinned.numpy().view("<u8")[:] = planes
+            st.upload(0, pinned.numpy().view("<u8"), wait=False)
+        else:
+            st.upload(0, planes.copy(), wait=False)                      # pageable: staged by the runtime before the call returns
+        st.set_mask(mask)
+        st.set_mask(mask)                                                # twice in a row: the second waits for the first's staging
+        got = st.triangle_values(rows, "r_square")
+        want = ld_oracle.packed_of(ld_oracle.triangle(planes, mask, n_hap, rows))
+        assert (got == ((want & 0xBFFF) | ((want >> 16) & 0x4000)).astype(np.uint16)).all(), step
+        n1, _, n_sel = st.counts()
+        assert n_sel == len(sel) and (n1 == ld_oracle.variant_counts(planes, mask, n_hap)).all()
+    st.close()

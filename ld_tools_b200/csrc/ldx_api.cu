@@ -136,6 +136,7 @@ extern "C" int32_t ldx_destroy(ldx_ctx *ctx) {
     if (ctx->h_fix_count) cudaFreeHost(ctx->h_fix_count);
     if (ctx->h_mailbox) cudaFreeHost((void *)ctx->h_mailbox);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_lists) cudaFreeHost(ctx->h_lists);
     if (ctx->d_mma_ops) cudaFree(ctx->d_mma_ops);
     if (ctx->d_trace) cudaFree(ctx->d_trace);
     for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
@@ -432,11 +433,23 @@ extern "C" int32_t ldx_calc_ld_lists(ldx_ctx *ctx, const uint8_t *g_a, int64_t l
     const size_t off_b = ((size_t)len_a + 15) / 16 * 16;
     LDX_TRY(arena_get(ctx, S_TEXT, off_b + (size_t)len_b + 16, (void **)&d_buf));
     LDX_TRY(arena_get(ctx, S_MISC, sizeof(ldx_ld_result), (void **)&d_out));
-    LDX_CUDA(cudaMemcpyAsync(d_buf, g_a, (size_t)len_a, cudaMemcpyHostToDevice, ctx->stream));
-    LDX_CUDA(cudaMemcpyAsync(d_buf + off_b, g_b, (size_t)len_b, cudaMemcpyHostToDevice, ctx->stream));
+    // both lists travel as ONE copy from the context's pinned staging (two pageable copies cost a runtime staging pass each), the
+    // result comes back into it: a scalar call is two copies, one kernel and one wait
+    const size_t res_off = (off_b + (size_t)len_b + 63) / 64 * 64, need = res_off + sizeof(ldx_ld_result);
+    if (ctx->h_lists_bytes < need) {
+        if (ctx->h_lists) cudaFreeHost(ctx->h_lists);
+        ctx->h_lists = nullptr; ctx->h_lists_bytes = 0;
+        const size_t cap = std::max<size_t>(need * 2, (size_t)1 << 16);
+        LDX_CUDA(cudaMallocHost((void **)&ctx->h_lists, cap));
+        ctx->h_lists_bytes = cap;
+    }
+    std::memcpy(ctx->h_lists, g_a, (size_t)len_a);
+    std::memcpy(ctx->h_lists + off_b, g_b, (size_t)len_b);
+    LDX_CUDA(cudaMemcpyAsync(d_buf, ctx->h_lists, off_b + (size_t)len_b, cudaMemcpyHostToDevice, ctx->stream));
     LDX_TRY(launch_lists(ctx, d_buf, len_a, d_buf + off_b, len_b, d_out));
-    LDX_CUDA(cudaMemcpyAsync(out, d_out, sizeof(ldx_ld_result), cudaMemcpyDeviceToHost, ctx->stream));
+    LDX_CUDA(cudaMemcpyAsync(ctx->h_lists + res_off, d_out, sizeof(ldx_ld_result), cudaMemcpyDeviceToHost, ctx->stream));
     LDX_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(out, ctx->h_lists + res_off, sizeof(ldx_ld_result));
     if (out->r2_is_int0 == 2) {   // near a rounding tie: the reference's libm pow decides (calc_ld.py:87)
         const double N = (double)out->n_hap;
         const double pa = (double)out->n_a1 / N, qa = (double)out->n_a0 / N;

@@ -60,6 +60,8 @@ struct ldx_ctx {
     bool rows_cache_valid = false;
     unsigned long long *d_trace = nullptr;   // diagnostics: globaltimer stamps written by the tcgen05 kernel
     void *h_stage = nullptr;              // pinned bounce buffer of the store files (allocated on first use)
+    uint8_t *h_lists = nullptr;           // pinned staging of ldx_calc_ld_lists: both genotype lists in, the result out
+    size_t h_lists_bytes = 0;
     int window_mq = 1;                    // LDX_TUNE_WINDOW_MQ: 0 = ld_area scans always use the one-query-per-pass kernel
     int defer_cap = 0;                    // LDX_TUNE_DEFER_CAP: capacity of the deferred-pair lists (0 = sized from the pair count)
     int mma_min_v = 256;                  // ENGINE_AUTO uses the tcgen05 engine from this many variants

@@ -396,6 +396,7 @@ extern "C" int32_t ldx_store_ingest_vcf_file(ldx_ctx *ctx, const char *path, int
         const int64_t n_max = (int64_t)total / min_line + 16;
         rc = ldx_store_create(ctx, n_max, 2 * n_samples, &s);
         if (rc == LDX_OK) rc = store_alloc_annotations(s);
+        slab_bytes = std::min<int64_t>(slab_bytes, std::max<int64_t>((int64_t)total, 4096));       // a small file: a small pinned buffer
         uint8_t *h_slab = nullptr;
         size_t slab_cap = (size_t)slab_bytes + (1u << 16) + 64;                       // + one member + the final newline
         if (rc == LDX_OK && cudaMallocHost((void **)&h_slab, slab_cap) != cudaSuccess) { cudaGetLastError(); rc = set_error(LDX_ERR_NOMEM, "vcf ingest: pinned slab buffer"); }

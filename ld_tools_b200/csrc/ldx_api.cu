@@ -47,6 +47,7 @@ static int arena_get(ldx_ctx *ctx, int slot, size_t bytes, void **out) {
     Arena *a = arena_of(ctx);
     if (bytes == 0) bytes = 16;
     if (a->bytes[slot] < bytes) {
+        cudaSetDevice(ctx->device);                 // an allocation lands on the CURRENT device: a fresh host thread starts on device 0
         if (a->ptr[slot]) { cudaStreamSynchronize(ctx->stream); cudaFree(a->ptr[slot]); a->ptr[slot] = nullptr; a->bytes[slot] = 0; }
         const size_t want = bytes + bytes / 4 + 256;
         cudaError_t e = cudaMalloc(&a->ptr[slot], want);
@@ -245,6 +246,7 @@ extern "C" int32_t ldx_kernel_timing(ldx_ctx *ctx, int32_t enable, double *ms_ou
 }
 
 extern "C" int32_t ldx_synchronize(ldx_ctx *ctx) {
+    if (ctx) cudaSetDevice(ctx->device);
     LDX_REQUIRE(ctx, "ctx is NULL");
     LDX_CUDA(cudaStreamSynchronize(ctx->stream));
     return LDX_OK;
@@ -790,6 +792,7 @@ extern "C" int32_t ldx_store_row_counts(const ldx_store *s, int32_t *n1_out, int
 }
 
 extern "C" int32_t ldx_store_subset(const ldx_store *src, const int32_t *sel, int32_t n_sel, ldx_store **store_out) {
+    if (src) cudaSetDevice(src->ctx->device);        // a fresh host thread starts on device 0
     LDX_REQUIRE(src && sel && store_out, "NULL argument");
     LDX_REQUIRE(n_sel > 0, "empty selection");
     for (int32_t k = 0; k < n_sel; ++k) LDX_REQUIRE(sel[k] >= 0 && sel[k] < src->n_hap, "sel[] outside the source haplotypes");
@@ -1105,6 +1108,7 @@ extern "C" int32_t ldx_window_dev(ldx_store *s, const int64_t *q_row, const int6
                                   const int32_t *win_start, const int32_t *win_end, int64_t nq,
                                   int32_t measure, int32_t thres_e4, ldx_hit *dev_hits, int64_t cap,
                                   int64_t *dev_n_hits) {
+    if (s) cudaSetDevice(s->ctx->device);
     LDX_REQUIRE(measure == LDX_MEASURE_R2 || measure == LDX_MEASURE_DPRIME, "bad measure");
     LDX_REQUIRE(dev_hits && dev_n_hits && cap >= 0, "bad output arguments");
     LDX_REQUIRE((reinterpret_cast<uintptr_t>(dev_hits) & 15) == 0, "dev_hits must be 16-byte aligned");
@@ -1148,6 +1152,7 @@ extern "C" int32_t ldx_window_dev(ldx_store *s, const int64_t *q_row, const int6
 extern "C" int32_t ldx_window(ldx_store *s, const int64_t *q_row, const int64_t *lo, const int64_t *hi,
                               const int32_t *win_start, const int32_t *win_end, int64_t nq, int32_t measure,
                               int32_t thres_e4, ldx_hit *hits, int64_t cap, int64_t *n_hits, int64_t *n_scanned) {
+    if (s) cudaSetDevice(s->ctx->device);
     LDX_REQUIRE(n_hits && cap >= 0 && (hits || cap == 0), "bad output arguments");
     LDX_REQUIRE(s, "store is NULL");
     ldx_ctx *ctx = s->ctx;
@@ -1242,6 +1247,7 @@ static int stage_rows(ldx_ctx *ctx, const RowList *lists, int n, int64_t **d_row
 extern "C" int32_t ldx_triangle_rows_dev(ldx_store *s, const int64_t *rows, int64_t v, int64_t row_begin, int64_t row_end,
                                          int32_t measure, int32_t has_thres, int32_t thres_e4, int32_t engine,
                                          uint32_t *dev_packed, int32_t *dev_n11) {
+    if (s) cudaSetDevice(s->ctx->device);
     LDX_REQUIRE(measure == LDX_MEASURE_R2 || measure == LDX_MEASURE_DPRIME, "bad measure");
     LDX_REQUIRE(engine >= LDX_ENGINE_AUTO && engine <= LDX_ENGINE_MMA, "bad engine");
     LDX_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= v, "bad row range");
@@ -1277,6 +1283,7 @@ extern "C" int32_t ldx_triangle_rows_dev(ldx_store *s, const int64_t *rows, int6
 // launch, pipeline-fill and drain latencies; a batch of them keeps every SM busy across sets.
 extern "C" int32_t ldx_triangle_batch_dev(ldx_ctx *ctx, const ldx_triangle_set *sets, int32_t n_sets, int32_t measure,
                                           int32_t has_thres, int32_t thres_e4, int32_t engine) {
+    if (ctx) cudaSetDevice(ctx->device);
     LDX_REQUIRE(ctx && (sets || n_sets == 0) && n_sets >= 0, "bad set list");
     LDX_REQUIRE(measure == LDX_MEASURE_R2 || measure == LDX_MEASURE_DPRIME, "bad measure");
     LDX_REQUIRE(engine >= LDX_ENGINE_AUTO && engine <= LDX_ENGINE_MMA, "bad engine");
@@ -1331,6 +1338,7 @@ extern "C" int32_t ldx_triangle_dev(ldx_store *s, const int64_t *rows, int64_t v
 extern "C" int32_t ldx_triangle_rows(ldx_store *s, const int64_t *rows, int64_t v, int64_t row_begin, int64_t row_end,
                                      int32_t measure, int32_t has_thres, int32_t thres_e4, int32_t engine,
                                      uint32_t *packed, int32_t *n11) {
+    if (s) cudaSetDevice(s->ctx->device);
     LDX_REQUIRE(s, "store is NULL");
     LDX_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= v, "bad row range");
     ldx_ctx *ctx = s->ctx;
@@ -1386,6 +1394,7 @@ static inline uint16_t narrow_word(uint32_t w, int measure) {
 
 extern "C" int32_t ldx_triangle_values(ldx_store *s, const int64_t *rows, int64_t v, int64_t row_begin, int64_t row_end, int32_t measure,
                                        int32_t has_thres, int32_t thres_e4, int32_t engine, uint16_t *values) {
+    if (s) cudaSetDevice(s->ctx->device);
     LDX_REQUIRE(s && values, "NULL argument");
     LDX_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= v, "bad row range");
     ldx_ctx *ctx = s->ctx;
@@ -1489,6 +1498,7 @@ __global__ void __launch_bounds__(256) write_passing_kernel(const uint32_t *__re
 
 extern "C" int32_t ldx_triangle_hits(ldx_store *s, const int64_t *rows, int64_t v, int32_t measure, int32_t thres_e4, int32_t engine,
                                      ldx_pair_hit *hits, int64_t cap, int64_t *n_hits) {
+    if (s) cudaSetDevice(s->ctx->device);
     LDX_REQUIRE(s && n_hits && cap >= 0 && (hits || cap == 0), "bad argument");
     *n_hits = 0;
     ldx_ctx *ctx = s->ctx;
@@ -1556,6 +1566,7 @@ extern "C" int32_t ldx_triangle_table(ldx_store *s, const int64_t *rows, int64_t
                                       int32_t measure, int32_t has_thres, int32_t thres_e4, int32_t engine,
                                       const char *prefixes, const int64_t *prefix_off, int32_t flags,
                                       char *text, int64_t cap, int64_t *n_bytes) {
+    if (s) cudaSetDevice(s->ctx->device);
     LDX_REQUIRE(s && n_bytes, "NULL argument");
     *n_bytes = 0;
     LDX_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= v, "bad row range");

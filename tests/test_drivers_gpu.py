@@ -106,19 +106,21 @@ def test_ld_triangle_320_variants_through_the_tensor_core_engine(data, ctx, tmp_
 
 @pytest.mark.parametrize("name,extra", [dc.AREA_CASES[0], dc.AREA_CASES[1]])
 def test_ld_area_fan_out_over_devices_same_tree(data, tmp_path, name, extra):
-    """devices=[0, 0]: two workers (own contexts; on a multi-GPU box they would be two GPUs) share the job's tables by
+    """Two workers with their own contexts (two GPUs when the box has them, else twice device 0) share the job's tables by
     chromosome -- here one chromosome, two source files -- and, for a lone table, its queries in slabs.  Same output tree."""
     import shutil
     from ld_tools_b200 import drivers
+    from ld_tools_b200.engine import device_count
     root, intgen, srcs = data
     kw = parse(extra, "area")
-    drivers.ld_area(srcs["area"], intgen, trg_top_dir_path=str(tmp_path / "two"), devices=[0, 0], **kw)
+    second = 1 if device_count() > 1 else 0
+    drivers.ld_area(srcs["area"], intgen, trg_top_dir_path=str(tmp_path / "two"), devices=[0, second], **kw)
     assert_same_tree(str(tmp_path / "two"), name)
     # a lone table: region sharding of its queries over three workers
     one = tmp_path / "src_one"
     os.makedirs(one)
     shutil.copy(os.path.join(srcs["area"], "gwas_hits.tsv"), one)
-    drivers.ld_area(str(one), intgen, trg_top_dir_path=str(tmp_path / "slabs"), devices=[0, 0, 0], **kw)
+    drivers.ld_area(str(one), intgen, trg_top_dir_path=str(tmp_path / "slabs"), devices=[0, second, 0], **kw)
     want = {k: v for k, v in dc.read_tree(os.path.join(GOLD, name)).items() if k.startswith("gwas_hits_in_LD")}
     got = dc.read_tree(str(tmp_path / "slabs"))
     assert sorted(got) == sorted(want) and all(got[k] == want[k] for k in want)
@@ -152,7 +154,9 @@ def test_ld_triangle_batched_tables_and_shared_matrix(data, ctx, tmp_path, monke
     kw = parse(extra, "triangle")
     kw.pop("matrix_type")
     monkeypatch.setattr(drivers, "BATCH_MAX_VARIANTS", 100)
-    drivers.ld_triangle(srcs["triangle_big"], intgen, trg_top_dir_path=str(tmp_path / "shared"), devices=[0, 0, 0], **kw)
+    from ld_tools_b200.engine import device_count
+    second = 1 if device_count() > 1 else 0
+    drivers.ld_triangle(srcs["triangle_big"], intgen, trg_top_dir_path=str(tmp_path / "shared"), devices=[0, second, 0], **kw)
     assert assert_same_tree(str(tmp_path / "shared"), name) == 1
 
 
@@ -528,3 +532,70 @@ def test_slab_ingest_edge_cases(data, ctx, tmp_path):
     assert st.n_variants == 3 and (st.download() == planes_w[:3]).all() and n_text == len(wide)
     st.close()
     whole.close()
+
+
+def test_a_second_device_from_fresh_host_threads(data, tmp_path):
+    """Every library call selects its context's device itself: a host thread that has never touched CUDA starts on device 0, and
+    an allocation made there for a context of device 1 is unreadable from device 1.  Each call below runs in its OWN fresh thread
+    against a context on the last device of the box (skipped on a one-GPU box)."""
+    import threading
+    import numpy as np
+    from ld_tools_b200 import Context, Store, drivers
+    from ld_tools_b200.engine import device_count, threshold_e4
+    from ld_tools_b200.synth import random_planes
+    from oracle import ld_oracle
+    if device_count() < 2:
+        pytest.skip("needs two GPUs")
+    dev = device_count() - 1
+    state, errors = {}, []
+
+    def in_thread(fn):
+        def run():
+            try:
+                fn()
+            except BaseException as e:      # noqa: BLE001
+                errors.append(e)
+        t = threading.Thread(target=run)
+        t.start()
+        t.join()
+        if errors:
+            raise errors[0]
+
+    n_var, n_hap = 900, 1300
+    planes = random_planes(n_var, n_hap, seed=3)
+    sel = np.sort(np.random.default_rng(1).choice(n_hap, 600, replace=False))
+    mask = ld_oracle.mask_from_haplotypes(sel, n_hap)
+    rows = np.arange(n_var, dtype=np.int64)
+    want = ld_oracle.packed_of(ld_oracle.triangle(planes, mask, n_hap, rows))
+    in_thread(lambda: state.update(ctx=Context(dev)))
+    in_thread(lambda: state.update(st=Store.from_planes(state["ctx"], planes, n_hap)))
+    in_thread(lambda: state["st"].set_mask(mask))
+    in_thread(lambda: state.update(tri=state["st"].triangle(rows)[0]))
+    assert (state["tri"] == want).all()
+    in_thread(lambda: state.update(vals=state["st"].triangle_values(rows, "d_prime")))
+    assert (state["vals"] == (want >> 16).astype(np.uint16)).all()
+    in_thread(lambda: state.update(hits=state["st"].triangle_hits(rows, "r_square", threshold_e4(0.3))))
+    assert len(state["hits"]) == int(((want & 0x3FFF) >= 3000).sum())
+    in_thread(lambda: state.update(sub=state["st"].subset(sel)))
+    pos0 = (np.arange(n_var) * 20 + 50).astype(np.int32)
+
+    def scan():
+        sub = state["sub"]
+        sub.set_annotations(pos0, pos0 + 1, np.arange(n_var, dtype=np.int64), np.ones(n_var, np.uint8))
+        q = np.arange(10, n_var, 37, dtype=np.int64)
+        lo, hi = np.maximum(q - 100, 0), np.minimum(q + 100, n_var)
+        state["win"] = sub.window(q, lo, hi, np.zeros(len(q), np.int32), np.full(len(q), 2**31 - 1, np.int32), "r_square", 0)[0]
+        state["q"] = q
+    in_thread(scan)
+    k = 3
+    q = int(state["q"][k])
+    got = state["win"][state["win"]["query"] == k]
+    idx = [max(q, r) * (max(q, r) - 1) // 2 + min(q, r) for r in got["row"]]
+    assert got["row"].tolist() == [r for r in range(q - 100, q + 100) if r != q]           # threshold 0: every candidate but the query
+    assert ((got["packed"] & 0x3FFF) == (want[idx] & 0x3FFF)).all()                          # r2 is symmetric in the pair
+    # the drivers on that device alone
+    root, intgen, srcs = data
+    name, extra = dc.AREA_CASES[0]
+    in_thread(lambda: drivers.ld_area(srcs["area"], intgen, trg_top_dir_path=str(tmp_path), devices=[dev], **parse(extra, "area")))
+    assert assert_same_tree(str(tmp_path), name) > 3
+    in_thread(lambda: (state["sub"].close(), state["st"].close(), state["ctx"].close()))

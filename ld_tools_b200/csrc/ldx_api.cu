@@ -9,6 +9,8 @@
 #include <cstring>
 #include <new>
 
+#include <cub/cub.cuh>
+
 #include "ldx_internal.h"
 #include "ldx_fixup.cuh"
 
@@ -138,6 +140,8 @@ extern "C" int32_t ldx_destroy(ldx_ctx *ctx) {
     if (ctx->h_mailbox) cudaFreeHost((void *)ctx->h_mailbox);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_lists) cudaFreeHost(ctx->h_lists);
+    if (ctx->h_win) cudaFreeHost(ctx->h_win);
+    if (ctx->win_staged) cudaEventDestroy(ctx->win_staged);
     if (ctx->d_mma_ops) cudaFree(ctx->d_mma_ops);
     if (ctx->d_trace) cudaFree(ctx->d_trace);
     for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
@@ -1041,7 +1045,7 @@ static int stage_window(ldx_store *s, const int64_t *q_row, const int64_t *lo, c
     }
     *n_chunks_out = prefix[nq];
     *n_candidates_out = cand;
-    if (nq == 0) return LDX_OK;
+    if (nq == 0 || !d_arrays5) return LDX_OK;           // validation and counts only
     ldx_ctx *ctx = s->ctx;
     LDX_CUDA(cudaSetDevice(ctx->device));
     // one staging block: q_row | lo | hi | prefix (int64) | ws | we (int32)
@@ -1113,7 +1117,7 @@ extern "C" int32_t ldx_window_dev(ldx_store *s, const int64_t *q_row, const int6
     LDX_REQUIRE(dev_hits && dev_n_hits && cap >= 0, "bad output arguments");
     LDX_REQUIRE((reinterpret_cast<uintptr_t>(dev_hits) & 15) == 0, "dev_hits must be 16-byte aligned");
     int64_t *arr[6] = {}; int64_t n_chunks = 0, cand = 0;
-    LDX_TRY(stage_window(s, q_row, lo, hi, win_start, win_end, nq, arr, &n_chunks, &cand));
+    LDX_TRY(stage_window(s, q_row, lo, hi, win_start, win_end, nq, nullptr, &n_chunks, &cand));       // validation and counts only
     ldx_ctx *ctx = s->ctx;
     // dev_n_hits: [0] hits, [1] pairs scanned
     LDX_CUDA(cudaMemsetAsync(dev_n_hits, 0, 2 * sizeof(int64_t), ctx->stream));
@@ -1128,24 +1132,80 @@ extern "C" int32_t ldx_window_dev(ldx_store *s, const int64_t *q_row, const int6
                         n_items < 0x7fffffffll && n_items * WINDOW_MQ < 3 * n_chunks;   // else: the windows barely overlap
     LDX_TRY(begin_dev_call(ctx));
     if (use_mq) {
-        std::vector<WindowMqQuery> sorted(order.size());
-        for (size_t k = 0; k < order.size(); ++k) { const int32_t q = order[k]; sorted[k] = WindowMqQuery{q, q_row[q], lo[q], hi[q]}; }
+        // The work lists -- block records, then one 48-byte record per query in sorted order with everything the host knows about
+        // it -- are assembled in the context's pinned staging and travel as ONE copy; nothing waits for it (the event guards the
+        // staging against the next call).  The kernels read nothing else about the queries.
+        const size_t n_srt = order.size();
+        const size_t blk_bytes = (blocks.size() * sizeof(WindowMqBlock) + 15) & ~(size_t)15, rec_bytes = n_srt * sizeof(WindowMqQueryX);
+        const size_t total = blk_bytes + rec_bytes;
+        if (ctx->h_win_bytes < total) {
+            if (ctx->h_win) { cudaEventSynchronize(ctx->win_staged); cudaFreeHost(ctx->h_win); ctx->h_win = nullptr; ctx->h_win_bytes = 0; }
+            const size_t want = total + total / 2 + 4096;
+            LDX_CUDA(cudaMallocHost((void **)&ctx->h_win, want));
+            ctx->h_win_bytes = want;
+            if (!ctx->win_staged) LDX_CUDA(cudaEventCreateWithFlags(&ctx->win_staged, cudaEventDisableTiming));
+        } else LDX_CUDA(cudaEventSynchronize(ctx->win_staged));           // the previous call's copy has left the staging
+        std::memcpy(ctx->h_win, blocks.data(), blocks.size() * sizeof(WindowMqBlock));
+        WindowMqQueryX *rec = reinterpret_cast<WindowMqQueryX *>(ctx->h_win + blk_bytes);
+        for (size_t k = 0; k < n_srt; ++k) {
+            const int32_t q = order[k];
+            rec[k] = WindowMqQueryX{0, q, (int32_t)q_row[q], (int32_t)lo[q], (int32_t)hi[q], win_start[q], win_end[q], 0, {0, 0, 0}};
+        }
         uint8_t *blk;
-        const size_t blk_bytes = blocks.size() * sizeof(WindowMqBlock), srt_bytes = sorted.size() * sizeof(WindowMqQuery);
-        const size_t ext_off = (blk_bytes + srt_bytes + 64 + 15) & ~(size_t)15;
-        LDX_TRY(arena_get(ctx, S_IB, ext_off + sorted.size() * WINDOW_MQ_EXT_BYTES, (void **)&blk));
-        LDX_CUDA(cudaMemcpyAsync(blk, blocks.data(), blk_bytes, cudaMemcpyHostToDevice, ctx->stream));
-        LDX_CUDA(cudaMemcpyAsync(blk + blk_bytes, sorted.data(), srt_bytes, cudaMemcpyHostToDevice, ctx->stream));
-        LDX_CUDA(cudaStreamSynchronize(ctx->stream));   // blocks / sorted are locals
-        LDX_TRY(launch_window_mq(s, arr[0], arr[1], arr[2], (const int32_t *)arr[4], (const int32_t *)arr[5], nq, blk, (int64_t)blocks.size(),
-                                 blk + blk_bytes, (int64_t)sorted.size(), blk + ext_off, reinterpret_cast<unsigned int *>(blk + blk_bytes + srt_bytes),
+        LDX_TRY(arena_get(ctx, S_IB, total + 64, (void **)&blk));
+        LDX_CUDA(cudaMemcpyAsync(blk, ctx->h_win, total, cudaMemcpyHostToDevice, ctx->stream));
+        LDX_CUDA(cudaEventRecord(ctx->win_staged, ctx->stream));
+        LDX_TRY(launch_window_mq(s, nq, blk, (int64_t)blocks.size(), blk + blk_bytes, (int64_t)n_srt, reinterpret_cast<unsigned int *>(blk + total),
                                  measure, thres_e4, dev_hits, cap, reinterpret_cast<unsigned long long *>(dev_n_hits)));
-    } else
-    LDX_TRY(launch_window(s, arr[0], arr[1], arr[2], (const int32_t *)arr[4], (const int32_t *)arr[5], arr[3], nq,
-                          n_chunks, measure, thres_e4, dev_hits, cap, reinterpret_cast<unsigned long long *>(dev_n_hits)));
+    } else {
+        LDX_TRY(stage_window(s, q_row, lo, hi, win_start, win_end, nq, arr, &n_chunks, &cand));
+        LDX_TRY(launch_window(s, arr[0], arr[1], arr[2], (const int32_t *)arr[4], (const int32_t *)arr[5], arr[3], nq,
+                              n_chunks, measure, thres_e4, dev_hits, cap, reinterpret_cast<unsigned long long *>(dev_n_hits)));
+    }
     ++ctx->seq;
     LDX_TRY(launch_publish(ctx));
     end_dev_call(ctx, 2, dev_hits, s->fc.n_hap, measure, 1, thres_e4);
+    return LDX_OK;
+}
+
+__global__ void scatter_words_kernel(uint8_t *base, const uint64_t *__restrict__ byte_off, const uint32_t *__restrict__ words, size_t n);
+
+// The kept pairs leave the scan kernels in no particular order; the reference emits rows in VCF order per query (ld_area.py:215).
+// They are sorted by (query, row) ON THE DEVICE before they cross PCIe: keys (query << row_bits | row) with the hit's position as
+// the value through cub's radix sort (only the bits the keys use), then one gather.  3 x 10^7 kept pairs (configs[2] at -z 0) take
+// milliseconds instead of the seconds std::sort needs for them on one host core.
+__global__ void hit_keys_kernel(const ldx_hit *__restrict__ hits, int64_t n, int row_bits, uint64_t *__restrict__ keys, uint32_t *__restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 h = __ldg(reinterpret_cast<const uint4 *>(hits + i));          // {query, row, n11, packed}
+    keys[i] = ((uint64_t)h.x << row_bits) | (uint64_t)h.y;
+    idx[i] = (uint32_t)i;
+}
+__global__ void hit_gather_kernel(const ldx_hit *__restrict__ src, const uint32_t *__restrict__ idx, int64_t n, ldx_hit *__restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    *reinterpret_cast<uint4 *>(dst + i) = __ldg(reinterpret_cast<const uint4 *>(src + idx[i]));
+}
+static int sort_hits_on_device(ldx_ctx *ctx, const ldx_hit *d_hits, int64_t n, int64_t n_variants, int64_t nq, ldx_hit **d_sorted_out) {
+    int row_bits = 1, q_bits = 1;
+    while ((1ll << row_bits) < n_variants) ++row_bits;
+    while ((1ll << q_bits) < nq) ++q_bits;
+    uint64_t *d_keys; uint32_t *d_idx; ldx_hit *d_out; void *d_tmp;
+    LDX_TRY(arena_get(ctx, S_D, 2 * sizeof(uint64_t) * (size_t)n, (void **)&d_keys));
+    LDX_TRY(arena_get(ctx, S_DP, 2 * sizeof(uint32_t) * (size_t)n, (void **)&d_idx));
+    LDX_TRY(arena_get(ctx, S_N11, sizeof(ldx_hit) * (size_t)n, (void **)&d_out));
+    size_t tmp_bytes = 0;
+    cub::DoubleBuffer<uint64_t> kb(d_keys, d_keys + n);
+    cub::DoubleBuffer<uint32_t> vb(d_idx, d_idx + n);
+    LDX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, (int)n, 0, row_bits + q_bits, ctx->stream));
+    LDX_TRY(arena_get(ctx, S_R2, tmp_bytes + 16, &d_tmp));
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    hit_keys_kernel<<<grid, 256, 0, ctx->stream>>>(d_hits, n, row_bits, d_keys, d_idx);
+    LDX_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, kb, vb, (int)n, 0, row_bits + q_bits, ctx->stream));
+    hit_gather_kernel<<<grid, 256, 0, ctx->stream>>>(d_hits, vb.Current(), n, d_out);
+    ctx->launches += 2;
+    LDX_CUDA(cudaGetLastError());
+    *d_sorted_out = d_out;
     return LDX_OK;
 }
 
@@ -1175,22 +1235,47 @@ extern "C" int32_t ldx_window(ldx_store *s, const int64_t *q_row, const int64_t 
         return set_error(LDX_ERR_CAPACITY, "hit buffer too small");
     }
     const int64_t n = h_cnt[0];
-    if (n) LDX_CUDA(cudaMemcpyAsync(hits, d_hits, sizeof(ldx_hit) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    const bool device_sort = n >= 4096 && n < (1ll << 31);
+    if (n && !device_sort) LDX_CUDA(cudaMemcpyAsync(hits, d_hits, sizeof(ldx_hit) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     LDX_TRY(collect_fixups(ctx, recs));   // synchronises
-    for (const FixupRec &r : recs) {
-        const uint32_t w = settle_word(r, s->fc.n_hap, measure, 1, thres_e4);
-        hits[r.out_index & FIX_INDEX_MASK].packed = w;      // LDX_BELOW_THRES marks hits the exact rounding rejects
+    if (device_sort) {
+        // the settled words of the near-ties go to the device list first (a handful), then the list is sorted there
+        if (!recs.empty()) {
+            const size_t nr = recs.size();
+            std::vector<uint64_t> stage(nr + (nr + 1) / 2);
+            uint32_t *words = reinterpret_cast<uint32_t *>(stage.data() + nr);
+            for (size_t i = 0; i < nr; ++i) {
+                words[i] = settle_word(recs[i], s->fc.n_hap, measure, 1, thres_e4);
+                stage[i] = reinterpret_cast<uint64_t>(d_hits) + (recs[i].out_index & FIX_INDEX_MASK) * sizeof(ldx_hit) + offsetof(ldx_hit, packed);
+            }
+            uint64_t *d_stage;
+            LDX_TRY(arena_get(ctx, S_MISC, stage.size() * sizeof(uint64_t) + 64, (void **)&d_stage));
+            LDX_CUDA(cudaMemcpyAsync(d_stage, stage.data(), stage.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+            scatter_words_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, ctx->stream>>>(nullptr, d_stage, reinterpret_cast<const uint32_t *>(d_stage + nr), nr);
+            ctx->launches++;
+            LDX_CUDA(cudaGetLastError());
+            LDX_CUDA(cudaStreamSynchronize(ctx->stream));                 // `stage` is a local
+        }
+        ldx_hit *d_sorted = nullptr;
+        LDX_TRY(sort_hits_on_device(ctx, d_hits, n, s->n_variants, nq, &d_sorted));
+        LDX_CUDA(cudaMemcpyAsync(hits, d_sorted, sizeof(ldx_hit) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        LDX_CUDA(cudaStreamSynchronize(ctx->stream));
+    } else {
+        for (const FixupRec &r : recs) {
+            const uint32_t w = settle_word(r, s->fc.n_hap, measure, 1, thres_e4);
+            hits[r.out_index & FIX_INDEX_MASK].packed = w;      // LDX_BELOW_THRES marks hits the exact rounding rejects
+        }
     }
     int64_t kept = n;
-    if (!recs.empty()) {
+    if (!recs.empty()) {                                        // (a stable compaction: the order survives)
         kept = 0;
         for (int64_t k = 0; k < n; ++k)
             if (!(hits[k].packed & LDX_BELOW_THRES)) hits[kept++] = hits[k];
     }
-    // the reference emits rows in VCF order per query (ld_area.py:215): sort by (query, row)
-    std::sort(hits, hits + kept, [](const ldx_hit &a, const ldx_hit &b) {
-        return a.query != b.query ? a.query < b.query : a.row < b.row;
-    });
+    if (!device_sort)
+        std::sort(hits, hits + kept, [](const ldx_hit &a, const ldx_hit &b) {
+            return a.query != b.query ? a.query < b.query : a.row < b.row;
+        });
     *n_hits = kept;
     return LDX_OK;
 }

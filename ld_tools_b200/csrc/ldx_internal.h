@@ -62,6 +62,9 @@ struct ldx_ctx {
     void *h_stage = nullptr;              // pinned bounce buffer of the store files (allocated on first use)
     uint8_t *h_lists = nullptr;           // pinned staging of ldx_calc_ld_lists: both genotype lists in, the result out
     size_t h_lists_bytes = 0;
+    uint8_t *h_win = nullptr;             // pinned staging of a multi-query window scan's work lists (one copy per call)
+    size_t h_win_bytes = 0;
+    cudaEvent_t win_staged = nullptr;     // recorded behind the copy out of h_win
     int window_mq = 1;                    // LDX_TUNE_WINDOW_MQ: 0 = ld_area scans always use the one-query-per-pass kernel
     int defer_cap = 0;                    // LDX_TUNE_DEFER_CAP: capacity of the deferred-pair lists (0 = sized from the pair count)
     int mma_min_v = 256;                  // ENGINE_AUTO uses the tcgen05 engine from this many variants
@@ -195,11 +198,12 @@ int read_whole_file(const char *path, std::vector<uint8_t> &in);
 constexpr int WINDOW_CHUNK = 256;   // rows per work item of the window kernel
 constexpr int WINDOW_MQ = 4;        // queries per work item of the multi-query window kernel (ldx_window.cu: MQ)
 struct WindowMqBlock { int64_t base, first_item; int32_t a, b; };   // = ldx::MqBlock (ldx_window.cu)
-struct WindowMqQuery { int64_t q, qrow, lo, hi; };                  // = ldx::MqQuery
+// One record per query in sorted order (= ldx::MqQueryX): the host fills q .. we, a small kernel adds the query row's idnum, n1
+// and its half of the r2 screen; the scan kernels read nothing else about a query.
+struct WindowMqQueryX { int64_t idnum; int32_t q, qrow, lo, hi, ws, we, n1, pad[3]; };
 bool window_mq_supported(const ldx_store *s);
-int launch_window_mq(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, const int64_t *d_hi, const int32_t *d_ws, const int32_t *d_we,
-                     int64_t nq, const void *d_blocks, int64_t n_blocks, const void *d_sorted, int64_t n_sorted, void *d_ext, unsigned int *d_next,
+int launch_window_mq(ldx_store *s, int64_t nq, const void *d_blocks, int64_t n_blocks, void *d_ext, int64_t n_sorted, unsigned int *d_next,
                      int measure, int thres_e4, ldx_hit *d_hits, int64_t cap, unsigned long long *d_counters);
-constexpr size_t WINDOW_MQ_EXT_BYTES = 48;   // per sorted query: scratch for the row-per-thread kernel's records (ldx_window.cu: MqQueryX)
+constexpr size_t WINDOW_MQ_EXT_BYTES = 48;
 
 }  // namespace ldx

@@ -236,15 +236,14 @@ struct MqQuery { int64_t q, qrow, lo, hi; };               // query index of the
 struct MqQueryX { int64_t idnum; int32_t q, qrow, lo, hi, ws, we, n1, pad[3]; };
 static_assert(sizeof(MqQueryX) == WINDOW_MQ_EXT_BYTES, "three 16-byte loads");
 
-__global__ void mq_extend_kernel(const WindowArgs A, const MqQuery *__restrict__ sorted, int64_t n, MqQueryX *__restrict__ out) {
+// The host has filled q, qrow, lo, hi, ws, we; what lives on the device is added here.
+__global__ void mq_extend_kernel(const WindowArgs A, int64_t n, MqQueryX *__restrict__ recs) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const MqQuery m = sorted[i];
-    MqQueryX x;
-    x.idnum = A.idnum[m.qrow]; x.q = (int32_t)m.q; x.qrow = (int32_t)m.qrow; x.lo = (int32_t)m.lo; x.hi = (int32_t)m.hi;
-    x.ws = A.win_start[m.q]; x.we = A.win_end[m.q]; x.n1 = A.freq[m.qrow].n1; x.pad[1] = x.pad[2] = 0;
-    x.pad[0] = __float_as_int(half_denominator_rcp(x.n1, A.n_sel, 1.0e4f));      // the query's half of the r2 screen (screen_below_r2_pre)
-    out[i] = x;
+    const int32_t qrow = recs[i].qrow, n1 = A.freq[qrow].n1;
+    recs[i].idnum = A.idnum[qrow];
+    recs[i].n1 = n1;
+    recs[i].pad[0] = __float_as_int(half_denominator_rcp(n1, A.n_sel, 1.0e4f));      // the query's half of the r2 screen (screen_below_r2_pre)
 }
 
 template <int NG, bool L1ROWS>
@@ -596,24 +595,23 @@ static void fill_window_args(ldx_store *s, WindowArgs &A, const int64_t *d_qrow,
 
 bool window_mq_supported(const ldx_store *s) { const int ng = s->stride_words / 16; return ng >= 1 && ng <= 5; }
 
-// d_blocks: MqBlock records, d_sorted: MqQuery records in sorted order (WindowMqBlock / WindowMqQuery on the host side);
-// d_next: one word of device scratch for the dynamic block counter
-int launch_window_mq(ldx_store *s, const int64_t *d_qrow, const int64_t *d_lo, const int64_t *d_hi, const int32_t *d_ws, const int32_t *d_we,
-                     int64_t nq, const void *d_blocks, int64_t n_blocks, const void *d_sorted, int64_t n_sorted, void *d_ext, unsigned int *d_next,
+// d_blocks: MqBlock records; d_ext: one MqQueryX record per query in sorted order, host part filled (WindowMqBlock / WindowMqQueryX
+// on the host side); d_next: one word of device scratch for the dynamic block counter
+int launch_window_mq(ldx_store *s, int64_t nq, const void *d_blocks, int64_t n_blocks, void *d_ext, int64_t n_sorted, unsigned int *d_next,
                      int measure, int thres_e4, ldx_hit *d_hits, int64_t cap, unsigned long long *d_counters) {
     if (n_blocks <= 0) return LDX_OK;
-    static_assert(sizeof(MqBlock) == sizeof(WindowMqBlock) && sizeof(MqQuery) == sizeof(WindowMqQuery), "host and device work-list records");
+    static_assert(sizeof(MqBlock) == sizeof(WindowMqBlock) && sizeof(MqQueryX) == sizeof(WindowMqQueryX) && offsetof(MqQueryX, ws) == offsetof(WindowMqQueryX, ws),
+                  "host and device work-list records");
     WindowArgs A;
-    fill_window_args(s, A, d_qrow, d_lo, d_hi, d_ws, d_we, nq, measure, thres_e4, d_hits, cap, d_counters);
+    fill_window_args(s, A, nullptr, nullptr, nullptr, nullptr, nullptr, nq, measure, thres_e4, d_hits, cap, d_counters);   // the kernels read the records only
     const MqBlock *blocks = reinterpret_cast<const MqBlock *>(d_blocks);
-    const MqQuery *sorted = reinterpret_cast<const MqQuery *>(d_sorted);
     static const bool rows1_off = getenv("LDX_WINDOW_ROWS1") && atoi(getenv("LDX_WINDOW_ROWS1")) == 0;
     if (!d_ext || n_sorted <= 0 || s->n_variants >= (1ll << 31)) return set_error(LDX_ERR_STATE, "multi-query window kernel: no record scratch");
     ldx_ctx *ctx = s->ctx;
     MqQueryX *ext = reinterpret_cast<MqQueryX *>(d_ext);
     LDX_CUDA(cudaMemsetAsync(d_next, 0, sizeof(unsigned int), ctx->stream));
     timing_begin(ctx);                      // one pair around the record kernel and the scan kernel
-    mq_extend_kernel<<<(unsigned)((n_sorted + 255) / 256), 256, 0, ctx->stream>>>(A, sorted, n_sorted, ext);
+    mq_extend_kernel<<<(unsigned)((n_sorted + 255) / 256), 256, 0, ctx->stream>>>(A, n_sorted, ext);
     ctx->launches++;
     LDX_LAUNCHED(ctx, "mq_extend_kernel");
     if ((A.stride_u4 == 8 || A.stride_u4 == 16) && !rows1_off) {     // 128- and 256-byte rows: a thread per row

@@ -829,3 +829,29 @@ def test_async_upload_and_no_wait_mask_give_the_same_results(ctx):
         n1, _, n_sel = st.counts()
         assert n_sel == len(sel) and (n1 == ld_oracle.variant_counts(planes, mask, n_hap)).all()
     st.close()
+
+
+def test_window_large_hit_lists_come_back_sorted(ctx):
+    """With threshold 0 every scanned pair is kept (half a million here): the list is sorted by (query, row) on the device
+    before it crosses PCIe -- strictly increasing keys, as many hits as pairs scanned, every query's rows exactly its candidates
+    that pass the filters, words equal to the oracle's for sampled hits."""
+    n_var, n_hap = 4000, 400
+    st, planes, mask, pos0, end0, idnum, elig = annotated_store(ctx, n_var, n_hap, seed=91)
+    rng = np.random.default_rng(4)
+    q_rows = np.sort(rng.choice(n_var, 150, replace=False)).astype(np.int64)
+    lo = np.zeros(len(q_rows), dtype=np.int64)
+    hi = np.full(len(q_rows), n_var, dtype=np.int64)
+    ws = np.zeros(len(q_rows), dtype=np.int32)
+    we = np.full(len(q_rows), 2**31 - 1, dtype=np.int32)
+    hits, scanned = st.window(q_rows, lo, hi, ws, we, "r_square", 0)
+    assert len(hits) == scanned > 400_000
+    key = hits["query"].astype(np.int64) * n_var + hits["row"]
+    assert (np.diff(key) > 0).all()
+    for k in (0, 77, 149):
+        q = int(q_rows[k])
+        want_rows = [r for r in range(n_var) if elig[r] and idnum[r] != idnum[q]]
+        assert hits["row"][hits["query"] == k].tolist() == want_rows
+    pick = rng.choice(len(hits), 300, replace=False)
+    ref = ld_oracle.pairs(planes, mask, n_hap, q_rows[hits["query"][pick]], hits["row"][pick].astype(np.int64))
+    assert (hits["packed"][pick] == ld_oracle.packed_of(ref)).all() and (hits["n11"][pick] == ref["n_11"]).all()
+    st.close()

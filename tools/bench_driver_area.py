@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--queries", type=int, default=1000)
     ap.add_argument("--samples", type=int, default=2504)
     ap.add_argument("--flank", type=int, default=500000)
+    ap.add_argument("--thres", type=float, default=0.8, help="-z of the job; 0.0 keeps every record in the windows (the writers at scale)")
     args = ap.parse_args()
     from ld_tools_b200 import Context, drivers
     from ld_tools_b200.synth import conversion_rows, make_panel, make_records, synth_haplotypes, write_intgen_dir
@@ -65,7 +66,7 @@ def main():
             trg = os.path.join(root, f"out{k}")
             t0 = time.perf_counter()
             drivers.ld_area(src, intgen, trg, pop_names="eur", flank_size=args.flank, ld_thres_measure="r_square",
-                            ld_low_thres=0.8, trg_file_type="tsv", ctx=ctx)
+                            ld_low_thres=args.thres, trg_file_type="tsv", ctx=ctx)
             runs.append(time.perf_counter() - t0)
         ctx.close()
         out["driver_s"] = {"first_run_inflate_ingest_cache": runs[0], "later_runs_from_store_cache": runs[1:]}
@@ -103,7 +104,7 @@ def main():
                 if recs[j]["id"] == qid:                                                                  # :222
                     continue
                 r2, dp, p_a, p_b, _ = calc_ld_port.finalise_counts(n_hap, c11, int(n1[q]), n_hap - int(n1[q]), int(n1[j]), n_hap - int(n1[j]))
-                if r2 < 0.8:                                                                              # :248
+                if r2 < args.thres:                                                                       # :248
                     continue
                 want.append("\t".join(map(str, [recs[j]["pos"], recs[j]["id"], recs[j]["ref"], recs[j]["alt"], recs[j]["vt"],
                                                  p_b, r2, dp, recs[j]["pos"] - recs[q]["pos"]])))

@@ -1000,6 +1000,43 @@ extern "C" int32_t ldx_pairs(ldx_store *s, const int64_t *ia, const int64_t *ib,
     ldx_ctx *ctx = s->ctx;
     LDX_CUDA(cudaSetDevice(ctx->device));
     LDX_TRY(settle_before_host_call(ctx));
+    if (n <= 16384) {
+        // A short list (ld_lite asks for ONE pair): indices in and every output out through the context's pinned staging -- two copies
+        // and one wait instead of up to seven pageable copies, each staged by the runtime.
+        const size_t nn = (size_t)n, in_bytes = 16 * nn;
+        const size_t o_n11 = in_bytes, o_d = o_n11 + ((4 * nn + 7) & ~(size_t)7), o_dp = o_d + 8 * nn, o_r2 = o_dp + 8 * nn, o_pk = o_r2 + 8 * nn, total = o_pk + 4 * nn;
+        if (ctx->h_lists_bytes < total) {
+            if (ctx->h_lists) cudaFreeHost(ctx->h_lists);
+            ctx->h_lists = nullptr; ctx->h_lists_bytes = 0;
+            const size_t cap = std::max<size_t>(total * 2, (size_t)1 << 16);
+            LDX_CUDA(cudaMallocHost((void **)&ctx->h_lists, cap));
+            ctx->h_lists_bytes = cap;
+        }
+        uint8_t *d_blk, *h = ctx->h_lists;
+        LDX_TRY(arena_get(ctx, S_TEXT, total + 64, (void **)&d_blk));
+        std::memcpy(h, ia, 8 * nn);
+        std::memcpy(h + 8 * nn, ib, 8 * nn);
+        LDX_CUDA(cudaMemcpyAsync(d_blk, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        LDX_TRY(launch_pairs(s, reinterpret_cast<int64_t *>(d_blk), reinterpret_cast<int64_t *>(d_blk + 8 * nn), n,
+                             n11 ? reinterpret_cast<int32_t *>(d_blk + o_n11) : nullptr, d ? reinterpret_cast<double *>(d_blk + o_d) : nullptr,
+                             dprime ? reinterpret_cast<double *>(d_blk + o_dp) : nullptr, r2 ? reinterpret_cast<double *>(d_blk + o_r2) : nullptr,
+                             packed ? reinterpret_cast<uint32_t *>(d_blk + o_pk) : nullptr));
+        LDX_CUDA(cudaMemcpyAsync(h + in_bytes, d_blk + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        std::vector<FixupRec> recs;
+        LDX_TRY(collect_fixups(ctx, recs));   // synchronises
+        if (n11) std::memcpy(n11, h + o_n11, 4 * nn);
+        if (d) std::memcpy(d, h + o_d, 8 * nn);
+        if (dprime) std::memcpy(dprime, h + o_dp, 8 * nn);
+        if (r2) std::memcpy(r2, h + o_r2, 8 * nn);
+        if (packed) std::memcpy(packed, h + o_pk, 4 * nn);
+        for (const FixupRec &r : recs) {
+            double r2_exact;
+            const uint32_t w = host_finalise_rec(r, s->fc.n_hap, &r2_exact);
+            if (packed) packed[r.out_index] = w;
+            if (r2) r2[r.out_index] = r2_exact;
+        }
+        return LDX_OK;
+    }
     int64_t *d_ia, *d_ib; int32_t *d_n11 = nullptr; double *d_d = nullptr, *d_dp = nullptr, *d_r2 = nullptr; uint32_t *d_pk = nullptr;
     LDX_TRY(arena_get(ctx, S_IA, sizeof(int64_t) * (size_t)n, (void **)&d_ia));
     LDX_TRY(arena_get(ctx, S_IB, sizeof(int64_t) * (size_t)n, (void **)&d_ib));
